@@ -1,0 +1,779 @@
+// capi.cu -- the C ABI of libbandup_gpu.so (include/bandup_gpu.h): contexts,
+// the double-buffered upload pipeline and the per-k-point kernel sequence.
+//
+// There is deliberately NO CPU fallback anywhere in this file: without a usable
+// sm_100 device bandup_gpu_init fails with BANDUP_GPU_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace bandup {
+namespace {
+
+constexpr int kDepth = 2;          // k-points in flight (double buffering)
+constexpr int kMaxHandles = 64;
+constexpr double kEpsDp = 2.220446049250313e-16;  // epsilon(1.0_dp)
+constexpr double kMaxTolVecEq = 1e-3;             // max_tol_for_vec_equality
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    // grow geometrically so k-points of slightly different n_pw do not realloc
+    size_t want = bytes + bytes / 16 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 16 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Flight {  // one SC k-point in flight
+  bool busy = false;
+  int ikpt = -1;
+  int n_spinor = 0, n_pw = 0, n_bands = 0, n_fold = 0, n_unique = 0;
+  int unique_of[kMaxFolds];
+  DevBuf coeffs, gfrac, energies, weights, dN, nsel, norms, slot, selected, workspace;
+  PinBuf h_weights, h_dN, h_nsel, h_norms;
+  cudaEvent_t uploaded = nullptr, done = nullptr;
+};
+
+struct Ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t copy = nullptr, compute = nullptr;
+  bool cells_set = false, grid_set = false;
+  double B_sc[9] = {0}, B_inv[9] = {0};  // row-major, row = vector
+  int32_t M[9] = {0};                    // row-major int_M
+  CosetParams coset{};
+  std::vector<double> grid;
+  DevBuf d_grid;
+  int nener = 0;
+  double sigma = kEpsDp;
+  Flight flights[kDepth];
+  int next_flight = 0;
+  int chunk_vecs = 0, ctas_per_sm = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> event_pool;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[BANDUP_GPU_K_COUNT];
+  double total_ms[BANDUP_GPU_K_COUNT] = {0};
+  int64_t count[BANDUP_GPU_K_COUNT] = {0};
+  int64_t launches = 0;
+  std::string err = "";
+};
+
+std::mutex g_mutex;
+Ctx* g_ctx[kMaxHandles] = {nullptr};
+std::string g_global_err = "";
+
+Ctx* get(int h) {
+  if (h < 0 || h >= kMaxHandles) return nullptr;
+  return g_ctx[h];
+}
+
+int fail(Ctx* c, int code, const std::string& msg) {
+  if (c)
+    c->err = msg;
+  else
+    g_global_err = msg;
+  return code;
+}
+
+int cuda_fail(Ctx* c, cudaError_t e, const char* where) {
+  return fail(c, BANDUP_GPU_ERR_CUDA,
+              std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return cuda_fail(c, e_, #call); \
+  } while (0)
+
+// ---- small host-side linear algebra (row-major, row = vector) -------------
+
+bool inv3(const double* m, double* inv) {
+  double c0 = m[4] * m[8] - m[5] * m[7];
+  double c1 = -(m[3] * m[8] - m[5] * m[6]);
+  double c2 = m[3] * m[7] - m[4] * m[6];
+  double det = m[0] * c0 + m[1] * c1 + m[2] * c2;
+  if (std::fabs(det) <= 1e-10) return false;
+  inv[0] = c0 / det;
+  inv[3] = c1 / det;
+  inv[6] = c2 / det;
+  inv[1] = -(m[1] * m[8] - m[2] * m[7]) / det;
+  inv[4] = (m[0] * m[8] - m[2] * m[6]) / det;
+  inv[7] = -(m[0] * m[7] - m[1] * m[6]) / det;
+  inv[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+  inv[5] = -(m[0] * m[5] - m[2] * m[3]) / det;
+  inv[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+  return true;
+}
+
+void from_fortran(const double* f, double* r) {  // column-major -> row-major
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r[3 * i + j] = f[3 * j + i];
+}
+
+// adjugate of transpose(M) and |det M| in 64-bit integers
+void coset_setup(const int32_t* M, long long* adjT, long long* D) {
+  long long T[9], cf[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) T[3 * i + j] = M[3 * j + i];
+  cf[0] = T[4] * T[8] - T[5] * T[7];
+  cf[1] = -(T[3] * T[8] - T[5] * T[6]);
+  cf[2] = T[3] * T[7] - T[4] * T[6];
+  cf[3] = -(T[1] * T[8] - T[2] * T[7]);
+  cf[4] = T[0] * T[8] - T[2] * T[6];
+  cf[5] = -(T[0] * T[7] - T[1] * T[6]);
+  cf[6] = T[1] * T[5] - T[2] * T[4];
+  cf[7] = -(T[0] * T[5] - T[2] * T[3]);
+  cf[8] = T[0] * T[4] - T[1] * T[3];
+  long long det = T[0] * cf[0] + T[1] * cf[1] + T[2] * cf[2];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) adjT[3 * i + j] = cf[3 * j + i];
+  *D = det < 0 ? -det : det;
+}
+
+void coset_key(const int32_t* g, const long long* adjT, long long D, int* key) {
+  for (int j = 0; j < 3; ++j) {
+    long long v = (long long)g[0] * adjT[j] + (long long)g[1] * adjT[3 + j] +
+                  (long long)g[2] * adjT[6 + j];
+    v %= D;
+    if (v < 0) v += D;
+    key[j] = (int)v;
+  }
+}
+
+// ---- profiling helpers ------------------------------------------------------
+
+cudaEvent_t take_event(Ctx* c) {
+  if (!c->event_pool.empty()) {
+    cudaEvent_t e = c->event_pool.back();
+    c->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct KernelScope {  // brackets one launch with events when profiling is on
+  Ctx* c;
+  int which;
+  cudaStream_t s;
+  cudaEvent_t a = nullptr, b = nullptr;
+  KernelScope(Ctx* c_, int which_, cudaStream_t s_) : c(c_), which(which_), s(s_) {
+    c->launches++;
+    if (c->profiling) {
+      a = take_event(c);
+      b = take_event(c);
+      cudaEventRecord(a, s);
+    }
+  }
+  ~KernelScope() {
+    if (a) {
+      cudaEventRecord(b, s);
+      c->pending[which].push_back({a, b});
+    }
+  }
+};
+
+void resolve_pending(Ctx* c) {
+  for (int k = 0; k < BANDUP_GPU_K_COUNT; ++k) {
+    for (auto& pr : c->pending[k]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+        c->total_ms[k] += ms;
+        c->count[k] += 1;
+      }
+      c->event_pool.push_back(pr.first);
+      c->event_pool.push_back(pr.second);
+    }
+    c->pending[k].clear();
+  }
+}
+
+// ---- the per-k-point kernel sequence ---------------------------------------
+
+struct FoldPlan {
+  int n_unique = 0;
+  int unique_of[kMaxFolds];  // user fold -> unique fold
+  int first_of[kMaxFolds];   // unique fold -> first user fold holding that coset
+  CosetParams cp;
+};
+
+int plan_folds(Ctx* c, int n_fold, const int32_t* g0, FoldPlan* plan) {
+  if (n_fold < 1 || n_fold > kMaxFolds)
+    return fail(c, BANDUP_GPU_ERR_TOO_MANY_FOLDS,
+                "n_fold must be in 1.." + std::to_string(kMaxFolds) + ", got " + std::to_string(n_fold));
+  plan->cp = c->coset;
+  plan->n_unique = 0;
+  for (int f = 0; f < n_fold; ++f) {
+    int key[3];
+    coset_key(g0 + 3 * f, c->coset.adjT, c->coset.D, key);
+    int u = -1;
+    for (int q = 0; q < plan->n_unique; ++q)
+      if (plan->cp.fold_key[q][0] == key[0] && plan->cp.fold_key[q][1] == key[1] &&
+          plan->cp.fold_key[q][2] == key[2])
+        u = q;
+    if (u < 0) {
+      u = plan->n_unique++;
+      plan->cp.fold_key[u][0] = key[0];
+      plan->cp.fold_key[u][1] = key[1];
+      plan->cp.fold_key[u][2] = key[2];
+      plan->first_of[u] = f;
+    }
+    plan->unique_of[f] = u;
+  }
+  plan->cp.n_fold = plan->n_unique;
+  return BANDUP_GPU_OK;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct WorkspaceLayout {
+  size_t slot_off, partials_off, tmp_w_off, tmp_dn_off, tmp_ns_off, total;
+};
+
+WorkspaceLayout workspace_layout(const Ctx* c, int n_spinor, int n_pw, int n_bands, int n_fold) {
+  WorkspaceLayout w;
+  const int cv = c->chunk_vecs > 0 ? c->chunk_vecs : weights_default_chunk_vecs();
+  const int n_chunks = weights_num_chunks((long long)n_pw * n_spinor, cv);
+  size_t off = 0;
+  w.slot_off = off;
+  off += align256((size_t)(n_pw > 0 ? n_pw : 1));
+  w.partials_off = off;
+  off += align256(weights_partials_bytes(n_bands, n_chunks, n_fold));
+  // scratch rows used only when two requested pc-kpts share a coset
+  w.tmp_w_off = off;
+  off += align256(sizeof(double) * (size_t)n_fold * (size_t)(n_bands > 0 ? n_bands : 1));
+  w.tmp_dn_off = off;
+  off += align256(sizeof(double) * (size_t)n_fold * (size_t)(c->nener > 0 ? c->nener : 1));
+  w.tmp_ns_off = off;
+  off += align256(sizeof(int32_t) * (size_t)n_fold);
+  w.total = off;
+  return w;
+}
+
+int run_kpt(Ctx* c, cudaStream_t s, int n_spinor, int n_pw, int n_bands, int layout,
+            long long stride_bytes, const void* d_coeffs, const int32_t* d_gfrac,
+            const double* d_energies, int n_fold, const FoldPlan& plan, double* d_weights,
+            double* d_dN, int32_t* d_nsel, double* d_norms, uint8_t* d_slot_out, void* d_ws,
+            size_t ws_bytes) {
+  const WorkspaceLayout wl = workspace_layout(c, n_spinor, n_pw, n_bands, n_fold);
+  if (ws_bytes < wl.total)
+    return fail(c, BANDUP_GPU_ERR_CAPACITY,
+                "workspace too small: need " + std::to_string(wl.total) + " bytes");
+  char* ws = static_cast<char*>(d_ws);
+  uint8_t* d_slot = d_slot_out ? d_slot_out : reinterpret_cast<uint8_t*>(ws + wl.slot_off);
+  double* d_partials = reinterpret_cast<double*>(ws + wl.partials_off);
+  const bool dup = plan.n_unique != n_fold;
+  double* w_out = dup ? reinterpret_cast<double*>(ws + wl.tmp_w_off) : d_weights;
+  double* dn_out = dup ? reinterpret_cast<double*>(ws + wl.tmp_dn_off) : d_dN;
+  int32_t* ns_out = dup ? reinterpret_cast<int32_t*>(ws + wl.tmp_ns_off) : d_nsel;
+  const int nu = plan.n_unique;
+
+  {
+    KernelScope k(c, BANDUP_GPU_K_COSET, s);
+    launch_coset_classify(d_gfrac, n_pw, plan.cp, d_slot, ns_out, s);
+  }
+  WeightsGeom g;
+  g.coeffs = static_cast<const char*>(d_coeffs);
+  g.stride_bytes = stride_bytes;
+  g.row_elems = (long long)n_pw * n_spinor;
+  g.n_bands = n_bands;
+  g.n_pw = n_pw;
+  g.n_spinor = n_spinor;
+  g.layout = layout;
+  g.slot = d_slot;
+  g.n_fold = nu;
+  g.chunk_vecs = c->chunk_vecs > 0 ? c->chunk_vecs : weights_default_chunk_vecs();
+  g.n_chunks = weights_num_chunks(g.row_elems, g.chunk_vecs);
+  g.partials = d_partials;
+  {
+    KernelScope k(c, BANDUP_GPU_K_WEIGHTS, s);
+    launch_weights_reduce(g, c->ctas_per_sm, c->sm_count, s);
+  }
+  {
+    KernelScope k(c, BANDUP_GPU_K_FINALIZE, s);
+    launch_weights_finalize(d_partials, n_bands, g.n_chunks, nu, w_out, d_norms, s);
+  }
+  {
+    KernelScope k(c, BANDUP_GPU_K_DELTA_N, s);
+    launch_delta_n(static_cast<const double*>(c->d_grid.p), c->nener, c->sigma, d_energies,
+                   w_out, n_bands, nu, dn_out, s);
+  }
+  CU(cudaGetLastError());
+  if (dup) {  // replicate rows of pc-kpts that share a coset
+    for (int f = 0; f < n_fold; ++f) {
+      const int u = plan.unique_of[f];
+      CU(cudaMemcpyAsync(d_weights + (size_t)f * n_bands, w_out + (size_t)u * n_bands,
+                         sizeof(double) * n_bands, cudaMemcpyDeviceToDevice, s));
+      CU(cudaMemcpyAsync(d_dN + (size_t)f * c->nener, dn_out + (size_t)u * c->nener,
+                         sizeof(double) * c->nener, cudaMemcpyDeviceToDevice, s));
+      CU(cudaMemcpyAsync(d_nsel + f, ns_out + u, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  return BANDUP_GPU_OK;
+}
+
+int check_shape(Ctx* c, int n_spinor, int n_pw, int n_bands, int layout, long long stride) {
+  if (!c->cells_set || !c->grid_set)
+    return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_set_cells and bandup_gpu_set_grid first");
+  if (n_spinor != 1 && n_spinor != 2)
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "n_spinor must be 1 or 2");
+  if (n_pw < 1 || n_bands < 1) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "n_pw and n_bands must be >= 1");
+  if (layout != BANDUP_GPU_LAYOUT_FORTRAN_INMEM && layout != BANDUP_GPU_LAYOUT_VASP_RECORD)
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "unknown coefficient layout");
+  if (stride < (long long)n_pw * n_spinor * 8 || (stride & 7))
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG,
+                "band_stride_bytes must be a multiple of 8 and >= n_pw*n_spinor*8");
+  return BANDUP_GPU_OK;
+}
+
+}  // namespace
+}  // namespace bandup
+
+using namespace bandup;
+
+extern "C" {
+
+int bandup_gpu_abi_version(void) { return BANDUP_GPU_ABI_VERSION; }
+
+int bandup_gpu_init(int device, int* handle) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  Ctx* c = nullptr;
+  if (!handle) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "handle is NULL");
+  *handle = -1;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev)
+    return fail(c, BANDUP_GPU_ERR_NO_DEVICE,
+                std::string("no usable CUDA device ") + std::to_string(device) + " (" +
+                    (e == cudaSuccess ? "device count " + std::to_string(n_dev) : cudaGetErrorString(e)) +
+                    "); libbandup_gpu has no CPU fallback");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+    return fail(c, BANDUP_GPU_ERR_NO_DEVICE,
+                "device is not compute capability 10.x; this library carries sm_100a code only");
+  int slot = -1;
+  for (int i = 0; i < kMaxHandles; ++i)
+    if (!g_ctx[i]) {
+      slot = i;
+      break;
+    }
+  if (slot < 0) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "too many open handles");
+  c = new Ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return fail(nullptr, BANDUP_GPU_ERR_CUDA, "stream creation failed");
+  }
+  for (auto& f : c->flights) {
+    cudaEventCreateWithFlags(&f.uploaded, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming);
+  }
+  g_ctx[slot] = c;
+  *handle = slot;
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_finalize(int handle) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  resolve_pending(c);
+  for (auto ev : c->event_pool) cudaEventDestroy(ev);
+  for (auto& f : c->flights) {
+    f.coeffs.release(); f.gfrac.release(); f.energies.release(); f.weights.release();
+    f.dN.release(); f.nsel.release(); f.norms.release(); f.slot.release();
+    f.selected.release(); f.workspace.release();
+    f.h_weights.release(); f.h_dN.release(); f.h_nsel.release(); f.h_norms.release();
+    if (f.uploaded) cudaEventDestroy(f.uploaded);
+    if (f.done) cudaEventDestroy(f.done);
+  }
+  c->d_grid.release();
+  if (c->copy) cudaStreamDestroy(c->copy);
+  if (c->compute) cudaStreamDestroy(c->compute);
+  delete c;
+  g_ctx[handle] = nullptr;
+  return BANDUP_GPU_OK;
+}
+
+const char* bandup_gpu_last_error(int handle) {
+  Ctx* c = get(handle);
+  return c ? c->err.c_str() : g_global_err.c_str();
+}
+
+int bandup_gpu_pinned_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return BANDUP_GPU_ERR_INVALID_ARG;
+  cudaError_t e = cudaMallocHost(ptr, bytes);
+  return e == cudaSuccess ? BANDUP_GPU_OK : cuda_fail(nullptr, e, "cudaMallocHost");
+}
+
+int bandup_gpu_pinned_free(void* ptr) {
+  cudaError_t e = cudaFreeHost(ptr);
+  return e == cudaSuccess ? BANDUP_GPU_OK : cuda_fail(nullptr, e, "cudaFreeHost");
+}
+
+int bandup_gpu_set_cells(int handle, const double* B_sc_f, const double* b_pc_f, double tol,
+                         int32_t* M_out) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (!B_sc_f || !b_pc_f) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "NULL lattice");
+  if (tol <= 0.0) tol = 1e-5;  // default_tol_for_int_commens_test
+  double b_pc[9];
+  from_fortran(B_sc_f, c->B_sc);
+  from_fortran(b_pc_f, b_pc);
+  if (!inv3(c->B_sc, c->B_inv)) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "singular SC reciprocal lattice");
+  // M = transpose(matmul(b_pc, inverse(B_sc)))   (crystals_mod.f90:66)
+  bool commensurate = true;
+  double worst = 0.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double p = 0.0;  // (b_pc . B_inv)(j, i)
+      for (int k = 0; k < 3; ++k) p += b_pc[3 * j + k] * c->B_inv[3 * k + i];
+      const long r = std::lround(p);
+      c->M[3 * i + j] = (int32_t)r;
+      const double res = std::fabs(p - (double)r);
+      if (res > worst) worst = res;
+      if (res > tol) commensurate = false;
+    }
+  if (M_out)
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) M_out[3 * j + i] = c->M[3 * i + j];
+  if (!commensurate) {
+    c->cells_set = false;
+    return fail(c, BANDUP_GPU_ERR_NOT_COMMENSURATE,
+                "pc and SC are not commensurate: max |M - nint(M)| = " + std::to_string(worst));
+  }
+  coset_setup(c->M, c->coset.adjT, &c->coset.D);
+  if (c->coset.D == 0) return fail(c, BANDUP_GPU_ERR_NOT_COMMENSURATE, "det M = 0");
+  if (c->coset.D > 2000000000LL) return fail(c, BANDUP_GPU_ERR_INT_OVERFLOW, "|det M| too large");
+  c->cells_set = true;
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_set_grid(int handle, double E_start, double E_end, double delta_e, double smearing,
+                        int32_t* nener_out) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (!(delta_e > 0.0) || !(E_end > E_start))
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "need delta_e > 0 and E_end > E_start");
+  // real_seq (lists_and_seqs_mod.f90:194-198)
+  const long long n = std::llround((E_end - E_start) / delta_e + 1.0);
+  if (n < 2 || n > 100000000LL) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "energy grid needs 2..1e8 points");
+  c->grid.resize((size_t)n);
+  for (long long i = 1; i <= n; ++i) {
+    volatile double step = (double)(i - 1) * delta_e;  // product rounded before the add (no FMA)
+    c->grid[(size_t)(i - 1)] = E_start + step;
+  }
+  c->nener = (int)n;
+  // get_delta_Ns_for_EBS (band_unfolding_routines_mod.f90:774-777)
+  c->sigma = kEpsDp;
+  if (smearing > 0.0) c->sigma = std::fmax(kEpsDp, std::fabs(smearing));
+  cudaSetDevice(c->device);
+  CU(cudaStreamSynchronize(c->compute));
+  CU(c->d_grid.reserve(sizeof(double) * (size_t)n));
+  CU(cudaMemcpy(c->d_grid.p, c->grid.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  c->grid_set = true;
+  if (nener_out) *nener_out = c->nener;
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_get_grid(int handle, double* energies) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (!c->grid_set || !energies) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "grid not set");
+  std::memcpy(energies, c->grid.data(), sizeof(double) * c->grid.size());
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_folding_g0(int handle, const double* folding_G, int n_fold, int32_t* g0,
+                          double* max_residual) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (!c->cells_set) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_set_cells first");
+  if (!folding_G || !g0 || n_fold < 0) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad arguments");
+  double worst = 0.0;
+  for (int f = 0; f < n_fold; ++f) {
+    const double* v = folding_G + 3 * f;
+    double back[3] = {0, 0, 0};
+    for (int i = 0; i < 3; ++i) {
+      // fractional coordinate i of v in the SC reciprocal basis: (v . B_inv)_i
+      const double fi = v[0] * c->B_inv[i] + v[1] * c->B_inv[3 + i] + v[2] * c->B_inv[6 + i];
+      const long r = std::lround(fi);
+      g0[3 * f + i] = (int32_t)r;
+      for (int j = 0; j < 3; ++j) back[j] += (double)r * c->B_sc[3 * i + j];
+    }
+    const double dx = back[0] - v[0], dy = back[1] - v[1], dz = back[2] - v[2];
+    const double res = std::sqrt(dx * dx + dy * dy + dz * dz);
+    if (res > worst) worst = res;
+  }
+  if (max_residual) *max_residual = worst;
+  if (worst > kMaxTolVecEq)
+    return fail(c, BANDUP_GPU_ERR_FOLDING_VECTOR,
+                "folding vector is not an SC reciprocal-lattice vector (residual " +
+                    std::to_string(worst) + " > 1e-3)");
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_pipeline_depth(int handle) {
+  return get(handle) ? kDepth : 0;
+}
+
+size_t bandup_gpu_workspace_bytes(int handle, int n_spinor, int n_pw, int n_bands, int n_fold) {
+  Ctx* c = get(handle);
+  if (!c) return 0;
+  return workspace_layout(c, n_spinor, n_pw, n_bands, n_fold).total;
+}
+
+int bandup_gpu_unfold_device(int handle, void* stream, int n_spinor, int n_pw, int n_bands,
+                             int layout, int64_t band_stride_bytes, const void* d_coeffs,
+                             const int32_t* d_g_frac, const double* d_band_energies, int n_fold,
+                             const int32_t* g0, double* d_weights, double* d_dN,
+                             int32_t* d_n_selected, double* d_norms, uint8_t* d_slot_out,
+                             void* d_workspace, size_t workspace_bytes) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  int rc = check_shape(c, n_spinor, n_pw, n_bands, layout, band_stride_bytes);
+  if (rc) return rc;
+  if (!d_coeffs || !d_g_frac || !d_band_energies || !g0 || !d_weights || !d_dN || !d_n_selected ||
+      !d_workspace)
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "NULL device pointer");
+  FoldPlan plan;
+  rc = plan_folds(c, n_fold, g0, &plan);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  return run_kpt(c, static_cast<cudaStream_t>(stream), n_spinor, n_pw, n_bands, layout,
+                 band_stride_bytes, d_coeffs, d_g_frac, d_band_energies, n_fold, plan, d_weights,
+                 d_dN, d_n_selected, d_norms, d_slot_out, d_workspace, workspace_bytes);
+}
+
+int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_bands, int layout,
+                          int64_t band_stride_bytes, const void* coeffs, const int32_t* g_frac,
+                          const double* band_energies, int n_fold, const int32_t* g0) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  int rc = check_shape(c, n_spinor, n_pw, n_bands, layout, band_stride_bytes);
+  if (rc) return rc;
+  if (!coeffs || !g_frac || !band_energies || !g0)
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "NULL host pointer");
+  FoldPlan plan;
+  rc = plan_folds(c, n_fold, g0, &plan);
+  if (rc) return rc;
+  for (auto& f : c->flights)
+    if (f.busy && f.ikpt == ikpt)
+      return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "ikpt already in flight; fetch it first");
+  cudaSetDevice(c->device);
+  Flight& fl = c->flights[c->next_flight];
+  if (fl.busy)
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG,
+                "pipeline full: fetch k-point " + std::to_string(fl.ikpt) + " before submitting more");
+  // The buffers of this flight may still be read by its previous kernels only if
+  // the caller skipped fetch; fetch synchronises on `done`, so they are idle here.
+  const size_t coeff_bytes = (size_t)band_stride_bytes * (size_t)(n_bands - 1) +
+                             (size_t)n_pw * n_spinor * 8;
+  const WorkspaceLayout wl = workspace_layout(c, n_spinor, n_pw, n_bands, n_fold);
+  CU(fl.coeffs.reserve(coeff_bytes));
+  CU(fl.gfrac.reserve(sizeof(int32_t) * 3 * (size_t)n_pw));
+  CU(fl.energies.reserve(sizeof(double) * (size_t)n_bands));
+  CU(fl.weights.reserve(sizeof(double) * (size_t)n_fold * n_bands));
+  CU(fl.dN.reserve(sizeof(double) * (size_t)n_fold * c->nener));
+  CU(fl.nsel.reserve(sizeof(int32_t) * (size_t)n_fold));
+  CU(fl.norms.reserve(sizeof(double) * (size_t)n_bands));
+  CU(fl.slot.reserve((size_t)n_pw));
+  CU(fl.workspace.reserve(wl.total));
+  CU(fl.h_weights.reserve(sizeof(double) * (size_t)n_fold * n_bands));
+  CU(fl.h_dN.reserve(sizeof(double) * (size_t)n_fold * c->nener));
+  CU(fl.h_nsel.reserve(sizeof(int32_t) * (size_t)n_fold));
+  CU(fl.h_norms.reserve(sizeof(double) * (size_t)n_bands));
+
+  // upload on the copy stream so it overlaps the previous k-point's kernels
+  CU(cudaMemcpyAsync(fl.coeffs.p, coeffs, coeff_bytes, cudaMemcpyHostToDevice, c->copy));
+  CU(cudaMemcpyAsync(fl.gfrac.p, g_frac, sizeof(int32_t) * 3 * (size_t)n_pw, cudaMemcpyHostToDevice, c->copy));
+  CU(cudaMemcpyAsync(fl.energies.p, band_energies, sizeof(double) * (size_t)n_bands, cudaMemcpyHostToDevice, c->copy));
+  CU(cudaEventRecord(fl.uploaded, c->copy));
+  CU(cudaStreamWaitEvent(c->compute, fl.uploaded, 0));
+
+  rc = run_kpt(c, c->compute, n_spinor, n_pw, n_bands, layout, band_stride_bytes, fl.coeffs.p,
+               static_cast<const int32_t*>(fl.gfrac.p), static_cast<const double*>(fl.energies.p),
+               n_fold, plan, static_cast<double*>(fl.weights.p), static_cast<double*>(fl.dN.p),
+               static_cast<int32_t*>(fl.nsel.p), static_cast<double*>(fl.norms.p),
+               static_cast<uint8_t*>(fl.slot.p), fl.workspace.p, fl.workspace.cap);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(fl.h_weights.p, fl.weights.p, sizeof(double) * (size_t)n_fold * n_bands, cudaMemcpyDeviceToHost, c->compute));
+  CU(cudaMemcpyAsync(fl.h_dN.p, fl.dN.p, sizeof(double) * (size_t)n_fold * c->nener, cudaMemcpyDeviceToHost, c->compute));
+  CU(cudaMemcpyAsync(fl.h_nsel.p, fl.nsel.p, sizeof(int32_t) * (size_t)n_fold, cudaMemcpyDeviceToHost, c->compute));
+  CU(cudaMemcpyAsync(fl.h_norms.p, fl.norms.p, sizeof(double) * (size_t)n_bands, cudaMemcpyDeviceToHost, c->compute));
+  CU(cudaEventRecord(fl.done, c->compute));
+  fl.busy = true;
+  fl.ikpt = ikpt;
+  fl.n_spinor = n_spinor;
+  fl.n_pw = n_pw;
+  fl.n_bands = n_bands;
+  fl.n_fold = n_fold;
+  fl.n_unique = plan.n_unique;
+  std::memcpy(fl.unique_of, plan.unique_of, sizeof(int) * (size_t)n_fold);
+  c->next_flight = (c->next_flight + 1) % kDepth;
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_fetch_kpt(int handle, int ikpt, double* weights, double* dN, int32_t* n_selected,
+                         double* norms, int32_t* selected, int64_t selected_capacity) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  Flight* fl = nullptr;
+  for (auto& f : c->flights)
+    if (f.busy && f.ikpt == ikpt) fl = &f;
+  if (!fl) return fail(c, BANDUP_GPU_ERR_UNKNOWN_KPT, "k-point " + std::to_string(ikpt) + " is not in flight");
+  cudaSetDevice(c->device);
+  CU(cudaEventSynchronize(fl->done));
+  const int nf = fl->n_fold;
+  if (weights) std::memcpy(weights, fl->h_weights.p, sizeof(double) * (size_t)nf * fl->n_bands);
+  if (dN) std::memcpy(dN, fl->h_dN.p, sizeof(double) * (size_t)nf * c->nener);
+  if (n_selected) std::memcpy(n_selected, fl->h_nsel.p, sizeof(int32_t) * (size_t)nf);
+  if (norms) std::memcpy(norms, fl->h_norms.p, sizeof(double) * (size_t)fl->n_bands);
+  int rc = BANDUP_GPU_OK;
+  if (selected) {
+    // The slot table holds every distinct coset once (slot id = unique fold);
+    // pc-kpts that share a coset share a list.
+    const int32_t* ns = static_cast<const int32_t*>(fl->h_nsel.p);
+    int64_t total = 0;
+    for (int f = 0; f < nf; ++f) total += ns[f];
+    if (total > selected_capacity) {
+      rc = fail(c, BANDUP_GPU_ERR_CAPACITY, "selected_capacity too small: need " + std::to_string(total));
+    } else if (total > 0) {
+      const int nu = fl->n_unique;
+      std::vector<int32_t> id_count((size_t)nu, 0);
+      for (int f = 0; f < nf; ++f) id_count[fl->unique_of[f]] = ns[f];
+      std::vector<int64_t> id_off((size_t)nu + 1, 0);
+      for (int q = 0; q < nu; ++q) id_off[q + 1] = id_off[q] + id_count[q];
+      std::vector<int32_t> id_lists((size_t)id_off[nu]);
+      CU(fl->selected.reserve(sizeof(int32_t) * ((size_t)id_off[nu] + (size_t)nu)));
+      int32_t* d_lists = static_cast<int32_t*>(fl->selected.p);
+      int32_t* d_cnt = d_lists + id_off[nu];
+      CU(cudaMemcpyAsync(d_cnt, id_count.data(), sizeof(int32_t) * (size_t)nu, cudaMemcpyHostToDevice, c->compute));
+      {
+        KernelScope k(c, BANDUP_GPU_K_COSET, c->compute);
+        launch_selected_lists(static_cast<const uint8_t*>(fl->slot.p), fl->n_pw, nu, d_cnt, d_lists, c->compute);
+      }
+      CU(cudaMemcpyAsync(id_lists.data(), d_lists, sizeof(int32_t) * (size_t)id_off[nu], cudaMemcpyDeviceToHost, c->compute));
+      CU(cudaStreamSynchronize(c->compute));
+      int64_t w = 0;
+      for (int f = 0; f < nf; ++f) {
+        const int q = fl->unique_of[f];
+        std::memcpy(selected + w, id_lists.data() + id_off[q], sizeof(int32_t) * (size_t)id_count[q]);
+        w += id_count[q];
+      }
+    }
+  }
+  fl->busy = false;
+  fl->ikpt = -1;
+  return rc;
+}
+
+int bandup_gpu_set_profiling(int handle, int enabled) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  c->profiling = enabled != 0;
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_kernel_time(int handle, int which, double* total_ms, int64_t* launches) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (which < 0 || which >= BANDUP_GPU_K_COUNT) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad kernel id");
+  cudaSetDevice(c->device);
+  CU(cudaDeviceSynchronize());
+  resolve_pending(c);
+  if (total_ms) *total_ms = c->total_ms[which];
+  if (launches) *launches = c->count[which];
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_reset_kernel_times(int handle) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  cudaSetDevice(c->device);
+  CU(cudaDeviceSynchronize());
+  resolve_pending(c);
+  for (int k = 0; k < BANDUP_GPU_K_COUNT; ++k) {
+    c->total_ms[k] = 0.0;
+    c->count[k] = 0;
+  }
+  return BANDUP_GPU_OK;
+}
+
+int64_t bandup_gpu_launch_count(int handle) {
+  Ctx* c = get(handle);
+  return c ? c->launches : -1;
+}
+
+int bandup_gpu_set_tuning(int handle, int chunk_vecs, int ctas_per_sm) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (chunk_vecs < 0 || ctas_per_sm < 0) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "negative tuning value");
+  for (auto& f : c->flights)
+    if (f.busy) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "cannot retune with k-points in flight");
+  c->chunk_vecs = chunk_vecs;
+  c->ctas_per_sm = ctas_per_sm;
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_synth_fill_device(int handle, void* stream, void* d_coeffs, int64_t row_elems,
+                                 int n_bands, int64_t band_stride_bytes, uint64_t seed,
+                                 uint64_t ikpt) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (!d_coeffs || row_elems < 1 || n_bands < 1 || band_stride_bytes < row_elems * 8)
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad synth_fill arguments");
+  cudaSetDevice(c->device);
+  launch_synth_fill(d_coeffs, row_elems, n_bands, band_stride_bytes, seed, ikpt,
+                    static_cast<cudaStream_t>(stream));
+  c->launches++;
+  CU(cudaGetLastError());
+  return BANDUP_GPU_OK;
+}
+
+}  // extern "C"

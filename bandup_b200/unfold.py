@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference's `band_unfolding` module for the hot path.
+
+Names, argument meaning and error behaviour follow the reference
+(/root/reference/src/band_unfolding_routines_mod.f90 and main_BandUP.f90:131-177)
+so that parity tests read like calls into the Fortran; every number is produced
+by libbandup_gpu.so through the C ABI (include/bandup_gpu.h).  Nothing here
+computes on the CPU and nothing here imports the oracle.
+
+Array conventions (NumPy, C order):
+  * lattices are (3,3) with ROW i = vector i, like `crystal%rec_latt_vecs(i,:)`;
+  * pw_coeffs has shape (n_bands, n_pw, n_spinor) complex64, which is byte for
+    byte the Fortran array pw_coeffs(n_spinor, n_pw, n_bands)
+    (constants_and_types_mod.f90:151);
+  * G_frac is (n_pw, 3) int32 == wf%G_frac(:)%coord(1:3).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import BandupGpuError, CONST, c_f64p, c_i32p
+
+LAYOUT_FORTRAN_INMEM = CONST["BANDUP_GPU_LAYOUT_FORTRAN_INMEM"]
+LAYOUT_VASP_RECORD = CONST["BANDUP_GPU_LAYOUT_VASP_RECORD"]
+MAX_FOLDS = CONST["BANDUP_GPU_MAX_FOLDS"]
+
+
+def _fortran_order(latt: np.ndarray) -> np.ndarray:
+    """(3,3) row=vector matrix -> the 9 doubles as Fortran stores latt(i,j)."""
+    a = np.asarray(latt, dtype=np.float64)
+    if a.shape != (3, 3):
+        raise ValueError("lattice must be 3x3")
+    return np.ascontiguousarray(a.T).ravel()
+
+
+@dataclass
+class PwWavefunction:
+    """type(pw_wavefunction) (constants_and_types_mod.f90:140-153), hot-path fields only."""
+    pw_coeffs: np.ndarray                 # complex64 (n_bands, n_pw, n_spinor) or a raw record buffer
+    G_frac: np.ndarray                    # int32 (n_pw, 3)
+    band_energies: np.ndarray             # float64 (n_bands,)
+    kpt_frac_coords: Optional[np.ndarray] = None
+    n_pw: int = 0
+    n_bands: int = 0
+    n_spinor: int = 1
+    layout: int = LAYOUT_FORTRAN_INMEM
+    band_stride_bytes: int = 0            # 0: densely packed rows
+
+    def __post_init__(self):
+        self.G_frac = np.ascontiguousarray(self.G_frac, dtype=np.int32)
+        self.band_energies = np.ascontiguousarray(self.band_energies, dtype=np.float64)
+        if self.layout == LAYOUT_FORTRAN_INMEM and self.pw_coeffs.ndim == 3:
+            c = self.pw_coeffs
+            if c.dtype != np.complex64 or not c.flags.c_contiguous:
+                c = np.ascontiguousarray(c, dtype=np.complex64)
+            self.pw_coeffs = c
+            self.n_bands, self.n_pw, self.n_spinor = c.shape
+        if not self.n_pw:
+            self.n_pw = int(self.G_frac.shape[0])
+        if not self.n_bands:
+            self.n_bands = int(self.band_energies.shape[0])
+        if not self.band_stride_bytes:
+            self.band_stride_bytes = self.n_pw * self.n_spinor * 8
+        if self.G_frac.shape != (self.n_pw, 3):
+            raise ValueError("G_frac must be (n_pw, 3)")
+        if self.band_energies.shape != (self.n_bands,):
+            raise ValueError("band_energies must be (n_bands,)")
+
+
+@dataclass
+class UnfoldedKpt:
+    """What perform_unfolding leaves behind for the pc-kpts folding onto one SC-kpt."""
+    spectral_weight: np.ndarray           # (n_fold, n_bands)   P_mK(k)
+    dN: np.ndarray                        # (n_fold, nener)     delta_N(k, E)
+    n_selected: np.ndarray                # (n_fold,)           size(selected_coeff_indices)
+    band_norms: np.ndarray                # (n_bands,)          sum_G |C|^2 before renormalisation
+    selected_coeff_indices: Optional[List[np.ndarray]] = None   # 1-based, ascending
+
+    def pckpt_cannot_be_parsed(self) -> np.ndarray:
+        """main_BandUP.f90:161-172: an empty selection is the reference's fatal branch."""
+        return self.n_selected == 0
+
+
+class GpuUnfolder:
+    """One device context; single caller thread (like the serial part of BandUP_main)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _capi.load()
+        h = C.c_int(-1)
+        rc = self._lib.bandup_gpu_init(int(device), C.byref(h))
+        if rc != 0:
+            raise BandupGpuError(rc, self._lib.bandup_gpu_last_error(-1).decode())
+        self.handle = h.value
+        self.device = device
+        self.nener = 0
+        self.energy_grid: Optional[np.ndarray] = None
+        self.M: Optional[np.ndarray] = None
+        self._inflight = {}
+
+    # -- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "handle", -1) >= 0:
+            self._lib.bandup_gpu_finalize(self.handle)
+            self.handle = -1
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        _capi.check(self.handle, rc)
+
+    # -- run-wide set-up ----------------------------------------------------
+    def verify_commens(self, rec_latt_pc: np.ndarray, rec_latt_SC: np.ndarray,
+                       tol: float = 0.0) -> np.ndarray:
+        """check_if_pc_and_SC_are_commensurate (crystals_mod.f90:41-73) as used by
+        verify_commens; returns int_M with A_i = sum_j M_ij a_j.  Raises
+        BandupGpuError(NOT_COMMENSURATE) where the reference prints and stops."""
+        b = _fortran_order(rec_latt_pc)
+        B = _fortran_order(rec_latt_SC)
+        M = np.zeros(9, dtype=np.int32)
+        self._check(self._lib.bandup_gpu_set_cells(
+            self.handle, B.ctypes.data_as(c_f64p), b.ctypes.data_as(c_f64p), float(tol),
+            M.ctypes.data_as(c_i32p)))
+        self.M = M.reshape(3, 3).T.copy()  # Fortran order -> row-major
+        return self.M
+
+    def set_energy_grid(self, E_start: float, E_end: float, delta_e: float,
+                        smearing_for_delta_function: Optional[float] = None) -> np.ndarray:
+        """real_seq (lists_and_seqs_mod.f90:188-200) + sigma of get_delta_Ns_for_EBS (:774-777)."""
+        n = C.c_int32(0)
+        sm = -1.0 if smearing_for_delta_function is None else abs(float(smearing_for_delta_function))
+        if smearing_for_delta_function is not None and sm == 0.0:
+            sm = 1e-300  # present but zero: max(epsilon, 0) = epsilon
+        self._check(self._lib.bandup_gpu_set_grid(self.handle, float(E_start), float(E_end),
+                                                  float(delta_e), sm, C.byref(n)))
+        self.nener = n.value
+        grid = np.zeros(self.nener, dtype=np.float64)
+        self._check(self._lib.bandup_gpu_get_grid(self.handle, grid.ctypes.data_as(c_f64p)))
+        self.energy_grid = grid
+        return grid
+
+    def folding_g0(self, folding_G: np.ndarray):
+        """folding_G = Scoords(k) - K (Cartesian) -> integer SC Miller triple + residual."""
+        fg = np.ascontiguousarray(np.atleast_2d(folding_G), dtype=np.float64)
+        g0 = np.zeros((fg.shape[0], 3), dtype=np.int32)
+        res = C.c_double(0.0)
+        self._check(self._lib.bandup_gpu_folding_g0(self.handle, fg.ctypes.data_as(c_f64p), fg.shape[0],
+                                                    g0.ctypes.data_as(c_i32p), C.byref(res)))
+        return g0, res.value
+
+    # -- per SC k-point -----------------------------------------------------
+    def submit(self, ikpt: int, wf: PwWavefunction, folding_G: Optional[np.ndarray] = None,
+               g0: Optional[np.ndarray] = None) -> None:
+        """Asynchronous: upload + kernels for all pc-kpts folding onto SC-kpt `ikpt`."""
+        if g0 is None:
+            g0, _ = self.folding_g0(folding_G)
+        g0 = np.ascontiguousarray(np.atleast_2d(g0), dtype=np.int32)
+        n_fold = g0.shape[0]
+        coeffs = wf.pw_coeffs
+        ptr = coeffs.ctypes.data if isinstance(coeffs, np.ndarray) else int(coeffs)
+        self._check(self._lib.bandup_gpu_submit_kpt(
+            self.handle, int(ikpt), wf.n_spinor, wf.n_pw, wf.n_bands, wf.layout,
+            int(wf.band_stride_bytes), C.c_void_p(ptr), wf.G_frac.ctypes.data_as(c_i32p),
+            wf.band_energies.ctypes.data_as(c_f64p), n_fold, g0.ctypes.data_as(c_i32p)))
+        # keep the host arrays alive until fetch (the upload is asynchronous)
+        self._inflight[int(ikpt)] = (wf, g0, n_fold)
+
+    def fetch(self, ikpt: int, want_selected: bool = False) -> UnfoldedKpt:
+        wf, g0, n_fold = self._inflight.pop(int(ikpt))
+        w = np.zeros((n_fold, wf.n_bands), dtype=np.float64)
+        dN = np.zeros((n_fold, self.nener), dtype=np.float64)
+        ns = np.zeros(n_fold, dtype=np.int32)
+        norms = np.zeros(wf.n_bands, dtype=np.float64)
+        sel = None
+        cap = 0
+        if want_selected:
+            cap = n_fold * wf.n_pw
+            sel = np.zeros(cap, dtype=np.int32)
+        self._check(self._lib.bandup_gpu_fetch_kpt(
+            self.handle, int(ikpt), w.ctypes.data_as(c_f64p), dN.ctypes.data_as(c_f64p),
+            ns.ctypes.data_as(c_i32p), norms.ctypes.data_as(c_f64p),
+            sel.ctypes.data_as(c_i32p) if sel is not None else None, cap))
+        lists = None
+        if sel is not None:
+            off = np.concatenate([[0], np.cumsum(ns)])
+            lists = [sel[off[f]:off[f + 1]].copy() for f in range(n_fold)]
+        return UnfoldedKpt(w, dN, ns, norms, lists)
+
+    def perform_unfolding(self, wf: PwWavefunction, folding_G: Optional[np.ndarray] = None,
+                          g0: Optional[np.ndarray] = None, ikpt: int = 1,
+                          want_selected: bool = True) -> UnfoldedKpt:
+        """The body of the reference's `if(pckpt_folds)` block (main_BandUP.f90:145-172) for
+        every pc-kpt folding onto this SC-kpt: renormalise -> select -> weights -> delta_N."""
+        self.submit(ikpt, wf, folding_G=folding_G, g0=g0)
+        return self.fetch(ikpt, want_selected=want_selected)
+
+    def select_coeffs_to_calc_spectral_weights(self, wf: PwWavefunction,
+                                               folding_G: np.ndarray) -> List[np.ndarray]:
+        """band_unfolding_routines_mod.f90:550-612; returns selected_coeff_indices (1-based,
+        ascending) per pc-kpt.  An empty list is the reference's 'not allocated'."""
+        return self.perform_unfolding(wf, folding_G, want_selected=True).selected_coeff_indices
+
+    # -- device-resident path (bench, torch interop) -------------------------
+    def workspace_bytes(self, n_spinor: int, n_pw: int, n_bands: int, n_fold: int) -> int:
+        return int(self._lib.bandup_gpu_workspace_bytes(self.handle, n_spinor, n_pw, n_bands, n_fold))
+
+    def unfold_device(self, stream: int, n_spinor: int, n_pw: int, n_bands: int, layout: int,
+                      band_stride_bytes: int, d_coeffs: int, d_g_frac: int, d_band_energies: int,
+                      g0: np.ndarray, d_weights: int, d_dN: int, d_n_selected: int,
+                      d_workspace: int, workspace_bytes: int, d_norms: int = 0,
+                      d_slot_out: int = 0) -> None:
+        g0 = np.ascontiguousarray(np.atleast_2d(g0), dtype=np.int32)
+        self._check(self._lib.bandup_gpu_unfold_device(
+            self.handle, C.c_void_p(stream), n_spinor, n_pw, n_bands, layout, int(band_stride_bytes),
+            C.c_void_p(d_coeffs), C.c_void_p(d_g_frac), C.c_void_p(d_band_energies), g0.shape[0],
+            g0.ctypes.data_as(c_i32p), C.c_void_p(d_weights), C.c_void_p(d_dN),
+            C.c_void_p(d_n_selected), C.c_void_p(d_norms or None), C.c_void_p(d_slot_out or None),
+            C.c_void_p(d_workspace), int(workspace_bytes)))
+
+    def synth_fill_device(self, stream: int, d_coeffs: int, row_elems: int, n_bands: int,
+                          band_stride_bytes: int, seed: int, ikpt: int) -> None:
+        self._check(self._lib.bandup_gpu_synth_fill_device(
+            self.handle, C.c_void_p(stream), C.c_void_p(d_coeffs), int(row_elems), int(n_bands),
+            int(band_stride_bytes), C.c_uint64(seed), C.c_uint64(ikpt)))
+
+    # -- instrumentation ------------------------------------------------------
+    def set_profiling(self, enabled: bool) -> None:
+        self._check(self._lib.bandup_gpu_set_profiling(self.handle, int(bool(enabled))))
+
+    def reset_kernel_times(self) -> None:
+        self._check(self._lib.bandup_gpu_reset_kernel_times(self.handle))
+
+    def kernel_time(self, which: int):
+        ms = C.c_double(0.0)
+        n = C.c_int64(0)
+        self._check(self._lib.bandup_gpu_kernel_time(self.handle, which, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def launch_count(self) -> int:
+        return int(self._lib.bandup_gpu_launch_count(self.handle))
+
+    def set_tuning(self, chunk_vecs: int = 0, ctas_per_sm: int = 0) -> None:
+        self._check(self._lib.bandup_gpu_set_tuning(self.handle, int(chunk_vecs), int(ctas_per_sm)))
+
+
+def pinned_empty(nbytes: int) -> np.ndarray:
+    """uint8 NumPy view of page-locked host memory (bandup_gpu_pinned_alloc)."""
+    lib = _capi.load()
+    p = C.c_void_p()
+    rc = lib.bandup_gpu_pinned_alloc(int(nbytes), C.byref(p))
+    if rc != 0:
+        raise BandupGpuError(rc, lib.bandup_gpu_last_error(-1).decode())
+    buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    return arr

@@ -1,0 +1,203 @@
+/*
+ * bandup_gpu.h -- C ABI of libbandup_gpu.so, the B200 (sm_100a) drop-in for the
+ * weight loop of BandUP's module `band_unfolding`.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative
+ * to the reference's src/).  The reference has no FFI seam on this path today:
+ * the procedures below are ordinary Fortran module procedures called from the
+ * main loop (main_BandUP.f90:145-172).  The binding a maintainer adds is the
+ * ISO_C_BINDING module fortran/bandup_gpu_mod.f90; the
+ * reference's only C-interop precedent, spglib_f08, sets the style: plain
+ * pointers, C ints by value, integer status returned.
+ *
+ * Conventions
+ *  - Every function returns BANDUP_GPU_OK (0) or a positive error code; nothing
+ *    aborts or throws across the boundary (the Fortran caller prints and
+ *    `stop`s exactly where the reference does).
+ *  - 3x3 matrices are passed in FORTRAN MEMORY ORDER (column-major) exactly as
+ *    `crystal%rec_latt_vecs` lies in memory, where Fortran row i is lattice
+ *    vector i: element (i,j) is at [ (j-1)*3 + (i-1) ].
+ *  - Handles are small ints (Fortran integer(c_int)).  One caller thread per
+ *    handle; handles on different devices are independent.
+ *  - The caller owns every host array; the library owns device memory and its
+ *    pinned result staging.
+ */
+#ifndef BANDUP_GPU_H_
+#define BANDUP_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BANDUP_GPU_ABI_VERSION 1
+
+/* status codes */
+#define BANDUP_GPU_OK 0
+#define BANDUP_GPU_ERR_INVALID_ARG 1
+#define BANDUP_GPU_ERR_CUDA 2
+/* band_unfolding_routines_mod.f90:132 (verify_commens): cells not commensurate */
+#define BANDUP_GPU_ERR_NOT_COMMENSURATE 3
+/* select_coeffs...:582-601 gave up: folding vector is not an SC reciprocal-lattice
+ * vector within max_tol_for_vec_equality (1e-3) */
+#define BANDUP_GPU_ERR_FOLDING_VECTOR 4
+#define BANDUP_GPU_ERR_TOO_MANY_FOLDS 5
+#define BANDUP_GPU_ERR_BAD_HANDLE 6
+#define BANDUP_GPU_ERR_NOT_CONFIGURED 7 /* set_cells / set_grid not called yet */
+#define BANDUP_GPU_ERR_UNKNOWN_KPT 8    /* fetch of an ikpt that is not in flight */
+#define BANDUP_GPU_ERR_NO_DEVICE 9      /* no usable sm_100 device: there is NO CPU fallback */
+#define BANDUP_GPU_ERR_CAPACITY 10      /* caller-provided output buffer too small */
+/* calc_rho :1070-1074 'ERROR (calc_rho): delta_N = 0.' */
+#define BANDUP_GPU_ERR_DELTA_N_ZERO 11
+#define BANDUP_GPU_ERR_INT_OVERFLOW 12  /* Miller indices x adjugate would overflow */
+
+/* most pc-kpts that may fold onto one SC-kpt in a single submit */
+#define BANDUP_GPU_MAX_FOLDS 96
+
+/* coefficient layouts accepted by submit_kpt / unfold_device */
+/* pw_coeffs(n_spinor, n_pw, n_bands) as it lies in Fortran memory:
+ * [band][pw][spinor] complex64 (constants_and_types_mod.f90:151) */
+#define BANDUP_GPU_LAYOUT_FORTRAN_INMEM 0
+/* raw WAVECAR band records: [band][spinor][pw] complex64, consecutive bands
+ * band_stride_bytes (= nrecl) apart (read_wavecar_mod.f90:570-577) */
+#define BANDUP_GPU_LAYOUT_VASP_RECORD 1
+
+/* ---- lifetime --------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device`.  Fails with ERR_NO_DEVICE when
+ * the device is absent or is not compute capability 10.x. */
+int bandup_gpu_init(int device, int *handle);
+int bandup_gpu_finalize(int handle);
+/* Human-readable text of the last error on this handle (never NULL). */
+const char *bandup_gpu_last_error(int handle);
+int bandup_gpu_abi_version(void);
+
+/* Pinned host memory for the wavefunction reader to read into, so that
+ * submit_kpt's upload is a true asynchronous DMA (optional). */
+int bandup_gpu_pinned_alloc(size_t bytes, void **ptr);
+int bandup_gpu_pinned_free(void *ptr);
+
+/* ---- run-wide set-up -------------------------------------------------- */
+
+/* Replaces check_if_pc_and_SC_are_commensurate (crystals_mod.f90:41-73) as
+ * called from verify_commens: M = transpose(b_pc . inverse(B_sc)),
+ * int_M = nint(M), commensurate iff max|M - int_M| <= tol (tol <= 0: 1e-5).
+ * Stores int_M, det M and the integer adjugate used by the coset kernel.
+ * M_out (nullable) receives int_M in Fortran order.  */
+int bandup_gpu_set_cells(int handle, const double *B_sc, const double *b_pc,
+                         double tol, int32_t *M_out);
+
+/* Replaces real_seq(E_start, E_end, delta_e) (lists_and_seqs_mod.f90:188-200)
+ * + the sigma choice of get_delta_Ns_for_EBS (band_unfolding_routines_mod.f90:
+ * 774-777): smearing <= 0 means "argument absent" -> sigma = epsilon(1.0_dp)
+ * (box integration); otherwise sigma = max(epsilon, |smearing|).
+ * nener_out (nullable) receives the number of grid points. */
+int bandup_gpu_set_grid(int handle, double E_start, double E_end, double delta_e,
+                        double smearing, int32_t *nener_out);
+/* Copies the energy grid (nener doubles) the kernels use. */
+int bandup_gpu_get_grid(int handle, double *energies);
+
+/* Replaces the float part of select_coeffs_to_calc_spectral_weights
+ * (band_unfolding_routines_mod.f90:571-576): folding_G = Scoords(k) - K in
+ * Cartesian 1/Angstrom, [n_fold][3].  Writes g0 = nint(folding_G . inverse(B_sc))
+ * ([n_fold][3], SC Miller indices) and, when non-NULL, the largest Cartesian
+ * residual |g0.B_sc - folding_G|.  Returns ERR_FOLDING_VECTOR when a residual
+ * exceeds 1e-3 (the reference's max_tol_for_vec_equality). */
+int bandup_gpu_folding_g0(int handle, const double *folding_G, int n_fold,
+                          int32_t *g0, double *max_residual);
+
+/* ---- per SC-k-point, host buffers (the drop-in path) -------------------- */
+
+/* Replaces, for ALL pc-kpts folding onto SC-kpt `ikpt` at once:
+ *   the renormalisation in read_wavefunction   (io_routines_mod.f90:1317-1330)
+ *   select_coeffs_to_calc_spectral_weights      (band_unfolding_routines_mod.f90:550-612)
+ *   spectral_weight_for_coeff + spinor sum      (:615-651, :1335-1345)
+ *   get_delta_Ns_for_EBS                        (:760-786, :719-757)
+ * Asynchronous: enqueues upload + kernels and returns; up to
+ * bandup_gpu_pipeline_depth() k-points may be in flight (double buffering), a
+ * further submit first waits for the oldest to be fetched.
+ *   coeffs         host pointer (pinned or pageable), layout as `layout`;
+ *                  NOT renormalised by the caller (renormalised input is also
+ *                  fine: the division by the band norm is then a no-op)
+ *   g_frac         int32 [n_pw][3] == wf%G_frac (read_wavecar_mod.f90:296-298)
+ *   band_energies  double [n_bands] == wf%band_energies
+ *   g0             int32 [n_fold][3] from bandup_gpu_folding_g0
+ */
+int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw,
+                          int n_bands, int layout, int64_t band_stride_bytes,
+                          const void *coeffs, const int32_t *g_frac,
+                          const double *band_energies, int n_fold,
+                          const int32_t *g0);
+
+/* Blocks until k-point `ikpt` is done and copies out:
+ *   weights    [n_fold][n_bands]  P_mK(k)           (spectral_weight, :1333-1345)
+ *   dN         [n_fold][nener]    delta_N(k, E_i)   (%dN, :1355-1360)
+ *   n_selected [n_fold]  size(selected_coeff_indices); 0 <=> the reference's
+ *              "pckpt cannot be parsed" branch (main_BandUP.f90:167-171)
+ *   norms      [n_bands] (nullable) sum_G |C|^2 before renormalisation
+ *   selected   (nullable) 1-based ascending plane-wave indices, the folds'
+ *              lists concatenated (CSR by n_selected); selected_capacity is
+ *              the number of int32 available.
+ * Any of weights / dN / n_selected may be NULL. */
+int bandup_gpu_fetch_kpt(int handle, int ikpt, double *weights, double *dN,
+                         int32_t *n_selected, double *norms, int32_t *selected,
+                         int64_t selected_capacity);
+
+int bandup_gpu_pipeline_depth(int handle);
+
+/* ---- per SC-k-point, device-resident buffers ---------------------------- */
+
+/* Scratch bytes unfold_device needs for these sizes. */
+size_t bandup_gpu_workspace_bytes(int handle, int n_spinor, int n_pw, int n_bands,
+                                  int n_fold);
+
+/* Same computation as submit+fetch but on buffers already in HBM; everything
+ * is enqueued on `stream` (a cudaStream_t; NULL = default stream), nothing is
+ * synchronised.  All d_* pointers are device pointers; g0 is a HOST pointer.
+ * d_norms, d_slot_out (uint8 [n_pw]: fold id or 255) may be NULL. */
+int bandup_gpu_unfold_device(int handle, void *stream, int n_spinor, int n_pw,
+                             int n_bands, int layout, int64_t band_stride_bytes,
+                             const void *d_coeffs, const int32_t *d_g_frac,
+                             const double *d_band_energies, int n_fold,
+                             const int32_t *g0, double *d_weights, double *d_dN,
+                             int32_t *d_n_selected, double *d_norms,
+                             uint8_t *d_slot_out, void *d_workspace,
+                             size_t workspace_bytes);
+
+/* ---- instrumentation ---------------------------------------------------- */
+
+/* Kernel ids for bandup_gpu_kernel_time */
+#define BANDUP_GPU_K_COSET 0
+#define BANDUP_GPU_K_WEIGHTS 1
+#define BANDUP_GPU_K_FINALIZE 2
+#define BANDUP_GPU_K_DELTA_N 3
+#define BANDUP_GPU_K_COUNT 4
+
+/* When enabled, every launch is bracketed by CUDA events on its own stream. */
+int bandup_gpu_set_profiling(int handle, int enabled);
+/* Synchronises the device, then returns summed milliseconds and launch count
+ * of kernel `which` since the last reset. */
+int bandup_gpu_kernel_time(int handle, int which, double *total_ms,
+                           int64_t *launches);
+int bandup_gpu_reset_kernel_times(int handle);
+/* Total number of kernels this handle has launched (never reset). */
+int64_t bandup_gpu_launch_count(int handle);
+
+/* Tuning knobs of the weights kernel (0 = keep default): tile size in 16-byte
+ * vectors per (band, chunk) tile and resident CTAs per SM. */
+int bandup_gpu_set_tuning(int handle, int chunk_vecs, int ctas_per_sm);
+
+/* Fills a device buffer with the synthetic coefficients bench.py and the tests
+ * use (same hash as oracle/bandup_oracle.c:bo_synth_fill): n_bands rows of
+ * row_elems complex64, rows band_stride_bytes apart. */
+int bandup_gpu_synth_fill_device(int handle, void *stream, void *d_coeffs,
+                                 int64_t row_elems, int n_bands,
+                                 int64_t band_stride_bytes, uint64_t seed,
+                                 uint64_t ikpt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BANDUP_GPU_H_ */
