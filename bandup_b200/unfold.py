@@ -27,6 +27,10 @@ from ._capi import BandupGpuError, CONST, c_f64p, c_i32p
 LAYOUT_FORTRAN_INMEM = CONST["BANDUP_GPU_LAYOUT_FORTRAN_INMEM"]
 LAYOUT_VASP_RECORD = CONST["BANDUP_GPU_LAYOUT_VASP_RECORD"]
 MAX_FOLDS = CONST["BANDUP_GPU_MAX_FOLDS"]
+K_COSET = CONST["BANDUP_GPU_K_COSET"]
+K_WEIGHTS = CONST["BANDUP_GPU_K_WEIGHTS"]
+K_FINALIZE = CONST["BANDUP_GPU_K_FINALIZE"]
+K_DELTA_N = CONST["BANDUP_GPU_K_DELTA_N"]
 
 
 def _fortran_order(latt: np.ndarray) -> np.ndarray:
@@ -177,6 +181,17 @@ class GpuUnfolder:
             wf.band_energies.ctypes.data_as(c_f64p), n_fold, g0.ctypes.data_as(c_i32p)))
         # keep the host arrays alive until fetch (the upload is asynchronous)
         self._inflight[int(ikpt)] = (wf, g0, n_fold)
+
+    def fetch_raw(self, ikpt: int, n_fold: int, n_bands: int):
+        """bandup_gpu_fetch_kpt without the bookkeeping of submit(): weights, dN, n_selected."""
+        w = np.zeros((n_fold, n_bands), dtype=np.float64)
+        dN = np.zeros((n_fold, max(self.nener, 1)), dtype=np.float64)
+        ns = np.zeros(n_fold, dtype=np.int32)
+        self._check(self._lib.bandup_gpu_fetch_kpt(
+            self.handle, int(ikpt), w.ctypes.data_as(c_f64p), dN.ctypes.data_as(c_f64p),
+            ns.ctypes.data_as(c_i32p), None, None, 0))
+        self._inflight.pop(int(ikpt), None)
+        return w, dN, ns
 
     def fetch(self, ikpt: int, want_selected: bool = False) -> UnfoldedKpt:
         wf, g0, n_fold = self._inflight.pop(int(ikpt))

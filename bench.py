@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- the unfolding hot path on B200: coefficient GB/s against the HBM roofline,
+SC-kpts/s end to end, and the CPU restatement of the reference timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload sige555|mos2_8x8_spinor|si333_vacancy|graphene4x4]
+                    [--kpts-per-step 4]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path (K1 coset
+classification -> K2 fused norm + masked |C|^2 reduction -> K2b -> K3 delta_N) over one batch
+of `kpts-per-step` SC k-points PER GPU (weak scaling: SC k-points are independent units;
+the only exchange is the gather of the disjoint delta_N rows, done with NCCL when N > 1).
+
+  value      coeff GB/s = sum over ranks of n_bands*n_pw*n_spinor*8 bytes / device time,
+             inputs resident in HBM (each SC-kpt block is 2.4 GB >> 126 MB L2: no flush needed)
+  e2e        the same metric through the host C ABI (bandup_gpu_submit_kpt/fetch_kpt) with
+             pinned HOST buffers: H2D of every coefficient block and D2H of weights/delta_N
+             inside the timed region (double-buffered, PCIe-bound)
+  roofline   K2 (k2_weights_reduce) alone: algorithmic bytes per launch / mean launch time,
+             measured live with CUDA events on the launching stream, vs MEASURED_PEAKS.json
+  cpu_baseline  oracle/ (C + OpenMP restatement of the reference's Fortran loops; the Fortran
+             itself cannot be compiled in this image) on a bounded sample of the same workload
+
+--impl reference times that CPU restatement alone (rank 0 only), same metric and config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+SEED = 20261019 + 5
+METRIC = "coeff_GB_per_s"
+UNIT = "GB/s"
+
+WORKLOADS = {
+    "sige555": "C5: 1000-atom Si-Ge 5x5x5 supercell, 3000 bands, ~100k PWs, det M=500, 200 SC k-points",
+    "mos2_8x8_spinor": "C3: MoS2 8x8 monolayer, spinor, 1200 bands, ~80k PWs, det M=64",
+    "si333_vacancy": "C2: Si 3x3x3 vacancy supercell, 500 bands, ~20k PWs, det M=108, 100 SC k-points",
+    "graphene4x4": "C1: graphene 4x4, 64 bands, ~23k PWs, det M=16, 30 SC k-points",
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sige555", choices=sorted(WORKLOADS))
+    ap.add_argument("--kpts-per-step", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 4)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons of one GPU, sampled every 200 ms while running."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # "under load": samples whose power is above half of the maximum seen
+        if sm:
+            thr = 0.5 * max(pw)
+            load = [s for s, p in zip(sm, pw) if p >= thr] or sm
+            return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                    "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+
+
+def make_energies(sc, rng):
+    return np.sort(rng.uniform(sc.e_fermi - 20.5, sc.e_fermi + 5.5, size=sc.n_bands))
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_sample(sc, k_indices, seconds_budget, max_kpts, threads=None):
+    """Times oracle.unfold_kpt (renormalise + select + weights + delta_N: the reference's loop
+    body, main_BandUP.f90:145-172) on full-size SC k-points of the workload.  Returns
+    (GB/s, kpts/s, cores, n_kpts_done, per-phase seconds)."""
+    from oracle import oracle as O
+    if threads:
+        O.set_num_threads(threads)
+    cores = O.num_threads()
+    grid = O.real_seq(*sc.energy_window())
+    rng = np.random.default_rng(SEED)
+    tot_bytes, tot_t, done = 0, 0.0, 0
+    phases = np.zeros(3)
+    block = None
+    for iK in k_indices[:max_kpts]:
+        gf = sc.gvecs(iK)
+        n_pw = gf.shape[0]
+        row = n_pw * sc.n_spinor
+        if block is None or block.shape[1] != row:
+            block = np.empty((sc.n_bands, row), dtype=np.complex64)
+        O.synth_fill(row, sc.n_bands, SEED, iK, out=block)
+        ener = make_energies(sc, rng)
+        gc = gf @ sc.B_sc
+        fG = sc.folding_G(iK)
+        t0 = time.perf_counter()
+        _, _, _, times = O.unfold_kpt(block.reshape(sc.n_bands, n_pw, sc.n_spinor), gc, ener, sc.b_pc, fG, grid,
+                                      norm_mode=0, in_place=True)
+        dt = time.perf_counter() - t0
+        tot_t += dt
+        phases += times
+        tot_bytes += sc.n_bands * row * 8
+        done += 1
+        if tot_t >= seconds_budget:
+            break
+    return tot_bytes / tot_t / 1e9, done / tot_t, cores, done, phases
+
+
+def run_reference(args, sc, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    ks = list(range(sc.n_sc_kpts))
+    n_w, n_s = max(args.warmup, 0), max(args.steps, 1)
+    # bounded sample: each step is ONE full-size SC k-point of the workload (its own batch of
+    # kpts_per_step would take minutes on the host)
+    if n_w:
+        cpu_sample(sc, ks, 1e9, min(n_w, 1))
+    gbs, kps, cores, done, phases = cpu_sample(sc, ks[1:], 1e9, n_s)
+    line = {
+        "metric": METRIC, "value": gbs, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+        "steps": n_s, "warmup": n_w, "ms_per_step": 1e3 / kps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "c64 in, f32 |C|^2, f64 accumulate",
+        "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "kpts_per_step": 1, "n_bands": sc.n_bands,
+                   "n_spinor": sc.n_spinor},
+        "sc_kpts_per_s": kps,
+        "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{done} full-size SC k-points, one per step; C+OpenMP restatement of "
+                                   "the reference loops (Fortran unbuildable here: no Fortran compiler)",
+                         "phase_seconds": {"renormalise": phases[0], "select+weights": phases[1],
+                                           "delta_N": phases[2]}},
+        "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_b200(args, sc, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from bandup_b200 import build as _build
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    else:
+        _build.build()
+    from bandup_b200.unfold import (GpuUnfolder, PwWavefunction, LAYOUT_FORTRAN_INMEM, pinned_empty, K_WEIGHTS)
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    u = GpuUnfolder(local_rank)
+    u.verify_commens(sc.b_pc, sc.B_sc)
+    grid = u.set_energy_grid(*sc.energy_window())
+    nener = len(grid)
+    kps = args.kpts_per_step
+    nb, nsp = sc.n_bands, sc.n_spinor
+    rng = np.random.default_rng(SEED + rank)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    # this rank's shard of SC k-points (contiguous blocks of the K list)
+    my_k = [(rank * kps + j) % sc.n_sc_kpts for j in range(kps)]
+    items = []
+    for iK in my_k:
+        gf = sc.gvecs(iK)
+        n_pw = gf.shape[0]
+        g0, _ = u.folding_g0(sc.folding_G(iK))
+        nf = g0.shape[0]
+        ener = make_energies(sc, rng)
+        d_c = torch.empty((nb, n_pw * nsp, 2), dtype=torch.float32, device=dev)
+        u.synth_fill_device(stream, d_c.data_ptr(), n_pw * nsp, nb, n_pw * nsp * 8, SEED, iK)
+        ws = u.workspace_bytes(nsp, n_pw, nb, nf)
+        items.append(dict(
+            iK=iK, n_pw=n_pw, nf=nf, g0=g0, gf=gf, ener=ener, d_c=d_c,
+            d_g=torch.from_numpy(gf).to(dev), d_e=torch.from_numpy(ener).to(dev),
+            d_w=torch.empty((nf, nb), dtype=torch.float64, device=dev),
+            d_ns=torch.empty(nf, dtype=torch.int32, device=dev),
+            d_ws=torch.empty(ws, dtype=torch.uint8, device=dev), ws=ws))
+    nf_max = max(len(f) for f in sc.folds)
+    # delta_N rows of the step, padded to nf_max rows per SC-kpt for the gather
+    d_dn = torch.zeros((kps, nf_max, nener), dtype=torch.float64, device=dev)
+    d_dn_all = torch.empty((world, kps, nf_max, nener), dtype=torch.float64, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+    step_bytes = sum(nb * it["n_pw"] * nsp * 8 for it in items)
+
+    def step():
+        for j, it in enumerate(items):
+            u.unfold_device(stream, nsp, it["n_pw"], nb, LAYOUT_FORTRAN_INMEM, it["n_pw"] * nsp * 8,
+                            it["d_c"].data_ptr(), it["d_g"].data_ptr(), it["d_e"].data_ptr(), it["g0"],
+                            it["d_w"].data_ptr(), d_dn[j].data_ptr(), it["d_ns"].data_ptr(),
+                            it["d_ws"].data_ptr(), it["ws"])
+        if world > 1:   # the path's only exchange: gather the disjoint delta_N rows
+            dist.all_gather_into_tensor(d_dn_all, d_dn)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing -------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    u.set_profiling(True)
+    u.reset_kernel_times()
+    launches0 = u.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    gpu_launches = u.launch_count() - launches0
+    k2_ms, k2_n = u.kernel_time(K_WEIGHTS)
+    all_ms = sum(u.kernel_time(k)[0] for k in range(4))
+    u.set_profiling(False)
+    # every rank streams its own shard; shard sizes differ only through n_pw(K) (a few per cent)
+    if world > 1:
+        t = torch.tensor([float(step_bytes)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        total_bytes = float(t.item()) * args.steps
+    else:
+        total_bytes = float(step_bytes) * args.steps
+    value = total_bytes / (ms * 1e-3) / 1e9
+    kpts_per_s = kps * world * args.steps / (ms * 1e-3)
+    k2_bytes = step_bytes / kps
+    peak, peak_src = measured_peak_gbs()
+    achieved = k2_bytes / (k2_ms / max(k2_n, 1) * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k2_weights_reduce", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": k2_bytes, "ms_per_launch": k2_ms / max(k2_n, 1),
+                "k2_share_of_kernel_time": k2_ms / all_ms if all_ms else None}
+    ncu_traffic = ROOT / "profiles" / "k2_traffic.json"
+    if ncu_traffic.exists():
+        try:
+            t = json.loads(ncu_traffic.read_text())
+            if t.get("workload") == args.workload:
+                roofline["traffic"] = t["dram_bytes_per_launch"]
+                roofline["traffic_source"] = t.get("source")
+        except Exception:
+            pass
+
+    # ---- end to end through the host C ABI ----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = args.e2e_steps or min(args.steps, 4)
+        host = []
+        for it in items[:2]:     # two distinct pinned blocks, cycled (2 x 2.4 GB per rank)
+            nbytes = nb * it["n_pw"] * nsp * 8
+            h = pinned_empty(nbytes)
+            torch.from_numpy(h).copy_(it["d_c"].view(torch.uint8).reshape(-1))
+            host.append((h, it))
+        torch.cuda.synchronize()
+        wfs = [PwWavefunction(h.view(np.complex64).reshape(nb, it["n_pw"], nsp), it["gf"], it["ener"])
+               for h, it in host]
+        seq = [(i % len(host)) for i in range(kps)]
+        h2d = sum(nb * host[i][1]["n_pw"] * nsp * 8 + host[i][1]["n_pw"] * 12 + nb * 8 for i in seq)
+        d2h = sum(host[i][1]["nf"] * (nb + nener) * 8 + host[i][1]["nf"] * 4 + nb * 8 for i in seq)
+
+        def e2e_step(base):
+            # double-buffered: SC-kpt j+1 uploads while j computes (bandup_gpu_pipeline_depth = 2)
+            u.submit(base, wfs[seq[0]], g0=host[seq[0]][1]["g0"])
+            out = None
+            for j in range(kps):
+                if j + 1 < kps:
+                    u.submit(base + j + 1, wfs[seq[j + 1]], g0=host[seq[j + 1]][1]["g0"])
+                out = u.fetch(base + j)
+            return out
+
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(n_e2e):
+            e2e_step(1000 * (s + 1))
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e_bytes = sum(nb * host[i][1]["n_pw"] * nsp * 8 for i in seq) * n_e2e * world
+        e2e = {"value": e2e_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "sc_kpts_per_s": kps * n_e2e * world / dt, "steps": n_e2e,
+               "timer": "host monotonic clock between device synchronisations, max over ranks",
+               "bound": "PCIe host->device copy of the coefficient blocks"}
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        gbs, ckps, cores, done, phases = cpu_sample(sc, my_k, args.cpu_seconds, kps)
+        cpu = {"value": gbs, "unit": UNIT, "cores": cores, "kind": "port", "sc_kpts_per_s": ckps,
+               "sample": f"{done} full-size SC k-point(s) of the step's batch; C+OpenMP restatement of the "
+                         "reference loops (renormalise, select, weights, delta_N)",
+               "phase_seconds": {"renormalise": phases[0], "select+weights": phases[1], "delta_N": phases[2]}}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "c64 in, f32 |C|^2, f64 accumulate",
+            "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "kpts_per_step_per_gpu": kps, "n_bands": nb,
+                       "n_spinor": nsp, "n_pw": [it["n_pw"] for it in items],
+                       "n_fold": [it["nf"] for it in items], "nener": nener,
+                       "l2": "inputs larger than L2 (each SC-kpt block >> 126 MB; batch cycles through "
+                             f"{step_bytes / 1e9:.1f} GB)",
+                       "parallelism": f"SC k-points sharded over {world} GPU(s), NCCL all_gather of delta_N rows"
+                       if world > 1 else "1 GPU"},
+            "sc_kpts_per_s": kpts_per_s, "gpu_launches": int(gpu_launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    u.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from bandup_b200 import synth
+    sc = synth.make_scenario(args.workload)
+    if args.impl == "reference":
+        run_reference(args, sc, rank, world)
+        return
+    run_b200(args, sc, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

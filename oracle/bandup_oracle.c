@@ -569,11 +569,12 @@ static inline uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
-void bo_synth_fill(float complex *coeffs, int64_t row_elems, int n_bands,
-                   uint64_t seed, uint64_t ikpt) {
+void bo_synth_fill_rows(float complex *coeffs, int64_t row_elems, int band0,
+                        int n_rows, uint64_t seed, uint64_t ikpt) {
 #pragma omp parallel for schedule(static)
-  for (int ib = 0; ib < n_bands; ++ib) {
-    float complex *c = coeffs + (int64_t)ib * row_elems;
+  for (int r = 0; r < n_rows; ++r) {
+    const int ib = band0 + r;
+    float complex *c = coeffs + (int64_t)r * row_elems;
     uint64_t key = splitmix64(seed ^ (ikpt * 0xD1B54A32D192ED03ull) ^
                               ((uint64_t)ib * 0x8CB92BA72F3D8DD7ull));
     for (int64_t e = 0; e < row_elems; ++e) {
@@ -584,4 +585,9 @@ void bo_synth_fill(float complex *coeffs, int64_t row_elems, int n_bands,
       c[e] = re * env + im * env * I;
     }
   }
+}
+
+void bo_synth_fill(float complex *coeffs, int64_t row_elems, int n_bands,
+                   uint64_t seed, uint64_t ikpt) {
+  bo_synth_fill_rows(coeffs, row_elems, 0, n_bands, seed, ikpt);
 }

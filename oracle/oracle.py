@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
                                     _f64p]
         L.bo_synth_fill.restype = None
         L.bo_synth_fill.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64]
+        L.bo_synth_fill_rows.restype = None
+        L.bo_synth_fill_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
         L.bo_num_threads.restype = C.c_int
         L.bo_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -209,7 +211,9 @@ def unfold_kpt(coeffs, G_cart, sc_ener, b_pc, folding_G, energies, smearing=0.0,
     return w, dN, ns, times
 
 
-def synth_fill(row_elems, n_bands, seed, ikpt):
-    c = np.zeros((n_bands, row_elems), dtype=np.complex64)
-    lib().bo_synth_fill(c.ctypes.data, int(row_elems), int(n_bands), C.c_uint64(seed), C.c_uint64(ikpt))
+def synth_fill(row_elems, n_bands, seed, ikpt, band0=0, out=None):
+    """Rows band0..band0+n_bands-1 of the counter-based synthetic coefficient block."""
+    c = np.zeros((n_bands, row_elems), dtype=np.complex64) if out is None else out
+    lib().bo_synth_fill_rows(c.ctypes.data, int(row_elems), int(band0), int(n_bands), C.c_uint64(seed),
+                             C.c_uint64(ikpt))
     return c

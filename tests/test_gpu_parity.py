@@ -1,0 +1,306 @@
+"""GPU parity tests: every call goes through the C ABI (libbandup_gpu.so) and is compared with
+the CPU oracle on the same seeded inputs.  Tolerances (BASELINE.json north_star): selected
+plane-wave indices bit-exact; spectral weights and delta_N within 1e-6 relative (abs floor
+1e-12) of the exact_fp64-norm oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from bandup_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-6
+ABS_FLOOR = 1e-12
+
+SCEN = [("graphene4x4", 0.2), ("si333_vacancy", 0.25), ("mos2_8x8_spinor", 0.08), ("sige555", 0.05)]
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), ABS_FLOOR))) if a.size else 0.0
+
+
+def oracle_kpt(sc, coeffs, gf, ener, fG, grid, smearing=0.0):
+    from oracle import oracle as O
+    gc = gf @ sc.B_sc
+    w, dN, ns, _ = O.unfold_kpt(coeffs, gc, ener, sc.b_pc, fG, grid, smearing=smearing, norm_mode=1)
+    sels = [O.select_coeffs(gc, f, sc.b_pc)[0] for f in fG]
+    return w, dN, ns, sels
+
+
+def setup(u, sc, smearing=None):
+    M = u.verify_commens(sc.b_pc, sc.B_sc)
+    assert np.array_equal(M, sc.M)
+    return u.set_energy_grid(*sc.energy_window(), smearing_for_delta_function=smearing)
+
+
+@pytest.mark.parametrize("name,scale", SCEN)
+def test_unfold_matches_oracle(unfolder, name, scale):
+    from bandup_b200.unfold import PwWavefunction
+    from oracle import oracle as O
+    sc = synth.make_scenario(name, scale=scale)
+    grid = setup(unfolder, sc)
+    assert np.array_equal(grid, O.real_seq(*sc.energy_window()))
+    for iK in sorted(set([0, sc.n_sc_kpts // 2, sc.n_sc_kpts - 1])):
+        coeffs, gf, ener = synth.make_wavefunction(sc, iK)
+        fG = sc.folding_G(iK)
+        res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), folding_G=fG, ikpt=iK + 1)
+        w, dN, ns, sels = oracle_kpt(sc, coeffs, gf, ener, fG, grid)
+        assert np.array_equal(res.n_selected, ns)
+        for a, b in zip(res.selected_coeff_indices, sels):
+            assert np.array_equal(a, b)                     # bit-exact coset indices
+        assert rel_err(res.spectral_weight, w) <= REL_TOL
+        assert rel_err(res.dN, dN) <= REL_TOL
+        # band norms before renormalisation (io_routines_mod.f90:1321-1324, fp64 accumulate)
+        _, norms = O.renormalize(coeffs, 1)
+        assert rel_err(res.band_norms, norms) <= REL_TOL
+        assert not res.pckpt_cannot_be_parsed().any()
+
+
+def test_all_cosets_sum_to_one(unfolder):
+    """Sum over the det(M)=16 cosets of P is 1 for every band; n_selected adds up to n_pw."""
+    from bandup_b200.unfold import PwWavefunction
+    sc = synth.make_scenario("graphene4x4", scale=0.15)
+    setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 2)
+    g0 = np.array([[n1, n2, 0] for n1 in range(4) for n2 in range(4)], dtype=np.int32)
+    res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), g0=g0)
+    assert int(res.n_selected.sum()) == gf.shape[0]
+    assert np.allclose(res.spectral_weight.sum(axis=0), 1.0, rtol=0, atol=1e-9)
+    allsel = np.sort(np.concatenate(res.selected_coeff_indices))
+    assert np.array_equal(allsel, np.arange(1, gf.shape[0] + 1))
+
+
+def test_folds_sharing_a_coset_and_many_folds(unfolder):
+    """Two pc-kpts whose folding vectors differ by a pc reciprocal vector get identical rows;
+    40 folds exercise the shared-memory bins beyond a handful."""
+    from bandup_b200.unfold import PwWavefunction
+    sc = synth.make_scenario("si333_vacancy", scale=0.2)
+    grid = setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 0)
+    rng = np.random.default_rng(3)
+    g0 = rng.integers(-4, 5, size=(40, 3)).astype(np.int32)
+    # b_i = sum_j M_ji B_j: adding a column of M to g0 stays in the same coset
+    g0[7] = g0[2] + sc.M[:, 0] - 2 * sc.M[:, 2]
+    res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), g0=g0)
+    assert np.array_equal(res.spectral_weight[7], res.spectral_weight[2])
+    assert np.array_equal(res.dN[7], res.dN[2])
+    assert np.array_equal(res.selected_coeff_indices[7], res.selected_coeff_indices[2])
+    fG = g0.astype(np.float64) @ sc.B_sc
+    w, dN, ns, sels = oracle_kpt(sc, coeffs, gf, ener, fG, grid)
+    assert np.array_equal(res.n_selected, ns)
+    for a, b in zip(res.selected_coeff_indices, sels):
+        assert np.array_equal(a, b)
+    assert rel_err(res.spectral_weight, w) <= REL_TOL
+    assert rel_err(res.dN, dN) <= REL_TOL
+
+
+@pytest.mark.parametrize("n_spinor", [1, 2])
+@pytest.mark.parametrize("n_pw_trim", [0, 1])
+def test_vasp_record_layout_and_odd_rows(unfolder, n_spinor, n_pw_trim):
+    """Raw WAVECAR band records ([band][spinor][pw], stride nrecl) give the same numbers as the
+    Fortran in-memory layout; odd n_pw makes every other row 8- but not 16-byte aligned."""
+    from bandup_b200.unfold import LAYOUT_VASP_RECORD, PwWavefunction
+    sc = synth.make_scenario("mos2_8x8_spinor" if n_spinor == 2 else "graphene4x4", scale=0.07)
+    grid = setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 1)
+    if (gf.shape[0] - n_pw_trim) % 2 == 0:
+        n_pw_trim += 1                                      # force an odd plane-wave count
+    if n_pw_trim:
+        coeffs, gf = np.ascontiguousarray(coeffs[:, :-n_pw_trim]), np.ascontiguousarray(gf[:-n_pw_trim])
+    nb, n_pw, _ = coeffs.shape
+    assert n_pw % 2 == 1
+    fG = sc.folding_G(1)
+    ref = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), folding_G=fG)
+    w, dN, ns, sels = oracle_kpt(sc, coeffs, gf, ener, fG, grid)
+    assert rel_err(ref.spectral_weight, w) <= REL_TOL and rel_err(ref.dN, dN) <= REL_TOL
+    for nrecl in (n_pw * n_spinor * 8, n_pw * n_spinor * 8 + 8 * 5):
+        rec = np.zeros((nb, nrecl // 8), dtype=np.complex64)
+        for isp in range(n_spinor):                         # spinor-up block then spinor-down block
+            rec[:, isp * n_pw:(isp + 1) * n_pw] = coeffs[:, :, isp]
+        wf = PwWavefunction(rec, gf, ener, n_pw=n_pw, n_bands=nb, n_spinor=n_spinor,
+                            layout=LAYOUT_VASP_RECORD, band_stride_bytes=nrecl)
+        res = unfolder.perform_unfolding(wf, folding_G=fG)
+        assert np.array_equal(res.n_selected, ns)
+        assert rel_err(res.spectral_weight, w) <= REL_TOL
+        assert rel_err(res.dN, dN) <= REL_TOL
+        assert np.allclose(res.spectral_weight, ref.spectral_weight, rtol=1e-12, atol=1e-15)
+
+
+def test_gaussian_smearing(unfolder):
+    from bandup_b200.unfold import PwWavefunction
+    sc = synth.make_scenario("graphene4x4", scale=0.1)
+    grid = setup(unfolder, sc, smearing=0.04)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 0)
+    fG = sc.folding_G(0)
+    res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), folding_G=fG)
+    w, dN, ns, _ = oracle_kpt(sc, coeffs, gf, ener, fG, grid, smearing=0.04)
+    assert rel_err(res.spectral_weight, w) <= REL_TOL
+    assert rel_err(res.dN, dN) <= REL_TOL
+
+
+def test_box_lambda_bin_edges(unfolder):
+    """Energies exactly on bin edges take lambda = 1/2 in both neighbouring bins."""
+    from bandup_b200.unfold import PwWavefunction
+    sc = synth.make_scenario("graphene4x4", scale=0.08)
+    grid = setup(unfolder, sc)
+    coeffs, gf, _ = synth.make_wavefunction(sc, 0)
+    nb = coeffs.shape[0]
+    de = grid[1] - grid[0]
+    ener = np.array([grid[3 + 2 * i] + 0.5 * de for i in range(nb)])
+    ener[0] = grid[0] - 0.5 * de          # lower edge of the first bin
+    ener[1] = grid[-1] + 0.5 * de         # upper edge of the last bin
+    ener[2] = grid[10]                    # bin centre
+    fG = sc.folding_G(0)
+    res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), folding_G=fG)
+    w, dN, _, _ = oracle_kpt(sc, coeffs, gf, ener, fG, grid)
+    assert rel_err(res.dN, dN) <= REL_TOL
+    assert np.count_nonzero(res.dN[0]) == np.count_nonzero(dN[0])
+
+
+def test_empty_selection_is_reported(unfolder):
+    """A coset with no plane wave in the cutoff sphere: n_selected == 0, the reference's
+    'pckpt cannot be parsed' branch (main_BandUP.f90:161-172); weights and delta_N are zero."""
+    from bandup_b200.unfold import PwWavefunction
+    sc = synth.make_scenario("si333_vacancy", scale=0.2)
+    setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 0)
+    keep = synth.coset_labels(gf, sc.M) != synth.coset_labels(gf, sc.M)[0]   # drop the G=0 coset
+    coeffs, gf = np.ascontiguousarray(coeffs[:, keep]), np.ascontiguousarray(gf[keep])
+    g0 = np.array([[0, 0, 0], [1, 0, 0]], dtype=np.int32)
+    res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), g0=g0)
+    assert res.n_selected[0] == 0 and res.n_selected[1] > 0
+    assert res.pckpt_cannot_be_parsed().tolist() == [True, False]
+    assert not res.spectral_weight[0].any() and not res.dN[0].any()
+    assert len(res.selected_coeff_indices[0]) == 0
+
+
+def test_zero_norm_band_is_left_unscaled(unfolder):
+    """io_routines_mod.f90:1325: a band with s <= epsilon is not rescaled."""
+    from bandup_b200.unfold import PwWavefunction
+    sc = synth.make_scenario("graphene4x4", scale=0.08)
+    grid = setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 0)
+    coeffs[1] = 0.0
+    coeffs[2] *= np.float32(1e-10)        # s ~ 1e-20 * O(n_pw) < epsilon
+    fG = sc.folding_G(0)
+    res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), folding_G=fG)
+    w, dN, _, _ = oracle_kpt(sc, coeffs, gf, ener, fG, grid)
+    assert not res.spectral_weight[:, 1].any()
+    assert res.band_norms[2] <= 2.3e-16
+    assert rel_err(res.spectral_weight, w) <= REL_TOL
+    assert rel_err(res.dN, dN) <= REL_TOL
+
+
+def test_pipeline_double_buffering(unfolder):
+    """Two SC-kpts in flight, fetched out of order; a third submit is refused until a fetch."""
+    from bandup_b200.unfold import BandupGpuError, PwWavefunction
+    sc = synth.make_scenario("graphene4x4", scale=0.1)
+    grid = setup(unfolder, sc)
+    data = [synth.make_wavefunction(sc, iK) for iK in range(3)]
+    wfs = [PwWavefunction(*d) for d in data]
+    unfolder.submit(10, wfs[0], folding_G=sc.folding_G(0))
+    unfolder.submit(11, wfs[1], folding_G=sc.folding_G(1))
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.submit(12, wfs[2], folding_G=sc.folding_G(2))
+    assert ei.value.code == 1
+    unfolder._inflight.pop(12, None)
+    r1 = unfolder.fetch(11)
+    unfolder.submit(12, wfs[2], folding_G=sc.folding_G(2))
+    r0 = unfolder.fetch(10)
+    r2 = unfolder.fetch(12)
+    for iK, r in enumerate([r0, r1, r2]):
+        w, dN, ns, _ = oracle_kpt(sc, *data[iK], sc.folding_G(iK), grid)
+        assert np.array_equal(r.n_selected, ns)
+        assert rel_err(r.spectral_weight, w) <= REL_TOL and rel_err(r.dN, dN) <= REL_TOL
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.fetch_raw(99, 1, 1)
+    assert ei.value.code == 8
+
+
+def test_error_codes(unfolder):
+    from bandup_b200.unfold import BandupGpuError, PwWavefunction
+    sc = synth.make_scenario("graphene4x4", scale=0.08)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 0)
+    wf = PwWavefunction(coeffs, gf, ener)
+    with pytest.raises(BandupGpuError) as ei:               # set_cells / set_grid not called
+        unfolder.submit(1, wf, g0=np.zeros((1, 3), np.int32))
+    assert ei.value.code == 7
+    unfolder._inflight.clear()
+    a = synth.hex_cell(2.467, 15.0)
+    with pytest.raises(BandupGpuError) as ei:               # verify_commens' stop
+        unfolder.verify_commens(synth.rec_latt(a), synth.rec_latt(np.diag([4.0, 4.1, 1.0]) @ a))
+    assert ei.value.code == 3
+    setup(unfolder, sc)
+    with pytest.raises(BandupGpuError) as ei:               # folding vector off the SC lattice
+        unfolder.folding_g0(sc.folding_G(0) + np.array([3e-3, 0.0, 0.0]))
+    assert ei.value.code == 4
+    g0, res = unfolder.folding_g0(sc.folding_G(0) + np.array([4e-5, 0.0, 0.0]))
+    assert res < 1e-3 and np.array_equal(g0, unfolder.folding_g0(sc.folding_G(0))[0])
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.submit(1, wf, g0=np.zeros((97, 3), np.int32))
+    assert ei.value.code == 5
+    unfolder._inflight.clear()
+    lib = unfolder._lib
+    assert lib.bandup_gpu_finalize(12345) == 6
+    h = C.c_int(-1)
+    assert lib.bandup_gpu_init(999, C.byref(h)) == 9 and h.value == -1
+
+
+def test_device_resident_full_size_sige555(unfolder):
+    """BASELINE config 5 at full size (3000 bands x ~100k plane waves, 2.4 GB): coefficients
+    are generated in HBM by the counter-based hash, all bands go through K1-K3, and sampled
+    bands are compared with the oracle fed with the same hash on the host.  Size-independent
+    properties: sum over folds of P <= 1, delta_N sums to the in-window weight."""
+    import torch
+    from bandup_b200.unfold import LAYOUT_FORTRAN_INMEM
+    from oracle import oracle as O
+    sc = synth.make_scenario("sige555")
+    grid = setup(unfolder, sc)
+    iK = 3
+    gf = sc.gvecs(iK)
+    n_pw, nb = gf.shape[0], sc.n_bands
+    assert 90_000 < n_pw < 115_000 and nb == 3000
+    fG = sc.folding_G(iK)
+    g0, _ = unfolder.folding_g0(fG)
+    g0 = np.concatenate([g0, g0 + np.array([[1, 0, 0]], np.int32), g0 + np.array([[0, 2, 1]], np.int32)])
+    nf = g0.shape[0]
+    rng = np.random.default_rng(11)
+    ener = np.sort(rng.uniform(-21.0, 6.0, nb))
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    d_c = torch.empty((nb, n_pw, 2), dtype=torch.float32, device=dev)
+    unfolder.synth_fill_device(stream, d_c.data_ptr(), n_pw, nb, n_pw * 8, 20261024, iK)
+    d_g = torch.from_numpy(gf).to(dev)
+    d_e = torch.from_numpy(ener).to(dev)
+    d_w = torch.empty((nf, nb), dtype=torch.float64, device=dev)
+    d_dn = torch.empty((nf, len(grid)), dtype=torch.float64, device=dev)
+    d_ns = torch.empty(nf, dtype=torch.int32, device=dev)
+    d_norm = torch.empty(nb, dtype=torch.float64, device=dev)
+    ws = unfolder.workspace_bytes(1, n_pw, nb, nf)
+    d_ws = torch.empty(ws, dtype=torch.uint8, device=dev)
+    unfolder.unfold_device(stream, 1, n_pw, nb, LAYOUT_FORTRAN_INMEM, n_pw * 8, d_c.data_ptr(),
+                           d_g.data_ptr(), d_e.data_ptr(), g0, d_w.data_ptr(), d_dn.data_ptr(),
+                           d_ns.data_ptr(), d_ws.data_ptr(), ws, d_norms=d_norm.data_ptr())
+    torch.cuda.synchronize()
+    w, dN, ns, norms = d_w.cpu().numpy(), d_dn.cpu().numpy(), d_ns.cpu().numpy(), d_norm.cpu().numpy()
+    gc = gf @ sc.B_sc
+    fG_all = g0.astype(np.float64) @ sc.B_sc
+    sample = [0, 1, 777, 1500, 2998, 2999]
+    for b in sample:
+        row = O.synth_fill(n_pw, 1, 20261024, iK, band0=b).reshape(1, n_pw, 1)
+        # generator check: the device block equals the host hash bit for bit
+        host = torch.view_as_complex(d_c[b]).cpu().numpy()
+        assert np.array_equal(host, row[0, :, 0])
+        wo, _, nso, _ = O.unfold_kpt(row, gc, ener[b:b + 1], sc.b_pc, fG_all, grid, norm_mode=1)
+        assert np.array_equal(ns, nso)
+        assert rel_err(w[:, b], wo[:, 0]) <= REL_TOL
+        _, n_o = O.renormalize(row, 1)
+        assert rel_err(norms[b:b + 1], n_o) <= REL_TOL
+    assert np.all(w.sum(axis=0) <= 1.0 + 1e-9) and np.all(w >= 0.0)
+    de = grid[1] - grid[0]
+    inside = (ener > grid[0] - 0.5 * de) & (ener < grid[-1] + 0.5 * de)
+    assert np.allclose(dN.sum(axis=1), w[:, inside].sum(axis=1), rtol=1e-12)
+    dN_o = O.delta_N(grid, ener, w[0])
+    assert rel_err(dN[0], dN_o) <= REL_TOL
