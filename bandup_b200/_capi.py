@@ -73,6 +73,14 @@ def load() -> C.CDLL:
                                             C.c_void_p, c_i32p, c_f64p, C.c_int, c_i32p]),
         "bandup_gpu_fetch_kpt": (C.c_int, [C.c_int, C.c_int, c_f64p, c_f64p, c_i32p, c_f64p, c_i32p, C.c_int64]),
         "bandup_gpu_pipeline_depth": (C.c_int, [C.c_int]),
+        "bandup_gpu_rho_count": (C.c_int, [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int64),
+                                           C.POINTER(C.c_int64)]),
+        "bandup_gpu_fetch_rho": (C.c_int, [C.c_int, C.c_int, C.c_int64, c_i32p, c_i32p, c_i32p, c_i32p,
+                                           C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "bandup_gpu_orb_contrib_matrix": (C.c_int, [C.c_int, C.c_int, C.c_int, c_f64p, c_f64p, c_u8p, c_f64p,
+                                                    C.c_double, C.c_double, c_f64p]),
+        "bandup_gpu_set_operator": (C.c_int, [C.c_int, C.c_int, c_f64p]),
+        "bandup_gpu_unfold_operator": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, c_f64p]),
         "bandup_gpu_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "bandup_gpu_unfold_device": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_i32p,
@@ -82,7 +90,7 @@ def load() -> C.CDLL:
         "bandup_gpu_kernel_time": (C.c_int, [C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int64)]),
         "bandup_gpu_reset_kernel_times": (C.c_int, [C.c_int]),
         "bandup_gpu_launch_count": (C.c_int64, [C.c_int]),
-        "bandup_gpu_set_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+        "bandup_gpu_set_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
         "bandup_gpu_synth_fill_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                                    C.c_int64, C.c_uint64, C.c_uint64]),
     }

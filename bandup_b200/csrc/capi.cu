@@ -3,6 +3,7 @@
 //
 // There is deliberately NO CPU fallback anywhere in this file: without a usable
 // sm_100 device bandup_gpu_init fails with BANDUP_GPU_ERR_NO_DEVICE.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -62,14 +63,30 @@ struct PinBuf {
   }
 };
 
+struct RhoEntry {  // one stored element of an unfolding-density operator (reference order)
+  int32_t fold, iener, m1, m2;
+  float re, im;
+};
+
 struct Flight {  // one SC k-point in flight
-  bool busy = false;
+  bool busy = false;      // submitted, not fetched yet
+  bool resident = false;  // device buffers still hold this k-point (for the rho calls)
   int ikpt = -1;
-  int n_spinor = 0, n_pw = 0, n_bands = 0, n_fold = 0, n_unique = 0;
+  int n_spinor = 0, n_pw = 0, n_bands = 0, n_fold = 0, n_unique = 0, layout = 0;
+  long long stride_bytes = 0;
   int unique_of[kMaxFolds];
   DevBuf coeffs, gfrac, energies, weights, dN, nsel, norms, slot, selected, workspace;
   PinBuf h_weights, h_dN, h_nsel, h_norms;
   cudaEvent_t uploaded = nullptr, done = nullptr;
+  // per-unique-fold results (alias weights/dN/nsel unless two pc-kpts share a coset)
+  const double* d_dn_unique = nullptr;
+  const int32_t* d_ns_unique = nullptr;
+  // projected variant
+  bool rho_ready = false;
+  DevBuf sel_off, csel, pair_count, pair_off, pairs, overflow, trace_out;
+  std::vector<long long> h_pair_off;
+  std::vector<RhoEntry> rho_entries;
+  long long rho_energies = 0;
 };
 
 struct Ctx {
@@ -82,11 +99,13 @@ struct Ctx {
   CosetParams coset{};
   std::vector<double> grid;
   DevBuf d_grid;
+  DevBuf d_operator;  // current general operator O [n_bands][n_bands] complex128
+  int operator_bands = 0;
   int nener = 0;
   double sigma = kEpsDp;
   Flight flights[kDepth];
   int next_flight = 0;
-  int chunk_vecs = 0, ctas_per_sm = 0;
+  int chunk_vecs = 0, ctas_per_sm = 0, n_stages = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> event_pool;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[BANDUP_GPU_K_COUNT];
@@ -267,15 +286,17 @@ int plan_folds(Ctx* c, int n_fold, const int32_t* g0, FoldPlan* plan) {
 size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct WorkspaceLayout {
-  size_t slot_off, partials_off, tmp_w_off, tmp_dn_off, tmp_ns_off, total;
+  size_t slot_off, slot_shift_off, partials_off, tmp_w_off, tmp_dn_off, tmp_ns_off, total;
 };
 
 WorkspaceLayout workspace_layout(const Ctx* c, int n_spinor, int n_pw, int n_bands, int n_fold) {
   WorkspaceLayout w;
-  const int cv = c->chunk_vecs > 0 ? c->chunk_vecs : weights_default_chunk_vecs();
+  const int cv = weights_pick_chunk_vecs(c->chunk_vecs, (long long)n_pw * n_spinor, n_bands, c->sm_count);
   const int n_chunks = weights_num_chunks((long long)n_pw * n_spinor, cv);
   size_t off = 0;
   w.slot_off = off;
+  off += align256((size_t)(n_pw > 0 ? n_pw : 1));
+  w.slot_shift_off = off;
   off += align256((size_t)(n_pw > 0 ? n_pw : 1));
   w.partials_off = off;
   off += align256(weights_partials_bytes(n_bands, n_chunks, n_fold));
@@ -294,24 +315,29 @@ int run_kpt(Ctx* c, cudaStream_t s, int n_spinor, int n_pw, int n_bands, int lay
             long long stride_bytes, const void* d_coeffs, const int32_t* d_gfrac,
             const double* d_energies, int n_fold, const FoldPlan& plan, double* d_weights,
             double* d_dN, int32_t* d_nsel, double* d_norms, uint8_t* d_slot_out, void* d_ws,
-            size_t ws_bytes) {
+            size_t ws_bytes, const double** dn_unique = nullptr,
+            const int32_t** ns_unique = nullptr) {
   const WorkspaceLayout wl = workspace_layout(c, n_spinor, n_pw, n_bands, n_fold);
   if (ws_bytes < wl.total)
     return fail(c, BANDUP_GPU_ERR_CAPACITY,
                 "workspace too small: need " + std::to_string(wl.total) + " bytes");
   char* ws = static_cast<char*>(d_ws);
-  uint8_t* d_slot = d_slot_out ? d_slot_out : reinterpret_cast<uint8_t*>(ws + wl.slot_off);
+  uint8_t* d_slot = reinterpret_cast<uint8_t*>(ws + wl.slot_off);
+  uint8_t* d_slot_shift = reinterpret_cast<uint8_t*>(ws + wl.slot_shift_off);
   double* d_partials = reinterpret_cast<double*>(ws + wl.partials_off);
   const bool dup = plan.n_unique != n_fold;
   double* w_out = dup ? reinterpret_cast<double*>(ws + wl.tmp_w_off) : d_weights;
   double* dn_out = dup ? reinterpret_cast<double*>(ws + wl.tmp_dn_off) : d_dN;
   int32_t* ns_out = dup ? reinterpret_cast<int32_t*>(ws + wl.tmp_ns_off) : d_nsel;
   const int nu = plan.n_unique;
+  if (dn_unique) *dn_unique = dn_out;
+  if (ns_unique) *ns_unique = ns_out;
 
   {
     KernelScope k(c, BANDUP_GPU_K_COSET, s);
-    launch_coset_classify(d_gfrac, n_pw, plan.cp, d_slot, ns_out, s);
+    launch_coset_classify(d_gfrac, n_pw, plan.cp, d_slot, d_slot_shift, ns_out, s);
   }
+  if (d_slot_out) CU(cudaMemcpyAsync(d_slot_out, d_slot, (size_t)n_pw, cudaMemcpyDeviceToDevice, s));
   WeightsGeom g;
   g.coeffs = static_cast<const char*>(d_coeffs);
   g.stride_bytes = stride_bytes;
@@ -321,13 +347,15 @@ int run_kpt(Ctx* c, cudaStream_t s, int n_spinor, int n_pw, int n_bands, int lay
   g.n_spinor = n_spinor;
   g.layout = layout;
   g.slot = d_slot;
+  g.slot_shift = d_slot_shift;
   g.n_fold = nu;
-  g.chunk_vecs = c->chunk_vecs > 0 ? c->chunk_vecs : weights_default_chunk_vecs();
+  g.n_stages = 0;
+  g.chunk_vecs = weights_pick_chunk_vecs(c->chunk_vecs, g.row_elems, n_bands, c->sm_count);
   g.n_chunks = weights_num_chunks(g.row_elems, g.chunk_vecs);
   g.partials = d_partials;
   {
     KernelScope k(c, BANDUP_GPU_K_WEIGHTS, s);
-    launch_weights_reduce(g, c->ctas_per_sm, c->sm_count, s);
+    launch_weights_reduce(g, c->ctas_per_sm, c->n_stages, c->sm_count, s);
   }
   {
     KernelScope k(c, BANDUP_GPU_K_FINALIZE, s);
@@ -428,11 +456,14 @@ int bandup_gpu_finalize(int handle) {
     f.coeffs.release(); f.gfrac.release(); f.energies.release(); f.weights.release();
     f.dN.release(); f.nsel.release(); f.norms.release(); f.slot.release();
     f.selected.release(); f.workspace.release();
+    f.sel_off.release(); f.csel.release(); f.pair_count.release(); f.pair_off.release();
+    f.pairs.release(); f.overflow.release(); f.trace_out.release();
     f.h_weights.release(); f.h_dN.release(); f.h_nsel.release(); f.h_norms.release();
     if (f.uploaded) cudaEventDestroy(f.uploaded);
     if (f.done) cudaEventDestroy(f.done);
   }
   c->d_grid.release();
+  c->d_operator.release();
   if (c->copy) cudaStreamDestroy(c->copy);
   if (c->compute) cudaStreamDestroy(c->compute);
   delete c;
@@ -606,10 +637,16 @@ int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_ba
     if (f.busy && f.ikpt == ikpt)
       return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "ikpt already in flight; fetch it first");
   cudaSetDevice(c->device);
-  Flight& fl = c->flights[c->next_flight];
-  if (fl.busy)
+  // any idle flight will do (k-points may be fetched in any order); prefer round-robin so
+  // consecutive k-points use different device buffers and their upload/compute overlap
+  int slot = -1;
+  for (int i = 0; i < kDepth && slot < 0; ++i)
+    if (!c->flights[(c->next_flight + i) % kDepth].busy) slot = (c->next_flight + i) % kDepth;
+  if (slot < 0)
     return fail(c, BANDUP_GPU_ERR_INVALID_ARG,
-                "pipeline full: fetch k-point " + std::to_string(fl.ikpt) + " before submitting more");
+                "pipeline full: fetch k-point " + std::to_string(c->flights[c->next_flight].ikpt) +
+                    " before submitting more");
+  Flight& fl = c->flights[slot];
   // The buffers of this flight may still be read by its previous kernels only if
   // the caller skipped fetch; fetch synchronises on `done`, so they are idle here.
   const size_t coeff_bytes = (size_t)band_stride_bytes * (size_t)(n_bands - 1) +
@@ -640,7 +677,8 @@ int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_ba
                static_cast<const int32_t*>(fl.gfrac.p), static_cast<const double*>(fl.energies.p),
                n_fold, plan, static_cast<double*>(fl.weights.p), static_cast<double*>(fl.dN.p),
                static_cast<int32_t*>(fl.nsel.p), static_cast<double*>(fl.norms.p),
-               static_cast<uint8_t*>(fl.slot.p), fl.workspace.p, fl.workspace.cap);
+               static_cast<uint8_t*>(fl.slot.p), fl.workspace.p, fl.workspace.cap, &fl.d_dn_unique,
+               &fl.d_ns_unique);
   if (rc) return rc;
   CU(cudaMemcpyAsync(fl.h_weights.p, fl.weights.p, sizeof(double) * (size_t)n_fold * n_bands, cudaMemcpyDeviceToHost, c->compute));
   CU(cudaMemcpyAsync(fl.h_dN.p, fl.dN.p, sizeof(double) * (size_t)n_fold * c->nener, cudaMemcpyDeviceToHost, c->compute));
@@ -648,6 +686,12 @@ int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_ba
   CU(cudaMemcpyAsync(fl.h_norms.p, fl.norms.p, sizeof(double) * (size_t)n_bands, cudaMemcpyDeviceToHost, c->compute));
   CU(cudaEventRecord(fl.done, c->compute));
   fl.busy = true;
+  fl.resident = true;
+  fl.rho_ready = false;
+  fl.layout = layout;
+  fl.stride_bytes = band_stride_bytes;
+  for (auto& other : c->flights)  // an older resident copy of the same ikpt is superseded
+    if (&other != &fl && !other.busy && other.ikpt == ikpt) other.resident = false;
   fl.ikpt = ikpt;
   fl.n_spinor = n_spinor;
   fl.n_pw = n_pw;
@@ -655,7 +699,7 @@ int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_ba
   fl.n_fold = n_fold;
   fl.n_unique = plan.n_unique;
   std::memcpy(fl.unique_of, plan.unique_of, sizeof(int) * (size_t)n_fold);
-  c->next_flight = (c->next_flight + 1) % kDepth;
+  c->next_flight = (slot + 1) % kDepth;
   return BANDUP_GPU_OK;
 }
 
@@ -708,9 +752,246 @@ int bandup_gpu_fetch_kpt(int handle, int ikpt, double* weights, double* dN, int3
       }
     }
   }
-  fl->busy = false;
-  fl->ikpt = -1;
+  fl->busy = false;  // the slot may be reused; until then the k-point stays resident
   return rc;
+}
+
+namespace {
+
+Flight* resident_flight(Ctx* c, int ikpt) {
+  for (auto& f : c->flights)
+    if (!f.busy && f.resident && f.ikpt == ikpt) return &f;
+  return nullptr;
+}
+
+int need_resident(Ctx* c, int ikpt, Flight** out) {
+  for (auto& f : c->flights)
+    if (f.busy && f.ikpt == ikpt)
+      return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "call bandup_gpu_fetch_kpt for this k-point first");
+  *out = resident_flight(c, ikpt);
+  if (!*out)
+    return fail(c, BANDUP_GPU_ERR_UNKNOWN_KPT,
+                "k-point " + std::to_string(ikpt) + " is no longer resident on the device");
+  return BANDUP_GPU_OK;
+}
+
+}  // namespace
+
+int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t* n_energies,
+                         int64_t* n_entries) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (!(min_dN >= kEpsDp))
+    return fail(c, BANDUP_GPU_ERR_DELTA_N_ZERO,
+                "ERROR (calc_rho): delta_N = 0. (min_dN must be >= epsilon(1.0_dp); the reference uses 1e-3)");
+  Flight* fl = nullptr;
+  int rc = need_resident(c, ikpt, &fl);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  cudaStream_t s = c->compute;
+  const int nu = fl->n_unique, nener = c->nener, nb = fl->n_bands;
+  const int cells = nu * nener;
+  const int cap = rho_active_cap(nb);
+  fl->rho_ready = false;
+  CU(fl->pair_count.reserve(sizeof(int) * (size_t)cells));
+  CU(fl->pair_off.reserve(sizeof(long long) * ((size_t)cells + 1)));
+  CU(fl->overflow.reserve(sizeof(int)));
+  CU(fl->sel_off.reserve(sizeof(long long) * ((size_t)nu + 1)));
+  CU(cudaMemsetAsync(fl->overflow.p, 0, sizeof(int), s));
+  const double* d_grid = static_cast<const double*>(c->d_grid.p);
+  const double* d_ener = static_cast<const double*>(fl->energies.p);
+  {
+    KernelScope k(c, BANDUP_GPU_K_RHO, s);
+    launch_rho_plan(d_grid, nener, c->sigma, d_ener, nb, nu, fl->d_dn_unique, min_dN, cap,
+                    static_cast<int*>(fl->pair_count.p), static_cast<long long*>(fl->pair_off.p),
+                    static_cast<int*>(fl->overflow.p), s);
+    c->launches++;  // plan + scan
+  }
+  // ordered selected lists of every unique fold + their offsets
+  std::vector<int32_t> h_ns((size_t)nu);
+  CU(cudaMemcpyAsync(h_ns.data(), fl->d_ns_unique, sizeof(int32_t) * (size_t)nu, cudaMemcpyDeviceToHost, s));
+  fl->h_pair_off.assign((size_t)cells + 1, 0);
+  CU(cudaMemcpyAsync(fl->h_pair_off.data(), fl->pair_off.p, sizeof(long long) * ((size_t)cells + 1),
+                     cudaMemcpyDeviceToHost, s));
+  int h_overflow = 0;
+  CU(cudaMemcpyAsync(&h_overflow, fl->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (h_overflow)
+    return fail(c, BANDUP_GPU_ERR_CAPACITY,
+                "more than " + std::to_string(cap) + " bands couple at one energy (smearing too wide)");
+  long long total_sel = 0;
+  for (int u = 0; u < nu; ++u) total_sel += h_ns[u];
+  const long long total_pairs = fl->h_pair_off[(size_t)cells];
+  fl->rho_entries.clear();
+  fl->rho_energies = 0;
+  for (int cell = 0; cell < cells; ++cell)
+    if (fl->h_pair_off[cell + 1] > fl->h_pair_off[cell]) fl->rho_energies++;
+  std::vector<RhoPair> h_pairs((size_t)total_pairs);
+  if (total_pairs > 0) {
+    CU(fl->selected.reserve(sizeof(int32_t) * (size_t)(total_sel > 0 ? total_sel : 1)));
+    CU(fl->csel.reserve(sizeof(float2) * (size_t)(total_sel > 0 ? total_sel : 1) * (size_t)nb * (size_t)fl->n_spinor));
+    CU(fl->pairs.reserve(sizeof(RhoPair) * (size_t)total_pairs));
+    {
+      KernelScope k(c, BANDUP_GPU_K_RHO, s);
+      launch_scan(fl->d_ns_unique, nu, static_cast<long long*>(fl->sel_off.p), s);
+    }
+    {
+      KernelScope k(c, BANDUP_GPU_K_COSET, s);
+      launch_selected_lists(static_cast<const uint8_t*>(fl->slot.p), fl->n_pw, nu, fl->d_ns_unique,
+                            static_cast<int32_t*>(fl->selected.p), s);
+    }
+    {
+      KernelScope k(c, BANDUP_GPU_K_RHO, s);
+      launch_rho_gather(fl->coeffs.p, fl->stride_bytes, fl->n_pw, fl->n_spinor, nb, fl->layout, nu,
+                        static_cast<const int32_t*>(fl->selected.p),
+                        static_cast<const long long*>(fl->sel_off.p),
+                        static_cast<const double*>(fl->norms.p), fl->csel.p, s);
+    }
+    {
+      KernelScope k(c, BANDUP_GPU_K_RHO, s);
+      launch_rho_pairs(d_grid, nener, c->sigma, d_ener, nb, nu, fl->d_dn_unique, cap, fl->n_spinor,
+                       static_cast<const long long*>(fl->sel_off.p), fl->csel.p,
+                       static_cast<const int*>(fl->pair_count.p),
+                       static_cast<const long long*>(fl->pair_off.p), static_cast<RhoPair*>(fl->pairs.p), s);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_pairs.data(), fl->pairs.p, sizeof(RhoPair) * (size_t)total_pairs,
+                       cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  // Expand to the list perform_unfolding appends (:1416-1425): full matrix, |rho| >= 1e-5
+  // (single-precision abs), m1 outer / m2 inner, for every pc-kpt (folds that share a coset
+  // share the operator), energies ascending.
+  for (int f = 0; f < fl->n_fold; ++f) {
+    const int u = fl->unique_of[f];
+    for (int ie = 0; ie < nener; ++ie) {
+      const long long p0 = fl->h_pair_off[(size_t)u * nener + ie], p1 = fl->h_pair_off[(size_t)u * nener + ie + 1];
+      if (p1 == p0) continue;
+      const size_t first = fl->rho_entries.size();
+      for (long long p = p0; p < p1; ++p) {
+        const RhoPair& r = h_pairs[(size_t)p];
+        if (hypotf(r.re, r.im) < 1e-5f) continue;
+        fl->rho_entries.push_back({f, ie + 1, r.m1 + 1, r.m2 + 1, r.re, r.im});
+        if (r.m1 != r.m2) fl->rho_entries.push_back({f, ie + 1, r.m2 + 1, r.m1 + 1, r.re, -r.im});
+      }
+      std::sort(fl->rho_entries.begin() + (long)first, fl->rho_entries.end(),
+                [](const RhoEntry& a, const RhoEntry& b) { return a.m1 != b.m1 ? a.m1 < b.m1 : a.m2 < b.m2; });
+    }
+  }
+  fl->rho_ready = true;
+  if (n_energies) {
+    long long ne = 0;
+    for (int f = 0; f < fl->n_fold; ++f) {
+      const int u = fl->unique_of[f];
+      for (int ie = 0; ie < nener; ++ie)
+        if (fl->h_pair_off[(size_t)u * nener + ie + 1] > fl->h_pair_off[(size_t)u * nener + ie]) ++ne;
+    }
+    *n_energies = ne;
+  }
+  if (n_entries) *n_entries = (int64_t)fl->rho_entries.size();
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_fetch_rho(int handle, int ikpt, int64_t capacity, int32_t* fold, int32_t* iener,
+                         int32_t* m1, int32_t* m2, float* rho_re, float* rho_im) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  Flight* fl = nullptr;
+  int rc = need_resident(c, ikpt, &fl);
+  if (rc) return rc;
+  if (!fl->rho_ready) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_rho_count first");
+  const size_t n = fl->rho_entries.size();
+  if ((int64_t)n > capacity)
+    return fail(c, BANDUP_GPU_ERR_CAPACITY, "capacity too small: need " + std::to_string(n));
+  for (size_t i = 0; i < n; ++i) {
+    const RhoEntry& e = fl->rho_entries[i];
+    if (fold) fold[i] = e.fold;
+    if (iener) iener[i] = e.iener;
+    if (m1) m1[i] = e.m1;
+    if (m2) m2[i] = e.m2;
+    if (rho_re) rho_re[i] = e.re;
+    if (rho_im) rho_im[i] = e.im;
+  }
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_set_operator(int handle, int n_bands, const double* O) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (n_bands < 1 || !O) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad operator");
+  cudaSetDevice(c->device);
+  const size_t bytes = sizeof(double) * 2 * (size_t)n_bands * (size_t)n_bands;
+  CU(cudaStreamSynchronize(c->compute));
+  CU(c->d_operator.reserve(bytes));
+  CU(cudaMemcpy(c->d_operator.p, O, bytes, cudaMemcpyHostToDevice));
+  c->operator_bands = n_bands;
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_orb_contrib_matrix(int handle, int n_bands, int n_ao, const double* dual,
+                                  const double* proj, const uint8_t* ao_mask,
+                                  const double* band_energies, double max_band_dE, double min_abs,
+                                  double* O_out) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (n_bands < 1 || n_ao < 1 || !dual || !proj || !ao_mask || !band_energies)
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad orbital-projection arguments");
+  cudaSetDevice(c->device);
+  cudaStream_t s = c->compute;
+  const size_t mat = sizeof(double) * 2 * (size_t)n_bands * (size_t)n_ao;
+  const size_t obytes = sizeof(double) * 2 * (size_t)n_bands * (size_t)n_bands;
+  DevBuf d_dual, d_proj, d_mask, d_ener;
+  cudaError_t e = cudaSuccess;
+  if ((e = d_dual.reserve(mat)) == cudaSuccess && (e = d_proj.reserve(mat)) == cudaSuccess &&
+      (e = d_mask.reserve((size_t)n_ao)) == cudaSuccess &&
+      (e = d_ener.reserve(sizeof(double) * (size_t)n_bands)) == cudaSuccess &&
+      (e = cudaStreamSynchronize(s)) == cudaSuccess && (e = c->d_operator.reserve(obytes)) == cudaSuccess) {
+    cudaMemcpyAsync(d_dual.p, dual, mat, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_proj.p, proj, mat, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_mask.p, ao_mask, (size_t)n_ao, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_ener.p, band_energies, sizeof(double) * (size_t)n_bands, cudaMemcpyHostToDevice, s);
+    {
+      KernelScope k(c, BANDUP_GPU_K_RHO, s);
+      launch_orb_contrib(n_bands, n_ao, d_dual.p, d_proj.p, static_cast<const uint8_t*>(d_mask.p),
+                         static_cast<const double*>(d_ener.p), max_band_dE, min_abs, c->d_operator.p, s);
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess && O_out) e = cudaMemcpyAsync(O_out, c->d_operator.p, obytes, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  }
+  d_dual.release(); d_proj.release(); d_mask.release(); d_ener.release();
+  if (e != cudaSuccess) return cuda_fail(c, e, "bandup_gpu_orb_contrib_matrix");
+  c->operator_bands = n_bands;
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_unfold_operator(int handle, int ikpt, double min_abs_rho, int clip, double* out) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  Flight* fl = nullptr;
+  int rc = need_resident(c, ikpt, &fl);
+  if (rc) return rc;
+  if (!fl->rho_ready) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_rho_count first");
+  if (!out) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "out is NULL");
+  if (c->operator_bands != fl->n_bands)
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "Incompatible matrix shapes! (operator vs n_bands)");
+  cudaSetDevice(c->device);
+  cudaStream_t s = c->compute;
+  const int nener = c->nener, cells = fl->n_unique * nener;
+  CU(fl->trace_out.reserve(sizeof(double) * (size_t)cells));
+  {
+    KernelScope k(c, BANDUP_GPU_K_RHO, s);
+    launch_trace(cells, fl->n_bands, fl->d_dn_unique, static_cast<const long long*>(fl->pair_off.p),
+                 static_cast<const RhoPair*>(fl->pairs.p), c->d_operator.p, min_abs_rho, clip,
+                 static_cast<double*>(fl->trace_out.p), s);
+  }
+  CU(cudaGetLastError());
+  std::vector<double> h((size_t)cells);
+  CU(cudaMemcpyAsync(h.data(), fl->trace_out.p, sizeof(double) * (size_t)cells, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (int f = 0; f < fl->n_fold; ++f)
+    std::memcpy(out + (size_t)f * nener, h.data() + (size_t)fl->unique_of[f] * nener, sizeof(double) * (size_t)nener);
+  return BANDUP_GPU_OK;
 }
 
 int bandup_gpu_set_profiling(int handle, int enabled) {
@@ -750,14 +1031,15 @@ int64_t bandup_gpu_launch_count(int handle) {
   return c ? c->launches : -1;
 }
 
-int bandup_gpu_set_tuning(int handle, int chunk_vecs, int ctas_per_sm) {
+int bandup_gpu_set_tuning(int handle, int chunk_vecs, int ctas_per_sm, int n_stages) {
   Ctx* c = get(handle);
   if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  if (chunk_vecs < 0 || ctas_per_sm < 0) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "negative tuning value");
+  if (chunk_vecs < 0 || ctas_per_sm < 0 || n_stages < 0) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "negative tuning value");
   for (auto& f : c->flights)
     if (f.busy) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "cannot retune with k-points in flight");
   c->chunk_vecs = chunk_vecs;
   c->ctas_per_sm = ctas_per_sm;
+  c->n_stages = n_stages;
   return BANDUP_GPU_OK;
 }
 

@@ -5,8 +5,9 @@
 // (crystals_mod.f90:204-255) once per plane wave and per folding pc-kpt.  Here
 // every plane wave's Miller triple is mapped ONCE to its coset key and compared
 // with the keys of all pc-kpts folding onto the current SC-kpt; the result is a
-// one-byte slot id per plane wave that K2 consumes.  Pure integer arithmetic:
-// bit-exact by construction.  HBM-trivial: 12 B read + 1 B written per wave.
+// one-byte slot id per plane wave that K2 consumes (written twice: slot[] and the
+// one-element-shifted slot_shift[], see kernels.cuh).  Pure integer arithmetic:
+// bit-exact by construction.  HBM-trivial: 12 B read + 2 B written per wave.
 #include "kernels.cuh"
 
 namespace bandup {
@@ -18,7 +19,8 @@ __device__ __forceinline__ int pos_mod(long long v, long long D) {
 
 __global__ void __launch_bounds__(256)
 k1_coset_classify(const int32_t* __restrict__ g_frac, int n_pw, CosetParams cp,
-                  uint8_t* __restrict__ slot, int32_t* __restrict__ n_selected) {
+                  uint8_t* __restrict__ slot, uint8_t* __restrict__ slot_shift,
+                  int32_t* __restrict__ n_selected) {
   __shared__ int s_count[kMaxFolds];
   for (int f = threadIdx.x; f < cp.n_fold; f += blockDim.x) s_count[f] = 0;
   __syncthreads();
@@ -33,6 +35,8 @@ k1_coset_classify(const int32_t* __restrict__ g_frac, int n_pw, CosetParams cp,
     for (int f = cp.n_fold - 1; f >= 0; --f)  // descending so the FIRST match wins
       if (cp.fold_key[f][0] == k0 && cp.fold_key[f][1] == k1 && cp.fold_key[f][2] == k2) s = f;
     slot[pw] = (uint8_t)s;
+    if (pw > 0) slot_shift[pw - 1] = (uint8_t)s;
+    if (pw == n_pw - 1) slot_shift[pw] = kNoFold;
     if (s != kNoFold) atomicAdd(&s_count[s], 1);
   }
   __syncthreads();
@@ -41,12 +45,13 @@ k1_coset_classify(const int32_t* __restrict__ g_frac, int n_pw, CosetParams cp,
 }
 
 void launch_coset_classify(const int32_t* d_g_frac, int n_pw, const CosetParams& cp,
-                           uint8_t* d_slot, int32_t* d_n_selected, cudaStream_t s) {
+                           uint8_t* d_slot, uint8_t* d_slot_shift, int32_t* d_n_selected,
+                           cudaStream_t s) {
   cudaMemsetAsync(d_n_selected, 0, sizeof(int32_t) * cp.n_fold, s);
   if (n_pw <= 0) return;
   int blocks = (n_pw + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k1_coset_classify<<<blocks, 256, 0, s>>>(d_g_frac, n_pw, cp, d_slot, d_n_selected);
+  k1_coset_classify<<<blocks, 256, 0, s>>>(d_g_frac, n_pw, cp, d_slot, d_slot_shift, d_n_selected);
 }
 
 // One CTA per fold walks the slot table in order and writes the 1-based indices

@@ -28,8 +28,11 @@ struct CosetParams {
 // slot[pw] = index of the first fold whose coset contains G(pw), else kNoFold;
 // n_selected[f] = number of plane waves of fold f (must be zeroed by the caller,
 // launch_coset_classify does it).
+// d_slot_shift[pw] = slot[pw+1] (kNoFold past the end): lets K2 fetch the two slot ids of
+// a 16-byte vector with one aligned 16-bit load whatever the row's alignment.
 void launch_coset_classify(const int32_t* d_g_frac, int n_pw, const CosetParams& cp,
-                           uint8_t* d_slot, int32_t* d_n_selected, cudaStream_t s);
+                           uint8_t* d_slot, uint8_t* d_slot_shift, int32_t* d_n_selected,
+                           cudaStream_t s);
 
 // Ordered compaction of the 1-based selected indices of every fold (CSR).
 // d_offsets[f] = exclusive prefix of n_selected, computed on device.
@@ -42,22 +45,26 @@ struct WeightsGeom {
   long long stride_bytes;  // distance between band records
   long long row_elems;     // n_pw * n_spinor complex64 per band
   int n_bands, n_pw, n_spinor, layout;
-  const uint8_t* slot;     // [n_pw]
+  const uint8_t* slot;        // [n_pw], 2-byte aligned
+  const uint8_t* slot_shift;  // [n_pw], slot_shift[i] = slot[i+1], 2-byte aligned
   int n_fold;
-  int chunk_vecs;          // 16-byte vectors per tile
+  int chunk_vecs;          // 16-byte vectors per tile (a multiple of the 1024-vector stage)
   int n_chunks;            // tiles per band
+  int n_stages;            // shared-memory ring depth (set by the launcher)
   double* partials;        // [n_bands][n_chunks][n_fold+1]; [..][0] = norm part
 };
 
 int weights_num_chunks(long long row_elems, int chunk_vecs);
 size_t weights_partials_bytes(int n_bands, int n_chunks, int n_fold);
-int weights_default_chunk_vecs();
+// requested > 0: rounded up to whole stages; 0: chosen from the block shape
+int weights_pick_chunk_vecs(int requested, long long row_elems, int n_bands, int sm_count);
+int weights_max_folds_supported();
 
 // K2 -- the roofline kernel: one pass over every complex64 coefficient of the
 // k-point; per (band, chunk) tile the band-norm part and the per-fold masked
 // |C|^2 sums.  Fuses io_routines_mod.f90:1317-1330 (norm) with
 // band_unfolding_routines_mod.f90:638-644 and :1337-1345 (weights, spinor sum).
-void launch_weights_reduce(const WeightsGeom& g, int ctas_per_sm, int sm_count,
+void launch_weights_reduce(const WeightsGeom& g, int ctas_per_sm, int n_stages, int sm_count,
                            cudaStream_t s);
 
 // K2b -- deterministic tile combine: s = sum_c norm part, S_f = sum_c fold part,
@@ -73,6 +80,33 @@ void launch_weights_finalize(const double* d_partials, int n_bands, int n_chunks
 void launch_delta_n(const double* d_grid, int nener, double sigma,
                     const double* d_band_energies, const double* d_weights,
                     int n_bands, int n_fold, double* d_dN, cudaStream_t s);
+
+// ---- projected variant (rho.cu) ----------------------------------------------
+struct RhoPair {  // one upper-triangle element of an unfolding-density operator
+  int m1, m2;     // 0-based band indices, m1 <= m2
+  float re, im;
+};
+
+int rho_active_cap(int n_bands);
+// K4a + scan: pair_count[f*nener + ie], pair_off = exclusive prefix (n+1 entries).
+void launch_rho_plan(const double* d_grid, int nener, double sigma, const double* d_band_energies,
+                     int n_bands, int n_fold, const double* d_dN, double min_dN, int cap,
+                     int* d_pair_count, long long* d_pair_off, int* d_overflow, cudaStream_t s);
+void launch_scan(const int* d_in, int n, long long* d_out, cudaStream_t s);
+void launch_rho_gather(const void* d_coeffs, long long stride_bytes, int n_pw, int n_spinor,
+                       int n_bands, int layout, int n_fold, const int32_t* d_lists,
+                       const long long* d_sel_off, const double* d_norms, void* d_csel,
+                       cudaStream_t s);
+void launch_rho_pairs(const double* d_grid, int nener, double sigma, const double* d_band_energies,
+                      int n_bands, int n_fold, const double* d_dN, int cap, int n_spinor,
+                      const long long* d_sel_off, const void* d_csel, const int* d_pair_count,
+                      const long long* d_pair_off, RhoPair* d_pairs, cudaStream_t s);
+void launch_orb_contrib(int n_bands, int n_ao, const void* d_dual, const void* d_proj,
+                        const uint8_t* d_mask, const double* d_ener, double max_dE, double min_abs,
+                        void* d_O, cudaStream_t s);
+void launch_trace(int n_cells, int n_bands, const double* d_dN, const long long* d_pair_off,
+                  const RhoPair* d_pairs, const void* d_O, double min_abs_rho, int clip, double* d_out,
+                  cudaStream_t s);
 
 void launch_synth_fill(void* d_coeffs, long long row_elems, int n_bands,
                        long long stride_bytes, uint64_t seed, uint64_t ikpt,

@@ -31,6 +31,7 @@ K_COSET = CONST["BANDUP_GPU_K_COSET"]
 K_WEIGHTS = CONST["BANDUP_GPU_K_WEIGHTS"]
 K_FINALIZE = CONST["BANDUP_GPU_K_FINALIZE"]
 K_DELTA_N = CONST["BANDUP_GPU_K_DELTA_N"]
+K_RHO = CONST["BANDUP_GPU_K_RHO"]
 
 
 def _fortran_order(latt: np.ndarray) -> np.ndarray:
@@ -87,6 +88,27 @@ class UnfoldedKpt:
     def pckpt_cannot_be_parsed(self) -> np.ndarray:
         """main_BandUP.f90:161-172: an empty selection is the reference's fatal branch."""
         return self.n_selected == 0
+
+
+@dataclass
+class UnfoldDensityOps:
+    """rhos(:) of every pc-kpt of one SC-kpt as perform_unfolding stores them
+    (band_unfolding_routines_mod.f90:1404-1427): COO, reference append order."""
+    n_energies: int               # sum over pc-kpts of size(rhos)
+    fold: np.ndarray              # 0-based pc-kpt index within the SC-kpt's fold list
+    iener: np.ndarray             # iener_in_full_pc_egrid (1-based)
+    m1: np.ndarray                # band_indices (1-based)
+    m2: np.ndarray
+    rho: np.ndarray               # complex64
+
+    def dense(self, fold: int, iener: int, n_bands: int) -> np.ndarray:
+        sel = (self.fold == fold) & (self.iener == iener)
+        out = np.zeros((n_bands, n_bands), dtype=np.complex64)
+        out[self.m1[sel] - 1, self.m2[sel] - 1] = self.rho[sel]
+        return out
+
+    def energies_of(self, fold: int) -> np.ndarray:
+        return np.unique(self.iener[self.fold == fold])
 
 
 class GpuUnfolder:
@@ -228,6 +250,65 @@ class GpuUnfolder:
         ascending) per pc-kpt.  An empty list is the reference's 'not allocated'."""
         return self.perform_unfolding(wf, folding_G, want_selected=True).selected_coeff_indices
 
+    # -- projected variant ------------------------------------------------------
+    def calc_rho(self, ikpt: int, min_dN: float = 1e-3) -> "UnfoldDensityOps":
+        """The energy selection + calc_rho loop of perform_unfolding
+        (band_unfolding_routines_mod.f90:1372-1428, :1046-1161) for every pc-kpt of an SC-kpt that
+        has been fetched and is still resident.  Returns the stored elements (|rho| >= 1e-5, both
+        triangles) in the reference's append order."""
+        ne, nn = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.bandup_gpu_rho_count(self.handle, int(ikpt), float(min_dN), C.byref(ne),
+                                                   C.byref(nn)))
+        n = nn.value
+        fold = np.zeros(n, dtype=np.int32)
+        iener = np.zeros(n, dtype=np.int32)
+        m1 = np.zeros(n, dtype=np.int32)
+        m2 = np.zeros(n, dtype=np.int32)
+        re = np.zeros(n, dtype=np.float32)
+        im = np.zeros(n, dtype=np.float32)
+        f32p = C.POINTER(C.c_float)
+        self._check(self._lib.bandup_gpu_fetch_rho(
+            self.handle, int(ikpt), n, fold.ctypes.data_as(c_i32p), iener.ctypes.data_as(c_i32p),
+            m1.ctypes.data_as(c_i32p), m2.ctypes.data_as(c_i32p), re.ctypes.data_as(f32p),
+            im.ctypes.data_as(f32p)))
+        return UnfoldDensityOps(ne.value, fold, iener, m1, m2, (re + 1j * im).astype(np.complex64))
+
+    def get_orbital_contribution_matrix(self, proj_matrix_dual: np.ndarray, proj_matrix: np.ndarray,
+                                        ao_mask: np.ndarray, band_energies: np.ndarray,
+                                        max_band_dE: float = 0.1, min_abs: float = 1e-2) -> np.ndarray:
+        """KptInfo.get_orbital_contribution_matrix, use_dual=True
+        (bandupy/orbital_contributions.py:304-362).  ao_mask selects the combined atom/orbital
+        indices iat*n_orbs_per_atom + iorb.  The result also becomes the current operator."""
+        dual = np.ascontiguousarray(proj_matrix_dual, dtype=np.complex128)
+        proj = np.ascontiguousarray(proj_matrix, dtype=np.complex128)
+        nb, n_ao = dual.shape
+        if proj.shape != (n_ao, nb):
+            raise ValueError("proj_matrix must be (n_ao, n_bands) and its dual (n_bands, n_ao)")
+        mask = np.ascontiguousarray(ao_mask, dtype=np.uint8)
+        ener = np.ascontiguousarray(band_energies, dtype=np.float64)
+        O = np.zeros((nb, nb), dtype=np.complex128)
+        self._check(self._lib.bandup_gpu_orb_contrib_matrix(
+            self.handle, nb, n_ao, dual.ctypes.data_as(c_f64p), proj.ctypes.data_as(c_f64p),
+            mask.ctypes.data_as(C.POINTER(C.c_uint8)), ener.ctypes.data_as(c_f64p), float(max_band_dE),
+            float(min_abs), O.ctypes.data_as(c_f64p)))
+        return O
+
+    def set_operator(self, general_operator: np.ndarray) -> None:
+        O = np.ascontiguousarray(general_operator, dtype=np.complex128)
+        if O.ndim != 2 or O.shape[0] != O.shape[1]:
+            raise ValueError("Incompatible matrix shapes!")
+        self._check(self._lib.bandup_gpu_set_operator(self.handle, O.shape[0], O.ctypes.data_as(c_f64p)))
+
+    def unfold_operator(self, ikpt: int, n_fold: int, min_abs_rho: float = 1e-5,
+                        clip: bool = True) -> np.ndarray:
+        """UnfDensOp.unfold(O, multiply_by_N=True, discard_imag=True, clip_interval=(0, N)) for every
+        (pc-kpt, energy) of SC-kpt `ikpt` (bandupy/unfolding_density_op.py:121-141 as called from
+        orbital_contributions.py:444-458); 0 where no operator exists."""
+        out = np.zeros((n_fold, self.nener), dtype=np.float64)
+        self._check(self._lib.bandup_gpu_unfold_operator(self.handle, int(ikpt), float(min_abs_rho),
+                                                         int(bool(clip)), out.ctypes.data_as(c_f64p)))
+        return out
+
     # -- device-resident path (bench, torch interop) -------------------------
     def workspace_bytes(self, n_spinor: int, n_pw: int, n_bands: int, n_fold: int) -> int:
         return int(self._lib.bandup_gpu_workspace_bytes(self.handle, n_spinor, n_pw, n_bands, n_fold))
@@ -267,8 +348,9 @@ class GpuUnfolder:
     def launch_count(self) -> int:
         return int(self._lib.bandup_gpu_launch_count(self.handle))
 
-    def set_tuning(self, chunk_vecs: int = 0, ctas_per_sm: int = 0) -> None:
-        self._check(self._lib.bandup_gpu_set_tuning(self.handle, int(chunk_vecs), int(ctas_per_sm)))
+    def set_tuning(self, chunk_vecs: int = 0, ctas_per_sm: int = 0, n_stages: int = 0) -> None:
+        self._check(self._lib.bandup_gpu_set_tuning(self.handle, int(chunk_vecs), int(ctas_per_sm),
+                                                    int(n_stages)))
 
 
 def pinned_empty(nbytes: int) -> np.ndarray:

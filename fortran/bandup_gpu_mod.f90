@@ -1,0 +1,262 @@
+!! bandup_gpu_mod.f90 -- ISO_C_BINDING interface of libbandup_gpu.so (include/bandup_gpu.h).
+!!
+!! This is the binding a BandUP maintainer adds to src/ to call the B200 path from
+!! the main loop of main_BandUP.f90 (see INTEGRATION.md for the patch and the link
+!! line).  Style follows the reference's only C interop, module spglib_f08
+!! (src/external/spglib-1.5.2/example/spglib_f08.f90): `interface` blocks with
+!! bind(c), scalars by value, arrays as assumed-size, C ints as status.
+!!
+!! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran front end
+!! (gfortran/flang/ifx absent).  tests/test_abi.py checks every bind(c) name,
+!! argument count and kind against include/bandup_gpu.h so the two cannot drift, and
+!! bandup_b200/unfold.py (ctypes) makes the identical sequence of C-ABI calls.
+module bandup_gpu
+use, intrinsic :: iso_c_binding
+implicit none
+private
+public :: bandup_gpu_init, bandup_gpu_finalize, bandup_gpu_last_error, &
+          bandup_gpu_abi_version, bandup_gpu_pinned_alloc, bandup_gpu_pinned_free, &
+          bandup_gpu_set_cells, bandup_gpu_set_grid, bandup_gpu_get_grid, &
+          bandup_gpu_folding_g0, bandup_gpu_submit_kpt, bandup_gpu_fetch_kpt, &
+          bandup_gpu_pipeline_depth, bandup_gpu_set_profiling, &
+          bandup_gpu_kernel_time, bandup_gpu_reset_kernel_times, &
+          bandup_gpu_launch_count, bandup_gpu_set_tuning, &
+          bandup_gpu_rho_count, bandup_gpu_fetch_rho, &
+          bandup_gpu_unfold_kpt_f, bandup_gpu_error_message
+public :: BANDUP_GPU_OK, BANDUP_GPU_LAYOUT_FORTRAN_INMEM, BANDUP_GPU_LAYOUT_VASP_RECORD, &
+          BANDUP_GPU_MAX_FOLDS
+
+integer(c_int), parameter :: BANDUP_GPU_OK = 0
+integer(c_int), parameter :: BANDUP_GPU_LAYOUT_FORTRAN_INMEM = 0
+integer(c_int), parameter :: BANDUP_GPU_LAYOUT_VASP_RECORD = 1
+integer(c_int), parameter :: BANDUP_GPU_MAX_FOLDS = 64
+
+interface
+
+    function bandup_gpu_abi_version() bind(c, name='bandup_gpu_abi_version')
+        import c_int
+        integer(c_int) :: bandup_gpu_abi_version
+    end function bandup_gpu_abi_version
+
+    function bandup_gpu_init(device, handle) bind(c, name='bandup_gpu_init')
+        import c_int
+        integer(c_int), intent(in), value :: device
+        integer(c_int), intent(out) :: handle
+        integer(c_int) :: bandup_gpu_init
+    end function bandup_gpu_init
+
+    function bandup_gpu_finalize(handle) bind(c, name='bandup_gpu_finalize')
+        import c_int
+        integer(c_int), intent(in), value :: handle
+        integer(c_int) :: bandup_gpu_finalize
+    end function bandup_gpu_finalize
+
+    function bandup_gpu_last_error(handle) bind(c, name='bandup_gpu_last_error')
+        import c_int, c_ptr
+        integer(c_int), intent(in), value :: handle
+        type(c_ptr) :: bandup_gpu_last_error
+    end function bandup_gpu_last_error
+
+    function bandup_gpu_pinned_alloc(bytes, ptr) bind(c, name='bandup_gpu_pinned_alloc')
+        import c_int, c_size_t, c_ptr
+        integer(c_size_t), intent(in), value :: bytes
+        type(c_ptr), intent(out) :: ptr
+        integer(c_int) :: bandup_gpu_pinned_alloc
+    end function bandup_gpu_pinned_alloc
+
+    function bandup_gpu_pinned_free(ptr) bind(c, name='bandup_gpu_pinned_free')
+        import c_int, c_ptr
+        type(c_ptr), intent(in), value :: ptr
+        integer(c_int) :: bandup_gpu_pinned_free
+    end function bandup_gpu_pinned_free
+
+    ! crystal%rec_latt_vecs(1:3,1:3) is passed as it lies in memory (column-major,
+    ! row i = vector i); M_out receives int_M the same way.
+    function bandup_gpu_set_cells(handle, B_sc, b_pc, tol, M_out) &
+        bind(c, name='bandup_gpu_set_cells')
+        import c_int, c_double, c_int32_t
+        integer(c_int), intent(in), value :: handle
+        real(c_double), intent(in) :: B_sc(3,3), b_pc(3,3)
+        real(c_double), intent(in), value :: tol
+        integer(c_int32_t), intent(out) :: M_out(3,3)
+        integer(c_int) :: bandup_gpu_set_cells
+    end function bandup_gpu_set_cells
+
+    function bandup_gpu_set_grid(handle, E_start, E_end, delta_e, smearing, nener_out) &
+        bind(c, name='bandup_gpu_set_grid')
+        import c_int, c_double, c_int32_t
+        integer(c_int), intent(in), value :: handle
+        real(c_double), intent(in), value :: E_start, E_end, delta_e, smearing
+        integer(c_int32_t), intent(out) :: nener_out
+        integer(c_int) :: bandup_gpu_set_grid
+    end function bandup_gpu_set_grid
+
+    function bandup_gpu_get_grid(handle, energies) bind(c, name='bandup_gpu_get_grid')
+        import c_int, c_double
+        integer(c_int), intent(in), value :: handle
+        real(c_double), intent(out) :: energies(*)
+        integer(c_int) :: bandup_gpu_get_grid
+    end function bandup_gpu_get_grid
+
+    function bandup_gpu_folding_g0(handle, folding_G, n_fold, g0, max_residual) &
+        bind(c, name='bandup_gpu_folding_g0')
+        import c_int, c_double, c_int32_t
+        integer(c_int), intent(in), value :: handle
+        real(c_double), intent(in) :: folding_G(3,*)
+        integer(c_int), intent(in), value :: n_fold
+        integer(c_int32_t), intent(out) :: g0(3,*)
+        real(c_double), intent(out) :: max_residual
+        integer(c_int) :: bandup_gpu_folding_g0
+    end function bandup_gpu_folding_g0
+
+    ! coeffs = c_loc(wf%pw_coeffs), g_frac = c_loc(wf%G_frac): type(vec3d_int) is three
+    ! default integers, i.e. int32 [n_pw][3] in memory.
+    function bandup_gpu_submit_kpt(handle, ikpt, n_spinor, n_pw, n_bands, layout, &
+                                   band_stride_bytes, coeffs, g_frac, band_energies, &
+                                   n_fold, g0) bind(c, name='bandup_gpu_submit_kpt')
+        import c_int, c_int64_t, c_int32_t, c_double, c_ptr
+        integer(c_int), intent(in), value :: handle, ikpt, n_spinor, n_pw, n_bands, layout
+        integer(c_int64_t), intent(in), value :: band_stride_bytes
+        type(c_ptr), intent(in), value :: coeffs, g_frac
+        real(c_double), intent(in) :: band_energies(*)
+        integer(c_int), intent(in), value :: n_fold
+        integer(c_int32_t), intent(in) :: g0(3,*)
+        integer(c_int) :: bandup_gpu_submit_kpt
+    end function bandup_gpu_submit_kpt
+
+    ! weights(n_bands, n_fold), dN(nener, n_fold) in Fortran order.  Optional C outputs
+    ! are passed as type(c_ptr): c_null_ptr to skip, c_loc(array) otherwise.
+    function bandup_gpu_fetch_kpt(handle, ikpt, weights, dN, n_selected, norms, selected, &
+                                  selected_capacity) bind(c, name='bandup_gpu_fetch_kpt')
+        import c_int, c_int64_t, c_ptr
+        integer(c_int), intent(in), value :: handle, ikpt
+        type(c_ptr), intent(in), value :: weights, dN, n_selected, norms, selected
+        integer(c_int64_t), intent(in), value :: selected_capacity
+        integer(c_int) :: bandup_gpu_fetch_kpt
+    end function bandup_gpu_fetch_kpt
+
+    function bandup_gpu_pipeline_depth(handle) bind(c, name='bandup_gpu_pipeline_depth')
+        import c_int
+        integer(c_int), intent(in), value :: handle
+        integer(c_int) :: bandup_gpu_pipeline_depth
+    end function bandup_gpu_pipeline_depth
+
+    ! projected variant (-write_unf_dens_op): energy selection + calc_rho of perform_unfolding
+    ! (band_unfolding_routines_mod.f90:1372-1428) for the resident SC-kpt ikpt
+    function bandup_gpu_rho_count(handle, ikpt, min_dN, n_energies, n_entries) &
+        bind(c, name='bandup_gpu_rho_count')
+        import c_int, c_double, c_int64_t
+        integer(c_int), intent(in), value :: handle, ikpt
+        real(c_double), intent(in), value :: min_dN
+        integer(c_int64_t), intent(out) :: n_energies, n_entries
+        integer(c_int) :: bandup_gpu_rho_count
+    end function bandup_gpu_rho_count
+
+    function bandup_gpu_fetch_rho(handle, ikpt, capacity, fold, iener, m1, m2, rho_re, rho_im) &
+        bind(c, name='bandup_gpu_fetch_rho')
+        import c_int, c_int64_t, c_int32_t, c_float
+        integer(c_int), intent(in), value :: handle, ikpt
+        integer(c_int64_t), intent(in), value :: capacity
+        integer(c_int32_t), intent(out) :: fold(*), iener(*), m1(*), m2(*)
+        real(c_float), intent(out) :: rho_re(*), rho_im(*)
+        integer(c_int) :: bandup_gpu_fetch_rho
+    end function bandup_gpu_fetch_rho
+
+    function bandup_gpu_set_profiling(handle, enabled) bind(c, name='bandup_gpu_set_profiling')
+        import c_int
+        integer(c_int), intent(in), value :: handle, enabled
+        integer(c_int) :: bandup_gpu_set_profiling
+    end function bandup_gpu_set_profiling
+
+    function bandup_gpu_kernel_time(handle, which, total_ms, launches) &
+        bind(c, name='bandup_gpu_kernel_time')
+        import c_int, c_double, c_int64_t
+        integer(c_int), intent(in), value :: handle, which
+        real(c_double), intent(out) :: total_ms
+        integer(c_int64_t), intent(out) :: launches
+        integer(c_int) :: bandup_gpu_kernel_time
+    end function bandup_gpu_kernel_time
+
+    function bandup_gpu_reset_kernel_times(handle) bind(c, name='bandup_gpu_reset_kernel_times')
+        import c_int
+        integer(c_int), intent(in), value :: handle
+        integer(c_int) :: bandup_gpu_reset_kernel_times
+    end function bandup_gpu_reset_kernel_times
+
+    function bandup_gpu_launch_count(handle) bind(c, name='bandup_gpu_launch_count')
+        import c_int, c_int64_t
+        integer(c_int), intent(in), value :: handle
+        integer(c_int64_t) :: bandup_gpu_launch_count
+    end function bandup_gpu_launch_count
+
+    function bandup_gpu_set_tuning(handle, chunk_vecs, ctas_per_sm, n_stages) &
+        bind(c, name='bandup_gpu_set_tuning')
+        import c_int
+        integer(c_int), intent(in), value :: handle, chunk_vecs, ctas_per_sm, n_stages
+        integer(c_int) :: bandup_gpu_set_tuning
+    end function bandup_gpu_set_tuning
+
+end interface
+
+contains
+
+    !! Last error text of a handle as a Fortran string (for `write(*,*) ...; stop`).
+    function bandup_gpu_error_message(handle) result(msg)
+        integer(c_int), intent(in) :: handle
+        character(len=:), allocatable :: msg
+        type(c_ptr) :: p
+        character(kind=c_char), dimension(:), pointer :: chars
+        integer :: n, i
+        p = bandup_gpu_last_error(handle)
+        msg = ''
+        if(.not. c_associated(p)) return
+        call c_f_pointer(p, chars, [1024])
+        n = 0
+        do while(n < 1024)
+            if(chars(n+1) == c_null_char) exit
+            n = n + 1
+        enddo
+        allocate(character(len=n) :: msg)
+        do i=1,n
+            msg(i:i) = chars(i)
+        enddo
+    end function bandup_gpu_error_message
+
+    !! Convenience wrapper with the reference's own argument kinds: everything the body of
+    !! `if(pckpt_folds)` computes (main_BandUP.f90:145-172) for ALL pc-kpts folding onto the
+    !! current SC-kpt, synchronously.  pw_coeffs is wf%pw_coeffs (n_spinor, n_pw, n_bands),
+    !! G_frac_flat is wf%G_frac viewed as integer(3, n_pw), folding_G(3, n_fold) holds
+    !! Scoords(k) - K in Cartesian coordinates (band_unfolding_routines_mod.f90:571-576).
+    !! On return n_selected(f) == 0 marks a pc-kpt that "cannot be parsed" (:161-172).
+    subroutine bandup_gpu_unfold_kpt_f(handle, ikpt, pw_coeffs, G_frac_flat, band_energies, &
+                                       folding_G, weights, dN, n_selected, ierr)
+        integer(c_int), intent(in) :: handle, ikpt
+        complex(c_float_complex), dimension(:,:,:), contiguous, target, intent(in) :: pw_coeffs
+        integer(c_int32_t), dimension(:,:), contiguous, target, intent(in) :: G_frac_flat
+        real(c_double), dimension(:), intent(in) :: band_energies
+        real(c_double), dimension(:,:), intent(in) :: folding_G
+        real(c_double), dimension(:,:), contiguous, target, intent(out) :: weights, dN
+        integer(c_int32_t), dimension(:), contiguous, target, intent(out) :: n_selected
+        integer(c_int), intent(out) :: ierr
+        integer(c_int) :: n_spinor, n_pw, n_bands, n_fold
+        integer(c_int32_t), dimension(:,:), allocatable :: g0
+        real(c_double) :: residual
+
+        n_spinor = size(pw_coeffs, dim=1)
+        n_pw = size(pw_coeffs, dim=2)
+        n_bands = size(pw_coeffs, dim=3)
+        n_fold = size(folding_G, dim=2)
+        allocate(g0(3, n_fold))
+        ierr = bandup_gpu_folding_g0(handle, folding_G, n_fold, g0, residual)
+        if(ierr /= BANDUP_GPU_OK) return
+        ierr = bandup_gpu_submit_kpt(handle, ikpt, n_spinor, n_pw, n_bands, &
+                                     BANDUP_GPU_LAYOUT_FORTRAN_INMEM, &
+                                     int(n_pw, c_int64_t)*int(n_spinor, c_int64_t)*8_c_int64_t, &
+                                     c_loc(pw_coeffs), c_loc(G_frac_flat), band_energies, &
+                                     n_fold, g0)
+        if(ierr /= BANDUP_GPU_OK) return
+        ierr = bandup_gpu_fetch_kpt(handle, ikpt, c_loc(weights), c_loc(dN), c_loc(n_selected), &
+                                    c_null_ptr, c_null_ptr, 0_c_int64_t)
+    end subroutine bandup_gpu_unfold_kpt_f
+
+end module bandup_gpu

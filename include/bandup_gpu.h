@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BANDUP_GPU_ABI_VERSION 1
+#define BANDUP_GPU_ABI_VERSION 2
 
 /* status codes */
 #define BANDUP_GPU_OK 0
@@ -54,7 +54,7 @@ extern "C" {
 #define BANDUP_GPU_ERR_INT_OVERFLOW 12  /* Miller indices x adjugate would overflow */
 
 /* most pc-kpts that may fold onto one SC-kpt in a single submit */
-#define BANDUP_GPU_MAX_FOLDS 96
+#define BANDUP_GPU_MAX_FOLDS 64
 
 /* coefficient layouts accepted by submit_kpt / unfold_device */
 /* pw_coeffs(n_spinor, n_pw, n_bands) as it lies in Fortran memory:
@@ -147,6 +147,57 @@ int bandup_gpu_fetch_kpt(int handle, int ikpt, double *weights, double *dN,
 
 int bandup_gpu_pipeline_depth(int handle);
 
+/* ---- projected variant: unfolding-density operator ---------------------- */
+/* (`bandup unfold --orbitals` = -write_unf_dens_op, consumed by `projected-unfold`)
+ *
+ * The device buffers of SC-kpt `ikpt` stay valid after bandup_gpu_fetch_kpt until
+ * bandup_gpu_pipeline_depth() further submits have reused them; the calls below work
+ * on that resident k-point.
+ *
+ * bandup_gpu_rho_count replaces, for every pc-kpt of the k-point, the energy selection
+ * and the calc_rho loop of perform_unfolding (band_unfolding_routines_mod.f90:1372-1428,
+ * calc_rho :1046-1161): for every energy with dN >= min_dN (reference: 1e-3) the operator
+ *   rho(m1,m2) = lambda(m1) lambda(m2) / dN * sum_spinor sum_{G in sel} conj(C_m1) C_m2
+ * between the bands with lambda >= 1e-5 (m1 = 1..n_bands-1 only, prefactor >= 1e-5).
+ * It blocks until done and returns
+ *   n_energies  number of (pc-kpt, energy) operators      == sum of size(rhos)
+ *   n_entries   number of stored elements, |rho| >= 1e-5, both triangles (:1416-1425)
+ * min_dN < epsilon(1.0_dp) is refused with ERR_DELTA_N_ZERO (calc_rho's fatal branch). */
+int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t *n_energies,
+                         int64_t *n_entries);
+/* Copies the elements counted by the last bandup_gpu_rho_count(ikpt), in the reference's
+ * append order (pc-kpt, energy ascending, m1 outer, m2 inner):
+ *   fold   0-based index into the submit's pc-kpt list
+ *   iener  1-based index into the energy grid   (iener_in_full_pc_egrid)
+ *   m1,m2  1-based band indices                 (band_indices)
+ *   rho_re, rho_im  complex(sp) value           (rho) */
+int bandup_gpu_fetch_rho(int handle, int ikpt, int64_t capacity, int32_t *fold, int32_t *iener,
+                         int32_t *m1, int32_t *m2, float *rho_re, float *rho_im);
+
+/* Replaces KptInfo.get_orbital_contribution_matrix with use_dual=True
+ * (python_interface/bandupy/orbital_contributions.py:226-362):
+ *   O(m1,m2) = sum_{a: ao_mask[a]} dual[m1,a] * proj[a,m2]
+ * kept when |E_m2 - E_m1| <= max_band_dE (0.1 eV) and |O| >= min_abs (1e-2), else 0.
+ * dual [n_bands][n_ao], proj [n_ao][n_bands], O_out [n_bands][n_bands]: complex128
+ * interleaved (re,im), row-major, HOST.  ao_mask[a] != 0 selects the combined index
+ * a = iat*n_orbs_per_atom + iorb of the picked atoms and orbitals.  The matrix stays on
+ * the device as the handle's current operator; O_out may be NULL. */
+int bandup_gpu_orb_contrib_matrix(int handle, int n_bands, int n_ao, const double *dual,
+                                  const double *proj, const uint8_t *ao_mask,
+                                  const double *band_energies, double max_band_dE,
+                                  double min_abs, double *O_out);
+/* Uploads a general operator O [n_bands][n_bands] complex128 (HOST) as the current one. */
+int bandup_gpu_set_operator(int handle, int n_bands, const double *O);
+/* Replaces UnfDensOp.unfold(O, multiply_by_N=True, discard_imag=True, clip_interval=(0,N))
+ * (unfolding_density_op.py:121-141 as called from orbital_contributions.py:444-458) for every
+ * operator counted by the last bandup_gpu_rho_count(ikpt):
+ *   out[fold][iener] = clip(dN * Re Tr(rho . O), 0, dN)    (0 where there is no rho)
+ * rho is Hermitian-completed from its upper triangle with a real diagonal, as the Python
+ * class does; elements with |rho| < min_abs_rho are dropped (the reference's rho file keeps
+ * |rho| >= 1e-4, io_routines_mod.f90:1861).  clip = 0 returns dN * Re Tr(rho.O) unclipped.
+ * out [n_fold][nener] HOST. */
+int bandup_gpu_unfold_operator(int handle, int ikpt, double min_abs_rho, int clip, double *out);
+
 /* ---- per SC-k-point, device-resident buffers ---------------------------- */
 
 /* Scratch bytes unfold_device needs for these sizes. */
@@ -173,7 +224,8 @@ int bandup_gpu_unfold_device(int handle, void *stream, int n_spinor, int n_pw,
 #define BANDUP_GPU_K_WEIGHTS 1
 #define BANDUP_GPU_K_FINALIZE 2
 #define BANDUP_GPU_K_DELTA_N 3
-#define BANDUP_GPU_K_COUNT 4
+#define BANDUP_GPU_K_RHO 4
+#define BANDUP_GPU_K_COUNT 5
 
 /* When enabled, every launch is bracketed by CUDA events on its own stream. */
 int bandup_gpu_set_profiling(int handle, int enabled);
@@ -186,8 +238,9 @@ int bandup_gpu_reset_kernel_times(int handle);
 int64_t bandup_gpu_launch_count(int handle);
 
 /* Tuning knobs of the weights kernel (0 = keep default): tile size in 16-byte
- * vectors per (band, chunk) tile and resident CTAs per SM. */
-int bandup_gpu_set_tuning(int handle, int chunk_vecs, int ctas_per_sm);
+ * vectors per (band, chunk) tile (rounded up to whole 1024-vector stages),
+ * resident CTAs per SM and depth of each CTA's shared-memory stage ring. */
+int bandup_gpu_set_tuning(int handle, int chunk_vecs, int ctas_per_sm, int n_stages);
 
 /* Fills a device buffer with the synthetic coefficients bench.py and the tests
  * use (same hash as oracle/bandup_oracle.c:bo_synth_fill): n_bands rows of

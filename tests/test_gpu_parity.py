@@ -220,7 +220,7 @@ def test_pipeline_double_buffering(unfolder):
 
 
 def test_error_codes(unfolder):
-    from bandup_b200.unfold import BandupGpuError, PwWavefunction
+    from bandup_b200.unfold import BandupGpuError, MAX_FOLDS, PwWavefunction
     sc = synth.make_scenario("graphene4x4", scale=0.08)
     coeffs, gf, ener = synth.make_wavefunction(sc, 0)
     wf = PwWavefunction(coeffs, gf, ener)
@@ -239,7 +239,7 @@ def test_error_codes(unfolder):
     g0, res = unfolder.folding_g0(sc.folding_G(0) + np.array([4e-5, 0.0, 0.0]))
     assert res < 1e-3 and np.array_equal(g0, unfolder.folding_g0(sc.folding_G(0))[0])
     with pytest.raises(BandupGpuError) as ei:
-        unfolder.submit(1, wf, g0=np.zeros((97, 3), np.int32))
+        unfolder.submit(1, wf, g0=np.zeros((MAX_FOLDS + 1, 3), np.int32))
     assert ei.value.code == 5
     unfolder._inflight.clear()
     lib = unfolder._lib

@@ -1,0 +1,200 @@
+"""GPU parity of the projected variant (`unfold --orbitals` -> `projected-unfold`): the
+unfolding-density operator rho (K4), the orbital-contribution matrix and N Re Tr(rho O) (K5),
+all through the C ABI, against the oracle (C calc_rho with the reference's single-precision
+accumulation, NumPy calc_rho with fp64 dots) and the golden vectors made from the reference's
+own Python."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from bandup_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def _setup(u, sc, smearing=None):
+    u.verify_commens(sc.b_pc, sc.B_sc)
+    return u.set_energy_grid(*sc.energy_window(), smearing_for_delta_function=smearing)
+
+
+def _oracle_rhos(sc, coeffs, gf, ener, fG, grid, sigma=None):
+    """{(fold, iener1): dense rho (fp64 dots)} for every energy with dN >= 1e-3, plus dN."""
+    from oracle import oracle as O
+    from oracle import oracle_np as ON
+    gc = gf @ sc.B_sc
+    c_ren, _ = O.renormalize(coeffs, 1)
+    de = grid[1] - grid[0]
+    out, dNs = {}, []
+    for f, g in enumerate(fG):
+        sel, _ = O.select_coeffs(gc, g, sc.b_pc)
+        w = O.spectral_weights(c_ren, sel)
+        dN = O.delta_N(grid, ener, w, smearing=sigma or 0.0)
+        dNs.append(dN)
+        for ie in np.nonzero(dN >= 1e-3)[0]:
+            rho = ON.calc_rho(c_ren, sel, ener, dN[ie], grid[ie], de, sigma=sigma or ON.EPS_DP)
+            rho32 = O.calc_rho(c_ren, sel, ener, dN[ie], grid[ie], de, sigma=sigma or 0.0)
+            out[(f, int(ie) + 1)] = (rho, rho32)
+    return out, np.array(dNs)
+
+
+def _check_rho(res, want, nb):
+    got_keys = {(int(f), int(i)) for f, i in zip(res.fold, res.iener)}
+    for key, (rho, rho32) in want.items():
+        dense = res.dense(key[0], key[1], nb).astype(np.complex128)
+        scale = max(np.abs(rho).max(), 1e-30)
+        big = np.abs(rho) >= 1.2e-5           # stored for sure (threshold 1e-5 on the fp32 value)
+        small = np.abs(rho) < 0.8e-5          # dropped for sure
+        assert np.all(np.abs(dense[big] - rho[big]) <= 2e-6 * scale + 2e-7 * np.abs(rho[big]))
+        assert not dense[small].any()
+        # the reference's own single-precision accumulation is within its rounding of ours
+        assert np.all(np.abs(dense[big] - rho32[big]) <= 3e-5 * scale)
+        assert np.allclose(dense, dense.conj().T)
+        if np.abs(rho).max() >= 1.2e-5:
+            assert key in got_keys
+    for key in got_keys:
+        assert key in want, f"rho at {key} although dN < 1e-3"
+    # append order: fold, energy ascending, m1 outer, m2 inner
+    order = np.lexsort((res.m2, res.m1, res.iener, res.fold))
+    assert np.array_equal(order, np.arange(len(order)))
+
+
+@pytest.mark.parametrize("name,scale,iK", [("si333_vacancy", 0.25, 0), ("graphene4x4", 0.2, 1),
+                                           ("mos2_8x8_spinor", 0.06, 2)])
+def test_rho_matches_oracle(unfolder, name, scale, iK):
+    from bandup_b200.unfold import PwWavefunction
+    sc = synth.make_scenario(name, scale=scale)
+    grid = _setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, iK)
+    nb = coeffs.shape[0]
+    # a few exact degeneracies and near-degeneracies so that bins couple several bands
+    ener[2] = ener[1]
+    ener[4] = ener[3] + 0.01
+    ener[nb - 1] = ener[nb - 2]               # top band shares a bin (m1 stops at nb-1 quirk)
+    ener = np.sort(ener)
+    fG = sc.folding_G(iK)
+    unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), folding_G=fG, ikpt=5)
+    res = unfolder.calc_rho(5)
+    want, _ = _oracle_rhos(sc, coeffs, gf, ener, fG, grid)
+    assert len(want) > 0 and len(res.rho) > 0
+    _check_rho(res, want, nb)
+    # Tr rho ~ 1 wherever the bin does not hold the top band alone (io_routines_mod.f90:1832-1839)
+    for (f, ie), (rho, _) in want.items():
+        tr = np.trace(res.dense(f, ie, nb)).real
+        assert abs(tr - np.trace(rho).real) < 1e-5
+    assert res.n_energies == len({k for k, (r, _) in want.items() if np.abs(r).max() > 0})
+
+
+def test_rho_with_gaussian_smearing_and_shared_coset(unfolder):
+    """sigma = 0.03 eV couples many bands per energy; two pc-kpts in the same coset share rho."""
+    from bandup_b200.unfold import PwWavefunction
+    sc = synth.make_scenario("graphene4x4", scale=0.12)
+    grid = _setup(unfolder, sc, smearing=0.03)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 0)
+    nb = coeffs.shape[0]
+    fG = sc.folding_G(0)
+    fG = np.concatenate([fG, fG[:1] + sc.b_pc[0] - sc.b_pc[1]])    # same coset as fold 0
+    unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), folding_G=fG, ikpt=9)
+    res = unfolder.calc_rho(9)
+    want, _ = _oracle_rhos(sc, coeffs, gf, ener, fG, grid, sigma=0.03)
+    _check_rho(res, want, nb)
+    last = fG.shape[0] - 1
+    a = res.fold == 0
+    b = res.fold == last
+    assert a.sum() == b.sum() > 0
+    assert np.array_equal(res.rho[a], res.rho[b]) and np.array_equal(res.iener[a], res.iener[b])
+
+
+def test_rho_needs_fetched_resident_kpt(unfolder):
+    from bandup_b200.unfold import BandupGpuError, PwWavefunction
+    sc = synth.make_scenario("graphene4x4", scale=0.08)
+    _setup(unfolder, sc)
+    wf = PwWavefunction(*synth.make_wavefunction(sc, 0))
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.calc_rho(3)
+    assert ei.value.code == 8                                   # never submitted
+    unfolder.submit(3, wf, folding_G=sc.folding_G(0))
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.calc_rho(3)
+    assert ei.value.code == 1                                   # not fetched yet
+    unfolder.fetch(3)
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.calc_rho(3, min_dN=0.0)
+    assert ei.value.code == 11                                  # calc_rho: delta_N = 0
+    assert len(unfolder.calc_rho(3).rho) > 0
+    for k in (4, 5):                                            # two more submits reuse both slots
+        unfolder.perform_unfolding(wf, folding_G=sc.folding_G(0), ikpt=k, want_selected=False)
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.calc_rho(3)
+    assert ei.value.code == 8
+
+
+def test_orbital_contribution_matrix_matches_reference_golden(unfolder):
+    g = np.load(GOLD / "orb_contrib_golden.npz")
+    meta = json.loads(str(g["meta"]))
+    for i, m in enumerate(meta):
+        O = unfolder.get_orbital_contribution_matrix(g[f"c{i}_dual"], g[f"c{i}_proj"], g[f"c{i}_mask"],
+                                                     g[f"c{i}_ener"], m["max_band_dE"], m["min_abs"])
+        ref = g[f"c{i}_O"]
+        assert np.array_equal(O != 0, ref != 0) and np.count_nonzero(O) == m["nnz"]
+        assert np.allclose(O, ref, rtol=1e-12, atol=1e-14)
+
+
+def test_projected_unfold_config4(unfolder):
+    """BASELINE config 4 in miniature: Si 3x3x3 vacancy cell with synthetic PROCAR-like projections
+    (atoms x 9 orbitals), dual = pinv; N Re Tr(rho O) per (k, E) against the oracle chain that the
+    golden vectors pin to the reference's Python."""
+    from bandup_b200.unfold import PwWavefunction
+    from oracle import oracle_np as ON
+    sc = synth.make_scenario("si333_vacancy", scale=0.3)
+    grid = _setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 1)
+    nb = coeffs.shape[0]
+    ener[5] = ener[4]
+    ener[9] = ener[8] + 0.02
+    ener = np.sort(ener)
+    fG = sc.folding_G(1)
+    out = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), folding_G=fG, ikpt=2)
+    res = unfolder.calc_rho(2)
+    rng = np.random.default_rng(8)
+    n_at, n_orb = 24, 9
+    n_ao = n_at * n_orb
+    proj = (rng.standard_normal((n_ao, nb)) + 1j * rng.standard_normal((n_ao, nb))) * \
+        np.repeat(rng.uniform(0.05, 0.4, n_at), n_orb)[:, None]
+    dual = np.linalg.pinv(proj)
+    mask = np.zeros(n_ao, np.uint8)
+    for iat in (0, 3, 7, 8):
+        mask[iat * n_orb + 1:iat * n_orb + 4] = 1                # the p orbitals of four atoms
+    O = unfolder.get_orbital_contribution_matrix(dual, proj, mask, ener)
+    O_ref = ON.orb_contrib_matrix(dual, proj, mask, ener)
+    assert np.array_equal(O != 0, O_ref != 0) and np.allclose(O, O_ref, rtol=1e-12, atol=1e-14)
+    assert np.count_nonzero(O) > nb // 2
+    vals = unfolder.unfold_operator(2, fG.shape[0], min_abs_rho=1e-4, clip=True)
+    raw = unfolder.unfold_operator(2, fG.shape[0], min_abs_rho=1e-4, clip=False)
+    checked = 0
+    for f in range(fG.shape[0]):
+        for ie in res.energies_of(f):
+            s = (res.fold == f) & (res.iener == ie) & (res.m1 <= res.m2)
+            N = out.dN[f, ie - 1]
+            want = ON.unfold_rho_operator(list(res.m1[s] - 1), list(res.m2[s] - 1), list(res.rho[s]), O, N,
+                                          min_abs_rho=1e-4, clip=True)
+            want_raw = ON.unfold_rho_operator(list(res.m1[s] - 1), list(res.m2[s] - 1), list(res.rho[s]), O, N,
+                                              min_abs_rho=1e-4, clip=False)
+            assert abs(vals[f, ie - 1] - want) <= 1e-9 * max(1.0, abs(want))
+            assert abs(raw[f, ie - 1] - want_raw) <= 1e-9 * max(1.0, abs(want_raw))
+            assert 0.0 <= vals[f, ie - 1] <= N
+            checked += 1
+    assert checked > 10
+    # no operator => exactly zero
+    has = np.zeros_like(vals, dtype=bool)
+    has[res.fold, res.iener - 1] = True
+    assert not vals[~has].any()
+    # identity operator: N Re Tr(rho) ~ N wherever Tr rho ~ 1
+    unfolder.set_operator(np.eye(nb))
+    ident = unfolder.unfold_operator(2, fG.shape[0], min_abs_rho=0.0, clip=False)
+    for f in range(fG.shape[0]):
+        for ie in res.energies_of(f):
+            tr = np.trace(res.dense(f, ie, nb)).real
+            assert abs(ident[f, ie - 1] - out.dN[f, ie - 1] * tr) <= 1e-6 * out.dN[f, ie - 1]
