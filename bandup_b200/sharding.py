@@ -1,0 +1,152 @@
+"""SC-k-point sharding across GPUs (one process per GPU, torch.distributed for the plumbing).
+
+The unit of work of the unfolding path is one SC k-point (loop `do i_SCKPT`, main_BandUP.f90:133):
+its coefficient block is private and every pc-kpt folds onto exactly one SC-kpt
+(band_unfolding_routines_mod.f90:317-324, 396-403), so ranks never exchange coefficients and the
+delta_N rows they produce are disjoint.  The only collective of the path is the gather of those
+rows (a few hundred rows x nener doubles, <= ~2 MB): NCCL all_gather over NVLink on GPUs, gloo in
+the CPU tests.  Symmetry averaging over needed_dirs (band_unfolding_routines_mod.f90:840-853)
+happens after the gather, on the host, unchanged.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def partition_kpts(costs: Sequence[float], world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous blocks [start, end) of the SC-kpt list, one per rank, balanced by cost
+    (n_bands * n_pw(K) * n_spinor).  Contiguity keeps the reader sequential in the wavefunction
+    file (read_wavecar_mod.f90 skips k-points it does not need).  Every rank gets a block (possibly
+    empty when there are fewer k-points than ranks); blocks tile 0..len(costs) exactly."""
+    n = len(costs)
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    c = np.asarray(costs, dtype=np.float64)
+    if n and np.any(c < 0):
+        raise ValueError("costs must be non-negative")
+    total = float(c.sum())
+    if total <= 0.0:
+        c = np.ones(n)
+        total = float(n)
+    bounds = [0]
+    prefix = np.concatenate([[0.0], np.cumsum(c)])
+    for r in range(1, world_size):
+        target = total * r / world_size
+        lo = bounds[-1]
+        j = lo + int(np.argmin(np.abs(prefix[lo:] - target)))   # closest cut at or after the previous one
+        bounds.append(j)
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
+@dataclass
+class GatheredDeltaN:
+    dN: np.ndarray            # (n_rows_total, nener) in global row order
+    row_ids: np.ndarray       # (n_rows_total,) the global pc-kpt row id of every row
+    rows_per_rank: List[int]
+
+
+def gather_delta_N(local_dN: np.ndarray, local_row_ids: np.ndarray, nener: int, device=None,
+                   group=None) -> GatheredDeltaN:
+    """All ranks contribute their (n_local, nener) delta_N rows + global row ids; every rank gets
+    the full table sorted by row id.  Rows are disjoint by construction; a duplicate id is an
+    error (it would mean a pc-kpt was unfolded twice).  Pads to the largest shard so that one
+    all_gather moves everything."""
+    import torch
+    import torch.distributed as dist
+    local_dN = np.ascontiguousarray(local_dN, dtype=np.float64).reshape(-1, nener)
+    ids = np.ascontiguousarray(local_row_ids, dtype=np.int64).reshape(-1)
+    if ids.shape[0] != local_dN.shape[0]:
+        raise ValueError("one row id per delta_N row")
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        order = np.argsort(ids, kind="stable")
+        _check_disjoint(ids[order])
+        return GatheredDeltaN(local_dN[order], ids[order], [int(ids.shape[0])])
+    world = dist.get_world_size(group)
+    dev = device if device is not None else torch.device("cpu")
+    n_local = torch.tensor([ids.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    n_max = max(max(counts), 1)
+    # one payload: [row id (as f64, exact below 2^53), nener values] per row, padded
+    payload = torch.zeros((n_max, nener + 1), dtype=torch.float64, device=dev)
+    if ids.shape[0]:
+        payload[:ids.shape[0], 0] = torch.from_numpy(ids.astype(np.float64)).to(dev)
+        payload[:ids.shape[0], 1:] = torch.from_numpy(local_dN).to(dev)
+    out = torch.empty((world, n_max, nener + 1), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out.view(world * n_max, nener + 1), payload, group=group)
+    out = out.cpu().numpy()
+    rows, rid = [], []
+    for r in range(world):
+        rows.append(out[r, :counts[r], 1:])
+        rid.append(out[r, :counts[r], 0].astype(np.int64))
+    dN = np.concatenate(rows, axis=0) if rows else np.zeros((0, nener))
+    rid = np.concatenate(rid) if rid else np.zeros(0, dtype=np.int64)
+    order = np.argsort(rid, kind="stable")
+    _check_disjoint(rid[order])
+    return GatheredDeltaN(dN[order], rid[order], counts)
+
+
+def _check_disjoint(sorted_ids: np.ndarray) -> None:
+    if sorted_ids.size > 1 and np.any(np.diff(sorted_ids) == 0):
+        dup = sorted_ids[1:][np.diff(sorted_ids) == 0][0]
+        raise ValueError(f"pc-kpt row {int(dup)} was produced by more than one SC-kpt / rank")
+
+
+class ShardedUnfoldJob:
+    """Runs this rank's block of SC k-points through an unfolder with double buffering and gathers
+    the delta_N rows.  `unfolder` is anything with submit(ikpt, wf, g0=/folding_G=) / fetch(ikpt)
+    (bandup_b200.unfold.GpuUnfolder on a GPU box; a stand-in in the CPU tests).
+
+    load_kpt(iK) -> (wf, folding_G, row_ids): the wavefunction of SC-kpt iK, the Cartesian folding
+    vectors of the pc-kpts that fold onto it and their global row ids in the output table."""
+
+    def __init__(self, unfolder, n_kpts: int, costs: Sequence[float], load_kpt: Callable,
+                 rank: int = 0, world_size: int = 1, depth: int = 2):
+        self.unfolder = unfolder
+        self.load_kpt = load_kpt
+        self.rank, self.world_size = rank, world_size
+        self.blocks = partition_kpts(costs, world_size)
+        self.my_block = self.blocks[rank]
+        self.depth = max(1, depth)
+        if len(costs) != n_kpts:
+            raise ValueError("one cost per SC-kpt")
+
+    def run_local(self):
+        """(dN rows, row ids, weights per row) of this rank's SC-kpts; submit runs `depth` ahead of
+        fetch so the upload of k-point j+1 overlaps the kernels of j."""
+        start, end = self.my_block
+        inflight: List[Tuple[int, np.ndarray]] = []
+        rows, ids, weights = [], [], []
+
+        def drain_one():
+            iK, rid = inflight.pop(0)
+            res = self.unfolder.fetch(iK)
+            if np.any(res.n_selected == 0):
+                bad = rid[np.nonzero(res.n_selected == 0)[0][0]]
+                # main_BandUP.f90:167-171 (stop_if_pckpt_cannot_be_parsed = .TRUE.)
+                raise RuntimeError(f"pc-kpt row {int(bad)} cannot be parsed (no plane wave selected)")
+            rows.append(res.dN)
+            weights.append(res.spectral_weight)
+            ids.append(rid)
+
+        for iK in range(start, end):
+            wf, folding_G, rid = self.load_kpt(iK)
+            if len(inflight) >= self.depth:
+                drain_one()
+            self.unfolder.submit(iK, wf, folding_G=folding_G)
+            inflight.append((iK, np.asarray(rid, dtype=np.int64)))
+        while inflight:
+            drain_one()
+        nener = self.unfolder.nener
+        dN = np.concatenate(rows, axis=0) if rows else np.zeros((0, nener))
+        rid = np.concatenate(ids) if ids else np.zeros(0, dtype=np.int64)
+        return dN, rid, weights
+
+    def run(self, device=None, group=None) -> GatheredDeltaN:
+        dN, rid, _ = self.run_local()
+        return gather_delta_N(dN, rid, self.unfolder.nener, device=device, group=group)

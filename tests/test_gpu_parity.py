@@ -304,3 +304,28 @@ def test_device_resident_full_size_sige555(unfolder):
     assert np.allclose(dN.sum(axis=1), w[:, inside].sum(axis=1), rtol=1e-12)
     dN_o = O.delta_N(grid, ener, w[0])
     assert rel_err(dN[0], dN_o) <= REL_TOL
+
+
+def test_sharded_job_whole_scenario(unfolder):
+    """Every SC-kpt of a (shrunken) graphene job through ShardedUnfoldJob with the real GPU
+    unfolder: double-buffered submit/fetch, rows assembled in pc-kpt order, against the oracle."""
+    from bandup_b200.sharding import ShardedUnfoldJob
+    from bandup_b200.unfold import PwWavefunction
+    from oracle import oracle as O
+    sc = synth.make_scenario("graphene4x4", scale=0.08, n_kpts=15)
+    grid = setup(unfolder, sc)
+    data = {}
+
+    def load(iK):
+        coeffs, gf, ener = synth.make_wavefunction(sc, iK)
+        data[iK] = (coeffs, gf, ener)
+        return PwWavefunction(coeffs, gf, ener), sc.folding_G(iK), np.asarray(sc.folds[iK])
+
+    costs = [sc.n_bands * sc.gvecs(iK).shape[0] for iK in range(sc.n_sc_kpts)]
+    got = ShardedUnfoldJob(unfolder, sc.n_sc_kpts, costs, load).run()
+    n_rows = sum(len(f) for f in sc.folds)
+    assert got.row_ids.tolist() == list(range(n_rows))
+    for iK in range(sc.n_sc_kpts):
+        coeffs, gf, ener = data[iK]
+        _, dN, _, _ = O.unfold_kpt(coeffs, gf @ sc.B_sc, ener, sc.b_pc, sc.folding_G(iK), grid, norm_mode=1)
+        assert rel_err(got.dN[np.asarray(sc.folds[iK])], dN) <= REL_TOL
