@@ -21,6 +21,15 @@ OK = 0
 ERR_NAMES = {}
 
 
+class KptDesc(C.Structure):
+    """struct bandup_gpu_kpt_desc (include/bandup_gpu.h)."""
+    _fields_ = [("n_spinor", C.c_int32), ("n_pw", C.c_int32), ("n_bands", C.c_int32), ("layout", C.c_int32),
+                ("n_fold", C.c_int32), ("reserved", C.c_int32), ("band_stride_bytes", C.c_int64),
+                ("d_coeffs", C.c_void_p), ("d_g_frac", C.c_void_p), ("d_band_energies", C.c_void_p),
+                ("g0", C.c_void_p), ("d_weights", C.c_void_p), ("d_dN", C.c_void_p),
+                ("d_n_selected", C.c_void_p), ("d_norms", C.c_void_p)]
+
+
 class BandupGpuError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"bandup_gpu error {code} ({ERR_NAMES.get(code, '?')}): {message}")
@@ -86,6 +95,9 @@ def load() -> C.CDLL:
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_i32p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_size_t]),
+        "bandup_gpu_batch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.POINTER(KptDesc)]),
+        "bandup_gpu_unfold_device_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(KptDesc),
+                                                     C.c_void_p, C.c_size_t]),
         "bandup_gpu_set_profiling": (C.c_int, [C.c_int, C.c_int]),
         "bandup_gpu_kernel_time": (C.c_int, [C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int64)]),
         "bandup_gpu_reset_kernel_times": (C.c_int, [C.c_int]),

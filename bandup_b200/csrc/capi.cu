@@ -68,6 +68,14 @@ struct RhoEntry {  // one stored element of an unfolding-density operator (refer
   float re, im;
 };
 
+constexpr int kDescRing = 8;
+struct DescSlot {  // pinned + device staging of one batch's KptGeom array
+  KptGeom* h = nullptr;
+  KptGeom* d = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+};
+
 struct Flight {  // one SC k-point in flight
   bool busy = false;      // submitted, not fetched yet
   bool resident = false;  // device buffers still hold this k-point (for the rho calls)
@@ -96,7 +104,9 @@ struct Ctx {
   bool cells_set = false, grid_set = false;
   double B_sc[9] = {0}, B_inv[9] = {0};  // row-major, row = vector
   int32_t M[9] = {0};                    // row-major int_M
-  CosetParams coset{};
+  CosetCommon coset{};
+  DescSlot desc_ring[kDescRing];
+  int desc_next = 0;
   std::vector<double> grid;
   DevBuf d_grid;
   DevBuf d_operator;  // current general operator O [n_bands][n_bands] complex128
@@ -251,42 +261,40 @@ void resolve_pending(Ctx* c) {
 
 struct FoldPlan {
   int n_unique = 0;
-  int unique_of[kMaxFolds];  // user fold -> unique fold
-  int first_of[kMaxFolds];   // unique fold -> first user fold holding that coset
-  CosetParams cp;
+  int unique_of[kMaxFolds];    // user fold -> unique fold
+  int first_of[kMaxFolds];     // unique fold -> first user fold holding that coset
+  int fold_key[kMaxFolds][3];  // key(g0) of every unique fold
 };
 
 int plan_folds(Ctx* c, int n_fold, const int32_t* g0, FoldPlan* plan) {
   if (n_fold < 1 || n_fold > kMaxFolds)
     return fail(c, BANDUP_GPU_ERR_TOO_MANY_FOLDS,
                 "n_fold must be in 1.." + std::to_string(kMaxFolds) + ", got " + std::to_string(n_fold));
-  plan->cp = c->coset;
   plan->n_unique = 0;
   for (int f = 0; f < n_fold; ++f) {
     int key[3];
     coset_key(g0 + 3 * f, c->coset.adjT, c->coset.D, key);
     int u = -1;
     for (int q = 0; q < plan->n_unique; ++q)
-      if (plan->cp.fold_key[q][0] == key[0] && plan->cp.fold_key[q][1] == key[1] &&
-          plan->cp.fold_key[q][2] == key[2])
+      if (plan->fold_key[q][0] == key[0] && plan->fold_key[q][1] == key[1] &&
+          plan->fold_key[q][2] == key[2])
         u = q;
     if (u < 0) {
       u = plan->n_unique++;
-      plan->cp.fold_key[u][0] = key[0];
-      plan->cp.fold_key[u][1] = key[1];
-      plan->cp.fold_key[u][2] = key[2];
+      plan->fold_key[u][0] = key[0];
+      plan->fold_key[u][1] = key[1];
+      plan->fold_key[u][2] = key[2];
       plan->first_of[u] = f;
     }
     plan->unique_of[f] = u;
   }
-  plan->cp.n_fold = plan->n_unique;
   return BANDUP_GPU_OK;
 }
 
 size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct WorkspaceLayout {
-  size_t slot_off, slot_shift_off, partials_off, tmp_w_off, tmp_dn_off, tmp_ns_off, total;
+  size_t slot_off, slot_shift_off, counts_off, partials_off, tmp_w_off, tmp_dn_off, tmp_ns_off, total;
 };
 
 WorkspaceLayout workspace_layout(const Ctx* c, int n_spinor, int n_pw, int n_bands, int n_fold) {
@@ -298,6 +306,8 @@ WorkspaceLayout workspace_layout(const Ctx* c, int n_spinor, int n_pw, int n_ban
   off += align256((size_t)(n_pw > 0 ? n_pw : 1));
   w.slot_shift_off = off;
   off += align256((size_t)(n_pw > 0 ? n_pw : 1));
+  w.counts_off = off;
+  off += align256(sizeof(int) * (size_t)kK1MaxBlocks * (size_t)n_fold);
   w.partials_off = off;
   off += align256(weights_partials_bytes(n_bands, n_chunks, n_fold));
   // scratch rows used only when two requested pc-kpts share a coset
@@ -311,70 +321,135 @@ WorkspaceLayout workspace_layout(const Ctx* c, int n_spinor, int n_pw, int n_ban
   return w;
 }
 
-int run_kpt(Ctx* c, cudaStream_t s, int n_spinor, int n_pw, int n_bands, int layout,
-            long long stride_bytes, const void* d_coeffs, const int32_t* d_gfrac,
-            const double* d_energies, int n_fold, const FoldPlan& plan, double* d_weights,
-            double* d_dN, int32_t* d_nsel, double* d_norms, uint8_t* d_slot_out, void* d_ws,
-            size_t ws_bytes, const double** dn_unique = nullptr,
-            const int32_t** ns_unique = nullptr) {
-  const WorkspaceLayout wl = workspace_layout(c, n_spinor, n_pw, n_bands, n_fold);
-  if (ws_bytes < wl.total)
-    return fail(c, BANDUP_GPU_ERR_CAPACITY,
-                "workspace too small: need " + std::to_string(wl.total) + " bytes");
-  char* ws = static_cast<char*>(d_ws);
-  uint8_t* d_slot = reinterpret_cast<uint8_t*>(ws + wl.slot_off);
-  uint8_t* d_slot_shift = reinterpret_cast<uint8_t*>(ws + wl.slot_shift_off);
-  double* d_partials = reinterpret_cast<double*>(ws + wl.partials_off);
-  const bool dup = plan.n_unique != n_fold;
-  double* w_out = dup ? reinterpret_cast<double*>(ws + wl.tmp_w_off) : d_weights;
-  double* dn_out = dup ? reinterpret_cast<double*>(ws + wl.tmp_dn_off) : d_dN;
-  int32_t* ns_out = dup ? reinterpret_cast<int32_t*>(ws + wl.tmp_ns_off) : d_nsel;
-  const int nu = plan.n_unique;
-  if (dn_unique) *dn_unique = dn_out;
-  if (ns_unique) *ns_unique = ns_out;
+struct BatchItem {  // one SC k-point of a launch batch (host side)
+  int n_spinor = 1, n_pw = 0, n_bands = 0, layout = 0, n_fold = 0;
+  long long stride_bytes = 0;
+  const void* d_coeffs = nullptr;
+  const int32_t* d_gfrac = nullptr;
+  const double* d_energies = nullptr;
+  FoldPlan plan;
+  double* d_weights = nullptr;
+  double* d_dN = nullptr;
+  int32_t* d_nsel = nullptr;
+  double* d_norms = nullptr;
+  uint8_t* d_slot_out = nullptr;
+  char* ws = nullptr;
+  // outputs of run_batch: where the per-distinct-coset rows live
+  const double* dn_unique = nullptr;
+  const int32_t* ns_unique = nullptr;
+  const uint8_t* d_slot = nullptr;
+};
 
+// The descriptors of a batch travel through a small ring of pinned/device blocks so that a
+// call never waits for the previous one (each entry carries the event of its own upload).
+KptGeom* stage_descriptors(Ctx* c, cudaStream_t s, const std::vector<KptGeom>& geoms, cudaError_t* err) {
+  DescSlot& d = c->desc_ring[c->desc_next];
+  c->desc_next = (c->desc_next + 1) % kDescRing;
+  const size_t n = geoms.size();
+  *err = cudaSuccess;
+  if (d.ev) {
+    if ((*err = cudaEventSynchronize(d.ev)) != cudaSuccess) return nullptr;
+  } else if ((*err = cudaEventCreateWithFlags(&d.ev, cudaEventDisableTiming)) != cudaSuccess) {
+    return nullptr;
+  }
+  if (d.cap < n) {
+    if (d.h) cudaFreeHost(d.h);
+    if (d.d) cudaFree(d.d);
+    d.h = nullptr;
+    d.d = nullptr;
+    d.cap = 0;
+    const size_t want = n < 8 ? 8 : n;
+    if ((*err = cudaMallocHost(reinterpret_cast<void**>(&d.h), want * sizeof(KptGeom))) != cudaSuccess) return nullptr;
+    if ((*err = cudaMalloc(reinterpret_cast<void**>(&d.d), want * sizeof(KptGeom))) != cudaSuccess) return nullptr;
+    d.cap = want;
+  }
+  std::memcpy(d.h, geoms.data(), n * sizeof(KptGeom));
+  if ((*err = cudaMemcpyAsync(d.d, d.h, n * sizeof(KptGeom), cudaMemcpyHostToDevice, s)) != cudaSuccess) return nullptr;
+  if ((*err = cudaEventRecord(d.ev, s)) != cudaSuccess) return nullptr;
+  return d.d;
+}
+
+// K1 -> K2 -> K2b -> K3 for every k-point of the batch: four launches in total.
+int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
+  const int n = (int)items.size();
+  if (n == 0) return BANDUP_GPU_OK;
+  std::vector<KptGeom> geoms((size_t)n);
+  long long tiles = 0;
+  int max_fold = 0, max_bands = 0, max_pw = 0;
+  bool any_dup = false;
+  for (int i = 0; i < n; ++i) {
+    BatchItem& it = items[(size_t)i];
+    if (it.n_spinor != items[0].n_spinor || it.layout != items[0].layout)
+      return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "all k-points of a batch must share n_spinor and layout");
+    const WorkspaceLayout wl = workspace_layout(c, it.n_spinor, it.n_pw, it.n_bands, it.n_fold);
+    const bool dup = it.plan.n_unique != it.n_fold;
+    any_dup = any_dup || dup;
+    KptGeom& g = geoms[(size_t)i];
+    g.coeffs = static_cast<const char*>(it.d_coeffs);
+    g.stride_bytes = it.stride_bytes;
+    g.row_elems = (long long)it.n_pw * it.n_spinor;
+    g.n_bands = it.n_bands;
+    g.n_pw = it.n_pw;
+    g.n_spinor = it.n_spinor;
+    g.layout = it.layout;
+    g.g_frac = it.d_gfrac;
+    g.energies = it.d_energies;
+    g.slot = reinterpret_cast<uint8_t*>(it.ws + wl.slot_off);
+    g.slot_shift = reinterpret_cast<uint8_t*>(it.ws + wl.slot_shift_off);
+    g.block_counts = reinterpret_cast<int*>(it.ws + wl.counts_off);
+    g.n_selected = dup ? reinterpret_cast<int32_t*>(it.ws + wl.tmp_ns_off) : it.d_nsel;
+    g.n_fold = it.plan.n_unique;
+    g.chunk_vecs = weights_pick_chunk_vecs(c->chunk_vecs, g.row_elems, it.n_bands, c->sm_count);
+    g.n_chunks = weights_num_chunks(g.row_elems, g.chunk_vecs);
+    g.tile_begin = tiles;
+    tiles += (long long)it.n_bands * g.n_chunks;
+    g.partials = reinterpret_cast<double*>(it.ws + wl.partials_off);
+    g.weights = dup ? reinterpret_cast<double*>(it.ws + wl.tmp_w_off) : it.d_weights;
+    g.norms = it.d_norms;
+    g.dN = dup ? reinterpret_cast<double*>(it.ws + wl.tmp_dn_off) : it.d_dN;
+    std::memcpy(g.fold_key, it.plan.fold_key, sizeof(g.fold_key));
+    it.dn_unique = g.dN;
+    it.ns_unique = g.n_selected;
+    it.d_slot = g.slot;
+    if (g.n_fold > max_fold) max_fold = g.n_fold;
+    if (it.n_bands > max_bands) max_bands = it.n_bands;
+    if (it.n_pw > max_pw) max_pw = it.n_pw;
+  }
+  cudaError_t e = cudaSuccess;
+  const KptGeom* d_geoms = stage_descriptors(c, s, geoms, &e);
+  if (!d_geoms) return cuda_fail(c, e, "staging the batch descriptors");
+  const CosetCommon cc = c->coset;
   {
     KernelScope k(c, BANDUP_GPU_K_COSET, s);
-    launch_coset_classify(d_gfrac, n_pw, plan.cp, d_slot, d_slot_shift, ns_out, s);
+    launch_coset_classify(d_geoms, n, max_pw, cc, s);
   }
-  if (d_slot_out) CU(cudaMemcpyAsync(d_slot_out, d_slot, (size_t)n_pw, cudaMemcpyDeviceToDevice, s));
-  WeightsGeom g;
-  g.coeffs = static_cast<const char*>(d_coeffs);
-  g.stride_bytes = stride_bytes;
-  g.row_elems = (long long)n_pw * n_spinor;
-  g.n_bands = n_bands;
-  g.n_pw = n_pw;
-  g.n_spinor = n_spinor;
-  g.layout = layout;
-  g.slot = d_slot;
-  g.slot_shift = d_slot_shift;
-  g.n_fold = nu;
-  g.n_stages = 0;
-  g.chunk_vecs = weights_pick_chunk_vecs(c->chunk_vecs, g.row_elems, n_bands, c->sm_count);
-  g.n_chunks = weights_num_chunks(g.row_elems, g.chunk_vecs);
-  g.partials = d_partials;
   {
     KernelScope k(c, BANDUP_GPU_K_WEIGHTS, s);
-    launch_weights_reduce(g, c->ctas_per_sm, c->n_stages, c->sm_count, s);
+    launch_weights_reduce(d_geoms, n, tiles, max_fold, items[0].n_spinor, items[0].layout, c->ctas_per_sm,
+                          c->n_stages, c->sm_count, s);
   }
   {
     KernelScope k(c, BANDUP_GPU_K_FINALIZE, s);
-    launch_weights_finalize(d_partials, n_bands, g.n_chunks, nu, w_out, d_norms, s);
+    launch_weights_finalize(d_geoms, n, max_bands, max_fold, s);
   }
   {
     KernelScope k(c, BANDUP_GPU_K_DELTA_N, s);
-    launch_delta_n(static_cast<const double*>(c->d_grid.p), c->nener, c->sigma, d_energies,
-                   w_out, n_bands, nu, dn_out, s);
+    launch_delta_n(d_geoms, n, max_fold, static_cast<const double*>(c->d_grid.p), c->nener, c->sigma, s);
   }
   CU(cudaGetLastError());
-  if (dup) {  // replicate rows of pc-kpts that share a coset
-    for (int f = 0; f < n_fold; ++f) {
-      const int u = plan.unique_of[f];
-      CU(cudaMemcpyAsync(d_weights + (size_t)f * n_bands, w_out + (size_t)u * n_bands,
-                         sizeof(double) * n_bands, cudaMemcpyDeviceToDevice, s));
-      CU(cudaMemcpyAsync(d_dN + (size_t)f * c->nener, dn_out + (size_t)u * c->nener,
+  for (int i = 0; i < n; ++i) {
+    BatchItem& it = items[(size_t)i];
+    if (it.d_slot_out)
+      CU(cudaMemcpyAsync(it.d_slot_out, it.d_slot, (size_t)it.n_pw, cudaMemcpyDeviceToDevice, s));
+    if (it.plan.n_unique == it.n_fold) continue;
+    // replicate the rows of pc-kpts that share a coset
+    for (int f = 0; f < it.n_fold; ++f) {
+      const int u = it.plan.unique_of[f];
+      CU(cudaMemcpyAsync(it.d_weights + (size_t)f * it.n_bands, geoms[(size_t)i].weights + (size_t)u * it.n_bands,
+                         sizeof(double) * it.n_bands, cudaMemcpyDeviceToDevice, s));
+      CU(cudaMemcpyAsync(it.d_dN + (size_t)f * c->nener, it.dn_unique + (size_t)u * c->nener,
                          sizeof(double) * c->nener, cudaMemcpyDeviceToDevice, s));
-      CU(cudaMemcpyAsync(d_nsel + f, ns_out + u, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+      CU(cudaMemcpyAsync(it.d_nsel + f, it.ns_unique + u, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
     }
   }
   return BANDUP_GPU_OK;
@@ -464,6 +539,11 @@ int bandup_gpu_finalize(int handle) {
   }
   c->d_grid.release();
   c->d_operator.release();
+  for (auto& d : c->desc_ring) {
+    if (d.h) cudaFreeHost(d.h);
+    if (d.d) cudaFree(d.d);
+    if (d.ev) cudaEventDestroy(d.ev);
+  }
   if (c->copy) cudaStreamDestroy(c->copy);
   if (c->compute) cudaStreamDestroy(c->compute);
   delete c;
@@ -520,6 +600,10 @@ int bandup_gpu_set_cells(int handle, const double* B_sc_f, const double* b_pc_f,
   }
   coset_setup(c->M, c->coset.adjT, &c->coset.D);
   if (c->coset.D == 0) return fail(c, BANDUP_GPU_ERR_NOT_COMMENSURATE, "det M = 0");
+  for (int i = 0; i < 9; ++i) {
+    long long r = c->coset.adjT[i] % c->coset.D;
+    c->coset.adj32[i] = (unsigned)(r < 0 ? r + c->coset.D : r);
+  }
   if (c->coset.D > 2000000000LL) return fail(c, BANDUP_GPU_ERR_INT_OVERFLOW, "|det M| too large");
   c->cells_set = true;
   return BANDUP_GPU_OK;
@@ -612,13 +696,60 @@ int bandup_gpu_unfold_device(int handle, void* stream, int n_spinor, int n_pw, i
   if (!d_coeffs || !d_g_frac || !d_band_energies || !g0 || !d_weights || !d_dN || !d_n_selected ||
       !d_workspace)
     return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "NULL device pointer");
-  FoldPlan plan;
-  rc = plan_folds(c, n_fold, g0, &plan);
+  std::vector<BatchItem> items(1);
+  BatchItem& it = items[0];
+  rc = plan_folds(c, n_fold, g0, &it.plan);
   if (rc) return rc;
+  const WorkspaceLayout wl = workspace_layout(c, n_spinor, n_pw, n_bands, n_fold);
+  if (workspace_bytes < wl.total)
+    return fail(c, BANDUP_GPU_ERR_CAPACITY, "workspace too small: need " + std::to_string(wl.total) + " bytes");
+  it.n_spinor = n_spinor; it.n_pw = n_pw; it.n_bands = n_bands; it.layout = layout; it.n_fold = n_fold;
+  it.stride_bytes = band_stride_bytes;
+  it.d_coeffs = d_coeffs; it.d_gfrac = d_g_frac; it.d_energies = d_band_energies;
+  it.d_weights = d_weights; it.d_dN = d_dN; it.d_nsel = d_n_selected; it.d_norms = d_norms;
+  it.d_slot_out = d_slot_out;
+  it.ws = static_cast<char*>(d_workspace);
   cudaSetDevice(c->device);
-  return run_kpt(c, static_cast<cudaStream_t>(stream), n_spinor, n_pw, n_bands, layout,
-                 band_stride_bytes, d_coeffs, d_g_frac, d_band_energies, n_fold, plan, d_weights,
-                 d_dN, d_n_selected, d_norms, d_slot_out, d_workspace, workspace_bytes);
+  return run_batch(c, static_cast<cudaStream_t>(stream), items);
+}
+
+size_t bandup_gpu_batch_workspace_bytes(int handle, int n_kpts, const bandup_gpu_kpt_desc* descs) {
+  Ctx* c = get(handle);
+  if (!c || !descs || n_kpts < 1) return 0;
+  size_t total = 0;
+  for (int i = 0; i < n_kpts; ++i)
+    total += workspace_layout(c, descs[i].n_spinor, descs[i].n_pw, descs[i].n_bands, descs[i].n_fold).total;
+  return total;
+}
+
+int bandup_gpu_unfold_device_batch(int handle, void* stream, int n_kpts, const bandup_gpu_kpt_desc* descs,
+                                   void* d_workspace, size_t workspace_bytes) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (n_kpts < 1 || !descs || !d_workspace) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad batch arguments");
+  std::vector<BatchItem> items((size_t)n_kpts);
+  size_t off = 0;
+  for (int i = 0; i < n_kpts; ++i) {
+    const bandup_gpu_kpt_desc& d = descs[i];
+    int rc = check_shape(c, d.n_spinor, d.n_pw, d.n_bands, d.layout, d.band_stride_bytes);
+    if (rc) return rc;
+    if (!d.d_coeffs || !d.d_g_frac || !d.d_band_energies || !d.g0 || !d.d_weights || !d.d_dN || !d.d_n_selected)
+      return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "NULL pointer in batch descriptor " + std::to_string(i));
+    BatchItem& it = items[(size_t)i];
+    rc = plan_folds(c, d.n_fold, d.g0, &it.plan);
+    if (rc) return rc;
+    it.n_spinor = d.n_spinor; it.n_pw = d.n_pw; it.n_bands = d.n_bands; it.layout = d.layout; it.n_fold = d.n_fold;
+    it.stride_bytes = d.band_stride_bytes;
+    it.d_coeffs = d.d_coeffs; it.d_gfrac = d.d_g_frac; it.d_energies = d.d_band_energies;
+    it.d_weights = d.d_weights; it.d_dN = d.d_dN; it.d_nsel = d.d_n_selected; it.d_norms = d.d_norms;
+    it.d_slot_out = nullptr;
+    it.ws = static_cast<char*>(d_workspace) + off;
+    off += workspace_layout(c, d.n_spinor, d.n_pw, d.n_bands, d.n_fold).total;
+  }
+  if (off > workspace_bytes)
+    return fail(c, BANDUP_GPU_ERR_CAPACITY, "workspace too small: need " + std::to_string(off) + " bytes");
+  cudaSetDevice(c->device);
+  return run_batch(c, static_cast<cudaStream_t>(stream), items);
 }
 
 int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_bands, int layout,
@@ -630,7 +761,9 @@ int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_ba
   if (rc) return rc;
   if (!coeffs || !g_frac || !band_energies || !g0)
     return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "NULL host pointer");
-  FoldPlan plan;
+  std::vector<BatchItem> items(1);
+  BatchItem& it = items[0];
+  FoldPlan& plan = it.plan;
   rc = plan_folds(c, n_fold, g0, &plan);
   if (rc) return rc;
   for (auto& f : c->flights)
@@ -673,12 +806,20 @@ int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_ba
   CU(cudaEventRecord(fl.uploaded, c->copy));
   CU(cudaStreamWaitEvent(c->compute, fl.uploaded, 0));
 
-  rc = run_kpt(c, c->compute, n_spinor, n_pw, n_bands, layout, band_stride_bytes, fl.coeffs.p,
-               static_cast<const int32_t*>(fl.gfrac.p), static_cast<const double*>(fl.energies.p),
-               n_fold, plan, static_cast<double*>(fl.weights.p), static_cast<double*>(fl.dN.p),
-               static_cast<int32_t*>(fl.nsel.p), static_cast<double*>(fl.norms.p),
-               static_cast<uint8_t*>(fl.slot.p), fl.workspace.p, fl.workspace.cap, &fl.d_dn_unique,
-               &fl.d_ns_unique);
+  it.n_spinor = n_spinor; it.n_pw = n_pw; it.n_bands = n_bands; it.layout = layout; it.n_fold = n_fold;
+  it.stride_bytes = band_stride_bytes;
+  it.d_coeffs = fl.coeffs.p;
+  it.d_gfrac = static_cast<const int32_t*>(fl.gfrac.p);
+  it.d_energies = static_cast<const double*>(fl.energies.p);
+  it.d_weights = static_cast<double*>(fl.weights.p);
+  it.d_dN = static_cast<double*>(fl.dN.p);
+  it.d_nsel = static_cast<int32_t*>(fl.nsel.p);
+  it.d_norms = static_cast<double*>(fl.norms.p);
+  it.d_slot_out = static_cast<uint8_t*>(fl.slot.p);
+  it.ws = static_cast<char*>(fl.workspace.p);
+  rc = run_batch(c, c->compute, items);
+  fl.d_dn_unique = it.dn_unique;
+  fl.d_ns_unique = it.ns_unique;
   if (rc) return rc;
   CU(cudaMemcpyAsync(fl.h_weights.p, fl.weights.p, sizeof(double) * (size_t)n_fold * n_bands, cudaMemcpyDeviceToHost, c->compute));
   CU(cudaMemcpyAsync(fl.h_dN.p, fl.dN.p, sizeof(double) * (size_t)n_fold * c->nener, cudaMemcpyDeviceToHost, c->compute));

@@ -17,41 +17,67 @@ __device__ __forceinline__ int pos_mod(long long v, long long D) {
   return (int)(r < 0 ? r + D : r);
 }
 
+// grid (CTAs per k-point <= kK1MaxBlocks, n_kpts).  Every CTA leaves its per-fold plane-wave
+// counts in block_counts[blockIdx.x][*]; K2b adds the rows up (fixed order, no atomics on
+// global memory, nothing to zero beforehand).
 __global__ void __launch_bounds__(256)
-k1_coset_classify(const int32_t* __restrict__ g_frac, int n_pw, CosetParams cp,
-                  uint8_t* __restrict__ slot, uint8_t* __restrict__ slot_shift,
-                  int32_t* __restrict__ n_selected) {
+k1_coset_classify(const KptGeom* __restrict__ geoms, CosetCommon cc) {
+  const KptGeom& g = geoms[blockIdx.y];
   __shared__ int s_count[kMaxFolds];
-  for (int f = threadIdx.x; f < cp.n_fold; f += blockDim.x) s_count[f] = 0;
-  __syncthreads();
-
-  const int stride = gridDim.x * blockDim.x;
-  for (int pw = blockIdx.x * blockDim.x + threadIdx.x; pw < n_pw; pw += stride) {
-    const long long g1 = g_frac[3 * pw], g2 = g_frac[3 * pw + 1], g3 = g_frac[3 * pw + 2];
-    const int k0 = pos_mod(g1 * cp.adjT[0] + g2 * cp.adjT[3] + g3 * cp.adjT[6], cp.D);
-    const int k1 = pos_mod(g1 * cp.adjT[1] + g2 * cp.adjT[4] + g3 * cp.adjT[7], cp.D);
-    const int k2 = pos_mod(g1 * cp.adjT[2] + g2 * cp.adjT[5] + g3 * cp.adjT[8], cp.D);
-    int s = kNoFold;
-    for (int f = cp.n_fold - 1; f >= 0; --f)  // descending so the FIRST match wins
-      if (cp.fold_key[f][0] == k0 && cp.fold_key[f][1] == k1 && cp.fold_key[f][2] == k2) s = f;
-    slot[pw] = (uint8_t)s;
-    if (pw > 0) slot_shift[pw - 1] = (uint8_t)s;
-    if (pw == n_pw - 1) slot_shift[pw] = kNoFold;
-    if (s != kNoFold) atomicAdd(&s_count[s], 1);
+  __shared__ int s_key[kMaxFolds][3];
+  const int n_fold = g.n_fold;
+  for (int f = threadIdx.x; f < n_fold; f += blockDim.x) {
+    s_count[f] = 0;
+    s_key[f][0] = g.fold_key[f][0];
+    s_key[f][1] = g.fold_key[f][1];
+    s_key[f][2] = g.fold_key[f][2];
   }
   __syncthreads();
-  for (int f = threadIdx.x; f < cp.n_fold; f += blockDim.x)
-    if (s_count[f]) atomicAdd(&n_selected[f], s_count[f]);
+
+  const int n_pw = g.n_pw;
+  const int32_t* __restrict__ g_frac = g.g_frac;
+  uint8_t* __restrict__ slot = g.slot;
+  uint8_t* __restrict__ slot_shift = g.slot_shift;
+  const int stride = gridDim.x * blockDim.x;
+  // |det M| < 2^15 (always, in practice): everything fits 32-bit unsigned arithmetic once the
+  // Miller indices and the adjugate are reduced mod D (3 * (D-1)^2 < 2^32); same residues.
+  const bool small = cc.D < 32768;
+  const int D32 = (int)cc.D;
+  const unsigned* a32 = cc.adj32;
+  for (int pw = blockIdx.x * blockDim.x + threadIdx.x; pw < n_pw; pw += stride) {
+    int k0, k1, k2;
+    if (small) {
+      int r1 = g_frac[3 * pw] % D32, r2 = g_frac[3 * pw + 1] % D32, r3 = g_frac[3 * pw + 2] % D32;
+      const unsigned u1 = (unsigned)(r1 < 0 ? r1 + D32 : r1), u2 = (unsigned)(r2 < 0 ? r2 + D32 : r2),
+                     u3 = (unsigned)(r3 < 0 ? r3 + D32 : r3);
+      k0 = (int)((u1 * a32[0] + u2 * a32[3] + u3 * a32[6]) % (unsigned)D32);
+      k1 = (int)((u1 * a32[1] + u2 * a32[4] + u3 * a32[7]) % (unsigned)D32);
+      k2 = (int)((u1 * a32[2] + u2 * a32[5] + u3 * a32[8]) % (unsigned)D32);
+    } else {
+      const long long g1 = g_frac[3 * pw], g2 = g_frac[3 * pw + 1], g3 = g_frac[3 * pw + 2];
+      k0 = pos_mod(g1 * cc.adjT[0] + g2 * cc.adjT[3] + g3 * cc.adjT[6], cc.D);
+      k1 = pos_mod(g1 * cc.adjT[1] + g2 * cc.adjT[4] + g3 * cc.adjT[7], cc.D);
+      k2 = pos_mod(g1 * cc.adjT[2] + g2 * cc.adjT[5] + g3 * cc.adjT[8], cc.D);
+    }
+    int q = kNoFold;
+    for (int f = n_fold - 1; f >= 0; --f)  // folds are distinct cosets: at most one matches
+      if (s_key[f][0] == k0 && s_key[f][1] == k1 && s_key[f][2] == k2) q = f;
+    slot[pw] = (uint8_t)q;
+    if (pw > 0) slot_shift[pw - 1] = (uint8_t)q;
+    if (pw == n_pw - 1) slot_shift[pw] = kNoFold;
+    if (q != kNoFold) atomicAdd(&s_count[q], 1);  // shared-memory integer count: order-free
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < n_fold; f += blockDim.x)
+    g.block_counts[blockIdx.x * n_fold + f] = s_count[f];
 }
 
-void launch_coset_classify(const int32_t* d_g_frac, int n_pw, const CosetParams& cp,
-                           uint8_t* d_slot, uint8_t* d_slot_shift, int32_t* d_n_selected,
+void launch_coset_classify(const KptGeom* d_geoms, int n_kpts, int max_n_pw, const CosetCommon& cc,
                            cudaStream_t s) {
-  cudaMemsetAsync(d_n_selected, 0, sizeof(int32_t) * cp.n_fold, s);
-  if (n_pw <= 0) return;
-  int blocks = (n_pw + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  k1_coset_classify<<<blocks, 256, 0, s>>>(d_g_frac, n_pw, cp, d_slot, d_slot_shift, d_n_selected);
+  if (n_kpts <= 0 || max_n_pw <= 0) return;
+  // always kK1MaxBlocks rows of counts so that K2b can add them up without knowing n_pw
+  dim3 grid((unsigned)kK1MaxBlocks, (unsigned)n_kpts);
+  k1_coset_classify<<<grid, 256, 0, s>>>(d_geoms, cc);
 }
 
 // One CTA per fold walks the slot table in order and writes the 1-based indices

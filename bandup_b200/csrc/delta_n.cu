@@ -20,6 +20,7 @@
 // staged through shared memory in tiles (a dependent global load per band made the first
 // version latency-bound: 38 us for 3000 bands), lanes stride over the bands and a shuffle
 // tree combines them (fixed order: deterministic).  Work is tiny next to K2.
+// Candidate bands are compacted first and their lambdas evaluated one per lane (see the kernel).
 #include "kernels.cuh"
 
 namespace bandup {
@@ -39,15 +40,19 @@ __device__ __forceinline__ double lambda_box_erf(double pc_ener, double sc_ener,
 constexpr int kK3Threads = 256;   // 8 warps = 8 energy bins of one fold per CTA
 constexpr int kK3BandTile = 2048;  // band energies staged in shared memory per pass
 
+// grid (ceil(nener/8) * max_n_fold, n_kpts)
 __global__ void __launch_bounds__(kK3Threads)
-k3_delta_n(const double* __restrict__ grid, int nener, double sigma,
-           const double* __restrict__ band_energies, const double* __restrict__ weights,
-           int n_bands, int n_fold, double* __restrict__ dN) {
+k3_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict__ grid, int nener, double sigma) {
   __shared__ double s_ener[kK3BandTile];
+  __shared__ int s_hit[kK3Threads / 32][64];
+  const KptGeom& g = geoms[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bins_per_cta = kK3Threads / 32;
   const int ctas_per_fold = (nener + bins_per_cta - 1) / bins_per_cta;
   const int f = blockIdx.x / ctas_per_fold;
+  if (f >= g.n_fold) return;
+  const int n_bands = g.n_bands;
+  const double* __restrict__ band_energies = g.energies;
   const int ie = (blockIdx.x - f * ctas_per_fold) * bins_per_cta + warp;
   const bool live = ie < nener;
   // delta_e = energies(2) - energies(1)  (:735)
@@ -55,39 +60,60 @@ k3_delta_n(const double* __restrict__ grid, int nener, double sigma,
   const double half_de = __dmul_rn(0.5, delta_e);
   const double sqrt2_sigma = __dmul_rn(sqrt(2.0), sigma);
   const double E = live ? grid[ie] : 0.0;
-  const double* w = weights + (long long)f * n_bands;
+  const double* w = g.weights + (long long)f * n_bands;
   const double reach = half_de + 8.0 * sqrt2_sigma;
   const double guard = reach + 1e-9 * (fabs(E) + reach);
+  int* hits = s_hit[warp];
+  int n_hit = 0;  // warp-uniform
   double acc = 0.0;
+  // The few bands that can contribute (|E_m - E_i| within the guard band) are first collected,
+  // in ascending band order, then lambda (two erf, two divisions) is evaluated for up to 32 of
+  // them at once, one per lane -- instead of one after the other inside a divergent loop.
+  auto flush = [&](int count) {
+    if (lane < count) {
+      const int m = hits[lane];
+      const double lam = lambda_box_erf(E, band_energies[m], half_de, sqrt2_sigma);
+      if (lam != 0.0) acc = __dadd_rn(acc, __dmul_rn(w[m], lam));
+    }
+    __syncwarp();
+  };
   for (int m0 = 0; m0 < n_bands; m0 += kK3BandTile) {
     const int nt = min(kK3BandTile, n_bands - m0);
     __syncthreads();
     for (int i = threadIdx.x; i < nt; i += kK3Threads) s_ener[i] = band_energies[m0 + i];
     __syncthreads();
     if (!live) continue;
-    // bands are visited in ascending order by every lane: lane l takes m = l, l+32, ...
-    for (int i = lane; i < nt; i += 32) {
-      const double Em = s_ener[i];
-      if (fabs(Em - E) > guard) continue;  // both erf saturated on the same side: term is exactly 0
-      const double lam = lambda_box_erf(E, Em, half_de, sqrt2_sigma);
-      if (lam != 0.0) acc = __dadd_rn(acc, __dmul_rn(w[m0 + i], lam));
+    for (int i0 = 0; i0 < nt; i0 += 32) {
+      const int i = i0 + lane;
+      const bool hit = i < nt && !(fabs(s_ener[i] - E) > guard);
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (bal == 0u) continue;
+      if (hit) hits[n_hit + __popc(bal & ((1u << lane) - 1u))] = m0 + i;
+      n_hit += __popc(bal);
+      __syncwarp();
+      if (n_hit >= 32) {
+        flush(32);
+        if (lane < n_hit - 32) hits[lane] = hits[32 + lane];
+        n_hit -= 32;
+        __syncwarp();
+      }
     }
   }
+  if (live && n_hit > 0) flush(n_hit);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-  if (live && lane == 0) dN[(long long)f * nener + ie] = acc;
+  if (live && lane == 0) g.dN[(long long)f * nener + ie] = acc;
 }
 
 }  // namespace
 
-void launch_delta_n(const double* d_grid, int nener, double sigma,
-                    const double* d_band_energies, const double* d_weights,
-                    int n_bands, int n_fold, double* d_dN, cudaStream_t s) {
-  if (nener <= 0 || n_fold <= 0) return;
+void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const double* d_grid,
+                    int nener, double sigma, cudaStream_t s) {
+  if (nener <= 0 || max_n_fold <= 0 || n_kpts <= 0) return;
   const int bins_per_cta = kK3Threads / 32;
   const int ctas_per_fold = (nener + bins_per_cta - 1) / bins_per_cta;
-  k3_delta_n<<<(unsigned)(ctas_per_fold * n_fold), kK3Threads, 0, s>>>(
-      d_grid, nener, sigma, d_band_energies, d_weights, n_bands, n_fold, d_dN);
+  dim3 grid((unsigned)(ctas_per_fold * max_n_fold), (unsigned)n_kpts);
+  k3_delta_n<<<grid, kK3Threads, 0, s>>>(d_geoms, d_grid, nener, sigma);
 }
 
 }  // namespace bandup

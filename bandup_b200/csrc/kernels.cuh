@@ -16,43 +16,52 @@ constexpr uint8_t kNoFold = 255;  // slot id of a plane wave no requested pc-kpt
 // differ by a pc reciprocal-lattice vector iff their keys are equal
 // (pc vectors in SC Miller coordinates are the rows of transpose(M), so
 // g = n.M^T has integer n iff g.adj(M^T) = 0 mod det M).
-struct CosetParams {
-  long long adjT[9];        // adjugate of transpose(M), row-major
-  long long D;              // |det M|
+struct CosetCommon {
+  long long adjT[9];   // adjugate of transpose(M), row-major
+  long long D;         // |det M|
+  unsigned adj32[9];   // adjT mod D in [0, D), valid when D < 2^15 (32-bit fast path of K1)
+};
+
+constexpr int kK1MaxBlocks = 128;  // CTAs of K1 per SC-kpt (each leaves one row of counts)
+
+// One SC k-point of a batch: the device-resident descriptor every kernel indexes with
+// blockIdx.y (K1, K2b, K3) or finds from the global tile index (K2).  "fold" here means a
+// DISTINCT coset among the pc-kpts folding onto the SC-kpt (the host replicates rows of
+// pc-kpts that share one).
+struct KptGeom {
+  const char* coeffs;         // first band record
+  long long stride_bytes;     // distance between band records
+  long long row_elems;        // n_pw * n_spinor complex64 per band
+  int n_bands, n_pw, n_spinor, layout;
+  const int32_t* g_frac;      // [n_pw][3]
+  const double* energies;     // [n_bands]
+  uint8_t* slot;              // [n_pw], 2-byte aligned: fold id of every plane wave, kNoFold = none
+  uint8_t* slot_shift;        // [n_pw], slot_shift[i] = slot[i+1]
+  int* block_counts;          // [kK1MaxBlocks][n_fold] plane waves per fold seen by each K1 CTA
+  int32_t* n_selected;        // [n_fold]
   int n_fold;
-  int fold_key[kMaxFolds][3];  // key(g0) of every requested pc-kpt
+  int chunk_vecs;             // 16-byte vectors per K2 tile (a multiple of the 1024-vector stage)
+  int n_chunks;               // tiles per band
+  long long tile_begin;       // global index of this k-point's first K2 tile
+  double* partials;           // [n_bands][n_chunks][n_fold+1]; [..][0] = norm part
+  double* weights;            // [n_fold][n_bands]
+  double* norms;              // [n_bands] or null
+  double* dN;                 // [n_fold][nener]
+  int fold_key[kMaxFolds][3]; // key(g0) of every fold
 };
 
 // K1 -- coset classification (replaces the vec_in_latt sweep of
 // select_coeffs_to_calc_spectral_weights, band_unfolding_routines_mod.f90:586-600).
-// slot[pw] = index of the first fold whose coset contains G(pw), else kNoFold;
-// n_selected[f] = number of plane waves of fold f (must be zeroed by the caller,
-// launch_coset_classify does it).
-// d_slot_shift[pw] = slot[pw+1] (kNoFold past the end): lets K2 fetch the two slot ids of
-// a 16-byte vector with one aligned 16-bit load whatever the row's alignment.
-void launch_coset_classify(const int32_t* d_g_frac, int n_pw, const CosetParams& cp,
-                           uint8_t* d_slot, uint8_t* d_slot_shift, int32_t* d_n_selected,
+// slot[pw] = index of the fold whose coset contains G(pw), else kNoFold; slot_shift lets K2
+// fetch the two slot ids of a 16-byte vector with one aligned 16-bit load whatever the row's
+// alignment.  Per-CTA fold counts go to block_counts (summed by K2b: no atomics, no memset).
+void launch_coset_classify(const KptGeom* d_geoms, int n_kpts, int max_n_pw, const CosetCommon& cc,
                            cudaStream_t s);
 
 // Ordered compaction of the 1-based selected indices of every fold (CSR).
-// d_offsets[f] = exclusive prefix of n_selected, computed on device.
 void launch_selected_lists(const uint8_t* d_slot, int n_pw, int n_fold,
                            const int32_t* d_n_selected, int32_t* d_selected,
                            cudaStream_t s);
-
-struct WeightsGeom {
-  const char* coeffs;      // device, first band record
-  long long stride_bytes;  // distance between band records
-  long long row_elems;     // n_pw * n_spinor complex64 per band
-  int n_bands, n_pw, n_spinor, layout;
-  const uint8_t* slot;        // [n_pw], 2-byte aligned
-  const uint8_t* slot_shift;  // [n_pw], slot_shift[i] = slot[i+1], 2-byte aligned
-  int n_fold;
-  int chunk_vecs;          // 16-byte vectors per tile (a multiple of the 1024-vector stage)
-  int n_chunks;            // tiles per band
-  int n_stages;            // shared-memory ring depth (set by the launcher)
-  double* partials;        // [n_bands][n_chunks][n_fold+1]; [..][0] = norm part
-};
 
 int weights_num_chunks(long long row_elems, int chunk_vecs);
 size_t weights_partials_bytes(int n_bands, int n_chunks, int n_fold);
@@ -60,26 +69,25 @@ size_t weights_partials_bytes(int n_bands, int n_chunks, int n_fold);
 int weights_pick_chunk_vecs(int requested, long long row_elems, int n_bands, int sm_count);
 int weights_max_folds_supported();
 
-// K2 -- the roofline kernel: one pass over every complex64 coefficient of the
-// k-point; per (band, chunk) tile the band-norm part and the per-fold masked
-// |C|^2 sums.  Fuses io_routines_mod.f90:1317-1330 (norm) with
-// band_unfolding_routines_mod.f90:638-644 and :1337-1345 (weights, spinor sum).
-void launch_weights_reduce(const WeightsGeom& g, int ctas_per_sm, int n_stages, int sm_count,
+// K2 -- the roofline kernel: one pass over every complex64 coefficient of every k-point of
+// the batch; per (band, chunk) tile the band-norm part and the per-fold masked |C|^2 sums.
+// Fuses io_routines_mod.f90:1317-1330 (norm) with band_unfolding_routines_mod.f90:638-644 and
+// :1337-1345 (weights, spinor sum).  All k-points of a batch share n_spinor and layout.
+void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int max_n_fold,
+                           int n_spinor, int layout, int ctas_per_sm, int n_stages, int sm_count,
                            cudaStream_t s);
 
 // K2b -- deterministic tile combine: s = sum_c norm part, S_f = sum_c fold part,
 // weights[f][b] = s > eps ? S_f / s : S_f (the reference leaves a band with
-// s <= epsilon unscaled, io_routines_mod.f90:1325).
-void launch_weights_finalize(const double* d_partials, int n_bands, int n_chunks,
-                             int n_fold, double* d_weights, double* d_norms,
+// s <= epsilon unscaled, io_routines_mod.f90:1325); also n_selected = sum of K1's CTA counts.
+void launch_weights_finalize(const KptGeom* d_geoms, int n_kpts, int max_bands, int max_n_fold,
                              cudaStream_t s);
 
 // K3 -- delta_N(k, E_i) = sum_m P_m * lambda(E_i; E_m, delta_e, sigma)
 // (calc_delta_N_pckpt, band_unfolding_routines_mod.f90:719-757, with lambda :701-716
 // and integral_delta_x_minus_x0, math_mod.f90:181-193).
-void launch_delta_n(const double* d_grid, int nener, double sigma,
-                    const double* d_band_energies, const double* d_weights,
-                    int n_bands, int n_fold, double* d_dN, cudaStream_t s);
+void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const double* d_grid,
+                    int nener, double sigma, cudaStream_t s);
 
 // ---- projected variant (rho.cu) ----------------------------------------------
 struct RhoPair {  // one upper-triangle element of an unfolding-density operator

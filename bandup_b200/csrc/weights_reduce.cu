@@ -97,7 +97,8 @@ __device__ __forceinline__ int pw_of(long long e, int n_pw) {
   return (int)(e >= n_pw ? e - n_pw : e);
 }
 
-struct TileGeom {  // where one (chunk, band) tile lies
+struct TileGeom {  // where one (k-point, chunk, band) tile lies
+  const KptGeom* g;
   const char* row;     // first byte of the band record
   int e_al;            // 1 when the row starts 8 bytes before a 16-byte boundary
   long long nvb;       // whole aligned 16-byte vectors in the row
@@ -105,55 +106,131 @@ struct TileGeom {  // where one (chunk, band) tile lies
   int band, chunk;
 };
 
-__device__ __forceinline__ TileGeom tile_geom(const WeightsGeom& g, long long tile) {
+// Tiles are numbered k-point-major, then chunk-major, then band: the CTAs resident together
+// work on the same stretch of one k-point's slot table.  `k` is a cursor: a CTA's tile indices
+// only grow, so the k-point is found by stepping forward.
+__device__ __forceinline__ TileGeom tile_geom(const KptGeom* __restrict__ geoms, int n_kpts, int& k,
+                                              long long tile) {
+  while (k + 1 < n_kpts && tile >= geoms[k + 1].tile_begin) ++k;
+  const KptGeom* g = geoms + k;
+  const long long local = tile - g->tile_begin;
   TileGeom t;
-  t.chunk = (int)(tile / g.n_bands);
-  t.band = (int)(tile - (long long)t.chunk * g.n_bands);
-  t.row = g.coeffs + (long long)t.band * g.stride_bytes;
+  t.g = g;
+  t.chunk = (int)(local / g->n_bands);
+  t.band = (int)(local - (long long)t.chunk * g->n_bands);
+  t.row = g->coeffs + (long long)t.band * g->stride_bytes;
   t.e_al = (int)((reinterpret_cast<unsigned long long>(t.row) >> 3) & 1ull);
-  t.nvb = (g.row_elems - t.e_al) >> 1;
-  t.j0 = (long long)t.chunk * g.chunk_vecs;
-  t.j1 = t.j0 + g.chunk_vecs;
+  t.nvb = (g->row_elems - t.e_al) >> 1;
+  t.j0 = (long long)t.chunk * g->chunk_vecs;
+  t.j1 = t.j0 + g->chunk_vecs;
   if (t.j1 > t.nvb) t.j1 = t.nvb;
   if (t.j0 > t.j1) t.j0 = t.j1;
   return t;
 }
 
-// slot ids of the two row elements (e, e+1) held by one 16-byte vector
+// Where the consumers find the slot ids of a tile's vectors (hoisted out of the stage loop:
+// the descriptor lives in global memory and the mbarrier asm statements are memory clobbers).
+struct SlotSrc {
+  const uint16_t* tab16;  // MODE 0: slot[] (16-byte aligned rows) or slot_shift[] (rows off by 8 bytes)
+  const uint8_t* slot;
+  int n_pw;
+  int e_al;
+};
+
 template <int MODE>
-__device__ __forceinline__ void slot_pair(const WeightsGeom& g, int e_al, long long J, unsigned& sa,
-                                          unsigned& sb) {
+__device__ __forceinline__ SlotSrc make_slot_src(const KptGeom& g, int e_al) {
+  SlotSrc ss;
+  ss.slot = g.slot;
+  ss.tab16 = reinterpret_cast<const uint16_t*>(e_al ? g.slot_shift : g.slot);
+  ss.n_pw = g.n_pw;
+  ss.e_al = e_al;
+  return ss;
+}
+
+// slot ids of the two row elements (e, e+1) held by 16-byte vector J of the row, packed
+// sa | sb << 8 (0xFFFF = neither is needed by any fold)
+template <int MODE>
+__device__ __forceinline__ unsigned slot_pair(const SlotSrc& ss, int J) {
   if (MODE == 0) {
-    // slot[] for rows that start on a 16-byte boundary, slot_shift[] (= slot[i+1]) otherwise:
     // either way ONE aligned 16-bit load
-    const uint16_t* tab = reinterpret_cast<const uint16_t*>(e_al ? g.slot_shift : g.slot);
-    const unsigned s = __ldg(tab + J);
-    sa = s & 0xffu;
-    sb = s >> 8;
-  } else if (MODE == 1 && e_al == 0) {
-    sa = sb = __ldg(g.slot + J);
+    return __ldg(ss.tab16 + J);
+  } else if (MODE == 1 && ss.e_al == 0) {
+    const unsigned q = __ldg(ss.slot + J);
+    return q | (q << 8);
   } else {
-    const long long e = e_al + 2 * J;
-    sa = __ldg(g.slot + pw_of<MODE>(e, g.n_pw));
-    sb = __ldg(g.slot + pw_of<MODE>(e + 1, g.n_pw));
+    const long long e = ss.e_al + 2LL * J;
+    const unsigned sa = __ldg(ss.slot + pw_of<MODE>(e, ss.n_pw));
+    const unsigned sb = __ldg(ss.slot + pw_of<MODE>(e + 1, ss.n_pw));
+    return sa | (sb << 8);
+  }
+}
+
+// One 16 KB stage: slot ids (L1/L2) are requested before the wait so they overlap it; the
+// stage is handed back to the producer as soon as its four vectors sit in registers.
+// FULL = all 1024 vectors present (no bounds checks in the hot path).
+template <int MODE, bool FULL>
+__device__ __forceinline__ void consume_stage(const float4* __restrict__ sv, uint64_t* full, uint64_t* empty,
+                                              uint32_t phase, const SlotSrc& ss, int j, int nv, int tid,
+                                              int lane, unsigned nf, double* __restrict__ bins,
+                                              double& nrm) {
+  unsigned sl[kVecPerThread];
+  float4 v[kVecPerThread];
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    const int i = tid + u * kConsumers;
+    sl[u] = (FULL || i < nv) ? slot_pair<MODE>(ss, j + i) : 0xFFFFu;
+  }
+  mbar_wait(full, phase);
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    const int i = tid + u * kConsumers;
+    v[u] = (FULL || i < nv) ? sv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty);
+
+  // |C|^2 in fp32 (the reference's abs() of a complex(sp) is fp32).  The band norm takes the
+  // eight terms of this stage as one short fp32 run promoted to fp64 (relative error of a run
+  // ~1e-7, of the whole norm ~1e-9); the coset bins take every selected term widened to fp64.
+  float p[2 * kVecPerThread];
+  float run = 0.f;
+  unsigned all = 0xFFFFu;
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    p[2 * u] = fmaf(v[u].y, v[u].y, v[u].x * v[u].x);
+    p[2 * u + 1] = fmaf(v[u].w, v[u].w, v[u].z * v[u].z);
+    run += p[2 * u];
+    run += p[2 * u + 1];
+    all &= sl[u];
+  }
+  nrm += (double)run;
+  if (all != 0xFFFFu) {  // some element of this thread's vectors belongs to a requested coset
+#pragma unroll
+    for (int u = 0; u < kVecPerThread; ++u) {
+      if (sl[u] != 0xFFFFu) {  // a real branch per vector: with det(M) in the hundreds most warps skip it
+        const unsigned sa = sl[u] & 0xFFu, sb = sl[u] >> 8;
+        if (sa < nf) bins[sa * kConsumers + tid] += (double)p[2 * u];
+        if (sb < nf) bins[sb * kConsumers + tid] += (double)p[2 * u + 1];
+      }
+    }
   }
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 3)
-k2_weights_reduce(WeightsGeom g) {
+k2_weights_reduce(const KptGeom* __restrict__ geoms, int n_kpts, long long total_tiles, int max_n_fold,
+                  int n_stages) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [n_stages][16 KB] | bins [n_fold][256] f64 | wpart [(n_fold+1)][8] f64 | barriers
+  // layout: [n_stages][16 KB] | acc [max_n_fold+1][256] f64 (row 0: norm, row f+1: fold f) | barriers
   float4* stage_base = reinterpret_cast<float4*>(smem_raw);
-  double* bins = reinterpret_cast<double*>(smem_raw + (size_t)g.n_stages * kStageBytes);
-  double* wpart = bins + (size_t)g.n_fold * kConsumers;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(wpart + (size_t)(g.n_fold + 1) * (kConsumers / 32));
+  double* acc = reinterpret_cast<double*>(smem_raw + (size_t)n_stages * kStageBytes);
+  double* bins = acc + kConsumers;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(acc + (size_t)(max_n_fold + 1) * kConsumers);
   uint64_t* empty_bar = full_bar + kMaxStages;
 
   const int tid = threadIdx.x;
-  const long long total_tiles = (long long)g.n_bands * g.n_chunks;
   if (tid == 0) {
-    for (int s = 0; s < g.n_stages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar + s, 1);                  // producer's expect_tx arrive
       mbar_init(empty_bar + s, kConsumers / 32);   // one arrive per consumer warp
     }
@@ -165,10 +242,10 @@ k2_weights_reduce(WeightsGeom g) {
     // ------------------------------ producer ------------------------------
     if (tid == kConsumers) {
       const uint64_t policy = l2_evict_first_policy();
-      int s = 0;
+      int s = 0, k = 0;
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileGeom t = tile_geom(g, tile);
+        const TileGeom t = tile_geom(geoms, n_kpts, k, tile);
         const char* src = t.row + 8 * t.e_al;
         for (long long j = t.j0; j < t.j1; j += kStageVecs) {
           const long long nv = (t.j1 - j < kStageVecs) ? (t.j1 - j) : kStageVecs;
@@ -176,7 +253,7 @@ k2_weights_reduce(WeightsGeom g) {
           mbar_expect_tx(full_bar + s, (uint32_t)(nv * 16));
           bulk_g2s(stage_base + (size_t)s * kStageVecs, src + j * 16, (uint32_t)(nv * 16), full_bar + s,
                    policy);
-          if (++s == g.n_stages) {
+          if (++s == n_stages) {
             s = 0;
             phase ^= 1u;
           }
@@ -188,149 +265,135 @@ k2_weights_reduce(WeightsGeom g) {
 
   // -------------------------------- consumers --------------------------------
   const int lane = tid & 31, warp = tid >> 5;
-  const int nslots = g.n_fold + 1;
-  const unsigned nf = (unsigned)g.n_fold;
-  int s = 0;
+  int s = 0, k = 0;
   uint32_t phase = 0;
   for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const TileGeom t = tile_geom(g, tile);
-    for (int f = 0; f < g.n_fold; ++f) bins[f * kConsumers + tid] = 0.0;
+    const TileGeom t = tile_geom(geoms, n_kpts, k, tile);
+    const KptGeom& g = *t.g;
+    const int n_fold = g.n_fold;
+    const unsigned nf = (unsigned)n_fold;
+    const SlotSrc ss = make_slot_src<MODE>(g, t.e_al);
+    const int j0 = (int)t.j0, j1 = (int)t.j1;  // vectors per row < 2^31
+    for (int f = 0; f < n_fold; ++f) bins[f * kConsumers + tid] = 0.0;
     double nrm = 0.0;
 
-    for (long long j = t.j0; j < t.j1; j += kStageVecs) {
-      const int nv = (int)((t.j1 - j < kStageVecs) ? (t.j1 - j) : kStageVecs);
-      const float4* sv = stage_base + (size_t)s * kStageVecs;
-      float4 v[kVecPerThread];
-      unsigned sa[kVecPerThread], sb[kVecPerThread];
-      // slot ids first: they come from L1/L2 and overlap the wait for the stage
-#pragma unroll
-      for (int u = 0; u < kVecPerThread; ++u) {
-        const int i = tid + u * kConsumers;
-        if (i < nv) {
-          slot_pair<MODE>(g, t.e_al, j + i, sa[u], sb[u]);
-        } else {
-          sa[u] = sb[u] = kNoFold;
-        }
-      }
-      mbar_wait(full_bar + s, phase);
-#pragma unroll
-      for (int u = 0; u < kVecPerThread; ++u) {
-        const int i = tid + u * kConsumers;
-        v[u] = (i < nv) ? sv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      // all of this warp's reads of the stage are done: hand it back to the producer
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar + s);
-      if (++s == g.n_stages) {
+    int j = j0;
+    for (; j + kStageVecs <= j1; j += kStageVecs) {
+      consume_stage<MODE, true>(stage_base + (size_t)s * kStageVecs, full_bar + s, empty_bar + s, phase, ss, j,
+                                kStageVecs, tid, lane, nf, bins, nrm);
+      if (++s == n_stages) {
         s = 0;
         phase ^= 1u;
       }
-#pragma unroll
-      for (int u = 0; u < kVecPerThread; ++u) {
-        const float pa = fmaf(v[u].y, v[u].y, v[u].x * v[u].x);
-        const float pb = fmaf(v[u].w, v[u].w, v[u].z * v[u].z);
-        // the SAME fp32 |C|^2 feeds the norm and the coset bins, each widened to
-        // fp64 before it is added: sum over all cosets of S == s to fp64 rounding
-        nrm += (double)pa;
-        nrm += (double)pb;
-        if (sa[u] < nf) bins[sa[u] * kConsumers + tid] += (double)pa;
-        if (sb[u] < nf) bins[sb[u] * kConsumers + tid] += (double)pb;
+    }
+    if (j < j1) {  // last, partial stage of a row
+      consume_stage<MODE, false>(stage_base + (size_t)s * kStageVecs, full_bar + s, empty_bar + s, phase, ss, j,
+                                 j1 - j, tid, lane, nf, bins, nrm);
+      if (++s == n_stages) {
+        s = 0;
+        phase ^= 1u;
       }
     }
 
     // row head / tail elements that do not fill an aligned vector
     if (tid == 0) {
       const float2* el = reinterpret_cast<const float2*>(t.row);
-      if (t.chunk == 0 && t.e_al == 1 && g.row_elems > 0) {
+      const long long row_elems = g.row_elems;
+      if (t.chunk == 0 && t.e_al == 1 && row_elems > 0) {
         const float2 c = el[0];
         const float p = fmaf(c.y, c.y, c.x * c.x);
         nrm += (double)p;
-        const unsigned q = g.slot[pw_of<MODE>(0, g.n_pw)];
+        const unsigned q = ss.slot[pw_of<MODE>(0, ss.n_pw)];
         if (q < nf) bins[q * kConsumers] += (double)p;
       }
       const long long e_tail = t.e_al + 2 * t.nvb;
-      if (t.chunk == g.n_chunks - 1 && e_tail < g.row_elems) {
+      if (t.chunk == g.n_chunks - 1 && e_tail < row_elems) {
         const float2 c = el[e_tail];
         const float p = fmaf(c.y, c.y, c.x * c.x);
         nrm += (double)p;
-        const unsigned q = g.slot[pw_of<MODE>(e_tail, g.n_pw)];
+        const unsigned q = ss.slot[pw_of<MODE>(e_tail, ss.n_pw)];
         if (q < nf) bins[q * kConsumers] += (double)p;
       }
     }
 
-    // tile reduction: warp shuffles, then the warps' partials through smem
-    {
-      const double w = warp_sum(nrm);
-      if (lane == 0) wpart[warp] = w;
-    }
-    for (int f = 0; f < g.n_fold; ++f) {
-      const double w = warp_sum(bins[f * kConsumers + tid]);
-      if (lane == 0) wpart[(f + 1) * (kConsumers / 32) + warp] = w;
-    }
+    // tile reduction through shared memory: thread partials are already there for the folds;
+    // warp q adds up row q (256 values: 8 per lane, conflict-free, then a shuffle tree).
+    // Fixed order => bit-reproducible.
+    acc[tid] = nrm;
     consumer_sync();
+    const int nslots = n_fold + 1;
     double* out = g.partials + ((long long)t.band * g.n_chunks + t.chunk) * nslots;
-    for (int q = tid; q < nslots; q += kConsumers) {
-      double acc = 0.0;
+    for (int q = warp; q < nslots; q += kConsumers / 32) {
+      const double* r = acc + q * kConsumers + lane;
+      double a = 0.0;
 #pragma unroll
-      for (int w = 0; w < kConsumers / 32; ++w) acc += wpart[q * (kConsumers / 32) + w];
-      out[q] = acc;
+      for (int i = 0; i < kConsumers / 32; ++i) a += r[32 * i];
+      a = warp_sum(a);
+      if (lane == 0) out[q] = a;
     }
     consumer_sync();
   }
 }
 
+// grid (ceil(max_bands * (max_n_fold+1) / 256), n_kpts)
 __global__ void __launch_bounds__(256)
-k2b_weights_finalize(const double* __restrict__ partials, int n_bands, int n_chunks,
-                     int n_fold, double* __restrict__ weights, double* __restrict__ norms) {
-  const int nslots = n_fold + 1;
+k2b_weights_finalize(const KptGeom* __restrict__ geoms) {
+  const KptGeom& g = geoms[blockIdx.y];
+  const int nslots = g.n_fold + 1;
+  const int n_chunks = g.n_chunks;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)n_bands * nslots) return;
+  if (idx >= (long long)g.n_bands * nslots) return;
   const int band = (int)(idx / nslots);
   const int q = (int)(idx - (long long)band * nslots);
-  const double* p = partials + (long long)band * n_chunks * nslots;
+  const double* p = g.partials + (long long)band * n_chunks * nslots;
   double s = 0.0;
   for (int c = 0; c < n_chunks; ++c) s += p[(long long)c * nslots];
   if (q == 0) {
-    if (norms) norms[band] = s;
+    if (g.norms) g.norms[band] = s;
     return;
   }
   double S = 0.0;
   for (int c = 0; c < n_chunks; ++c) S += p[(long long)c * nslots + q];
   // io_routines_mod.f90:1325: bands with s <= epsilon(1.0_dp) stay unscaled
-  weights[(long long)(q - 1) * n_bands + band] = (s > 2.220446049250313e-16) ? S / s : S;
+  g.weights[(long long)(q - 1) * g.n_bands + band] = (s > 2.220446049250313e-16) ? S / s : S;
+  if (band == 0) {  // size(selected_coeff_indices) of fold q-1: K1's per-CTA counts added up
+    int n = 0;
+    for (int b = 0; b < kK1MaxBlocks; ++b) n += g.block_counts[b * g.n_fold + (q - 1)];
+    g.n_selected[q - 1] = n;
+  }
 }
 
 constexpr size_t kSmemBudget = 227 * 1024;
 
 size_t k2_fixed_smem(int n_fold) {  // everything but the stage ring
-  return sizeof(double) * ((size_t)n_fold * kConsumers + (size_t)(n_fold + 1) * (kConsumers / 32)) +
-         sizeof(uint64_t) * 2 * kMaxStages + 128;
+  return sizeof(double) * (size_t)(n_fold + 1) * kConsumers + sizeof(uint64_t) * 2 * kMaxStages + 128;
 }
 
 template <int MODE>
-void launch_mode(WeightsGeom g, int ctas_per_sm, int n_stages, int sm_count, cudaStream_t s) {
-  const size_t fixed = k2_fixed_smem(g.n_fold);
-  // default: 3 CTAs per SM with 4 stages each (192 KB of loads in flight per SM; the B200
-  // sweep in profiles/ has 3x4 and 2x4 within 1 % of each other and ahead of deeper rings);
-  // many folds eat shared memory for the bins, so the ring shrinks before occupancy does
-  if (ctas_per_sm <= 0) ctas_per_sm = 3;
-  if (n_stages <= 0) n_stages = 4;
+void launch_mode(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int max_n_fold,
+                 int ctas_per_sm, int n_stages, int sm_count, cudaStream_t s) {
+  const size_t fixed = k2_fixed_smem(max_n_fold);
+  // default: 2 CTAs per SM with 3 stages each (96 KB of loads in flight per SM, about twice
+  // what latency x bandwidth asks for; the B200 sweep in profiles/ has 2x3 ahead of 3x4 and of
+  // deeper rings by 2-4 %); many folds eat shared memory for the bins, so the ring shrinks
+  // before occupancy does
+  if (ctas_per_sm <= 0) ctas_per_sm = 2;
+  if (n_stages <= 0) n_stages = 3;
   if (n_stages > kMaxStages) n_stages = kMaxStages;
   while (ctas_per_sm > 1 && (fixed + 2 * (size_t)kStageBytes + 1024) * ctas_per_sm > kSmemBudget) --ctas_per_sm;
   const size_t per_cta = kSmemBudget / ctas_per_sm - 1024;  // 1 KB per CTA is reserved by the driver
   while (n_stages > 2 && fixed + (size_t)n_stages * kStageBytes > per_cta) --n_stages;
-  g.n_stages = n_stages;
   const size_t smem = fixed + (size_t)n_stages * kStageBytes;
   cudaFuncSetAttribute(k2_weights_reduce<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_weights_reduce<MODE>, kThreads, smem);
   if (occ < 1) occ = 1;
   if (occ > ctas_per_sm) occ = ctas_per_sm;
-  long long tiles = (long long)g.n_bands * g.n_chunks;
   long long grid = (long long)sm_count * occ;
-  if (grid > tiles) grid = tiles;
+  if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return;
-  k2_weights_reduce<MODE><<<(unsigned)grid, kThreads, smem, s>>>(g);
+  k2_weights_reduce<MODE><<<(unsigned)grid, kThreads, smem, s>>>(d_geoms, n_kpts, total_tiles, max_n_fold,
+                                                                  n_stages);
 }
 
 }  // namespace
@@ -342,7 +405,7 @@ void launch_mode(WeightsGeom g, int ctas_per_sm, int n_stages, int sm_count, cud
 int weights_pick_chunk_vecs(int requested, long long row_elems, int n_bands, int sm_count) {
   if (requested > 0) return ((requested + kStageVecs - 1) / kStageVecs) * kStageVecs;
   const long long nv = row_elems / 2;
-  const long long want_tiles = 6LL * sm_count * 3;
+  const long long want_tiles = 6LL * sm_count * 2;
   int cv = 8 * kStageVecs;
   while (cv > kStageVecs && (long long)n_bands * ((nv + cv - 1) / cv) < want_tiles) cv >>= 1;
   return cv;
@@ -360,30 +423,29 @@ size_t weights_partials_bytes(int n_bands, int n_chunks, int n_fold) {
 
 int weights_max_folds_supported() {
   // bins + 2 stages must fit one CTA
-  int nf = (int)((kSmemBudget - 1024 - 2 * kStageBytes - sizeof(uint64_t) * 2 * kMaxStages - 128 -
-                  sizeof(double) * (kConsumers / 32)) /
-                 (sizeof(double) * (kConsumers + kConsumers / 32)));
+  int nf = (int)((kSmemBudget - 1024 - 2 * kStageBytes - sizeof(uint64_t) * 2 * kMaxStages - 128) /
+                 (sizeof(double) * kConsumers)) - 1;
   return nf;
 }
 
-void launch_weights_reduce(const WeightsGeom& g, int ctas_per_sm, int n_stages, int sm_count,
+void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int max_n_fold,
+                           int n_spinor, int layout, int ctas_per_sm, int n_stages, int sm_count,
                            cudaStream_t s) {
-  if (g.n_bands <= 0) return;
-  if (g.n_spinor == 1)
-    launch_mode<0>(g, ctas_per_sm, n_stages, sm_count, s);
-  else if (g.layout == BANDUP_GPU_LAYOUT_FORTRAN_INMEM)
-    launch_mode<1>(g, ctas_per_sm, n_stages, sm_count, s);
+  if (n_kpts <= 0 || total_tiles <= 0) return;
+  if (n_spinor == 1)
+    launch_mode<0>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, s);
+  else if (layout == BANDUP_GPU_LAYOUT_FORTRAN_INMEM)
+    launch_mode<1>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, s);
   else
-    launch_mode<2>(g, ctas_per_sm, n_stages, sm_count, s);
+    launch_mode<2>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, s);
 }
 
-void launch_weights_finalize(const double* d_partials, int n_bands, int n_chunks,
-                             int n_fold, double* d_weights, double* d_norms,
+void launch_weights_finalize(const KptGeom* d_geoms, int n_kpts, int max_bands, int max_n_fold,
                              cudaStream_t s) {
-  const long long n = (long long)n_bands * (n_fold + 1);
-  if (n <= 0) return;
-  k2b_weights_finalize<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
-      d_partials, n_bands, n_chunks, n_fold, d_weights, d_norms);
+  const long long n = (long long)max_bands * (max_n_fold + 1);
+  if (n <= 0 || n_kpts <= 0) return;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)n_kpts);
+  k2b_weights_finalize<<<grid, 256, 0, s>>>(d_geoms);
 }
 
 }  // namespace bandup

@@ -326,6 +326,32 @@ class GpuUnfolder:
             C.c_void_p(d_n_selected), C.c_void_p(d_norms or None), C.c_void_p(d_slot_out or None),
             C.c_void_p(d_workspace), int(workspace_bytes)))
 
+    def make_batch(self, kpts: Sequence[dict]):
+        """Array of bandup_gpu_kpt_desc from dicts with the keyword names of unfold_device
+        (n_spinor, n_pw, n_bands, layout, band_stride_bytes, d_coeffs, d_g_frac, d_band_energies, g0,
+        d_weights, d_dN, d_n_selected[, d_norms]).  Returns (descs, keepalive)."""
+        arr = (_capi.KptDesc * len(kpts))()
+        keep = []
+        for d, k in zip(arr, kpts):
+            g0 = np.ascontiguousarray(np.atleast_2d(k["g0"]), dtype=np.int32)
+            keep.append(g0)
+            d.n_spinor, d.n_pw, d.n_bands = int(k["n_spinor"]), int(k["n_pw"]), int(k["n_bands"])
+            d.layout, d.n_fold, d.reserved = int(k["layout"]), g0.shape[0], 0
+            d.band_stride_bytes = int(k["band_stride_bytes"])
+            d.d_coeffs, d.d_g_frac, d.d_band_energies = k["d_coeffs"], k["d_g_frac"], k["d_band_energies"]
+            d.g0 = g0.ctypes.data
+            d.d_weights, d.d_dN, d.d_n_selected = k["d_weights"], k["d_dN"], k["d_n_selected"]
+            d.d_norms = k.get("d_norms") or None
+        return arr, keep
+
+    def batch_workspace_bytes(self, descs) -> int:
+        return int(self._lib.bandup_gpu_batch_workspace_bytes(self.handle, len(descs), descs))
+
+    def unfold_device_batch(self, stream: int, descs, d_workspace: int, workspace_bytes: int) -> None:
+        """All k-points of `descs` with one launch per kernel (K1, K2, K2b, K3)."""
+        self._check(self._lib.bandup_gpu_unfold_device_batch(
+            self.handle, C.c_void_p(stream), len(descs), descs, C.c_void_p(d_workspace), int(workspace_bytes)))
+
     def synth_fill_device(self, stream: int, d_coeffs: int, row_elems: int, n_bands: int,
                           band_stride_bytes: int, seed: int, ikpt: int) -> None:
         self._check(self._lib.bandup_gpu_synth_fill_device(

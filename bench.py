@@ -64,6 +64,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--per-kpt-launch", action="store_true",
+                    help="launch K1..K3 once per SC k-point instead of once per step (batch)")
     return ap.parse_args()
 
 
@@ -254,12 +256,24 @@ def run_b200(args, sc, rank, world, local_rank):
     torch.cuda.synchronize()
     step_bytes = sum(nb * it["n_pw"] * nsp * 8 for it in items)
 
+    # one batch descriptor per step: K1, K2, K2b, K3 are each launched once for all kps k-points
+    descs, _keep = u.make_batch([dict(
+        n_spinor=nsp, n_pw=it["n_pw"], n_bands=nb, layout=LAYOUT_FORTRAN_INMEM,
+        band_stride_bytes=it["n_pw"] * nsp * 8, d_coeffs=it["d_c"].data_ptr(), d_g_frac=it["d_g"].data_ptr(),
+        d_band_energies=it["d_e"].data_ptr(), g0=it["g0"], d_weights=it["d_w"].data_ptr(),
+        d_dN=d_dn[j].data_ptr(), d_n_selected=it["d_ns"].data_ptr()) for j, it in enumerate(items)])
+    ws_batch = u.batch_workspace_bytes(descs)
+    d_ws_batch = torch.empty(ws_batch, dtype=torch.uint8, device=dev)
+
     def step():
-        for j, it in enumerate(items):
-            u.unfold_device(stream, nsp, it["n_pw"], nb, LAYOUT_FORTRAN_INMEM, it["n_pw"] * nsp * 8,
-                            it["d_c"].data_ptr(), it["d_g"].data_ptr(), it["d_e"].data_ptr(), it["g0"],
-                            it["d_w"].data_ptr(), d_dn[j].data_ptr(), it["d_ns"].data_ptr(),
-                            it["d_ws"].data_ptr(), it["ws"])
+        if args.per_kpt_launch:
+            for j, it in enumerate(items):
+                u.unfold_device(stream, nsp, it["n_pw"], nb, LAYOUT_FORTRAN_INMEM, it["n_pw"] * nsp * 8,
+                                it["d_c"].data_ptr(), it["d_g"].data_ptr(), it["d_e"].data_ptr(), it["g0"],
+                                it["d_w"].data_ptr(), d_dn[j].data_ptr(), it["d_ns"].data_ptr(),
+                                it["d_ws"].data_ptr(), it["ws"])
+        else:
+            u.unfold_device_batch(stream, descs, d_ws_batch.data_ptr(), ws_batch)
         if world > 1:   # the path's only exchange: gather the disjoint delta_N rows
             dist.all_gather_into_tensor(d_dn_all, d_dn)
 
@@ -307,7 +321,7 @@ def run_b200(args, sc, rank, world, local_rank):
         total_bytes = float(step_bytes) * args.steps
     value = total_bytes / (ms * 1e-3) / 1e9
     kpts_per_s = kps * world * args.steps / (ms * 1e-3)
-    k2_bytes = step_bytes / kps
+    k2_bytes = step_bytes / kps if args.per_kpt_launch else step_bytes
     peak, peak_src = measured_peak_gbs()
     achieved = k2_bytes / (k2_ms / max(k2_n, 1) * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k2_weights_reduce", "achieved": achieved, "peak": peak,
@@ -318,7 +332,8 @@ def run_b200(args, sc, rank, world, local_rank):
     if ncu_traffic.exists():
         try:
             t = json.loads(ncu_traffic.read_text())
-            if t.get("workload") == args.workload:
+            # the capture must be of the same launch shape (same workload, same k-points per launch)
+            if t.get("workload") == args.workload and abs(t["dram_bytes_per_launch"] / k2_bytes - 1.0) < 0.05:
                 roofline["traffic"] = t["dram_bytes_per_launch"]
                 roofline["traffic_source"] = t.get("source")
         except Exception:
@@ -385,6 +400,8 @@ def run_b200(args, sc, rank, world, local_rank):
             "config": {"workload": WORKLOADS[args.workload], "kpts_per_step_per_gpu": kps, "n_bands": nb,
                        "n_spinor": nsp, "n_pw": [it["n_pw"] for it in items],
                        "n_fold": [it["nf"] for it in items], "nener": nener,
+                       "launches": "per SC k-point" if args.per_kpt_launch else
+                       "one launch of K1, K2, K2b, K3 per step (bandup_gpu_unfold_device_batch)",
                        "l2": "inputs larger than L2 (each SC-kpt block >> 126 MB; batch cycles through "
                              f"{step_bytes / 1e9:.1f} GB)",
                        "parallelism": f"SC k-points sharded over {world} GPU(s), NCCL all_gather of delta_N rows"

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BANDUP_GPU_ABI_VERSION 2
+#define BANDUP_GPU_ABI_VERSION 3
 
 /* status codes */
 #define BANDUP_GPU_OK 0
@@ -216,6 +216,31 @@ int bandup_gpu_unfold_device(int handle, void *stream, int n_spinor, int n_pw,
                              int32_t *d_n_selected, double *d_norms,
                              uint8_t *d_slot_out, void *d_workspace,
                              size_t workspace_bytes);
+
+/* One SC k-point of a batch for bandup_gpu_unfold_device_batch: the arguments of
+ * bandup_gpu_unfold_device as a struct (d_* device pointers, g0 HOST [n_fold][3]). */
+typedef struct bandup_gpu_kpt_desc {
+  int32_t n_spinor, n_pw, n_bands, layout, n_fold, reserved;
+  int64_t band_stride_bytes;
+  const void *d_coeffs;
+  const int32_t *d_g_frac;
+  const double *d_band_energies;
+  const int32_t *g0;
+  double *d_weights;      /* [n_fold][n_bands] */
+  double *d_dN;           /* [n_fold][nener]   */
+  int32_t *d_n_selected;  /* [n_fold]          */
+  double *d_norms;        /* [n_bands] or NULL */
+} bandup_gpu_kpt_desc;
+
+size_t bandup_gpu_batch_workspace_bytes(int handle, int n_kpts, const bandup_gpu_kpt_desc *descs);
+/* The same computation as n_kpts calls of bandup_gpu_unfold_device, but every kernel is
+ * launched ONCE for the whole batch (four launches in total): the k-points' (band, chunk)
+ * tiles form one persistent grid, so small k-points (graphene: 12 MB) are no longer
+ * launch-bound and large ones lose the per-k-point ramp and tail.  All k-points of a batch
+ * share n_spinor and layout. */
+int bandup_gpu_unfold_device_batch(int handle, void *stream, int n_kpts,
+                                   const bandup_gpu_kpt_desc *descs, void *d_workspace,
+                                   size_t workspace_bytes);
 
 /* ---- instrumentation ---------------------------------------------------- */
 

@@ -67,7 +67,7 @@ def test_all_cosets_sum_to_one(unfolder):
     g0 = np.array([[n1, n2, 0] for n1 in range(4) for n2 in range(4)], dtype=np.int32)
     res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), g0=g0)
     assert int(res.n_selected.sum()) == gf.shape[0]
-    assert np.allclose(res.spectral_weight.sum(axis=0), 1.0, rtol=0, atol=1e-9)
+    assert np.allclose(res.spectral_weight.sum(axis=0), 1.0, rtol=0, atol=1e-7)
     allsel = np.sort(np.concatenate(res.selected_coeff_indices))
     assert np.array_equal(allsel, np.arange(1, gf.shape[0] + 1))
 
@@ -125,7 +125,7 @@ def test_vasp_record_layout_and_odd_rows(unfolder, n_spinor, n_pw_trim):
         assert np.array_equal(res.n_selected, ns)
         assert rel_err(res.spectral_weight, w) <= REL_TOL
         assert rel_err(res.dN, dN) <= REL_TOL
-        assert np.allclose(res.spectral_weight, ref.spectral_weight, rtol=1e-12, atol=1e-15)
+        assert np.allclose(res.spectral_weight, ref.spectral_weight, rtol=1e-7, atol=1e-15)  # fp32 8-term runs group differently per alignment
 
 
 def test_gaussian_smearing(unfolder):
@@ -329,3 +329,57 @@ def test_sharded_job_whole_scenario(unfolder):
         coeffs, gf, ener = data[iK]
         _, dN, _, _ = O.unfold_kpt(coeffs, gf @ sc.B_sc, ener, sc.b_pc, sc.folding_G(iK), grid, norm_mode=1)
         assert rel_err(got.dN[np.asarray(sc.folds[iK])], dN) <= REL_TOL
+
+
+def test_device_batch_equals_per_kpt_calls(unfolder):
+    """bandup_gpu_unfold_device_batch (one launch of each kernel for several SC-kpts with different
+    n_pw / n_fold, one of them with two pc-kpts in the same coset) gives bit-identical results to
+    per-k-point bandup_gpu_unfold_device calls, and both agree with the oracle."""
+    import torch
+    from bandup_b200.unfold import LAYOUT_FORTRAN_INMEM
+    sc = synth.make_scenario("si333_vacancy", scale=0.25)
+    grid = setup(unfolder, sc)
+    nener = len(grid)
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    kpts, host = [], []
+    for iK in (0, 3, sc.n_sc_kpts - 1):
+        coeffs, gf, ener = synth.make_wavefunction(sc, iK)
+        fG = sc.folding_G(iK)
+        if iK == 3:
+            fG = np.concatenate([fG, fG[:1] + 2 * sc.b_pc[1]])      # same coset as its first fold
+        g0, _ = unfolder.folding_g0(fG)
+        nb, n_pw, _ = coeffs.shape
+        nf = g0.shape[0]
+        t = dict(c=torch.from_numpy(coeffs.view(np.float32).reshape(nb, n_pw, 2)).to(dev),
+                 g=torch.from_numpy(gf).to(dev), e=torch.from_numpy(ener).to(dev))
+        outs = [dict(w=torch.zeros((nf, nb), dtype=torch.float64, device=dev),
+                     dn=torch.zeros((nf, nener), dtype=torch.float64, device=dev),
+                     ns=torch.zeros(nf, dtype=torch.int32, device=dev),
+                     nr=torch.zeros(nb, dtype=torch.float64, device=dev)) for _ in range(2)]
+        host.append((coeffs, gf, ener, fG, t, outs, g0))
+        kpts.append(dict(n_spinor=1, n_pw=n_pw, n_bands=nb, layout=LAYOUT_FORTRAN_INMEM, band_stride_bytes=n_pw * 8,
+                         d_coeffs=t["c"].data_ptr(), d_g_frac=t["g"].data_ptr(), d_band_energies=t["e"].data_ptr(),
+                         g0=g0, d_weights=outs[0]["w"].data_ptr(), d_dN=outs[0]["dn"].data_ptr(),
+                         d_n_selected=outs[0]["ns"].data_ptr(), d_norms=outs[0]["nr"].data_ptr()))
+    descs, keep = unfolder.make_batch(kpts)
+    ws = unfolder.batch_workspace_bytes(descs)
+    d_ws = torch.empty(ws, dtype=torch.uint8, device=dev)
+    l0 = unfolder.launch_count()
+    unfolder.unfold_device_batch(stream, descs, d_ws.data_ptr(), ws)
+    assert unfolder.launch_count() - l0 == 4                        # K1, K2, K2b, K3 once each
+    for coeffs, gf, ener, fG, t, outs, g0 in host:
+        nb, n_pw, _ = coeffs.shape
+        w1 = unfolder.workspace_bytes(1, n_pw, nb, g0.shape[0])
+        d_w1 = torch.empty(w1, dtype=torch.uint8, device=dev)
+        o = outs[1]
+        unfolder.unfold_device(stream, 1, n_pw, nb, LAYOUT_FORTRAN_INMEM, n_pw * 8, t["c"].data_ptr(),
+                               t["g"].data_ptr(), t["e"].data_ptr(), g0, o["w"].data_ptr(), o["dn"].data_ptr(),
+                               o["ns"].data_ptr(), d_w1.data_ptr(), w1, d_norms=o["nr"].data_ptr())
+        torch.cuda.synchronize()
+        for key in ("w", "dn", "ns", "nr"):
+            assert torch.equal(outs[0][key], outs[1][key]), key
+        w, dN, ns, _ = oracle_kpt(sc, coeffs, gf, ener, fG, grid)
+        assert np.array_equal(outs[0]["ns"].cpu().numpy(), ns)
+        assert rel_err(outs[0]["w"].cpu().numpy(), w) <= REL_TOL
+        assert rel_err(outs[0]["dn"].cpu().numpy(), dN) <= REL_TOL
