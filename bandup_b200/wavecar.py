@@ -1,0 +1,226 @@
+"""VASP WAVECAR container: the on-disk layout the reference's reader consumes
+(src/vasp_related_modules/read_wavecar_mod.f90), parsed so that the raw band records can be handed
+to the GPU untouched (layout BANDUP_GPU_LAYOUT_VASP_RECORD, stride nrecl) -- no host de-interleave.
+
+Direct-access records of `nrecl` bytes (read_wavecar_mod.f90:112-127):
+  rec 1   nrecl, nspin, nprec                       3 doubles; nprec = 45200 <=> complex64 (:356-377)
+  rec 2   nkpts, nbands, ENCUT, a1(3), a2(3), a3(3) 12 doubles                              (:386)
+  then, per spin, per k-point:
+    1 header record  nplane, k(3), {Re E, Im E, occ} x nbands   doubles                    (:420-427)
+    nbands records   complex64[nplane]; for a spinor nplane = 2 n_G, spin-up block first   (:446-452, :570-577)
+each zero-padded to nrecl.  The plane-wave list is NOT stored: it is regenerated from k, ENCUT and
+the lattice (:255-304), with a small adaptive tweak of 2m/hbar^2 when the count is off (:459-535).
+
+This module is input plumbing (and the writer the tests use to synthesise files); it computes no
+weights.  The reference's Fortran reader stays what BandUP itself uses (north_star: readers kept).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from pathlib import Path
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import synth
+
+NPREC_COMPLEX64 = 45200
+
+
+@dataclass
+class KptHeader:
+    nplane: int                 # as stored: n_G * n_spinor
+    kpt_frac_coords: np.ndarray
+    band_energies: np.ndarray   # Re(cener)
+    band_occupations: np.ndarray
+    first_band_record: int      # 0-based record index of band 1
+
+
+def write_wavecar(path, A: np.ndarray, ecut: float, kpts_frac: Sequence[np.ndarray],
+                  coeffs: Sequence[np.ndarray], energies: Sequence[np.ndarray],
+                  occupations: Optional[Sequence[np.ndarray]] = None, nspin: int = 1,
+                  extra_pad: int = 0) -> int:
+    """Writes a single-precision WAVECAR.  coeffs[ik] is (n_bands, n_pw, n_spinor) complex64 in the
+    plane-wave order of synth.gen_gvecs (== the reader's enumeration).  Returns nrecl."""
+    A = np.asarray(A, dtype=np.float64)
+    nk = len(kpts_frac)
+    nb = coeffs[0].shape[0]
+    max_plane = max(c.shape[1] * c.shape[2] for c in coeffs)
+    nrecl = max(8 * max_plane, 8 * (4 + 3 * nb), 8 * 12) + 8 * int(extra_pad)
+    with open(path, "wb") as f:
+        def put(rec_bytes: bytes):
+            assert len(rec_bytes) <= nrecl
+            f.write(rec_bytes + b"\0" * (nrecl - len(rec_bytes)))
+
+        put(np.array([nrecl, nspin, NPREC_COMPLEX64], dtype="<f8").tobytes())
+        put(np.concatenate([[nk, nb, ecut], A.reshape(9)]).astype("<f8").tobytes())
+        for _spin in range(nspin):
+            for ik in range(nk):
+                c = np.ascontiguousarray(coeffs[ik], dtype=np.complex64)
+                if c.shape[0] != nb:
+                    raise ValueError("every k-point must have the same number of bands")
+                n_pw, nsp = c.shape[1], c.shape[2]
+                occ = np.ones(nb) if occupations is None else np.asarray(occupations[ik], dtype=np.float64)
+                ener = np.asarray(energies[ik], dtype=np.float64)
+                hdr = np.empty(4 + 3 * nb, dtype="<f8")
+                hdr[0] = n_pw * nsp
+                hdr[1:4] = np.asarray(kpts_frac[ik], dtype=np.float64)
+                hdr[4::3] = ener
+                hdr[5::3] = 0.0
+                hdr[6::3] = occ
+                put(hdr.tobytes())
+                for ib in range(nb):
+                    # spinor-up block, then spinor-down block
+                    put(np.ascontiguousarray(c[ib].T).astype("<c8").tobytes())
+    return nrecl
+
+
+class Wavecar:
+    """Read-only view of a WAVECAR file."""
+
+    def __init__(self, path):
+        self.path = Path(path)
+        with open(self.path, "rb") as f:
+            head = np.frombuffer(f.read(24), dtype="<f8")
+            self.nrecl = int(round(head[0]))
+            self.nspin = int(round(head[1]))
+            self.nprec = int(round(head[2]))
+            if self.nprec != NPREC_COMPLEX64:
+                # read_wavecar_mod.f90:360-377: a WAVECAR_double needs a dp build of the reference
+                raise ValueError("double-precision WAVECAR: only complex64 coefficients are supported")
+            if self.nrecl < 96 or self.nrecl % 8:
+                raise ValueError(f"unexpected record length {self.nrecl}")
+            f.seek(self.nrecl)
+            rec2 = np.frombuffer(f.read(96), dtype="<f8")
+        self.nkpts = int(round(rec2[0]))
+        self.nbands = int(round(rec2[1]))
+        self.encut = float(rec2[2])
+        if self.nkpts == 0:
+            raise ValueError("ERROR (read_wavecar): Unexpected file format")
+        self.A_matrix = rec2[3:12].reshape(3, 3).copy()
+        self.B_matrix = synth.rec_latt(self.A_matrix)
+        self._gcache = {}
+
+    def header_record(self, ikpt: int, ispin: int = 1) -> int:
+        """0-based record index of the k-point header (ikpt, ispin 1-based) (:409-414)."""
+        if not (1 <= ikpt <= self.nkpts) or not (1 <= ispin <= self.nspin):
+            raise IndexError("ikpt / ispin out of range")
+        return 2 + (ispin - 1) * self.nkpts * (1 + self.nbands) + (ikpt - 1) * (1 + self.nbands)
+
+    def kpt_header(self, ikpt: int, ispin: int = 1) -> KptHeader:
+        rec = self.header_record(ikpt, ispin)
+        with open(self.path, "rb") as f:
+            f.seek(rec * self.nrecl)
+            h = np.frombuffer(f.read(8 * (4 + 3 * self.nbands)), dtype="<f8")
+        return KptHeader(int(round(h[0])), h[1:4].copy(), h[4::3].copy(), h[6::3].copy(), rec + 1)
+
+    def gvecs(self, ikpt: int, ispin: int = 1) -> Tuple[np.ndarray, int]:
+        """(G_frac int32 (n_G, 3), n_spinor): the reader's regeneration incl. its adaptive tweak of
+        2m/hbar^2 (read_wavecar_mod.f90:440-535)."""
+        key = (ikpt, ispin)
+        if key in self._gcache:
+            return self._gcache[key]
+        h = self.kpt_header(ikpt, ispin)
+        c = synth.VASP_2M_OVER_HBAR_SQRD
+        g = synth.gen_gvecs(h.kpt_frac_coords, self.encut, self.B_matrix, c)
+        nplane = h.nplane
+        n_spinor = 1
+        if g.shape[0] and int(round(nplane / g.shape[0])) == 2:
+            n_spinor = 2
+            nplane //= 2
+        step = 1e-10 if nplane >= g.shape[0] else -1e-10
+        i = 0
+        while g.shape[0] != nplane and abs(i * step) <= 1000 * 1e-10:
+            i += 1
+            g = synth.gen_gvecs(h.kpt_frac_coords, self.encut, self.B_matrix, c + i * step)
+        if g.shape[0] != nplane:
+            # :519-531 'ERROR (read_wavecar): The number of plane-waves ... does not match'
+            raise ValueError(f"WAVECAR holds {nplane} plane waves, {g.shape[0]} were generated")
+        self._gcache[key] = (g, n_spinor)
+        return g, n_spinor
+
+    def band_block_bytes(self) -> int:
+        return self.nbands * self.nrecl
+
+    def read_band_records(self, ikpt: int, ispin: int = 1, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """The nbands raw coefficient records of a k-point, contiguous on disk, as uint8
+        [nbands * nrecl] -- read straight into `out` (e.g. page-locked memory from
+        bandup_b200.unfold.pinned_empty) so the upload is one DMA."""
+        n = self.band_block_bytes()
+        if out is None:
+            out = np.empty(n, dtype=np.uint8)
+        if out.dtype != np.uint8 or out.size < n:
+            raise ValueError("out must be a uint8 buffer of at least nbands*nrecl bytes")
+        first = self.header_record(ikpt, ispin) + 1
+        with open(self.path, "rb", buffering=0) as f:
+            f.seek(first * self.nrecl)
+            got = f.readinto(memoryview(out[:n]))
+        if got != n:
+            raise IOError(f"short read: {got} of {n} bytes")
+        return out[:n]
+
+    def coefficients(self, ikpt: int, ispin: int = 1) -> np.ndarray:
+        """(n_bands, n_pw, n_spinor) complex64 as read_wavecar leaves wf%pw_coeffs -- a HOST
+        de-interleave used only by tests; the GPU path consumes read_band_records directly."""
+        g, nsp = self.gvecs(ikpt, ispin)
+        raw = self.read_band_records(ikpt, ispin).reshape(self.nbands, self.nrecl)
+        c = raw[:, :8 * g.shape[0] * nsp].copy().view("<c8").reshape(self.nbands, nsp, g.shape[0])
+        return np.ascontiguousarray(c.transpose(0, 2, 1))
+
+    def wavefunction(self, ikpt: int, ispin: int = 1, out: Optional[np.ndarray] = None):
+        """bandup_b200.unfold.PwWavefunction over the raw records (VASP_RECORD layout)."""
+        from .unfold import LAYOUT_VASP_RECORD, PwWavefunction
+        h = self.kpt_header(ikpt, ispin)
+        g, nsp = self.gvecs(ikpt, ispin)
+        raw = self.read_band_records(ikpt, ispin, out=out)
+        return PwWavefunction(raw, g, h.band_energies, kpt_frac_coords=h.kpt_frac_coords, n_pw=g.shape[0],
+                              n_bands=self.nbands, n_spinor=nsp, layout=LAYOUT_VASP_RECORD,
+                              band_stride_bytes=self.nrecl)
+
+
+def fold_pckpts_onto_sckpts(pc_kpts_cart: np.ndarray, sc_kpts_frac: np.ndarray, B_sc: np.ndarray,
+                            tol: float = 1e-5) -> List[List[int]]:
+    """For every SC-kpt of the file, the pc-kpts k with k - K on the SC reciprocal lattice (the
+    geometric unfolding relation under -no_symm_sckpts, band_unfolding_routines_mod.f90:192-204,
+    317-324).  Raises when a pc-kpt folds onto none (main_BandUP.f90:114)."""
+    Binv = np.linalg.inv(B_sc)
+    K = np.asarray(sc_kpts_frac, dtype=np.float64) @ B_sc
+    folds: List[List[int]] = [[] for _ in range(K.shape[0])]
+    for ik, k in enumerate(np.asarray(pc_kpts_cart, dtype=np.float64)):
+        frac = (k[None, :] - K) @ Binv
+        resid = np.abs((frac - np.rint(frac)) @ B_sc).max(axis=1)
+        hit = np.nonzero(resid <= tol)[0]
+        if hit.size == 0:
+            raise ValueError(f"pc-kpt {ik} does not fold onto any SC-kpt of the wavefunction file")
+        folds[int(hit[0])].append(ik)
+    return folds
+
+
+def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_cart: np.ndarray,
+                   E_start: float, E_end: float, delta_e: float, ispin: int = 1, rank: int = 0,
+                   world_size: int = 1, device=None, group=None):
+    """The reference's main loop (main_BandUP.f90:131-177) over a WAVECAR under its no-symmetry
+    flags (-no_symm_sckpts -no_symm_avg): every SC-kpt of the file, all pc-kpts folding onto it in
+    one pass, raw band records read into two page-locked buffers and uploaded as they are while the
+    previous k-point computes.  Returns sharding.GatheredDeltaN (rows in pc-kpt order) and the
+    energy grid."""
+    from .sharding import ShardedUnfoldJob
+    from .unfold import pinned_empty
+    unfolder.verify_commens(rec_latt_pc, wavecar.B_matrix)
+    grid = unfolder.set_energy_grid(E_start, E_end, delta_e)
+    sc_k = np.array([wavecar.kpt_header(i + 1, ispin).kpt_frac_coords for i in range(wavecar.nkpts)])
+    folds = fold_pckpts_onto_sckpts(pc_kpts_cart, sc_k, wavecar.B_matrix)
+    used = [i for i in range(wavecar.nkpts) if folds[i]]       # SC-kpts no pc-kpt folds onto are skipped
+    costs = [float(wavecar.nbands) * wavecar.kpt_header(i + 1, ispin).nplane for i in used]
+    # one buffer more than the pipeline depth: a buffer is refilled only after its k-point was fetched
+    bufs = [pinned_empty(wavecar.band_block_bytes()) for _ in range(3)]
+    K_cart = sc_k @ wavecar.B_matrix
+
+    def load(j):
+        i = used[j]
+        wf = wavecar.wavefunction(i + 1, ispin, out=bufs[j % len(bufs)])
+        fG = np.asarray(pc_kpts_cart)[folds[i]] - K_cart[i]
+        return wf, fG, np.asarray(folds[i])
+
+    job = ShardedUnfoldJob(unfolder, len(used), costs, load, rank=rank, world_size=world_size, depth=2)
+    return job.run(device=device, group=group), grid

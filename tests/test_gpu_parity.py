@@ -383,3 +383,25 @@ def test_device_batch_equals_per_kpt_calls(unfolder):
         assert np.array_equal(outs[0]["ns"].cpu().numpy(), ns)
         assert rel_err(outs[0]["w"].cpu().numpy(), w) <= REL_TOL
         assert rel_err(outs[0]["dn"].cpu().numpy(), dN) <= REL_TOL
+
+
+@pytest.mark.parametrize("name,scale", [("graphene4x4", 0.1), ("mos2_8x8_spinor", 0.05)])
+def test_unfold_from_wavecar_file(unfolder, tmp_path, name, scale):
+    """File-level path: a synthetic WAVECAR in the reader's own record format, raw band records
+    uploaded untouched (VASP_RECORD layout, stride nrecl), against the oracle fed with the
+    de-interleaved coefficients."""
+    from bandup_b200.wavecar import Wavecar, unfold_wavecar, write_wavecar
+    from oracle import oracle as O
+    sc = synth.make_scenario(name, scale=scale, n_kpts=9)
+    data = [synth.make_wavefunction(sc, iK) for iK in range(sc.n_sc_kpts)]
+    path = tmp_path / "WAVECAR"
+    write_wavecar(path, sc.A_sc, sc.ecut, list(sc.sc_kpts_frac), [d[0] for d in data], [d[2] for d in data],
+                  extra_pad=1)
+    wc = Wavecar(path)
+    got, grid = unfold_wavecar(unfolder, wc, sc.b_pc, sc.pc_kpts_cart, *sc.energy_window())
+    n_rows = sum(len(f) for f in sc.folds)
+    assert got.row_ids.tolist() == list(range(n_rows))
+    for iK in range(sc.n_sc_kpts):
+        coeffs, gf, ener = data[iK]
+        _, dN, _, _ = O.unfold_kpt(coeffs, gf @ sc.B_sc, ener, sc.b_pc, sc.folding_G(iK), grid, norm_mode=1)
+        assert rel_err(got.dN[np.asarray(sc.folds[iK])], dN) <= REL_TOL
