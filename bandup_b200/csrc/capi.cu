@@ -89,6 +89,7 @@ struct Flight {  // one SC k-point in flight
   // per-unique-fold results (alias weights/dN/nsel unless two pc-kpts share a coset)
   const double* d_dn_unique = nullptr;
   const int32_t* d_ns_unique = nullptr;
+  const double* d_w_unique = nullptr;
   // projected variant
   bool rho_ready = false;
   DevBuf sel_off, csel, pair_count, pair_off, pairs, overflow, trace_out;
@@ -117,6 +118,7 @@ struct Ctx {
   int next_flight = 0;
   int chunk_vecs = 0, ctas_per_sm = 0, n_stages = 0;
   bool profiling = false;
+  bool perform_unfold = true;  // args%perform_unfold; false == -dont_unfold
   std::vector<cudaEvent_t> event_pool;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[BANDUP_GPU_K_COUNT];
   double total_ms[BANDUP_GPU_K_COUNT] = {0};
@@ -337,6 +339,7 @@ struct BatchItem {  // one SC k-point of a launch batch (host side)
   // outputs of run_batch: where the per-distinct-coset rows live
   const double* dn_unique = nullptr;
   const int32_t* ns_unique = nullptr;
+  const double* w_unique = nullptr;
   const uint8_t* d_slot = nullptr;
 };
 
@@ -401,6 +404,7 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
     g.n_fold = it.plan.n_unique;
     g.chunk_vecs = weights_pick_chunk_vecs(c->chunk_vecs, g.row_elems, it.n_bands, c->sm_count);
     g.n_chunks = weights_num_chunks(g.row_elems, g.chunk_vecs);
+    g.perform_unfold = c->perform_unfold ? 1 : 0;
     g.tile_begin = tiles;
     tiles += (long long)it.n_bands * g.n_chunks;
     g.partials = reinterpret_cast<double*>(it.ws + wl.partials_off);
@@ -409,6 +413,7 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
     g.dN = dup ? reinterpret_cast<double*>(it.ws + wl.tmp_dn_off) : it.d_dN;
     std::memcpy(g.fold_key, it.plan.fold_key, sizeof(g.fold_key));
     it.dn_unique = g.dN;
+    it.w_unique = g.weights;
     it.ns_unique = g.n_selected;
     it.d_slot = g.slot;
     if (g.n_fold > max_fold) max_fold = g.n_fold;
@@ -819,6 +824,7 @@ int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_ba
   it.ws = static_cast<char*>(fl.workspace.p);
   rc = run_batch(c, c->compute, items);
   fl.d_dn_unique = it.dn_unique;
+  fl.d_w_unique = it.w_unique;
   fl.d_ns_unique = it.ns_unique;
   if (rc) return rc;
   CU(cudaMemcpyAsync(fl.h_weights.p, fl.weights.p, sizeof(double) * (size_t)n_fold * n_bands, cudaMemcpyDeviceToHost, c->compute));
@@ -922,6 +928,8 @@ int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t* n_energie
                          int64_t* n_entries) {
   Ctx* c = get(handle);
   if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (!c->perform_unfold)
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "rho with -dont_unfold is not offered by the GPU path");
   if (!(min_dN >= kEpsDp))
     return fail(c, BANDUP_GPU_ERR_DELTA_N_ZERO,
                 "ERROR (calc_rho): delta_N = 0. (min_dN must be >= epsilon(1.0_dp); the reference uses 1e-3)");
@@ -1053,6 +1061,40 @@ int bandup_gpu_fetch_rho(int handle, int ikpt, int64_t capacity, int32_t* fold, 
     if (rho_re) rho_re[i] = e.re;
     if (rho_im) rho_im[i] = e.im;
   }
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_set_perform_unfold(int handle, int perform_unfold) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  c->perform_unfold = perform_unfold != 0;
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_spectral_function(int handle, int ikpt, double std_dev, double* sf) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  Flight* fl = nullptr;
+  int rc = need_resident(c, ikpt, &fl);
+  if (rc) return rc;
+  if (!sf) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "sf is NULL");
+  const double sigma = std_dev > 0.0 ? std_dev : 0.025;  // calc_spectral_function's default (:671)
+  cudaSetDevice(c->device);
+  cudaStream_t s = c->compute;
+  const int nener = c->nener, nu = fl->n_unique;
+  CU(fl->trace_out.reserve(sizeof(double) * (size_t)nu * nener));
+  {
+    KernelScope k(c, BANDUP_GPU_K_DELTA_N, s);
+    launch_spectral_function(static_cast<const double*>(c->d_grid.p), nener, sigma,
+                             static_cast<const double*>(fl->energies.p), fl->d_w_unique, fl->n_bands, nu,
+                             static_cast<double*>(fl->trace_out.p), s);
+  }
+  CU(cudaGetLastError());
+  std::vector<double> h((size_t)nu * nener);
+  CU(cudaMemcpyAsync(h.data(), fl->trace_out.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (int f = 0; f < fl->n_fold; ++f)
+    std::memcpy(sf + (size_t)f * nener, h.data() + (size_t)fl->unique_of[f] * nener, sizeof(double) * (size_t)nener);
   return BANDUP_GPU_OK;
 }
 

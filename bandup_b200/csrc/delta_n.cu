@@ -105,6 +105,34 @@ k3_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict__ grid, i
   if (live && lane == 0) g.dN[(long long)f * nener + ie] = acc;
 }
 
+// A(k, E_i) = sum_m P_m * delta(E_m - E_i), delta = Gaussian of standard deviation sigma
+// (calc_spectral_function, band_unfolding_routines_mod.f90:654-698, with delta, math_mod.f90:159-178;
+// dead code in the reference build -- calc_spec_func_explicitly = .FALSE.,
+// constants_and_types_mod.f90:75 -- offered here on request).  One warp per (energy, fold).
+__global__ void __launch_bounds__(kK3Threads)
+k3_spectral_function(const double* __restrict__ grid, int nener, double stddev,
+                     const double* __restrict__ band_energies, const double* __restrict__ weights,
+                     int n_bands, int n_fold, double* __restrict__ sf) {
+  const int lane = threadIdx.x & 31;
+  const long long wg = (long long)blockIdx.x * (kK3Threads / 32) + (threadIdx.x >> 5);
+  if (wg >= (long long)nener * n_fold) return;
+  const int f = (int)(wg / nener), ie = (int)(wg - (long long)f * nener);
+  const double E = grid[ie];
+  const double twopi = 2.0 * (4.0 * atan(1.0));
+  const double denom = __dmul_rn(stddev, sqrt(twopi));
+  const double* w = weights + (long long)f * n_bands;
+  double acc = 0.0;
+  for (int m = lane; m < n_bands; m += 32) {
+    const double x = __ddiv_rn(__dsub_rn(band_energies[m], E), stddev);
+    const double a = __ddiv_rn(__dmul_rn(x, x), 2.0);
+    if (a > 746.0) continue;  // exp(-a) is exactly 0 in double precision
+    acc = __dadd_rn(acc, __dmul_rn(w[m], __ddiv_rn(exp(-a), denom)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+  if (lane == 0) sf[(long long)f * nener + ie] = acc;
+}
+
 }  // namespace
 
 void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const double* d_grid,
@@ -114,6 +142,16 @@ void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const do
   const int ctas_per_fold = (nener + bins_per_cta - 1) / bins_per_cta;
   dim3 grid((unsigned)(ctas_per_fold * max_n_fold), (unsigned)n_kpts);
   k3_delta_n<<<grid, kK3Threads, 0, s>>>(d_geoms, d_grid, nener, sigma);
+}
+
+void launch_spectral_function(const double* d_grid, int nener, double stddev, const double* d_band_energies,
+                              const double* d_weights, int n_bands, int n_fold, double* d_sf,
+                              cudaStream_t s) {
+  const long long warps = (long long)nener * n_fold;
+  if (warps <= 0) return;
+  const int wpb = kK3Threads / 32;
+  k3_spectral_function<<<(unsigned)((warps + wpb - 1) / wpb), kK3Threads, 0, s>>>(
+      d_grid, nener, stddev, d_band_energies, d_weights, n_bands, n_fold, d_sf);
 }
 
 }  // namespace bandup

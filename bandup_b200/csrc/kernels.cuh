@@ -42,6 +42,7 @@ struct KptGeom {
   int n_fold;
   int chunk_vecs;             // 16-byte vectors per K2 tile (a multiple of the 1024-vector stage)
   int n_chunks;               // tiles per band
+  int perform_unfold;         // 0: -dont_unfold, every spectral weight is 1 (:1346-1351)
   long long tile_begin;       // global index of this k-point's first K2 tile
   double* partials;           // [n_bands][n_chunks][n_fold+1]; [..][0] = norm part
   double* weights;            // [n_fold][n_bands]
@@ -88,6 +89,11 @@ void launch_weights_finalize(const KptGeom* d_geoms, int n_kpts, int max_bands, 
 // and integral_delta_x_minus_x0, math_mod.f90:181-193).
 void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const double* d_grid,
                     int nener, double sigma, cudaStream_t s);
+
+// A(k,E) with a Gaussian delta (calc_spectral_function, :654-698); weights per distinct fold.
+void launch_spectral_function(const double* d_grid, int nener, double stddev, const double* d_band_energies,
+                              const double* d_weights, int n_bands, int n_fold, double* d_sf,
+                              cudaStream_t s);
 
 // ---- projected variant (rho.cu) ----------------------------------------------
 struct RhoPair {  // one upper-triangle element of an unfolding-density operator

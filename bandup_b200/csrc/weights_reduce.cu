@@ -355,7 +355,9 @@ k2b_weights_finalize(const KptGeom* __restrict__ geoms) {
   double S = 0.0;
   for (int c = 0; c < n_chunks; ++c) S += p[(long long)c * nslots + q];
   // io_routines_mod.f90:1325: bands with s <= epsilon(1.0_dp) stay unscaled
-  g.weights[(long long)(q - 1) * g.n_bands + band] = (s > 2.220446049250313e-16) ? S / s : S;
+  const double P = (s > 2.220446049250313e-16) ? S / s : S;
+  // -dont_unfold: spectral_weight = 1.0_dp (band_unfolding_routines_mod.f90:1346-1351)
+  g.weights[(long long)(q - 1) * g.n_bands + band] = g.perform_unfold ? P : 1.0;
   if (band == 0) {  // size(selected_coeff_indices) of fold q-1: K1's per-CTA counts added up
     int n = 0;
     for (int b = 0; b < kK1MaxBlocks; ++b) n += g.block_counts[b * g.n_fold + (q - 1)];

@@ -250,6 +250,18 @@ class GpuUnfolder:
         ascending) per pc-kpt.  An empty list is the reference's 'not allocated'."""
         return self.perform_unfolding(wf, folding_G, want_selected=True).selected_coeff_indices
 
+    def set_perform_unfold(self, perform_unfold: bool) -> None:
+        """args%perform_unfold; False == the reference's -dont_unfold (every weight is 1)."""
+        self._check(self._lib.bandup_gpu_set_perform_unfold(self.handle, int(bool(perform_unfold))))
+
+    def calc_spectral_function(self, ikpt: int, n_fold: int, std_dev: Optional[float] = None) -> np.ndarray:
+        """calc_spectral_function (band_unfolding_routines_mod.f90:654-698) for a fetched, still
+        resident SC-kpt: A(k, E_i) with a Gaussian delta (default std_dev 0.025 eV)."""
+        out = np.zeros((n_fold, self.nener), dtype=np.float64)
+        self._check(self._lib.bandup_gpu_spectral_function(
+            self.handle, int(ikpt), -1.0 if std_dev is None else float(std_dev), out.ctypes.data_as(c_f64p)))
+        return out
+
     # -- projected variant ------------------------------------------------------
     def calc_rho(self, ikpt: int, min_dN: float = 1e-3) -> "UnfoldDensityOps":
         """The energy selection + calc_rho loop of perform_unfolding

@@ -147,6 +147,17 @@ int bandup_gpu_fetch_kpt(int handle, int ikpt, double *weights, double *dN,
 
 int bandup_gpu_pipeline_depth(int handle);
 
+/* args%perform_unfold (cla_wrappers_mod.f90, flag -dont_unfold): with 0 every spectral weight
+ * is 1 (band_unfolding_routines_mod.f90:1346-1351) and delta_N counts the SC bands.  Default 1. */
+int bandup_gpu_set_perform_unfold(int handle, int perform_unfold);
+
+/* Replaces calc_spectral_function (band_unfolding_routines_mod.f90:654-698) for the resident
+ * SC-kpt `ikpt` (see the residency rule below): sf[fold][iener] = sum_m P_m * Gaussian(E_m - E_i)
+ * with standard deviation std_dev (<= 0: the reference's default 0.025 eV).  The reference
+ * compiles this step out (calc_spec_func_explicitly = .FALSE.); it is offered on request.
+ * sf [n_fold][nener] HOST. */
+int bandup_gpu_spectral_function(int handle, int ikpt, double std_dev, double *sf);
+
 /* ---- projected variant: unfolding-density operator ---------------------- */
 /* (`bandup unfold --orbitals` = -write_unf_dens_op, consumed by `projected-unfold`)
  *

@@ -331,6 +331,27 @@ void bo_delta_N(const double *energies, int64_t nener, const double *sc_ener,
   }
 }
 
+/* ---- math_mod.f90:159-178  delta (a Gaussian; std_dev given) --------------- */
+double bo_delta(double x, double std_dev) {
+  const double twopi = 2.0 * (4.0 * atan(1.0));
+  double stddev = fabs(std_dev);
+  double r = x / stddev;
+  return exp(-(r * r) / 2.0) / (stddev * sqrt(twopi));
+}
+
+/* ---- band_unfolding_routines_mod.f90:654-698  calc_spectral_function -------
+ * std_dev <= 0 means "not passed": sigma = 0.025. */
+void bo_spectral_function(const double *energies, int64_t nener, const double *sc_ener,
+                          const double *weights, int n_bands, double std_dev, double *sf) {
+  double sigma = std_dev > 0.0 ? std_dev : 0.025;
+#pragma omp parallel for schedule(guided)
+  for (int64_t ie = 0; ie < nener; ++ie) {
+    double E = energies[ie], acc = 0.0;
+    for (int ib = 0; ib < n_bands; ++ib) acc = acc + weights[ib] * bo_delta(sc_ener[ib] - E, sigma);
+    sf[ie] = acc;
+  }
+}
+
 /* ---- vasp_related_modules/read_wavecar_mod.f90:151-210
  *      get_max_nb1_nb2_and_nb3 ---------------------------------------------- */
 static double norm3(const double *a) {

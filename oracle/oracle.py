@@ -55,6 +55,8 @@ def lib() -> C.CDLL:
         L.bo_spectral_weights.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, _i32p, C.c_int64, _f64p]
         L.bo_delta_N.restype = None
         L.bo_delta_N.argtypes = [_f64p, C.c_int64, _f64p, _f64p, C.c_int, C.c_double, _f64p]
+        L.bo_spectral_function.restype = None
+        L.bo_spectral_function.argtypes = [_f64p, C.c_int64, _f64p, _f64p, C.c_int, C.c_double, _f64p]
         L.bo_commensurate.restype = C.c_int
         L.bo_commensurate.argtypes = [_f64p, _f64p, _f64p, _i32p, C.c_double]
         L.bo_vec_in_latt.restype = C.c_int
@@ -173,6 +175,14 @@ def delta_N(energies, sc_ener, weights, smearing=0.0):
     lib().bo_delta_N(_p(e, _f64p), e.shape[0], _p(s, _f64p), _p(w, _f64p), s.shape[0], float(smearing),
                      _p(dN, _f64p))
     return dN
+
+
+def spectral_function(energies, sc_ener, weights, std_dev=0.0):
+    e, s, w = _f64(energies), _f64(sc_ener), _f64(weights)
+    sf = np.zeros(e.shape[0])
+    lib().bo_spectral_function(_p(e, _f64p), e.shape[0], _p(s, _f64p), _p(w, _f64p), s.shape[0], float(std_dev),
+                               _p(sf, _f64p))
+    return sf
 
 
 def lam(pc_ener, sc_ener, delta_e, sigma):

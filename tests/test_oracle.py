@@ -241,3 +241,19 @@ def test_synth_fill_is_deterministic():
     c = O.synth_fill(1001, 3, 7, 3)
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     assert np.all(np.abs(a.real) <= 1.0) and a.std() > 0.05
+
+
+def test_spectral_function_c_vs_numpy():
+    rng = np.random.default_rng(2)
+    grid = O.real_seq(-3.0, 2.0, 0.05)
+    ener = np.sort(rng.uniform(-4.0, 3.0, 40))
+    w = rng.uniform(0.0, 1.0, 40)
+    for sd in (0.025, 0.1):
+        a = O.spectral_function(grid, ener, w, sd)
+        b = ON.spectral_function(grid, ener, w, sd)
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-300)
+    assert np.array_equal(O.spectral_function(grid, ener, w), O.spectral_function(grid, ener, w, 0.025))
+    # integrates to the total weight of the bands well inside the window
+    inside = (ener > -2.5) & (ener < 1.5)
+    fine = O.real_seq(-4.5, 3.5, 0.002)
+    assert abs(np.sum(O.spectral_function(fine, ener[inside], w[inside], 0.025)) * 0.002 - w[inside].sum()) < 1e-6
