@@ -64,6 +64,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not pin the rank to the CPU cores of its GPU's NUMA node")
     ap.add_argument("--per-kpt-launch", action="store_true",
                     help="launch K1..K3 once per SC k-point instead of once per step (batch)")
     return ap.parse_args()
@@ -145,8 +147,9 @@ def cpu_sample(sc, k_indices, seconds_budget, max_kpts, threads=None):
     body, main_BandUP.f90:145-172) on full-size SC k-points of the workload.  Returns
     (GB/s, kpts/s, cores, n_kpts_done, per-phase seconds)."""
     from oracle import oracle as O
-    if threads:
-        O.set_num_threads(threads)
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the
+    # reference's OpenMP loops are meant to run on every core)
+    O.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = O.num_threads()
     grid = O.real_seq(*sc.energy_window())
     rng = np.random.default_rng(SEED)
@@ -214,6 +217,8 @@ def run_b200(args, sc, rank, world, local_rank):
     if rank == 0:
         _build.build()
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"    # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     else:
@@ -222,6 +227,11 @@ def run_b200(args, sc, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = {"bound": False}
+    all_cpus = os.sched_getaffinity(0)
+    if not args.no_numa_bind:
+        from bandup_b200.numa import bind_to_gpu_node
+        numa = bind_to_gpu_node(local_rank)      # before any page-locked allocation (first touch)
     u = GpuUnfolder(local_rank)
     u.verify_commens(sc.b_pc, sc.B_sc)
     grid = u.set_energy_grid(*sc.energy_window())
@@ -377,7 +387,7 @@ def run_b200(args, sc, rank, world, local_rank):
         e2e = {"value": e2e_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "sc_kpts_per_s": kps * n_e2e * world / dt, "steps": n_e2e,
                "timer": "host monotonic clock between device synchronisations, max over ranks",
-               "bound": "PCIe host->device copy of the coefficient blocks"}
+               "bound": "PCIe host->device copy of the coefficient blocks", "numa": numa}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------
@@ -385,6 +395,7 @@ def run_b200(args, sc, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()
+        os.sched_setaffinity(0, all_cpus)        # the CPU baseline gets every host core again
         gbs, ckps, cores, done, phases = cpu_sample(sc, my_k, args.cpu_seconds, kps)
         cpu = {"value": gbs, "unit": UNIT, "cores": cores, "kind": "port", "sc_kpts_per_s": ckps,
                "sample": f"{done} full-size SC k-point(s) of the step's batch; C+OpenMP restatement of the "
