@@ -89,6 +89,7 @@ def load() -> C.CDLL:
         "bandup_gpu_orb_contrib_matrix": (C.c_int, [C.c_int, C.c_int, C.c_int, c_f64p, c_f64p, c_u8p, c_f64p,
                                                     C.c_double, C.c_double, c_f64p]),
         "bandup_gpu_set_operator": (C.c_int, [C.c_int, C.c_int, c_f64p]),
+        "bandup_gpu_pauli_vectors": (C.c_int, [C.c_int, C.c_int, c_f64p]),
         "bandup_gpu_set_perform_unfold": (C.c_int, [C.c_int, C.c_int]),
         "bandup_gpu_spectral_function": (C.c_int, [C.c_int, C.c_int, C.c_double, c_f64p]),
         "bandup_gpu_unfold_operator": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, c_f64p]),

@@ -951,7 +951,9 @@ int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t* n_energie
   const double* d_ener = static_cast<const double*>(fl->energies.p);
   {
     KernelScope k(c, BANDUP_GPU_K_RHO, s);
-    launch_rho_plan(d_grid, nener, c->sigma, d_ener, nb, nu, fl->d_dn_unique, min_dN, cap,
+    // perform_unfolding calls calc_rho WITHOUT std_dev (:1404-1407): lambda is the box
+    // (sigma = epsilon) here whatever smearing the delta_N grid was given
+    launch_rho_plan(d_grid, nener, kEpsDp, d_ener, nb, nu, fl->d_dn_unique, min_dN, cap,
                     static_cast<int*>(fl->pair_count.p), static_cast<long long*>(fl->pair_off.p),
                     static_cast<int*>(fl->overflow.p), s);
     c->launches++;  // plan + scan
@@ -998,7 +1000,7 @@ int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t* n_energie
     }
     {
       KernelScope k(c, BANDUP_GPU_K_RHO, s);
-      launch_rho_pairs(d_grid, nener, c->sigma, d_ener, nb, nu, fl->d_dn_unique, cap, fl->n_spinor,
+      launch_rho_pairs(d_grid, nener, kEpsDp, d_ener, nb, nu, fl->d_dn_unique, cap, fl->n_spinor,
                        static_cast<const long long*>(fl->sel_off.p), fl->csel.p,
                        static_cast<const int*>(fl->pair_count.p),
                        static_cast<const long long*>(fl->pair_off.p), static_cast<RhoPair*>(fl->pairs.p), s);
@@ -1095,6 +1097,42 @@ int bandup_gpu_spectral_function(int handle, int ikpt, double std_dev, double* s
   CU(cudaStreamSynchronize(s));
   for (int f = 0; f < fl->n_fold; ++f)
     std::memcpy(sf + (size_t)f * nener, h.data() + (size_t)fl->unique_of[f] * nener, sizeof(double) * (size_t)nener);
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_pauli_vectors(int handle, int ikpt, double* sigma) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  Flight* fl = nullptr;
+  int rc = need_resident(c, ikpt, &fl);
+  if (rc) return rc;
+  if (!fl->rho_ready) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_rho_count first");
+  if (fl->n_spinor != 2) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "Pauli vectors need a spinor wavefunction");
+  if (!sigma) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "sigma is NULL");
+  cudaSetDevice(c->device);
+  cudaStream_t s = c->compute;
+  const int nener = c->nener, cells = fl->n_unique * nener;
+  const long long n_pairs = fl->h_pair_off.empty() ? 0 : fl->h_pair_off[(size_t)cells];
+  DevBuf contrib;
+  CU(fl->trace_out.reserve(sizeof(double) * 3 * (size_t)cells));
+  cudaError_t e = contrib.reserve(sizeof(double) * 3 * (size_t)(n_pairs > 0 ? n_pairs : 1));
+  if (e != cudaSuccess) return cuda_fail(c, e, "pauli scratch");
+  {
+    KernelScope k(c, BANDUP_GPU_K_RHO, s);
+    launch_pauli(fl->coeffs.p, fl->stride_bytes, fl->n_pw, fl->layout, static_cast<const double*>(fl->norms.p),
+                 static_cast<const RhoPair*>(fl->pairs.p), n_pairs, cells,
+                 static_cast<const long long*>(fl->pair_off.p), static_cast<double*>(contrib.p),
+                 static_cast<double*>(fl->trace_out.p), s);
+  }
+  std::vector<double> h(3 * (size_t)cells);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), fl->trace_out.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  contrib.release();
+  if (e != cudaSuccess) return cuda_fail(c, e, "bandup_gpu_pauli_vectors");
+  for (int f = 0; f < fl->n_fold; ++f)
+    std::memcpy(sigma + 3 * (size_t)f * nener, h.data() + 3 * (size_t)fl->unique_of[f] * nener,
+                sizeof(double) * 3 * (size_t)nener);
   return BANDUP_GPU_OK;
 }
 

@@ -118,6 +118,10 @@ void launch_rho_pairs(const double* d_grid, int nener, double sigma, const doubl
 void launch_orb_contrib(int n_bands, int n_ao, const void* d_dual, const void* d_proj,
                         const uint8_t* d_mask, const double* d_ener, double max_dE, double min_abs,
                         void* d_O, cudaStream_t s);
+// K6: expectation values of the Pauli matrices, Re Tr(rho . sigma_i), spinor wavefunctions only
+void launch_pauli(const void* d_coeffs, long long stride_bytes, int n_pw, int layout, const double* d_norms,
+                  const RhoPair* d_pairs, long long n_pairs, int n_cells, const long long* d_pair_off,
+                  double* d_contrib, double* d_sigma, cudaStream_t s);
 void launch_trace(int n_cells, int n_bands, const double* d_dN, const long long* d_pair_off,
                   const RhoPair* d_pairs, const void* d_O, double min_abs_rho, int clip, double* d_out,
                   cudaStream_t s);

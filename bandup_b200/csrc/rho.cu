@@ -328,6 +328,84 @@ k5_trace(int n_cells, int n_bands, const double* __restrict__ dN_all,
   }
 }
 
+// K6a -- Pauli matrix elements between the two bands of every rho pair over ALL plane waves
+// (get_SC_pauli_matrix_elmnts, band_unfolding_routines_mod.f90:1164-1263), contracted on the
+// spot with rho: contrib[p][i] = the share of pair p in Re Tr(rho . sigma_i) (:1468-1476 with
+// trace_AB_A_is_rho_B_is_cplx, math_mod.f90:321-341):
+//   sigma_x(m2,m1) = <m2 a|m1 b> + <m2 b|m1 a>,  sigma_y = i(<m2 b|m1 a> - <m2 a|m1 b>),
+//   sigma_z = <m2 a|m1 a> - <m2 b|m1 b>,   <u|v> = sum_G conj(u) v  (renormalised coefficients)
+//   upper element rho(m1,m2), m1 < m2:  rho12 sigma(m2,m1) + conj(rho12) conj(sigma(m2,m1))
+// Only stored elements (|rho| >= 1e-5) enter, as in the reference's rhos(:).  One CTA per pair.
+template <int MODE>  // 1: [pw][spinor] interleaved, 2: [spinor][pw] blocked
+__global__ void __launch_bounds__(256)
+k6_pauli_pairs(const char* __restrict__ coeffs, long long stride_bytes, int n_pw,
+               const double* __restrict__ norms, const RhoPair* __restrict__ pairs,
+               double* __restrict__ contrib) {
+  __shared__ double s_red[8][8];
+  const RhoPair pr = pairs[blockIdx.x];
+  double* out = contrib + 3LL * blockIdx.x;
+  if (hypotf(pr.re, pr.im) < 1e-5f) {  // not stored by perform_unfolding (:1418)
+    if (threadIdx.x < 3) out[threadIdx.x] = 0.0;
+    return;
+  }
+  const float2* r1 = reinterpret_cast<const float2*>(coeffs + (long long)pr.m1 * stride_bytes);
+  const float2* r2 = reinterpret_cast<const float2*>(coeffs + (long long)pr.m2 * stride_bytes);
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ab, ba, aa, bb (re, im each)
+  for (int pw = threadIdx.x; pw < n_pw; pw += blockDim.x) {
+    const long long ia = (MODE == 1) ? 2LL * pw : pw, ib = (MODE == 1) ? 2LL * pw + 1 : (long long)n_pw + pw;
+    const float2 xa = r2[ia], xb = r2[ib], ya = r1[ia], yb = r1[ib];  // x: band m2 (bra), y: band m1 (ket)
+    const double xar = xa.x, xai = xa.y, xbr = xb.x, xbi = xb.y, yar = ya.x, yai = ya.y, ybr = yb.x, ybi = yb.y;
+    acc[0] += xar * ybr + xai * ybi;  acc[1] += xar * ybi - xai * ybr;   // conj(x_a) y_b
+    acc[2] += xbr * yar + xbi * yai;  acc[3] += xbr * yai - xbi * yar;   // conj(x_b) y_a
+    acc[4] += xar * yar + xai * yai;  acc[5] += xar * yai - xai * yar;   // conj(x_a) y_a
+    acc[6] += xbr * ybr + xbi * ybi;  acc[7] += xbr * ybi - xbi * ybr;   // conj(x_b) y_b
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    double v = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[8];
+    for (int q = 0; q < 8; ++q) {
+      double v = 0.0;
+      for (int w = 0; w < 8; ++w) v += s_red[w][q];
+      t[q] = v;
+    }
+    const double s1 = norms[pr.m1], s2 = norms[pr.m2];
+    const double f = (s1 > kEps ? 1.0 / sqrt(fabs(s1)) : 1.0) * (s2 > kEps ? 1.0 / sqrt(fabs(s2)) : 1.0);
+    const double sxr = f * (t[0] + t[2]), sxi = f * (t[1] + t[3]);
+    const double syr = -f * (t[3] - t[1]), syi = f * (t[2] - t[0]);  // i * (ba - ab)
+    const double szr = f * (t[4] - t[6]), szi = f * (t[5] - t[7]);
+    const double rr = pr.re, ri = pr.im;
+    const double w = (pr.m1 == pr.m2) ? 1.0 : 2.0;
+    out[0] = w * (rr * sxr - ri * sxi);
+    out[1] = w * (rr * syr - ri * syi);
+    out[2] = w * (rr * szr - ri * szi);
+  }
+}
+
+// K6b -- sigma[cell][i] = sum over the cell's pairs, in pair order (deterministic).
+__global__ void __launch_bounds__(128)
+k6_pauli_cells(int n_cells, const long long* __restrict__ pair_off, const double* __restrict__ contrib,
+               double* __restrict__ sigma) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (long long p = pair_off[cell]; p < pair_off[cell + 1]; ++p) {
+    a += contrib[3 * p];
+    b += contrib[3 * p + 1];
+    c += contrib[3 * p + 2];
+  }
+  sigma[3LL * cell] = a;
+  sigma[3LL * cell + 1] = b;
+  sigma[3LL * cell + 2] = c;
+}
+
 }  // namespace
 
 size_t rho_plan_smem(int cap) { return (size_t)cap * 12 + 64 * sizeof(int); }
@@ -391,6 +469,20 @@ void launch_orb_contrib(int n_bands, int n_ao, const void* d_dual, const void* d
   k5_orb_contrib<<<n_bands, 256, 0, s>>>(n_bands, n_ao, static_cast<const double2*>(d_dual),
                                          static_cast<const double2*>(d_proj), d_mask, d_ener, max_dE,
                                          min_abs, static_cast<double2*>(d_O));
+}
+
+void launch_pauli(const void* d_coeffs, long long stride_bytes, int n_pw, int layout, const double* d_norms,
+                  const RhoPair* d_pairs, long long n_pairs, int n_cells, const long long* d_pair_off,
+                  double* d_contrib, double* d_sigma, cudaStream_t s) {
+  if (n_cells <= 0) return;
+  const char* c = static_cast<const char*>(d_coeffs);
+  if (n_pairs > 0) {
+    if (layout == BANDUP_GPU_LAYOUT_FORTRAN_INMEM)
+      k6_pauli_pairs<1><<<(unsigned)n_pairs, 256, 0, s>>>(c, stride_bytes, n_pw, d_norms, d_pairs, d_contrib);
+    else
+      k6_pauli_pairs<2><<<(unsigned)n_pairs, 256, 0, s>>>(c, stride_bytes, n_pw, d_norms, d_pairs, d_contrib);
+  }
+  k6_pauli_cells<<<(n_cells + 127) / 128, 128, 0, s>>>(n_cells, d_pair_off, d_contrib, d_sigma);
 }
 
 void launch_trace(int n_cells, int n_bands, const double* d_dN, const long long* d_pair_off,

@@ -285,6 +285,13 @@ class GpuUnfolder:
             im.ctypes.data_as(f32p)))
         return UnfoldDensityOps(ne.value, fold, iener, m1, m2, (re + 1j * im).astype(np.complex64))
 
+    def pauli_vectors(self, ikpt: int, n_fold: int) -> np.ndarray:
+        """unf_pauli_vec = Re Tr(rho . sigma_i) for every (pc-kpt, energy) with a rho
+        (get_SC_pauli_matrix_elmnts + band_unfolding_routines_mod.f90:1459-1481); (n_fold, nener, 3)."""
+        out = np.zeros((n_fold, self.nener, 3), dtype=np.float64)
+        self._check(self._lib.bandup_gpu_pauli_vectors(self.handle, int(ikpt), out.ctypes.data_as(c_f64p)))
+        return out
+
     def get_orbital_contribution_matrix(self, proj_matrix_dual: np.ndarray, proj_matrix: np.ndarray,
                                         ao_mask: np.ndarray, band_energies: np.ndarray,
                                         max_band_dE: float = 0.1, min_abs: float = 1e-2) -> np.ndarray:
@@ -389,6 +396,21 @@ class GpuUnfolder:
     def set_tuning(self, chunk_vecs: int = 0, ctas_per_sm: int = 0, n_stages: int = 0) -> None:
         self._check(self._lib.bandup_gpu_set_tuning(self.handle, int(chunk_vecs), int(ctas_per_sm),
                                                     int(n_stages)))
+
+
+def calc_spin_projections(pauli_vector, cart_coords_kpt, normal_to_proj_plane, origin=None):
+    """calc_spin_projections (band_unfolding_routines_mod.f90:1266-1286; BETA in the reference):
+    components of the unfolded Pauli vector perpendicular / parallel to the k-point direction
+    within the plane of normal `normal_to_proj_plane`.  Plain 3-vector algebra on the host, as in
+    the reference.  Returns (spin_proj_perp, spin_proj_para)."""
+    def versor(v):
+        v = np.asarray(v, dtype=np.float64)
+        return v / np.linalg.norm(v)
+    o = np.zeros(3) if origin is None else np.asarray(origin, dtype=np.float64)
+    para = versor(np.asarray(cart_coords_kpt, dtype=np.float64) - o)
+    perp = versor(np.cross(versor(normal_to_proj_plane), para))
+    pv = np.asarray(pauli_vector, dtype=np.float64)
+    return float(np.dot(pv, perp)), float(np.dot(pv, para))
 
 
 def pinned_empty(nbytes: int) -> np.ndarray:

@@ -21,7 +21,9 @@ public :: bandup_gpu_init, bandup_gpu_finalize, bandup_gpu_last_error, &
           bandup_gpu_pipeline_depth, bandup_gpu_set_profiling, &
           bandup_gpu_kernel_time, bandup_gpu_reset_kernel_times, &
           bandup_gpu_launch_count, bandup_gpu_set_tuning, &
-          bandup_gpu_rho_count, bandup_gpu_fetch_rho, &
+          bandup_gpu_rho_count, bandup_gpu_fetch_rho, bandup_gpu_pauli_vectors, &
+          bandup_gpu_spectral_function, bandup_gpu_set_perform_unfold, &
+          bandup_gpu_orb_contrib_matrix, bandup_gpu_set_operator, bandup_gpu_unfold_operator, &
           bandup_gpu_unfold_kpt_f, bandup_gpu_error_message
 public :: BANDUP_GPU_OK, BANDUP_GPU_LAYOUT_FORTRAN_INMEM, BANDUP_GPU_LAYOUT_VASP_RECORD, &
           BANDUP_GPU_MAX_FOLDS
@@ -161,6 +163,64 @@ interface
         real(c_float), intent(out) :: rho_re(*), rho_im(*)
         integer(c_int) :: bandup_gpu_fetch_rho
     end function bandup_gpu_fetch_rho
+
+    ! spinor wavefunctions: sigma(3, nener, n_fold) = Re Tr(rho . sigma_i)
+    ! (get_SC_pauli_matrix_elmnts + band_unfolding_routines_mod.f90:1459-1481)
+    function bandup_gpu_pauli_vectors(handle, ikpt, sigma) bind(c, name='bandup_gpu_pauli_vectors')
+        import c_int, c_double
+        integer(c_int), intent(in), value :: handle, ikpt
+        real(c_double), intent(out) :: sigma(3,*)
+        integer(c_int) :: bandup_gpu_pauli_vectors
+    end function bandup_gpu_pauli_vectors
+
+    ! calc_spectral_function (:654-698) for the resident SC-kpt; sf(nener, n_fold)
+    function bandup_gpu_spectral_function(handle, ikpt, std_dev, sf) &
+        bind(c, name='bandup_gpu_spectral_function')
+        import c_int, c_double
+        integer(c_int), intent(in), value :: handle, ikpt
+        real(c_double), intent(in), value :: std_dev
+        real(c_double), intent(out) :: sf(*)
+        integer(c_int) :: bandup_gpu_spectral_function
+    end function bandup_gpu_spectral_function
+
+    ! args%perform_unfold: 0 == -dont_unfold
+    function bandup_gpu_set_perform_unfold(handle, perform_unfold) &
+        bind(c, name='bandup_gpu_set_perform_unfold')
+        import c_int
+        integer(c_int), intent(in), value :: handle, perform_unfold
+        integer(c_int) :: bandup_gpu_set_perform_unfold
+    end function bandup_gpu_set_perform_unfold
+
+    ! projected-unfold without the text round trip (bandupy/orbital_contributions.py:304-362,
+    ! unfolding_density_op.py:121-141); complex(c_double_complex) arrays in C (row-major) order
+    function bandup_gpu_orb_contrib_matrix(handle, n_bands, n_ao, dual, proj, ao_mask, band_energies, &
+                                           max_band_dE, min_abs, O_out) &
+        bind(c, name='bandup_gpu_orb_contrib_matrix')
+        import c_int, c_double, c_int8_t, c_ptr
+        integer(c_int), intent(in), value :: handle, n_bands, n_ao
+        real(c_double), intent(in) :: dual(*), proj(*), band_energies(*)
+        integer(c_int8_t), intent(in) :: ao_mask(*)
+        real(c_double), intent(in), value :: max_band_dE, min_abs
+        type(c_ptr), intent(in), value :: O_out
+        integer(c_int) :: bandup_gpu_orb_contrib_matrix
+    end function bandup_gpu_orb_contrib_matrix
+
+    function bandup_gpu_set_operator(handle, n_bands, O) bind(c, name='bandup_gpu_set_operator')
+        import c_int, c_double
+        integer(c_int), intent(in), value :: handle, n_bands
+        real(c_double), intent(in) :: O(*)
+        integer(c_int) :: bandup_gpu_set_operator
+    end function bandup_gpu_set_operator
+
+    function bandup_gpu_unfold_operator(handle, ikpt, min_abs_rho, clip, out) &
+        bind(c, name='bandup_gpu_unfold_operator')
+        import c_int, c_double
+        integer(c_int), intent(in), value :: handle, ikpt
+        real(c_double), intent(in), value :: min_abs_rho
+        integer(c_int), intent(in), value :: clip
+        real(c_double), intent(out) :: out(*)
+        integer(c_int) :: bandup_gpu_unfold_operator
+    end function bandup_gpu_unfold_operator
 
     function bandup_gpu_set_profiling(handle, enabled) bind(c, name='bandup_gpu_set_profiling')
         import c_int

@@ -185,6 +185,15 @@ int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t *n_energie
 int bandup_gpu_fetch_rho(int handle, int ikpt, int64_t capacity, int32_t *fold, int32_t *iener,
                          int32_t *m1, int32_t *m2, float *rho_re, float *rho_im);
 
+/* Spinor wavefunctions: replaces get_SC_pauli_matrix_elmnts + the trace loop of
+ * perform_unfolding (band_unfolding_routines_mod.f90:1164-1263, :1459-1481) for every operator
+ * counted by the last bandup_gpu_rho_count(ikpt):
+ *   sigma[fold][iener][i] = Re Tr(rho . sigma_i),  i = x, y, z      (0 where there is no rho)
+ * the three spin columns of the reference's output file (io_routines_mod.f90:950-960); the
+ * in-plane projections (calc_spin_projections, :1266-1286) are 3-vector algebra the caller
+ * does from these.  sigma [n_fold][nener][3] HOST.  ERR_INVALID_ARG for n_spinor = 1. */
+int bandup_gpu_pauli_vectors(int handle, int ikpt, double *sigma);
+
 /* Replaces KptInfo.get_orbital_contribution_matrix with use_dual=True
  * (python_interface/bandupy/orbital_contributions.py:226-362):
  *   O(m1,m2) = sum_{a: ao_mask[a]} dual[m1,a] * proj[a,m2]

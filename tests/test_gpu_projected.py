@@ -21,7 +21,9 @@ def _setup(u, sc, smearing=None):
 
 
 def _oracle_rhos(sc, coeffs, gf, ener, fG, grid, sigma=None):
-    """{(fold, iener1): dense rho (fp64 dots)} for every energy with dN >= 1e-3, plus dN."""
+    """{(fold, iener1): dense rho (fp64 dots)} for every energy with dN >= 1e-3, plus dN.
+    `sigma` smears delta_N only: perform_unfolding calls calc_rho without std_dev, so rho's
+    lambdas are always the box (band_unfolding_routines_mod.f90:1404-1407)."""
     from oracle import oracle as O
     from oracle import oracle_np as ON
     gc = gf @ sc.B_sc
@@ -34,8 +36,8 @@ def _oracle_rhos(sc, coeffs, gf, ener, fG, grid, sigma=None):
         dN = O.delta_N(grid, ener, w, smearing=sigma or 0.0)
         dNs.append(dN)
         for ie in np.nonzero(dN >= 1e-3)[0]:
-            rho = ON.calc_rho(c_ren, sel, ener, dN[ie], grid[ie], de, sigma=sigma or ON.EPS_DP)
-            rho32 = O.calc_rho(c_ren, sel, ener, dN[ie], grid[ie], de, sigma=sigma or 0.0)
+            rho = ON.calc_rho(c_ren, sel, ener, dN[ie], grid[ie], de, sigma=ON.EPS_DP)
+            rho32 = O.calc_rho(c_ren, sel, ener, dN[ie], grid[ie], de, sigma=0.0)
             out[(f, int(ie) + 1)] = (rho, rho32)
     return out, np.array(dNs)
 
@@ -88,7 +90,8 @@ def test_rho_matches_oracle(unfolder, name, scale, iK):
 
 
 def test_rho_with_gaussian_smearing_and_shared_coset(unfolder):
-    """sigma = 0.03 eV couples many bands per energy; two pc-kpts in the same coset share rho."""
+    """delta_N smeared with sigma = 0.03 eV (rho keeps the box lambda, as in the reference); two
+    pc-kpts in the same coset share rho."""
     from bandup_b200.unfold import PwWavefunction
     sc = synth.make_scenario("graphene4x4", scale=0.12)
     grid = _setup(unfolder, sc, smearing=0.03)
@@ -198,3 +201,49 @@ def test_projected_unfold_config4(unfolder):
         for ie in res.energies_of(f):
             tr = np.trace(res.dense(f, ie, nb)).real
             assert abs(ident[f, ie - 1] - out.dN[f, ie - 1] * tr) <= 1e-6 * out.dN[f, ie - 1]
+
+
+def test_pauli_vectors_spinor(unfolder):
+    """Config 3 in miniature (MoS2 8x8, spinor): Re Tr(rho sigma_i) per (k, E) against the NumPy
+    restatement of get_SC_pauli_matrix_elmnts + the trace loop, including its keep-what-was-computed
+    cache across energies; spin projections are host 3-vector algebra."""
+    from bandup_b200.unfold import BandupGpuError, PwWavefunction, calc_spin_projections
+    from oracle import oracle as O
+    from oracle import oracle_np as ON
+    sc = synth.make_scenario("mos2_8x8_spinor", scale=0.06)
+    grid = _setup(unfolder, sc)
+    iK = 1
+    coeffs, gf, ener = synth.make_wavefunction(sc, iK)
+    nb = coeffs.shape[0]
+    ener[2] = ener[1]
+    ener[5] = ener[4] + 0.01
+    ener = np.sort(ener)
+    fG = sc.folding_G(iK)
+    unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), folding_G=fG, ikpt=7)
+    res = unfolder.calc_rho(7)
+    pv = unfolder.pauli_vectors(7, fG.shape[0])
+    assert pv.shape == (fG.shape[0], len(grid), 3)
+    c_ren, _ = O.renormalize(coeffs, 1)
+    de = grid[1] - grid[0]
+    checked = 0
+    for f in range(fG.shape[0]):
+        rhos = {int(ie): res.dense(f, int(ie), nb) for ie in res.energies_of(f)}
+        want = ON.unfolded_pauli_vectors(c_ren, ener, grid, rhos, de)
+        for ie, vec in want.items():
+            assert np.all(np.abs(pv[f, ie - 1] - vec) <= 2e-6 * max(1.0, np.abs(vec).max())), (f, ie)
+            assert np.all(np.abs(vec) <= 1.0 + 1e-4)            # |<sigma>| <= Tr rho ~ 1
+            checked += 1
+        has = np.zeros(len(grid), dtype=bool)
+        has[np.array(sorted(rhos), dtype=int) - 1] = True
+        assert not pv[f][~has].any()
+    assert checked > 5
+    perp, para = calc_spin_projections([0.3, -0.2, 0.9], [1.0, 1.0, 0.0], [0.0, 0.0, 1.0])
+    assert abs(para - (0.3 - 0.2) / np.sqrt(2)) < 1e-14 and abs(perp - (-0.3 - 0.2) / np.sqrt(2)) < 1e-14
+    # scalar wavefunctions have no Pauli vector
+    sc1 = synth.make_scenario("graphene4x4", scale=0.08)
+    _setup(unfolder, sc1)
+    unfolder.perform_unfolding(PwWavefunction(*synth.make_wavefunction(sc1, 0)), folding_G=sc1.folding_G(0), ikpt=8)
+    unfolder.calc_rho(8)
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.pauli_vectors(8, 1)
+    assert ei.value.code == 1
