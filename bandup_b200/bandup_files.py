@@ -1,0 +1,221 @@
+"""BandUP's text input/output files on either side of the unfolding path -- just enough of the
+reference's formats for a file-level drop-in of `bandup unfold` under its no-symmetry flags
+(-no_symm_sckpts -no_symm_avg): the lattices, the pc k-point path, the energy window go in, the
+`unfolded_EBS_*.dat` table comes out in the column format `bandup plot` reads with np.loadtxt
+(python_interface/bandupy/plot.py:143-175).  Nothing here computes weights.
+
+  prim_cell_lattice.in / supercell_lattice.in   POSCAR-style (read_vasp_files_mod.f90:63-200):
+        comment / scaling factor / three lattice vectors; atoms, if any, are ignored here
+  KPOINTS_prim_cell.in    VASP line-mode style (io_routines_mod.f90:981-1211): title / numbers of
+        k-points per direction / 'Line-mode [zero_of_kpts_scale]' / 'Reciprocal' or
+        'Cartesian a0' / pairs of start-end lines separated by blank lines
+  energy_info.in          E_Fermi / Emin-E_F / Emax-E_F / dE or 'auto' (io_routines_mod.f90:334-388)
+  unfolded_EBS_*.dat      '(2(f8.4,2X),ES10.3)' k-coordinate, E-E_F, delta_N; k outer, E inner,
+        directions concatenated (write_band_struc, io_routines_mod.f90:889-977); with spin info
+        five more ES10.3 columns (sigma_x, sigma_y, sigma_z, spin perp, spin para)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from pathlib import Path
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import synth
+
+TWOPI = 2.0 * (4.0 * math.atan(1.0))
+
+
+def read_lattice(path) -> np.ndarray:
+    """Rows = lattice vectors in Angstrom (scaling factor applied)."""
+    lines = Path(path).read_text().splitlines()
+    scale = float(lines[1].split()[0])
+    vecs = np.array([[float(x) for x in lines[2 + i].split("#")[0].split("!")[0].split()[:3]] for i in range(3)])
+    return scale * vecs
+
+
+def write_lattice(path, latt: np.ndarray, comment: str = "cell") -> None:
+    a = np.asarray(latt, dtype=np.float64)
+    rows = "\n".join("  %22.16f %22.16f %22.16f" % tuple(v) for v in a)
+    Path(path).write_text(f"{comment}\n   1.0\n{rows}\n")
+
+
+def kpts_line(kstart, kend, nk: int) -> np.ndarray:
+    """lists_and_seqs_mod.f90:219-241: nk points from kstart to kend inclusive."""
+    kstart, kend = np.asarray(kstart, dtype=np.float64), np.asarray(kend, dtype=np.float64)
+    step = (kend - kstart) / float(nk - 1) if nk > 1 else np.zeros(3)
+    return np.array([kstart + float(i) * step for i in range(nk)])
+
+
+@dataclass
+class PcKptsPath:
+    directions: List[np.ndarray]      # per direction: (n_k, 3) Cartesian pc k-points
+    zero_of_kpts_scale: float
+
+    @property
+    def all_kpts(self) -> np.ndarray:
+        return np.concatenate(self.directions, axis=0)
+
+
+def read_pckpts(path, b_matrix_pc: np.ndarray) -> PcKptsPath:
+    """read_pckpts_selected_by_user + kpts_line for every direction
+    (define_pckpts_to_be_checked, band_unfolding_routines_mod.f90:486-547)."""
+    lines = Path(path).read_text().splitlines()
+    if len(lines) < 6:
+        raise ValueError("ERROR reading input pc-kpts file. Please check the format.")
+    n_line, mode_line, coord_line = lines[1].strip(), lines[2].strip(), lines[3].strip()
+    try:
+        counts = [int(x) for x in n_line.split()]
+    except ValueError:
+        raise ValueError("automatic scan for pc-kpts (non-numeric second line) is not supported here")
+    toks = mode_line.split()
+    zero = 0.0
+    if len(toks) > 1:
+        try:
+            zero = float(toks[1])
+        except ValueError:
+            zero = 0.0
+    ctoks = coord_line.split()
+    cartesian = ctoks[0][:1].upper() == "C"
+    a0 = None
+    if len(ctoks) > 1:
+        try:
+            a0 = float(ctoks[1])
+        except ValueError:
+            a0 = None
+    if cartesian and a0 is None:
+        try:
+            a0 = float(lines[0].split()[0])           # deprecated: a0 on the first line
+        except (ValueError, IndexError):
+            raise ValueError('cartesian coordinates need the scaling parameter "a0" after the tag')
+    pairs: List[Tuple[np.ndarray, np.ndarray]] = []
+    body = [ln.split("!")[0].strip() for ln in lines[4:]]
+    block: List[np.ndarray] = []
+    for ln in body + [""]:
+        if ln == "":
+            if len(block) == 2:
+                pairs.append((block[0], block[1]))
+            elif len(block) != 0:
+                raise ValueError("ERROR reading input pc-kpts file. Please check the format.")
+            block = []
+        else:
+            block.append(np.array([float(x) for x in ln.split()[:3]]))
+    if not pairs:
+        raise ValueError("no pc-kpt direction found")
+    if len(counts) < len(pairs):
+        counts = [counts[0]] * len(pairs)
+    b = np.asarray(b_matrix_pc, dtype=np.float64)
+    dirs = []
+    for (ks, ke), nk in zip(pairs, counts):
+        if cartesian:
+            ks_c, ke_c = TWOPI * ks / a0, TWOPI * ke / a0
+        else:
+            ks_c, ke_c = ks @ b, ke @ b
+        if np.linalg.norm(ks_c - ke_c) < np.finfo(float).eps:
+            nk = 1
+        dirs.append(kpts_line(ks_c, ke_c, nk))
+    return PcKptsPath(dirs, zero)
+
+
+def write_pckpts(path, segments_frac: Sequence[Tuple[Sequence[float], Sequence[float]]], counts: Sequence[int],
+                 title: str = "pc k-points", zero: float = 0.0) -> None:
+    out = [title, " " + " ".join(str(int(c)) for c in counts), f"Line-mode {zero:.9f}", "Reciprocal"]
+    for i, (a, b) in enumerate(segments_frac):
+        out.append("   %.12f  %.12f  %.12f    1" % tuple(a))
+        out.append("   %.12f  %.12f  %.12f    1" % tuple(b))
+        if i + 1 < len(segments_frac):
+            out.append("")
+    Path(path).write_text("\n".join(out) + "\n")
+
+
+def read_energy_info(path) -> Tuple[float, float, float, float]:
+    """(e_fermi, E_start, E_end, delta_e) as read_energy_info_for_band_search builds them."""
+    vals = []
+    for ln in Path(path).read_text().splitlines():
+        t = ln.strip()
+        if not t or t.startswith("#"):
+            continue
+        vals.append(t.split("!")[0].split()[0])
+        if len(vals) == 4:
+            break
+    if len(vals) < 4:
+        raise ValueError("energy file needs E_Fermi, Emin-E_F, Emax-E_F and dE")
+    e_fermi = float(vals[0])
+    e_start, e_end = float(vals[1]) + e_fermi, float(vals[2]) + e_fermi
+    if e_end < e_start:
+        e_start, e_end = e_end, e_start
+    try:
+        de = abs(float(vals[3]))
+    except ValueError:
+        de = abs(0.4e-2 * (e_end - e_start))          # 'auto': 0.4 % of the window
+    return e_fermi, e_start, e_end, de
+
+
+def write_energy_info(path, e_fermi: float, emin: float, emax: float, dE) -> None:
+    Path(path).write_text(f" {e_fermi}  ! E-Fermi, in eV\n{emin}    ! Emin - E-Fermi, in eV\n"
+                          f"{emax}     ! Emax - E-Fermi, in eV\n{dE}     ! Increment, in eV\n")
+
+
+def _es(x: float) -> str:
+    """Fortran ES10.3."""
+    return "%10.3E" % x
+
+
+def write_band_struc(path, kpath: PcKptsPath, energy_grid: np.ndarray, dN: np.ndarray, e_fermi: float = 0.0,
+                     sigma: Optional[np.ndarray] = None, spin_proj: Optional[np.ndarray] = None,
+                     header: str = "# File created by bandup-b200 (GPU unfolding path)") -> None:
+    """write_band_struc (io_routines_mod.f90:889-977).  dN: (n_pckpts_total, nener) in the order of
+    kpath.all_kpts; sigma (n, nener, 3) and spin_proj (n, nener, 2) add the five spin columns."""
+    grid = np.asarray(energy_grid, dtype=np.float64)
+    with open(path, "w") as f:
+        f.write(header.rstrip("\n") + "\n")
+        if sigma is not None:
+            f.write("#KptCoord #E-E_Fermi #delta_N   #sigma_x    #sigma_y    #sigma_z    #Spin _|_ k #Spin // k \n")
+        else:
+            f.write("#KptCoord #E-E_Fermi #delta_N \n")
+        coord_first = kpath.zero_of_kpts_scale
+        row = 0
+        coord_k = coord_first
+        for d in kpath.directions:
+            first = d[0]
+            for k in d:
+                coord_k = coord_first + float(np.linalg.norm(k - first))
+                for ie, E in enumerate(grid):
+                    line = "%8.4f  %8.4f  %s" % (coord_k, E - e_fermi, _es(dN[row, ie]))
+                    if sigma is not None:
+                        cols = list(sigma[row, ie]) + (list(spin_proj[row, ie]) if spin_proj is not None else [0.0, 0.0])
+                        line += "  " + "  ".join(_es(c) for c in cols) + "  "
+                    f.write(line + "\n")
+                row += 1
+            coord_first = coord_k
+
+
+def read_band_struc(path) -> np.ndarray:
+    """The numeric columns, the way `bandup plot` loads them (plot.py:143-175: np.loadtxt)."""
+    return np.loadtxt(path, comments="#")
+
+
+def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_file, energy_file,
+                out_file: Optional[str] = None, spin_channel: int = 1):
+    """`bandup unfold` at file level for -no_symm_sckpts -no_symm_avg: parse the reference's input
+    files, run every SC-kpt of the WAVECAR through the GPU (wavecar.unfold_wavecar) and write
+    unfolded_EBS_not-symmetry_averaged.dat.  Returns (kpath, energy_grid, dN)."""
+    from .wavecar import Wavecar, unfold_wavecar
+    a_pc = read_lattice(prim_cell_file)
+    A_sc = read_lattice(supercell_file)
+    b_pc = synth.rec_latt(a_pc)
+    wc = Wavecar(wavecar_path)
+    # the SC of the wavefunction file must be the one of supercell_lattice.in (main_BandUP.f90:57-70)
+    if not np.allclose(A_sc, wc.A_matrix, rtol=0, atol=1e-4 * np.abs(A_sc).max()):
+        raise ValueError("supercell_lattice.in and the WAVECAR disagree about the supercell")
+    kpath = read_pckpts(pckpts_file, b_pc)
+    e_fermi, e_start, e_end, de = read_energy_info(energy_file)
+    got, grid = unfold_wavecar(unfolder, wc, b_pc, kpath.all_kpts, e_start, e_end, de, ispin=spin_channel)
+    if got.row_ids.tolist() != list(range(kpath.all_kpts.shape[0])):
+        # main_BandUP.f90:114: every requested pc-kpt must have been unfolded exactly once
+        raise RuntimeError("not every pc-kpt was unfolded")
+    if out_file:
+        write_band_struc(out_file, kpath, grid, got.dN, e_fermi)
+    return kpath, grid, got.dN

@@ -449,3 +449,43 @@ def test_deviation_from_faithful_fp32_norm_is_bounded(unfolder):
     assert dev <= 5e-5
     print(f"max rel deviation from the fp32-norm restatement: {dev:.2e}; fp32 vs fp64 oracle: "
           f"{rel_err(w32, w64):.2e}")
+
+
+def test_unfold_task_file_level(unfolder, tmp_path):
+    """`bandup unfold` at file level (-no_symm_sckpts -no_symm_avg): prim_cell_lattice.in,
+    supercell_lattice.in, KPOINTS_prim_cell.in, energy_info.in and a WAVECAR go in,
+    unfolded_EBS_not-symmetry_averaged.dat comes out in the format `bandup plot` loads; the numbers
+    are the oracle's (in memory to 1e-6; in the file to the 4 digits ES10.3 keeps)."""
+    from bandup_b200 import bandup_files as BF
+    from bandup_b200.wavecar import write_wavecar
+    from oracle import oracle as O
+    a = synth.hex_cell(2.467, 15.0)
+    b = synth.rec_latt(a)
+    segs = [([1 / 3, 1 / 3, 0.0], [0.0, 0.0, 0.0]), ([0.0, 0.0, 0.0], [0.5, 0.0, 0.0])]
+    counts = [5, 4]
+    kcart = np.concatenate([BF.kpts_line(np.array(s) @ b, np.array(e) @ b, n) for (s, e), n in zip(segs, counts)])
+    sc = synth.Scenario("graphene4x4", a, np.diag([4, 4, 1]), 400.0 * 0.08, 6, 1, kcart, e_fermi=-1.25,
+                        emin=-12.0, emax=6.0, dE=0.1)
+    data = [synth.make_wavefunction(sc, iK) for iK in range(sc.n_sc_kpts)]
+    BF.write_lattice(tmp_path / "prim_cell_lattice.in", a, "graphene pc")
+    BF.write_lattice(tmp_path / "supercell_lattice.in", sc.A_sc, "graphene 4x4")
+    BF.write_pckpts(tmp_path / "KPOINTS_prim_cell.in", segs, counts)
+    BF.write_energy_info(tmp_path / "energy_info.in", sc.e_fermi, sc.emin, sc.emax, sc.dE)
+    write_wavecar(tmp_path / "WAVECAR", sc.A_sc, sc.ecut, list(sc.sc_kpts_frac), [d[0] for d in data],
+                  [d[2] for d in data])
+    out = tmp_path / "unfolded_EBS_not-symmetry_averaged.dat"
+    kpath, grid, dN = BF.unfold_task(unfolder, tmp_path / "WAVECAR", tmp_path / "prim_cell_lattice.in",
+                                     tmp_path / "supercell_lattice.in", tmp_path / "KPOINTS_prim_cell.in",
+                                     tmp_path / "energy_info.in", out_file=str(out))
+    assert np.array_equal(grid, O.real_seq(*sc.energy_window()))
+    want = np.zeros_like(dN)
+    for iK in range(sc.n_sc_kpts):
+        coeffs, gf, ener = data[iK]
+        _, d, _, _ = O.unfold_kpt(coeffs, gf @ sc.B_sc, ener, sc.b_pc, sc.folding_G(iK), grid, norm_mode=1)
+        want[np.asarray(sc.folds[iK])] = d
+    assert rel_err(dN, want) <= REL_TOL
+    tab = BF.read_band_struc(out)
+    assert tab.shape == (sum(counts) * len(grid), 3)
+    assert np.allclose(tab[:, 2].reshape(sum(counts), len(grid)), want, rtol=6e-4, atol=1e-12)
+    assert np.allclose(tab[:len(grid), 1], grid - sc.e_fermi, atol=5e-5)
+    assert tab[-1, 0] > tab[0, 0] and np.all(np.diff(tab[::len(grid), 0]) >= -1e-12)
