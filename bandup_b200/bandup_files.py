@@ -198,10 +198,12 @@ def read_band_struc(path) -> np.ndarray:
 
 
 def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_file, energy_file,
-                out_file: Optional[str] = None, spin_channel: int = 1):
+                out_file: Optional[str] = None, spin_channel: int = 1, unf_dens_op_file: Optional[str] = None):
     """`bandup unfold` at file level for -no_symm_sckpts -no_symm_avg: parse the reference's input
     files, run every SC-kpt of the WAVECAR through the GPU (wavecar.unfold_wavecar) and write
-    unfolded_EBS_not-symmetry_averaged.dat.  Returns (kpath, energy_grid, dN)."""
+    unfolded_EBS_not-symmetry_averaged.dat; with unf_dens_op_file (the reference's
+    -write_unf_dens_op, i.e. `bandup unfold --orbitals`) also the unfolding-density operators in the
+    text format `bandup projected-unfold` reads.  Returns (kpath, energy_grid, dN)."""
     from .wavecar import Wavecar, unfold_wavecar
     a_pc = read_lattice(prim_cell_file)
     A_sc = read_lattice(supercell_file)
@@ -212,10 +214,154 @@ def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_f
         raise ValueError("supercell_lattice.in and the WAVECAR disagree about the supercell")
     kpath = read_pckpts(pckpts_file, b_pc)
     e_fermi, e_start, e_end, de = read_energy_info(energy_file)
-    got, grid = unfold_wavecar(unfolder, wc, b_pc, kpath.all_kpts, e_start, e_end, de, ispin=spin_channel)
+    rho_by_row = {}
+
+    def collect_rho(iK, res, row_ids):
+        ops = unfolder.calc_rho(iK)
+        for f, row in enumerate(row_ids):
+            s = ops.fold == f
+            rho_by_row[int(row)] = (ops.iener[s], ops.m1[s], ops.m2[s], ops.rho[s])
+
+    got, grid = unfold_wavecar(unfolder, wc, b_pc, kpath.all_kpts, e_start, e_end, de, ispin=spin_channel,
+                               after_fetch=collect_rho if unf_dens_op_file else None)
     if got.row_ids.tolist() != list(range(kpath.all_kpts.shape[0])):
         # main_BandUP.f90:114: every requested pc-kpt must have been unfolded exactly once
         raise RuntimeError("not every pc-kpt was unfolded")
     if out_file:
         write_band_struc(out_file, kpath, grid, got.dN, e_fermi)
+    if unf_dens_op_file:
+        n = kpath.all_kpts.shape[0]
+        write_unf_dens_op(unf_dens_op_file, kpath, grid, got.dN, [rho_by_row[i] for i in range(n)], wc.nbands,
+                          wc.B_matrix, b_pc, [got.sckpt_of_row[i] for i in range(n)], got.sckpts_cart,
+                          e_fermi=e_fermi, spin_channel=spin_channel)
     return kpath, grid, got.dN
+
+
+# ---- unfolding_density_operator_*.dat (write_unf_dens_op, io_routines_mod.f90:1637-1882) ---------
+
+@dataclass
+class UdoRecord:
+    """One (pc-kpt, energy) block of the rho file."""
+    pckpt_number: int               # 1-based, in output order
+    iener: int                      # 1-based index into the energy grid
+    energy: float
+    unfolded_N: float
+    rows: np.ndarray                # 0-based m1 (upper triangle, m1 <= m2)
+    cols: np.ndarray
+    entries: np.ndarray             # complex
+    folding_sckpt_number: int = 1
+    pckpt_coord_in_plot: float = 0.0
+
+
+def write_unf_dens_op(path, kpath: PcKptsPath, energy_grid: np.ndarray, dN: np.ndarray, rho_ops, n_sc_bands: int,
+                      B_matrix_SC: np.ndarray, b_matrix_pc: np.ndarray, sckpt_of_pckpt: Sequence[int],
+                      sckpts_cart: np.ndarray, e_fermi: float = 0.0, spin_channel: int = 1,
+                      min_allowed_dN: float = 1e-3) -> None:
+    """The text file `bandup projected-unfold` parses (python_interface/bandupy/
+    unfolding_density_op.py:143-235).  rho_ops[ipc] is a list of (iener1, m1, m2, rho) arrays with the
+    STORED elements of that pc-kpt (1-based band indices, both triangles allowed); like the
+    reference only the upper triangle with |rho| >= 1e-4 is written, next to GenSpecWeight = rho*N."""
+    grid = np.asarray(energy_grid, dtype=np.float64)
+    Binv_sc = np.linalg.inv(np.asarray(B_matrix_SC, dtype=np.float64))
+    binv_pc = np.linalg.inv(np.asarray(b_matrix_pc, dtype=np.float64))
+    bar = "#" * 88
+    with open(path, "w") as f:
+        f.write(bar + "\n# File created by bandup-b200 (GPU unfolding path)\n" + bar + "\n")
+        f.write("# This file contains all information needed to unfold the expectation values of any\n"
+                "# operator defined in the (k,E) space. In particular, it reports, for each point in\n"
+                f"# the (k,E) grid satisfying N(k,E) >= {_es(min_allowed_dN)}, the following information:\n"
+                "#     * Unfolding-density operators (UnfDensOp)\n"
+                "#     * Generalized spectral weight matrices (GenSpecWeight)\n"
+                "# Both UnfDensOp and GenSpecWeight are hermitian; only the upper-triangular matrix\n"
+                "# elements are present. They are represented as (RealPart, ImagPart), and were\n"
+                "# evaluated between SC states with band indices indicated by m1 and m2.\n#\n")
+        f.write(f"# SpinChannel = {spin_channel}\n# nScBands = {n_sc_bands}\n")
+        f.write(f"# emin = {grid.min() - e_fermi:.5f} eV\n# emax = {grid.max() - e_fermi:.5f} eV\n")
+        f.write(f"# nEner = {grid.size}\n# OriginalEfermi = {e_fermi:.5f} eV\n")
+        f.write("# The energies were shifted so that the Fermi level is at 0 eV.\n" + bar + "\n")
+        ipc = 0
+        coord_first = 0.0
+        coord_k = 0.0
+        for d in kpath.directions:
+            first = d[0]
+            for k in d:
+                coord_k = coord_first + float(np.linalg.norm(k - first))
+                isc = int(sckpt_of_pckpt[ipc])
+                K = np.asarray(sckpts_cart[isc], dtype=np.float64)
+                f.write("\n")
+                f.write(f"# PcKptNumber = {ipc + 1}\n")
+                f.write("#     PcKptCartesianCoords =  %.8f  %.8f  %.8f  (A^{-1})\n" % tuple(k))
+                f.write("#     PcKptFractionalCoords =  %.8f  %.8f  %.8f  (w.r.t. SCRL basis)\n" % tuple(k @ Binv_sc))
+                f.write("#     PcKptFractionalCoords =  %.8f  %.8f  %.8f  (w.r.t. PCRL basis)\n" % tuple(k @ binv_pc))
+                f.write("#     PcKptLinearCoordsInBandPlot = %.4f  (A^{-1})\n" % coord_k)
+                f.write(f"#     Folds into ScKptNumber = {isc + 1}\n")
+                f.write("#         ScKptCartesianCoords =  %.8f  %.8f  %.8f  (A^{-1})\n" % tuple(K))
+                f.write("#         ScKptFractionalCoords =  %.8f  %.8f  %.8f  (w.r.t. SCRL basis)\n#\n"
+                        % tuple(K @ Binv_sc))
+                iener_a, m1_a, m2_a, rho_a = rho_ops[ipc]
+                for ie in np.unique(iener_a):
+                    N = float(dN[ipc, ie - 1])
+                    if N < min_allowed_dN:
+                        continue
+                    s = iener_a == ie
+                    m1s, m2s, vals = m1_a[s], m2_a[s], rho_a[s]
+                    trace = float(np.sum(vals[m1s == m2s].real))
+                    tr = "%8.1E" % trace + ("" if abs(trace - 1.0) < 1e-1 else " (!=1)")
+                    f.write("#     iEnerPC = %d  E = %.4f eV  N(k,E) = %s  Tr{UnfDensOp} = %s\n"
+                            % (ie, grid[ie - 1], _es(N), tr.strip()))
+                    f.write("#        m1      m2        GenSpecWeight[m1,m2]         UnfDensOp[m1,m2]\n")
+                    order = np.lexsort((m2s, m1s))
+                    for j in order:
+                        if m2s[j] < m1s[j] or abs(np.complex64(vals[j])) < np.float32(1e-4):
+                            continue
+                        g = vals[j] * N
+                        f.write("      %5d   %5d      (%s, %s)   (%s, %s)\n"
+                                % (m1s[j], m2s[j], _es(g.real), _es(g.imag), _es(vals[j].real), _es(vals[j].imag)))
+                ipc += 1
+            coord_first = coord_k
+
+
+def read_unf_dens_op(path) -> Tuple[dict, List[UdoRecord]]:
+    """Restatement of read_unf_dens_ops (unfolding_density_op.py:143-235): header dict + one record
+    per (pc-kpt, energy) block that has at least one matrix element line."""
+    hdr: dict = {}
+    recs: List[UdoRecord] = []
+    lines = Path(path).read_text().splitlines()
+    pck, coord, isc = 0, 0.0, 1
+    cur = None
+    in_rows = False
+    for i, line in enumerate(lines):
+        nxt = lines[i + 1] if i + 1 < len(lines) else None
+        if "SpinChannel" in line:
+            hdr["spin_channel"] = int(line.split("=")[-1])
+        elif "nScBands" in line:
+            hdr["nbands"] = int(line.split("=")[-1])
+        elif "emin" in line:
+            hdr["emin"] = float(line.split("=")[1].split()[0])
+        elif "emax" in line:
+            hdr["emax"] = float(line.split("=")[1].split()[0])
+        elif "nEner" in line:
+            hdr["nener"] = int(line.split("=")[1])
+        elif "PcKptNumber" in line:
+            pck = int(line.split("=")[-1])
+        elif "PcKptLinearCoordsInBandPlot" in line:
+            coord = float(line.split("=")[-1].split()[0])
+        elif "Folds into ScKptNumber" in line:
+            isc = int(line.split("=")[-1])
+        elif "iEnerPC" in line:
+            t = line.split()
+            cur = dict(iener=int(t[3]), energy=float(t[6]), N=float(t[10]), rows=[], cols=[], vals=[])
+        elif "m1" in line and "m2" in line and "GenSpecWeight" in line and "UnfDensOp" in line:
+            in_rows = True
+        elif in_rows:
+            t = line.replace(")", "").replace("(", "").replace(",", "").split()
+            r, c = int(t[0]) - 1, int(t[1]) - 1
+            v = complex(float(t[4]), float(t[5]) if r != c else 0.0)
+            cur["rows"].append(r)
+            cur["cols"].append(c)
+            cur["vals"].append(v)
+            if nxt is None or nxt.startswith("#") or not nxt.strip():
+                in_rows = False
+                recs.append(UdoRecord(pck, cur["iener"], cur["energy"], cur["N"], np.array(cur["rows"]),
+                                      np.array(cur["cols"]), np.array(cur["vals"]), isc, coord))
+    return hdr, recs

@@ -106,9 +106,13 @@ class ShardedUnfoldJob:
     vectors of the pc-kpts that fold onto it and their global row ids in the output table."""
 
     def __init__(self, unfolder, n_kpts: int, costs: Sequence[float], load_kpt: Callable,
-                 rank: int = 0, world_size: int = 1, depth: int = 2):
+                 rank: int = 0, world_size: int = 1, depth: int = 2,
+                 after_fetch: Optional[Callable] = None):
         self.unfolder = unfolder
         self.load_kpt = load_kpt
+        # after_fetch(iK, result, row_ids): called right after a k-point is fetched, while it is
+        # still resident on the device (rho, Pauli vectors, spectral function can be asked for)
+        self.after_fetch = after_fetch
         self.rank, self.world_size = rank, world_size
         self.blocks = partition_kpts(costs, world_size)
         self.my_block = self.blocks[rank]
@@ -133,6 +137,8 @@ class ShardedUnfoldJob:
             rows.append(res.dN)
             weights.append(res.spectral_weight)
             ids.append(rid)
+            if self.after_fetch is not None:
+                self.after_fetch(iK, res, rid)
 
         for iK in range(start, end):
             wf, folding_G, rid = self.load_kpt(iK)

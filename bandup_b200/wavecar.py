@@ -198,7 +198,7 @@ def fold_pckpts_onto_sckpts(pc_kpts_cart: np.ndarray, sc_kpts_frac: np.ndarray, 
 
 def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_cart: np.ndarray,
                    E_start: float, E_end: float, delta_e: float, ispin: int = 1, rank: int = 0,
-                   world_size: int = 1, device=None, group=None):
+                   world_size: int = 1, device=None, group=None, after_fetch=None):
     """The reference's main loop (main_BandUP.f90:131-177) over a WAVECAR under its no-symmetry
     flags (-no_symm_sckpts -no_symm_avg): every SC-kpt of the file, all pc-kpts folding onto it in
     one pass, raw band records read into two page-locked buffers and uploaded as they are while the
@@ -222,5 +222,9 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
         fG = np.asarray(pc_kpts_cart)[folds[i]] - K_cart[i]
         return wf, fG, np.asarray(folds[i])
 
-    job = ShardedUnfoldJob(unfolder, len(used), costs, load, rank=rank, world_size=world_size, depth=2)
-    return job.run(device=device, group=group), grid
+    job = ShardedUnfoldJob(unfolder, len(used), costs, load, rank=rank, world_size=world_size, depth=2,
+                           after_fetch=after_fetch)
+    got = job.run(device=device, group=group)
+    got.sckpt_of_row = {int(r): used[j] for j in range(len(used)) for r in folds[used[j]]}
+    got.sckpts_cart = K_cart
+    return got, grid

@@ -104,7 +104,63 @@ def make_orb_contrib_cases():
     return out
 
 
+def make_udo_file_golden():
+    """Our writer (bandup_b200.bandup_files.write_unf_dens_op) -> the REFERENCE's reader
+    (bandupy.unfolding_density_op.read_unf_dens_ops): what the reference parses out of our file."""
+    sys.path.insert(0, str(HERE.parent.parent))
+    from bandup_b200 import bandup_files as BF
+    from bandup_b200 import synth
+    from bandupy.unfolding_density_op import read_unf_dens_ops
+    a = synth.hex_cell(2.467, 15.0)
+    b = synth.rec_latt(a)
+    B = synth.rec_latt(np.diag([4, 4, 1]) @ a)
+    kp = BF.PcKptsPath([BF.kpts_line(np.array([1 / 3, 1 / 3, 0]) @ b, np.zeros(3), 3),
+                        BF.kpts_line(np.zeros(3), np.array([0.5, 0, 0]) @ b, 2)], 0.0)
+    grid = np.array([-3.0 + 0.05 * i for i in range(40)])
+    nk, nb = 5, 12
+    r = np.random.default_rng(77)
+    dN = r.uniform(0.0, 2.0, (nk, grid.size))
+    dN[r.random(dN.shape) < 0.5] = 1e-4                  # below min_allowed_dN: skipped by the writer
+    ops = []
+    for ipc in range(nk):
+        ie_l, m1_l, m2_l, v_l = [], [], [], []
+        for ie in sorted(r.choice(np.arange(1, grid.size + 1), size=4, replace=False)):
+            bands = sorted(r.choice(np.arange(1, nb + 1), size=3, replace=False))
+            for x in bands:
+                for y in bands:
+                    if y < x:
+                        continue
+                    v = complex(r.uniform(0.05, 0.6), 0.0) if x == y else complex(r.normal(0, 0.2), r.normal(0, 0.2))
+                    if r.random() < 0.15:
+                        v *= 1e-4                         # below the writer's |rho| >= 1e-4 filter
+                    for (p, q, w) in ([(x, y, v)] if x == y else [(x, y, v), (y, x, np.conj(v))]):
+                        ie_l.append(ie); m1_l.append(p); m2_l.append(q); v_l.append(w)
+        ops.append((np.array(ie_l), np.array(m1_l), np.array(m2_l), np.array(v_l, dtype=np.complex64)))
+    sck_of = [0, 1, 2, 2, 3]
+    sck = r.uniform(-0.2, 0.2, (4, 3))
+    out = HERE / "udo_file_fixture.dat"
+    BF.write_unf_dens_op(out, kp, grid, dN, ops, nb, B, b, sck_of, sck, e_fermi=-1.5)
+    parsed = read_unf_dens_ops(filename=str(out))
+    recs = []
+    for per_k in parsed:
+        for u in per_k:
+            m = u.csr_matrix.tocoo()
+            recs.append(dict(pckpt_number=u.pckpt_number, iener=u.iener, energy=u.energy, unfolded_N=u.unfolded_N,
+                             nbands=u.nbands, folding_sckpt_number=u.folding_sckpt_number,
+                             pckpt_coord_in_plot=u.pckpt_coord_in_plot, nener=u.nener_parent_grid,
+                             emin=u.emin_parent_grid, emax=u.emax_parent_grid,
+                             hermitian_rows=m.row.tolist(), hermitian_cols=m.col.tolist(),
+                             hermitian_re=m.data.real.tolist(), hermitian_im=m.data.imag.tolist()))
+    np.savez_compressed(HERE / "udo_file_inputs.npz", grid=grid, dN=dN, sck_of=np.array(sck_of), sck=sck,
+                        **{f"op{i}_{n}": arr for i, o in enumerate(ops) for n, arr in zip(("ie", "m1", "m2", "v"), o)})
+    (HERE / "udo_file_golden.json").write_text(json.dumps(
+        {"source": "bandupy.unfolding_density_op.read_unf_dens_ops (reference) reading udo_file_fixture.dat",
+         "records": recs}))
+    return len(recs)
+
+
 if __name__ == "__main__":
+    print("udo file records parsed by the reference reader:", make_udo_file_golden())
     (HERE / "udo_golden.json").write_text(json.dumps(
         {"source": "bandupy.unfolding_density_op.UnfDensOp (reference, imported unmodified)",
          "cases": make_udo_cases()}))

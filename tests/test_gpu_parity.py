@@ -474,9 +474,10 @@ def test_unfold_task_file_level(unfolder, tmp_path):
     write_wavecar(tmp_path / "WAVECAR", sc.A_sc, sc.ecut, list(sc.sc_kpts_frac), [d[0] for d in data],
                   [d[2] for d in data])
     out = tmp_path / "unfolded_EBS_not-symmetry_averaged.dat"
+    udo = tmp_path / "unfolding_density_operator_not-symm_avgd.dat"
     kpath, grid, dN = BF.unfold_task(unfolder, tmp_path / "WAVECAR", tmp_path / "prim_cell_lattice.in",
                                      tmp_path / "supercell_lattice.in", tmp_path / "KPOINTS_prim_cell.in",
-                                     tmp_path / "energy_info.in", out_file=str(out))
+                                     tmp_path / "energy_info.in", out_file=str(out), unf_dens_op_file=str(udo))
     assert np.array_equal(grid, O.real_seq(*sc.energy_window()))
     want = np.zeros_like(dN)
     for iK in range(sc.n_sc_kpts):
@@ -489,3 +490,20 @@ def test_unfold_task_file_level(unfolder, tmp_path):
     assert np.allclose(tab[:, 2].reshape(sum(counts), len(grid)), want, rtol=6e-4, atol=1e-12)
     assert np.allclose(tab[:len(grid), 1], grid - sc.e_fermi, atol=5e-5)
     assert tab[-1, 0] > tab[0, 0] and np.all(np.diff(tab[::len(grid), 0]) >= -1e-12)
+    # the rho file (-write_unf_dens_op): every block against the oracle's calc_rho, to the file's 4 digits
+    from oracle import oracle_np as ON
+    hdr, recs = BF.read_unf_dens_op(udo)
+    assert hdr["nbands"] == sc.n_bands and hdr["nener"] == len(grid) and len(recs) > 5
+    de = grid[1] - grid[0]
+    for r in recs:
+        row = r.pckpt_number - 1
+        iK = next(i for i, f in enumerate(sc.folds) if row in f)
+        assert r.folding_sckpt_number == iK + 1
+        coeffs, gf, ener = data[iK]
+        c_ren, _ = O.renormalize(coeffs, 1)
+        sel, _ = O.select_coeffs(gf @ sc.B_sc, sc.pc_kpts_cart[row] - sc.sc_kpts_cart[iK], sc.b_pc)
+        rho = ON.calc_rho(c_ren, sel, ener, want[row, r.iener - 1], grid[r.iener - 1], de)
+        assert abs(r.unfolded_N - want[row, r.iener - 1]) <= 6e-4 * want[row, r.iener - 1]
+        for i, j, v in zip(r.rows, r.cols, r.entries):
+            assert i <= j and abs(v - (rho[i, j] if i != j else rho[i, j].real)) <= 6e-4 * abs(rho[i, j]) + 1e-7
+        assert np.count_nonzero(np.abs(np.triu(rho)) >= 1.2e-4) <= len(r.entries) <= np.count_nonzero(np.abs(np.triu(rho)) >= 0.8e-4)
