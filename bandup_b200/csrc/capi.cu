@@ -82,7 +82,7 @@ struct Flight {  // one SC k-point in flight
   int ikpt = -1;
   int n_spinor = 0, n_pw = 0, n_bands = 0, n_fold = 0, n_unique = 0, layout = 0;
   long long stride_bytes = 0;
-  int unique_of[kMaxFolds];
+  std::vector<int> unique_of;  // pc-kpt (user fold) -> distinct coset
   DevBuf coeffs, gfrac, energies, weights, dN, nsel, norms, slot, selected, workspace;
   PinBuf h_weights, h_dN, h_nsel, h_norms;
   cudaEvent_t uploaded = nullptr, done = nullptr;
@@ -263,16 +263,16 @@ void resolve_pending(Ctx* c) {
 
 struct FoldPlan {
   int n_unique = 0;
-  int unique_of[kMaxFolds];    // user fold -> unique fold
-  int first_of[kMaxFolds];     // unique fold -> first user fold holding that coset
+  std::vector<int> unique_of;  // user fold (pc-kpt) -> unique fold (distinct coset)
   int fold_key[kMaxFolds][3];  // key(g0) of every unique fold
 };
 
 int plan_folds(Ctx* c, int n_fold, const int32_t* g0, FoldPlan* plan) {
-  if (n_fold < 1 || n_fold > kMaxFolds)
+  if (n_fold < 1 || n_fold > BANDUP_GPU_MAX_PCKPTS)
     return fail(c, BANDUP_GPU_ERR_TOO_MANY_FOLDS,
-                "n_fold must be in 1.." + std::to_string(kMaxFolds) + ", got " + std::to_string(n_fold));
+                "n_fold must be in 1.." + std::to_string(BANDUP_GPU_MAX_PCKPTS) + ", got " + std::to_string(n_fold));
   plan->n_unique = 0;
+  plan->unique_of.assign((size_t)n_fold, 0);
   for (int f = 0; f < n_fold; ++f) {
     int key[3];
     coset_key(g0 + 3 * f, c->coset.adjT, c->coset.D, key);
@@ -282,11 +282,13 @@ int plan_folds(Ctx* c, int n_fold, const int32_t* g0, FoldPlan* plan) {
           plan->fold_key[q][2] == key[2])
         u = q;
     if (u < 0) {
+      if (plan->n_unique == kMaxFolds)
+        return fail(c, BANDUP_GPU_ERR_TOO_MANY_FOLDS,
+                    "more than " + std::to_string(kMaxFolds) + " distinct cosets among the pc-kpts of one submit");
       u = plan->n_unique++;
       plan->fold_key[u][0] = key[0];
       plan->fold_key[u][1] = key[1];
       plan->fold_key[u][2] = key[2];
-      plan->first_of[u] = f;
     }
     plan->unique_of[f] = u;
   }
@@ -845,7 +847,7 @@ int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_ba
   fl.n_bands = n_bands;
   fl.n_fold = n_fold;
   fl.n_unique = plan.n_unique;
-  std::memcpy(fl.unique_of, plan.unique_of, sizeof(int) * (size_t)n_fold);
+  fl.unique_of = plan.unique_of;
   c->next_flight = (slot + 1) % kDepth;
   return BANDUP_GPU_OK;
 }

@@ -53,8 +53,11 @@ extern "C" {
 #define BANDUP_GPU_ERR_DELTA_N_ZERO 11
 #define BANDUP_GPU_ERR_INT_OVERFLOW 12  /* Miller indices x adjugate would overflow */
 
-/* most pc-kpts that may fold onto one SC-kpt in a single submit */
+/* most DISTINCT cosets (pc-kpts whose folding vectors differ by more than a pc reciprocal
+ * vector) among the pc-kpts of one submit, and most pc-kpts per submit; pc-kpts that share a
+ * coset are computed once and their rows replicated */
 #define BANDUP_GPU_MAX_FOLDS 64
+#define BANDUP_GPU_MAX_PCKPTS 4096
 
 /* coefficient layouts accepted by submit_kpt / unfold_device */
 /* pw_coeffs(n_spinor, n_pw, n_bands) as it lies in Fortran memory:

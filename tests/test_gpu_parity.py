@@ -94,6 +94,14 @@ def test_folds_sharing_a_coset_and_many_folds(unfolder):
         assert np.array_equal(a, b)
     assert rel_err(res.spectral_weight, w) <= REL_TOL
     assert rel_err(res.dN, dN) <= REL_TOL
+    # more than BANDUP_GPU_MAX_FOLDS DISTINCT cosets in one submit is refused (det M = 108 here)
+    from bandup_b200.unfold import BandupGpuError
+    cube = np.array([[i, j, k] for i in range(5) for j in range(5) for k in range(5)], dtype=np.int32)
+    assert len(np.unique(synth.coset_labels(cube, sc.M))) > 64
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.submit(2, PwWavefunction(coeffs, gf, ener), g0=cube)
+    assert ei.value.code == 5
+    unfolder._inflight.clear()
 
 
 @pytest.mark.parametrize("n_spinor", [1, 2])
@@ -238,8 +246,13 @@ def test_error_codes(unfolder):
     assert ei.value.code == 4
     g0, res = unfolder.folding_g0(sc.folding_G(0) + np.array([4e-5, 0.0, 0.0]))
     assert res < 1e-3 and np.array_equal(g0, unfolder.folding_g0(sc.folding_G(0))[0])
-    with pytest.raises(BandupGpuError) as ei:
-        unfolder.submit(1, wf, g0=np.zeros((MAX_FOLDS + 1, 3), np.int32))
+    many = np.zeros((MAX_FOLDS + 1, 3), np.int32)
+    many[:, 0] = np.arange(MAX_FOLDS + 1)                   # 4x4 cell: only 4 distinct cosets along B1
+    unfolder.submit(1, wf, g0=many)                         # > MAX_FOLDS pc-kpts is fine ...
+    r = unfolder.fetch(1)
+    assert np.array_equal(r.spectral_weight[0], r.spectral_weight[4]) and r.spectral_weight.shape[0] == MAX_FOLDS + 1
+    with pytest.raises(BandupGpuError) as ei:               # ... too many pc-kpts per submit is not
+        unfolder.submit(1, wf, g0=np.zeros((5000, 3), np.int32))
     assert ei.value.code == 5
     unfolder._inflight.clear()
     lib = unfolder._lib
