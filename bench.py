@@ -217,8 +217,10 @@ def run_b200(args, sc, rank, world, local_rank):
     if rank == 0:
         _build.build()
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"    # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is
+        # VERSION (also via /etc/nccl.conf); an explicit INFO/TRACE from the caller is respected
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     else:
