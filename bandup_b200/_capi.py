@@ -80,6 +80,10 @@ def load() -> C.CDLL:
         "bandup_gpu_folding_g0": (C.c_int, [C.c_int, c_f64p, C.c_int, c_i32p, c_f64p]),
         "bandup_gpu_submit_kpt": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                             C.c_void_p, c_i32p, c_f64p, C.c_int, c_i32p]),
+        "bandup_gpu_submit_kpt_vasp": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p,
+                                                 c_f64p, C.c_double, C.c_double, c_f64p, C.c_int, c_i32p,
+                                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "bandup_gpu_fetch_gvecs": (C.c_int, [C.c_int, C.c_int, c_i32p, C.c_int64]),
         "bandup_gpu_fetch_kpt": (C.c_int, [C.c_int, C.c_int, c_f64p, c_f64p, c_i32p, c_f64p, c_i32p, C.c_int64]),
         "bandup_gpu_pipeline_depth": (C.c_int, [C.c_int]),
         "bandup_gpu_rho_count": (C.c_int, [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int64),

@@ -18,7 +18,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libbandup_gpu.so"
-SOURCES = ["capi.cu", "coset_classify.cu", "weights_reduce.cu", "delta_n.cu", "rho.cu", "synth.cu"]
+SOURCES = ["capi.cu", "coset_classify.cu", "weights_reduce.cu", "delta_n.cu", "rho.cu", "gvecs.cu", "synth.cu"]
 HEADERS = [CSRC / "kernels.cuh", PKG.parent / "include" / "bandup_gpu.h"]
 
 NVCC_FLAGS = [

@@ -110,6 +110,7 @@ struct Ctx {
   int desc_next = 0;
   std::vector<double> grid;
   DevBuf d_grid;
+  DevBuf gvec_scratch;  // per-CTA counts/offsets of the device plane-wave enumeration
   DevBuf d_operator;  // current general operator O [n_bands][n_bands] complex128
   int operator_bands = 0;
   int nener = 0;
@@ -546,6 +547,7 @@ int bandup_gpu_finalize(int handle) {
   }
   c->d_grid.release();
   c->d_operator.release();
+  c->gvec_scratch.release();
   for (auto& d : c->desc_ring) {
     if (d.h) cudaFreeHost(d.h);
     if (d.d) cudaFree(d.d);
@@ -759,14 +761,161 @@ int bandup_gpu_unfold_device_batch(int handle, void* stream, int n_kpts, const b
   return run_batch(c, static_cast<cudaStream_t>(stream), items);
 }
 
+namespace {
+
+struct GvecRequest {  // regenerate the plane-wave list on the device instead of uploading it
+  double kfrac[3];
+  double ecut;
+  double c_const;  // <= 0: VASP's 2m/hbar^2 as the reference holds it (a float32-rounded literal)
+  // filled by resolve_gvecs
+  double c_used = 0.0;
+  int nb[3] = {0, 0, 0};
+  long long* d_off = nullptr;
+};
+
+double norm3(const double* a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+double angle3(const double* a, const double* b) {
+  return std::acos((a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) / (norm3(a) * norm3(b)));
+}
+void cross3(const double* a, const double* b, double* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// get_max_nb1_nb2_and_nb3 (read_wavecar_mod.f90:151-210): the search box of the enumeration
+void max_nb(const double* B, double ecut, double cc, int* nb) {
+  const double *b1 = B, *b2 = B + 3, *b3 = B + 6;
+  const double p12 = angle3(b1, b2), p13 = angle3(b1, b3), p23 = angle3(b2, b3);
+  const double m1 = norm3(b1), m2 = norm3(b2), m3 = norm3(b3), r = std::sqrt(ecut * cc);
+  double x[3];
+  cross3(b1, b2, x);
+  double s = std::cos(angle3(b3, x));
+  const int a1 = (int)(r / (m1 * std::fabs(std::sin(p12))) + 1.0), a2 = (int)(r / (m2 * std::fabs(std::sin(p12))) + 1.0),
+            a3 = (int)(r / (m3 * std::fabs(s)) + 1.0);
+  cross3(b1, b3, x);
+  s = std::cos(angle3(b2, x));
+  const int c1 = (int)(r / (m1 * std::fabs(std::sin(p13))) + 1.0), c2 = (int)(r / (m2 * std::fabs(s)) + 1.0),
+            c3 = (int)(r / (m3 * std::fabs(std::sin(p13))) + 1.0);
+  cross3(b2, b3, x);
+  s = std::cos(angle3(b1, x));
+  const int d1 = (int)(r / (m1 * std::fabs(s)) + 1.0), d2 = (int)(r / (m2 * std::fabs(std::sin(p23))) + 1.0),
+            d3 = (int)(r / (m3 * std::fabs(std::sin(p23))) + 1.0);
+  nb[0] = std::max(a1, std::max(c1, d1));
+  nb[1] = std::max(a2, std::max(c2, d2));
+  nb[2] = std::max(a3, std::max(c3, d3));
+}
+
+// Counts the plane waves of the k-point on the device, decides scalar vs spinor the way the
+// reader does (nint(nplane / n_Gvecs) == 2, read_wavecar_mod.f90:446-452) and adjusts 2m/hbar^2 in
+// steps of 1e-10 (at most 1000) until the count equals the file's (:459-472).  Leaves the per-CTA
+// offsets of the successful count in rq.scratch for write_gvecs.
+int resolve_gvecs(Ctx* c, cudaStream_t s, GvecRequest* rq, int nplane, int* n_spinor, int* n_pw) {
+  const double c0 = rq->c_const > 0.0 ? rq->c_const : (double)0.262465831f;
+  long long n_found = -1;
+  double step = 1e-10;
+  int want = nplane;
+  *n_spinor = 1;
+  for (int it = 0; it <= 1000; ++it) {
+    rq->c_used = c0 + step * it;
+    max_nb(c->B_sc, rq->ecut, rq->c_used, rq->nb);
+    const long long blocks = gvec_num_blocks(rq->nb);
+    if (blocks > 2000000000LL / 256) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "plane-wave search box too large");
+    CU(c->gvec_scratch.reserve(align256(sizeof(int) * (size_t)blocks) + sizeof(long long) * ((size_t)blocks + 1)));
+    int* d_cnt = static_cast<int*>(c->gvec_scratch.p);
+    rq->d_off = reinterpret_cast<long long*>(static_cast<char*>(c->gvec_scratch.p) + align256(sizeof(int) * (size_t)blocks));
+    {
+      KernelScope k(c, BANDUP_GPU_K_COSET, s);
+      launch_gvec_count(rq->kfrac, c->B_sc, rq->c_used, rq->ecut, rq->nb, d_cnt, rq->d_off, s);
+      c->launches++;  // count + scan
+    }
+    CU(cudaMemcpyAsync(&n_found, rq->d_off + blocks, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (it == 0) {
+      if (n_found > 0 && std::lround((double)nplane / (double)n_found) == 2) {
+        *n_spinor = 2;
+        want = nplane / 2;
+      }
+      if (want < n_found) step = -1e-10;  // fewer waves in the file than generated (:466-468)
+    }
+    if (n_found == want) {
+      *n_pw = want;
+      return BANDUP_GPU_OK;
+    }
+  }
+  return fail(c, BANDUP_GPU_ERR_INVALID_ARG,
+              "ERROR (read_wavecar): the file holds " + std::to_string(want) + " plane waves for this k-point, " +
+                  std::to_string(n_found) + " were generated");
+}
+
+int write_gvecs(Ctx* c, cudaStream_t s, const GvecRequest& rq, int n_pw, int32_t* d_gfrac) {
+  KernelScope k(c, BANDUP_GPU_K_COSET, s);
+  launch_gvec_write(rq.kfrac, c->B_sc, rq.c_used, rq.ecut, rq.nb, rq.d_off, d_gfrac, n_pw, s);
+  CU(cudaGetLastError());
+  return BANDUP_GPU_OK;
+}
+
+int submit_impl(int handle, int ikpt, int n_spinor, int n_pw, int n_bands, int layout,
+                int64_t band_stride_bytes, const void* coeffs, const int32_t* g_frac,
+                const GvecRequest* gen, const double* band_energies, int n_fold, const int32_t* g0);
+
+}  // namespace
+
 int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_bands, int layout,
                           int64_t band_stride_bytes, const void* coeffs, const int32_t* g_frac,
                           const double* band_energies, int n_fold, const int32_t* g0) {
+  if (!g_frac) return fail(get(handle), BANDUP_GPU_ERR_INVALID_ARG, "NULL host pointer");
+  return submit_impl(handle, ikpt, n_spinor, n_pw, n_bands, layout, band_stride_bytes, coeffs, g_frac, nullptr,
+                     band_energies, n_fold, g0);
+}
+
+int bandup_gpu_submit_kpt_vasp(int handle, int ikpt, int nplane, int n_bands, int64_t nrecl,
+                               const void* band_records, const double* kpt_frac_coords, double ecut,
+                               double two_m_over_hbar_sqrd, const double* band_energies, int n_fold,
+                               const int32_t* g0, int* n_spinor_out, int* n_pw_out) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (!c->cells_set) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_set_cells first");
+  if (!kpt_frac_coords || !(ecut > 0.0) || nplane < 1)
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "k-point coordinates, ENCUT and nplane are needed");
+  GvecRequest rq;
+  for (int i = 0; i < 3; ++i) rq.kfrac[i] = kpt_frac_coords[i];
+  rq.ecut = ecut;
+  rq.c_const = two_m_over_hbar_sqrd;
+  cudaSetDevice(c->device);
+  int n_spinor = 1, n_pw = 0;
+  int rc = resolve_gvecs(c, c->compute, &rq, nplane, &n_spinor, &n_pw);
+  if (rc) return rc;
+  if (n_spinor_out) *n_spinor_out = n_spinor;
+  if (n_pw_out) *n_pw_out = n_pw;
+  return submit_impl(handle, ikpt, n_spinor, n_pw, n_bands, BANDUP_GPU_LAYOUT_VASP_RECORD, nrecl, band_records,
+                     nullptr, &rq, band_energies, n_fold, g0);
+}
+
+int bandup_gpu_fetch_gvecs(int handle, int ikpt, int32_t* g_frac, int64_t capacity) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  Flight* fl = nullptr;
+  for (auto& f : c->flights)
+    if (f.ikpt == ikpt && (f.busy || f.resident)) fl = &f;
+  if (!fl) return fail(c, BANDUP_GPU_ERR_UNKNOWN_KPT, "k-point " + std::to_string(ikpt) + " is not on the device");
+  if (!g_frac || capacity < fl->n_pw) return fail(c, BANDUP_GPU_ERR_CAPACITY, "need room for n_pw triples");
+  cudaSetDevice(c->device);
+  CU(cudaMemcpyAsync(g_frac, fl->gfrac.p, sizeof(int32_t) * 3 * (size_t)fl->n_pw, cudaMemcpyDeviceToHost, c->compute));
+  CU(cudaStreamSynchronize(c->compute));
+  return BANDUP_GPU_OK;
+}
+
+namespace {
+
+int submit_impl(int handle, int ikpt, int n_spinor, int n_pw, int n_bands, int layout,
+                int64_t band_stride_bytes, const void* coeffs, const int32_t* g_frac,
+                const GvecRequest* gen, const double* band_energies, int n_fold, const int32_t* g0) {
   Ctx* c = get(handle);
   if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
   int rc = check_shape(c, n_spinor, n_pw, n_bands, layout, band_stride_bytes);
   if (rc) return rc;
-  if (!coeffs || !g_frac || !band_energies || !g0)
+  if (!coeffs || (!g_frac && !gen) || !band_energies || !g0)
     return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "NULL host pointer");
   std::vector<BatchItem> items(1);
   BatchItem& it = items[0];
@@ -808,9 +957,14 @@ int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_ba
 
   // upload on the copy stream so it overlaps the previous k-point's kernels
   CU(cudaMemcpyAsync(fl.coeffs.p, coeffs, coeff_bytes, cudaMemcpyHostToDevice, c->copy));
-  CU(cudaMemcpyAsync(fl.gfrac.p, g_frac, sizeof(int32_t) * 3 * (size_t)n_pw, cudaMemcpyHostToDevice, c->copy));
+  if (g_frac)
+    CU(cudaMemcpyAsync(fl.gfrac.p, g_frac, sizeof(int32_t) * 3 * (size_t)n_pw, cudaMemcpyHostToDevice, c->copy));
   CU(cudaMemcpyAsync(fl.energies.p, band_energies, sizeof(double) * (size_t)n_bands, cudaMemcpyHostToDevice, c->copy));
   CU(cudaEventRecord(fl.uploaded, c->copy));
+  if (gen) {  // while the coefficient block is on its way: the plane-wave list, made on the device
+    rc = write_gvecs(c, c->compute, *gen, n_pw, static_cast<int32_t*>(fl.gfrac.p));
+    if (rc) return rc;
+  }
   CU(cudaStreamWaitEvent(c->compute, fl.uploaded, 0));
 
   it.n_spinor = n_spinor; it.n_pw = n_pw; it.n_bands = n_bands; it.layout = layout; it.n_fold = n_fold;
@@ -851,6 +1005,8 @@ int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw, int n_ba
   c->next_flight = (slot + 1) % kDepth;
   return BANDUP_GPU_OK;
 }
+
+}  // namespace
 
 int bandup_gpu_fetch_kpt(int handle, int ikpt, double* weights, double* dN, int32_t* n_selected,
                          double* norms, int32_t* selected, int64_t selected_capacity) {

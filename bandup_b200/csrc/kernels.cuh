@@ -90,6 +90,15 @@ void launch_weights_finalize(const KptGeom* d_geoms, int n_kpts, int max_bands, 
 void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const double* d_grid,
                     int nener, double sigma, cudaStream_t s);
 
+// K0 -- plane-wave list of an SC k-point regenerated on the device in the WAVECAR reader's order
+// (read_wavecar_mod.f90:213-304).  count: per-CTA counts + exclusive scan (total at
+// d_block_off[gvec_num_blocks]); write: ordered compaction into d_g_frac [n][3].
+long long gvec_num_blocks(const int* nb);
+void launch_gvec_count(const double* kfrac, const double* B_rows, double c, double ecut, const int* nb,
+                       int* d_block_count, long long* d_block_off, cudaStream_t s);
+void launch_gvec_write(const double* kfrac, const double* B_rows, double c, double ecut, const int* nb,
+                       const long long* d_block_off, int32_t* d_g_frac, long long capacity, cudaStream_t s);
+
 // A(k,E) with a Gaussian delta (calc_spectral_function, :654-698); weights per distinct fold.
 void launch_spectral_function(const double* d_grid, int nener, double stddev, const double* d_band_energies,
                               const double* d_weights, int n_bands, int n_fold, double* d_sf,

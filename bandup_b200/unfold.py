@@ -204,6 +204,33 @@ class GpuUnfolder:
         # keep the host arrays alive until fetch (the upload is asynchronous)
         self._inflight[int(ikpt)] = (wf, g0, n_fold)
 
+    def submit_vasp(self, ikpt: int, band_records: np.ndarray, nrecl: int, nplane: int, n_bands: int,
+                    kpt_frac_coords: np.ndarray, ecut: float, band_energies: np.ndarray,
+                    folding_G: Optional[np.ndarray] = None, g0: Optional[np.ndarray] = None,
+                    two_m_over_hbar_sqrd: float = 0.0):
+        """Raw WAVECAR band records in; plane-wave list, scalar/spinor decision and the reader's
+        2m/hbar^2 adjustment done on the device (read_wavecar_mod.f90:213-304, 446-472); otherwise
+        like submit().  Returns (n_spinor, n_pw)."""
+        if g0 is None:
+            g0, _ = self.folding_g0(folding_G)
+        g0 = np.ascontiguousarray(np.atleast_2d(g0), dtype=np.int32)
+        k = np.ascontiguousarray(kpt_frac_coords, dtype=np.float64)
+        e = np.ascontiguousarray(band_energies, dtype=np.float64)
+        nsp, npw = C.c_int(0), C.c_int(0)
+        self._check(self._lib.bandup_gpu_submit_kpt_vasp(
+            self.handle, int(ikpt), int(nplane), int(n_bands), int(nrecl), C.c_void_p(band_records.ctypes.data),
+            k.ctypes.data_as(c_f64p), float(ecut), float(two_m_over_hbar_sqrd), e.ctypes.data_as(c_f64p),
+            g0.shape[0], g0.ctypes.data_as(c_i32p), C.byref(nsp), C.byref(npw)))
+        wf = PwWavefunction(band_records, np.zeros((npw.value, 3), np.int32), e, n_pw=npw.value, n_bands=n_bands,
+                            n_spinor=nsp.value, layout=LAYOUT_VASP_RECORD, band_stride_bytes=nrecl)
+        self._inflight[int(ikpt)] = (wf, g0, g0.shape[0])
+        return nsp.value, npw.value
+
+    def fetch_gvecs(self, ikpt: int, n_pw: int) -> np.ndarray:
+        g = np.zeros((n_pw, 3), dtype=np.int32)
+        self._check(self._lib.bandup_gpu_fetch_gvecs(self.handle, int(ikpt), g.ctypes.data_as(c_i32p), n_pw))
+        return g
+
     def fetch_raw(self, ikpt: int, n_fold: int, n_bands: int):
         """bandup_gpu_fetch_kpt without the bookkeeping of submit(): weights, dN, n_selected."""
         w = np.zeros((n_fold, n_bands), dtype=np.float64)

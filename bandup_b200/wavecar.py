@@ -167,6 +167,15 @@ class Wavecar:
         c = raw[:, :8 * g.shape[0] * nsp].copy().view("<c8").reshape(self.nbands, nsp, g.shape[0])
         return np.ascontiguousarray(c.transpose(0, 2, 1))
 
+    def submit_to(self, unfolder, job_ikpt: int, ikpt: int, folding_G: np.ndarray, ispin: int = 1,
+                  out: Optional[np.ndarray] = None):
+        """Header + raw records of file k-point `ikpt` (1-based) straight to the device
+        (GpuUnfolder.submit_vasp): no plane-wave enumeration, no de-interleave on the host."""
+        h = self.kpt_header(ikpt, ispin)
+        raw = self.read_band_records(ikpt, ispin, out=out)
+        return unfolder.submit_vasp(job_ikpt, raw, self.nrecl, h.nplane, self.nbands, h.kpt_frac_coords, self.encut,
+                                    h.band_energies, folding_G=folding_G)
+
     def wavefunction(self, ikpt: int, ispin: int = 1, out: Optional[np.ndarray] = None):
         """bandup_b200.unfold.PwWavefunction over the raw records (VASP_RECORD layout)."""
         from .unfold import LAYOUT_VASP_RECORD, PwWavefunction

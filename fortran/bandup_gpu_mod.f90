@@ -17,7 +17,7 @@ private
 public :: bandup_gpu_init, bandup_gpu_finalize, bandup_gpu_last_error, &
           bandup_gpu_abi_version, bandup_gpu_pinned_alloc, bandup_gpu_pinned_free, &
           bandup_gpu_set_cells, bandup_gpu_set_grid, bandup_gpu_get_grid, &
-          bandup_gpu_folding_g0, bandup_gpu_submit_kpt, bandup_gpu_fetch_kpt, &
+          bandup_gpu_folding_g0, bandup_gpu_submit_kpt, bandup_gpu_submit_kpt_vasp, bandup_gpu_fetch_kpt, &
           bandup_gpu_pipeline_depth, bandup_gpu_set_profiling, &
           bandup_gpu_kernel_time, bandup_gpu_reset_kernel_times, &
           bandup_gpu_launch_count, bandup_gpu_set_tuning, &
@@ -125,6 +125,24 @@ interface
         integer(c_int32_t), intent(in) :: g0(3,*)
         integer(c_int) :: bandup_gpu_submit_kpt
     end function bandup_gpu_submit_kpt
+
+    ! raw WAVECAR band records + plane-wave list regenerated on the device (read_wavecar_mod.f90:213-304)
+    function bandup_gpu_submit_kpt_vasp(handle, ikpt, nplane, n_bands, nrecl, band_records, &
+                                        kpt_frac_coords, ecut, two_m_over_hbar_sqrd, band_energies, &
+                                        n_fold, g0, n_spinor_out, n_pw_out) &
+        bind(c, name='bandup_gpu_submit_kpt_vasp')
+        import c_int, c_int64_t, c_int32_t, c_double, c_ptr
+        integer(c_int), intent(in), value :: handle, ikpt, nplane, n_bands
+        integer(c_int64_t), intent(in), value :: nrecl
+        type(c_ptr), intent(in), value :: band_records
+        real(c_double), intent(in) :: kpt_frac_coords(3)
+        real(c_double), intent(in), value :: ecut, two_m_over_hbar_sqrd
+        real(c_double), intent(in) :: band_energies(*)
+        integer(c_int), intent(in), value :: n_fold
+        integer(c_int32_t), intent(in) :: g0(3,*)
+        integer(c_int), intent(out) :: n_spinor_out, n_pw_out
+        integer(c_int) :: bandup_gpu_submit_kpt_vasp
+    end function bandup_gpu_submit_kpt_vasp
 
     ! weights(n_bands, n_fold), dN(nener, n_fold) in Fortran order.  Optional C outputs
     ! are passed as type(c_ptr): c_null_ptr to skip, c_loc(array) otherwise.

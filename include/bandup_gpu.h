@@ -134,6 +134,25 @@ int bandup_gpu_submit_kpt(int handle, int ikpt, int n_spinor, int n_pw,
                           const double *band_energies, int n_fold,
                           const int32_t *g0);
 
+/* The VASP reader's path without its host work: `band_records` are the n_bands raw WAVECAR
+ * coefficient records of the k-point exactly as they lie in the file (nrecl bytes apart,
+ * spinor-up block then spinor-down block; read_wavecar_mod.f90:570-577), `nplane` is the count
+ * in the k-point's header record, and the plane-wave list is regenerated ON THE DEVICE from
+ * the k-point, ENCUT and the SC lattice given to bandup_gpu_set_cells, in the reader's own
+ * enumeration order (n_Gvecs_2b_generated + populate_wf_with_G_vec_coords, :213-304),
+ * including its scalar/spinor decision (nint(nplane / n_Gvecs) == 2, :446-452) and its
+ * adaptive adjustment of 2m/hbar^2 (steps of 1e-10, at most 1000) when the count is off
+ * (:459-472).  two_m_over_hbar_sqrd <= 0 selects the reference's constant (:107).
+ * n_spinor_out / n_pw_out (nullable) receive what was decided.  Otherwise as
+ * bandup_gpu_submit_kpt; ERR_INVALID_ARG when no adjustment yields the file's count. */
+int bandup_gpu_submit_kpt_vasp(int handle, int ikpt, int nplane, int n_bands, int64_t nrecl,
+                               const void *band_records, const double *kpt_frac_coords,
+                               double ecut, double two_m_over_hbar_sqrd,
+                               const double *band_energies, int n_fold, const int32_t *g0,
+                               int *n_spinor_out, int *n_pw_out);
+/* The plane-wave list (int32 [n_pw][3]) of a submitted or still resident k-point. */
+int bandup_gpu_fetch_gvecs(int handle, int ikpt, int32_t *g_frac, int64_t capacity);
+
 /* Blocks until k-point `ikpt` is done and copies out:
  *   weights    [n_fold][n_bands]  P_mK(k)           (spectral_weight, :1333-1345)
  *   dN         [n_fold][nener]    delta_N(k, E_i)   (%dN, :1355-1360)

@@ -520,3 +520,59 @@ def test_unfold_task_file_level(unfolder, tmp_path):
         for i, j, v in zip(r.rows, r.cols, r.entries):
             assert i <= j and abs(v - (rho[i, j] if i != j else rho[i, j].real)) <= 6e-4 * abs(rho[i, j]) + 1e-7
         assert np.count_nonzero(np.abs(np.triu(rho)) >= 1.2e-4) <= len(r.entries) <= np.count_nonzero(np.abs(np.triu(rho)) >= 0.8e-4)
+
+
+@pytest.mark.parametrize("name,scale", [("graphene4x4", 0.1), ("mos2_8x8_spinor", 0.05), ("si333_vacancy", 0.2)])
+def test_wavecar_records_with_device_gvecs(unfolder, tmp_path, name, scale):
+    """bandup_gpu_submit_kpt_vasp: header values + raw band records in; the plane-wave list, the
+    scalar/spinor decision and the count check happen on the device.  The list must equal the
+    reader's enumeration (oracle bo_gen_gvecs) element for element."""
+    from bandup_b200.unfold import BandupGpuError
+    from bandup_b200.wavecar import Wavecar, write_wavecar
+    from oracle import oracle as O
+    sc = synth.make_scenario(name, scale=scale, n_kpts=9)
+    grid = setup(unfolder, sc)
+    ks = [0, sc.n_sc_kpts - 1]
+    data = [synth.make_wavefunction(sc, iK) for iK in ks]
+    path = tmp_path / "WAVECAR"
+    write_wavecar(path, sc.A_sc, sc.ecut, [sc.sc_kpts_frac[iK] for iK in ks], [d[0] for d in data],
+                  [d[2] for d in data], extra_pad=2)
+    wc = Wavecar(path)
+    for i, iK in enumerate(ks):
+        coeffs, gf, ener = data[i]
+        nsp, npw = wc.submit_to(unfolder, 40 + i, i + 1, sc.folding_G(iK))
+        assert (nsp, npw) == (sc.n_spinor, gf.shape[0])
+        g_dev = unfolder.fetch_gvecs(40 + i, npw)
+        g_ref, _ = O.gen_gvecs(sc.sc_kpts_frac[iK], sc.ecut, sc.B_sc)
+        assert np.array_equal(g_dev, g_ref) and np.array_equal(g_dev, gf)
+        res = unfolder.fetch(40 + i, want_selected=True)
+        w, dN, ns, sels = oracle_kpt(sc, coeffs, gf, ener, sc.folding_G(iK), grid)
+        assert np.array_equal(res.n_selected, ns)
+        for a, b in zip(res.selected_coeff_indices, sels):
+            assert np.array_equal(a, b)
+        assert rel_err(res.spectral_weight, w) <= REL_TOL and rel_err(res.dN, dN) <= REL_TOL
+    # a header whose plane-wave count no adjustment of 2m/hbar^2 can reproduce is the reader's error
+    h = wc.kpt_header(1)
+    raw = wc.read_band_records(1)
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.submit_vasp(50, raw, wc.nrecl, h.nplane - 7 * sc.n_spinor, wc.nbands, h.kpt_frac_coords, wc.encut,
+                             h.band_energies, folding_G=sc.folding_G(ks[0]))
+    assert ei.value.code == 1 and "plane waves" in str(ei.value)
+
+
+def test_device_gvecs_full_size(unfolder):
+    """~100k plane waves of a C5 k-point: device enumeration == the reader's, in order."""
+    from oracle import oracle as O
+    sc = synth.make_scenario("sige555")
+    setup(unfolder, sc)
+    iK = 5
+    g_ref, _ = O.gen_gvecs(sc.sc_kpts_frac[iK], sc.ecut, sc.B_sc)
+    nb = 3
+    raw = np.zeros(nb * g_ref.shape[0] * 8, dtype=np.uint8)
+    raw.view(np.complex64)[:] = 1.0
+    nsp, npw = unfolder.submit_vasp(60, raw, g_ref.shape[0] * 8, g_ref.shape[0], nb, sc.sc_kpts_frac[iK], sc.ecut,
+                                    np.array([-1.0, 0.0, 1.0]), folding_G=sc.folding_G(iK))
+    assert (nsp, npw) == (1, g_ref.shape[0]) and npw > 90_000
+    assert np.array_equal(unfolder.fetch_gvecs(60, npw), g_ref)
+    res = unfolder.fetch(60)
+    assert np.allclose(res.band_norms, npw) and np.all(res.n_selected > 0)
