@@ -102,8 +102,9 @@ class ShardedUnfoldJob:
     the delta_N rows.  `unfolder` is anything with submit(ikpt, wf, g0=/folding_G=) / fetch(ikpt)
     (bandup_b200.unfold.GpuUnfolder on a GPU box; a stand-in in the CPU tests).
 
-    load_kpt(iK) -> (wf, folding_G, row_ids): the wavefunction of SC-kpt iK, the Cartesian folding
-    vectors of the pc-kpts that fold onto it and their global row ids in the output table."""
+    load_kpt(iK) -> (wf, folding_G, row_ids): the wavefunction of SC-kpt iK (or a callable
+    (unfolder, iK, folding_G) that submits it), the Cartesian folding vectors of the pc-kpts that
+    fold onto it and their global row ids in the output table."""
 
     def __init__(self, unfolder, n_kpts: int, costs: Sequence[float], load_kpt: Callable,
                  rank: int = 0, world_size: int = 1, depth: int = 2,
@@ -144,7 +145,10 @@ class ShardedUnfoldJob:
             wf, folding_G, rid = self.load_kpt(iK)
             if len(inflight) >= self.depth:
                 drain_one()
-            self.unfolder.submit(iK, wf, folding_G=folding_G)
+            if callable(wf):      # the loader submits by itself (e.g. raw file records, device-made G list)
+                wf(self.unfolder, iK, folding_G)
+            else:
+                self.unfolder.submit(iK, wf, folding_G=folding_G)
             inflight.append((iK, np.asarray(rid, dtype=np.int64)))
         while inflight:
             drain_one()

@@ -440,8 +440,12 @@ def calc_spin_projections(pauli_vector, cart_coords_kpt, normal_to_proj_plane, o
     return float(np.dot(pv, perp)), float(np.dot(pv, para))
 
 
+_PINNED = {}   # data address -> base pointer of live bandup_gpu_pinned_alloc blocks
+
+
 def pinned_empty(nbytes: int) -> np.ndarray:
-    """uint8 NumPy view of page-locked host memory (bandup_gpu_pinned_alloc)."""
+    """uint8 NumPy view of page-locked host memory (bandup_gpu_pinned_alloc); release it with
+    pinned_free once no upload from it is in flight."""
     lib = _capi.load()
     p = C.c_void_p()
     rc = lib.bandup_gpu_pinned_alloc(int(nbytes), C.byref(p))
@@ -449,4 +453,12 @@ def pinned_empty(nbytes: int) -> np.ndarray:
         raise BandupGpuError(rc, lib.bandup_gpu_last_error(-1).decode())
     buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=np.uint8)
+    _PINNED[arr.ctypes.data] = p.value
     return arr
+
+
+def pinned_free(arr: np.ndarray) -> None:
+    """bandup_gpu_pinned_free for a buffer from pinned_empty (the array must not be used afterwards)."""
+    base = _PINNED.pop(arr.ctypes.data, None)
+    if base is not None:
+        _capi.load().bandup_gpu_pinned_free(C.c_void_p(base))

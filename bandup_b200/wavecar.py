@@ -207,14 +207,14 @@ def fold_pckpts_onto_sckpts(pc_kpts_cart: np.ndarray, sc_kpts_frac: np.ndarray, 
 
 def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_cart: np.ndarray,
                    E_start: float, E_end: float, delta_e: float, ispin: int = 1, rank: int = 0,
-                   world_size: int = 1, device=None, group=None, after_fetch=None):
+                   world_size: int = 1, device=None, group=None, after_fetch=None, device_gvecs: bool = True):
     """The reference's main loop (main_BandUP.f90:131-177) over a WAVECAR under its no-symmetry
     flags (-no_symm_sckpts -no_symm_avg): every SC-kpt of the file, all pc-kpts folding onto it in
     one pass, raw band records read into two page-locked buffers and uploaded as they are while the
     previous k-point computes.  Returns sharding.GatheredDeltaN (rows in pc-kpt order) and the
     energy grid."""
     from .sharding import ShardedUnfoldJob
-    from .unfold import pinned_empty
+    from .unfold import pinned_empty, pinned_free
     unfolder.verify_commens(rec_latt_pc, wavecar.B_matrix)
     grid = unfolder.set_energy_grid(E_start, E_end, delta_e)
     sc_k = np.array([wavecar.kpt_header(i + 1, ispin).kpt_frac_coords for i in range(wavecar.nkpts)])
@@ -227,13 +227,22 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
 
     def load(j):
         i = used[j]
-        wf = wavecar.wavefunction(i + 1, ispin, out=bufs[j % len(bufs)])
         fG = np.asarray(pc_kpts_cart)[folds[i]] - K_cart[i]
-        return wf, fG, np.asarray(folds[i])
+        buf = bufs[j % len(bufs)]
+        if device_gvecs:   # header + raw records only; the plane-wave list is made on the device
+
+            def submit(u, job_ikpt, folding_G):
+                wavecar.submit_to(u, job_ikpt, i + 1, folding_G, ispin, out=buf)
+            return submit, fG, np.asarray(folds[i])
+        return wavecar.wavefunction(i + 1, ispin, out=buf), fG, np.asarray(folds[i])
 
     job = ShardedUnfoldJob(unfolder, len(used), costs, load, rank=rank, world_size=world_size, depth=2,
                            after_fetch=after_fetch)
-    got = job.run(device=device, group=group)
+    try:
+        got = job.run(device=device, group=group)
+    finally:
+        for b in bufs:     # every k-point has been fetched (or the job failed): no upload is in flight
+            pinned_free(b)
     got.sckpt_of_row = {int(r): used[j] for j in range(len(used)) for r in folds[used[j]]}
     got.sckpts_cart = K_cart
     return got, grid

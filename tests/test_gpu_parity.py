@@ -412,6 +412,8 @@ def test_unfold_from_wavecar_file(unfolder, tmp_path, name, scale):
                   extra_pad=1)
     wc = Wavecar(path)
     got, grid = unfold_wavecar(unfolder, wc, sc.b_pc, sc.pc_kpts_cart, *sc.energy_window())
+    host_g, _ = unfold_wavecar(unfolder, wc, sc.b_pc, sc.pc_kpts_cart, *sc.energy_window(), device_gvecs=False)
+    assert np.array_equal(got.dN, host_g.dN)            # device-made and host-made plane-wave lists agree
     n_rows = sum(len(f) for f in sc.folds)
     assert got.row_ids.tolist() == list(range(n_rows))
     for iK in range(sc.n_sc_kpts):
