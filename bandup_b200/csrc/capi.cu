@@ -302,9 +302,17 @@ struct WorkspaceLayout {
   size_t slot_off, slot_shift_off, counts_off, partials_off, tmp_w_off, tmp_dn_off, tmp_ns_off, total;
 };
 
-WorkspaceLayout workspace_layout(const Ctx* c, int n_spinor, int n_pw, int n_bands, int n_fold) {
+// batch_n: k-points launched together -- the K2 tile size is chosen so that the WHOLE launch
+// has enough tiles to balance the persistent grid (k-points of a job are alike)
+int pick_chunk_vecs(const Ctx* c, long long row_elems, int n_bands, int batch_n) {
+  const long long rows = (long long)n_bands * (batch_n > 0 ? batch_n : 1);
+  return weights_pick_chunk_vecs(c->chunk_vecs, row_elems, (int)(rows > 2000000000LL ? 2000000000LL : rows),
+                                 c->sm_count);
+}
+
+WorkspaceLayout workspace_layout(const Ctx* c, int n_spinor, int n_pw, int n_bands, int n_fold, int batch_n = 1) {
   WorkspaceLayout w;
-  const int cv = weights_pick_chunk_vecs(c->chunk_vecs, (long long)n_pw * n_spinor, n_bands, c->sm_count);
+  const int cv = pick_chunk_vecs(c, (long long)n_pw * n_spinor, n_bands, batch_n);
   const int n_chunks = weights_num_chunks((long long)n_pw * n_spinor, cv);
   size_t off = 0;
   w.slot_off = off;
@@ -387,7 +395,7 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
     BatchItem& it = items[(size_t)i];
     if (it.n_spinor != items[0].n_spinor || it.layout != items[0].layout)
       return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "all k-points of a batch must share n_spinor and layout");
-    const WorkspaceLayout wl = workspace_layout(c, it.n_spinor, it.n_pw, it.n_bands, it.n_fold);
+    const WorkspaceLayout wl = workspace_layout(c, it.n_spinor, it.n_pw, it.n_bands, it.n_fold, n);
     const bool dup = it.plan.n_unique != it.n_fold;
     any_dup = any_dup || dup;
     KptGeom& g = geoms[(size_t)i];
@@ -405,7 +413,7 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
     g.block_counts = reinterpret_cast<int*>(it.ws + wl.counts_off);
     g.n_selected = dup ? reinterpret_cast<int32_t*>(it.ws + wl.tmp_ns_off) : it.d_nsel;
     g.n_fold = it.plan.n_unique;
-    g.chunk_vecs = weights_pick_chunk_vecs(c->chunk_vecs, g.row_elems, it.n_bands, c->sm_count);
+    g.chunk_vecs = pick_chunk_vecs(c, g.row_elems, it.n_bands, n);
     g.n_chunks = weights_num_chunks(g.row_elems, g.chunk_vecs);
     g.perform_unfold = c->perform_unfold ? 1 : 0;
     g.tile_begin = tiles;
@@ -727,7 +735,7 @@ size_t bandup_gpu_batch_workspace_bytes(int handle, int n_kpts, const bandup_gpu
   if (!c || !descs || n_kpts < 1) return 0;
   size_t total = 0;
   for (int i = 0; i < n_kpts; ++i)
-    total += workspace_layout(c, descs[i].n_spinor, descs[i].n_pw, descs[i].n_bands, descs[i].n_fold).total;
+    total += workspace_layout(c, descs[i].n_spinor, descs[i].n_pw, descs[i].n_bands, descs[i].n_fold, n_kpts).total;
   return total;
 }
 
@@ -753,7 +761,7 @@ int bandup_gpu_unfold_device_batch(int handle, void* stream, int n_kpts, const b
     it.d_weights = d.d_weights; it.d_dN = d.d_dN; it.d_nsel = d.d_n_selected; it.d_norms = d.d_norms;
     it.d_slot_out = nullptr;
     it.ws = static_cast<char*>(d_workspace) + off;
-    off += workspace_layout(c, d.n_spinor, d.n_pw, d.n_bands, d.n_fold).total;
+    off += workspace_layout(c, d.n_spinor, d.n_pw, d.n_bands, d.n_fold, n_kpts).total;
   }
   if (off > workspace_bytes)
     return fail(c, BANDUP_GPU_ERR_CAPACITY, "workspace too small: need " + std::to_string(off) + " bytes");

@@ -346,7 +346,7 @@ def test_sharded_job_whole_scenario(unfolder):
 
 def test_device_batch_equals_per_kpt_calls(unfolder):
     """bandup_gpu_unfold_device_batch (one launch of each kernel for several SC-kpts with different
-    n_pw / n_fold, one of them with two pc-kpts in the same coset) gives bit-identical results to
+    n_pw / n_fold, one of them with two pc-kpts in the same coset) gives the same results as
     per-k-point bandup_gpu_unfold_device calls, and both agree with the oracle."""
     import torch
     from bandup_b200.unfold import LAYOUT_FORTRAN_INMEM
@@ -390,8 +390,11 @@ def test_device_batch_equals_per_kpt_calls(unfolder):
                                t["g"].data_ptr(), t["e"].data_ptr(), g0, o["w"].data_ptr(), o["dn"].data_ptr(),
                                o["ns"].data_ptr(), d_w1.data_ptr(), w1, d_norms=o["nr"].data_ptr())
         torch.cuda.synchronize()
-        for key in ("w", "dn", "ns", "nr"):
-            assert torch.equal(outs[0][key], outs[1][key]), key
+        # same numbers; the tile size may differ between a batch and a single k-point, so the fp64
+        # partial sums may be grouped differently (last-bit differences only)
+        assert torch.equal(outs[0]["ns"], outs[1]["ns"])
+        for key in ("w", "dn", "nr"):
+            assert torch.allclose(outs[0][key], outs[1][key], rtol=1e-12, atol=1e-300), key
         w, dN, ns, _ = oracle_kpt(sc, coeffs, gf, ener, fG, grid)
         assert np.array_equal(outs[0]["ns"].cpu().numpy(), ns)
         assert rel_err(outs[0]["w"].cpu().numpy(), w) <= REL_TOL
