@@ -581,3 +581,44 @@ def test_device_gvecs_full_size(unfolder):
     assert np.array_equal(unfolder.fetch_gvecs(60, npw), g_ref)
     res = unfolder.fetch(60)
     assert np.allclose(res.band_norms, npw) and np.all(res.n_selected > 0)
+
+
+@pytest.mark.parametrize("n_pw,n_bands,n_spinor", [(1, 1, 1), (2, 3, 1), (3, 2, 2), (5, 1, 2), (1025, 2, 1)])
+def test_tiny_and_ragged_blocks(unfolder, n_pw, n_bands, n_spinor):
+    """Rows shorter than one 16-byte vector, rows of exactly one stage + 1, single bands."""
+    from bandup_b200.unfold import PwWavefunction
+    from oracle import oracle as O
+    sc = synth.make_scenario("graphene4x4", scale=0.3)
+    grid = setup(unfolder, sc)
+    gf = sc.gvecs(0)[:n_pw]
+    rng = np.random.default_rng(n_pw * 7 + n_bands)
+    coeffs = (rng.standard_normal((n_bands, n_pw, n_spinor)) + 1j * rng.standard_normal((n_bands, n_pw, n_spinor))
+              ).astype(np.complex64)
+    ener = np.sort(rng.uniform(-5, 2, n_bands))
+    g0 = np.array([[0, 0, 0], [1, 0, 0]], dtype=np.int32)
+    res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), g0=g0)
+    fG = g0.astype(np.float64) @ sc.B_sc
+    w, dN, ns, _ = O.unfold_kpt(coeffs, gf @ sc.B_sc, ener, sc.b_pc, fG, grid, norm_mode=1)
+    assert np.array_equal(res.n_selected, ns)
+    assert rel_err(res.spectral_weight, w) <= REL_TOL and rel_err(res.dN, dN) <= REL_TOL
+    _, norms = O.renormalize(coeffs, 1)
+    assert rel_err(res.band_norms, norms) <= REL_TOL
+
+
+def test_sixty_four_distinct_cosets(unfolder):
+    """BANDUP_GPU_MAX_FOLDS distinct cosets in one pass: the shared-memory bins take 130 KB and the
+    stage ring shrinks to what is left."""
+    from bandup_b200.unfold import MAX_FOLDS, PwWavefunction
+    sc = synth.make_scenario("si333_vacancy", scale=0.25)
+    grid = setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 1)
+    cube = np.array([[i, j, k] for i in range(5) for j in range(5) for k in range(5)], dtype=np.int32)
+    lab = synth.coset_labels(cube, sc.M)
+    _, first = np.unique(lab, return_index=True)
+    g0 = cube[np.sort(first)[:MAX_FOLDS]]
+    assert g0.shape[0] == MAX_FOLDS
+    res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), g0=g0, want_selected=False)
+    w, dN, ns, _ = oracle_kpt(sc, coeffs, gf, ener, g0.astype(np.float64) @ sc.B_sc, grid)
+    assert np.array_equal(res.n_selected, ns)
+    assert rel_err(res.spectral_weight, w) <= REL_TOL and rel_err(res.dN, dN) <= REL_TOL
+    assert np.all(res.spectral_weight.sum(axis=0) <= 1.0 + 1e-7)
