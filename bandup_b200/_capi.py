@@ -105,6 +105,11 @@ def load() -> C.CDLL:
         "bandup_gpu_batch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.POINTER(KptDesc)]),
         "bandup_gpu_unfold_device_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(KptDesc),
                                                      C.c_void_p, C.c_size_t]),
+        "bandup_gpu_comm_unique_id": (C.c_int, [C.c_void_p]),
+        "bandup_gpu_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+        "bandup_gpu_comm_finalize": (C.c_int, [C.c_int]),
+        "bandup_gpu_gather_dN": (C.c_int, [C.c_int, c_f64p, C.POINTER(C.c_int64), C.c_int64, c_f64p,
+                                           C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]),
         "bandup_gpu_set_profiling": (C.c_int, [C.c_int, C.c_int]),
         "bandup_gpu_kernel_time": (C.c_int, [C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int64)]),
         "bandup_gpu_reset_kernel_times": (C.c_int, [C.c_int]),

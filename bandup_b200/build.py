@@ -18,8 +18,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libbandup_gpu.so"
-SOURCES = ["capi.cu", "coset_classify.cu", "weights_reduce.cu", "delta_n.cu", "rho.cu", "gvecs.cu", "synth.cu"]
-HEADERS = [CSRC / "kernels.cuh", PKG.parent / "include" / "bandup_gpu.h"]
+SOURCES = ["capi.cu", "coset_classify.cu", "weights_reduce.cu", "delta_n.cu", "rho.cu", "gvecs.cu", "comm.cu", "synth.cu"]
+HEADERS = [CSRC / "kernels.cuh", CSRC / "nccl_dyn.h", PKG.parent / "include" / "bandup_gpu.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     env.pop("CXX", None)
     cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", shutil.which("g++") or "g++",
            "-I", str(PKG.parent / "include"),
-           "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
+           "-o", str(LIB), *[str(CSRC / s) for s in SOURCES], "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)
     (LIBDIR / "build.log").write_text(" ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose or res.returncode != 0:

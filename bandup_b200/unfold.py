@@ -404,6 +404,40 @@ class GpuUnfolder:
             self.handle, C.c_void_p(stream), C.c_void_p(d_coeffs), int(row_elems), int(n_bands),
             int(band_stride_bytes), C.c_uint64(seed), C.c_uint64(ikpt)))
 
+    # -- multi-GPU gather (NCCL inside the library) ------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL id made by rank 0; hand it to the other ranks, then comm_init everywhere."""
+        lib = _capi.load()
+        buf = C.create_string_buffer(CONST["BANDUP_GPU_COMM_ID_BYTES"])
+        rc = lib.bandup_gpu_comm_unique_id(buf)
+        if rc != 0:
+            raise BandupGpuError(rc, lib.bandup_gpu_last_error(-1).decode())
+        return buf.raw
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes) -> None:
+        buf = C.create_string_buffer(unique_id, CONST["BANDUP_GPU_COMM_ID_BYTES"])
+        self._check(self._lib.bandup_gpu_comm_init(self.handle, int(n_ranks), int(rank), buf))
+
+    def comm_finalize(self) -> None:
+        self._check(self._lib.bandup_gpu_comm_finalize(self.handle))
+
+    def gather_dN(self, dN_local: np.ndarray, row_ids_local: np.ndarray):
+        """ncclAllGather of the disjoint delta_N rows of all ranks; returns (dN_all, row_ids_all)
+        in ascending global row id on every rank."""
+        d = np.ascontiguousarray(dN_local, dtype=np.float64).reshape(-1, self.nener)
+        ids = np.ascontiguousarray(row_ids_local, dtype=np.int64).reshape(-1)
+        i64p = C.POINTER(C.c_int64)
+        tot = C.c_int64(0)
+        self._check(self._lib.bandup_gpu_gather_dN(self.handle, d.ctypes.data_as(c_f64p), ids.ctypes.data_as(i64p),
+                                                   ids.shape[0], None, None, 0, C.byref(tot)))
+        out = np.zeros((tot.value, self.nener), dtype=np.float64)
+        oid = np.zeros(tot.value, dtype=np.int64)
+        self._check(self._lib.bandup_gpu_gather_dN(self.handle, d.ctypes.data_as(c_f64p), ids.ctypes.data_as(i64p),
+                                                   ids.shape[0], out.ctypes.data_as(c_f64p), oid.ctypes.data_as(i64p),
+                                                   tot.value, C.byref(tot)))
+        return out, oid
+
     # -- instrumentation ------------------------------------------------------
     def set_profiling(self, enabled: bool) -> None:
         self._check(self._lib.bandup_gpu_set_profiling(self.handle, int(bool(enabled))))

@@ -24,6 +24,7 @@ public :: bandup_gpu_init, bandup_gpu_finalize, bandup_gpu_last_error, &
           bandup_gpu_rho_count, bandup_gpu_fetch_rho, bandup_gpu_pauli_vectors, &
           bandup_gpu_spectral_function, bandup_gpu_set_perform_unfold, &
           bandup_gpu_orb_contrib_matrix, bandup_gpu_set_operator, bandup_gpu_unfold_operator, &
+          bandup_gpu_comm_unique_id, bandup_gpu_comm_init, bandup_gpu_comm_finalize, bandup_gpu_gather_dN, &
           bandup_gpu_unfold_kpt_f, bandup_gpu_error_message
 public :: BANDUP_GPU_OK, BANDUP_GPU_LAYOUT_FORTRAN_INMEM, BANDUP_GPU_LAYOUT_VASP_RECORD, &
           BANDUP_GPU_MAX_FOLDS
@@ -239,6 +240,40 @@ interface
         real(c_double), intent(out) :: out(*)
         integer(c_int) :: bandup_gpu_unfold_operator
     end function bandup_gpu_unfold_operator
+
+    ! multi-GPU (one BandUP process per GPU): rank 0 makes the id, MPI_Bcast's its 128 bytes,
+    ! every rank calls comm_init; gather_dN is the path's only collective (ncclAllGather)
+    function bandup_gpu_comm_unique_id(id) bind(c, name='bandup_gpu_comm_unique_id')
+        import c_int, c_char
+        character(kind=c_char), intent(out) :: id(128)
+        integer(c_int) :: bandup_gpu_comm_unique_id
+    end function bandup_gpu_comm_unique_id
+
+    function bandup_gpu_comm_init(handle, n_ranks, rank, id) bind(c, name='bandup_gpu_comm_init')
+        import c_int, c_char
+        integer(c_int), intent(in), value :: handle, n_ranks, rank
+        character(kind=c_char), intent(in) :: id(128)
+        integer(c_int) :: bandup_gpu_comm_init
+    end function bandup_gpu_comm_init
+
+    function bandup_gpu_comm_finalize(handle) bind(c, name='bandup_gpu_comm_finalize')
+        import c_int
+        integer(c_int), intent(in), value :: handle
+        integer(c_int) :: bandup_gpu_comm_finalize
+    end function bandup_gpu_comm_finalize
+
+    function bandup_gpu_gather_dN(handle, dN_local, row_ids_local, n_local, dN_all, row_ids_all, &
+                                  capacity_rows, n_total) bind(c, name='bandup_gpu_gather_dN')
+        import c_int, c_int64_t, c_double, c_ptr
+        integer(c_int), intent(in), value :: handle
+        real(c_double), intent(in) :: dN_local(*)
+        integer(c_int64_t), intent(in) :: row_ids_local(*)
+        integer(c_int64_t), intent(in), value :: n_local
+        type(c_ptr), intent(in), value :: dN_all, row_ids_all
+        integer(c_int64_t), intent(in), value :: capacity_rows
+        integer(c_int64_t), intent(out) :: n_total
+        integer(c_int) :: bandup_gpu_gather_dN
+    end function bandup_gpu_gather_dN
 
     function bandup_gpu_set_profiling(handle, enabled) bind(c, name='bandup_gpu_set_profiling')
         import c_int

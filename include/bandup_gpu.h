@@ -52,6 +52,7 @@ extern "C" {
 /* calc_rho :1070-1074 'ERROR (calc_rho): delta_N = 0.' */
 #define BANDUP_GPU_ERR_DELTA_N_ZERO 11
 #define BANDUP_GPU_ERR_INT_OVERFLOW 12  /* Miller indices x adjugate would overflow */
+#define BANDUP_GPU_ERR_NCCL 13          /* libnccl not found, or a NCCL call failed */
 
 /* most DISTINCT cosets (pc-kpts whose folding vectors differ by more than a pc reciprocal
  * vector) among the pc-kpts of one submit, and most pc-kpts per submit; pc-kpts that share a
@@ -283,6 +284,26 @@ size_t bandup_gpu_batch_workspace_bytes(int handle, int n_kpts, const bandup_gpu
 int bandup_gpu_unfold_device_batch(int handle, void *stream, int n_kpts,
                                    const bandup_gpu_kpt_desc *descs, void *d_workspace,
                                    size_t workspace_bytes);
+
+/* ---- multi-GPU: one process per GPU, SC k-points sharded, delta_N gathered ---- */
+/* SC k-points are independent and every pc-kpt folds onto exactly one SC-kpt
+ * (band_unfolding_routines_mod.f90:317-324, 396-403), so ranks exchange nothing but their
+ * disjoint delta_N rows at the end: one ncclAllGather over NVLink.  libnccl is resolved at run
+ * time (dlopen; $BANDUP_GPU_NCCL_LIB overrides the search).
+ *   rank 0 calls bandup_gpu_comm_unique_id and hands the 128 bytes to the other processes by
+ *   whatever means the host has (MPI_Bcast in a Fortran host, a file, torch.distributed ...);
+ *   every rank calls bandup_gpu_comm_init with them. */
+#define BANDUP_GPU_COMM_ID_BYTES 128
+int bandup_gpu_comm_unique_id(void *id);
+int bandup_gpu_comm_init(int handle, int n_ranks, int rank, const void *id);
+int bandup_gpu_comm_finalize(int handle);
+/* Collective.  dN_local [n_local][nener] + the global pc-kpt row id of every row (HOST); every
+ * rank receives all rows in ascending row id: dN_all [n_total][nener], row_ids_all [n_total]
+ * (HOST, capacity_rows rows).  With dN_all == NULL only *n_total is returned.  A row id
+ * contributed twice is an error (a pc-kpt unfolded by two ranks). */
+int bandup_gpu_gather_dN(int handle, const double *dN_local, const int64_t *row_ids_local,
+                         int64_t n_local, double *dN_all, int64_t *row_ids_all,
+                         int64_t capacity_rows, int64_t *n_total);
 
 /* ---- instrumentation ---------------------------------------------------- */
 

@@ -1,0 +1,70 @@
+"""Two processes, two GPUs: SC-kpt shards unfolded independently, delta_N rows gathered with the
+library's own ncclAllGather (bandup_gpu_gather_dN).  Skipped on boxes with fewer than 2 GPUs."""
+import os
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from bandup_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, tmp, ret):
+    from bandup_b200.sharding import ShardedUnfoldJob
+    from bandup_b200.unfold import GpuUnfolder, PwWavefunction
+    sc = synth.make_scenario("graphene4x4", scale=0.08, n_kpts=12)
+    idf = Path(tmp) / "nccl_id"
+    if rank == 0:
+        uid = GpuUnfolder.comm_unique_id()
+        (Path(tmp) / "nccl_id.tmp").write_bytes(uid)
+        os.replace(Path(tmp) / "nccl_id.tmp", idf)          # the host's own way of sharing 128 bytes
+    else:
+        t0 = time.time()
+        while not idf.exists():
+            if time.time() - t0 > 60:
+                raise TimeoutError("no NCCL id from rank 0")
+            time.sleep(0.05)
+        uid = idf.read_bytes()
+    with GpuUnfolder(rank) as u:
+        u.verify_commens(sc.b_pc, sc.B_sc)
+        u.set_energy_grid(*sc.energy_window())
+        u.comm_init(world, rank, uid)
+
+        def load(iK):
+            coeffs, gf, ener = synth.make_wavefunction(sc, iK)
+            return PwWavefunction(coeffs, gf, ener), sc.folding_G(iK), np.asarray(sc.folds[iK])
+
+        costs = [sc.n_bands * sc.gvecs(iK).shape[0] for iK in range(sc.n_sc_kpts)]
+        job = ShardedUnfoldJob(u, sc.n_sc_kpts, costs, load, rank=rank, world_size=world)
+        dN, rid, _ = job.run_local()
+        allrows, allids = u.gather_dN(dN, rid)
+        ret[rank] = (allrows, allids, job.my_block, len(rid))
+        u.comm_finalize()
+
+
+def test_two_gpus_shard_and_nccl_gather():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import oracle as O
+    sc = synth.make_scenario("graphene4x4", scale=0.08, n_kpts=12)
+    with tempfile.TemporaryDirectory() as tmp, mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(2, tmp, ret), nprocs=2, join=True)
+        r0, r1 = ret[0], ret[1]
+    n_rows = sum(len(f) for f in sc.folds)
+    assert r0[1].tolist() == list(range(n_rows)) and np.array_equal(r0[1], r1[1])
+    assert np.array_equal(r0[0], r1[0])                       # every rank holds the same table
+    assert r0[3] > 0 and r1[3] > 0 and r0[3] + r1[3] == n_rows
+    assert r0[2][1] == r1[2][0]
+    grid = O.real_seq(*sc.energy_window())
+    for iK in range(sc.n_sc_kpts):
+        coeffs, gf, ener = synth.make_wavefunction(sc, iK)
+        _, dN, _, _ = O.unfold_kpt(coeffs, gf @ sc.B_sc, ener, sc.b_pc, sc.folding_G(iK), grid, norm_mode=1)
+        got = r0[0][np.asarray(sc.folds[iK])]
+        assert np.max(np.abs(got - dN) / np.maximum(np.abs(dN), 1e-12)) <= 1e-6
