@@ -322,7 +322,9 @@ def run_b200(args, sc, rank, world, local_rank):
     ms = max_over_ranks(e0.elapsed_time(e1))
     gpu_launches = u.launch_count() - launches0
     k2_ms, k2_n = u.kernel_time(K_WEIGHTS)
-    all_ms = sum(u.kernel_time(k)[0] for k in range(4))
+    per_kernel = {name: u.kernel_time(k)[0] / args.steps for k, name in
+                  enumerate(["k1_coset_classify", "k2_weights_reduce", "k2b_weights_finalize", "k3_delta_n"])}
+    all_ms = sum(per_kernel.values()) * args.steps
     u.set_profiling(False)
     # every rank streams its own shard; shard sizes differ only through n_pw(K) (a few per cent)
     if world > 1:
@@ -339,7 +341,8 @@ def run_b200(args, sc, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": "k2_weights_reduce", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_launch": k2_bytes, "ms_per_launch": k2_ms / max(k2_n, 1),
-                "k2_share_of_kernel_time": k2_ms / all_ms if all_ms else None}
+                "k2_share_of_kernel_time": k2_ms / all_ms if all_ms else None,
+                "kernel_ms_per_step": per_kernel}
     ncu_traffic = ROOT / "profiles" / "k2_traffic.json"
     if ncu_traffic.exists():
         try:

@@ -1,0 +1,46 @@
+"""bench.py's one-JSON-line contract (what the driver parses)."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"}
+
+
+def _run(args, timeout=600):
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), *args], capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout                  # exactly ONE line on stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_json_line():
+    d = _run(["--impl", "reference", "--workload", "graphene4x4", "--steps", "2", "--warmup", "1"])
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["metric"] == "coeff_GB_per_s" and d["unit"] == "GB/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["vs_baseline"] is None and d["scaling"] == "weak"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+@pytest.mark.gpu
+def test_b200_arm_json_line():
+    d = _run(["--workload", "si333_vacancy", "--steps", "3", "--warmup", "3", "--kpts-per-step", "2",
+              "--cpu-seconds", "1"])
+    assert BASE_KEYS | {"roofline", "clocks", "gpu_launches"} <= set(d)
+    assert d["n_gpus"] == 1 and d["gpu_launches"] == 4 * 3 and d["value"] > 0
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert set(rf["kernel_ms_per_step"]) == {"k1_coset_classify", "k2_weights_reduce", "k2b_weights_finalize", "k3_delta_n"}
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 2 * 500 * 19000 * 8 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] < d["value"]                    # host<->device copies are inside the e2e region
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
