@@ -40,40 +40,51 @@ __device__ __forceinline__ double lambda_box_erf(double pc_ener, double sc_ener,
 constexpr int kK3Threads = 256;   // 8 warps = 8 energy bins of one fold per CTA
 constexpr int kK3BandTile = 2048;  // band energies staged in shared memory per pass
 
-// grid (ceil(nener/8) * max_n_fold, n_kpts)
+// grid (ceil(nener/8), n_kpts): one warp per energy bin, ALL folds of the k-point.  Which bands
+// can contribute to a bin, and lambda itself, depend on the bin and the band energy only -- not on
+// the fold -- so the scan and the erf evaluations are done once and reused for every fold.
 __global__ void __launch_bounds__(kK3Threads)
 k3_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict__ grid, int nener, double sigma) {
   __shared__ double s_ener[kK3BandTile];
   __shared__ int s_hit[kK3Threads / 32][64];
+  __shared__ double s_acc[kK3Threads / 32][kMaxFolds];
   const KptGeom& g = geoms[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int bins_per_cta = kK3Threads / 32;
-  const int ctas_per_fold = (nener + bins_per_cta - 1) / bins_per_cta;
-  const int f = blockIdx.x / ctas_per_fold;
-  if (f >= g.n_fold) return;
-  const int n_bands = g.n_bands;
+  const int n_bands = g.n_bands, n_fold = g.n_fold;
   const double* __restrict__ band_energies = g.energies;
-  const int ie = (blockIdx.x - f * ctas_per_fold) * bins_per_cta + warp;
+  const double* __restrict__ weights = g.weights;
+  const int ie = blockIdx.x * (kK3Threads / 32) + warp;
   const bool live = ie < nener;
   // delta_e = energies(2) - energies(1)  (:735)
   const double delta_e = __dsub_rn(grid[1], grid[0]);
   const double half_de = __dmul_rn(0.5, delta_e);
   const double sqrt2_sigma = __dmul_rn(sqrt(2.0), sigma);
   const double E = live ? grid[ie] : 0.0;
-  const double* w = g.weights + (long long)f * n_bands;
   const double reach = half_de + 8.0 * sqrt2_sigma;
   const double guard = reach + 1e-9 * (fabs(E) + reach);
   int* hits = s_hit[warp];
+  double* acc = s_acc[warp];
+  for (int f = lane; f < n_fold; f += 32) acc[f] = 0.0;
+  __syncwarp();
   int n_hit = 0;  // warp-uniform
-  double acc = 0.0;
   // The few bands that can contribute (|E_m - E_i| within the guard band) are first collected,
   // in ascending band order, then lambda (two erf, two divisions) is evaluated for up to 32 of
-  // them at once, one per lane -- instead of one after the other inside a divergent loop.
+  // them at once, one per lane; every fold then takes its sum_m P_m(f) * lambda_m with a
+  // shuffle tree (fixed order: deterministic).
   auto flush = [&](int count) {
+    double lam = 0.0;
+    int m = 0;
     if (lane < count) {
-      const int m = hits[lane];
-      const double lam = lambda_box_erf(E, band_energies[m], half_de, sqrt2_sigma);
-      if (lam != 0.0) acc = __dadd_rn(acc, __dmul_rn(w[m], lam));
+      m = hits[lane];
+      lam = lambda_box_erf(E, band_energies[m], half_de, sqrt2_sigma);
+    }
+    if (__ballot_sync(0xffffffffu, lam != 0.0) != 0u) {
+      for (int f = 0; f < n_fold; ++f) {
+        double v = (lam != 0.0) ? __dmul_rn(weights[(long long)f * n_bands + m], lam) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) acc[f] = __dadd_rn(acc[f], v);
+      }
     }
     __syncwarp();
   };
@@ -99,10 +110,9 @@ k3_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict__ grid, i
       }
     }
   }
-  if (live && n_hit > 0) flush(n_hit);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-  if (live && lane == 0) g.dN[(long long)f * nener + ie] = acc;
+  if (!live) return;
+  if (n_hit > 0) flush(n_hit);
+  for (int f = lane; f < n_fold; f += 32) g.dN[(long long)f * nener + ie] = acc[f];
 }
 
 // A(k, E_i) = sum_m P_m * delta(E_m - E_i), delta = Gaussian of standard deviation sigma
@@ -139,8 +149,7 @@ void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const do
                     int nener, double sigma, cudaStream_t s) {
   if (nener <= 0 || max_n_fold <= 0 || n_kpts <= 0) return;
   const int bins_per_cta = kK3Threads / 32;
-  const int ctas_per_fold = (nener + bins_per_cta - 1) / bins_per_cta;
-  dim3 grid((unsigned)(ctas_per_fold * max_n_fold), (unsigned)n_kpts);
+  dim3 grid((unsigned)((nener + bins_per_cta - 1) / bins_per_cta), (unsigned)n_kpts);
   k3_delta_n<<<grid, kK3Threads, 0, s>>>(d_geoms, d_grid, nener, sigma);
 }
 

@@ -402,7 +402,11 @@ def run_b200(args, sc, rank, world, local_rank):
         O.build()
         os.sched_setaffinity(0, all_cpus)        # the CPU baseline gets every host core again
         gbs, ckps, cores, done, phases = cpu_sample(sc, my_k, args.cpu_seconds, kps)
+        # the reference author's habit: OMP_NUM_THREADS = n_cores/2 (tutorial run script)
+        half = max(1, cores // 2)
+        gbs_half, _, _, _, _ = cpu_sample(sc, my_k, args.cpu_seconds / 4, 1, threads=half)
         cpu = {"value": gbs, "unit": UNIT, "cores": cores, "kind": "port", "sc_kpts_per_s": ckps,
+               "half_cores": {"cores": half, "value": gbs_half},
                "sample": f"{done} full-size SC k-point(s) of the step's batch; C+OpenMP restatement of the "
                          "reference loops (renormalise, select, weights, delta_N)",
                "phase_seconds": {"renormalise": phases[0], "select+weights": phases[1], "delta_N": phases[2]}}
