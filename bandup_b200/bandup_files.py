@@ -197,13 +197,88 @@ def read_band_struc(path) -> np.ndarray:
     return np.loadtxt(path, comments="#")
 
 
+SPDF = ['s', 'py', 'pz', 'px', 'dxy', 'dyz', 'dz2', 'dxz', 'dx2',
+        'fy(3x2-y2)', 'fxyz', 'fyz2', 'fz3', 'fxz2', 'fz(x2-y2)', 'fx(x2-3y2)']
+
+
+def formatted_orb_choice(orb_choices, supported: Sequence[str]) -> List[str]:
+    """bandupy/orbital_contributions.py:40-80: 'all', 's'/'p'/'d'/'f', 'sp2', 'sp3', ... or explicit
+    orbital names -> the picked orbitals in PROCAR order."""
+    if orb_choices is None:
+        orb_choices = 'all'
+    if isinstance(orb_choices, (list, tuple)):
+        picked = set()
+        for o in orb_choices:
+            picked.update(formatted_orb_choice(o, supported))
+        return [o for o in SPDF if o in picked]
+    table = {o: [o] for o in supported}
+    table['all'] = list(supported)
+    for general in ('s', 'p', 'd', 'f'):
+        table[general] = [o for o in supported if general in o.lower()]
+    table['sp2'] = table['spxy'] = table['spyx'] = ['s', 'px', 'py']
+    table['spxz'] = table['spzx'] = ['s', 'px', 'pz']
+    table['spyz'] = table['spzy'] = ['s', 'py', 'pz']
+    table['sp3'] = table['sp2'] + ['pz']
+    key = str(orb_choices).lower().strip()
+    if key not in table:
+        raise ValueError(f'ERROR: Invalid choice of orbital: "{orb_choices}".')
+    return table[key]
+
+
+def ao_mask(n_ions: int, orbitals: Sequence[str], picked_orbitals, selected_ion_indices=None) -> np.ndarray:
+    """uint8 mask over the combined atom/orbital index a = iat*n_orbs_per_atom + iorb
+    (KptInfo.combined_atom_orb_index, orbital_contributions.py:195-197)."""
+    picked = formatted_orb_choice(picked_orbitals, orbitals)
+    ions = range(n_ions) if selected_ion_indices is None else selected_ion_indices
+    mask = np.zeros(n_ions * len(orbitals), dtype=np.uint8)
+    for iat in ions:
+        for orb in picked:
+            mask[iat * len(orbitals) + list(orbitals).index(orb)] = 1
+    return mask
+
+
+def write_orb_dependent_ebs(path, kpath: PcKptsPath, energy_grid: np.ndarray, values: np.ndarray, e_fermi: float,
+                            n_atoms_sc: int, picked_atoms: str, picked_orbitals: Sequence[str],
+                            spin_channel: int = 1) -> None:
+    """unfolded_EBS_orb_dependent.dat (orbital_contributions.py:473-488): '%.4f  %.4f   %.4f' lines,
+    k outer / E inner, k coordinate as in the band-structure file, energies relative to E_F."""
+    grid = np.asarray(energy_grid, dtype=np.float64)
+    with open(path, "w") as f:
+        f.write("# File created by bandup-b200 (GPU unfolding path)\n"
+                "# Orbital/atom-decomposed unfolded band structure\n"
+                f"# nAtomsSC: {n_atoms_sc}\n# PickedAtomIndicesSC: {picked_atoms}\n"
+                f"# OrbitalProjector: {'+'.join(picked_orbitals)}\n# SpinChannel: {spin_channel}\n"
+                "#KCoord #E-E_Fermi #{N*Unf[<Proj>]}(k,E)\n")
+        coord_first = kpath.zero_of_kpts_scale
+        coord_k = coord_first
+        row = 0
+        for d in kpath.directions:
+            first = d[0]
+            for k in d:
+                coord_k = coord_first + float(np.linalg.norm(k - first))
+                for ie, E in enumerate(grid):
+                    f.write("%.4f  %.4f   %.4f\n" % (coord_k, E - e_fermi, values[row, ie]))
+                row += 1
+            coord_first = coord_k
+
+
 def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_file, energy_file,
-                out_file: Optional[str] = None, spin_channel: int = 1, unf_dens_op_file: Optional[str] = None):
+                out_file: Optional[str] = None, spin_channel: int = 1, unf_dens_op_file: Optional[str] = None,
+                normal_to_proj_plane: Sequence[float] = (0.0, 0.0, 1.0), origin_for_spin_proj=None,
+                projections=None, orb_out_file: Optional[str] = None):
     """`bandup unfold` at file level for -no_symm_sckpts -no_symm_avg: parse the reference's input
     files, run every SC-kpt of the WAVECAR through the GPU (wavecar.unfold_wavecar) and write
-    unfolded_EBS_not-symmetry_averaged.dat; with unf_dens_op_file (the reference's
-    -write_unf_dens_op, i.e. `bandup unfold --orbitals`) also the unfolding-density operators in the
-    text format `bandup projected-unfold` reads.  Returns (kpath, energy_grid, dN)."""
+    unfolded_EBS_not-symmetry_averaged.dat -- for a spinor WAVECAR with the reference's five spin
+    columns (sigma_x, sigma_y, sigma_z, spin perp / para to k; io_routines_mod.f90:950-960).
+    unf_dens_op_file: the reference's -write_unf_dens_op (`bandup unfold --orbitals`), the
+        unfolding-density operators in the text format `bandup projected-unfold` reads.
+    projections + orb_out_file: `bandup projected-unfold` without the text round trip.
+        projections = dict(load=callable(sc_kpt_number 1-based) -> (proj_matrix (n_ao, n_bands),
+        proj_matrix_dual (n_bands, n_ao)) -- the 'direct'/'dual' arrays of the reference's
+        orbital_projections/proj_matrices_iKpt_*_iSpin_*.npz --, n_ions, orbitals, picked_orbitals,
+        selected_ion_indices); writes unfolded_EBS_orb_dependent.dat.
+    Returns (kpath, energy_grid, dN)."""
+    from .unfold import calc_spin_projections
     from .wavecar import Wavecar, unfold_wavecar
     a_pc = read_lattice(prim_cell_file)
     A_sc = read_lattice(supercell_file)
@@ -213,27 +288,79 @@ def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_f
     if not np.allclose(A_sc, wc.A_matrix, rtol=0, atol=1e-4 * np.abs(A_sc).max()):
         raise ValueError("supercell_lattice.in and the WAVECAR disagree about the supercell")
     kpath = read_pckpts(pckpts_file, b_pc)
+    all_k = kpath.all_kpts
     e_fermi, e_start, e_end, de = read_energy_info(energy_file)
-    rho_by_row = {}
+    rho_by_row, sigma_by_row, orb_by_row = {}, {}, {}
+    want_rho = bool(unf_dens_op_file)
+    want_orb = projections is not None and bool(orb_out_file)
+    file_kpt_of_job = {}
 
-    def collect_rho(iK, res, row_ids):
+    def after_fetch(iK, res, row_ids):
+        need_spin = res.n_spinor == 2
+        if need_spin:
+            spinor_kpts.add(iK)
+        if not (want_rho or want_orb or need_spin):
+            return
         ops = unfolder.calc_rho(iK)
-        for f, row in enumerate(row_ids):
-            s = ops.fold == f
-            rho_by_row[int(row)] = (ops.iener[s], ops.m1[s], ops.m2[s], ops.rho[s])
+        n_fold = len(row_ids)
+        if want_rho:
+            for f, row in enumerate(row_ids):
+                s = ops.fold == f
+                rho_by_row[int(row)] = (ops.iener[s], ops.m1[s], ops.m2[s], ops.rho[s])
+        if need_spin:
+            pv = unfolder.pauli_vectors(iK, n_fold)
+            for f, row in enumerate(row_ids):
+                sigma_by_row[int(row)] = pv[f]
+        if want_orb:
+            proj, dual = projections["load"](file_kpt_of_job[iK])
+            mask = ao_mask(projections["n_ions"], projections["orbitals"], projections.get("picked_orbitals", "all"),
+                           projections.get("selected_ion_indices"))
+            unfolder.get_orbital_contribution_matrix(dual, proj, mask, energies_of_job[iK])
+            vals = unfolder.unfold_operator(iK, n_fold, min_abs_rho=1e-4, clip=True)
+            for f, row in enumerate(row_ids):
+                orb_by_row[int(row)] = vals[f]
 
-    got, grid = unfold_wavecar(unfolder, wc, b_pc, kpath.all_kpts, e_start, e_end, de, ispin=spin_channel,
-                               after_fetch=collect_rho if unf_dens_op_file else None)
-    if got.row_ids.tolist() != list(range(kpath.all_kpts.shape[0])):
+    # band energies and file k-point numbers of the job's k-points: the headers say (scalar vs
+    # spinor is decided on the device when the k-point is submitted)
+    spinor_kpts, energies_of_job = set(), {}
+    sc_k = np.array([wc.kpt_header(i + 1, spin_channel).kpt_frac_coords for i in range(wc.nkpts)])
+    from .wavecar import fold_pckpts_onto_sckpts
+    folds = fold_pckpts_onto_sckpts(all_k, sc_k, wc.B_matrix)
+    used = [i for i in range(wc.nkpts) if folds[i]]
+    for j, i in enumerate(used):
+        h = wc.kpt_header(i + 1, spin_channel)
+        energies_of_job[j] = h.band_energies
+        file_kpt_of_job[j] = i + 1
+
+    got, grid = unfold_wavecar(unfolder, wc, b_pc, all_k, e_start, e_end, de, ispin=spin_channel,
+                               after_fetch=after_fetch)
+    n = all_k.shape[0]
+    if got.row_ids.tolist() != list(range(n)):
         # main_BandUP.f90:114: every requested pc-kpt must have been unfolded exactly once
         raise RuntimeError("not every pc-kpt was unfolded")
     if out_file:
-        write_band_struc(out_file, kpath, grid, got.dN, e_fermi)
-    if unf_dens_op_file:
-        n = kpath.all_kpts.shape[0]
+        sigma = spin_proj = None
+        if spinor_kpts:
+            sigma = np.stack([sigma_by_row[i] for i in range(n)])
+            spin_proj = np.zeros((n, grid.size, 2))
+            for i in range(n):
+                if np.linalg.norm(all_k[i] - (np.zeros(3) if origin_for_spin_proj is None
+                                              else np.asarray(origin_for_spin_proj))) < 1e-12:
+                    continue                      # the direction of k is undefined at the origin
+                for ie in np.nonzero(np.any(sigma[i] != 0.0, axis=1))[0]:
+                    spin_proj[i, ie] = calc_spin_projections(sigma[i, ie], all_k[i], normal_to_proj_plane,
+                                                             origin_for_spin_proj)
+        write_band_struc(out_file, kpath, grid, got.dN, e_fermi, sigma=sigma, spin_proj=spin_proj)
+    if want_rho:
         write_unf_dens_op(unf_dens_op_file, kpath, grid, got.dN, [rho_by_row[i] for i in range(n)], wc.nbands,
                           wc.B_matrix, b_pc, [got.sckpt_of_row[i] for i in range(n)], got.sckpts_cart,
                           e_fermi=e_fermi, spin_channel=spin_channel)
+    if want_orb:
+        ions = projections.get("selected_ion_indices")
+        write_orb_dependent_ebs(orb_out_file, kpath, grid, np.stack([orb_by_row[i] for i in range(n)]), e_fermi,
+                                projections["n_ions"], "All" if ions is None else ",".join(str(i + 1) for i in ions),
+                                formatted_orb_choice(projections.get("picked_orbitals", "all"), projections["orbitals"]),
+                                spin_channel)
     return kpath, grid, got.dN
 
 

@@ -84,6 +84,7 @@ class UnfoldedKpt:
     n_selected: np.ndarray                # (n_fold,)           size(selected_coeff_indices)
     band_norms: np.ndarray                # (n_bands,)          sum_G |C|^2 before renormalisation
     selected_coeff_indices: Optional[List[np.ndarray]] = None   # 1-based, ascending
+    n_spinor: int = 1
 
     def pckpt_cannot_be_parsed(self) -> np.ndarray:
         """main_BandUP.f90:161-172: an empty selection is the reference's fatal branch."""
@@ -261,7 +262,7 @@ class GpuUnfolder:
         if sel is not None:
             off = np.concatenate([[0], np.cumsum(ns)])
             lists = [sel[off[f]:off[f + 1]].copy() for f in range(n_fold)]
-        return UnfoldedKpt(w, dN, ns, norms, lists)
+        return UnfoldedKpt(w, dN, ns, norms, lists, n_spinor=wf.n_spinor)
 
     def perform_unfolding(self, wf: PwWavefunction, folding_G: Optional[np.ndarray] = None,
                           g0: Optional[np.ndarray] = None, ikpt: int = 1,

@@ -247,3 +247,79 @@ def test_pauli_vectors_spinor(unfolder):
     with pytest.raises(BandupGpuError) as ei:
         unfolder.pauli_vectors(8, 1)
     assert ei.value.code == 1
+
+
+def test_file_level_spinor_and_projected_outputs(unfolder, tmp_path):
+    """unfold_task on a spinor WAVECAR: the 8-column band-structure file (sigma_x,y,z + spin
+    projections) and, with PROCAR-like projections, unfolded_EBS_orb_dependent.dat
+    (`bandup projected-unfold` without the text round trip) -- against the oracle chain."""
+    from bandup_b200 import bandup_files as BF
+    from bandup_b200.unfold import calc_spin_projections
+    from bandup_b200.wavecar import write_wavecar
+    from oracle import oracle as O
+    from oracle import oracle_np as ON
+    a = synth.hex_cell(3.16, 18.0)
+    b = synth.rec_latt(a)
+    segs = [([0.0, 0.0, 0.0], [0.5, 0.0, 0.0]), ([0.5, 0.0, 0.0], [1 / 3, 1 / 3, 0.0])]
+    counts = [4, 3]
+    kcart = np.concatenate([BF.kpts_line(np.array(s) @ b, np.array(e) @ b, n) for (s, e), n in zip(segs, counts)])
+    sc = synth.Scenario("mos2", a, np.diag([4, 4, 1]), 25.0, 8, 2, kcart, e_fermi=0.4, emin=-10.0, emax=5.0, dE=0.1)
+    data = [synth.make_wavefunction(sc, iK) for iK in range(sc.n_sc_kpts)]
+    for d in data:
+        d[2][2] = d[2][1]                                   # a degenerate pair in every k-point
+    BF.write_lattice(tmp_path / "prim_cell_lattice.in", a)
+    BF.write_lattice(tmp_path / "supercell_lattice.in", sc.A_sc)
+    BF.write_pckpts(tmp_path / "KPOINTS_prim_cell.in", segs, counts)
+    BF.write_energy_info(tmp_path / "energy_info.in", sc.e_fermi, sc.emin, sc.emax, sc.dE)
+    write_wavecar(tmp_path / "WAVECAR", sc.A_sc, sc.ecut, list(sc.sc_kpts_frac), [d[0] for d in data],
+                  [d[2] for d in data])
+    n_ions, orbitals = 5, ['s', 'py', 'pz', 'px', 'dxy', 'dyz', 'dz2', 'dxz', 'dx2']
+    rng = np.random.default_rng(4)
+    projs = {}
+    for iK in range(sc.n_sc_kpts):
+        p = (rng.standard_normal((n_ions * 9, sc.n_bands)) + 1j * rng.standard_normal((n_ions * 9, sc.n_bands))) * 0.3
+        projs[iK + 1] = (p, np.linalg.pinv(p))
+    out, orb = tmp_path / "unfolded_EBS.dat", tmp_path / "unfolded_EBS_orb_dependent.dat"
+    kpath, grid, dN = BF.unfold_task(
+        unfolder, tmp_path / "WAVECAR", tmp_path / "prim_cell_lattice.in", tmp_path / "supercell_lattice.in",
+        tmp_path / "KPOINTS_prim_cell.in", tmp_path / "energy_info.in", out_file=str(out),
+        projections=dict(load=lambda ik: projs[ik], n_ions=n_ions, orbitals=orbitals, picked_orbitals='d',
+                         selected_ion_indices=[0, 2]), orb_out_file=str(orb))
+    tab = BF.read_band_struc(out)
+    n = sum(counts)
+    assert tab.shape == (n * len(grid), 8)
+    tab_orb = np.loadtxt(orb, comments="#")
+    assert tab_orb.shape == (n * len(grid), 3)
+    assert np.allclose(tab_orb[:, 0], tab[:, 0], atol=1e-4) and np.allclose(tab_orb[:, 1], tab[:, 1], atol=1e-4)
+    mask = BF.ao_mask(n_ions, orbitals, 'd', [0, 2])
+    assert mask.sum() == 2 * 5
+    de = grid[1] - grid[0]
+    checked = 0
+    for iK in range(sc.n_sc_kpts):
+        coeffs, gf, ener = data[iK]
+        gc = gf @ sc.B_sc
+        c_ren, _ = O.renormalize(coeffs, 1)
+        Omat = ON.orb_contrib_matrix(projs[iK + 1][1], projs[iK + 1][0], mask, ener)
+        for row in sc.folds[iK]:
+            sel, _ = O.select_coeffs(gc, sc.pc_kpts_cart[row] - sc.sc_kpts_cart[iK], sc.b_pc)
+            w = O.spectral_weights(c_ren, sel)
+            dn = O.delta_N(grid, ener, w)
+            rhos = {}
+            for ie in np.nonzero(dn >= 1e-3)[0]:
+                rho = ON.calc_rho(c_ren, sel, ener, dn[ie], grid[ie], de)
+                rho[np.abs(rho) < 1e-5] = 0.0
+                rhos[int(ie) + 1] = rho
+            pv = ON.unfolded_pauli_vectors(c_ren, ener, grid, rhos, de)
+            for ie1, vec in pv.items():
+                line = tab[row * len(grid) + ie1 - 1]
+                assert abs(line[2] - dn[ie1 - 1]) <= 6e-4 * dn[ie1 - 1]
+                assert np.all(np.abs(line[3:6] - vec) <= 6e-4 * np.abs(vec) + 2e-4)
+                if np.linalg.norm(sc.pc_kpts_cart[row]) > 1e-9:
+                    perp, para = calc_spin_projections(vec, sc.pc_kpts_cart[row], [0, 0, 1])
+                    assert abs(line[6] - perp) <= 2e-3 and abs(line[7] - para) <= 2e-3
+                up = np.triu(rhos[ie1])
+                r, c = np.nonzero(np.abs(up) >= 1e-4)
+                want = ON.unf_dens_op_unfold(list(r), list(c), list(up[r, c]), sc.n_bands, dn[ie1 - 1], Omat, True, True)
+                assert abs(tab_orb[row * len(grid) + ie1 - 1, 2] - want) <= 2e-4 + 1e-3 * abs(want)
+                checked += 1
+    assert checked > 10
