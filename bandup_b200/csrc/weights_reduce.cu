@@ -411,14 +411,14 @@ void launch_mode(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int 
 }  // namespace
 
 // Tile size.  Large tiles amortise the per-tile reduction (measured on B200, 3000 x 100k
-// block: 64 KB tiles 5.9 TB/s, 128 KB tiles 6.7 TB/s); small blocks need enough tiles to
+// block: 64 KB tiles 5.9 TB/s, 128 KB 6.7, 256 KB 6.75); small blocks need enough tiles to
 // balance the persistent grid, so the tile shrinks (down to one 16 KB stage) until there are
 // at least 6 tiles per CTA.
 int weights_pick_chunk_vecs(int requested, long long row_elems, int n_bands, int sm_count) {
   if (requested > 0) return ((requested + kStageVecs - 1) / kStageVecs) * kStageVecs;
   const long long nv = row_elems / 2;
   const long long want_tiles = 6LL * sm_count * 2;
-  int cv = 8 * kStageVecs;
+  int cv = 16 * kStageVecs;
   while (cv > kStageVecs && (long long)n_bands * ((nv + cv - 1) / cv) < want_tiles) cv >>= 1;
   return cv;
 }

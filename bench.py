@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="do not pin the rank to the CPU cores of its GPU's NUMA node")
+    ap.add_argument("--tuning", default="", help="chunk_vecs,ctas_per_sm,n_stages of K2 (0 = default), for sweeps")
     ap.add_argument("--per-kpt-launch", action="store_true",
                     help="launch K1..K3 once per SC k-point instead of once per step (batch)")
     return ap.parse_args()
@@ -237,6 +238,8 @@ def run_b200(args, sc, rank, world, local_rank):
     u = GpuUnfolder(local_rank)
     u.verify_commens(sc.b_pc, sc.B_sc)
     grid = u.set_energy_grid(*sc.energy_window())
+    if args.tuning:
+        u.set_tuning(*[int(x) for x in args.tuning.split(",")])
     nener = len(grid)
     kps = args.kpts_per_step
     nb, nsp = sc.n_bands, sc.n_spinor
