@@ -10,6 +10,7 @@ happens after the gather, on the host, unchanged.
 """
 from __future__ import annotations
 
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -108,12 +109,15 @@ class ShardedUnfoldJob:
 
     def __init__(self, unfolder, n_kpts: int, costs: Sequence[float], load_kpt: Callable,
                  rank: int = 0, world_size: int = 1, depth: int = 2,
-                 after_fetch: Optional[Callable] = None):
+                 after_fetch: Optional[Callable] = None, prefetch: bool = False):
         self.unfolder = unfolder
         self.load_kpt = load_kpt
         # after_fetch(iK, result, row_ids): called right after a k-point is fetched, while it is
         # still resident on the device (rho, Pauli vectors, spectral function can be asked for)
         self.after_fetch = after_fetch
+        # prefetch: load_kpt(iK+1) runs on a helper thread while iK is submitted / older k-points are
+        # fetched (load_kpt must then not touch the unfolder)
+        self.prefetch = prefetch
         self.rank, self.world_size = rank, world_size
         self.blocks = partition_kpts(costs, world_size)
         self.my_block = self.blocks[rank]
@@ -141,8 +145,15 @@ class ShardedUnfoldJob:
             if self.after_fetch is not None:
                 self.after_fetch(iK, res, rid)
 
+        pool = ThreadPoolExecutor(1) if self.prefetch and end - start > 1 else None
+        ahead = pool.submit(self.load_kpt, start) if pool else None
         for iK in range(start, end):
-            wf, folding_G, rid = self.load_kpt(iK)
+            if pool:
+                wf, folding_G, rid = ahead.result()
+                # iK+1 goes into the buffer of iK-3, fetched two iterations ago (depth 2)
+                ahead = pool.submit(self.load_kpt, iK + 1) if iK + 1 < end else None
+            else:
+                wf, folding_G, rid = self.load_kpt(iK)
             if len(inflight) >= self.depth:
                 drain_one()
             if callable(wf):      # the loader submits by itself (e.g. raw file records, device-made G list)
@@ -152,6 +163,8 @@ class ShardedUnfoldJob:
             inflight.append((iK, np.asarray(rid, dtype=np.int64)))
         while inflight:
             drain_one()
+        if pool:
+            pool.shutdown()
         nener = self.unfolder.nener
         dN = np.concatenate(rows, axis=0) if rows else np.zeros((0, nener))
         rid = np.concatenate(ids) if ids else np.zeros(0, dtype=np.int64)

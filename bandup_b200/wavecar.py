@@ -16,6 +16,8 @@ weights.  The reference's Fortran reader stays what BandUP itself uses (north_st
 """
 from __future__ import annotations
 
+import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from pathlib import Path
 from typing import List, Optional, Sequence, Tuple
@@ -25,6 +27,18 @@ import numpy as np
 from . import synth
 
 NPREC_COMPLEX64 = 45200
+READ_THREADS = int(os.environ.get("BANDUP_GPU_READ_THREADS", "8"))
+
+
+def _pread_full(fd: int, mv: memoryview, offset: int) -> int:
+    """preadv until `mv` is full (or EOF); returns the number of bytes read."""
+    done = 0
+    while done < len(mv):
+        k = os.preadv(fd, [mv[done:]], offset + done)
+        if k <= 0:
+            break
+        done += k
+    return done
 
 
 @dataclass
@@ -152,9 +166,23 @@ class Wavecar:
         if out.dtype != np.uint8 or out.size < n:
             raise ValueError("out must be a uint8 buffer of at least nbands*nrecl bytes")
         first = self.header_record(ikpt, ispin) + 1
-        with open(self.path, "rb", buffering=0) as f:
-            f.seek(first * self.nrecl)
-            got = f.readinto(memoryview(out[:n]))
+        base = first * self.nrecl
+        mv = memoryview(out[:n])
+        fd = os.open(self.path, os.O_RDONLY)
+        try:
+            # big blocks (GBs per k-point) are read by several threads: preadv releases the GIL, and
+            # one thread copying out of the page cache is far slower than the PCIe upload that follows
+            n_thr = min(READ_THREADS, max(1, n // (32 << 20)))
+            if n_thr <= 1:
+                got = _pread_full(fd, mv, base)
+            else:
+                step = -(-n // n_thr)
+                step += (-step) % 4096
+                parts = [(lo, min(lo + step, n)) for lo in range(0, n, step)]
+                with ThreadPoolExecutor(len(parts)) as ex:
+                    got = sum(ex.map(lambda p: _pread_full(fd, mv[p[0]:p[1]], base + p[0]), parts))
+        finally:
+            os.close(fd)
         if got != n:
             raise IOError(f"short read: {got} of {n} bytes")
         return out[:n]
@@ -168,11 +196,13 @@ class Wavecar:
         return np.ascontiguousarray(c.transpose(0, 2, 1))
 
     def submit_to(self, unfolder, job_ikpt: int, ikpt: int, folding_G: np.ndarray, ispin: int = 1,
-                  out: Optional[np.ndarray] = None):
+                  out: Optional[np.ndarray] = None, raw: Optional[np.ndarray] = None):
         """Header + raw records of file k-point `ikpt` (1-based) straight to the device
-        (GpuUnfolder.submit_vasp): no plane-wave enumeration, no de-interleave on the host."""
+        (GpuUnfolder.submit_vasp): no plane-wave enumeration, no de-interleave on the host.
+        `raw`: the records if they have been read already (read_band_records)."""
         h = self.kpt_header(ikpt, ispin)
-        raw = self.read_band_records(ikpt, ispin, out=out)
+        if raw is None:
+            raw = self.read_band_records(ikpt, ispin, out=out)
         return unfolder.submit_vasp(job_ikpt, raw, self.nrecl, h.nplane, self.nbands, h.kpt_frac_coords, self.encut,
                                     h.band_energies, folding_G=folding_G)
 
@@ -221,8 +251,9 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
     folds = fold_pckpts_onto_sckpts(pc_kpts_cart, sc_k, wavecar.B_matrix)
     used = [i for i in range(wavecar.nkpts) if folds[i]]       # SC-kpts no pc-kpt folds onto are skipped
     costs = [float(wavecar.nbands) * wavecar.kpt_header(i + 1, ispin).nplane for i in used]
-    # one buffer more than the pipeline depth: a buffer is refilled only after its k-point was fetched
-    bufs = [pinned_empty(wavecar.band_block_bytes()) for _ in range(3)]
+    # two buffers more than the pipeline depth: k-points j-1 and j-2 may be in flight and j+1 is being
+    # read ahead while j is submitted; a buffer is refilled only after its k-point was fetched
+    bufs = [pinned_empty(wavecar.band_block_bytes()) for _ in range(4)]
     K_cart = sc_k @ wavecar.B_matrix
 
     def load(j):
@@ -230,14 +261,17 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
         fG = np.asarray(pc_kpts_cart)[folds[i]] - K_cart[i]
         buf = bufs[j % len(bufs)]
         if device_gvecs:   # header + raw records only; the plane-wave list is made on the device
+            raw = wavecar.read_band_records(i + 1, ispin, out=buf)      # file -> page-locked memory, here
 
             def submit(u, job_ikpt, folding_G):
-                wavecar.submit_to(u, job_ikpt, i + 1, folding_G, ispin, out=buf)
+                wavecar.submit_to(u, job_ikpt, i + 1, folding_G, ispin, raw=raw)
             return submit, fG, np.asarray(folds[i])
         return wavecar.wavefunction(i + 1, ispin, out=buf), fG, np.asarray(folds[i])
 
+    # load() only touches the file and its own buffer, so the next k-point is parsed by a helper
+    # thread while this one uploads and computes (file parsing overlaps compute)
     job = ShardedUnfoldJob(unfolder, len(used), costs, load, rank=rank, world_size=world_size, depth=2,
-                           after_fetch=after_fetch)
+                           after_fetch=after_fetch, prefetch=True)
     try:
         got = job.run(device=device, group=group)
     finally:
