@@ -492,6 +492,31 @@ def pinned_empty(nbytes: int) -> np.ndarray:
     return arr
 
 
+_POOL = []     # idle page-locked buffers kept for reuse (cudaMallocHost costs ~1 s per GB)
+
+
+def pinned_pool_get(nbytes: int) -> np.ndarray:
+    """A page-locked buffer of at least nbytes from the reuse pool (allocated on a miss)."""
+    best = None
+    for i, a in enumerate(_POOL):
+        if a.size >= nbytes and (best is None or a.size < _POOL[best].size):
+            best = i
+    if best is not None:
+        return _POOL.pop(best)
+    return pinned_empty(nbytes)
+
+
+def pinned_pool_put(arr: np.ndarray) -> None:
+    """Hands a buffer back for reuse (no upload from it may be in flight)."""
+    _POOL.append(arr)
+
+
+def pinned_pool_release() -> None:
+    """Frees every idle buffer of the pool."""
+    while _POOL:
+        pinned_free(_POOL.pop())
+
+
 def pinned_free(arr: np.ndarray) -> None:
     """bandup_gpu_pinned_free for a buffer from pinned_empty (the array must not be used afterwards)."""
     base = _PINNED.pop(arr.ctypes.data, None)

@@ -27,7 +27,7 @@ import numpy as np
 from . import synth
 
 NPREC_COMPLEX64 = 45200
-READ_THREADS = int(os.environ.get("BANDUP_GPU_READ_THREADS", "8"))
+READ_THREADS = int(os.environ.get("BANDUP_GPU_READ_THREADS", str(min(16, os.cpu_count() or 8))))
 
 
 def _pread_full(fd: int, mv: memoryview, offset: int) -> int:
@@ -244,7 +244,7 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
     previous k-point computes.  Returns sharding.GatheredDeltaN (rows in pc-kpt order) and the
     energy grid."""
     from .sharding import ShardedUnfoldJob
-    from .unfold import pinned_empty, pinned_free
+    from .unfold import pinned_pool_get, pinned_pool_put
     unfolder.verify_commens(rec_latt_pc, wavecar.B_matrix)
     grid = unfolder.set_energy_grid(E_start, E_end, delta_e)
     sc_k = np.array([wavecar.kpt_header(i + 1, ispin).kpt_frac_coords for i in range(wavecar.nkpts)])
@@ -253,7 +253,8 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
     costs = [float(wavecar.nbands) * wavecar.kpt_header(i + 1, ispin).nplane for i in used]
     # two buffers more than the pipeline depth: k-points j-1 and j-2 may be in flight and j+1 is being
     # read ahead while j is submitted; a buffer is refilled only after its k-point was fetched
-    bufs = [pinned_empty(wavecar.band_block_bytes()) for _ in range(4)]
+    # (taken from / returned to a reuse pool: page-locking memory costs about a second per GB)
+    bufs = [pinned_pool_get(wavecar.band_block_bytes()) for _ in range(min(4, max(1, len(used))))]
     K_cart = sc_k @ wavecar.B_matrix
 
     def load(j):
@@ -276,7 +277,7 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
         got = job.run(device=device, group=group)
     finally:
         for b in bufs:     # every k-point has been fetched (or the job failed): no upload is in flight
-            pinned_free(b)
+            pinned_pool_put(b)
     got.sckpt_of_row = {int(r): used[j] for j in range(len(used)) for r in folds[used[j]]}
     got.sckpts_cart = K_cart
     return got, grid
