@@ -102,7 +102,8 @@ struct Flight {  // one SC k-point in flight
 struct Ctx {
   int device = 0;
   int sm_count = 148;
-  cudaStream_t copy = nullptr, compute = nullptr;
+  cudaStream_t copy = nullptr, compute = nullptr, aux = nullptr;  // aux: device plane-wave lists
+  cudaEvent_t aux_done = nullptr;
   bool cells_set = false, grid_set = false;
   double B_sc[9] = {0}, B_inv[9] = {0};  // row-major, row = vector
   int32_t M[9] = {0};                    // row-major int_M
@@ -526,7 +527,9 @@ int bandup_gpu_init(int device, int* handle) {
   c->sm_count = prop.multiProcessorCount;
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->aux_done, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
     return fail(nullptr, BANDUP_GPU_ERR_CUDA, "stream creation failed");
   }
@@ -570,6 +573,8 @@ int bandup_gpu_finalize(int handle) {
   }
   if (c->copy) cudaStreamDestroy(c->copy);
   if (c->compute) cudaStreamDestroy(c->compute);
+  if (c->aux) cudaStreamDestroy(c->aux);
+  if (c->aux_done) cudaEventDestroy(c->aux_done);
   delete c;
   g_ctx[handle] = nullptr;
   return BANDUP_GPU_OK;
@@ -899,7 +904,9 @@ int bandup_gpu_submit_kpt_vasp(int handle, int ikpt, int nplane, int n_bands, in
   rq.c_const = two_m_over_hbar_sqrd;
   cudaSetDevice(c->device);
   int n_spinor = 1, n_pw = 0;
-  int rc = resolve_gvecs(c, c->compute, &rq, nplane, &n_spinor, &n_pw);
+  // on its own stream: the count's host synchronisation must not wait for the previous k-point's
+  // upload and kernels
+  int rc = resolve_gvecs(c, c->aux, &rq, nplane, &n_spinor, &n_pw);
   if (rc) return rc;
   if (n_spinor_out) *n_spinor_out = n_spinor;
   if (n_pw_out) *n_pw_out = n_pw;
@@ -977,8 +984,10 @@ int submit_impl(int handle, int ikpt, int n_spinor, int n_pw, int n_bands, int l
   CU(cudaMemcpyAsync(fl.energies.p, band_energies, sizeof(double) * (size_t)n_bands, cudaMemcpyHostToDevice, c->copy));
   CU(cudaEventRecord(fl.uploaded, c->copy));
   if (gen) {  // while the coefficient block is on its way: the plane-wave list, made on the device
-    rc = write_gvecs(c, c->compute, *gen, n_pw, static_cast<int32_t*>(fl.gfrac.p));
+    rc = write_gvecs(c, c->aux, *gen, n_pw, static_cast<int32_t*>(fl.gfrac.p));
     if (rc) return rc;
+    CU(cudaEventRecord(c->aux_done, c->aux));
+    CU(cudaStreamWaitEvent(c->compute, c->aux_done, 0));
   }
   CU(cudaStreamWaitEvent(c->compute, fl.uploaded, 0));
 

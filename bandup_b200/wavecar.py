@@ -30,6 +30,16 @@ NPREC_COMPLEX64 = 45200
 READ_THREADS = int(os.environ.get("BANDUP_GPU_READ_THREADS", str(min(16, os.cpu_count() or 8))))
 
 
+_POOL_EX = None
+
+
+def _read_pool() -> ThreadPoolExecutor:
+    global _POOL_EX
+    if _POOL_EX is None:
+        _POOL_EX = ThreadPoolExecutor(READ_THREADS, thread_name_prefix="wavecar-read")
+    return _POOL_EX
+
+
 def _pread_full(fd: int, mv: memoryview, offset: int) -> int:
     """preadv until `mv` is full (or EOF); returns the number of bytes read."""
     done = 0
@@ -114,6 +124,7 @@ class Wavecar:
         self.A_matrix = rec2[3:12].reshape(3, 3).copy()
         self.B_matrix = synth.rec_latt(self.A_matrix)
         self._gcache = {}
+        self._hcache = {}
 
     def header_record(self, ikpt: int, ispin: int = 1) -> int:
         """0-based record index of the k-point header (ikpt, ispin 1-based) (:409-414)."""
@@ -122,11 +133,14 @@ class Wavecar:
         return 2 + (ispin - 1) * self.nkpts * (1 + self.nbands) + (ikpt - 1) * (1 + self.nbands)
 
     def kpt_header(self, ikpt: int, ispin: int = 1) -> KptHeader:
-        rec = self.header_record(ikpt, ispin)
-        with open(self.path, "rb") as f:
-            f.seek(rec * self.nrecl)
-            h = np.frombuffer(f.read(8 * (4 + 3 * self.nbands)), dtype="<f8")
-        return KptHeader(int(round(h[0])), h[1:4].copy(), h[4::3].copy(), h[6::3].copy(), rec + 1)
+        key = (ikpt, ispin)
+        if key not in self._hcache:
+            rec = self.header_record(ikpt, ispin)
+            with open(self.path, "rb") as f:
+                f.seek(rec * self.nrecl)
+                h = np.frombuffer(f.read(8 * (4 + 3 * self.nbands)), dtype="<f8")
+            self._hcache[key] = KptHeader(int(round(h[0])), h[1:4].copy(), h[4::3].copy(), h[6::3].copy(), rec + 1)
+        return self._hcache[key]
 
     def gvecs(self, ikpt: int, ispin: int = 1) -> Tuple[np.ndarray, int]:
         """(G_frac int32 (n_G, 3), n_spinor): the reader's regeneration incl. its adaptive tweak of
@@ -179,8 +193,7 @@ class Wavecar:
                 step = -(-n // n_thr)
                 step += (-step) % 4096
                 parts = [(lo, min(lo + step, n)) for lo in range(0, n, step)]
-                with ThreadPoolExecutor(len(parts)) as ex:
-                    got = sum(ex.map(lambda p: _pread_full(fd, mv[p[0]:p[1]], base + p[0]), parts))
+                got = sum(_read_pool().map(lambda p: _pread_full(fd, mv[p[0]:p[1]], base + p[0]), parts))
         finally:
             os.close(fd)
         if got != n:
