@@ -186,7 +186,7 @@ class Wavecar:
         try:
             # big blocks (GBs per k-point) are read by several threads: preadv releases the GIL, and
             # one thread copying out of the page cache is far slower than the PCIe upload that follows
-            n_thr = min(READ_THREADS, max(1, n // (32 << 20)))
+            n_thr = min(READ_THREADS, max(1, n // (4 << 20)))
             if n_thr <= 1:
                 got = _pread_full(fd, mv, base)
             else:
