@@ -672,3 +672,66 @@ def test_random_cells_and_shapes(unfolder):
         assert rel_err(res.spectral_weight, w) <= REL_TOL, done
         assert rel_err(res.dN, dN) <= REL_TOL, done
         done += 1
+
+
+def test_full_size_si333_host_path(unfolder):
+    """BASELINE config 2 at full size (500 bands x ~20k plane waves, det M = 108) through the host
+    C ABI, every band against the oracle."""
+    from bandup_b200.unfold import PwWavefunction
+    sc = synth.make_scenario("si333_vacancy")
+    grid = setup(unfolder, sc)
+    iK = 7
+    coeffs, gf, ener = synth.make_wavefunction(sc, iK)
+    assert coeffs.shape[0] == 500 and 18_000 < gf.shape[0] < 22_000
+    fG = sc.folding_G(iK)
+    res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), folding_G=fG)
+    w, dN, ns, sels = oracle_kpt(sc, coeffs, gf, ener, fG, grid)
+    assert np.array_equal(res.n_selected, ns)
+    for a, b in zip(res.selected_coeff_indices, sels):
+        assert np.array_equal(a, b)
+    assert rel_err(res.spectral_weight, w) <= REL_TOL and rel_err(res.dN, dN) <= REL_TOL
+
+
+def test_device_resident_full_size_mos2_spinor(unfolder):
+    """BASELINE config 3 at full size (1200 bands x ~79k plane waves x 2 spinor components, 1.5 GB,
+    [pw][spinor] interleaved): sampled bands against the oracle, invariants on all."""
+    import torch
+    from bandup_b200.unfold import LAYOUT_FORTRAN_INMEM
+    from oracle import oracle as O
+    sc = synth.make_scenario("mos2_8x8_spinor")
+    grid = setup(unfolder, sc)
+    iK = 2
+    gf = sc.gvecs(iK)
+    n_pw, nb = gf.shape[0], sc.n_bands
+    assert nb == 1200 and 70_000 < n_pw < 90_000
+    g0, _ = unfolder.folding_g0(sc.folding_G(iK))
+    nf = g0.shape[0]
+    ener = np.sort(np.random.default_rng(5).uniform(-21.0, 6.0, nb))
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    row = 2 * n_pw
+    d_c = torch.empty((nb, row, 2), dtype=torch.float32, device=dev)
+    unfolder.synth_fill_device(stream, d_c.data_ptr(), row, nb, row * 8, 777, iK)
+    d_g, d_e = torch.from_numpy(gf).to(dev), torch.from_numpy(ener).to(dev)
+    d_w = torch.empty((nf, nb), dtype=torch.float64, device=dev)
+    d_dn = torch.empty((nf, len(grid)), dtype=torch.float64, device=dev)
+    d_ns = torch.empty(nf, dtype=torch.int32, device=dev)
+    d_norm = torch.empty(nb, dtype=torch.float64, device=dev)
+    ws = unfolder.workspace_bytes(2, n_pw, nb, nf)
+    d_ws = torch.empty(ws, dtype=torch.uint8, device=dev)
+    unfolder.unfold_device(stream, 2, n_pw, nb, LAYOUT_FORTRAN_INMEM, row * 8, d_c.data_ptr(), d_g.data_ptr(),
+                           d_e.data_ptr(), g0, d_w.data_ptr(), d_dn.data_ptr(), d_ns.data_ptr(), d_ws.data_ptr(), ws,
+                           d_norms=d_norm.data_ptr())
+    torch.cuda.synchronize()
+    w, dN, ns, norms = d_w.cpu().numpy(), d_dn.cpu().numpy(), d_ns.cpu().numpy(), d_norm.cpu().numpy()
+    gc = gf @ sc.B_sc
+    fG = g0.astype(np.float64) @ sc.B_sc
+    for b in (0, 599, 1199):
+        rowdata = O.synth_fill(row, 1, 777, iK, band0=b).reshape(1, n_pw, 2)     # [pw][spinor] interleaved
+        wo, _, nso, _ = O.unfold_kpt(rowdata, gc, ener[b:b + 1], sc.b_pc, fG, grid, norm_mode=1)
+        assert np.array_equal(ns, nso)
+        assert rel_err(w[:, b], wo[:, 0]) <= REL_TOL
+        _, n_o = O.renormalize(rowdata, 1)
+        assert rel_err(norms[b:b + 1], n_o) <= REL_TOL
+    assert np.all(w >= 0.0) and np.all(w.sum(axis=0) <= 1.0 + 1e-7)
+    assert rel_err(dN[0], O.delta_N(grid, ener, w[0])) <= REL_TOL
