@@ -323,3 +323,55 @@ def test_file_level_spinor_and_projected_outputs(unfolder, tmp_path):
                 assert abs(tab_orb[row * len(grid) + ie1 - 1, 2] - want) <= 2e-4 + 1e-3 * abs(want)
                 checked += 1
     assert checked > 10
+
+
+def test_projected_unfold_full_size_config4(unfolder):
+    """BASELINE config 4 at full size: Si 3x3x3 vacancy cell (215 atoms x 9 orbitals = 1935 atomic
+    orbitals, 500 bands, ~20k plane waves).  rho against the C oracle (the reference's own
+    single-precision accumulation, so loosely), the orbital-contribution matrix and N Re Tr(rho O)
+    against the NumPy chain pinned by the golden vectors."""
+    from bandup_b200.unfold import PwWavefunction
+    from oracle import oracle as O
+    from oracle import oracle_np as ON
+    sc = synth.make_scenario("si333_vacancy")
+    grid = _setup(unfolder, sc)
+    iK = 11
+    coeffs, gf, ener = synth.make_wavefunction(sc, iK)
+    nb = coeffs.shape[0]
+    assert nb == 500
+    fG = sc.folding_G(iK)
+    out = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), folding_G=fG, ikpt=3)
+    res = unfolder.calc_rho(3)
+    assert res.n_energies > 50
+    gc = gf @ sc.B_sc
+    c_ren, _ = O.renormalize(coeffs, 1)
+    de = grid[1] - grid[0]
+    sel, _ = O.select_coeffs(gc, fG[0], sc.b_pc)
+    ies = res.energies_of(0)
+    for ie in ies[:: max(1, len(ies) // 12)]:               # a dozen energies spread over the window
+        rho32 = O.calc_rho(c_ren, sel, ener, out.dN[0, ie - 1], grid[ie - 1], de)
+        dense = res.dense(0, int(ie), nb)
+        big = np.abs(rho32) >= 2e-5
+        scale = max(np.abs(rho32).max(), 1e-30)
+        assert np.all(np.abs(dense[big] - rho32[big]) <= 5e-5 * scale)
+        assert not dense[np.abs(rho32) < 0.5e-5].any()
+    rng = np.random.default_rng(12)
+    n_at, n_orb = 215, 9
+    proj = (rng.standard_normal((n_at * n_orb, nb)) + 1j * rng.standard_normal((n_at * n_orb, nb))) * \
+        np.repeat(rng.uniform(0.02, 0.2, n_at), n_orb)[:, None]
+    dual = np.linalg.pinv(proj)
+    mask = np.zeros(n_at * n_orb, np.uint8)
+    mask.reshape(n_at, n_orb)[:108, 1:4] = 1                 # p orbitals of half of the atoms
+    Omat = unfolder.get_orbital_contribution_matrix(dual, proj, mask, ener)
+    O_ref = ON.orb_contrib_matrix(dual, proj, mask, ener)
+    assert np.array_equal(Omat != 0, O_ref != 0) and np.allclose(Omat, O_ref, rtol=1e-11, atol=1e-14)
+    vals = unfolder.unfold_operator(3, fG.shape[0], min_abs_rho=1e-4, clip=True)
+    checked = 0
+    for ie in ies:
+        s = (res.fold == 0) & (res.iener == ie) & (res.m1 <= res.m2)
+        N = out.dN[0, ie - 1]
+        want = ON.unfold_rho_operator(list(res.m1[s] - 1), list(res.m2[s] - 1), list(res.rho[s]), Omat, N,
+                                      min_abs_rho=1e-4, clip=True)
+        assert abs(vals[0, ie - 1] - want) <= 1e-9 * max(1.0, abs(want))
+        checked += 1
+    assert checked == len(ies)
