@@ -735,3 +735,22 @@ def test_device_resident_full_size_mos2_spinor(unfolder):
         assert rel_err(norms[b:b + 1], n_o) <= REL_TOL
     assert np.all(w >= 0.0) and np.all(w.sum(axis=0) <= 1.0 + 1e-7)
     assert rel_err(dN[0], O.delta_N(grid, ener, w[0])) <= REL_TOL
+
+
+def test_full_job_config1_graphene(unfolder, tmp_path):
+    """BASELINE config 1 as a whole job: graphene 4x4, ENCUT 400 eV, 64 bands, every SC-kpt of the
+    K-Gamma-M-K path from a synthetic WAVECAR (the reader's record format), all rows vs the oracle."""
+    from bandup_b200.wavecar import Wavecar, unfold_wavecar, write_wavecar
+    from oracle import oracle as O
+    sc = synth.make_scenario("graphene4x4")
+    assert sc.n_bands == 64 and sc.ecut == 400.0
+    data = [synth.make_wavefunction(sc, iK) for iK in range(sc.n_sc_kpts)]
+    assert 22_000 < data[0][1].shape[0] < 24_000
+    write_wavecar(tmp_path / "WAVECAR", sc.A_sc, sc.ecut, list(sc.sc_kpts_frac), [d[0] for d in data],
+                  [d[2] for d in data])
+    got, grid = unfold_wavecar(unfolder, Wavecar(tmp_path / "WAVECAR"), sc.b_pc, sc.pc_kpts_cart, *sc.energy_window())
+    assert got.row_ids.tolist() == list(range(sc.pc_kpts_cart.shape[0]))
+    for iK in range(sc.n_sc_kpts):
+        coeffs, gf, ener = data[iK]
+        _, dN, _, _ = O.unfold_kpt(coeffs, gf @ sc.B_sc, ener, sc.b_pc, sc.folding_G(iK), grid, norm_mode=1)
+        assert rel_err(got.dN[np.asarray(sc.folds[iK])], dN) <= REL_TOL
