@@ -65,3 +65,22 @@ def test_fold_map_matches_scenario():
     assert folds == sc.folds
     with pytest.raises(ValueError):
         fold_pckpts_onto_sckpts(sc.pc_kpts_cart, sc.sc_kpts_frac[:1], sc.B_sc)
+
+
+def test_second_spin_channel_record_indexing(tmp_path):
+    """nspin = 2: the records of spin 2 follow all k-points of spin 1 (read_wavecar_mod.f90:409-414)."""
+    sc = synth.make_scenario("graphene4x4", scale=0.06, n_kpts=6)
+    ks = [0, 1]
+    data = [synth.make_wavefunction(sc, iK) for iK in ks]
+    path = tmp_path / "WAVECAR"
+    nrecl = write_wavecar(path, sc.A_sc, sc.ecut, [sc.sc_kpts_frac[i] for i in ks], [d[0] for d in data],
+                          [d[2] for d in data], nspin=2)
+    wc = Wavecar(path)
+    assert wc.nspin == 2 and path.stat().st_size == nrecl * (2 + 2 * 2 * (1 + sc.n_bands))
+    assert wc.header_record(1, 2) == 2 + 2 * (1 + sc.n_bands)
+    for ispin in (1, 2):
+        for i in range(2):
+            assert np.array_equal(wc.coefficients(i + 1, ispin), data[i][0])
+            assert np.array_equal(wc.kpt_header(i + 1, ispin).band_energies, data[i][2])
+    with pytest.raises(IndexError):
+        wc.header_record(1, 3)
