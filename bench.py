@@ -83,59 +83,95 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons of one GPU, sampled every 200 ms while running."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons of one GPU while the timed regions run.  NVML is polled
+    in-process every ~2 ms (the device-timed region of the default run lasts only ~15 ms, far
+    below nvidia-smi's 200 ms period); nvidia-smi is the fallback when pynvml is missing."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
         self.index = index
+        self.samples = []          # (t, sm_mhz, power_w, reasons bitmask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.thread = None
+        self.source = None
         self.proc = None
-        self.lines = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append((time.perf_counter(),
+                                             float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons_fn(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
+            self.source = "nvml, 2 ms period"
+        except Exception:
+            self._start_smi()
+
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms",
+                                          "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+
+            def pump():
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for line in self.proc.stdout:
+                    f = [x.strip() for x in line.split(",")]
+                    try:
+                        mask = sum(self.REASONS[n] for n, v in zip(names, f[3:7]) if v.lower().startswith("active"))
+                        self.samples.append((time.perf_counter(), float(f[0]), float(f[2]), mask))
+                        self.max_mhz = float(f[1])
+                    except (ValueError, IndexError):
+                        continue
+            self.thread = threading.Thread(target=pump, daemon=True)
+            self.thread.start()
+            self.source = "nvidia-smi, 200 ms period"
         except Exception:
             self.proc = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+        if self.thread:
+            self.thread.join(timeout=2)
 
-    def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        # "under load": samples whose power is above half of the maximum seen
-        if sm:
-            thr = 0.5 * max(pw)
-            load = [s for s, p in zip(sm, pw) if p >= thr] or sm
-            return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "power_w_max": max(pw),
-                    "samples": len(sm), "reasons": sorted(reasons)}
-        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+    def summary(self, t0: float, t1: float) -> dict:
+        """Median SM clock and the throttle reasons seen between t0 and t1 (perf_counter times)."""
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        note = None
+        if not inside:     # region shorter than the sampling period: the nearest samples on either side
+            inside = sorted(self.samples, key=lambda x: min(abs(x[0] - t0), abs(x[0] - t1)))[:2]
+            note = "region shorter than the sampling period; nearest samples used"
+        mask = 0
+        for x in inside:
+            mask |= x[3]
+        out = {"sm_mhz": float(np.median([x[1] for x in inside])), "sm_max_mhz": self.max_mhz,
+               "power_w_max": max(x[2] for x in inside), "samples": len(inside),
+               "reasons": sorted(n for n, bit in self.REASONS.items() if mask & bit), "source": self.source}
+        if note:
+            out["note"] = note
+        return out
 
 
 def make_energies(sc, rng):
@@ -317,11 +353,13 @@ def run_b200(args, sc, rank, world, local_rank):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_dev0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    t_dev1 = time.perf_counter()
     ms = max_over_ranks(e0.elapsed_time(e1))
     gpu_launches = u.launch_count() - launches0
     k2_ms, k2_n = u.kernel_time(K_WEIGHTS)
@@ -359,6 +397,7 @@ def run_b200(args, sc, rank, world, local_rank):
 
     # ---- end to end through the host C ABI ----------------------------------------
     e2e = None
+    t_e2e = (0.0, 0.0)
     if not args.no_e2e:
         n_e2e = args.e2e_steps or min(args.steps, 4)
         host = []
@@ -390,13 +429,19 @@ def run_b200(args, sc, rank, world, local_rank):
         for s in range(n_e2e):
             e2e_step(1000 * (s + 1))
         torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
+        t_e2e = (t0, time.perf_counter())
+        dt = max_over_ranks(t_e2e[1] - t0)
         e2e_bytes = sum(nb * host[i][1]["n_pw"] * nsp * 8 for i in seq) * n_e2e * world
         e2e = {"value": e2e_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "sc_kpts_per_s": kps * n_e2e * world / dt, "steps": n_e2e,
                "timer": "host monotonic clock between device synchronisations, max over ranks",
                "bound": "PCIe host->device copy of the coefficient blocks", "numa": numa}
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.summary(t_dev0, t_dev1)          # the device-timed region (`value`, `roofline`)
+        if e2e is not None:
+            e2e["clocks"] = sampler.summary(*t_e2e)
 
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------
     cpu = None
