@@ -120,8 +120,8 @@ int bandup_gpu_folding_g0(int handle, const double *folding_G, int n_fold,
  *   spectral_weight_for_coeff + spinor sum      (:615-651, :1335-1345)
  *   get_delta_Ns_for_EBS                        (:760-786, :719-757)
  * Asynchronous: enqueues upload + kernels and returns; up to
- * bandup_gpu_pipeline_depth() k-points may be in flight (double buffering), a
- * further submit first waits for the oldest to be fetched.
+ * bandup_gpu_pipeline_depth() k-points may be in flight (double buffering); a
+ * further submit is refused with ERR_INVALID_ARG until one of them has been fetched.
  *   coeffs         host pointer (pinned or pageable), layout as `layout`;
  *                  NOT renormalised by the caller (renormalised input is also
  *                  fine: the division by the band norm is then a no-op)
@@ -192,9 +192,11 @@ int bandup_gpu_spectral_function(int handle, int ikpt, double std_dev, double *s
  * and the calc_rho loop of perform_unfolding (band_unfolding_routines_mod.f90:1372-1428,
  * calc_rho :1046-1161): for every energy with dN >= min_dN (reference: 1e-3) the operator
  *   rho(m1,m2) = lambda(m1) lambda(m2) / dN * sum_spinor sum_{G in sel} conj(C_m1) C_m2
- * between the bands with lambda >= 1e-5 (m1 = 1..n_bands-1 only, prefactor >= 1e-5).
+ * between the bands with lambda >= 1e-5 (m1 = 1..n_bands-1 only, prefactor >= 1e-5); lambda is
+ * the box (sigma = epsilon) whatever smearing the grid was given, because perform_unfolding
+ * calls calc_rho without std_dev (:1404-1407).
  * It blocks until done and returns
- *   n_energies  number of (pc-kpt, energy) operators      == sum of size(rhos)
+ *   n_energies  number of (pc-kpt, energy) operators with at least one coupled band pair
  *   n_entries   number of stored elements, |rho| >= 1e-5, both triangles (:1416-1425)
  * min_dN < epsilon(1.0_dp) is refused with ERR_DELTA_N_ZERO (calc_rho's fatal branch). */
 int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t *n_energies,
