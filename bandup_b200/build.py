@@ -18,6 +18,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libbandup_gpu.so"
+HOST_SRC = PKG / "host" / "bandup_unfold_gpu.cpp"
+HOST_EXE = LIBDIR / "BandUP_gpu.x"   # the native (C++) host above the C ABI: `bandup unfold` without symmetry
 SOURCES = ["capi.cu", "coset_classify.cu", "weights_reduce.cu", "delta_n.cu", "rho.cu", "gvecs.cu", "comm.cu", "synth.cu"]
 HEADERS = [CSRC / "kernels.cuh", CSRC / "nccl_dyn.h", PKG.parent / "include" / "bandup_gpu.h"]
 
@@ -39,7 +41,7 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for p in [CSRC / s for s in SOURCES] + HEADERS:
+    for p in [CSRC / s for s in SOURCES] + HEADERS + [HOST_SRC]:
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -49,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
     stamp = LIBDIR / "libbandup_gpu.digest"
     digest = _digest()
-    if LIB.exists() and stamp.exists() and stamp.read_text() == digest and not force:
+    if LIB.exists() and HOST_EXE.exists() and stamp.exists() and stamp.read_text() == digest and not force:
         return LIB
     env = dict(os.environ)
     env.pop("CC", None)   # this image exports CC/CXX pointing at a gcc without libgomp specs
@@ -63,6 +65,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libbandup_gpu.so (see bandup_b200/lib/build.log)")
+    host = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", str(PKG.parent / "include"),
+            str(HOST_SRC), "-L", str(LIBDIR), "-lbandup_gpu", "-Wl,-rpath,$ORIGIN", "-o", str(HOST_EXE)]
+    res = subprocess.run(host, capture_output=True, text=True, env=env)
+    with open(LIBDIR / "build.log", "a") as f:
+        f.write(" ".join(host) + "\n" + res.stdout + res.stderr)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed building BandUP_gpu.x (see bandup_b200/lib/build.log)")
     stamp.write_text(digest)
     return LIB
 

@@ -1,0 +1,82 @@
+"""BandUP_gpu.x -- the C++ host above the C ABI (bandup_b200/host/bandup_unfold_gpu.cpp): the
+reference's `bandup unfold` flow for -no_symm_sckpts -no_symm_avg with the reference's own
+command-line flags and files, no Python in the process."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from bandup_b200 import bandup_files as BF
+from bandup_b200 import synth
+
+ROOT = Path(__file__).resolve().parent.parent
+EXE = ROOT / "bandup_b200" / "lib" / "BandUP_gpu.x"
+
+
+def _job(tmp_path, spinor):
+    from bandup_b200.wavecar import write_wavecar
+    a = synth.hex_cell(3.16, 18.0) if spinor else synth.hex_cell(2.467, 15.0)
+    b = synth.rec_latt(a)
+    segs = [([1 / 3, 1 / 3, 0.0], [0.0, 0.0, 0.0]), ([0.0, 0.0, 0.0], [0.5, 0.0, 0.0])]
+    counts = [5, 4]
+    kcart = np.concatenate([BF.kpts_line(np.array(s) @ b, np.array(e) @ b, n) for (s, e), n in zip(segs, counts)])
+    sc = synth.Scenario("job", a, np.diag([4, 4, 1]), 28.0, 7, 2 if spinor else 1, kcart, e_fermi=-1.25,
+                        emin=-12.0, emax=6.0, dE=0.1)
+    data = [synth.make_wavefunction(sc, iK) for iK in range(sc.n_sc_kpts)]
+    for d in data:
+        d[2][2] = d[2][1]
+    BF.write_lattice(tmp_path / "prim_cell_lattice.in", a, "pc")
+    BF.write_lattice(tmp_path / "supercell_lattice.in", sc.A_sc, "SC")
+    BF.write_pckpts(tmp_path / "KPOINTS_prim_cell.in", segs, counts)
+    BF.write_energy_info(tmp_path / "energy_info.in", sc.e_fermi, sc.emin, sc.emax, sc.dE)
+    write_wavecar(tmp_path / "WAVECAR", sc.A_sc, sc.ecut, list(sc.sc_kpts_frac), [d[0] for d in data],
+                  [d[2] for d in data], extra_pad=1)
+    return sc, data, counts
+
+
+def test_host_exe_is_built_and_has_no_cpu_fallback(gpu_lib, tmp_path):
+    import torch
+    assert EXE.exists()
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    _job(tmp_path, False)
+    r = subprocess.run([str(EXE), "-no_symm_sckpts", "-no_symm_avg"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr and "Stopping now." in r.stderr
+    r = subprocess.run([str(EXE), "-bogus"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "unknown command-line option" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spinor", [False, True])
+def test_host_exe_reproduces_the_python_path_and_the_oracle(gpu_lib, unfolder, tmp_path, spinor):
+    from oracle import oracle as O
+    sc, data, counts = _job(tmp_path, spinor)
+    r = subprocess.run([str(EXE), "-no_symm_sckpts", "-no_symm_avg", "-write_unf_dens_op", "-wf_file", "WAVECAR",
+                        "-out_file_nosymm", "exe_EBS.dat", "-output_file_only_user_selec_direcs_unf_dens_op", "exe_udo.dat"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "pc-kpts unfolded" in r.stdout
+    # the same job through the Python mirror
+    kpath, grid, dN = BF.unfold_task(unfolder, tmp_path / "WAVECAR", tmp_path / "prim_cell_lattice.in",
+                                     tmp_path / "supercell_lattice.in", tmp_path / "KPOINTS_prim_cell.in",
+                                     tmp_path / "energy_info.in", out_file=str(tmp_path / "py_EBS.dat"),
+                                     unf_dens_op_file=str(tmp_path / "py_udo.dat"))
+    exe_tab, py_tab = BF.read_band_struc(tmp_path / "exe_EBS.dat"), BF.read_band_struc(tmp_path / "py_EBS.dat")
+    assert exe_tab.shape == py_tab.shape == (sum(counts) * len(grid), 8 if spinor else 3)
+    assert np.array_equal(exe_tab, py_tab)                     # same library, same numbers, same format
+    body = lambda p: [ln for ln in Path(p).read_text().splitlines() if not ln.startswith("# File created")]
+    assert body(tmp_path / "exe_EBS.dat")[1:] == body(tmp_path / "py_EBS.dat")[1:]
+    _, exe_recs = BF.read_unf_dens_op(tmp_path / "exe_udo.dat")
+    _, py_recs = BF.read_unf_dens_op(tmp_path / "py_udo.dat")
+    assert len(exe_recs) == len(py_recs) > 3
+    for x, y in zip(exe_recs, py_recs):
+        assert (x.pckpt_number, x.iener, x.folding_sckpt_number) == (y.pckpt_number, y.iener, y.folding_sckpt_number)
+        assert np.array_equal(x.rows, y.rows) and np.array_equal(x.cols, y.cols) and np.array_equal(x.entries, y.entries)
+    # and against the oracle (to the file's 4 digits)
+    for iK in range(sc.n_sc_kpts):
+        coeffs, gf, ener = data[iK]
+        _, d, _, _ = O.unfold_kpt(coeffs, gf @ sc.B_sc, ener, sc.b_pc, sc.folding_G(iK), grid, norm_mode=1)
+        for f, row in enumerate(sc.folds[iK]):
+            got = exe_tab[row * len(grid):(row + 1) * len(grid), 2]
+            assert np.allclose(got, d[f], rtol=6e-4, atol=1e-12)
