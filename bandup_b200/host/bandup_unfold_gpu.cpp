@@ -24,6 +24,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <future>
@@ -317,7 +318,8 @@ Args parse_args(int argc, char** argv) {
   const std::vector<std::string> with_value = {"-wf_file", "-pc_file", "-sc_file", "-pckpts_file", "-energy_file",
       "-out_file_nosymm", "-out_file_symm", "-output_file_only_user_selec_direcs_unf_dens_op",
       "-output_file_symm_averaged_unf_dens_op", "-spin_channel", "-n_sckpts_to_skip", "-normal_to_proj_plane",
-      "-origin_for_spin_proj_cart", "-device", "-read_threads", "-outdir", "-saxis"};
+      "-origin_for_spin_proj_cart", "-device", "-read_threads", "-outdir", "-saxis", "-n_ranks", "-rank",
+      "-nccl_id_file"};
   const std::vector<std::string> switches = {"-write_unf_dens_op", "-no_symm_sckpts", "-no_symm_avg", "-dont_unfold",
       "-continue_if_not_commensurate", "--continue_if_npw_smaller_than_expected", "-skip_propose_pc_for_given_pc",
       "-skip_propose_pc_for_given_sc"};
@@ -360,8 +362,35 @@ int main(int argc, char** argv) {
   if (!args.has("-no_symm_sckpts") || !args.has("-no_symm_avg"))
     std::printf("NOTICE: BandUP_gpu.x works without symmetry (as if -no_symm_sckpts -no_symm_avg had been given).\n");
 
+  // one process per GPU: rank r of n_ranks unfolds a contiguous block of the SC-kpts and the
+  // delta_N rows are gathered with NCCL (the 128-byte id travels through -nccl_id_file)
+  const int n_ranks = std::atoi(args.get("-n_ranks", "1").c_str());
+  const int rank = std::atoi(args.get("-rank", "0").c_str());
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) die("ERROR: bad -rank / -n_ranks");
+  if (n_ranks > 1 && (write_udo))
+    die("ERROR: -write_unf_dens_op is supported by BandUP_gpu.x with one rank only.");
+
   int h = -1;
-  gpu_check(-1, bandup_gpu_init(std::atoi(args.get("-device", "0").c_str()), &h), "bandup_gpu_init");
+  gpu_check(-1, bandup_gpu_init(std::atoi(args.get("-device", std::to_string(rank)).c_str()), &h), "bandup_gpu_init");
+  if (n_ranks > 1) {
+    const std::string idf = args.get("-nccl_id_file", "bandup_gpu_nccl_id");
+    char id[BANDUP_GPU_COMM_ID_BYTES];
+    if (rank == 0) {
+      gpu_check(h, bandup_gpu_comm_unique_id(id), "comm_unique_id");
+      std::ofstream o(idf + ".tmp", std::ios::binary);
+      o.write(id, sizeof id);
+      o.close();
+      std::rename((idf + ".tmp").c_str(), idf.c_str());
+    } else {
+      for (int tries = 0;; ++tries) {
+        std::ifstream in(idf, std::ios::binary);
+        if (in && in.read(id, sizeof id)) break;
+        if (tries > 1200) die("ERROR: no NCCL id from rank 0 in " + idf);
+        std::this_thread::sleep_for(std::chrono::milliseconds(50));
+      }
+    }
+    gpu_check(h, bandup_gpu_comm_init(h, n_ranks, rank, id), "comm_init");
+  }
 
   // cells and commensurability (main_BandUP.f90:57-82)
   Wavecar wc;
@@ -431,9 +460,22 @@ int main(int argc, char** argv) {
     if (sck_of[ik] < 0)  // main_BandUP.f90:114
       die("ERROR: pc-kpt #" + std::to_string(ik + 1) + " does not fold onto any SC-kpt of the wavefunction file.");
   }
-  std::vector<int> used;
+  std::vector<int> used_all, used;
   for (int i = 0; i < wc.nkpts; ++i)
-    if (!folds[(size_t)i].empty()) used.push_back(i);
+    if (!folds[(size_t)i].empty()) used_all.push_back(i);
+  {  // this rank's contiguous block, balanced by n_bands * nplane (main_BandUP.f90:133 becomes first..last)
+    double total = 0.0;
+    for (int i : used_all) total += (double)nplane[(size_t)i];
+    double acc = 0.0;
+    for (int i : used_all) {
+      const double mid = acc + 0.5 * (double)nplane[(size_t)i];
+      const int owner = std::min(n_ranks - 1, (int)(mid / total * n_ranks));
+      if (owner == rank) used.push_back(i);
+      acc += (double)nplane[(size_t)i];
+    }
+  }
+  size_t n_pck_mine = 0;
+  for (int i : used) n_pck_mine += folds[(size_t)i].size();
 
   // MAIN LOOP (:131-177), double buffered: records of k-point j+1 are read while j uploads/computes
   const size_t block = (size_t)wc.nbands * (size_t)wc.nrecl;
@@ -519,7 +561,29 @@ int main(int argc, char** argv) {
     std::printf("SC-kpt #%d: %d plane waves%s, %d pc-kpt(s) fold onto it\n", i + 1, npw, nsp == 2 ? " (spinor)" : "", nf);
   }
   for (int j : inflight) drain(j);
-  if (n_parsed != n_pck) die("ERROR: not every pc-kpt could be unfolded.");
+  if (n_parsed != n_pck_mine) die("ERROR: not every pc-kpt could be unfolded.");
+  if (n_ranks > 1) {  // the path's only collective: every rank's disjoint delta_N rows (ncclAllGather)
+    if (spinor) die("ERROR: spinor output is supported by BandUP_gpu.x with one rank only.");
+    std::vector<double> mine(n_pck_mine * (size_t)nener), all(n_pck * (size_t)nener);
+    std::vector<int64_t> ids, all_ids(n_pck);
+    for (int i : used)
+      for (int r : folds[(size_t)i]) {
+        std::memcpy(&mine[ids.size() * (size_t)nener], &dN_all[(size_t)r * (size_t)nener], sizeof(double) * (size_t)nener);
+        ids.push_back(r);
+      }
+    int64_t n_total = 0;
+    gpu_check(h, bandup_gpu_gather_dN(h, mine.data(), ids.data(), (int64_t)ids.size(), all.data(), all_ids.data(),
+                                      (int64_t)n_pck, &n_total), "gather_dN");
+    if ((size_t)n_total != n_pck) die("ERROR: not every pc-kpt could be unfolded.");
+    for (size_t r = 0; r < n_pck; ++r)
+      std::memcpy(&dN_all[(size_t)all_ids[r] * (size_t)nener], &all[r * (size_t)nener], sizeof(double) * (size_t)nener);
+    gpu_check(h, bandup_gpu_comm_finalize(h), "comm_finalize");
+    if (rank != 0) {  // rank 0 writes the files
+      for (auto b : bufs) bandup_gpu_pinned_free(b);
+      bandup_gpu_finalize(h);
+      return 0;
+    }
+  }
 
   // write_band_struc (io_routines_mod.f90:889-977): '(2(f8.4,2X),ES10.3)' [+ 5 spin columns]
   double normal[3] = {0, 0, 1}, origin[3] = {0, 0, 0};

@@ -68,3 +68,28 @@ def test_two_gpus_shard_and_nccl_gather():
         _, dN, _, _ = O.unfold_kpt(coeffs, gf @ sc.B_sc, ener, sc.b_pc, sc.folding_G(iK), grid, norm_mode=1)
         got = r0[0][np.asarray(sc.folds[iK])]
         assert np.max(np.abs(got - dN) / np.maximum(np.abs(dN), 1e-12)) <= 1e-6
+
+
+def test_host_exe_two_ranks(tmp_path, gpu_lib):
+    """BandUP_gpu.x as two processes on two GPUs (-n_ranks 2): the gathered output file equals the
+    one-rank output."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from bandup_b200 import bandup_files as BF
+    from tests.test_host_exe import EXE, _job
+    _job(tmp_path, False)
+    common = [str(EXE), "-no_symm_sckpts", "-no_symm_avg"]
+    r = subprocess.run(common + ["-out_file_nosymm", "one.dat"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    procs = [subprocess.Popen(common + ["-out_file_nosymm", "two.dat", "-n_ranks", "2", "-rank", str(k),
+                                        "-nccl_id_file", "ncclid"], cwd=tmp_path, stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for k in (0, 1)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert np.array_equal(BF.read_band_struc(tmp_path / "one.dat"), BF.read_band_struc(tmp_path / "two.dat"))
+    # each rank took a share of the SC-kpts
+    n0 = outs[0][0].count("SC-kpt #")
+    n1 = outs[1][0].count("SC-kpt #")
+    assert n0 > 0 and n1 > 0
