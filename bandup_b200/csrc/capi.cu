@@ -1,137 +1,17 @@
-// capi.cu -- the C ABI of libbandup_gpu.so (include/bandup_gpu.h): contexts,
-// the double-buffered upload pipeline and the per-k-point kernel sequence.
+// capi.cu -- the C ABI of libbandup_gpu.so (include/bandup_gpu.h): contexts, run-wide set-up,
+// the double-buffered upload pipeline and the per-k-point / per-batch kernel sequence.
+// (capi_projected.cu: rho, Pauli vectors, operators; capi_comm.cu: the NCCL gather.)
 //
-// There is deliberately NO CPU fallback anywhere in this file: without a usable
-// sm_100 device bandup_gpu_init fails with BANDUP_GPU_ERR_NO_DEVICE.
+// There is deliberately NO CPU fallback anywhere in this library: without a usable sm_100
+// device bandup_gpu_init fails with BANDUP_GPU_ERR_NO_DEVICE.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
-#include <mutex>
-#include <string>
-#include <utility>
-#include <vector>
 
-#include "kernels.cuh"
-#include "nccl_dyn.h"
+#include "ctx.cuh"
 
 namespace bandup {
-namespace {
-
-constexpr int kDepth = 2;          // k-points in flight (double buffering)
-constexpr int kMaxHandles = 64;
-constexpr double kEpsDp = 2.220446049250313e-16;  // epsilon(1.0_dp)
-constexpr double kMaxTolVecEq = 1e-3;             // max_tol_for_vec_equality
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    // grow geometrically so k-points of slightly different n_pw do not realloc
-    size_t want = bytes + bytes / 16 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-
-struct PinBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 16 + 256;
-    cudaError_t e = cudaMallocHost(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-
-struct RhoEntry {  // one stored element of an unfolding-density operator (reference order)
-  int32_t fold, iener, m1, m2;
-  float re, im;
-};
-
-constexpr int kDescRing = 8;
-struct DescSlot {  // pinned + device staging of one batch's KptGeom array
-  KptGeom* h = nullptr;
-  KptGeom* d = nullptr;
-  size_t cap = 0;
-  cudaEvent_t ev = nullptr;
-};
-
-struct Flight {  // one SC k-point in flight
-  bool busy = false;      // submitted, not fetched yet
-  bool resident = false;  // device buffers still hold this k-point (for the rho calls)
-  int ikpt = -1;
-  int n_spinor = 0, n_pw = 0, n_bands = 0, n_fold = 0, n_unique = 0, layout = 0;
-  long long stride_bytes = 0;
-  std::vector<int> unique_of;  // pc-kpt (user fold) -> distinct coset
-  DevBuf coeffs, gfrac, energies, weights, dN, nsel, norms, slot, selected, workspace;
-  PinBuf h_weights, h_dN, h_nsel, h_norms;
-  cudaEvent_t uploaded = nullptr, done = nullptr;
-  // per-unique-fold results (alias weights/dN/nsel unless two pc-kpts share a coset)
-  const double* d_dn_unique = nullptr;
-  const int32_t* d_ns_unique = nullptr;
-  const double* d_w_unique = nullptr;
-  // projected variant
-  bool rho_ready = false;
-  DevBuf sel_off, csel, pair_count, pair_off, pairs, overflow, trace_out;
-  std::vector<long long> h_pair_off;
-  std::vector<RhoEntry> rho_entries;
-  long long rho_energies = 0;
-};
-
-struct Ctx {
-  int device = 0;
-  int sm_count = 148;
-  cudaStream_t copy = nullptr, compute = nullptr, aux = nullptr;  // aux: device plane-wave lists
-  cudaEvent_t aux_done = nullptr;
-  bool cells_set = false, grid_set = false;
-  double B_sc[9] = {0}, B_inv[9] = {0};  // row-major, row = vector
-  int32_t M[9] = {0};                    // row-major int_M
-  CosetCommon coset{};
-  DescSlot desc_ring[kDescRing];
-  int desc_next = 0;
-  std::vector<double> grid;
-  DevBuf d_grid;
-  NcclComm comm = nullptr;  // delta_N gather across ranks (one process per GPU)
-  int comm_ranks = 0, comm_rank = -1;
-  DevBuf comm_send, comm_recv;
-  DevBuf gvec_scratch;  // per-CTA counts/offsets of the device plane-wave enumeration
-  DevBuf d_operator;  // current general operator O [n_bands][n_bands] complex128
-  int operator_bands = 0;
-  int nener = 0;
-  double sigma = kEpsDp;
-  Flight flights[kDepth];
-  int next_flight = 0;
-  int chunk_vecs = 0, ctas_per_sm = 0, n_stages = 0;
-  bool profiling = false;
-  bool perform_unfold = true;  // args%perform_unfold; false == -dont_unfold
-  std::vector<cudaEvent_t> event_pool;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[BANDUP_GPU_K_COUNT];
-  double total_ms[BANDUP_GPU_K_COUNT] = {0};
-  int64_t count[BANDUP_GPU_K_COUNT] = {0};
-  int64_t launches = 0;
-  std::string err = "";
-};
 
 std::mutex g_mutex;
 Ctx* g_ctx[kMaxHandles] = {nullptr};
@@ -155,11 +35,7 @@ int cuda_fail(Ctx* c, cudaError_t e, const char* where) {
               std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
 }
 
-#define CU(call)                                         \
-  do {                                                   \
-    cudaError_t e_ = (call);                             \
-    if (e_ != cudaSuccess) return cuda_fail(c, e_, #call); \
-  } while (0)
+
 
 // ---- small host-side linear algebra (row-major, row = vector) -------------
 
@@ -229,26 +105,7 @@ cudaEvent_t take_event(Ctx* c) {
   return e;
 }
 
-struct KernelScope {  // brackets one launch with events when profiling is on
-  Ctx* c;
-  int which;
-  cudaStream_t s;
-  cudaEvent_t a = nullptr, b = nullptr;
-  KernelScope(Ctx* c_, int which_, cudaStream_t s_) : c(c_), which(which_), s(s_) {
-    c->launches++;
-    if (c->profiling) {
-      a = take_event(c);
-      b = take_event(c);
-      cudaEventRecord(a, s);
-    }
-  }
-  ~KernelScope() {
-    if (a) {
-      cudaEventRecord(b, s);
-      c->pending[which].push_back({a, b});
-    }
-  }
-};
+
 
 void resolve_pending(Ctx* c) {
   for (int k = 0; k < BANDUP_GPU_K_COUNT; ++k) {
@@ -264,6 +121,8 @@ void resolve_pending(Ctx* c) {
     c->pending[k].clear();
   }
 }
+
+namespace {
 
 // ---- the per-k-point kernel sequence ---------------------------------------
 
@@ -300,8 +159,6 @@ int plan_folds(Ctx* c, int n_fold, const int32_t* g0, FoldPlan* plan) {
   }
   return BANDUP_GPU_OK;
 }
-
-size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct WorkspaceLayout {
   size_t slot_off, slot_shift_off, counts_off, partials_off, tmp_w_off, tmp_dn_off, tmp_ns_off, total;
@@ -494,6 +351,7 @@ int check_shape(Ctx* c, int n_spinor, int n_pw, int n_bands, int layout, long lo
 }  // namespace bandup
 
 using namespace bandup;
+
 
 extern "C" {
 
@@ -1083,429 +941,6 @@ int bandup_gpu_fetch_kpt(int handle, int ikpt, double* weights, double* dN, int3
   }
   fl->busy = false;  // the slot may be reused; until then the k-point stays resident
   return rc;
-}
-
-namespace {
-
-Flight* resident_flight(Ctx* c, int ikpt) {
-  for (auto& f : c->flights)
-    if (!f.busy && f.resident && f.ikpt == ikpt) return &f;
-  return nullptr;
-}
-
-int need_resident(Ctx* c, int ikpt, Flight** out) {
-  for (auto& f : c->flights)
-    if (f.busy && f.ikpt == ikpt)
-      return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "call bandup_gpu_fetch_kpt for this k-point first");
-  *out = resident_flight(c, ikpt);
-  if (!*out)
-    return fail(c, BANDUP_GPU_ERR_UNKNOWN_KPT,
-                "k-point " + std::to_string(ikpt) + " is no longer resident on the device");
-  return BANDUP_GPU_OK;
-}
-
-}  // namespace
-
-int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t* n_energies,
-                         int64_t* n_entries) {
-  Ctx* c = get(handle);
-  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  if (!c->perform_unfold)
-    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "rho with -dont_unfold is not offered by the GPU path");
-  if (!(min_dN >= kEpsDp))
-    return fail(c, BANDUP_GPU_ERR_DELTA_N_ZERO,
-                "ERROR (calc_rho): delta_N = 0. (min_dN must be >= epsilon(1.0_dp); the reference uses 1e-3)");
-  Flight* fl = nullptr;
-  int rc = need_resident(c, ikpt, &fl);
-  if (rc) return rc;
-  cudaSetDevice(c->device);
-  cudaStream_t s = c->compute;
-  const int nu = fl->n_unique, nener = c->nener, nb = fl->n_bands;
-  const int cells = nu * nener;
-  const int cap = rho_active_cap(nb);
-  fl->rho_ready = false;
-  CU(fl->pair_count.reserve(sizeof(int) * (size_t)cells));
-  CU(fl->pair_off.reserve(sizeof(long long) * ((size_t)cells + 1)));
-  CU(fl->overflow.reserve(sizeof(int)));
-  CU(fl->sel_off.reserve(sizeof(long long) * ((size_t)nu + 1)));
-  CU(cudaMemsetAsync(fl->overflow.p, 0, sizeof(int), s));
-  const double* d_grid = static_cast<const double*>(c->d_grid.p);
-  const double* d_ener = static_cast<const double*>(fl->energies.p);
-  {
-    KernelScope k(c, BANDUP_GPU_K_RHO, s);
-    // perform_unfolding calls calc_rho WITHOUT std_dev (:1404-1407): lambda is the box
-    // (sigma = epsilon) here whatever smearing the delta_N grid was given
-    launch_rho_plan(d_grid, nener, kEpsDp, d_ener, nb, nu, fl->d_dn_unique, min_dN, cap,
-                    static_cast<int*>(fl->pair_count.p), static_cast<long long*>(fl->pair_off.p),
-                    static_cast<int*>(fl->overflow.p), s);
-    c->launches++;  // plan + scan
-  }
-  // ordered selected lists of every unique fold + their offsets
-  std::vector<int32_t> h_ns((size_t)nu);
-  CU(cudaMemcpyAsync(h_ns.data(), fl->d_ns_unique, sizeof(int32_t) * (size_t)nu, cudaMemcpyDeviceToHost, s));
-  fl->h_pair_off.assign((size_t)cells + 1, 0);
-  CU(cudaMemcpyAsync(fl->h_pair_off.data(), fl->pair_off.p, sizeof(long long) * ((size_t)cells + 1),
-                     cudaMemcpyDeviceToHost, s));
-  int h_overflow = 0;
-  CU(cudaMemcpyAsync(&h_overflow, fl->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  if (h_overflow)
-    return fail(c, BANDUP_GPU_ERR_CAPACITY,
-                "more than " + std::to_string(cap) + " bands couple at one energy (smearing too wide)");
-  long long total_sel = 0;
-  for (int u = 0; u < nu; ++u) total_sel += h_ns[u];
-  const long long total_pairs = fl->h_pair_off[(size_t)cells];
-  fl->rho_entries.clear();
-  fl->rho_energies = 0;
-  for (int cell = 0; cell < cells; ++cell)
-    if (fl->h_pair_off[cell + 1] > fl->h_pair_off[cell]) fl->rho_energies++;
-  std::vector<RhoPair> h_pairs((size_t)total_pairs);
-  if (total_pairs > 0) {
-    CU(fl->selected.reserve(sizeof(int32_t) * (size_t)(total_sel > 0 ? total_sel : 1)));
-    CU(fl->csel.reserve(sizeof(float2) * (size_t)(total_sel > 0 ? total_sel : 1) * (size_t)nb * (size_t)fl->n_spinor));
-    CU(fl->pairs.reserve(sizeof(RhoPair) * (size_t)total_pairs));
-    {
-      KernelScope k(c, BANDUP_GPU_K_RHO, s);
-      launch_scan(fl->d_ns_unique, nu, static_cast<long long*>(fl->sel_off.p), s);
-    }
-    {
-      KernelScope k(c, BANDUP_GPU_K_COSET, s);
-      launch_selected_lists(static_cast<const uint8_t*>(fl->slot.p), fl->n_pw, nu, fl->d_ns_unique,
-                            static_cast<int32_t*>(fl->selected.p), s);
-    }
-    {
-      KernelScope k(c, BANDUP_GPU_K_RHO, s);
-      launch_rho_gather(fl->coeffs.p, fl->stride_bytes, fl->n_pw, fl->n_spinor, nb, fl->layout, nu,
-                        static_cast<const int32_t*>(fl->selected.p),
-                        static_cast<const long long*>(fl->sel_off.p),
-                        static_cast<const double*>(fl->norms.p), fl->csel.p, s);
-    }
-    {
-      KernelScope k(c, BANDUP_GPU_K_RHO, s);
-      launch_rho_pairs(d_grid, nener, kEpsDp, d_ener, nb, nu, fl->d_dn_unique, cap, fl->n_spinor,
-                       static_cast<const long long*>(fl->sel_off.p), fl->csel.p,
-                       static_cast<const int*>(fl->pair_count.p),
-                       static_cast<const long long*>(fl->pair_off.p), static_cast<RhoPair*>(fl->pairs.p), s);
-    }
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(h_pairs.data(), fl->pairs.p, sizeof(RhoPair) * (size_t)total_pairs,
-                       cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-  }
-  // Expand to the list perform_unfolding appends (:1416-1425): full matrix, |rho| >= 1e-5
-  // (single-precision abs), m1 outer / m2 inner, for every pc-kpt (folds that share a coset
-  // share the operator), energies ascending.
-  for (int f = 0; f < fl->n_fold; ++f) {
-    const int u = fl->unique_of[f];
-    for (int ie = 0; ie < nener; ++ie) {
-      const long long p0 = fl->h_pair_off[(size_t)u * nener + ie], p1 = fl->h_pair_off[(size_t)u * nener + ie + 1];
-      if (p1 == p0) continue;
-      const size_t first = fl->rho_entries.size();
-      for (long long p = p0; p < p1; ++p) {
-        const RhoPair& r = h_pairs[(size_t)p];
-        if (hypotf(r.re, r.im) < 1e-5f) continue;
-        fl->rho_entries.push_back({f, ie + 1, r.m1 + 1, r.m2 + 1, r.re, r.im});
-        if (r.m1 != r.m2) fl->rho_entries.push_back({f, ie + 1, r.m2 + 1, r.m1 + 1, r.re, -r.im});
-      }
-      std::sort(fl->rho_entries.begin() + (long)first, fl->rho_entries.end(),
-                [](const RhoEntry& a, const RhoEntry& b) { return a.m1 != b.m1 ? a.m1 < b.m1 : a.m2 < b.m2; });
-    }
-  }
-  fl->rho_ready = true;
-  if (n_energies) {
-    long long ne = 0;
-    for (int f = 0; f < fl->n_fold; ++f) {
-      const int u = fl->unique_of[f];
-      for (int ie = 0; ie < nener; ++ie)
-        if (fl->h_pair_off[(size_t)u * nener + ie + 1] > fl->h_pair_off[(size_t)u * nener + ie]) ++ne;
-    }
-    *n_energies = ne;
-  }
-  if (n_entries) *n_entries = (int64_t)fl->rho_entries.size();
-  return BANDUP_GPU_OK;
-}
-
-int bandup_gpu_fetch_rho(int handle, int ikpt, int64_t capacity, int32_t* fold, int32_t* iener,
-                         int32_t* m1, int32_t* m2, float* rho_re, float* rho_im) {
-  Ctx* c = get(handle);
-  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  Flight* fl = nullptr;
-  int rc = need_resident(c, ikpt, &fl);
-  if (rc) return rc;
-  if (!fl->rho_ready) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_rho_count first");
-  const size_t n = fl->rho_entries.size();
-  if ((int64_t)n > capacity)
-    return fail(c, BANDUP_GPU_ERR_CAPACITY, "capacity too small: need " + std::to_string(n));
-  for (size_t i = 0; i < n; ++i) {
-    const RhoEntry& e = fl->rho_entries[i];
-    if (fold) fold[i] = e.fold;
-    if (iener) iener[i] = e.iener;
-    if (m1) m1[i] = e.m1;
-    if (m2) m2[i] = e.m2;
-    if (rho_re) rho_re[i] = e.re;
-    if (rho_im) rho_im[i] = e.im;
-  }
-  return BANDUP_GPU_OK;
-}
-
-int bandup_gpu_set_perform_unfold(int handle, int perform_unfold) {
-  Ctx* c = get(handle);
-  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  c->perform_unfold = perform_unfold != 0;
-  return BANDUP_GPU_OK;
-}
-
-int bandup_gpu_spectral_function(int handle, int ikpt, double std_dev, double* sf) {
-  Ctx* c = get(handle);
-  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  Flight* fl = nullptr;
-  int rc = need_resident(c, ikpt, &fl);
-  if (rc) return rc;
-  if (!sf) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "sf is NULL");
-  const double sigma = std_dev > 0.0 ? std_dev : 0.025;  // calc_spectral_function's default (:671)
-  cudaSetDevice(c->device);
-  cudaStream_t s = c->compute;
-  const int nener = c->nener, nu = fl->n_unique;
-  CU(fl->trace_out.reserve(sizeof(double) * (size_t)nu * nener));
-  {
-    KernelScope k(c, BANDUP_GPU_K_DELTA_N, s);
-    launch_spectral_function(static_cast<const double*>(c->d_grid.p), nener, sigma,
-                             static_cast<const double*>(fl->energies.p), fl->d_w_unique, fl->n_bands, nu,
-                             static_cast<double*>(fl->trace_out.p), s);
-  }
-  CU(cudaGetLastError());
-  std::vector<double> h((size_t)nu * nener);
-  CU(cudaMemcpyAsync(h.data(), fl->trace_out.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  for (int f = 0; f < fl->n_fold; ++f)
-    std::memcpy(sf + (size_t)f * nener, h.data() + (size_t)fl->unique_of[f] * nener, sizeof(double) * (size_t)nener);
-  return BANDUP_GPU_OK;
-}
-
-int bandup_gpu_pauli_vectors(int handle, int ikpt, double* sigma) {
-  Ctx* c = get(handle);
-  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  Flight* fl = nullptr;
-  int rc = need_resident(c, ikpt, &fl);
-  if (rc) return rc;
-  if (!fl->rho_ready) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_rho_count first");
-  if (fl->n_spinor != 2) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "Pauli vectors need a spinor wavefunction");
-  if (!sigma) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "sigma is NULL");
-  cudaSetDevice(c->device);
-  cudaStream_t s = c->compute;
-  const int nener = c->nener, cells = fl->n_unique * nener;
-  const long long n_pairs = fl->h_pair_off.empty() ? 0 : fl->h_pair_off[(size_t)cells];
-  DevBuf contrib;
-  CU(fl->trace_out.reserve(sizeof(double) * 3 * (size_t)cells));
-  cudaError_t e = contrib.reserve(sizeof(double) * 3 * (size_t)(n_pairs > 0 ? n_pairs : 1));
-  if (e != cudaSuccess) return cuda_fail(c, e, "pauli scratch");
-  {
-    KernelScope k(c, BANDUP_GPU_K_RHO, s);
-    launch_pauli(fl->coeffs.p, fl->stride_bytes, fl->n_pw, fl->layout, static_cast<const double*>(fl->norms.p),
-                 static_cast<const RhoPair*>(fl->pairs.p), n_pairs, cells,
-                 static_cast<const long long*>(fl->pair_off.p), static_cast<double*>(contrib.p),
-                 static_cast<double*>(fl->trace_out.p), s);
-  }
-  std::vector<double> h(3 * (size_t)cells);
-  e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), fl->trace_out.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  contrib.release();
-  if (e != cudaSuccess) return cuda_fail(c, e, "bandup_gpu_pauli_vectors");
-  for (int f = 0; f < fl->n_fold; ++f)
-    std::memcpy(sigma + 3 * (size_t)f * nener, h.data() + 3 * (size_t)fl->unique_of[f] * nener,
-                sizeof(double) * 3 * (size_t)nener);
-  return BANDUP_GPU_OK;
-}
-
-int bandup_gpu_set_operator(int handle, int n_bands, const double* O) {
-  Ctx* c = get(handle);
-  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  if (n_bands < 1 || !O) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad operator");
-  cudaSetDevice(c->device);
-  const size_t bytes = sizeof(double) * 2 * (size_t)n_bands * (size_t)n_bands;
-  CU(cudaStreamSynchronize(c->compute));
-  CU(c->d_operator.reserve(bytes));
-  CU(cudaMemcpy(c->d_operator.p, O, bytes, cudaMemcpyHostToDevice));
-  c->operator_bands = n_bands;
-  return BANDUP_GPU_OK;
-}
-
-int bandup_gpu_orb_contrib_matrix(int handle, int n_bands, int n_ao, const double* dual,
-                                  const double* proj, const uint8_t* ao_mask,
-                                  const double* band_energies, double max_band_dE, double min_abs,
-                                  double* O_out) {
-  Ctx* c = get(handle);
-  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  if (n_bands < 1 || n_ao < 1 || !dual || !proj || !ao_mask || !band_energies)
-    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad orbital-projection arguments");
-  cudaSetDevice(c->device);
-  cudaStream_t s = c->compute;
-  const size_t mat = sizeof(double) * 2 * (size_t)n_bands * (size_t)n_ao;
-  const size_t obytes = sizeof(double) * 2 * (size_t)n_bands * (size_t)n_bands;
-  DevBuf d_dual, d_proj, d_mask, d_ener;
-  cudaError_t e = cudaSuccess;
-  if ((e = d_dual.reserve(mat)) == cudaSuccess && (e = d_proj.reserve(mat)) == cudaSuccess &&
-      (e = d_mask.reserve((size_t)n_ao)) == cudaSuccess &&
-      (e = d_ener.reserve(sizeof(double) * (size_t)n_bands)) == cudaSuccess &&
-      (e = cudaStreamSynchronize(s)) == cudaSuccess && (e = c->d_operator.reserve(obytes)) == cudaSuccess) {
-    cudaMemcpyAsync(d_dual.p, dual, mat, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(d_proj.p, proj, mat, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(d_mask.p, ao_mask, (size_t)n_ao, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(d_ener.p, band_energies, sizeof(double) * (size_t)n_bands, cudaMemcpyHostToDevice, s);
-    {
-      KernelScope k(c, BANDUP_GPU_K_RHO, s);
-      launch_orb_contrib(n_bands, n_ao, d_dual.p, d_proj.p, static_cast<const uint8_t*>(d_mask.p),
-                         static_cast<const double*>(d_ener.p), max_band_dE, min_abs, c->d_operator.p, s);
-    }
-    e = cudaGetLastError();
-    if (e == cudaSuccess && O_out) e = cudaMemcpyAsync(O_out, c->d_operator.p, obytes, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  }
-  d_dual.release(); d_proj.release(); d_mask.release(); d_ener.release();
-  if (e != cudaSuccess) return cuda_fail(c, e, "bandup_gpu_orb_contrib_matrix");
-  c->operator_bands = n_bands;
-  return BANDUP_GPU_OK;
-}
-
-int bandup_gpu_unfold_operator(int handle, int ikpt, double min_abs_rho, int clip, double* out) {
-  Ctx* c = get(handle);
-  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  Flight* fl = nullptr;
-  int rc = need_resident(c, ikpt, &fl);
-  if (rc) return rc;
-  if (!fl->rho_ready) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_rho_count first");
-  if (!out) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "out is NULL");
-  if (c->operator_bands != fl->n_bands)
-    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "Incompatible matrix shapes! (operator vs n_bands)");
-  cudaSetDevice(c->device);
-  cudaStream_t s = c->compute;
-  const int nener = c->nener, cells = fl->n_unique * nener;
-  CU(fl->trace_out.reserve(sizeof(double) * (size_t)cells));
-  {
-    KernelScope k(c, BANDUP_GPU_K_RHO, s);
-    launch_trace(cells, fl->n_bands, fl->d_dn_unique, static_cast<const long long*>(fl->pair_off.p),
-                 static_cast<const RhoPair*>(fl->pairs.p), c->d_operator.p, min_abs_rho, clip,
-                 static_cast<double*>(fl->trace_out.p), s);
-  }
-  CU(cudaGetLastError());
-  std::vector<double> h((size_t)cells);
-  CU(cudaMemcpyAsync(h.data(), fl->trace_out.p, sizeof(double) * (size_t)cells, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  for (int f = 0; f < fl->n_fold; ++f)
-    std::memcpy(out + (size_t)f * nener, h.data() + (size_t)fl->unique_of[f] * nener, sizeof(double) * (size_t)nener);
-  return BANDUP_GPU_OK;
-}
-
-// ---- the delta_N gather (one process per GPU) ---------------------------------
-
-int bandup_gpu_comm_unique_id(void* id) {
-  const NcclApi& n = nccl_api();
-  if (!n.ok) return fail(nullptr, BANDUP_GPU_ERR_NCCL, n.why);
-  if (!id) return fail(nullptr, BANDUP_GPU_ERR_INVALID_ARG, "id is NULL");
-  NcclUniqueId u;
-  const int rc = n.GetUniqueId(&u);
-  if (rc != kNcclSuccess) return fail(nullptr, BANDUP_GPU_ERR_NCCL, std::string("ncclGetUniqueId: ") + n.GetErrorString(rc));
-  std::memcpy(id, u.internal, sizeof(u.internal));
-  return BANDUP_GPU_OK;
-}
-
-int bandup_gpu_comm_init(int handle, int n_ranks, int rank, const void* id) {
-  Ctx* c = get(handle);
-  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  const NcclApi& n = nccl_api();
-  if (!n.ok) return fail(c, BANDUP_GPU_ERR_NCCL, n.why);
-  if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad rank / id");
-  if (c->comm) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "communicator already initialised");
-  cudaSetDevice(c->device);
-  NcclUniqueId u;
-  std::memcpy(u.internal, id, sizeof(u.internal));
-  const int rc = n.CommInitRank(&c->comm, n_ranks, u, rank);
-  if (rc != kNcclSuccess) {
-    c->comm = nullptr;
-    return fail(c, BANDUP_GPU_ERR_NCCL, std::string("ncclCommInitRank: ") + n.GetErrorString(rc));
-  }
-  c->comm_ranks = n_ranks;
-  c->comm_rank = rank;
-  return BANDUP_GPU_OK;
-}
-
-int bandup_gpu_comm_finalize(int handle) {
-  Ctx* c = get(handle);
-  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  if (c->comm) {
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->compute);
-    nccl_api().CommDestroy(c->comm);
-    c->comm = nullptr;
-  }
-  c->comm_ranks = 0;
-  c->comm_rank = -1;
-  return BANDUP_GPU_OK;
-}
-
-int bandup_gpu_gather_dN(int handle, const double* dN_local, const int64_t* row_ids_local, int64_t n_local,
-                         double* dN_all, int64_t* row_ids_all, int64_t capacity_rows, int64_t* n_total) {
-  Ctx* c = get(handle);
-  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  if (!c->comm) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_comm_init first");
-  if (!c->grid_set) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_set_grid first");
-  if (n_local < 0 || (n_local > 0 && (!dN_local || !row_ids_local)) || !n_total)
-    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad gather arguments");
-  const NcclApi& n = nccl_api();
-  const int R = c->comm_ranks, nener = c->nener;
-  cudaSetDevice(c->device);
-  cudaStream_t s = c->compute;
-  // 1. how many rows everyone has
-  CU(c->comm_send.reserve(sizeof(long long)));
-  CU(c->comm_recv.reserve(sizeof(long long) * (size_t)R));
-  const long long mine = n_local;
-  CU(cudaMemcpyAsync(c->comm_send.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
-  int rc = n.AllGather(c->comm_send.p, c->comm_recv.p, 1, kNcclInt64, c->comm, s);
-  if (rc != kNcclSuccess) return fail(c, BANDUP_GPU_ERR_NCCL, std::string("ncclAllGather: ") + n.GetErrorString(rc));
-  std::vector<long long> counts((size_t)R);
-  CU(cudaMemcpyAsync(counts.data(), c->comm_recv.p, sizeof(long long) * (size_t)R, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  long long n_max = 1, total = 0;
-  for (long long v : counts) {
-    if (v > n_max) n_max = v;
-    total += v;
-  }
-  *n_total = total;
-  // 2. one padded payload per rank: [row id (exact in a double below 2^53), nener values] per row
-  const size_t row = (size_t)nener + 1, per_rank = row * (size_t)n_max;
-  std::vector<double> send(per_rank, 0.0);
-  for (long long i = 0; i < n_local; ++i) {
-    send[(size_t)i * row] = (double)row_ids_local[i];
-    std::memcpy(&send[(size_t)i * row + 1], dN_local + (size_t)i * nener, sizeof(double) * (size_t)nener);
-  }
-  CU(c->comm_send.reserve(sizeof(double) * per_rank));
-  CU(c->comm_recv.reserve(sizeof(double) * per_rank * (size_t)R));
-  CU(cudaMemcpyAsync(c->comm_send.p, send.data(), sizeof(double) * per_rank, cudaMemcpyHostToDevice, s));
-  rc = n.AllGather(c->comm_send.p, c->comm_recv.p, per_rank, kNcclFloat64, c->comm, s);
-  if (rc != kNcclSuccess) return fail(c, BANDUP_GPU_ERR_NCCL, std::string("ncclAllGather: ") + n.GetErrorString(rc));
-  std::vector<double> recv(per_rank * (size_t)R);
-  CU(cudaMemcpyAsync(recv.data(), c->comm_recv.p, sizeof(double) * recv.size(), cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  if (!dN_all || !row_ids_all) return BANDUP_GPU_OK;  // count query only
-  if (capacity_rows < total) return fail(c, BANDUP_GPU_ERR_CAPACITY, "capacity_rows too small: need " + std::to_string(total));
-  // 3. rows in ascending global row id; a duplicate id means a pc-kpt was unfolded twice
-  std::vector<std::pair<long long, const double*>> rows;
-  rows.reserve((size_t)total);
-  for (int r = 0; r < R; ++r)
-    for (long long i = 0; i < counts[(size_t)r]; ++i) {
-      const double* p = &recv[(size_t)r * per_rank + (size_t)i * row];
-      rows.push_back({(long long)p[0], p + 1});
-    }
-  std::stable_sort(rows.begin(), rows.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
-  for (size_t i = 0; i < rows.size(); ++i) {
-    if (i > 0 && rows[i].first == rows[i - 1].first)
-      return fail(c, BANDUP_GPU_ERR_INVALID_ARG,
-                  "pc-kpt row " + std::to_string(rows[i].first) + " was produced by more than one rank");
-    row_ids_all[i] = rows[i].first;
-    std::memcpy(dN_all + i * (size_t)nener, rows[i].second, sizeof(double) * (size_t)nener);
-  }
-  return BANDUP_GPU_OK;
 }
 
 int bandup_gpu_set_profiling(int handle, int enabled) {
