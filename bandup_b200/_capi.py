@@ -78,6 +78,8 @@ def load() -> C.CDLL:
         "bandup_gpu_set_grid": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_i32p]),
         "bandup_gpu_get_grid": (C.c_int, [C.c_int, c_f64p]),
         "bandup_gpu_folding_g0": (C.c_int, [C.c_int, c_f64p, C.c_int, c_i32p, c_f64p]),
+        "bandup_gpu_fold_map": (C.c_int, [C.c_int, C.c_int, c_f64p, C.c_int, c_i32p, c_f64p, C.c_int, c_i32p, c_i32p,
+                                          c_f64p]),
         "bandup_gpu_submit_kpt": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                             C.c_void_p, c_i32p, c_f64p, C.c_int, c_i32p]),
         "bandup_gpu_submit_kpt_vasp": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p,

@@ -560,6 +560,71 @@ int bandup_gpu_folding_g0(int handle, const double* folding_G, int n_fold, int32
   return BANDUP_GPU_OK;
 }
 
+int bandup_gpu_fold_map(int handle, int n_pckpts, const double* pckpts_cart, int n_sckpts,
+                        const int32_t* eqv_offsets, const double* eqv_cart, int n_sckpts_to_skip,
+                        int32_t* fold_sckpt, int32_t* fold_eqv, double* tol_used) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (!c->cells_set) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_set_cells first");
+  if (n_pckpts < 1 || n_sckpts < 1 || !pckpts_cart || !eqv_offsets || !eqv_cart || !fold_sckpt || n_sckpts_to_skip < 0)
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad fold_map arguments");
+  const int n_eqv = eqv_offsets[n_sckpts];
+  if (eqv_offsets[0] != 0 || n_eqv < n_sckpts) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad eqv_offsets");
+  // coords_cart_vec_in_new_basis uses inverse(transpose(latt)) (math_mod.f90:243-246)
+  double t[9], aux[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) t[3 * i + j] = c->B_sc[3 * j + i];
+  if (!inv3(t, aux)) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "singular SC reciprocal lattice");
+  cudaSetDevice(c->device);
+  cudaStream_t s = c->aux;
+  DevBuf d_pck, d_off, d_eqv, d_out;
+  cudaError_t e = cudaSuccess;
+  int rc = BANDUP_GPU_OK;
+  const size_t out_bytes = sizeof(int) * (2 * (size_t)n_pckpts + 1);
+  if ((e = d_pck.reserve(sizeof(double) * 3 * (size_t)n_pckpts)) != cudaSuccess ||
+      (e = d_off.reserve(sizeof(int) * ((size_t)n_sckpts + 1))) != cudaSuccess ||
+      (e = d_eqv.reserve(sizeof(double) * 3 * (size_t)n_eqv)) != cudaSuccess ||
+      (e = d_out.reserve(out_bytes)) != cudaSuccess) {
+    rc = cuda_fail(c, e, "fold_map buffers");
+  } else {
+    cudaMemcpyAsync(d_pck.p, pckpts_cart, sizeof(double) * 3 * (size_t)n_pckpts, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_off.p, eqv_offsets, sizeof(int) * ((size_t)n_sckpts + 1), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_eqv.p, eqv_cart, sizeof(double) * 3 * (size_t)n_eqv, cudaMemcpyHostToDevice, s);
+    int* d_sck = static_cast<int*>(d_out.p);
+    int* d_e = d_sck + n_pckpts;
+    int* d_n = d_e + n_pckpts;
+    // get_geom_unfolding_relations (:430-483): start at default_tol_for_vec_equality, add 5 % of it
+    // per attempt until every pc-kpt folds or max_tol_for_vec_equality is passed
+    double tol = 1e-5;
+    int n_folding = -1;
+    std::vector<int> h(2 * (size_t)n_pckpts + 1);
+    while (n_folding != n_pckpts && tol <= kMaxTolVecEq) {
+      {
+        KernelScope k(c, BANDUP_GPU_K_COSET, s);
+        launch_fold_map(c->B_sc, aux, tol, n_pckpts, static_cast<const double*>(d_pck.p), n_sckpts, n_sckpts_to_skip,
+                        static_cast<const int*>(d_off.p), static_cast<const double*>(d_eqv.p), d_sck, d_e, d_n, s);
+      }
+      if ((e = cudaMemcpyAsync(h.data(), d_out.p, out_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+          (e = cudaStreamSynchronize(s)) != cudaSuccess) {
+        rc = cuda_fail(c, e, "fold_map");
+        break;
+      }
+      n_folding = h[2 * (size_t)n_pckpts];
+      if (tol_used) *tol_used = tol;
+      tol += 0.05 * 1e-5;
+    }
+    if (rc == BANDUP_GPU_OK) {
+      std::memcpy(fold_sckpt, h.data(), sizeof(int) * (size_t)n_pckpts);
+      if (fold_eqv) std::memcpy(fold_eqv, h.data() + n_pckpts, sizeof(int) * (size_t)n_pckpts);
+      if (n_folding != n_pckpts)  // main_BandUP.f90:114: n_pckpts /= n_folding_pckpts
+        rc = fail(c, BANDUP_GPU_ERR_FOLDING_VECTOR,
+                  std::to_string(n_pckpts - n_folding) + " pc-kpt(s) fold onto none of the SC-kpts");
+    }
+  }
+  d_pck.release(); d_off.release(); d_eqv.release(); d_out.release();
+  return rc;
+}
+
 int bandup_gpu_pipeline_depth(int handle) {
   return get(handle) ? kDepth : 0;
 }

@@ -99,6 +99,12 @@ void launch_gvec_count(const double* kfrac, const double* B_rows, double c, doub
 void launch_gvec_write(const double* kfrac, const double* B_rows, double c, double ecut, const int* nb,
                        const long long* d_block_off, int32_t* d_g_frac, long long capacity, cudaStream_t s);
 
+// K7 -- geometric unfolding relations: first (SC-kpt, equivalent point) every pc-kpt folds onto,
+// with the reference's floating-point vec_in_latt (band_unfolding_routines_mod.f90:306-429).
+void launch_fold_map(const double* latt, const double* aux, double tol, int n_pck, const double* d_pck, int n_sck,
+                     int n_skip, const int* d_eqv_off, const double* d_eqv, int* d_fold_sck, int* d_fold_eqv,
+                     int* d_n_folding, cudaStream_t s);
+
 // A(k,E) with a Gaussian delta (calc_spectral_function, :654-698); weights per distinct fold.
 void launch_spectral_function(const double* d_grid, int nener, double stddev, const double* d_band_energies,
                               const double* d_weights, int n_bands, int n_fold, double* d_sf,

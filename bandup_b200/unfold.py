@@ -188,6 +188,29 @@ class GpuUnfolder:
                                                     g0.ctypes.data_as(c_i32p), C.byref(res)))
         return g0, res.value
 
+    def get_geom_unfolding_relations(self, pckpts_cart: np.ndarray, sckpts_cart: np.ndarray,
+                                     eqv_points: Optional[Sequence[np.ndarray]] = None, n_sckpts_to_skip: int = 0):
+        """get_geom_unfolding_relations (band_unfolding_routines_mod.f90:430-483): for every pc-kpt the
+        SC-kpt it folds onto.  eqv_points[s] are the Cartesian points equivalent to SC-kpt s under the
+        SC's symmetry operations (None: no symmetry, each SC-kpt alone).  Returns
+        (fold_sckpt, fold_eqv, tol_used); raises BandupGpuError(FOLDING_VECTOR) when a pc-kpt folds
+        onto none."""
+        pk = np.ascontiguousarray(np.atleast_2d(pckpts_cart), dtype=np.float64)
+        sk = np.ascontiguousarray(np.atleast_2d(sckpts_cart), dtype=np.float64)
+        if eqv_points is None:
+            eqv_points = [sk[i:i + 1] for i in range(sk.shape[0])]
+        off = np.zeros(sk.shape[0] + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(e) for e in eqv_points])
+        eq = np.ascontiguousarray(np.concatenate([np.atleast_2d(e) for e in eqv_points]), dtype=np.float64)
+        fs = np.full(pk.shape[0], -1, dtype=np.int32)
+        fe = np.full(pk.shape[0], -1, dtype=np.int32)
+        tol = C.c_double(0.0)
+        self._check(self._lib.bandup_gpu_fold_map(
+            self.handle, pk.shape[0], pk.ctypes.data_as(c_f64p), sk.shape[0], off.ctypes.data_as(c_i32p),
+            eq.ctypes.data_as(c_f64p), int(n_sckpts_to_skip), fs.ctypes.data_as(c_i32p), fe.ctypes.data_as(c_i32p),
+            C.byref(tol)))
+        return fs, fe, tol.value
+
     # -- per SC k-point -----------------------------------------------------
     def submit(self, ikpt: int, wf: PwWavefunction, folding_G: Optional[np.ndarray] = None,
                g0: Optional[np.ndarray] = None) -> None:

@@ -112,6 +112,23 @@ int bandup_gpu_get_grid(int handle, double *energies);
 int bandup_gpu_folding_g0(int handle, const double *folding_G, int n_fold,
                           int32_t *g0, double *max_residual);
 
+/* Replaces the search of get_geom_unfolding_relations / get_GUR_not_public
+ * (band_unfolding_routines_mod.f90:306-483): for every pc-kpt (Cartesian, [n_pckpts][3]) the first
+ * SC-kpt of the list -- the first n_sckpts_to_skip ignored -- having a symmetry-equivalent point
+ * eqv with  vec_in_latt(pc_kpt - eqv, B_matrix_SC, tol)  (crystals_mod.f90:204-255, the
+ * reference's floating-point recipe).  The equivalent points of SC-kpt s are
+ * eqv_cart[eqv_offsets[s] .. eqv_offsets[s+1]) (Cartesian; they come from the host's symmetry
+ * analysis, symmetry_mod.f90:311-484; without symmetry: the SC-kpt itself).  tol starts at 1e-5 and
+ * grows by 5e-7 per attempt until every pc-kpt folds or 1e-3 is passed (:455-479).
+ *   fold_sckpt [n_pckpts]  0-based SC-kpt index, -1 = folds onto none
+ *   fold_eqv   [n_pckpts]  (nullable) index into eqv_cart of the point it folded onto
+ *   tol_used   (nullable)  tolerance of the last attempt
+ * ERR_FOLDING_VECTOR when some pc-kpt folds onto none (main_BandUP.f90:114); the maps are still
+ * filled in. */
+int bandup_gpu_fold_map(int handle, int n_pckpts, const double *pckpts_cart, int n_sckpts,
+                        const int32_t *eqv_offsets, const double *eqv_cart, int n_sckpts_to_skip,
+                        int32_t *fold_sckpt, int32_t *fold_eqv, double *tol_used);
+
 /* ---- per SC-k-point, host buffers (the drop-in path) -------------------- */
 
 /* Replaces, for ALL pc-kpts folding onto SC-kpt `ikpt` at once:

@@ -754,3 +754,50 @@ def test_full_job_config1_graphene(unfolder, tmp_path):
         coeffs, gf, ener = data[iK]
         _, dN, _, _ = O.unfold_kpt(coeffs, gf @ sc.B_sc, ener, sc.b_pc, sc.folding_G(iK), grid, norm_mode=1)
         assert rel_err(got.dN[np.asarray(sc.folds[iK])], dN) <= REL_TOL
+
+
+def test_fold_map_matches_float_vec_in_latt(unfolder):
+    """K7: the geometric unfolding relations (which SC-kpt each pc-kpt folds onto) against a brute
+    force with the oracle's vec_in_latt, including symmetry-equivalent point lists, skipped
+    SC-kpts and the tolerance escalation of get_geom_unfolding_relations."""
+    from bandup_b200.unfold import BandupGpuError
+    from oracle import oracle as O
+    sc = synth.make_scenario("si333_vacancy", scale=0.2, n_kpts=40)
+    setup(unfolder, sc)
+    pk = sc.pc_kpts_cart.copy()
+    K = sc.sc_kpts_cart
+    # exact folding first: must reproduce the scenario's own map
+    fs, fe, tol = unfolder.get_geom_unfolding_relations(pk, K)
+    want = np.empty(pk.shape[0], dtype=int)
+    for iK, rows in enumerate(sc.folds):
+        want[rows] = iK
+    assert np.array_equal(fs, want) and np.array_equal(fe, want) and abs(tol - 1e-5) < 1e-18
+
+    def brute(pk, eqv, skip, tol):
+        out = np.full(pk.shape[0], -1)
+        for i, k in enumerate(pk):
+            for s in range(skip, len(eqv)):
+                if any(O.vec_in_latt(k - e, sc.B_sc, tol) for e in eqv[s]):
+                    out[i] = s
+                    break
+        return out
+    # equivalent-point lists (each SC-kpt plus two images), the first two SC-kpts skipped, and
+    # pc-kpts nudged off the lattice by up to 3e-5: the tolerance has to grow
+    rng = np.random.default_rng(9)
+    eqv = [np.stack([K[s], -K[s], K[s] + 0.37 * sc.B_sc[0]]) for s in range(K.shape[0])]
+    pk2 = pk + rng.uniform(-1, 1, pk.shape) * 3e-5 / np.sqrt(3)
+    skip = 2
+    keep = np.array([want[i] >= skip or np.any([O.vec_in_latt(pk[i] + K[s], sc.B_sc, 1e-5) for s in range(skip, K.shape[0])])
+                     for i in range(pk.shape[0])])
+    pk2 = pk2[keep]
+    fs2, fe2, tol2 = unfolder.get_geom_unfolding_relations(pk2, K, eqv_points=eqv, n_sckpts_to_skip=skip)
+    assert tol2 > 1e-5 and tol2 < 4e-5
+    assert np.array_equal(fs2, brute(pk2, eqv, skip, tol2))
+    assert np.all(fs2 >= skip)
+    # the attempt before must have left somebody unfolded
+    assert np.any(brute(pk2, eqv, skip, tol2 - 0.05e-5) < 0)
+    # a pc-kpt that folds nowhere: error, maps still filled
+    bad = np.vstack([pk[:3], pk[3] + 0.013 * sc.B_sc[1]])
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.get_geom_unfolding_relations(bad, K)
+    assert ei.value.code == 4
