@@ -432,7 +432,7 @@ int main(int argc, char** argv) {
   std::vector<std::array<double, 3>> pck;
   for (auto& d : kp.dirs) pck.insert(pck.end(), d.begin(), d.end());
   const size_t n_pck = pck.size();
-  Mat3 Binv;
+  Mat3 Binv;  // only for the fractional coordinates printed in the rho file
   if (!inverse(B_sc, &Binv)) die("ERROR: singular SC reciprocal lattice");
   std::vector<std::array<double, 3>> Kfrac((size_t)wc.nkpts), Kcart((size_t)wc.nkpts);
   std::vector<int> nplane((size_t)wc.nkpts);
@@ -441,24 +441,35 @@ int main(int argc, char** argv) {
     wc.kpt_header(i + 1, spin_channel, &nplane[(size_t)i], Kfrac[(size_t)i].data(), &ener[(size_t)i]);
     vec_mat(Kfrac[(size_t)i].data(), B_sc, Kcart[(size_t)i].data());
   }
+  // get_geom_unfolding_relations (band_unfolding_routines_mod.f90:430-483) on the device; without
+  // symmetry every SC-kpt is its own only equivalent point
   std::vector<std::vector<int>> folds((size_t)wc.nkpts);
   std::vector<int> sck_of((size_t)n_pck, -1);
-  for (size_t ik = 0; ik < n_pck; ++ik) {
-    for (int i = n_skip; i < wc.nkpts && sck_of[ik] < 0; ++i) {
-      double d[3], f[3], back[3];
-      for (int j = 0; j < 3; ++j) d[j] = pck[ik][j] - Kcart[(size_t)i][j];
-      vec_mat(d, Binv, f);
-      for (int j = 0; j < 3; ++j) f[j] = std::nearbyint(f[j]);
-      vec_mat(f, B_sc, back);
-      double r = 0.0;
-      for (int j = 0; j < 3; ++j) r = std::max(r, std::fabs(back[j] - d[j]));
-      if (r <= 1e-5) {
-        sck_of[ik] = i;
-        folds[(size_t)i].push_back((int)ik);
-      }
+  {
+    std::vector<double> pk(n_pck * 3), eq((size_t)wc.nkpts * 3);
+    std::vector<int32_t> off((size_t)wc.nkpts + 1), fs(n_pck);
+    for (size_t i = 0; i < n_pck; ++i)
+      for (int j = 0; j < 3; ++j) pk[3 * i + (size_t)j] = pck[i][(size_t)j];
+    for (int i = 0; i < wc.nkpts; ++i) {
+      off[(size_t)i] = i;
+      for (int j = 0; j < 3; ++j) eq[3 * (size_t)i + (size_t)j] = Kcart[(size_t)i][(size_t)j];
     }
-    if (sck_of[ik] < 0)  // main_BandUP.f90:114
-      die("ERROR: pc-kpt #" + std::to_string(ik + 1) + " does not fold onto any SC-kpt of the wavefunction file.");
+    off[(size_t)wc.nkpts] = wc.nkpts;
+    double tol_used = 0.0;
+    const int rc = bandup_gpu_fold_map(h, (int)n_pck, pk.data(), wc.nkpts, off.data(), eq.data(), n_skip, fs.data(),
+                                       nullptr, &tol_used);
+    if (rc == BANDUP_GPU_ERR_FOLDING_VECTOR) {  // main_BandUP.f90:114
+      for (size_t ik = 0; ik < n_pck; ++ik)
+        if (fs[ik] < 0)
+          die("ERROR: pc-kpt #" + std::to_string(ik + 1) + " does not fold onto any SC-kpt of the wavefunction file.");
+    }
+    gpu_check(h, rc, "get_geom_unfolding_relations");
+    if (tol_used > 1.0000001e-5)
+      std::printf("WARNING (get_geom_unfolding_relations): the tolerance for vector equality had to be raised to %.3e.\n", tol_used);
+    for (size_t ik = 0; ik < n_pck; ++ik) {
+      sck_of[ik] = fs[ik];
+      folds[(size_t)fs[ik]].push_back((int)ik);
+    }
   }
   std::vector<int> used_all, used;
   for (int i = 0; i < wc.nkpts; ++i)

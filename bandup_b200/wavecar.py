@@ -261,7 +261,13 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
     unfolder.verify_commens(rec_latt_pc, wavecar.B_matrix)
     grid = unfolder.set_energy_grid(E_start, E_end, delta_e)
     sc_k = np.array([wavecar.kpt_header(i + 1, ispin).kpt_frac_coords for i in range(wavecar.nkpts)])
-    folds = fold_pckpts_onto_sckpts(pc_kpts_cart, sc_k, wavecar.B_matrix)
+    if hasattr(unfolder, "get_geom_unfolding_relations"):     # K7 on the device
+        fs, _, _ = unfolder.get_geom_unfolding_relations(pc_kpts_cart, sc_k @ wavecar.B_matrix)
+        folds = [[] for _ in range(wavecar.nkpts)]
+        for ik, s in enumerate(fs):
+            folds[int(s)].append(ik)
+    else:
+        folds = fold_pckpts_onto_sckpts(pc_kpts_cart, sc_k, wavecar.B_matrix)
     used = [i for i in range(wavecar.nkpts) if folds[i]]       # SC-kpts no pc-kpt folds onto are skipped
     costs = [float(wavecar.nbands) * wavecar.kpt_header(i + 1, ispin).nplane for i in used]
     # two buffers more than the pipeline depth: k-points j-1 and j-2 may be in flight and j+1 is being
