@@ -17,7 +17,8 @@ private
 public :: bandup_gpu_init, bandup_gpu_finalize, bandup_gpu_last_error, &
           bandup_gpu_abi_version, bandup_gpu_pinned_alloc, bandup_gpu_pinned_free, &
           bandup_gpu_set_cells, bandup_gpu_set_grid, bandup_gpu_get_grid, &
-          bandup_gpu_folding_g0, bandup_gpu_submit_kpt, bandup_gpu_submit_kpt_vasp, bandup_gpu_fetch_kpt, &
+          bandup_gpu_folding_g0, bandup_gpu_fold_map, bandup_gpu_submit_kpt, bandup_gpu_submit_kpt_vasp, &
+          bandup_gpu_fetch_kpt, &
           bandup_gpu_pipeline_depth, bandup_gpu_set_profiling, &
           bandup_gpu_kernel_time, bandup_gpu_reset_kernel_times, &
           bandup_gpu_launch_count, bandup_gpu_set_tuning, &
@@ -111,6 +112,19 @@ interface
         real(c_double), intent(out) :: max_residual
         integer(c_int) :: bandup_gpu_folding_g0
     end function bandup_gpu_folding_g0
+
+    ! get_geom_unfolding_relations (band_unfolding_routines_mod.f90:430-483) on the device
+    function bandup_gpu_fold_map(handle, n_pckpts, pckpts_cart, n_sckpts, eqv_offsets, eqv_cart, &
+                                 n_sckpts_to_skip, fold_sckpt, fold_eqv, tol_used) &
+        bind(c, name='bandup_gpu_fold_map')
+        import c_int, c_int32_t, c_double
+        integer(c_int), intent(in), value :: handle, n_pckpts, n_sckpts, n_sckpts_to_skip
+        real(c_double), intent(in) :: pckpts_cart(3,*), eqv_cart(3,*)
+        integer(c_int32_t), intent(in) :: eqv_offsets(*)
+        integer(c_int32_t), intent(out) :: fold_sckpt(*), fold_eqv(*)
+        real(c_double), intent(out) :: tol_used
+        integer(c_int) :: bandup_gpu_fold_map
+    end function bandup_gpu_fold_map
 
     ! coeffs = c_loc(wf%pw_coeffs), g_frac = c_loc(wf%G_frac): type(vec3d_int) is three
     ! default integers, i.e. int32 [n_pw][3] in memory.
@@ -321,8 +335,10 @@ contains
         character(kind=c_char), dimension(:), pointer :: chars
         integer :: n, i
         p = bandup_gpu_last_error(handle)
-        msg = ''
-        if(.not. c_associated(p)) return
+        if(.not. c_associated(p))then
+            msg = ''
+            return
+        endif
         call c_f_pointer(p, chars, [1024])
         n = 0
         do while(n < 1024)
