@@ -801,3 +801,45 @@ def test_fold_map_matches_float_vec_in_latt(unfolder):
     with pytest.raises(BandupGpuError) as ei:
         unfolder.get_geom_unfolding_relations(bad, K)
     assert ei.value.code == 4
+
+
+def test_pipeline_soak(unfolder):
+    """300 SC-kpts of changing shape through the double-buffered submit/fetch pipeline (buffers grow
+    and are reused, k-points fetched in and out of order, rho asked for now and then): every result
+    must equal the first one computed for the same input, bit for bit (the path is deterministic),
+    and the first ones are checked against the oracle."""
+    from bandup_b200.unfold import PwWavefunction
+    sc = synth.make_scenario("si333_vacancy", scale=0.12)
+    grid = setup(unfolder, sc)
+    inputs = []
+    for iK in range(6):
+        coeffs, gf, ener = synth.make_wavefunction(sc, iK)
+        nb = 3 + 2 * iK
+        inputs.append((PwWavefunction(np.ascontiguousarray(coeffs[:nb]), gf, ener[:nb]), sc.folding_G(iK), iK))
+    first = {}
+    rng = np.random.default_rng(0)
+    pending = []
+    for it in range(300):
+        wf, fG, iK = inputs[int(rng.integers(0, len(inputs)))]
+        ik = 1000 + it
+        unfolder.submit(ik, wf, folding_G=fG)
+        pending.append((ik, iK))
+        if len(pending) == 2:
+            j = int(rng.integers(0, 2))                     # fetch the older or the newer one
+            ik_f, iK_f = pending.pop(j)
+            res = unfolder.fetch(ik_f)
+            if iK_f not in first:
+                w, dN, ns, _ = oracle_kpt(sc, inputs[iK_f][0].pw_coeffs, inputs[iK_f][0].G_frac,
+                                          inputs[iK_f][0].band_energies, inputs[iK_f][1], grid)
+                assert np.array_equal(res.n_selected, ns)
+                assert rel_err(res.spectral_weight, w) <= REL_TOL and rel_err(res.dN, dN) <= REL_TOL
+                first[iK_f] = res
+            else:
+                ref = first[iK_f]
+                assert np.array_equal(res.spectral_weight, ref.spectral_weight)
+                assert np.array_equal(res.dN, ref.dN) and np.array_equal(res.band_norms, ref.band_norms)
+            if it % 37 == 0:
+                assert len(unfolder.calc_rho(ik_f).rho) > 0
+    for ik_f, iK_f in pending:
+        unfolder.fetch(ik_f)
+    assert len(first) == len(inputs)
