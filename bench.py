@@ -254,10 +254,11 @@ def run_b200(args, sc, rank, world, local_rank):
     if rank == 0:
         _build.build()
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is
-        # VERSION (also via /etc/nccl.conf); an explicit INFO/TRACE from the caller is respected
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: NCCL prints its version banner there at the VERSION and
+        # WARN levels (showVersion in NCCL's init.cc; the level may also come from /etc/nccl.conf);
+        # an explicit INFO/TRACE from the caller is respected
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     else:
