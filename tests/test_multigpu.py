@@ -93,3 +93,24 @@ def test_host_exe_two_ranks(tmp_path, gpu_lib):
     n0 = outs[0][0].count("SC-kpt #")
     n1 = outs[1][0].count("SC-kpt #")
     assert n0 > 0 and n1 > 0
+
+
+def test_bench_two_ranks_prints_one_json_line():
+    """The driver's N>1 launch line: torchrun, one rank per GPU, rank 0 prints exactly one JSON line."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577", str(root / "bench.py"), "--gpus", "2",
+                        "--steps", "3", "--warmup", "3", "--workload", "si333_vacancy", "--kpts-per-step", "2"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["cpu_baseline"] is None                     # rank 0 at N = 1 only
