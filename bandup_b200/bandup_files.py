@@ -265,7 +265,7 @@ def write_orb_dependent_ebs(path, kpath: PcKptsPath, energy_grid: np.ndarray, va
 def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_file, energy_file,
                 out_file: Optional[str] = None, spin_channel: int = 1, unf_dens_op_file: Optional[str] = None,
                 normal_to_proj_plane: Sequence[float] = (0.0, 0.0, 1.0), origin_for_spin_proj=None,
-                projections=None, orb_out_file: Optional[str] = None):
+                projections=None, orb_out_file: Optional[str] = None, n_sckpts_to_skip: int = 0):
     """`bandup unfold` at file level for -no_symm_sckpts -no_symm_avg: parse the reference's input
     files, run every SC-kpt of the WAVECAR through the GPU (wavecar.unfold_wavecar) and write
     unfolded_EBS_not-symmetry_averaged.dat -- for a spinor WAVECAR with the reference's five spin
@@ -325,7 +325,10 @@ def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_f
     spinor_kpts, energies_of_job = set(), {}
     sc_k = np.array([wc.kpt_header(i + 1, spin_channel).kpt_frac_coords for i in range(wc.nkpts)])
     from .wavecar import fold_pckpts_onto_sckpts
-    folds = fold_pckpts_onto_sckpts(all_k, sc_k, wc.B_matrix)
+    fs, _, _ = unfolder.get_geom_unfolding_relations(all_k, sc_k @ wc.B_matrix, n_sckpts_to_skip=n_sckpts_to_skip)
+    folds = [[] for _ in range(wc.nkpts)]
+    for ik, s_ in enumerate(fs):
+        folds[int(s_)].append(ik)
     used = [i for i in range(wc.nkpts) if folds[i]]
     for j, i in enumerate(used):
         h = wc.kpt_header(i + 1, spin_channel)
@@ -333,7 +336,7 @@ def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_f
         file_kpt_of_job[j] = i + 1
 
     got, grid = unfold_wavecar(unfolder, wc, b_pc, all_k, e_start, e_end, de, ispin=spin_channel,
-                               after_fetch=after_fetch)
+                               after_fetch=after_fetch, n_sckpts_to_skip=n_sckpts_to_skip)
     n = all_k.shape[0]
     if got.row_ids.tolist() != list(range(n)):
         # main_BandUP.f90:114: every requested pc-kpt must have been unfolded exactly once

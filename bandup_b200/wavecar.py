@@ -250,7 +250,8 @@ def fold_pckpts_onto_sckpts(pc_kpts_cart: np.ndarray, sc_kpts_frac: np.ndarray, 
 
 def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_cart: np.ndarray,
                    E_start: float, E_end: float, delta_e: float, ispin: int = 1, rank: int = 0,
-                   world_size: int = 1, device=None, group=None, after_fetch=None, device_gvecs: bool = True):
+                   world_size: int = 1, device=None, group=None, after_fetch=None, device_gvecs: bool = True,
+                   n_sckpts_to_skip: int = 0):
     """The reference's main loop (main_BandUP.f90:131-177) over a WAVECAR under its no-symmetry
     flags (-no_symm_sckpts -no_symm_avg): every SC-kpt of the file, all pc-kpts folding onto it in
     one pass, raw band records read into two page-locked buffers and uploaded as they are while the
@@ -262,7 +263,10 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
     grid = unfolder.set_energy_grid(E_start, E_end, delta_e)
     sc_k = np.array([wavecar.kpt_header(i + 1, ispin).kpt_frac_coords for i in range(wavecar.nkpts)])
     if hasattr(unfolder, "get_geom_unfolding_relations"):     # K7 on the device
-        fs, _, _ = unfolder.get_geom_unfolding_relations(pc_kpts_cart, sc_k @ wavecar.B_matrix)
+        # -n_sckpts_to_skip: the first k-points of a hybrid-functional WAVECAR carry no bands
+        # (cla_wrappers_mod.f90:258-268, band_unfolding_routines_mod.f90:311-315)
+        fs, _, _ = unfolder.get_geom_unfolding_relations(pc_kpts_cart, sc_k @ wavecar.B_matrix,
+                                                         n_sckpts_to_skip=n_sckpts_to_skip)
         folds = [[] for _ in range(wavecar.nkpts)]
         for ik, s in enumerate(fs):
             folds[int(s)].append(ik)
