@@ -99,6 +99,12 @@ def load() -> C.CDLL:
         "bandup_gpu_set_perform_unfold": (C.c_int, [C.c_int, C.c_int]),
         "bandup_gpu_spectral_function": (C.c_int, [C.c_int, C.c_int, C.c_double, c_f64p]),
         "bandup_gpu_unfold_operator": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, c_f64p]),
+        "bandup_gpu_symm_average": (C.c_int, [C.c_int, C.c_int, C.c_int64, c_f64p, c_f64p, c_f64p]),
+        "bandup_gpu_symm_average_rho": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f64p, c_f64p,
+                                                  C.c_double, C.POINTER(C.c_int64), c_i32p, c_i32p, c_i32p, c_i32p,
+                                                  C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int64,
+                                                  C.POINTER(C.c_int64), c_i32p, c_i32p, c_i32p, c_i32p,
+                                                  C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "bandup_gpu_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "bandup_gpu_unfold_device": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_i32p,

@@ -20,7 +20,7 @@ LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libbandup_gpu.so"
 HOST_SRC = PKG / "host" / "bandup_unfold_gpu.cpp"
 HOST_EXE = LIBDIR / "BandUP_gpu.x"   # the native (C++) host above the C ABI: `bandup unfold` without symmetry
-SOURCES = ["capi.cu", "capi_projected.cu", "coset_classify.cu", "weights_reduce.cu", "delta_n.cu", "rho.cu", "gvecs.cu", "fold_map.cu", "comm.cu", "synth.cu"]
+SOURCES = ["capi.cu", "capi_projected.cu", "capi_symm.cu", "coset_classify.cu", "weights_reduce.cu", "delta_n.cu", "rho.cu", "symm_average.cu", "gvecs.cu", "fold_map.cu", "comm.cu", "synth.cu"]
 HEADERS = [CSRC / "kernels.cuh", CSRC / "ctx.cuh", CSRC / "nccl_dyn.h", PKG.parent / "include" / "bandup_gpu.h"]
 
 NVCC_FLAGS = [

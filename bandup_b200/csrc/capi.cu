@@ -420,6 +420,7 @@ int bandup_gpu_finalize(int handle) {
   }
   c->d_grid.release();
   c->d_operator.release();
+  c->avg_in.release(); c->avg_out.release(); c->avg_tmp.release();
   c->gvec_scratch.release();
   if (c->comm) nccl_api().CommDestroy(c->comm);
   c->comm_send.release();

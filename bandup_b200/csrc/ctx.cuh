@@ -111,6 +111,7 @@ struct Ctx {
   int comm_ranks = 0, comm_rank = -1;
   DevBuf comm_send, comm_recv;
   DevBuf gvec_scratch;  // per-CTA counts/offsets of the device plane-wave enumeration
+  DevBuf avg_in, avg_out, avg_tmp;  // symmetry averaging (K8/K9) staging
   DevBuf d_operator;  // current general operator O [n_bands][n_bands] complex128
   int operator_bands = 0;
   int nener = 0;

@@ -141,6 +141,22 @@ void launch_trace(int n_cells, int n_bands, const double* d_dN, const long long*
                   const RhoPair* d_pairs, const void* d_O, double min_abs_rho, int clip, double* d_out,
                   cudaStream_t s);
 
+// ---- symmetry averaging over the needed directions (symm_average.cu) ----------
+// K8: out[r] = sum_d w[d] * in[d][r], direction order, dp (get_delta_Ns_for_output :789-855, :975-1043)
+void launch_symm_average(const double* d_in, const double* d_w, int n_dirs, long long n_values, double* d_out,
+                         int sm_count, cudaStream_t s);
+// K9: symmetry-averaged unfolding-density operators (:857-973); plan = keys + first flags + scan
+// (d_scan has n+1 entries, d_scan[n] = number of averaged elements), merge = slots + values.
+void launch_symm_average_rho_plan(const int32_t* d_pck, const int32_t* d_ien, const int32_t* d_m1,
+                                  const int32_t* d_m2, long long n, const long long* d_dir_off, int n_dirs,
+                                  int n_pckpts, int nener, int n_bands, const double* d_avg_dN, double min_dN,
+                                  long long* d_key, int* d_flag, long long* d_scan, int* d_err, cudaStream_t s);
+void launch_symm_average_rho_merge(const long long* d_key, long long n, const long long* d_dir_off, int n_dirs,
+                                   int nener, int n_bands, const double* d_w, const float* d_re,
+                                   const float* d_im, const int* d_flag, const long long* d_scan,
+                                   int32_t* o_pck, int32_t* o_ien, int32_t* o_m1, int32_t* o_m2, float* o_re,
+                                   float* o_im, cudaStream_t s);
+
 void launch_synth_fill(void* d_coeffs, long long row_elems, int n_bands,
                        long long stride_bytes, uint64_t seed, uint64_t ikpt,
                        cudaStream_t s);

@@ -32,6 +32,9 @@ K_WEIGHTS = CONST["BANDUP_GPU_K_WEIGHTS"]
 K_FINALIZE = CONST["BANDUP_GPU_K_FINALIZE"]
 K_DELTA_N = CONST["BANDUP_GPU_K_DELTA_N"]
 K_RHO = CONST["BANDUP_GPU_K_RHO"]
+K_SYMM_AVG = CONST["BANDUP_GPU_K_SYMM_AVG"]
+# `if(symm_avg_dNs(iener) < 1E-3) cycle` (band_unfolding_routines_mod.f90:906): a default-real literal
+MIN_DN_SYMM_AVG = float(np.float32(1e-3))
 
 
 def _fortran_order(latt: np.ndarray) -> np.ndarray:
@@ -335,6 +338,55 @@ class GpuUnfolder:
             m1.ctypes.data_as(c_i32p), m2.ctypes.data_as(c_i32p), re.ctypes.data_as(f32p),
             im.ctypes.data_as(f32p)))
         return UnfoldDensityOps(ne.value, fold, iener, m1, m2, (re + 1j * im).astype(np.complex64))
+
+    # -- symmetry averaging over the needed directions ---------------------------
+    def symm_average(self, weights: np.ndarray, per_dir: np.ndarray) -> np.ndarray:
+        """The dense averaging loops of get_delta_Ns_for_output (band_unfolding_routines_mod.f90:826-853
+        delta_N; :984-1036 spin_proj_perp / spin_proj_para / sigma): sum_d weights[d] * per_dir[d],
+        accumulated in direction order in dp.  per_dir: (n_dirs, ...) -> (...)."""
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        x = np.ascontiguousarray(per_dir, dtype=np.float64)
+        if x.ndim < 1 or x.shape[0] != w.shape[0]:
+            raise ValueError("per_dir must have one leading slice per direction")
+        out = np.zeros(x.shape[1:], dtype=np.float64)
+        self._check(self._lib.bandup_gpu_symm_average(self.handle, w.shape[0], out.size,
+                                                      w.ctypes.data_as(c_f64p), x.ctypes.data_as(c_f64p),
+                                                      out.ctypes.data_as(c_f64p)))
+        return out
+
+    def symm_average_rho(self, weights: np.ndarray, per_dir: "list[UnfoldDensityOps]", avg_dN: np.ndarray,
+                         n_bands: int, min_dN: float = MIN_DN_SYMM_AVG) -> "UnfoldDensityOps":
+        """The symmetry average of the unfolding-density operators (band_unfolding_routines_mod.f90:
+        857-973).  per_dir[d]: the operators of direction d with `fold` = index of the pc-kpt along
+        the direction, in (fold, iener, m1, m2) order; avg_dN (n_pckpts, nener) the averaged delta_N.
+        Returns the averaged operators in the reference's element order."""
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        dn = np.ascontiguousarray(avg_dN, dtype=np.float64)
+        if dn.ndim != 2 or len(per_dir) != w.shape[0]:
+            raise ValueError("avg_dN must be (n_pckpts, nener) and per_dir one entry per direction")
+        off = np.zeros(len(per_dir) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(r.rho) for r in per_dir])
+        n = int(off[-1])
+        cat = lambda name, dt: np.ascontiguousarray(  # noqa: E731
+            np.concatenate([np.asarray(getattr(r, name)) for r in per_dir]) if n else np.zeros(0), dtype=dt)
+        fold, iener, m1, m2 = (cat(a, np.int32) for a in ("fold", "iener", "m1", "m2"))
+        rho = cat("rho", np.complex64)
+        re, im = np.ascontiguousarray(rho.real), np.ascontiguousarray(rho.imag)
+        outs = [np.zeros(max(n, 1), dtype=np.int32) for _ in range(4)]
+        ore, oim = np.zeros(max(n, 1), dtype=np.float32), np.zeros(max(n, 1), dtype=np.float32)
+        f32p = C.POINTER(C.c_float)
+        n_out = C.c_int64(0)
+        self._check(self._lib.bandup_gpu_symm_average_rho(
+            self.handle, w.shape[0], dn.shape[0], dn.shape[1], int(n_bands), w.ctypes.data_as(c_f64p),
+            dn.ctypes.data_as(c_f64p), float(min_dN), off.ctypes.data_as(C.POINTER(C.c_int64)),
+            *[a.ctypes.data_as(c_i32p) for a in (fold, iener, m1, m2)], re.ctypes.data_as(f32p),
+            im.ctypes.data_as(f32p), n, C.byref(n_out), *[a.ctypes.data_as(c_i32p) for a in outs],
+            ore.ctypes.data_as(f32p), oim.ctypes.data_as(f32p)))
+        m = n_out.value
+        o_fold, o_iener = outs[0][:m].copy(), outs[1][:m].copy()
+        n_ops = int(np.unique(o_fold.astype(np.int64) * dn.shape[1] + o_iener).size)
+        return UnfoldDensityOps(n_ops, o_fold, o_iener, outs[2][:m].copy(), outs[3][:m].copy(),
+                                (ore[:m] + 1j * oim[:m]).astype(np.complex64))
 
     def pauli_vectors(self, ikpt: int, n_fold: int) -> np.ndarray:
         """unf_pauli_vec = Re Tr(rho . sigma_i) for every (pc-kpt, energy) with a rho

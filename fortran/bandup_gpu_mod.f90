@@ -25,6 +25,7 @@ public :: bandup_gpu_init, bandup_gpu_finalize, bandup_gpu_last_error, &
           bandup_gpu_rho_count, bandup_gpu_fetch_rho, bandup_gpu_pauli_vectors, &
           bandup_gpu_spectral_function, bandup_gpu_set_perform_unfold, &
           bandup_gpu_orb_contrib_matrix, bandup_gpu_set_operator, bandup_gpu_unfold_operator, &
+          bandup_gpu_symm_average, bandup_gpu_symm_average_rho, &
           bandup_gpu_comm_unique_id, bandup_gpu_comm_init, bandup_gpu_comm_finalize, bandup_gpu_gather_dN, &
           bandup_gpu_unfold_kpt_f, bandup_gpu_error_message
 public :: BANDUP_GPU_OK, BANDUP_GPU_LAYOUT_FORTRAN_INMEM, BANDUP_GPU_LAYOUT_VASP_RECORD, &
@@ -196,6 +197,37 @@ interface
         real(c_float), intent(out) :: rho_re(*), rho_im(*)
         integer(c_int) :: bandup_gpu_fetch_rho
     end function bandup_gpu_fetch_rho
+
+    ! symmetry average over the needed directions (get_delta_Ns_for_output,
+    ! band_unfolding_routines_mod.f90:826-853, :984-1036): out(r) = sum_d weights(d)*x(r,d)
+    function bandup_gpu_symm_average(handle, n_dirs, n_values, weights, x, out) &
+        bind(c, name='bandup_gpu_symm_average')
+        import c_int, c_int64_t, c_double
+        integer(c_int), intent(in), value :: handle, n_dirs
+        integer(c_int64_t), intent(in), value :: n_values
+        real(c_double), intent(in) :: weights(*), x(*)
+        real(c_double), intent(out) :: out(*)
+        integer(c_int) :: bandup_gpu_symm_average
+    end function bandup_gpu_symm_average
+
+    ! symmetry-averaged unfolding-density operators (:857-973); avg_dN(nener, n_pckpts)
+    function bandup_gpu_symm_average_rho(handle, n_dirs, n_pckpts, nener, n_bands, weights, avg_dN, min_dN, &
+                                         dir_offsets, pckpt, iener, m1, m2, rho_re, rho_im, capacity, n_out, &
+                                         pckpt_out, iener_out, m1_out, m2_out, rho_re_out, rho_im_out) &
+        bind(c, name='bandup_gpu_symm_average_rho')
+        import c_int, c_int64_t, c_int32_t, c_double, c_float
+        integer(c_int), intent(in), value :: handle, n_dirs, n_pckpts, nener, n_bands
+        real(c_double), intent(in) :: weights(*), avg_dN(*)
+        real(c_double), intent(in), value :: min_dN
+        integer(c_int64_t), intent(in) :: dir_offsets(*)
+        integer(c_int32_t), intent(in) :: pckpt(*), iener(*), m1(*), m2(*)
+        real(c_float), intent(in) :: rho_re(*), rho_im(*)
+        integer(c_int64_t), intent(in), value :: capacity
+        integer(c_int64_t), intent(out) :: n_out
+        integer(c_int32_t), intent(out) :: pckpt_out(*), iener_out(*), m1_out(*), m2_out(*)
+        real(c_float), intent(out) :: rho_re_out(*), rho_im_out(*)
+        integer(c_int) :: bandup_gpu_symm_average_rho
+    end function bandup_gpu_symm_average_rho
 
     ! spinor wavefunctions: sigma(3, nener, n_fold) = Re Tr(rho . sigma_i)
     ! (get_SC_pauli_matrix_elmnts + band_unfolding_routines_mod.f90:1459-1481)

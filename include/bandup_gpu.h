@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BANDUP_GPU_ABI_VERSION 3
+#define BANDUP_GPU_ABI_VERSION 4
 
 /* status codes */
 #define BANDUP_GPU_OK 0
@@ -260,6 +260,40 @@ int bandup_gpu_set_operator(int handle, int n_bands, const double *O);
  * out [n_fold][nener] HOST. */
 int bandup_gpu_unfold_operator(int handle, int ikpt, double min_abs_rho, int clip, double *out);
 
+/* ---- symmetry averaging over the needed directions ---------------------- */
+/* After the SC-kpt loop the reference averages what every pc-kpt got along the symmetry-
+ * equivalent ("needed") directions of its pc-BZ direction, with the directions' weights
+ * (get_delta_Ns_for_output, band_unfolding_routines_mod.f90:789-1043).  The directions and their
+ * weights come from the caller's symmetry analysis (spglib in BandUP); with -no_symm_avg there
+ * is one direction of weight 1 and these calls are the identity.
+ *
+ * bandup_gpu_symm_average replaces the dense loops (:826-853 delta_N; :984-1036 spin_proj_perp,
+ * spin_proj_para, sigma):  out[r] = sum_d weights[d] * in[d][r], accumulated in dp in direction
+ * order exactly as `avrgd = avrgd + weight*x` does.  in [n_dirs][n_values], out [n_values], HOST. */
+int bandup_gpu_symm_average(int handle, int n_dirs, int64_t n_values, const double *weights,
+                            const double *in, double *out);
+/* Replaces the symmetry average of the unfolding-density operators (:857-973).  Input: the stored
+ * elements of all n_dirs directions concatenated, direction d = [dir_offsets[d], dir_offsets[d+1]),
+ * each direction in the order bandup_gpu_fetch_rho returns them (pckpt, iener ascending, m1 outer,
+ * m2 inner; no element twice) with `pckpt` the 0-based index of the pc-kpt along the direction
+ * (< n_pckpts), iener/m1/m2 1-based.  avg_dN [n_pckpts][nener] is the symmetry-averaged delta_N
+ * (bandup_gpu_symm_average); operators at energies with avg_dN < min_dN are dropped (:906, the
+ * reference's literal 1E-3 is default real: pass (double)1e-3f for bit parity).  Every remaining
+ * (m1,m2) is created by the first direction that stores it as cmplx(weight*rho, kind=sp) and
+ * updated by the later ones as sp(dp(avg) + weight*rho) (:934-957).
+ * Output (HOST, `capacity` entries each; capacity = dir_offsets[n_dirs] always suffices): the
+ * averaged elements by (pckpt, iener) and, inside one operator, in the reference's append order
+ * (direction, then m1 outer, m2 inner).  *n_out = their number; when it exceeds `capacity` nothing
+ * is copied and BANDUP_GPU_ERR_INVALID_ARG is returned.  Unsorted input is ERR_INVALID_ARG. */
+int bandup_gpu_symm_average_rho(int handle, int n_dirs, int n_pckpts, int nener, int n_bands,
+                                const double *weights, const double *avg_dN, double min_dN,
+                                const int64_t *dir_offsets, const int32_t *pckpt,
+                                const int32_t *iener, const int32_t *m1, const int32_t *m2,
+                                const float *rho_re, const float *rho_im, int64_t capacity,
+                                int64_t *n_out, int32_t *pckpt_out, int32_t *iener_out,
+                                int32_t *m1_out, int32_t *m2_out, float *rho_re_out,
+                                float *rho_im_out);
+
 /* ---- per SC-k-point, device-resident buffers ---------------------------- */
 
 /* Scratch bytes unfold_device needs for these sizes. */
@@ -332,7 +366,8 @@ int bandup_gpu_gather_dN(int handle, const double *dN_local, const int64_t *row_
 #define BANDUP_GPU_K_FINALIZE 2
 #define BANDUP_GPU_K_DELTA_N 3
 #define BANDUP_GPU_K_RHO 4
-#define BANDUP_GPU_K_COUNT 5
+#define BANDUP_GPU_K_SYMM_AVG 5
+#define BANDUP_GPU_K_COUNT 6
 
 /* When enabled, every launch is bracketed by CUDA events on its own stream. */
 int bandup_gpu_set_profiling(int handle, int enabled);

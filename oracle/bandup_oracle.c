@@ -478,6 +478,95 @@ int bo_calc_rho(const float complex *coeffs, int n_spinor, int64_t n_pw,
   return 0;
 }
 
+/* ---- band_unfolding_routines_mod.f90:789-855, :975-1043  symmetry average --
+ * avrgd = 0; do i_needed_dirs: avrgd = avrgd + weight * x(i_needed_dirs) -- dp, direction order.
+ * in [n_dirs][n_values], out [n_values]. */
+void bo_symm_average(const double *weights, int n_dirs, int64_t n_values,
+                     const double *in, double *out) {
+  for (int64_t r = 0; r < n_values; ++r) {
+    double acc = 0.0;
+    for (int d = 0; d < n_dirs; ++d) {
+      volatile double t = weights[d] * in[(int64_t)d * n_values + r]; /* no fma contraction */
+      acc = acc + t;
+    }
+    out[r] = acc;
+  }
+}
+
+/* ---- band_unfolding_routines_mod.f90:857-973  symmetry-averaged rho --------
+ * Entries of all directions concatenated, direction d = [dir_off[d], dir_off[d+1]), each
+ * direction in the reference's append order (pckpt, energy ascending, m1 outer, m2 inner;
+ * pckpt 0-based, iener/m1/m2 1-based).  Operators at energies whose AVERAGED delta_N is below
+ * min_dN are skipped (:906; the literal 1E-3 is default real).  The first direction holding
+ * (m1,m2) creates the element as cmplx(weight*rho, kind=sp) (:934-941), later ones add
+ * weight*rho in dp and store to sp (:952-957).  Output: (pckpt, iener) ascending and, inside an
+ * operator, the reference's append order (direction, then m1/m2).  Returns the number of
+ * averaged entries (<= dir_off[n_dirs], which is the capacity the caller provides). */
+typedef struct {
+  int64_t group, pair, seq;
+  float re, im;
+} bo_avg_entry;
+
+static int bo_avg_cmp(const void *a, const void *b) {
+  const bo_avg_entry *x = (const bo_avg_entry *)a, *y = (const bo_avg_entry *)b;
+  if (x->group != y->group) return x->group < y->group ? -1 : 1;
+  return x->seq < y->seq ? -1 : (x->seq > y->seq ? 1 : 0);
+}
+
+int64_t bo_symm_average_rho(const double *weights, int n_dirs, int nener, int n_bands,
+                            const double *avg_dN, double min_dN, const int64_t *dir_off,
+                            const int32_t *pckpt, const int32_t *iener, const int32_t *m1,
+                            const int32_t *m2, const float *rho_re, const float *rho_im,
+                            int32_t *pckpt_out, int32_t *iener_out, int32_t *m1_out,
+                            int32_t *m2_out, float *re_out, float *im_out) {
+  const int64_t n_in = dir_off[n_dirs];
+  if (n_in == 0) return 0;
+  bo_avg_entry *out = (bo_avg_entry *)malloc(sizeof(bo_avg_entry) * (size_t)n_in);
+  int64_t cap = 16;
+  while (cap < 2 * n_in) cap <<= 1;
+  int64_t *table = (int64_t *)malloc(sizeof(int64_t) * (size_t)cap); /* open addressing -> out index */
+  for (int64_t i = 0; i < cap; ++i) table[i] = -1;
+  int64_t n_out = 0;
+  for (int d = 0; d < n_dirs; ++d) {
+    for (int64_t i = dir_off[d]; i < dir_off[d + 1]; ++i) {
+      const int64_t group = (int64_t)pckpt[i] * nener + (iener[i] - 1);
+      if (avg_dN[group] < min_dN) continue;
+      const int64_t pair = (int64_t)(m1[i] - 1) * n_bands + (m2[i] - 1);
+      uint64_t h = ((uint64_t)group * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)pair * 0xC2B2AE3D27D4EB4Full);
+      int64_t slot = (int64_t)(h & (uint64_t)(cap - 1));
+      while (table[slot] >= 0 && !(out[table[slot]].group == group && out[table[slot]].pair == pair))
+        slot = (slot + 1) & (cap - 1);
+      const double tr = weights[d] * (double)rho_re[i], ti = weights[d] * (double)rho_im[i];
+      if (table[slot] < 0) {
+        table[slot] = n_out;
+        out[n_out].group = group;
+        out[n_out].pair = pair;
+        out[n_out].seq = n_out;
+        out[n_out].re = (float)tr;
+        out[n_out].im = (float)ti;
+        ++n_out;
+      } else {
+        bo_avg_entry *e = &out[table[slot]];
+        volatile double sr = (double)e->re + tr, si = (double)e->im + ti;
+        e->re = (float)sr;
+        e->im = (float)si;
+      }
+    }
+  }
+  qsort(out, (size_t)n_out, sizeof(bo_avg_entry), bo_avg_cmp);
+  for (int64_t i = 0; i < n_out; ++i) {
+    pckpt_out[i] = (int32_t)(out[i].group / nener);
+    iener_out[i] = (int32_t)(out[i].group % nener) + 1;
+    m1_out[i] = (int32_t)(out[i].pair / n_bands) + 1;
+    m2_out[i] = (int32_t)(out[i].pair % n_bands) + 1;
+    re_out[i] = out[i].re;
+    im_out[i] = out[i].im;
+  }
+  free(table);
+  free(out);
+  return n_out;
+}
+
 /* ---- Integer coset test (the arithmetic the GPU kernel uses; NOT in the
  * reference).  Used by tests to assert float selection == integer selection.
  * adjT = adjugate(transpose(M)) (integer), D = |det M|.

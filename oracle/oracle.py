@@ -74,6 +74,12 @@ def lib() -> C.CDLL:
         L.bo_synth_fill.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64]
         L.bo_synth_fill_rows.restype = None
         L.bo_synth_fill_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
+        L.bo_symm_average.restype = None
+        L.bo_symm_average.argtypes = [_f64p, C.c_int, C.c_int64, _f64p, _f64p]
+        _f32p = C.POINTER(C.c_float)
+        L.bo_symm_average_rho.restype = C.c_int64
+        L.bo_symm_average_rho.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, _f64p, C.c_double, _i64p] + \
+            [_i32p] * 4 + [_f32p] * 2 + [_i32p] * 4 + [_f32p] * 2
         L.bo_num_threads.restype = C.c_int
         L.bo_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -227,3 +233,34 @@ def synth_fill(row_elems, n_bands, seed, ikpt, band0=0, out=None):
     lib().bo_synth_fill_rows(c.ctypes.data, int(row_elems), int(band0), int(n_bands), C.c_uint64(seed),
                              C.c_uint64(ikpt))
     return c
+
+
+def symm_average(weights, per_dir):
+    """out = sum_d weights[d] * per_dir[d], accumulated in direction order (dp)."""
+    w = _f64(weights)
+    x = _f64(per_dir)
+    out = np.zeros(x.shape[1:])
+    lib().bo_symm_average(_p(w, _f64p), w.shape[0], out.size, _p(x, _f64p), _p(out, _f64p))
+    return out
+
+
+def symm_average_rho(weights, dir_off, pckpt, iener, m1, m2, rho, avg_dN, n_bands, min_dN=None):
+    """Symmetry-averaged unfolding-density operators; see bo_symm_average_rho.  rho complex64.
+    Returns (pckpt, iener, m1, m2, rho) arrays of the averaged entries."""
+    if min_dN is None:
+        min_dN = float(np.float32(1e-3))
+    w = _f64(weights)
+    off = np.ascontiguousarray(dir_off, dtype=np.int64)
+    ints = [np.ascontiguousarray(a, dtype=np.int32) for a in (pckpt, iener, m1, m2)]
+    r = np.ascontiguousarray(rho, dtype=np.complex64)
+    re, im = np.ascontiguousarray(r.real), np.ascontiguousarray(r.imag)
+    dn = _f64(avg_dN)
+    n = int(off[-1])
+    outs = [np.zeros(max(n, 1), dtype=np.int32) for _ in range(4)]
+    ore, oim = np.zeros(max(n, 1), dtype=np.float32), np.zeros(max(n, 1), dtype=np.float32)
+    f32p = C.POINTER(C.c_float)
+    m = lib().bo_symm_average_rho(_p(w, _f64p), w.shape[0], dn.shape[1], int(n_bands), _p(dn, _f64p),
+                                  float(min_dN), _p(off, _i64p), *[_p(a, _i32p) for a in ints],
+                                  _p(re, f32p), _p(im, f32p), *[_p(a, _i32p) for a in outs],
+                                  _p(ore, f32p), _p(oim, f32p))
+    return tuple(a[:m].copy() for a in outs) + ((ore[:m] + 1j * oim[:m]).astype(np.complex64),)

@@ -257,3 +257,34 @@ def test_spectral_function_c_vs_numpy():
     inside = (ener > -2.5) & (ener < 1.5)
     fine = O.real_seq(-4.5, 3.5, 0.002)
     assert abs(np.sum(O.spectral_function(fine, ener[inside], w[inside], 0.025)) * 0.002 - w[inside].sum()) < 1e-6
+
+
+# ---- symmetry averaging over the needed directions (band_unfolding_routines_mod.f90:789-1043) ----
+def test_symm_average_c_equals_numpy_twin():
+    from tests._symm_cases import make_case
+    case = make_case()
+    a = O.symm_average(case["weights"], case["dN"])
+    b = ON.symm_average(case["weights"], case["dN"])
+    assert np.array_equal(a, b)
+    one = O.symm_average([1.0], case["dN"][:1])              # -no_symm_avg: one direction of weight 1
+    assert np.array_equal(one, case["dN"][0])
+
+
+@pytest.mark.parametrize("seed,n_dirs,equal", [(7, 4, False), (8, 1, False), (9, 6, True)])
+def test_symm_average_rho_c_equals_numpy_twin(seed, n_dirs, equal):
+    from tests._symm_cases import make_case
+    case = make_case(seed=seed, n_dirs=n_dirs, equal_weights=equal)
+    avg = O.symm_average(case["weights"], case["dN"])
+    ref = ON.symm_average_rho(case["weights"], case["per_dir"], avg)
+    got = O.symm_average_rho(case["weights"], case["off"], *case["cols"], avg, case["nb"])
+    assert len(ref) == len(got[0]) > 0
+    for i, r in enumerate(ref):
+        assert r[:4] == tuple(int(got[c][i]) for c in range(4))
+        assert r[4] == got[4][i]                             # bit-equal complex64
+    # energies below the averaged-delta_N cut carry no operator
+    kept = {(int(k), int(e)) for k, e in zip(got[0], got[1])}
+    assert all(avg[k, e - 1] >= ON.MIN_DN_SYMM_AVG for k, e in kept)
+    if n_dirs == 1:                                          # weight 1: the surviving operators unchanged
+        k, e, m1, m2, rho = case["cols"]
+        keep = avg[k, e - 1] >= ON.MIN_DN_SYMM_AVG
+        assert np.array_equal(got[4], rho[keep]) and np.array_equal(got[2], m1[keep])
