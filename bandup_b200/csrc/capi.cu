@@ -1012,7 +1012,14 @@ int bandup_gpu_fetch_kpt(int handle, int ikpt, double* weights, double* dN, int3
 int bandup_gpu_set_profiling(int handle, int enabled) {
   Ctx* c = get(handle);
   if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  c->profiling = enabled != 0;
+  c->profiling = enabled != 0 ? ~0u : 0u;
+  return BANDUP_GPU_OK;
+}
+
+int bandup_gpu_set_profiling_mask(int handle, unsigned kernel_mask) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  c->profiling = kernel_mask;
   return BANDUP_GPU_OK;
 }
 

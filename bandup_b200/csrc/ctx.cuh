@@ -119,7 +119,7 @@ struct Ctx {
   Flight flights[kDepth];
   int next_flight = 0;
   int chunk_vecs = 0, ctas_per_sm = 0, n_stages = 0;
-  bool profiling = false;
+  unsigned profiling = 0;  // bit k: launches of kernel id k are bracketed by events
   bool perform_unfold = true;  // args%perform_unfold; false == -dont_unfold
   std::vector<cudaEvent_t> event_pool;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[BANDUP_GPU_K_COUNT];
@@ -155,7 +155,7 @@ struct KernelScope {  // brackets one launch with events when profiling is on
   cudaEvent_t a = nullptr, b = nullptr;
   KernelScope(Ctx* c_, int which_, cudaStream_t s_) : c(c_), which(which_), s(s_) {
     c->launches++;
-    if (c->profiling) {
+    if (c->profiling >> which & 1u) {
       a = take_event(c);
       b = take_event(c);
       cudaEventRecord(a, s);

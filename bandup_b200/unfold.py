@@ -515,8 +515,15 @@ class GpuUnfolder:
         return out, oid
 
     # -- instrumentation ------------------------------------------------------
-    def set_profiling(self, enabled: bool) -> None:
-        self._check(self._lib.bandup_gpu_set_profiling(self.handle, int(bool(enabled))))
+    def set_profiling(self, enabled: bool, kernels=None) -> None:
+        """Bracket launches with CUDA events; `kernels` (ids) restricts it to those kernels."""
+        if enabled and kernels is not None:
+            mask = 0
+            for k in kernels:
+                mask |= 1 << int(k)
+            self._check(self._lib.bandup_gpu_set_profiling_mask(self.handle, mask))
+        else:
+            self._check(self._lib.bandup_gpu_set_profiling(self.handle, int(bool(enabled))))
 
     def reset_kernel_times(self) -> None:
         self._check(self._lib.bandup_gpu_reset_kernel_times(self.handle))

@@ -371,6 +371,10 @@ int bandup_gpu_gather_dN(int handle, const double *dN_local, const int64_t *row_
 
 /* When enabled, every launch is bracketed by CUDA events on its own stream. */
 int bandup_gpu_set_profiling(int handle, int enabled);
+/* Same, for the kernels whose id bit is set only (bit k = kernel id k): an event pair between two
+ * back-to-back launches costs a few microseconds of device time, so a timed region that wants one
+ * kernel's duration brackets that kernel alone. */
+int bandup_gpu_set_profiling_mask(int handle, unsigned kernel_mask);
 /* Synchronises the device, then returns summed milliseconds and launch count
  * of kernel `which` since the last reset. */
 int bandup_gpu_kernel_time(int handle, int which, double *total_ms,
