@@ -129,7 +129,10 @@ namespace {
 struct FoldPlan {
   int n_unique = 0;
   std::vector<int> unique_of;  // user fold (pc-kpt) -> unique fold (distinct coset)
-  int fold_key[kMaxFolds][3];  // key(g0) of every unique fold
+  std::vector<int> fold_key;   // key(g0) of every unique fold, 3 ints each
+  // more than kMaxFolds distinct cosets are worked off in passes of kMaxFolds (K2's bins are
+  // sized for that many); pass p holds the unique folds [p*kMaxFolds, (p+1)*kMaxFolds)
+  int passes() const { return n_unique > 0 ? (n_unique + kMaxFolds - 1) / kMaxFolds : 1; }
 };
 
 int plan_folds(Ctx* c, int n_fold, const int32_t* g0, FoldPlan* plan) {
@@ -137,23 +140,19 @@ int plan_folds(Ctx* c, int n_fold, const int32_t* g0, FoldPlan* plan) {
     return fail(c, BANDUP_GPU_ERR_TOO_MANY_FOLDS,
                 "n_fold must be in 1.." + std::to_string(BANDUP_GPU_MAX_PCKPTS) + ", got " + std::to_string(n_fold));
   plan->n_unique = 0;
+  plan->fold_key.clear();
   plan->unique_of.assign((size_t)n_fold, 0);
   for (int f = 0; f < n_fold; ++f) {
     int key[3];
     coset_key(g0 + 3 * f, c->coset.adjT, c->coset.D, key);
     int u = -1;
     for (int q = 0; q < plan->n_unique; ++q)
-      if (plan->fold_key[q][0] == key[0] && plan->fold_key[q][1] == key[1] &&
-          plan->fold_key[q][2] == key[2])
+      if (plan->fold_key[3 * q] == key[0] && plan->fold_key[3 * q + 1] == key[1] &&
+          plan->fold_key[3 * q + 2] == key[2])
         u = q;
     if (u < 0) {
-      if (plan->n_unique == kMaxFolds)
-        return fail(c, BANDUP_GPU_ERR_TOO_MANY_FOLDS,
-                    "more than " + std::to_string(kMaxFolds) + " distinct cosets among the pc-kpts of one submit");
       u = plan->n_unique++;
-      plan->fold_key[u][0] = key[0];
-      plan->fold_key[u][1] = key[1];
-      plan->fold_key[u][2] = key[2];
+      plan->fold_key.insert(plan->fold_key.end(), key, key + 3);
     }
     plan->unique_of[f] = u;
   }
@@ -162,6 +161,8 @@ int plan_folds(Ctx* c, int n_fold, const int32_t* g0, FoldPlan* plan) {
 
 struct WorkspaceLayout {
   size_t slot_off, slot_shift_off, counts_off, partials_off, tmp_w_off, tmp_dn_off, tmp_ns_off, total;
+  size_t slot_pitch;  // bytes between the slot tables of two passes
+  size_t band_chunks; // n_bands * n_chunks: doubles per fold row of the K2 partials
 };
 
 // batch_n: k-points launched together -- the K2 tile size is chosen so that the WHOLE launch
@@ -176,15 +177,19 @@ WorkspaceLayout workspace_layout(const Ctx* c, int n_spinor, int n_pw, int n_ban
   WorkspaceLayout w;
   const int cv = pick_chunk_vecs(c, (long long)n_pw * n_spinor, n_bands, batch_n);
   const int n_chunks = weights_num_chunks((long long)n_pw * n_spinor, cv);
+  // distinct cosets <= pc-kpts: room for the worst case number of passes
+  const size_t max_passes = (size_t)((n_fold > 0 ? n_fold : 1) + kMaxFolds - 1) / kMaxFolds;
   size_t off = 0;
+  w.slot_pitch = align256((size_t)(n_pw > 0 ? n_pw : 1));
+  w.band_chunks = (size_t)n_bands * (size_t)n_chunks;
   w.slot_off = off;
-  off += align256((size_t)(n_pw > 0 ? n_pw : 1));
+  off += w.slot_pitch * max_passes;
   w.slot_shift_off = off;
-  off += align256((size_t)(n_pw > 0 ? n_pw : 1));
+  off += w.slot_pitch * max_passes;
   w.counts_off = off;
   off += align256(sizeof(int) * (size_t)kK1MaxBlocks * (size_t)n_fold);
-  w.partials_off = off;
-  off += align256(weights_partials_bytes(n_bands, n_chunks, n_fold));
+  w.partials_off = off;  // every pass: (its folds + 1 norm row) * band_chunks doubles
+  off += align256(weights_partials_bytes(n_bands, n_chunks, n_fold) + sizeof(double) * w.band_chunks * (max_passes - 1));
   // scratch rows used only when two requested pc-kpts share a coset
   w.tmp_w_off = off;
   off += align256(sizeof(double) * (size_t)n_fold * (size_t)(n_bands > 0 ? n_bands : 1));
@@ -207,7 +212,7 @@ struct BatchItem {  // one SC k-point of a launch batch (host side)
   double* d_dN = nullptr;
   int32_t* d_nsel = nullptr;
   double* d_norms = nullptr;
-  uint8_t* d_slot_out = nullptr;
+  uint8_t* d_slot_out = nullptr;  // [passes][n_pw] (the public entry points allow one pass only)
   char* ws = nullptr;
   // outputs of run_batch: where the per-distinct-coset rows live
   const double* dn_unique = nullptr;
@@ -249,81 +254,93 @@ KptGeom* stage_descriptors(Ctx* c, cudaStream_t s, const std::vector<KptGeom>& g
 int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
   const int n = (int)items.size();
   if (n == 0) return BANDUP_GPU_OK;
-  std::vector<KptGeom> geoms((size_t)n);
+  std::vector<KptGeom> geoms;  // one per (k-point, pass of <= kMaxFolds distinct cosets)
+  geoms.reserve((size_t)n);
   long long tiles = 0;
   int max_fold = 0, max_bands = 0, max_pw = 0;
-  bool any_dup = false;
   for (int i = 0; i < n; ++i) {
     BatchItem& it = items[(size_t)i];
     if (it.n_spinor != items[0].n_spinor || it.layout != items[0].layout)
       return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "all k-points of a batch must share n_spinor and layout");
     const WorkspaceLayout wl = workspace_layout(c, it.n_spinor, it.n_pw, it.n_bands, it.n_fold, n);
     const bool dup = it.plan.n_unique != it.n_fold;
-    any_dup = any_dup || dup;
-    KptGeom& g = geoms[(size_t)i];
-    g.coeffs = static_cast<const char*>(it.d_coeffs);
-    g.stride_bytes = it.stride_bytes;
-    g.row_elems = (long long)it.n_pw * it.n_spinor;
-    g.n_bands = it.n_bands;
-    g.n_pw = it.n_pw;
-    g.n_spinor = it.n_spinor;
-    g.layout = it.layout;
-    g.g_frac = it.d_gfrac;
-    g.energies = it.d_energies;
-    g.slot = reinterpret_cast<uint8_t*>(it.ws + wl.slot_off);
-    g.slot_shift = reinterpret_cast<uint8_t*>(it.ws + wl.slot_shift_off);
-    g.block_counts = reinterpret_cast<int*>(it.ws + wl.counts_off);
-    g.n_selected = dup ? reinterpret_cast<int32_t*>(it.ws + wl.tmp_ns_off) : it.d_nsel;
-    g.n_fold = it.plan.n_unique;
-    g.chunk_vecs = pick_chunk_vecs(c, g.row_elems, it.n_bands, n);
-    g.n_chunks = weights_num_chunks(g.row_elems, g.chunk_vecs);
-    g.perform_unfold = c->perform_unfold ? 1 : 0;
-    g.tile_begin = tiles;
-    tiles += (long long)it.n_bands * g.n_chunks;
-    g.partials = reinterpret_cast<double*>(it.ws + wl.partials_off);
-    g.weights = dup ? reinterpret_cast<double*>(it.ws + wl.tmp_w_off) : it.d_weights;
-    g.norms = it.d_norms;
-    g.dN = dup ? reinterpret_cast<double*>(it.ws + wl.tmp_dn_off) : it.d_dN;
-    std::memcpy(g.fold_key, it.plan.fold_key, sizeof(g.fold_key));
-    it.dn_unique = g.dN;
-    it.w_unique = g.weights;
-    it.ns_unique = g.n_selected;
-    it.d_slot = g.slot;
-    if (g.n_fold > max_fold) max_fold = g.n_fold;
+    double* w_rows = dup ? reinterpret_cast<double*>(it.ws + wl.tmp_w_off) : it.d_weights;
+    double* dn_rows = dup ? reinterpret_cast<double*>(it.ws + wl.tmp_dn_off) : it.d_dN;
+    int32_t* ns_rows = dup ? reinterpret_cast<int32_t*>(it.ws + wl.tmp_ns_off) : it.d_nsel;
+    it.dn_unique = dn_rows;
+    it.w_unique = w_rows;
+    it.ns_unique = ns_rows;
+    it.d_slot = reinterpret_cast<uint8_t*>(it.ws + wl.slot_off);
+    const int passes = it.plan.passes();
+    for (int p = 0; p < passes; ++p) {
+      const int u0 = p * kMaxFolds;
+      const int nf = std::min(kMaxFolds, it.plan.n_unique - u0);
+      KptGeom g{};
+      g.coeffs = static_cast<const char*>(it.d_coeffs);
+      g.stride_bytes = it.stride_bytes;
+      g.row_elems = (long long)it.n_pw * it.n_spinor;
+      g.n_bands = it.n_bands;
+      g.n_pw = it.n_pw;
+      g.n_spinor = it.n_spinor;
+      g.layout = it.layout;
+      g.g_frac = it.d_gfrac;
+      g.energies = it.d_energies;
+      g.slot = reinterpret_cast<uint8_t*>(it.ws + wl.slot_off + wl.slot_pitch * (size_t)p);
+      g.slot_shift = reinterpret_cast<uint8_t*>(it.ws + wl.slot_shift_off + wl.slot_pitch * (size_t)p);
+      g.block_counts = reinterpret_cast<int*>(it.ws + wl.counts_off) + (size_t)kK1MaxBlocks * (size_t)u0;
+      g.n_selected = ns_rows + u0;
+      g.n_fold = nf;
+      g.chunk_vecs = pick_chunk_vecs(c, g.row_elems, it.n_bands, n);
+      g.n_chunks = weights_num_chunks(g.row_elems, g.chunk_vecs);
+      g.perform_unfold = c->perform_unfold ? 1 : 0;
+      g.tile_begin = tiles;
+      tiles += (long long)it.n_bands * g.n_chunks;
+      g.partials = reinterpret_cast<double*>(it.ws + wl.partials_off) + wl.band_chunks * (size_t)(u0 + p);
+      g.weights = w_rows + (size_t)u0 * it.n_bands;
+      g.norms = p == 0 ? it.d_norms : nullptr;  // every pass renormalises; one writes the norms out
+      g.dN = dn_rows + (size_t)u0 * c->nener;
+      std::memcpy(g.fold_key, it.plan.fold_key.data() + 3 * (size_t)u0, sizeof(int) * 3 * (size_t)nf);
+      geoms.push_back(g);
+      if (nf > max_fold) max_fold = nf;
+    }
     if (it.n_bands > max_bands) max_bands = it.n_bands;
     if (it.n_pw > max_pw) max_pw = it.n_pw;
   }
+  const int n_geoms = (int)geoms.size();
   cudaError_t e = cudaSuccess;
   const KptGeom* d_geoms = stage_descriptors(c, s, geoms, &e);
   if (!d_geoms) return cuda_fail(c, e, "staging the batch descriptors");
   const CosetCommon cc = c->coset;
   {
     KernelScope k(c, BANDUP_GPU_K_COSET, s);
-    launch_coset_classify(d_geoms, n, max_pw, cc, s);
+    launch_coset_classify(d_geoms, n_geoms, max_pw, cc, s);
   }
   {
     KernelScope k(c, BANDUP_GPU_K_WEIGHTS, s);
-    launch_weights_reduce(d_geoms, n, tiles, max_fold, items[0].n_spinor, items[0].layout, c->ctas_per_sm,
+    launch_weights_reduce(d_geoms, n_geoms, tiles, max_fold, items[0].n_spinor, items[0].layout, c->ctas_per_sm,
                           c->n_stages, c->sm_count, s);
   }
   {
     KernelScope k(c, BANDUP_GPU_K_FINALIZE, s);
-    launch_weights_finalize(d_geoms, n, max_bands, max_fold, s);
+    launch_weights_finalize(d_geoms, n_geoms, max_bands, max_fold, s);
   }
   {
     KernelScope k(c, BANDUP_GPU_K_DELTA_N, s);
-    launch_delta_n(d_geoms, n, max_fold, static_cast<const double*>(c->d_grid.p), c->nener, c->sigma, s);
+    launch_delta_n(d_geoms, n_geoms, max_fold, static_cast<const double*>(c->d_grid.p), c->nener, c->sigma, s);
   }
   CU(cudaGetLastError());
   for (int i = 0; i < n; ++i) {
     BatchItem& it = items[(size_t)i];
-    if (it.d_slot_out)
-      CU(cudaMemcpyAsync(it.d_slot_out, it.d_slot, (size_t)it.n_pw, cudaMemcpyDeviceToDevice, s));
+    if (it.d_slot_out) {
+      const WorkspaceLayout wl = workspace_layout(c, it.n_spinor, it.n_pw, it.n_bands, it.n_fold, n);
+      CU(cudaMemcpy2DAsync(it.d_slot_out, (size_t)it.n_pw, it.d_slot, wl.slot_pitch, (size_t)it.n_pw,
+                           (size_t)it.plan.passes(), cudaMemcpyDeviceToDevice, s));
+    }
     if (it.plan.n_unique == it.n_fold) continue;
     // replicate the rows of pc-kpts that share a coset
     for (int f = 0; f < it.n_fold; ++f) {
       const int u = it.plan.unique_of[f];
-      CU(cudaMemcpyAsync(it.d_weights + (size_t)f * it.n_bands, geoms[(size_t)i].weights + (size_t)u * it.n_bands,
+      CU(cudaMemcpyAsync(it.d_weights + (size_t)f * it.n_bands, it.w_unique + (size_t)u * it.n_bands,
                          sizeof(double) * it.n_bands, cudaMemcpyDeviceToDevice, s));
       CU(cudaMemcpyAsync(it.d_dN + (size_t)f * c->nener, it.dn_unique + (size_t)u * c->nener,
                          sizeof(double) * c->nener, cudaMemcpyDeviceToDevice, s));
@@ -660,6 +677,10 @@ int bandup_gpu_unfold_device(int handle, void* stream, int n_spinor, int n_pw, i
   it.stride_bytes = band_stride_bytes;
   it.d_coeffs = d_coeffs; it.d_gfrac = d_g_frac; it.d_energies = d_band_energies;
   it.d_weights = d_weights; it.d_dN = d_dN; it.d_nsel = d_n_selected; it.d_norms = d_norms;
+  if (d_slot_out && it.plan.passes() > 1)
+    return fail(c, BANDUP_GPU_ERR_TOO_MANY_FOLDS,
+                "d_slot_out holds one byte per plane wave: at most " + std::to_string(kMaxFolds) +
+                    " distinct cosets (pass NULL, or split the pc-kpts)");
   it.d_slot_out = d_slot_out;
   it.ws = static_cast<char*>(d_workspace);
   cudaSetDevice(c->device);
@@ -894,7 +915,7 @@ int submit_impl(int handle, int ikpt, int n_spinor, int n_pw, int n_bands, int l
   CU(fl.dN.reserve(sizeof(double) * (size_t)n_fold * c->nener));
   CU(fl.nsel.reserve(sizeof(int32_t) * (size_t)n_fold));
   CU(fl.norms.reserve(sizeof(double) * (size_t)n_bands));
-  CU(fl.slot.reserve((size_t)n_pw));
+  CU(fl.slot.reserve((size_t)n_pw * (size_t)plan.passes()));
   CU(fl.workspace.reserve(wl.total));
   CU(fl.h_weights.reserve(sizeof(double) * (size_t)n_fold * n_bands));
   CU(fl.h_dN.reserve(sizeof(double) * (size_t)n_fold * c->nener));
@@ -993,7 +1014,7 @@ int bandup_gpu_fetch_kpt(int handle, int ikpt, double* weights, double* dN, int3
       CU(cudaMemcpyAsync(d_cnt, id_count.data(), sizeof(int32_t) * (size_t)nu, cudaMemcpyHostToDevice, c->compute));
       {
         KernelScope k(c, BANDUP_GPU_K_COSET, c->compute);
-        launch_selected_lists(static_cast<const uint8_t*>(fl->slot.p), fl->n_pw, nu, d_cnt, d_lists, c->compute);
+        launch_selected_lists(static_cast<const uint8_t*>(fl->slot.p), (size_t)fl->n_pw, fl->n_pw, nu, d_cnt, d_lists, c->compute);
       }
       CU(cudaMemcpyAsync(id_lists.data(), d_lists, sizeof(int32_t) * (size_t)id_off[nu], cudaMemcpyDeviceToHost, c->compute));
       CU(cudaStreamSynchronize(c->compute));

@@ -100,7 +100,7 @@ int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t* n_energie
     }
     {
       KernelScope k(c, BANDUP_GPU_K_COSET, s);
-      launch_selected_lists(static_cast<const uint8_t*>(fl->slot.p), fl->n_pw, nu, fl->d_ns_unique,
+      launch_selected_lists(static_cast<const uint8_t*>(fl->slot.p), (size_t)fl->n_pw, fl->n_pw, nu, fl->d_ns_unique,
                             static_cast<int32_t*>(fl->selected.p), s);
     }
     {

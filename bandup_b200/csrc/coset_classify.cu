@@ -83,15 +83,18 @@ void launch_coset_classify(const KptGeom* d_geoms, int n_kpts, int max_n_pw, con
 // One CTA per fold walks the slot table in order and writes the 1-based indices
 // of its plane waves: the same list the reference builds with append() under
 // `omp critical` (band_unfolding_routines_mod.f90:596-598), here always ascending.
+// Fold f lives in the table of pass f / kMaxFolds under the id f % kMaxFolds.
 __global__ void __launch_bounds__(1024)
-k1_selected_lists(const uint8_t* __restrict__ slot, int n_pw, int n_fold,
+k1_selected_lists(const uint8_t* __restrict__ slot_tables, size_t slot_pitch, int n_pw, int n_fold,
                   const int32_t* __restrict__ n_selected, int32_t* __restrict__ selected) {
-  const int f = blockIdx.x;
+  const int f_global = blockIdx.x;
+  const uint8_t* __restrict__ slot = slot_tables + slot_pitch * (size_t)(f_global / kMaxFolds);
+  const int f = f_global % kMaxFolds;
   __shared__ int s_warp[32];
   __shared__ int s_base;
   if (threadIdx.x == 0) {
     int off = 0;
-    for (int i = 0; i < f; ++i) off += n_selected[i];
+    for (int i = 0; i < f_global; ++i) off += n_selected[i];
     s_base = off;
   }
   __syncthreads();
@@ -115,11 +118,11 @@ k1_selected_lists(const uint8_t* __restrict__ slot, int n_pw, int n_fold,
   }
 }
 
-void launch_selected_lists(const uint8_t* d_slot, int n_pw, int n_fold,
+void launch_selected_lists(const uint8_t* d_slot, size_t slot_pitch, int n_pw, int n_fold,
                            const int32_t* d_n_selected, int32_t* d_selected,
                            cudaStream_t s) {
   if (n_fold <= 0 || n_pw <= 0) return;
-  k1_selected_lists<<<n_fold, 1024, 0, s>>>(d_slot, n_pw, n_fold, d_n_selected, d_selected);
+  k1_selected_lists<<<n_fold, 1024, 0, s>>>(d_slot, slot_pitch, n_pw, n_fold, d_n_selected, d_selected);
 }
 
 }  // namespace bandup

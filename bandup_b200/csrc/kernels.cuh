@@ -59,8 +59,9 @@ struct KptGeom {
 void launch_coset_classify(const KptGeom* d_geoms, int n_kpts, int max_n_pw, const CosetCommon& cc,
                            cudaStream_t s);
 
-// Ordered compaction of the 1-based selected indices of every fold (CSR).
-void launch_selected_lists(const uint8_t* d_slot, int n_pw, int n_fold,
+// Ordered compaction of the 1-based selected indices of every fold (CSR).  d_slot: one table per
+// pass of kMaxFolds folds, slot_pitch bytes apart.
+void launch_selected_lists(const uint8_t* d_slot, size_t slot_pitch, int n_pw, int n_fold,
                            const int32_t* d_n_selected, int32_t* d_selected,
                            cudaStream_t s);
 

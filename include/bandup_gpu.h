@@ -54,9 +54,10 @@ extern "C" {
 #define BANDUP_GPU_ERR_INT_OVERFLOW 12  /* Miller indices x adjugate would overflow */
 #define BANDUP_GPU_ERR_NCCL 13          /* libnccl not found, or a NCCL call failed */
 
-/* most DISTINCT cosets (pc-kpts whose folding vectors differ by more than a pc reciprocal
- * vector) among the pc-kpts of one submit, and most pc-kpts per submit; pc-kpts that share a
- * coset are computed once and their rows replicated */
+/* DISTINCT cosets (pc-kpts whose folding vectors differ by more than a pc reciprocal vector)
+ * unfolded by ONE pass over the coefficients; a k-point with more of them (up to |det M|) is
+ * worked off in ceil(n/64) passes inside the same launches, transparently.  pc-kpts that share
+ * a coset are computed once and their rows replicated.  MAX_PCKPTS: most pc-kpts per submit. */
 #define BANDUP_GPU_MAX_FOLDS 64
 #define BANDUP_GPU_MAX_PCKPTS 4096
 
@@ -303,7 +304,8 @@ size_t bandup_gpu_workspace_bytes(int handle, int n_spinor, int n_pw, int n_band
 /* Same computation as submit+fetch but on buffers already in HBM; everything
  * is enqueued on `stream` (a cudaStream_t; NULL = default stream), nothing is
  * synchronised.  All d_* pointers are device pointers; g0 is a HOST pointer.
- * d_norms, d_slot_out (uint8 [n_pw]: fold id or 255) may be NULL. */
+ * d_norms, d_slot_out (uint8 [n_pw]: fold id or 255) may be NULL; d_slot_out needs
+ * <= BANDUP_GPU_MAX_FOLDS distinct cosets (ERR_TOO_MANY_FOLDS otherwise). */
 int bandup_gpu_unfold_device(int handle, void *stream, int n_spinor, int n_pw,
                              int n_bands, int layout, int64_t band_stride_bytes,
                              const void *d_coeffs, const int32_t *d_g_frac,

@@ -94,14 +94,80 @@ def test_folds_sharing_a_coset_and_many_folds(unfolder):
         assert np.array_equal(a, b)
     assert rel_err(res.spectral_weight, w) <= REL_TOL
     assert rel_err(res.dN, dN) <= REL_TOL
-    # more than BANDUP_GPU_MAX_FOLDS DISTINCT cosets in one submit is refused (det M = 108 here)
-    from bandup_b200.unfold import BandupGpuError
-    cube = np.array([[i, j, k] for i in range(5) for j in range(5) for k in range(5)], dtype=np.int32)
+
+
+def test_all_108_cosets_in_one_submit_two_passes(unfolder):
+    """More than BANDUP_GPU_MAX_FOLDS distinct cosets (here every one of the det M = 108, plus 108
+    repeats) are worked off in passes inside the same launches: rows, counts, selected lists and
+    the projected variant behave as with one pass, and the weights of every band sum to one."""
+    from bandup_b200.unfold import MAX_FOLDS, PwWavefunction
+    sc = synth.make_scenario("si333_vacancy", scale=0.25)
+    grid = setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 0)
+    ener[2] = ener[1]
+    ener = np.sort(ener)
+    cube = np.array([[i, j, k] for i in range(6) for j in range(6) for k in range(6)], dtype=np.int32)
+    lab = synth.coset_labels(cube, sc.M)
+    n_distinct = len(np.unique(lab))
+    assert n_distinct == 108 > MAX_FOLDS
+    res = unfolder.perform_unfolding(PwWavefunction(coeffs, gf, ener), g0=cube, ikpt=4)
+    fG = cube.astype(np.float64) @ sc.B_sc
+    w, dN, ns, sels = oracle_kpt(sc, coeffs, gf, ener, fG, grid)
+    assert np.array_equal(res.n_selected, ns) and ns.min() > 0
+    for a, b in zip(res.selected_coeff_indices, sels):
+        assert np.array_equal(a, b)
+    assert rel_err(res.spectral_weight, w) <= REL_TOL
+    assert rel_err(res.dN, dN) <= REL_TOL
+    _, first = np.unique(lab, return_index=True)
+    assert np.allclose(res.spectral_weight[first].sum(axis=0), 1.0, atol=1e-7)     # all cosets: sum_k P = 1
+    for f in range(cube.shape[0]):                                                  # repeats share rows
+        assert np.array_equal(res.spectral_weight[f], res.spectral_weight[first[np.searchsorted(np.unique(lab), lab[f])]])
+    # the unfolding-density operator of a fold in the second pass
+    from oracle import oracle as O
+    from oracle import oracle_np as ON
+    rho = unfolder.calc_rho(4)
+    f = int(np.sort(first)[100])            # the 101st distinct coset in submit order: second pass
+    c_ren, _ = O.renormalize(coeffs, 1)
+    ies = np.nonzero(dN[f] >= 1e-3)[0]
+    assert len(ies) > 0
+    for ie in ies[:4]:
+        want = ON.calc_rho(c_ren, sels[f], ener, dN[f][ie], grid[ie], grid[1] - grid[0], sigma=ON.EPS_DP)
+        got = rho.dense(f, int(ie) + 1, coeffs.shape[0]).astype(np.complex128)
+        big = np.abs(want) >= 1.2e-5
+        assert np.all(np.abs(got[big] - want[big]) <= 2e-6 * max(np.abs(want).max(), 1e-30) + 2e-7 * np.abs(want[big]))
+
+
+def test_device_entry_point_with_more_than_64_cosets(unfolder):
+    """bandup_gpu_unfold_device: two passes work; the one-byte slot table output is refused."""
+    import torch
+    from bandup_b200.unfold import BandupGpuError, LAYOUT_FORTRAN_INMEM
+    sc = synth.make_scenario("si333_vacancy", scale=0.2)
+    grid = setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 2)
+    nb, n_pw, nsp = coeffs.shape
+    cube = np.array([[i, j, k] for i in range(5) for j in range(4) for k in range(4)], dtype=np.int32)
     assert len(np.unique(synth.coset_labels(cube, sc.M))) > 64
+    dev = torch.device("cuda:0")
+    nf = cube.shape[0]
+    d_c = torch.from_numpy(coeffs.view(np.float32).reshape(nb, n_pw * nsp, 2)).to(dev)
+    d_g, d_e = torch.from_numpy(gf).to(dev), torch.from_numpy(ener).to(dev)
+    d_w = torch.zeros((nf, nb), dtype=torch.float64, device=dev)
+    d_dn = torch.zeros((nf, len(grid)), dtype=torch.float64, device=dev)
+    d_ns = torch.zeros(nf, dtype=torch.int32, device=dev)
+    d_slot = torch.zeros(n_pw, dtype=torch.uint8, device=dev)
+    ws = unfolder.workspace_bytes(nsp, n_pw, nb, nf)
+    d_ws = torch.empty(ws, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    args = (stream, nsp, n_pw, nb, LAYOUT_FORTRAN_INMEM, n_pw * nsp * 8, d_c.data_ptr(), d_g.data_ptr(),
+            d_e.data_ptr(), cube, d_w.data_ptr(), d_dn.data_ptr(), d_ns.data_ptr())
     with pytest.raises(BandupGpuError) as ei:
-        unfolder.submit(2, PwWavefunction(coeffs, gf, ener), g0=cube)
+        unfolder.unfold_device(*args, d_slot_out=d_slot.data_ptr(), d_workspace=d_ws.data_ptr(), workspace_bytes=ws)
     assert ei.value.code == 5
-    unfolder._inflight.clear()
+    unfolder.unfold_device(*args, d_workspace=d_ws.data_ptr(), workspace_bytes=ws)
+    torch.cuda.synchronize()
+    w, dN, ns, _ = oracle_kpt(sc, coeffs, gf, ener, cube.astype(np.float64) @ sc.B_sc, grid)
+    assert np.array_equal(d_ns.cpu().numpy(), ns)
+    assert rel_err(d_w.cpu().numpy(), w) <= REL_TOL and rel_err(d_dn.cpu().numpy(), dN) <= REL_TOL
 
 
 @pytest.mark.parametrize("n_spinor", [1, 2])
