@@ -43,6 +43,44 @@ def partition_kpts(costs: Sequence[float], world_size: int) -> List[Tuple[int, i
     return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
 
 
+class KptTickets:
+    """Hands out SC-kpt indices 0..n_kpts-1 to whoever asks first: a counter in the
+    torch.distributed key-value store (the rendezvous store every rank already shares), so that a
+    rank whose host->device link is slower -- on the 8-GPU boxes measured here four GPUs get 23 GB/s
+    and four 35 GB/s when all copy at once -- simply ends up with fewer k-points instead of holding
+    the job back.  The output does not depend on who computed what: rows are gathered by row id.
+    Without a store (single process) it is a local counter."""
+
+    def __init__(self, n_kpts: int, store=None, job: str = "0"):
+        self.n_kpts = int(n_kpts)
+        self.store = store
+        self.key = f"bandup_b200/next_kpt/{job}"
+        self._local = 0
+        if store is not None:
+            store.add(self.key, 0)        # creates the counter; every rank may do it
+
+    @classmethod
+    def from_default_group(cls, n_kpts: int, job: str = "0") -> "KptTickets":
+        """Counter in the store of the default process group (None => local counter)."""
+        store = None
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                from torch.distributed import distributed_c10d as c10d
+                store = c10d._get_default_store()
+        except Exception:
+            store = None
+        return cls(n_kpts, store, job)
+
+    def take(self) -> Optional[int]:
+        if self.store is None:
+            i = self._local
+            self._local += 1
+        else:
+            i = int(self.store.add(self.key, 1)) - 1
+        return i if i < self.n_kpts else None
+
+
 @dataclass
 class GatheredDeltaN:
     dN: np.ndarray            # (n_rows_total, nener) in global row order
@@ -109,8 +147,13 @@ class ShardedUnfoldJob:
 
     def __init__(self, unfolder, n_kpts: int, costs: Sequence[float], load_kpt: Callable,
                  rank: int = 0, world_size: int = 1, depth: int = 2,
-                 after_fetch: Optional[Callable] = None, prefetch: bool = False):
+                 after_fetch: Optional[Callable] = None, prefetch: bool = False,
+                 tickets: Optional[KptTickets] = None):
         self.unfolder = unfolder
+        # tickets: dynamic assignment (KptTickets shared by all ranks) instead of the static
+        # contiguous blocks; the k-points this rank ended up with are in self.done_kpts
+        self.tickets = tickets
+        self.done_kpts: List[int] = []
         self.load_kpt = load_kpt
         # after_fetch(iK, result, row_ids): called right after a k-point is fetched, while it is
         # still resident on the device (rho, Pauli vectors, spectral function can be asked for)
@@ -128,9 +171,13 @@ class ShardedUnfoldJob:
     def run_local(self):
         """(dN rows, row ids, weights per row) of this rank's SC-kpts; submit runs `depth` ahead of
         fetch so the upload of k-point j+1 overlaps the kernels of j."""
-        start, end = self.my_block
+        if self.tickets is not None:
+            source = iter(self.tickets.take, None)
+        else:
+            source = iter(range(*self.my_block))
         inflight: List[Tuple[int, np.ndarray]] = []
         rows, ids, weights = [], [], []
+        self.done_kpts = []
 
         def drain_one():
             iK, rid = inflight.pop(0)
@@ -145,13 +192,15 @@ class ShardedUnfoldJob:
             if self.after_fetch is not None:
                 self.after_fetch(iK, res, rid)
 
-        pool = ThreadPoolExecutor(1) if self.prefetch and end - start > 1 else None
-        ahead = pool.submit(self.load_kpt, start) if pool else None
-        for iK in range(start, end):
+        pool = ThreadPoolExecutor(1) if self.prefetch else None
+        iK = next(source, None)
+        ahead = pool.submit(self.load_kpt, iK) if pool and iK is not None else None
+        while iK is not None:
+            nxt = next(source, None)      # with tickets: this rank holds one k-point ahead
             if pool:
                 wf, folding_G, rid = ahead.result()
-                # iK+1 goes into the buffer of iK-3, fetched two iterations ago (depth 2)
-                ahead = pool.submit(self.load_kpt, iK + 1) if iK + 1 < end else None
+                # the next one goes into the buffer of iK-2, fetched two iterations ago (depth 2)
+                ahead = pool.submit(self.load_kpt, nxt) if nxt is not None else None
             else:
                 wf, folding_G, rid = self.load_kpt(iK)
             if len(inflight) >= self.depth:
@@ -161,6 +210,8 @@ class ShardedUnfoldJob:
             else:
                 self.unfolder.submit(iK, wf, folding_G=folding_G)
             inflight.append((iK, np.asarray(rid, dtype=np.int64)))
+            self.done_kpts.append(iK)
+            iK = nxt
         while inflight:
             drain_one()
         if pool:

@@ -434,16 +434,50 @@ def run_b200(args, sc, rank, world, local_rank):
             return out
 
         e2e_step(0)
+        # The timed job: kps * n_e2e SC-kpts per GPU in total, handed out one at a time from a
+        # counter all ranks share (bandup_b200.sharding.KptTickets), so a rank behind a slower
+        # host link takes fewer k-points instead of holding the others back -- SC-kpts are
+        # independent and the result does not depend on who computed which.
+        from bandup_b200.sharding import KptTickets
+        n_total = kps * n_e2e * world
+        tickets = KptTickets.from_default_group(n_total, job="bench_e2e")
+        blk_bytes = [nb * host[i][1]["n_pw"] * nsp * 8 for i in range(len(host))]
+        blk_h2d = [b + host[i][1]["n_pw"] * 12 + nb * 8 for i, b in enumerate(blk_bytes)]
+        blk_d2h = [host[i][1]["nf"] * (nb + nener) * 8 + host[i][1]["nf"] * 4 + nb * 8 for i in range(len(host))]
+        mine = 0
         barrier()
         t0 = time.perf_counter()
-        for s in range(n_e2e):
-            e2e_step(1000 * (s + 1))
+        cur = tickets.take()
+        if cur is not None:
+            u.submit(10_000 + cur, wfs[0], g0=host[0][1]["g0"])
+        while cur is not None:
+            nxt = tickets.take()
+            if nxt is not None:
+                b = (mine + 1) % len(host)
+                u.submit(10_000 + nxt, wfs[b], g0=host[b][1]["g0"])
+            u.fetch(10_000 + cur)
+            mine += 1
+            cur = nxt
         torch.cuda.synchronize()
         t_e2e = (t0, time.perf_counter())
         dt = max_over_ranks(t_e2e[1] - t0)
-        e2e_bytes = sum(nb * host[i][1]["n_pw"] * nsp * 8 for i in seq) * n_e2e * world
-        e2e = {"value": e2e_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "sc_kpts_per_s": kps * n_e2e * world / dt, "steps": n_e2e,
+        n0, n1 = (mine + 1) // 2, mine // 2          # k-points taken from host block 0 / 1
+        sums = torch.tensor([n0 * blk_bytes[0] + n1 * blk_bytes[-1], n0 * blk_h2d[0] + n1 * blk_h2d[-1],
+                             n0 * blk_d2h[0] + n1 * blk_d2h[-1]], dtype=torch.float64, device=dev)
+        counts = [mine]
+        if world > 1:
+            dist.all_reduce(sums)
+            cnt = torch.zeros(world, dtype=torch.int64, device=dev)
+            cnt[rank] = mine
+            dist.all_reduce(cnt)
+            counts = [int(v) for v in cnt.tolist()]
+        e2e_bytes, h2d_tot, d2h_tot = (float(v) for v in sums.tolist())
+        e2e = {"value": e2e_bytes / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d_tot / n_e2e / world), "d2h_bytes_per_step": int(d2h_tot / n_e2e / world),
+               "sc_kpts_per_s": n_total / dt, "steps": n_e2e,
+               "schedule": "SC-kpts pulled one at a time from a counter shared by all ranks "
+                           "(bandup_b200.sharding.KptTickets); bytes per step = per-GPU average",
+               "kpts_per_rank": counts,
                "timer": "host monotonic clock between device synchronisations, max over ranks",
                "bound": "PCIe host->device copy of the coefficient blocks", "numa": numa}
     clocks = None

@@ -110,3 +110,55 @@ def test_world_size_2_gloo_matches_single_process():
         assert sum(per_rank) == n_rows and min(per_rank) > 0
         assert inflight == 2                                        # double buffering was exercised
     assert r0[3][1] == r1[3][0] and r0[3][0] == 0 and r1[3][1] == sc.n_sc_kpts
+
+
+# ---- dynamic assignment: ranks pull SC-kpts from a shared counter ---------------------------
+def test_tickets_local_counter():
+    from bandup_b200.sharding import KptTickets
+    t = KptTickets(3)
+    assert [t.take(), t.take(), t.take(), t.take(), t.take()] == [0, 1, 2, None, None]
+    sc = synth.make_scenario("graphene4x4", scale=0.06, n_kpts=5)
+    job = _job(sc, 0, 1)
+    static = job.run()
+    job2 = _job(sc, 0, 1)
+    job2.tickets = KptTickets(sc.n_sc_kpts)
+    dyn = job2.run()
+    assert job2.done_kpts == list(range(sc.n_sc_kpts))
+    assert np.array_equal(dyn.dN, static.dN) and np.array_equal(dyn.row_ids, static.row_ids)
+
+
+def _worker_dynamic(rank, world, port, ret):
+    import time
+    import torch.distributed as dist
+    from bandup_b200.sharding import KptTickets
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sc = synth.make_scenario("graphene4x4", scale=0.06, n_kpts=24)
+        job = _job(sc, rank, world)
+        job.tickets = KptTickets.from_default_group(sc.n_sc_kpts, job="t1")
+        assert job.tickets.store is not None
+        if rank == 1:                      # a rank with a slow link: every fetch takes much longer
+            fetch = job.unfolder.fetch
+            job.unfolder.fetch = lambda ikpt: (time.sleep(0.4), fetch(ikpt))[1]
+        dist.barrier()
+        g = job.run()
+        ret[rank] = (g.dN, g.row_ids, list(job.done_kpts))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_dynamic_tickets_balance_a_slow_rank():
+    import torch.multiprocessing as mp
+    sc = synth.make_scenario("graphene4x4", scale=0.06, n_kpts=24)
+    single = _job(sc, 0, 1).run()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker_dynamic, args=(2, _free_port(), ret), nprocs=2, join=True)
+        r0, r1 = ret[0], ret[1]
+    for dN, ids, _ in (r0, r1):
+        assert np.array_equal(ids, single.row_ids)
+        assert np.array_equal(dN, single.dN)                        # who computed what does not matter
+    assert sorted(r0[2] + r1[2]) == list(range(sc.n_sc_kpts))       # every SC-kpt exactly once
+    assert len(r0[2]) > len(r1[2]) >= 1                             # the slow rank ended up with fewer
