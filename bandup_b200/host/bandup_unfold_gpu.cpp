@@ -16,6 +16,7 @@
 //   [rho, Pauli vectors] -> write unfolded_EBS_not-symmetry_averaged.dat [+ rho file].
 // Every number comes from the GPU library; nothing is computed on the host.
 #include <fcntl.h>
+#include <sys/file.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -319,7 +320,7 @@ Args parse_args(int argc, char** argv) {
       "-out_file_nosymm", "-out_file_symm", "-output_file_only_user_selec_direcs_unf_dens_op",
       "-output_file_symm_averaged_unf_dens_op", "-spin_channel", "-n_sckpts_to_skip", "-normal_to_proj_plane",
       "-origin_for_spin_proj_cart", "-device", "-read_threads", "-outdir", "-saxis", "-n_ranks", "-rank",
-      "-nccl_id_file"};
+      "-nccl_id_file", "-ticket_file"};
   const std::vector<std::string> switches = {"-write_unf_dens_op", "-no_symm_sckpts", "-no_symm_avg", "-dont_unfold",
       "-continue_if_not_commensurate", "--continue_if_npw_smaller_than_expected", "-skip_propose_pc_for_given_pc",
       "-skip_propose_pc_for_given_sc"};
@@ -471,7 +472,7 @@ int main(int argc, char** argv) {
       folds[(size_t)fs[ik]].push_back((int)ik);
     }
   }
-  std::vector<int> used_all, used;
+  std::vector<int> used_all, used, mine_static;
   for (int i = 0; i < wc.nkpts; ++i)
     if (!folds[(size_t)i].empty()) used_all.push_back(i);
   {  // this rank's contiguous block, balanced by n_bands * nplane (main_BandUP.f90:133 becomes first..last)
@@ -481,16 +482,38 @@ int main(int argc, char** argv) {
     for (int i : used_all) {
       const double mid = acc + 0.5 * (double)nplane[(size_t)i];
       const int owner = std::min(n_ranks - 1, (int)(mid / total * n_ranks));
-      if (owner == rank) used.push_back(i);
+      if (owner == rank) mine_static.push_back(i);
       acc += (double)nplane[(size_t)i];
     }
   }
-  size_t n_pck_mine = 0;
-  for (int i : used) n_pck_mine += folds[(size_t)i].size();
+  // -ticket_file F: instead of the static blocks, every rank takes the next SC-kpt from a counter
+  // in F (flock + fetch-and-add; F must not exist when the job starts), so that a rank behind a
+  // slower host link simply unfolds fewer k-points.  The delta_N rows are gathered by row id.
+  const std::string ticket_file = args.get("-ticket_file", "");
+  size_t static_pos = 0;
+  auto next_used = [&]() -> bool {  // appends this rank's next SC-kpt to `used`
+    if (ticket_file.empty()) {
+      if (static_pos >= mine_static.size()) return false;
+      used.push_back(mine_static[static_pos++]);
+      return true;
+    }
+    const int fd = ::open(ticket_file.c_str(), O_RDWR | O_CREAT, 0644);
+    if (fd < 0) die("ERROR: cannot open -ticket_file " + ticket_file);
+    int64_t v = 0;
+    if (::flock(fd, LOCK_EX) != 0) die("ERROR: cannot lock -ticket_file " + ticket_file);
+    if (::pread(fd, &v, sizeof(v), 0) != (ssize_t)sizeof(v)) v = 0;
+    const int64_t nv = v + 1;
+    if (::pwrite(fd, &nv, sizeof(nv), 0) != (ssize_t)sizeof(nv)) die("ERROR: cannot write -ticket_file " + ticket_file);
+    ::flock(fd, LOCK_UN);
+    ::close(fd);
+    if (v >= (int64_t)used_all.size()) return false;
+    used.push_back(used_all[(size_t)v]);
+    return true;
+  };
 
   // MAIN LOOP (:131-177), double buffered: records of k-point j+1 are read while j uploads/computes
   const size_t block = (size_t)wc.nbands * (size_t)wc.nrecl;
-  const int n_buf = (int)std::min<size_t>(4, std::max<size_t>(1, used.size()));
+  const int n_buf = (int)std::min<size_t>(4, std::max<size_t>(1, ticket_file.empty() ? mine_static.size() : used_all.size()));
   std::vector<void*> bufs((size_t)n_buf, nullptr);
   for (auto& b : bufs) gpu_check(h, bandup_gpu_pinned_alloc(block, &b), "pinned_alloc");
   std::vector<double> dN_all(n_pck * (size_t)nener, 0.0), sigma_all;
@@ -542,14 +565,16 @@ int main(int argc, char** argv) {
   };
 
   std::future<void> ahead;
-  if (!used.empty())
+  if (next_used())
     ahead = std::async(std::launch::async, [&] { wc.read_band_records(used[0] + 1, spin_channel, bufs[0], read_threads); });
   for (size_t j = 0; j < used.size(); ++j) {
     ahead.get();
-    if (j + 1 < used.size())
-      ahead = std::async(std::launch::async, [&, j] {
-        wc.read_band_records(used[j + 1] + 1, spin_channel, bufs[(j + 1) % (size_t)n_buf], read_threads);
+    if (next_used()) {  // one k-point ahead: its records are read while k-point j uploads / computes
+      const int i_next = used[j + 1];
+      ahead = std::async(std::launch::async, [&, j, i_next] {
+        wc.read_band_records(i_next + 1, spin_channel, bufs[(j + 1) % (size_t)n_buf], read_threads);
       });
+    }
     if ((int)inflight.size() >= depth) {
       drain(inflight.front());
       inflight.erase(inflight.begin());
@@ -572,6 +597,8 @@ int main(int argc, char** argv) {
     std::printf("SC-kpt #%d: %d plane waves%s, %d pc-kpt(s) fold onto it\n", i + 1, npw, nsp == 2 ? " (spinor)" : "", nf);
   }
   for (int j : inflight) drain(j);
+  size_t n_pck_mine = 0;
+  for (int i : used) n_pck_mine += folds[(size_t)i].size();
   if (n_parsed != n_pck_mine) die("ERROR: not every pc-kpt could be unfolded.");
   if (n_ranks > 1) {  // the path's only collective: every rank's disjoint delta_N rows (ncclAllGather)
     if (spinor) die("ERROR: spinor output is supported by BandUP_gpu.x with one rank only.");

@@ -73,6 +73,12 @@ def test_host_exe_reproduces_the_python_path_and_the_oracle(gpu_lib, unfolder, t
     for x, y in zip(exe_recs, py_recs):
         assert (x.pckpt_number, x.iener, x.folding_sckpt_number) == (y.pckpt_number, y.iener, y.folding_sckpt_number)
         assert np.array_equal(x.rows, y.rows) and np.array_equal(x.cols, y.cols) and np.array_equal(x.entries, y.entries)
+    # SC-kpts taken from a counter file (-ticket_file, the multi-rank load balancer): same output
+    r = subprocess.run([str(EXE), "-no_symm_sckpts", "-no_symm_avg", "-wf_file", "WAVECAR", "-out_file_nosymm",
+                        "dyn_EBS.dat", "-ticket_file", "tickets.bin"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert np.array_equal(BF.read_band_struc(tmp_path / "dyn_EBS.dat"), exe_tab)
+    assert int(np.fromfile(tmp_path / "tickets.bin", dtype=np.int64)[0]) == sc.n_sc_kpts + 1   # every k-point once + the take that found none left
     # and against the oracle (to the file's 4 digits)
     for iK in range(sc.n_sc_kpts):
         coeffs, gf, ener = data[iK]

@@ -93,6 +93,14 @@ def test_host_exe_two_ranks(tmp_path, gpu_lib):
     n0 = outs[0][0].count("SC-kpt #")
     n1 = outs[1][0].count("SC-kpt #")
     assert n0 > 0 and n1 > 0
+    # dynamic assignment: both ranks pull SC-kpts from a counter file; same output, every k-point once
+    procs = [subprocess.Popen(common + ["-out_file_nosymm", "dyn.dat", "-n_ranks", "2", "-rank", str(k),
+                                        "-nccl_id_file", "ncclid2", "-ticket_file", "tickets"], cwd=tmp_path,
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for k in (0, 1)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert np.array_equal(BF.read_band_struc(tmp_path / "one.dat"), BF.read_band_struc(tmp_path / "dyn.dat"))
+    assert outs[0][0].count("SC-kpt #") + outs[1][0].count("SC-kpt #") == n0 + n1
 
 
 def test_bench_two_ranks_prints_one_json_line():
