@@ -51,31 +51,34 @@ class KptTickets:
     the job back.  The output does not depend on who computed what: rows are gathered by row id.
     Without a store (single process) it is a local counter."""
 
-    def __init__(self, n_kpts: int, store=None, job: str = "0"):
+    def __init__(self, n_kpts: int, store=None, job: str = "0", offset: int = 0, stride: int = 1):
         self.n_kpts = int(n_kpts)
         self.store = store
         self.key = f"bandup_b200/next_kpt/{job}"
-        self._local = 0
+        # without a store: offset, offset+stride, ... (round-robin over ranks when there are several)
+        self._local, self._stride = int(offset), max(1, int(stride))
         if store is not None:
             store.add(self.key, 0)        # creates the counter; every rank may do it
 
     @classmethod
     def from_default_group(cls, n_kpts: int, job: str = "0") -> "KptTickets":
-        """Counter in the store of the default process group (None => local counter)."""
-        store = None
+        """Counter in the store of the default process group.  One process: a local counter.  Several
+        processes whose store cannot be reached: static round-robin (rank, rank + world, ...)."""
+        store, rank, world = None, 0, 1
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                rank, world = dist.get_rank(), dist.get_world_size()
                 from torch.distributed import distributed_c10d as c10d
                 store = c10d._get_default_store()
         except Exception:
             store = None
-        return cls(n_kpts, store, job)
+        return cls(n_kpts, store, job, offset=rank, stride=world)
 
     def take(self) -> Optional[int]:
         if self.store is None:
             i = self._local
-            self._local += 1
+            self._local += self._stride
         else:
             i = int(self.store.add(self.key, 1)) - 1
         return i if i < self.n_kpts else None

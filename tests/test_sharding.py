@@ -117,6 +117,8 @@ def test_tickets_local_counter():
     from bandup_b200.sharding import KptTickets
     t = KptTickets(3)
     assert [t.take(), t.take(), t.take(), t.take(), t.take()] == [0, 1, 2, None, None]
+    t = KptTickets(7, offset=1, stride=3)          # no shared store: round-robin share of rank 1 of 3
+    assert [t.take(), t.take(), t.take(), t.take()] == [1, 4, None, None]
     sc = synth.make_scenario("graphene4x4", scale=0.06, n_kpts=5)
     job = _job(sc, 0, 1)
     static = job.run()
