@@ -16,11 +16,9 @@
 // with a conservative guard band (|E_m - E_i| > delta_e/2 + 8 sqrt2 sigma + 1e-9
 // relative slack) rejects almost every pair before any division or erf.
 //
-// One warp per (energy bin, fold), eight bins of a fold per CTA; the band energies are
-// staged through shared memory in tiles (a dependent global load per band made the first
-// version latency-bound: 38 us for 3000 bands), lanes stride over the bands and a shuffle
-// tree combines them (fixed order: deterministic).  Work is tiny next to K2.
-// Candidate bands are compacted first and their lambdas evaluated one per lane (see the kernel).
+// One warp per energy bin (all folds), eight consecutive bins per CTA; candidate bands are
+// compacted first (CTA window, then the warp's own bin) and their lambdas evaluated one per lane,
+// a shuffle tree combines them (fixed order: deterministic).  Work is tiny next to K2.
 #include "kernels.cuh"
 
 namespace bandup {
@@ -37,38 +35,58 @@ __device__ __forceinline__ double lambda_box_erf(double pc_ener, double sc_ener,
   return __dmul_rn(0.5, __dsub_rn(erf(x2), erf(x1)));
 }
 
-constexpr int kK3Threads = 256;   // 8 warps = 8 energy bins of one fold per CTA
-constexpr int kK3BandTile = 2048;  // band energies staged in shared memory per pass
+constexpr int kK3Threads = 256;    // 8 warps = 8 consecutive energy bins per CTA
+constexpr int kK3Warps = kK3Threads / 32;
+constexpr int kK3BandTile = 2048;  // bands examined per pass (8 per thread)
+constexpr int kK3PerThread = kK3BandTile / kK3Threads;
+static_assert(kK3PerThread * kK3Warps == 64, "the count scan below handles two entries per lane of one warp");
 
 // grid (ceil(nener/8), n_kpts): one warp per energy bin, ALL folds of the k-point.  Which bands
 // can contribute to a bin, and lambda itself, depend on the bin and the band energy only -- not on
 // the fold -- so the scan and the erf evaluations are done once and reused for every fold.
+//
+// Two-level candidate search.  The CTA's eight bins span a narrow energy window; the whole CTA
+// first compacts, in ascending band order, the bands within reach of that window (8 independent
+// coalesced loads per thread, one ballot each, one 64-entry scan) -- typically a few dozen of
+// thousands -- and each warp then tests only those against its own bin.  (Staging every band
+// energy through shared memory and letting every warp walk all of them cost 16 us of dependent
+// load->store chains and 94 loop trips per warp on the 3000-band case.)
 __global__ void __launch_bounds__(kK3Threads)
 k3_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict__ grid, int nener, double sigma) {
-  __shared__ double s_ener[kK3BandTile];
-  __shared__ int s_hit[kK3Threads / 32][64];
-  __shared__ double s_acc[kK3Threads / 32][kMaxFolds];
+  __shared__ double s_ener[kK3BandTile];  // candidates of the CTA window: energy ...
+  __shared__ int s_band[kK3BandTile];     // ... and band index, ascending
+  __shared__ int s_cnt[kK3PerThread * kK3Warps], s_off[kK3PerThread * kK3Warps + 1];
+  __shared__ int s_hit[kK3Warps][64];
+  __shared__ double s_hit_e[kK3Warps][64];
+  __shared__ double s_acc[kK3Warps][kMaxFolds];
   const KptGeom& g = geoms[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_bands = g.n_bands, n_fold = g.n_fold;
   const double* __restrict__ band_energies = g.energies;
   const double* __restrict__ weights = g.weights;
-  const int ie = blockIdx.x * (kK3Threads / 32) + warp;
+  const int ie_first = blockIdx.x * kK3Warps;
+  const int ie_last = min(ie_first + kK3Warps, nener) - 1;
+  const int ie = ie_first + warp;
   const bool live = ie < nener;
   // delta_e = energies(2) - energies(1)  (:735)
-  const double delta_e = __dsub_rn(grid[1], grid[0]);
+  const double g0 = grid[0], g1 = grid[1], Ea = grid[ie_first], Eb = grid[ie_last];
+  const double E = live ? grid[ie] : 0.0;
+  const double delta_e = __dsub_rn(g1, g0);
   const double half_de = __dmul_rn(0.5, delta_e);
   const double sqrt2_sigma = __dmul_rn(sqrt(2.0), sigma);
-  const double E = live ? grid[ie] : 0.0;
   const double reach = half_de + 8.0 * sqrt2_sigma;
   const double guard = reach + 1e-9 * (fabs(E) + reach);
+  // CTA window: a superset of every warp's |E_m - E_i| <= guard (the grid is monotonic)
+  const double w_lo = fmin(Ea, Eb), w_hi = fmax(Ea, Eb);
+  const double w_guard = 1.000001 * (reach + 1e-9 * (fmax(fabs(w_lo), fabs(w_hi)) + reach));
   int* hits = s_hit[warp];
+  double* hits_e = s_hit_e[warp];
   double* acc = s_acc[warp];
   for (int f = lane; f < n_fold; f += 32) acc[f] = 0.0;
   __syncwarp();
   int n_hit = 0;  // warp-uniform
-  // The few bands that can contribute (|E_m - E_i| within the guard band) are first collected,
-  // in ascending band order, then lambda (two erf, two divisions) is evaluated for up to 32 of
+  // The few bands that can contribute (|E_m - E_i| within the guard band) are collected in
+  // ascending band order, then lambda (two erf, two divisions) is evaluated for up to 32 of
   // them at once, one per lane; every fold then takes its sum_m P_m(f) * lambda_m with a
   // shuffle tree (fixed order: deterministic).
   auto flush = [&](int count) {
@@ -76,35 +94,90 @@ k3_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict__ grid, i
     int m = 0;
     if (lane < count) {
       m = hits[lane];
-      lam = lambda_box_erf(E, band_energies[m], half_de, sqrt2_sigma);
+      lam = lambda_box_erf(E, hits_e[lane], half_de, sqrt2_sigma);
     }
     if (__ballot_sync(0xffffffffu, lam != 0.0) != 0u) {
-      for (int f = 0; f < n_fold; ++f) {
-        double v = (lam != 0.0) ? __dmul_rn(weights[(long long)f * n_bands + m], lam) : 0.0;
+      for (int f0 = 0; f0 < n_fold; f0 += 4) {  // the weight loads of four folds in flight together
+        double w[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (lane == 0) acc[f] = __dadd_rn(acc[f], v);
+        for (int k = 0; k < 4; ++k)
+          w[k] = (lam != 0.0 && f0 + k < n_fold) ? weights[(long long)(f0 + k) * n_bands + m] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (f0 + k >= n_fold) break;
+          double v = (lam != 0.0) ? __dmul_rn(w[k], lam) : 0.0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+          if (lane == 0) acc[f0 + k] = __dadd_rn(acc[f0 + k], v);
+        }
       }
     }
     __syncwarp();
   };
   for (int m0 = 0; m0 < n_bands; m0 += kK3BandTile) {
     const int nt = min(kK3BandTile, n_bands - m0);
+    // (a) CTA-level ordered compaction of the window's candidates
+    double e[kK3PerThread];
+    unsigned bal[kK3PerThread];
+#pragma unroll
+    for (int j = 0; j < kK3PerThread; ++j) {
+      const int i = j * kK3Threads + threadIdx.x;
+      e[j] = i < nt ? band_energies[m0 + i] : 0.0;
+    }
+    __syncthreads();  // the previous tile's candidates are no longer read
+#pragma unroll
+    for (int j = 0; j < kK3PerThread; ++j) {
+      const int i = j * kK3Threads + threadIdx.x;
+      const bool cand = i < nt && !(e[j] < w_lo - w_guard) && !(e[j] > w_hi + w_guard);
+      bal[j] = __ballot_sync(0xffffffffu, cand);
+      if (lane == 0) s_cnt[j * kK3Warps + warp] = __popc(bal[j]);
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < nt; i += kK3Threads) s_ener[i] = band_energies[m0 + i];
+    if (warp == 0) {  // exclusive scan of the 64 (pass, warp) counts, in band order
+      constexpr int n = kK3PerThread * kK3Warps;
+      const int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+      int x = a + b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      s_off[2 * lane] = x - a - b;
+      s_off[2 * lane + 1] = x - b;
+      if (lane == 31) s_off[n] = x;
+    }
     __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kK3PerThread; ++j) {
+      if (bal[j] >> lane & 1u) {
+        const int pos = s_off[j * kK3Warps + warp] + __popc(bal[j] & ((1u << lane) - 1u));
+        s_ener[pos] = e[j];
+        s_band[pos] = m0 + j * kK3Threads + threadIdx.x;
+      }
+    }
+    __syncthreads();
+    const int nc = s_off[kK3PerThread * kK3Warps];
     if (!live) continue;
-    for (int i0 = 0; i0 < nt; i0 += 32) {
+    // (b) this warp's bin against the window's candidates
+    for (int i0 = 0; i0 < nc; i0 += 32) {
       const int i = i0 + lane;
-      const bool hit = i < nt && !(fabs(s_ener[i] - E) > guard);
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if (bal == 0u) continue;
-      if (hit) hits[n_hit + __popc(bal & ((1u << lane) - 1u))] = m0 + i;
-      n_hit += __popc(bal);
+      const double em = i < nc ? s_ener[i] : 0.0;
+      const bool hit = i < nc && !(fabs(em - E) > guard);
+      const unsigned hb = __ballot_sync(0xffffffffu, hit);
+      if (hb == 0u) continue;
+      if (hit) {
+        const int at = n_hit + __popc(hb & ((1u << lane) - 1u));
+        hits[at] = s_band[i];
+        hits_e[at] = em;
+      }
+      n_hit += __popc(hb);
       __syncwarp();
       if (n_hit >= 32) {
         flush(32);
-        if (lane < n_hit - 32) hits[lane] = hits[32 + lane];
+        if (lane < n_hit - 32) {
+          hits[lane] = hits[32 + lane];
+          hits_e[lane] = hits_e[32 + lane];
+        }
         n_hit -= 32;
         __syncwarp();
       }
