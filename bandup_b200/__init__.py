@@ -1,7 +1,7 @@
 """bandup_b200 -- B200-native (sm_100a) unfolding hot path of BandUP behind a C ABI.
 
     csrc/            CUDA kernels (K0 plane-wave lists, K1 coset classification, K2 fused norm +
-                     masked |C|^2 reduction, K2b, K3 delta_N, K4-K6 projected/spinor variant, K7 fold
+                     masked |C|^2 reduction, K3 finalisation + delta_N, K4-K6 projected/spinor variant, K7 fold
                      map) and the C ABI of libbandup_gpu.so (include/bandup_gpu.h)
     host/            BandUP_gpu.x: the native C++ host mirroring the reference's unfold driver
     unfold.py        Python mirror of the reference's band_unfolding module (ctypes over the C ABI)

@@ -250,7 +250,7 @@ KptGeom* stage_descriptors(Ctx* c, cudaStream_t s, const std::vector<KptGeom>& g
   return d.d;
 }
 
-// K1 -> K2 -> K2b -> K3 for every k-point of the batch: four launches in total.
+// K1 -> K2 -> K3 for every k-point of the batch: three launches in total.
 int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
   const int n = (int)items.size();
   if (n == 0) return BANDUP_GPU_OK;
@@ -319,10 +319,6 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
     KernelScope k(c, BANDUP_GPU_K_WEIGHTS, s);
     launch_weights_reduce(d_geoms, n_geoms, tiles, max_fold, items[0].n_spinor, items[0].layout, c->ctas_per_sm,
                           c->n_stages, c->sm_count, s);
-  }
-  {
-    KernelScope k(c, BANDUP_GPU_K_FINALIZE, s);
-    launch_weights_finalize(d_geoms, n_geoms, max_bands, max_fold, s);
   }
   {
     KernelScope k(c, BANDUP_GPU_K_DELTA_N, s);

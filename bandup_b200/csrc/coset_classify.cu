@@ -18,7 +18,7 @@ __device__ __forceinline__ int pos_mod(long long v, long long D) {
 }
 
 // grid (CTAs per k-point <= kK1MaxBlocks, n_kpts).  Every CTA leaves its per-fold plane-wave
-// counts in block_counts[blockIdx.x][*]; K2b adds the rows up (fixed order, no atomics on
+// counts in block_counts[blockIdx.x][*]; K3 adds the rows up (fixed order, no atomics on
 // global memory, nothing to zero beforehand).
 __global__ void __launch_bounds__(256)
 k1_coset_classify(const KptGeom* __restrict__ geoms, CosetCommon cc) {
@@ -75,7 +75,7 @@ k1_coset_classify(const KptGeom* __restrict__ geoms, CosetCommon cc) {
 void launch_coset_classify(const KptGeom* d_geoms, int n_kpts, int max_n_pw, const CosetCommon& cc,
                            cudaStream_t s) {
   if (n_kpts <= 0 || max_n_pw <= 0) return;
-  // always kK1MaxBlocks rows of counts so that K2b can add them up without knowing n_pw
+  // always kK1MaxBlocks rows of counts so that K3 can add them up without knowing n_pw
   dim3 grid((unsigned)kK1MaxBlocks, (unsigned)n_kpts);
   k1_coset_classify<<<grid, 256, 0, s>>>(d_geoms, cc);
 }

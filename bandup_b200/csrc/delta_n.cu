@@ -35,6 +35,25 @@ __device__ __forceinline__ double lambda_box_erf(double pc_ener, double sc_ener,
   return __dmul_rn(0.5, __dsub_rn(erf(x2), erf(x1)));
 }
 
+// The finalisation of K2's per-tile partials, partials[band][chunk][0 = norm, 1 + fold]:
+// s = sum_chunks norm, S = sum_chunks fold (fixed chunk order: bit-reproducible), P = S / s.
+__device__ __forceinline__ double band_norm(const double* __restrict__ p, int n_chunks, int nslots) {
+  double s = 0.0;
+#pragma unroll 4
+  for (int c = 0; c < n_chunks; ++c) s += p[(long long)c * nslots];
+  return s;
+}
+__device__ __forceinline__ double band_weight(const double* __restrict__ p, int n_chunks, int nslots, int q,
+                                              double s, int perform_unfold) {
+  double S = 0.0;
+#pragma unroll 4
+  for (int c = 0; c < n_chunks; ++c) S += p[(long long)c * nslots + q];
+  // io_routines_mod.f90:1325: bands with s <= epsilon(1.0_dp) stay unscaled
+  const double P = (s > 2.220446049250313e-16) ? S / s : S;
+  // -dont_unfold: spectral_weight = 1.0_dp (band_unfolding_routines_mod.f90:1346-1351)
+  return perform_unfold ? P : 1.0;
+}
+
 constexpr int kK3Threads = 256;    // 8 warps = 8 consecutive energy bins per CTA
 constexpr int kK3Warps = kK3Threads / 32;
 constexpr int kK3BandTile = 2048;  // bands examined per pass (8 per thread)
@@ -51,8 +70,13 @@ static_assert(kK3PerThread * kK3Warps == 64, "the count scan below handles two e
 // thousands -- and each warp then tests only those against its own bin.  (Staging every band
 // energy through shared memory and letting every warp walk all of them cost 16 us of dependent
 // load->store chains and 94 loop trips per warp on the 3000-band case.)
+//
+// The kernel also finishes K2 (what used to be a launch of its own): every CTA turns its slice of
+// the (band, slot) partials into the spectral weights P = S/s and the band norms, CTA 0 of a
+// k-point adds up K1's per-CTA plane-wave counts.  The bins do not wait for that: a bin needs P of
+// its few candidate bands only and forms it from the same partials with the same arithmetic.
 __global__ void __launch_bounds__(kK3Threads)
-k3_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict__ grid, int nener, double sigma) {
+k3_finalize_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict__ grid, int nener, double sigma) {
   __shared__ double s_ener[kK3BandTile];  // candidates of the CTA window: energy ...
   __shared__ int s_band[kK3BandTile];     // ... and band index, ascending
   __shared__ int s_cnt[kK3PerThread * kK3Warps], s_off[kK3PerThread * kK3Warps + 1];
@@ -63,7 +87,32 @@ k3_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict__ grid, i
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_bands = g.n_bands, n_fold = g.n_fold;
   const double* __restrict__ band_energies = g.energies;
-  const double* __restrict__ weights = g.weights;
+  const double* __restrict__ partials = g.partials;
+  const int n_chunks = g.n_chunks, nslots = n_fold + 1, perform_unfold = g.perform_unfold;
+  {  // ---- finalisation of K2: this CTA's slice of the (band, slot) pairs -------------------
+    const long long items = (long long)n_bands * nslots;
+    const long long per_cta = (items + gridDim.x - 1) / gridDim.x;
+    const long long hi = min(items, per_cta * (blockIdx.x + 1));
+    for (long long idx = per_cta * blockIdx.x + threadIdx.x; idx < hi; idx += kK3Threads) {
+      const int band = (int)(idx / nslots), q = (int)(idx - (long long)band * nslots);
+      const double* p = partials + (long long)band * n_chunks * nslots;
+      const double s = band_norm(p, n_chunks, nslots);
+      if (q == 0) {
+        if (g.norms) g.norms[band] = s;
+      } else {
+        g.weights[(long long)(q - 1) * n_bands + band] = band_weight(p, n_chunks, nslots, q, s, perform_unfold);
+      }
+    }
+    if (blockIdx.x == 0) {  // size(selected_coeff_indices) of every fold: K1's per-CTA counts
+      for (int f = warp; f < n_fold; f += kK3Warps) {
+        int n = 0;
+        for (int b = lane; b < kK1MaxBlocks; b += 32) n += g.block_counts[b * n_fold + f];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        if (lane == 0) g.n_selected[f] = n;
+      }
+    }
+  }
   const int ie_first = blockIdx.x * kK3Warps;
   const int ie_last = min(ie_first + kK3Warps, nener) - 1;
   const int ie = ie_first + warp;
@@ -97,11 +146,13 @@ k3_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict__ grid, i
       lam = lambda_box_erf(E, hits_e[lane], half_de, sqrt2_sigma);
     }
     if (__ballot_sync(0xffffffffu, lam != 0.0) != 0u) {
-      for (int f0 = 0; f0 < n_fold; f0 += 4) {  // the weight loads of four folds in flight together
+      const double* p = partials + (long long)m * n_chunks * nslots;
+      const double s = lam != 0.0 ? band_norm(p, n_chunks, nslots) : 0.0;
+      for (int f0 = 0; f0 < n_fold; f0 += 4) {  // the partial loads of four folds in flight together
         double w[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          w[k] = (lam != 0.0 && f0 + k < n_fold) ? weights[(long long)(f0 + k) * n_bands + m] : 0.0;
+          w[k] = (lam != 0.0 && f0 + k < n_fold) ? band_weight(p, n_chunks, nslots, f0 + k + 1, s, perform_unfold) : 0.0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (f0 + k >= n_fold) break;
@@ -220,10 +271,10 @@ k3_spectral_function(const double* __restrict__ grid, int nener, double stddev,
 
 void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const double* d_grid,
                     int nener, double sigma, cudaStream_t s) {
-  if (nener <= 0 || max_n_fold <= 0 || n_kpts <= 0) return;
+  if (nener <= 0 || max_n_fold <= 0 || n_kpts <= 0) return;  // set_grid guarantees nener >= 1
   const int bins_per_cta = kK3Threads / 32;
   dim3 grid((unsigned)((nener + bins_per_cta - 1) / bins_per_cta), (unsigned)n_kpts);
-  k3_delta_n<<<grid, kK3Threads, 0, s>>>(d_geoms, d_grid, nener, sigma);
+  k3_finalize_delta_n<<<grid, kK3Threads, 0, s>>>(d_geoms, d_grid, nener, sigma);
 }
 
 void launch_spectral_function(const double* d_grid, int nener, double stddev, const double* d_band_energies,

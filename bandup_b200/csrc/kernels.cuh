@@ -25,7 +25,7 @@ struct CosetCommon {
 constexpr int kK1MaxBlocks = 128;  // CTAs of K1 per SC-kpt (each leaves one row of counts)
 
 // One SC k-point of a batch: the device-resident descriptor every kernel indexes with
-// blockIdx.y (K1, K2b, K3) or finds from the global tile index (K2).  "fold" here means a
+// blockIdx.y (K1, K3) or finds from the global tile index (K2).  "fold" here means a
 // DISTINCT coset among the pc-kpts folding onto the SC-kpt (the host replicates rows of
 // pc-kpts that share one).
 struct KptGeom {
@@ -55,7 +55,7 @@ struct KptGeom {
 // select_coeffs_to_calc_spectral_weights, band_unfolding_routines_mod.f90:586-600).
 // slot[pw] = index of the fold whose coset contains G(pw), else kNoFold; slot_shift lets K2
 // fetch the two slot ids of a 16-byte vector with one aligned 16-bit load whatever the row's
-// alignment.  Per-CTA fold counts go to block_counts (summed by K2b: no atomics, no memset).
+// alignment.  Per-CTA fold counts go to block_counts (summed by K3: no atomics, no memset).
 void launch_coset_classify(const KptGeom* d_geoms, int n_kpts, int max_n_pw, const CosetCommon& cc,
                            cudaStream_t s);
 
@@ -79,13 +79,10 @@ void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_t
                            int n_spinor, int layout, int ctas_per_sm, int n_stages, int sm_count,
                            cudaStream_t s);
 
-// K2b -- deterministic tile combine: s = sum_c norm part, S_f = sum_c fold part,
-// weights[f][b] = s > eps ? S_f / s : S_f (the reference leaves a band with
-// s <= epsilon unscaled, io_routines_mod.f90:1325); also n_selected = sum of K1's CTA counts.
-void launch_weights_finalize(const KptGeom* d_geoms, int n_kpts, int max_bands, int max_n_fold,
-                             cudaStream_t s);
-
-// K3 -- delta_N(k, E_i) = sum_m P_m * lambda(E_i; E_m, delta_e, sigma)
+// K3 -- first the deterministic tile combine of K2's partials (s = sum_c norm part,
+// S_f = sum_c fold part, weights[f][b] = s > eps ? S_f / s : S_f -- the reference leaves a band
+// with s <= epsilon unscaled, io_routines_mod.f90:1325 -- and n_selected = sum of K1's CTA
+// counts), then delta_N(k, E_i) = sum_m P_m * lambda(E_i; E_m, delta_e, sigma)
 // (calc_delta_N_pckpt, band_unfolding_routines_mod.f90:719-757, with lambda :701-716
 // and integral_delta_x_minus_x0, math_mod.f90:181-193).
 void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const double* d_grid,

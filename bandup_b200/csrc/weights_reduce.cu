@@ -6,7 +6,7 @@
 //     (io_routines_mod.f90:1317-1330): s_m = sum_{spinor,G} |C_m(G)|^2
 //   * spectral_weight_for_coeff (band_unfolding_routines_mod.f90:638-644) and its
 //     spinor sum (:1337-1345): S_{m,f} = sum_{G in coset f} |C_m(G)|^2
-// for ALL pc-kpts f folding onto the SC-kpt at once.  P = S/s is formed by K2b.
+// for ALL pc-kpts f folding onto the SC-kpt at once.  P = S/s is formed by K3's finalisation phase.
 //
 // Roofline: HBM.  Algorithmic bytes = n_bands * n_pw * n_spinor * 8 (each
 // complex64 read exactly once) + the slot table (L2/L1-resident, re-read per
@@ -335,46 +335,6 @@ k2_weights_reduce(const KptGeom* __restrict__ geoms, int n_kpts, long long total
   }
 }
 
-// grid (ceil(max_bands * (max_n_fold+1) / 256) + 1, n_kpts); the extra CTA of each k-point adds up
-// K1's per-CTA plane-wave counts (one warp per fold).
-__global__ void __launch_bounds__(256)
-k2b_weights_finalize(const KptGeom* __restrict__ geoms) {
-  const KptGeom& g = geoms[blockIdx.y];
-  const int nslots = g.n_fold + 1;
-  const int n_chunks = g.n_chunks;
-  if (blockIdx.x == gridDim.x - 1) {  // size(selected_coeff_indices) of every fold
-    const int lane = threadIdx.x & 31;
-    for (int f = threadIdx.x >> 5; f < g.n_fold; f += blockDim.x >> 5) {
-      int n = 0;
-      for (int b = lane; b < kK1MaxBlocks; b += 32) n += g.block_counts[b * g.n_fold + f];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-      if (lane == 0) g.n_selected[f] = n;
-    }
-    return;
-  }
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)g.n_bands * nslots) return;
-  const int band = (int)(idx / nslots);
-  const int q = (int)(idx - (long long)band * nslots);
-  const double* p = g.partials + (long long)band * n_chunks * nslots;
-  // every thread of a band needs the norm; the loads are independent, only the adds are ordered
-  double s = 0.0, S = 0.0;
-  for (int c = 0; c < n_chunks; ++c) {
-    const double a = p[(long long)c * nslots], b = p[(long long)c * nslots + q];
-    s += a;
-    S += b;
-  }
-  if (q == 0) {
-    if (g.norms) g.norms[band] = s;
-    return;
-  }
-  // io_routines_mod.f90:1325: bands with s <= epsilon(1.0_dp) stay unscaled
-  const double P = (s > 2.220446049250313e-16) ? S / s : S;
-  // -dont_unfold: spectral_weight = 1.0_dp (band_unfolding_routines_mod.f90:1346-1351)
-  g.weights[(long long)(q - 1) * g.n_bands + band] = g.perform_unfold ? P : 1.0;
-}
-
 constexpr size_t kSmemBudget = 227 * 1024;
 
 size_t k2_fixed_smem(int n_fold) {  // everything but the stage ring
@@ -450,14 +410,6 @@ void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_t
     launch_mode<1>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, s);
   else
     launch_mode<2>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, s);
-}
-
-void launch_weights_finalize(const KptGeom* d_geoms, int n_kpts, int max_bands, int max_n_fold,
-                             cudaStream_t s) {
-  const long long n = (long long)max_bands * (max_n_fold + 1);
-  if (n <= 0 || n_kpts <= 0) return;
-  dim3 grid((unsigned)((n + 255) / 256) + 1u, (unsigned)n_kpts);
-  k2b_weights_finalize<<<grid, 256, 0, s>>>(d_geoms);
 }
 
 }  // namespace bandup

@@ -470,7 +470,7 @@ class GpuUnfolder:
         return int(self._lib.bandup_gpu_batch_workspace_bytes(self.handle, len(descs), descs))
 
     def unfold_device_batch(self, stream: int, descs, d_workspace: int, workspace_bytes: int) -> None:
-        """All k-points of `descs` with one launch per kernel (K1, K2, K2b, K3)."""
+        """All k-points of `descs` with one launch per kernel (K1, K2, K3)."""
         self._check(self._lib.bandup_gpu_unfold_device_batch(
             self.handle, C.c_void_p(stream), len(descs), descs, C.c_void_p(d_workspace), int(workspace_bytes)))
 

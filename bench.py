@@ -7,7 +7,7 @@ SC-kpts/s end to end, and the CPU restatement of the reference timed beside it.
                     [--kpts-per-step 4]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path (K1 coset
-classification -> K2 fused norm + masked |C|^2 reduction -> K2b -> K3 delta_N) over one batch
+classification -> K2 fused norm + masked |C|^2 reduction -> K3 finalisation + delta_N) over one batch
 of `kpts-per-step` SC k-points PER GPU (weak scaling: SC k-points are independent units;
 the only exchange is the gather of the disjoint delta_N rows, done with NCCL when N > 1).
 
@@ -263,7 +263,7 @@ def run_b200(args, sc, rank, world, local_rank):
         dist.barrier()
     else:
         _build.build()
-    from bandup_b200.unfold import (GpuUnfolder, PwWavefunction, LAYOUT_FORTRAN_INMEM, pinned_empty, K_WEIGHTS)
+    from bandup_b200.unfold import (GpuUnfolder, PwWavefunction, LAYOUT_FORTRAN_INMEM, pinned_empty, K_COSET, K_WEIGHTS, K_DELTA_N)
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -308,7 +308,7 @@ def run_b200(args, sc, rank, world, local_rank):
     torch.cuda.synchronize()
     step_bytes = sum(nb * it["n_pw"] * nsp * 8 for it in items)
 
-    # one batch descriptor per step: K1, K2, K2b, K3 are each launched once for all kps k-points
+    # one batch descriptor per step: K1, K2, K3 are each launched once for all kps k-points
     descs, _keep = u.make_batch([dict(
         n_spinor=nsp, n_pw=it["n_pw"], n_bands=nb, layout=LAYOUT_FORTRAN_INMEM,
         band_stride_bytes=it["n_pw"] * nsp * 8, d_coeffs=it["d_c"].data_ptr(), d_g_frac=it["d_g"].data_ptr(),
@@ -355,7 +355,8 @@ def run_b200(args, sc, rank, world, local_rank):
         step()
     torch.cuda.synchronize()
     per_kernel = {name: u.kernel_time(k)[0] / n_breakdown for k, name in
-                  enumerate(["k1_coset_classify", "k2_weights_reduce", "k2b_weights_finalize", "k3_delta_n"])}
+                  ((K_COSET, "k1_coset_classify"), (K_WEIGHTS, "k2_weights_reduce"),
+                   (K_DELTA_N, "k3_finalize_delta_n"))}
     u.set_profiling(True, kernels=[K_WEIGHTS])
     u.reset_kernel_times()
     launches0 = u.launch_count()
@@ -513,7 +514,7 @@ def run_b200(args, sc, rank, world, local_rank):
                        "n_spinor": nsp, "n_pw": [it["n_pw"] for it in items],
                        "n_fold": [it["nf"] for it in items], "nener": nener,
                        "launches": "per SC k-point" if args.per_kpt_launch else
-                       "one launch of K1, K2, K2b, K3 per step (bandup_gpu_unfold_device_batch)",
+                       "one launch of K1, K2, K3 per step (bandup_gpu_unfold_device_batch)",
                        "l2": "inputs larger than L2 (each SC-kpt block >> 126 MB; batch cycles through "
                              f"{step_bytes / 1e9:.1f} GB)",
                        "parallelism": f"SC k-points sharded over {world} GPU(s), NCCL all_gather of delta_N rows"

@@ -332,7 +332,7 @@ typedef struct bandup_gpu_kpt_desc {
 
 size_t bandup_gpu_batch_workspace_bytes(int handle, int n_kpts, const bandup_gpu_kpt_desc *descs);
 /* The same computation as n_kpts calls of bandup_gpu_unfold_device, but every kernel is
- * launched ONCE for the whole batch (four launches in total): the k-points' (band, chunk)
+ * launched ONCE for the whole batch (three launches in total): the k-points' (band, chunk)
  * tiles form one persistent grid, so small k-points (graphene: 12 MB) are no longer
  * launch-bound and large ones lose the per-k-point ramp and tail.  All k-points of a batch
  * share n_spinor and layout. */
@@ -365,7 +365,7 @@ int bandup_gpu_gather_dN(int handle, const double *dN_local, const int64_t *row_
 /* Kernel ids for bandup_gpu_kernel_time */
 #define BANDUP_GPU_K_COSET 0
 #define BANDUP_GPU_K_WEIGHTS 1
-#define BANDUP_GPU_K_FINALIZE 2
+#define BANDUP_GPU_K_FINALIZE 2  /* fused into K_DELTA_N: reports 0 launches */
 #define BANDUP_GPU_K_DELTA_N 3
 #define BANDUP_GPU_K_RHO 4
 #define BANDUP_GPU_K_SYMM_AVG 5

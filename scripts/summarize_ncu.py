@@ -34,7 +34,7 @@ for k, v in per.items():
 own = {k: v for k, v in per.items() if k.startswith("k")}
 hot = {k: v for k, v in own.items() if "synth" not in k}
 tot_hot = sum(t for v in hot.values() for t, _, _ in v)
-lines += ["", "Share within the hot path only (K1, K2, K2b, K3; the synthetic generator and torch fills excluded):", ""]
+lines += ["", "Share within the hot path only (K1, K2, K3; the synthetic generator and torch fills excluded):", ""]
 for k, v in hot.items():
     lines.append(f"* `{k}`: {100 * sum(t for t, _, _ in v) / tot_hot:.1f} %")
 (P / f"{out}_launches.md").write_text("\n".join(lines) + "\n")

@@ -88,4 +88,4 @@ def test_c_driver_matches_oracle(tmp_path, gpu_lib):
             assert g["nsel"] == ns[f]
             assert np.max(np.abs(g["W"] - w[f]) / np.maximum(np.abs(w[f]), 1e-12)) <= 1e-6
             assert np.max(np.abs(g["dN"] - dN[f]) / np.maximum(np.abs(dN[f]), 1e-12)) <= 1e-6
-    assert int(lines[-1].split()[1]) == 4 * len(ks)              # K1, K2, K2b, K3 per submit
+    assert int(lines[-1].split()[1]) == 3 * len(ks)              # K1, K2, K3 per submit
