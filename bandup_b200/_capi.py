@@ -74,6 +74,8 @@ def load() -> C.CDLL:
         "bandup_gpu_last_error": (C.c_char_p, [C.c_int]),
         "bandup_gpu_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
         "bandup_gpu_pinned_free": (C.c_int, [C.c_void_p]),
+        "bandup_gpu_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+        "bandup_gpu_host_unregister": (C.c_int, [C.c_void_p]),
         "bandup_gpu_set_cells": (C.c_int, [C.c_int, c_f64p, c_f64p, C.c_double, c_i32p]),
         "bandup_gpu_set_grid": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_i32p]),
         "bandup_gpu_get_grid": (C.c_int, [C.c_int, c_f64p]),

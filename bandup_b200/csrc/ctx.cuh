@@ -111,6 +111,11 @@ struct Ctx {
   int comm_ranks = 0, comm_rank = -1;
   DevBuf comm_send, comm_recv;
   DevBuf gvec_scratch;  // per-CTA counts/offsets of the device plane-wave enumeration
+  // pageable caller memory goes to the device through these page-locked chunks (upload_block)
+  static constexpr int kStageBufs = 3;
+  PinBuf stage[kStageBufs];
+  cudaEvent_t stage_free[kStageBufs] = {nullptr, nullptr, nullptr};
+  int stage_next = 0;
   DevBuf avg_in, avg_out, avg_tmp;  // symmetry averaging (K8/K9) staging
   DevBuf d_operator;  // current general operator O [n_bands][n_bands] complex128
   int operator_bands = 0;

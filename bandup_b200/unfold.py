@@ -574,6 +574,24 @@ def pinned_empty(nbytes: int) -> np.ndarray:
     return arr
 
 
+def host_register(arr: np.ndarray) -> None:
+    """Page-lock a NumPy array the caller owns, in place (bandup_gpu_host_register), so that
+    submits from it are asynchronous DMA; host_unregister(arr) before it is freed."""
+    lib = _capi.load()
+    if not arr.flags["C_CONTIGUOUS"]:
+        raise ValueError("host_register needs a C-contiguous array")
+    rc = lib.bandup_gpu_host_register(C.c_void_p(arr.ctypes.data), int(arr.nbytes))
+    if rc != 0:
+        raise BandupGpuError(rc, lib.bandup_gpu_last_error(-1).decode())
+
+
+def host_unregister(arr: np.ndarray) -> None:
+    lib = _capi.load()
+    rc = lib.bandup_gpu_host_unregister(C.c_void_p(arr.ctypes.data))
+    if rc != 0:
+        raise BandupGpuError(rc, lib.bandup_gpu_last_error(-1).decode())
+
+
 _POOL = []     # idle page-locked buffers kept for reuse (cudaMallocHost costs ~1 s per GB)
 
 

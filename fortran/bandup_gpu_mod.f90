@@ -16,6 +16,7 @@ implicit none
 private
 public :: bandup_gpu_init, bandup_gpu_finalize, bandup_gpu_last_error, &
           bandup_gpu_abi_version, bandup_gpu_pinned_alloc, bandup_gpu_pinned_free, &
+          bandup_gpu_host_register, bandup_gpu_host_unregister, &
           bandup_gpu_set_cells, bandup_gpu_set_grid, bandup_gpu_get_grid, &
           bandup_gpu_folding_g0, bandup_gpu_fold_map, bandup_gpu_submit_kpt, bandup_gpu_submit_kpt_vasp, &
           bandup_gpu_fetch_kpt, &
@@ -74,6 +75,20 @@ interface
         type(c_ptr), intent(in), value :: ptr
         integer(c_int) :: bandup_gpu_pinned_free
     end function bandup_gpu_pinned_free
+
+    ! page-lock an array Fortran allocated (c_loc(wf%pw_coeffs), storage_size/8 * size bytes)
+    function bandup_gpu_host_register(ptr, bytes) bind(c, name='bandup_gpu_host_register')
+        import c_int, c_ptr, c_size_t
+        type(c_ptr), intent(in), value :: ptr
+        integer(c_size_t), intent(in), value :: bytes
+        integer(c_int) :: bandup_gpu_host_register
+    end function bandup_gpu_host_register
+
+    function bandup_gpu_host_unregister(ptr) bind(c, name='bandup_gpu_host_unregister')
+        import c_int, c_ptr
+        type(c_ptr), intent(in), value :: ptr
+        integer(c_int) :: bandup_gpu_host_unregister
+    end function bandup_gpu_host_unregister
 
     ! crystal%rec_latt_vecs(1:3,1:3) is passed as it lies in memory (column-major,
     ! row i = vector i); M_out receives int_M the same way.

@@ -83,6 +83,12 @@ int bandup_gpu_abi_version(void);
  * submit_kpt's upload is a true asynchronous DMA (optional). */
 int bandup_gpu_pinned_alloc(size_t bytes, void **ptr);
 int bandup_gpu_pinned_free(void *ptr);
+/* The same for memory the caller already owns -- a Fortran ALLOCATEd wf%pw_coeffs, the buffer a
+ * reader fills: page-locks [ptr, ptr + bytes) in place (cudaHostRegister) so uploads from it are
+ * asynchronous DMA at full PCIe rate instead of staged copies.  Register once, reuse the buffer
+ * for every k-point (locking costs about as much as allocating); unregister before freeing it. */
+int bandup_gpu_host_register(void *ptr, size_t bytes);
+int bandup_gpu_host_unregister(void *ptr);
 
 /* ---- run-wide set-up -------------------------------------------------- */
 
