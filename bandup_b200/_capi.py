@@ -120,6 +120,8 @@ def load() -> C.CDLL:
         "bandup_gpu_comm_finalize": (C.c_int, [C.c_int]),
         "bandup_gpu_gather_dN": (C.c_int, [C.c_int, c_f64p, C.POINTER(C.c_int64), C.c_int64, c_f64p,
                                            C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]),
+        "bandup_gpu_gather_rows": (C.c_int, [C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int64), C.c_int64, c_f64p,
+                                             C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]),
         "bandup_gpu_set_profiling": (C.c_int, [C.c_int, C.c_int]),
         "bandup_gpu_set_profiling_mask": (C.c_int, [C.c_int, C.c_uint]),
         "bandup_gpu_kernel_time": (C.c_int, [C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int64)]),

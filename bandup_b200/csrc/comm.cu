@@ -95,12 +95,21 @@ int bandup_gpu_gather_dN(int handle, const double* dN_local, const int64_t* row_
                          double* dN_all, int64_t* row_ids_all, int64_t capacity_rows, int64_t* n_total) {
   Ctx* c = get(handle);
   if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  if (!c->comm) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_comm_init first");
   if (!c->grid_set) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_set_grid first");
-  if (n_local < 0 || (n_local > 0 && (!dN_local || !row_ids_local)) || !n_total)
+  return bandup_gpu_gather_rows(handle, c->nener, dN_local, row_ids_local, n_local, dN_all, row_ids_all,
+                                capacity_rows, n_total);
+}
+
+int bandup_gpu_gather_rows(int handle, int row_len, const double* dN_local, const int64_t* row_ids_local,
+                           int64_t n_local, double* dN_all, int64_t* row_ids_all, int64_t capacity_rows,
+                           int64_t* n_total) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (!c->comm) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_comm_init first");
+  if (row_len < 1 || n_local < 0 || (n_local > 0 && (!dN_local || !row_ids_local)) || !n_total)
     return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad gather arguments");
   const NcclApi& n = nccl_api();
-  const int R = c->comm_ranks, nener = c->nener;
+  const int R = c->comm_ranks, nener = row_len;
   cudaSetDevice(c->device);
   cudaStream_t s = c->compute;
   // 1. how many rows everyone has

@@ -601,7 +601,6 @@ int main(int argc, char** argv) {
   for (int i : used) n_pck_mine += folds[(size_t)i].size();
   if (n_parsed != n_pck_mine) die("ERROR: not every pc-kpt could be unfolded.");
   if (n_ranks > 1) {  // the path's only collective: every rank's disjoint delta_N rows (ncclAllGather)
-    if (spinor) die("ERROR: spinor output is supported by BandUP_gpu.x with one rank only.");
     std::vector<double> mine(n_pck_mine * (size_t)nener), all(n_pck * (size_t)nener);
     std::vector<int64_t> ids, all_ids(n_pck);
     for (int i : used)
@@ -615,6 +614,23 @@ int main(int argc, char** argv) {
     if ((size_t)n_total != n_pck) die("ERROR: not every pc-kpt could be unfolded.");
     for (size_t r = 0; r < n_pck; ++r)
       std::memcpy(&dN_all[(size_t)all_ids[r] * (size_t)nener], &all[r * (size_t)nener], sizeof(double) * (size_t)nener);
+    {  // spinor or not is learnt from the k-points a rank submitted: agree on it (a rank may have none)
+      double flag = spinor ? 1.0 : 0.0, flags[1024];
+      int64_t me = rank, who[1024], n_flags = 0;
+      gpu_check(h, bandup_gpu_gather_rows(h, 1, &flag, &me, 1, flags, who, 1024, &n_flags), "gather_rows");
+      for (int64_t r = 0; r < n_flags; ++r) spinor = spinor || flags[r] != 0.0;
+    }
+    if (spinor) {  // the spin columns travel the same way: rows of 3*nener doubles
+      const size_t rl = (size_t)nener * 3;
+      if (sigma_all.empty()) sigma_all.assign(n_pck * rl, 0.0);
+      std::vector<double> smine(n_pck_mine * rl), sall(n_pck * rl);
+      for (size_t k = 0; k < ids.size(); ++k)
+        std::memcpy(&smine[k * rl], &sigma_all[(size_t)ids[k] * rl], sizeof(double) * rl);
+      gpu_check(h, bandup_gpu_gather_rows(h, (int)rl, smine.data(), ids.data(), (int64_t)ids.size(), sall.data(),
+                                          all_ids.data(), (int64_t)n_pck, &n_total), "gather_rows");
+      for (size_t r = 0; r < n_pck; ++r)
+        std::memcpy(&sigma_all[(size_t)all_ids[r] * rl], &sall[r * rl], sizeof(double) * rl);
+    }
     gpu_check(h, bandup_gpu_comm_finalize(h), "comm_finalize");
     if (rank != 0) {  // rank 0 writes the files
       for (auto b : bufs) bandup_gpu_pinned_free(b);

@@ -501,18 +501,30 @@ class GpuUnfolder:
     def gather_dN(self, dN_local: np.ndarray, row_ids_local: np.ndarray):
         """ncclAllGather of the disjoint delta_N rows of all ranks; returns (dN_all, row_ids_all)
         in ascending global row id on every rank."""
-        d = np.ascontiguousarray(dN_local, dtype=np.float64).reshape(-1, self.nener)
+        return self.gather_rows(np.asarray(dN_local, dtype=np.float64).reshape(-1, self.nener), row_ids_local)
+
+    def gather_rows(self, rows_local: np.ndarray, row_ids_local: np.ndarray):
+        """The same collective for rows of any shape (sigma: (n, nener, 3)); returns
+        (rows_all, row_ids_all) in ascending global row id on every rank."""
+        r = np.ascontiguousarray(rows_local, dtype=np.float64)
         ids = np.ascontiguousarray(row_ids_local, dtype=np.int64).reshape(-1)
+        if r.ndim < 2 or r.shape[0] != ids.shape[0]:
+            raise ValueError("rows_local must be (n_rows, ...) with one row id per row")
+        shape = r.shape[1:]
+        row_len = int(np.prod(shape))
+        d = r.reshape(-1, row_len)
         i64p = C.POINTER(C.c_int64)
         tot = C.c_int64(0)
-        self._check(self._lib.bandup_gpu_gather_dN(self.handle, d.ctypes.data_as(c_f64p), ids.ctypes.data_as(i64p),
-                                                   ids.shape[0], None, None, 0, C.byref(tot)))
-        out = np.zeros((tot.value, self.nener), dtype=np.float64)
+        self._check(self._lib.bandup_gpu_gather_rows(self.handle, row_len, d.ctypes.data_as(c_f64p),
+                                                     ids.ctypes.data_as(i64p), ids.shape[0], None, None, 0,
+                                                     C.byref(tot)))
+        out = np.zeros((tot.value, row_len), dtype=np.float64)
         oid = np.zeros(tot.value, dtype=np.int64)
-        self._check(self._lib.bandup_gpu_gather_dN(self.handle, d.ctypes.data_as(c_f64p), ids.ctypes.data_as(i64p),
-                                                   ids.shape[0], out.ctypes.data_as(c_f64p), oid.ctypes.data_as(i64p),
-                                                   tot.value, C.byref(tot)))
-        return out, oid
+        self._check(self._lib.bandup_gpu_gather_rows(self.handle, row_len, d.ctypes.data_as(c_f64p),
+                                                     ids.ctypes.data_as(i64p), ids.shape[0],
+                                                     out.ctypes.data_as(c_f64p), oid.ctypes.data_as(i64p),
+                                                     tot.value, C.byref(tot)))
+        return out.reshape((tot.value,) + shape), oid
 
     # -- instrumentation ------------------------------------------------------
     def set_profiling(self, enabled: bool, kernels=None) -> None:

@@ -28,6 +28,7 @@ public :: bandup_gpu_init, bandup_gpu_finalize, bandup_gpu_last_error, &
           bandup_gpu_orb_contrib_matrix, bandup_gpu_set_operator, bandup_gpu_unfold_operator, &
           bandup_gpu_symm_average, bandup_gpu_symm_average_rho, &
           bandup_gpu_comm_unique_id, bandup_gpu_comm_init, bandup_gpu_comm_finalize, bandup_gpu_gather_dN, &
+          bandup_gpu_gather_rows, &
           bandup_gpu_unfold_kpt_f, bandup_gpu_error_message
 public :: BANDUP_GPU_OK, BANDUP_GPU_LAYOUT_FORTRAN_INMEM, BANDUP_GPU_LAYOUT_VASP_RECORD, &
           BANDUP_GPU_MAX_FOLDS
@@ -335,6 +336,20 @@ interface
         integer(c_int64_t), intent(out) :: n_total
         integer(c_int) :: bandup_gpu_gather_dN
     end function bandup_gpu_gather_dN
+
+    ! the same for rows of row_len doubles (sigma: 3*nener)
+    function bandup_gpu_gather_rows(handle, row_len, rows_local, row_ids_local, n_local, rows_all, row_ids_all, &
+                                    capacity_rows, n_total) bind(c, name='bandup_gpu_gather_rows')
+        import c_int, c_int64_t, c_double, c_ptr
+        integer(c_int), intent(in), value :: handle, row_len
+        real(c_double), intent(in) :: rows_local(*)
+        integer(c_int64_t), intent(in) :: row_ids_local(*)
+        integer(c_int64_t), intent(in), value :: n_local
+        type(c_ptr), intent(in), value :: rows_all, row_ids_all
+        integer(c_int64_t), intent(in), value :: capacity_rows
+        integer(c_int64_t), intent(out) :: n_total
+        integer(c_int) :: bandup_gpu_gather_rows
+    end function bandup_gpu_gather_rows
 
     function bandup_gpu_set_profiling(handle, enabled) bind(c, name='bandup_gpu_set_profiling')
         import c_int

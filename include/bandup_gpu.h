@@ -366,6 +366,11 @@ int bandup_gpu_gather_dN(int handle, const double *dN_local, const int64_t *row_
                          int64_t n_local, double *dN_all, int64_t *row_ids_all,
                          int64_t capacity_rows, int64_t *n_total);
 
+/* The same collective for rows of any length (the spin columns: sigma rows of 3*nener doubles). */
+int bandup_gpu_gather_rows(int handle, int row_len, const double *rows_local,
+                           const int64_t *row_ids_local, int64_t n_local, double *rows_all,
+                           int64_t *row_ids_all, int64_t capacity_rows, int64_t *n_total);
+
 /* ---- instrumentation ---------------------------------------------------- */
 
 /* Kernel ids for bandup_gpu_kernel_time */

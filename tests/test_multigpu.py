@@ -42,6 +42,11 @@ def _worker(rank, world, tmp, ret):
         job = ShardedUnfoldJob(u, sc.n_sc_kpts, costs, load, rank=rank, world_size=world)
         dN, rid, _ = job.run_local()
         allrows, allids = u.gather_dN(dN, rid)
+        # rows of another shape through the same collective (what the spin columns use)
+        extra = np.stack([dN * (rank + 1), -dN, dN + 1.0], axis=2)          # (n, nener, 3)
+        xrows, xids = u.gather_rows(extra, rid)
+        assert np.array_equal(xids, allids) and xrows.shape == (len(allids), dN.shape[1], 3)
+        assert np.array_equal(xrows[:, :, 1], -allrows) and np.array_equal(xrows[:, :, 2], allrows + 1.0)
         ret[rank] = (allrows, allids, job.my_block, len(rid))
         u.comm_finalize()
 
@@ -70,16 +75,17 @@ def test_two_gpus_shard_and_nccl_gather():
         assert np.max(np.abs(got - dN) / np.maximum(np.abs(dN), 1e-12)) <= 1e-6
 
 
-def test_host_exe_two_ranks(tmp_path, gpu_lib):
-    """BandUP_gpu.x as two processes on two GPUs (-n_ranks 2): the gathered output file equals the
-    one-rank output."""
+@pytest.mark.parametrize("spinor", [False, True])
+def test_host_exe_two_ranks(tmp_path, gpu_lib, spinor):
+    """BandUP_gpu.x as two processes on two GPUs (-n_ranks 2): the gathered output file (with the
+    five spin columns for a spinor WAVECAR) equals the one-rank output."""
     import subprocess
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from bandup_b200 import bandup_files as BF
     from tests.test_host_exe import EXE, _job
-    _job(tmp_path, False)
+    _job(tmp_path, spinor)
     common = [str(EXE), "-no_symm_sckpts", "-no_symm_avg"]
     r = subprocess.run(common + ["-out_file_nosymm", "one.dat"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
