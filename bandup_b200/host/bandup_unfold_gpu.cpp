@@ -368,8 +368,6 @@ int main(int argc, char** argv) {
   const int n_ranks = std::atoi(args.get("-n_ranks", "1").c_str());
   const int rank = std::atoi(args.get("-rank", "0").c_str());
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks) die("ERROR: bad -rank / -n_ranks");
-  if (n_ranks > 1 && (write_udo))
-    die("ERROR: -write_unf_dens_op is supported by BandUP_gpu.x with one rank only.");
 
   int h = -1;
   gpu_check(-1, bandup_gpu_init(std::atoi(args.get("-device", std::to_string(rank)).c_str()), &h), "bandup_gpu_init");
@@ -614,11 +612,49 @@ int main(int argc, char** argv) {
     if ((size_t)n_total != n_pck) die("ERROR: not every pc-kpt could be unfolded.");
     for (size_t r = 0; r < n_pck; ++r)
       std::memcpy(&dN_all[(size_t)all_ids[r] * (size_t)nener], &all[r * (size_t)nener], sizeof(double) * (size_t)nener);
+    // the unfolding-density operators have no fixed row length: the other ranks leave theirs in a
+    // part file next to the output (one node, one file system) and rank 0 merges them after the
+    // next collective, which doubles as the barrier
+    const auto part_name = [&](int r) { return udo_file + ".part" + std::to_string(r); };
+    if (write_udo && rank != 0) {
+      std::FILE* pf = std::fopen(part_name(rank).c_str(), "wb");
+      if (!pf) die("ERROR: cannot write " + part_name(rank));
+      for (int64_t r : ids) {
+        const RhoRows& rr = rho_of[(size_t)r];
+        const int64_t head[2] = {r, (int64_t)rr.ie.size()};
+        std::fwrite(head, sizeof(int64_t), 2, pf);
+        std::fwrite(rr.ie.data(), sizeof(int32_t), rr.ie.size(), pf);
+        std::fwrite(rr.m1.data(), sizeof(int32_t), rr.m1.size(), pf);
+        std::fwrite(rr.m2.data(), sizeof(int32_t), rr.m2.size(), pf);
+        std::fwrite(rr.re.data(), sizeof(float), rr.re.size(), pf);
+        std::fwrite(rr.im.data(), sizeof(float), rr.im.size(), pf);
+      }
+      if (std::fclose(pf) != 0) die("ERROR: cannot write " + part_name(rank));
+    }
     {  // spinor or not is learnt from the k-points a rank submitted: agree on it (a rank may have none)
       double flag = spinor ? 1.0 : 0.0, flags[1024];
       int64_t me = rank, who[1024], n_flags = 0;
       gpu_check(h, bandup_gpu_gather_rows(h, 1, &flag, &me, 1, flags, who, 1024, &n_flags), "gather_rows");
       for (int64_t r = 0; r < n_flags; ++r) spinor = spinor || flags[r] != 0.0;
+    }
+    if (write_udo && rank == 0) {
+      for (int r = 1; r < n_ranks; ++r) {
+        std::FILE* pf = std::fopen(part_name(r).c_str(), "rb");
+        if (!pf) die("ERROR: cannot read " + part_name(r));
+        int64_t head[2];
+        while (std::fread(head, sizeof(int64_t), 2, pf) == 2) {
+          if (head[0] < 0 || (size_t)head[0] >= n_pck || head[1] < 0) die("ERROR: corrupt " + part_name(r));
+          RhoRows& rr = rho_of[(size_t)head[0]];
+          const size_t n = (size_t)head[1];
+          rr.ie.resize(n); rr.m1.resize(n); rr.m2.resize(n); rr.re.resize(n); rr.im.resize(n);
+          if (std::fread(rr.ie.data(), sizeof(int32_t), n, pf) != n || std::fread(rr.m1.data(), sizeof(int32_t), n, pf) != n ||
+              std::fread(rr.m2.data(), sizeof(int32_t), n, pf) != n || std::fread(rr.re.data(), sizeof(float), n, pf) != n ||
+              std::fread(rr.im.data(), sizeof(float), n, pf) != n)
+            die("ERROR: truncated " + part_name(r));
+        }
+        std::fclose(pf);
+        std::remove(part_name(r).c_str());
+      }
     }
     if (spinor) {  // the spin columns travel the same way: rows of 3*nener doubles
       const size_t rl = (size_t)nener * 3;

@@ -107,6 +107,19 @@ def test_host_exe_two_ranks(tmp_path, gpu_lib, spinor):
     assert all(p.returncode == 0 for p in procs), outs
     assert np.array_equal(BF.read_band_struc(tmp_path / "one.dat"), BF.read_band_struc(tmp_path / "dyn.dat"))
     assert outs[0][0].count("SC-kpt #") + outs[1][0].count("SC-kpt #") == n0 + n1
+    # the unfolding-density operator file with two ranks (part files merged by rank 0)
+    udo = ["-write_unf_dens_op", "-output_file_only_user_selec_direcs_unf_dens_op"]
+    r = subprocess.run(common + ["-out_file_nosymm", "one_b.dat"] + udo + ["one_udo.dat"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    procs = [subprocess.Popen(common + ["-out_file_nosymm", "two_b.dat", "-n_ranks", "2", "-rank", str(k),
+                                        "-nccl_id_file", "ncclid3"] + udo + ["two_udo.dat"], cwd=tmp_path,
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for k in (0, 1)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    one, two = (tmp_path / "one_udo.dat").read_text(), (tmp_path / "two_udo.dat").read_text()
+    assert one == two and "UnfDensOp[m1,m2]" in one
+    assert not list(tmp_path.glob("two_udo.dat.part*"))
 
 
 def test_bench_two_ranks_prints_one_json_line():
