@@ -124,6 +124,53 @@ void resolve_pending(Ctx* c) {
   }
 }
 
+// Host -> device copy of a coefficient block on the copy stream.  Page-locked memory
+// (bandup_gpu_pinned_alloc, bandup_gpu_host_register) is a single asynchronous DMA.  Pageable
+// memory -- what a Fortran ALLOCATE gives the reference's reader -- would make cudaMemcpyAsync
+// stage it internally at 2-3 GB/s (measured); here it is cut into 16 MB chunks that a few host
+// threads copy into a ring of page-locked buffers while the previous chunks are on the wire.
+constexpr size_t kStageChunk = size_t(16) << 20;
+
+int upload_block(Ctx* c, void* dst, const void* src, size_t bytes) {
+  cudaPointerAttributes attr{};
+  const bool locked = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
+                      (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+  cudaGetLastError();  // an unregistered pointer may leave an error behind on older drivers
+  if (locked || bytes < (size_t(1) << 20)) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->copy));
+    return BANDUP_GPU_OK;
+  }
+  unsigned hw = std::thread::hardware_concurrency();
+  int n_thr = (int)std::min<unsigned>(8u, hw > 1 ? hw / 2 : 1u);
+  if (const char* e = std::getenv("BANDUP_GPU_STAGE_THREADS")) n_thr = std::max(1, std::atoi(e));
+  // small blocks: smaller chunks, so that the wire starts early and the ring still overlaps
+  const size_t chunk = std::min(kStageChunk, std::max(size_t(1) << 20, (bytes / 8 + 4095) & ~size_t(4095)));
+  for (size_t off = 0; off < bytes; off += chunk) {
+    const size_t n = std::min(chunk, bytes - off);
+    const int k = c->stage_next;
+    c->stage_next = (k + 1) % Ctx::kStageBufs;
+    CU(c->stage[k].reserve(kStageChunk));
+    if (!c->stage_free[k])
+      CU(cudaEventCreateWithFlags(&c->stage_free[k], cudaEventDisableTiming));
+    else
+      CU(cudaEventSynchronize(c->stage_free[k]));  // its previous chunk has left the buffer
+    char* s = static_cast<char*>(c->stage[k].p);
+    const char* u = static_cast<const char*>(src) + off;
+    const size_t part = ((n + (size_t)n_thr - 1) / (size_t)n_thr + 4095) & ~size_t(4095);
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_thr; ++t) {
+      const size_t a = part * (size_t)t;
+      if (a >= n) break;
+      pool.emplace_back([=] { std::memcpy(s + a, u + a, std::min(part, n - a)); });
+    }
+    std::memcpy(s, u, std::min(part, n));
+    for (auto& th : pool) th.join();
+    CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, s, n, cudaMemcpyHostToDevice, c->copy));
+    CU(cudaEventRecord(c->stage_free[k], c->copy));
+  }
+  return BANDUP_GPU_OK;
+}
+
 namespace {
 
 // ---- the per-k-point kernel sequence ---------------------------------------
@@ -222,53 +269,6 @@ struct BatchItem {  // one SC k-point of a launch batch (host side)
   const double* w_unique = nullptr;
   const uint8_t* d_slot = nullptr;
 };
-
-// Host -> device copy of a coefficient block on the copy stream.  Page-locked memory
-// (bandup_gpu_pinned_alloc, bandup_gpu_host_register) is a single asynchronous DMA.  Pageable
-// memory -- what a Fortran ALLOCATE gives the reference's reader -- would make cudaMemcpyAsync
-// stage it internally at 2-3 GB/s (measured); here it is cut into 16 MB chunks that a few host
-// threads copy into a ring of page-locked buffers while the previous chunks are on the wire.
-constexpr size_t kStageChunk = size_t(16) << 20;
-
-int upload_block(Ctx* c, void* dst, const void* src, size_t bytes) {
-  cudaPointerAttributes attr{};
-  const bool locked = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
-                      (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
-  cudaGetLastError();  // an unregistered pointer may leave an error behind on older drivers
-  if (locked || bytes < (size_t(1) << 20)) {
-    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->copy));
-    return BANDUP_GPU_OK;
-  }
-  unsigned hw = std::thread::hardware_concurrency();
-  int n_thr = (int)std::min<unsigned>(8u, hw > 1 ? hw / 2 : 1u);
-  if (const char* e = std::getenv("BANDUP_GPU_STAGE_THREADS")) n_thr = std::max(1, std::atoi(e));
-  // small blocks: smaller chunks, so that the wire starts early and the ring still overlaps
-  const size_t chunk = std::min(kStageChunk, std::max(size_t(1) << 20, (bytes / 8 + 4095) & ~size_t(4095)));
-  for (size_t off = 0; off < bytes; off += chunk) {
-    const size_t n = std::min(chunk, bytes - off);
-    const int k = c->stage_next;
-    c->stage_next = (k + 1) % Ctx::kStageBufs;
-    CU(c->stage[k].reserve(kStageChunk));
-    if (!c->stage_free[k])
-      CU(cudaEventCreateWithFlags(&c->stage_free[k], cudaEventDisableTiming));
-    else
-      CU(cudaEventSynchronize(c->stage_free[k]));  // its previous chunk has left the buffer
-    char* s = static_cast<char*>(c->stage[k].p);
-    const char* u = static_cast<const char*>(src) + off;
-    const size_t part = ((n + (size_t)n_thr - 1) / (size_t)n_thr + 4095) & ~size_t(4095);
-    std::vector<std::thread> pool;
-    for (int t = 1; t < n_thr; ++t) {
-      const size_t a = part * (size_t)t;
-      if (a >= n) break;
-      pool.emplace_back([=] { std::memcpy(s + a, u + a, std::min(part, n - a)); });
-    }
-    std::memcpy(s, u, std::min(part, n));
-    for (auto& th : pool) th.join();
-    CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, s, n, cudaMemcpyHostToDevice, c->copy));
-    CU(cudaEventRecord(c->stage_free[k], c->copy));
-  }
-  return BANDUP_GPU_OK;
-}
 
 // The descriptors of a batch travel through a small ring of pinned/device blocks so that a
 // call never waits for the previous one (each entry carries the event of its own upload).
@@ -482,6 +482,7 @@ int bandup_gpu_finalize(int handle) {
   }
   c->d_grid.release();
   c->d_operator.release();
+  c->d_proj_dual.release(); c->d_proj.release(); c->d_ao_mask.release(); c->d_proj_ener.release();
   c->avg_in.release(); c->avg_out.release(); c->avg_tmp.release();
   for (int k = 0; k < Ctx::kStageBufs; ++k) {
     c->stage[k].release();

@@ -273,16 +273,20 @@ int bandup_gpu_orb_contrib_matrix(int handle, int n_bands, int n_ao, const doubl
   cudaStream_t s = c->compute;
   const size_t mat = sizeof(double) * 2 * (size_t)n_bands * (size_t)n_ao;
   const size_t obytes = sizeof(double) * 2 * (size_t)n_bands * (size_t)n_bands;
-  DevBuf d_dual, d_proj, d_mask, d_ener;
+  // device copies of the projections live in the context: one k-point after another reuses them
+  DevBuf &d_dual = c->d_proj_dual, &d_proj = c->d_proj, &d_mask = c->d_ao_mask, &d_ener = c->d_proj_ener;
   cudaError_t e = cudaSuccess;
-  if ((e = d_dual.reserve(mat)) == cudaSuccess && (e = d_proj.reserve(mat)) == cudaSuccess &&
-      (e = d_mask.reserve((size_t)n_ao)) == cudaSuccess &&
+  if ((e = cudaStreamSynchronize(s)) == cudaSuccess && (e = d_dual.reserve(mat)) == cudaSuccess &&
+      (e = d_proj.reserve(mat)) == cudaSuccess && (e = d_mask.reserve((size_t)n_ao)) == cudaSuccess &&
       (e = d_ener.reserve(sizeof(double) * (size_t)n_bands)) == cudaSuccess &&
-      (e = cudaStreamSynchronize(s)) == cudaSuccess && (e = c->d_operator.reserve(obytes)) == cudaSuccess) {
-    cudaMemcpyAsync(d_dual.p, dual, mat, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(d_proj.p, proj, mat, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(d_mask.p, ao_mask, (size_t)n_ao, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(d_ener.p, band_energies, sizeof(double) * (size_t)n_bands, cudaMemcpyHostToDevice, s);
+      (e = c->d_operator.reserve(obytes)) == cudaSuccess) {
+    // the two projection matrices are the bulk (C4: 2 x 15 MB) and usually pageable NumPy memory
+    int rc = upload_block(c, d_dual.p, dual, mat);
+    if (!rc) rc = upload_block(c, d_proj.p, proj, mat);
+    if (rc) return rc;
+    cudaMemcpyAsync(d_mask.p, ao_mask, (size_t)n_ao, cudaMemcpyHostToDevice, c->copy);
+    cudaMemcpyAsync(d_ener.p, band_energies, sizeof(double) * (size_t)n_bands, cudaMemcpyHostToDevice, c->copy);
+    if ((e = cudaStreamSynchronize(c->copy)) != cudaSuccess) return cuda_fail(c, e, "uploading the projections");
     {
       KernelScope k(c, BANDUP_GPU_K_RHO, s);
       launch_orb_contrib(n_bands, n_ao, d_dual.p, d_proj.p, static_cast<const uint8_t*>(d_mask.p),
@@ -292,7 +296,6 @@ int bandup_gpu_orb_contrib_matrix(int handle, int n_bands, int n_ao, const doubl
     if (e == cudaSuccess && O_out) e = cudaMemcpyAsync(O_out, c->d_operator.p, obytes, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   }
-  d_dual.release(); d_proj.release(); d_mask.release(); d_ener.release();
   if (e != cudaSuccess) return cuda_fail(c, e, "bandup_gpu_orb_contrib_matrix");
   c->operator_bands = n_bands;
   return BANDUP_GPU_OK;

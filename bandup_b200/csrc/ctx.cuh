@@ -117,6 +117,7 @@ struct Ctx {
   cudaEvent_t stage_free[kStageBufs] = {nullptr, nullptr, nullptr};
   int stage_next = 0;
   DevBuf avg_in, avg_out, avg_tmp;  // symmetry averaging (K8/K9) staging
+  DevBuf d_proj_dual, d_proj, d_ao_mask, d_proj_ener;  // inputs of the orbital-contribution matrix
   DevBuf d_operator;  // current general operator O [n_bands][n_bands] complex128
   int operator_bands = 0;
   int nener = 0;
@@ -173,6 +174,9 @@ struct KernelScope {  // brackets one launch with events when profiling is on
     }
   }
 };
+
+// Host -> device copy on the copy stream; pageable sources go through the pinned staging ring.
+int upload_block(Ctx* c, void* dst, const void* src, size_t bytes);
 
 // The flight that still holds SC-kpt `ikpt` after it has been fetched (rho, Pauli vectors, the
 // spectral function work on it); error when it is still in flight or its buffers were reused.
