@@ -216,15 +216,15 @@ struct WorkspaceLayout {
 
 // batch_n: k-points launched together -- the K2 tile size is chosen so that the WHOLE launch
 // has enough tiles to balance the persistent grid (k-points of a job are alike)
-int pick_chunk_vecs(const Ctx* c, long long row_elems, int n_bands, int batch_n) {
+int pick_chunk_vecs(const Ctx* c, long long row_elems, int n_bands, int batch_n, int n_spinor) {
   const long long rows = (long long)n_bands * (batch_n > 0 ? batch_n : 1);
   return weights_pick_chunk_vecs(c->chunk_vecs, row_elems, (int)(rows > 2000000000LL ? 2000000000LL : rows),
-                                 c->sm_count);
+                                 c->sm_count, n_spinor);
 }
 
 WorkspaceLayout workspace_layout(const Ctx* c, int n_spinor, int n_pw, int n_bands, int n_fold, int batch_n = 1) {
   WorkspaceLayout w;
-  const int cv = pick_chunk_vecs(c, (long long)n_pw * n_spinor, n_bands, batch_n);
+  const int cv = pick_chunk_vecs(c, (long long)n_pw * n_spinor, n_bands, batch_n, n_spinor);
   const int n_chunks = weights_num_chunks((long long)n_pw * n_spinor, cv);
   // distinct cosets <= pc-kpts: room for the worst case number of passes
   const size_t max_passes = (size_t)((n_fold > 0 ? n_fold : 1) + kMaxFolds - 1) / kMaxFolds;
@@ -339,7 +339,7 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
       g.block_counts = reinterpret_cast<int*>(it.ws + wl.counts_off) + (size_t)kK1MaxBlocks * (size_t)u0;
       g.n_selected = ns_rows + u0;
       g.n_fold = nf;
-      g.chunk_vecs = pick_chunk_vecs(c, g.row_elems, it.n_bands, n);
+      g.chunk_vecs = pick_chunk_vecs(c, g.row_elems, it.n_bands, n, it.n_spinor);
       g.n_chunks = weights_num_chunks(g.row_elems, g.chunk_vecs);
       g.perform_unfold = c->perform_unfold ? 1 : 0;
       g.tile_begin = tiles;

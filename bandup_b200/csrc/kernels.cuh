@@ -68,7 +68,7 @@ void launch_selected_lists(const uint8_t* d_slot, size_t slot_pitch, int n_pw, i
 int weights_num_chunks(long long row_elems, int chunk_vecs);
 size_t weights_partials_bytes(int n_bands, int n_chunks, int n_fold);
 // requested > 0: rounded up to whole stages; 0: chosen from the block shape
-int weights_pick_chunk_vecs(int requested, long long row_elems, int n_bands, int sm_count);
+int weights_pick_chunk_vecs(int requested, long long row_elems, int n_bands, int sm_count, int n_spinor);
 int weights_max_folds_supported();
 
 // K2 -- the roofline kernel: one pass over every complex64 coefficient of every k-point of

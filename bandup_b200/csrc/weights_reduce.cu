@@ -26,6 +26,8 @@
 // (conflict-free: bin f of thread t lives at bins[f*256 + t]); then release the
 // stage through its `empty` barrier.  Warp shuffles + one shared-memory hop
 // reduce the tile.  Fully deterministic: no atomics, fixed combination order.
+#include <cmath>
+
 #include "kernels.cuh"
 
 namespace bandup {
@@ -370,17 +372,40 @@ void launch_mode(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int 
 
 }  // namespace
 
-// Tile size.  Large tiles amortise the per-tile reduction (measured on B200, 3000 x 100k
-// block: 64 KB tiles 5.9 TB/s, 128 KB 6.7, 256 KB 6.75); small blocks need enough tiles to
-// balance the persistent grid, so the tile shrinks (down to one 16 KB stage) until there are
-// at least 6 tiles per CTA.
-int weights_pick_chunk_vecs(int requested, long long row_elems, int n_bands, int sm_count) {
+// Tile size, from a small cost model fitted to B200 sweeps (profiles/r01_tile_sweep.md): a CTA of
+// the full persistent grid streams ~24 GB/s (7.2 TB/s / 296), a tile costs its bytes at that rate
+// plus the part of its epilogue (shared-memory reduction, partials, two barriers: ~1.2 us) that the
+// stage ring does not hide.  Large tiles amortise
+// the epilogue (3000 x 100k block: 64 KB tiles 5.9 TB/s, 128 KB 6.7, 256 KB 7.25, 512 KB 7.33); with few rows
+// the number of ROUNDS of the grid is what counts (graphene, 512 rows of 184 KB: one tile per row
+// 25.5 us, six 32 KB tiles per row 31.0 us).  The candidate with the lowest estimate wins.
+int weights_pick_chunk_vecs(int requested, long long row_elems, int n_bands, int sm_count, int n_spinor) {
   if (requested > 0) return ((requested + kStageVecs - 1) / kStageVecs) * kStageVecs;
-  const long long nv = row_elems / 2;
-  const long long want_tiles = 6LL * sm_count * 2;
-  int cv = 16 * kStageVecs;
-  while (cv > kStageVecs && (long long)n_bands * ((nv + cv - 1) / cv) < want_tiles) cv >>= 1;
-  return cv;
+  const double nv = (double)(row_elems / 2 > 0 ? row_elems / 2 : 1);
+  const double grid = 2.0 * sm_count, rows = n_bands > 0 ? n_bands : 1;
+  const double t_epi = 0.5e-6, full_rate = 7.2e12 / grid;  // what the stage ring does not hide of the epilogue
+  // 512 KB tiles pay off for scalar rows (C5 +1.1 %); spinor rows measured best at 256 KB
+  const int cv_max = (n_spinor == 1 ? 32 : 16) * kStageVecs;
+  int best = cv_max;
+  double best_t = 1e30;
+  for (int cv = cv_max; cv >= kStageVecs; cv >>= 1) {
+    const double chunks = std::ceil(nv / cv), tiles = rows * chunks;
+    const double active = tiles < grid ? tiles : grid;
+    double rate = 7.2e12 / active;  // fewer CTAs than the grid: each gets more, up to what one ring sustains
+    if (rate > 48e9) rate = 48e9;
+    if (rate < full_rate) rate = full_rate;
+    const double tile_vecs = nv < cv ? nv : cv;
+    double t;
+    if (tiles >= 4.0 * grid)
+      t = rows * (nv * 16.0 / rate + chunks * t_epi) / grid + (tile_vecs * 16.0 / rate + t_epi);
+    else
+      t = std::ceil(tiles / grid) * (tile_vecs * 16.0 / rate + t_epi);
+    if (t < best_t * 0.999) {  // ties go to the larger tile
+      best_t = t;
+      best = cv;
+    }
+  }
+  return best;
 }
 
 int weights_num_chunks(long long row_elems, int chunk_vecs) {
