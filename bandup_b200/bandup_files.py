@@ -324,7 +324,6 @@ def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_f
     # spinor is decided on the device when the k-point is submitted)
     spinor_kpts, energies_of_job = set(), {}
     sc_k = np.array([wc.kpt_header(i + 1, spin_channel).kpt_frac_coords for i in range(wc.nkpts)])
-    from .wavecar import fold_pckpts_onto_sckpts
     unfolder.verify_commens(b_pc, wc.B_matrix)               # the fold map needs the SC lattice on the device
     fs, _, _ = unfolder.get_geom_unfolding_relations(all_k, sc_k @ wc.B_matrix, n_sckpts_to_skip=n_sckpts_to_skip)
     folds = [[] for _ in range(wc.nkpts)]
