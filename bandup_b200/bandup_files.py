@@ -165,13 +165,20 @@ def _es(x: float) -> str:
 
 def write_band_struc(path, kpath: PcKptsPath, energy_grid: np.ndarray, dN: np.ndarray, e_fermi: float = 0.0,
                      sigma: Optional[np.ndarray] = None, spin_proj: Optional[np.ndarray] = None,
-                     header: str = "# File created by bandup-b200 (GPU unfolding path)") -> None:
+                     header: str = "# File created by bandup-b200 (GPU unfolding path)",
+                     saxis: Sequence[float] = (0.0, 0.0, 1.0),
+                     normal_to_proj_plane: Sequence[float] = (0.0, 0.0, 1.0)) -> None:
     """write_band_struc (io_routines_mod.f90:889-977).  dN: (n_pckpts_total, nener) in the order of
     kpath.all_kpts; sigma (n, nener, 3) and spin_proj (n, nener, 2) add the five spin columns."""
     grid = np.asarray(energy_grid, dtype=np.float64)
     with open(path, "w") as f:
         f.write(header.rstrip("\n") + "\n")
         if sigma is not None:
+            # the three comment lines of the reference's spinor output (:921-929)
+            f.write("# NB.: Unfolding of Pauli matrices eigenvs is a test feature.\n")
+            f.write("# The quantization axis assumed was saxis = [%s, %s, %s]\n" % tuple(_es(v) for v in saxis))
+            f.write('# The projection axis used for "#Spin _|_ k" is also _|_ to [%s, %s, %s].\n'
+                    % tuple(_es(v) for v in normal_to_proj_plane))
             f.write("#KptCoord #E-E_Fermi #delta_N   #sigma_x    #sigma_y    #sigma_z    #Spin _|_ k #Spin // k \n")
         else:
             f.write("#KptCoord #E-E_Fermi #delta_N \n")
@@ -353,7 +360,8 @@ def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_f
                 for ie in np.nonzero(np.any(sigma[i] != 0.0, axis=1))[0]:
                     spin_proj[i, ie] = calc_spin_projections(sigma[i, ie], all_k[i], normal_to_proj_plane,
                                                              origin_for_spin_proj)
-        write_band_struc(out_file, kpath, grid, got.dN, e_fermi, sigma=sigma, spin_proj=spin_proj)
+        write_band_struc(out_file, kpath, grid, got.dN, e_fermi, sigma=sigma, spin_proj=spin_proj,
+                         normal_to_proj_plane=normal_to_proj_plane)
     if want_rho:
         write_unf_dens_op(unf_dens_op_file, kpath, grid, got.dN, [rho_by_row[i] for i in range(n)], wc.nbands,
                           wc.B_matrix, b_pc, [got.sckpt_of_row[i] for i in range(n)], got.sckpts_cart,

@@ -684,7 +684,15 @@ int main(int argc, char** argv) {
     if (!f) die("ERROR: cannot write " + out_file);
     std::fprintf(f, "# File created by BandUP_gpu.x (bandup-b200, GPU unfolding path)\n");
     if (spinor)
+    {  // the three comment lines of the reference's spinor output (io_routines_mod.f90:921-929)
+      const double sax[3] = {0, 0, 1};  // the reference resets args%saxis to (0,0,1) whatever -saxis says (cla_wrappers_mod.f90:436)
+      std::fprintf(f, "# NB.: Unfolding of Pauli matrices eigenvs is a test feature.\n");
+      std::fprintf(f, "# The quantization axis assumed was saxis = [%s, %s, %s]\n", es10_3(sax[0]).c_str(),
+                   es10_3(sax[1]).c_str(), es10_3(sax[2]).c_str());
+      std::fprintf(f, "# The projection axis used for \"#Spin _|_ k\" is also _|_ to [%s, %s, %s].\n",
+                   es10_3(normal[0]).c_str(), es10_3(normal[1]).c_str(), es10_3(normal[2]).c_str());
       std::fprintf(f, "#KptCoord #E-E_Fermi #delta_N   #sigma_x    #sigma_y    #sigma_z    #Spin _|_ k #Spin // k \n");
+    }
     else
       std::fprintf(f, "#KptCoord #E-E_Fermi #delta_N \n");
     double coord_first = kp.zero, coord_k = kp.zero;
