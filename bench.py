@@ -4,7 +4,7 @@ SC-kpts/s end to end, and the CPU restatement of the reference timed beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
                     [--workload sige555|mos2_8x8_spinor|si333_vacancy|graphene4x4]
-                    [--kpts-per-step 4]
+                    [--kpts-per-step 0]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path (K1 coset
 classification -> K2 fused norm + masked |C|^2 reduction -> K3 finalisation + delta_N) over one batch
@@ -59,7 +59,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sige555", choices=sorted(WORKLOADS))
-    ap.add_argument("--kpts-per-step", type=int, default=4)
+    ap.add_argument("--kpts-per-step", type=int, default=0,
+                    help="SC k-points per GPU per step; 0: as many of the configuration's k-points as fit ~10 GB "
+                         "(C5: 4 of 200, C1: all 30)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 4)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -278,8 +280,10 @@ def run_b200(args, sc, rank, world, local_rank):
     if args.tuning:
         u.set_tuning(*[int(x) for x in args.tuning.split(",")])
     nener = len(grid)
-    kps = args.kpts_per_step
     nb, nsp = sc.n_bands, sc.n_spinor
+    kps = args.kpts_per_step
+    if kps <= 0:  # one batch = as much of the job as ~10 GB of HBM holds (small cells: the whole job)
+        kps = max(1, min(sc.n_sc_kpts, int(10e9 // (nb * sc.gvecs(0).shape[0] * nsp * 8))))
     rng = np.random.default_rng(SEED + rank)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
@@ -515,8 +519,9 @@ def run_b200(args, sc, rank, world, local_rank):
                        "n_fold": [it["nf"] for it in items], "nener": nener,
                        "launches": "per SC k-point" if args.per_kpt_launch else
                        "one launch of K1, K2, K3 per step (bandup_gpu_unfold_device_batch)",
-                       "l2": "inputs larger than L2 (each SC-kpt block >> 126 MB; batch cycles through "
-                             f"{step_bytes / 1e9:.1f} GB)",
+                       "l2": (f"inputs larger than L2: every step streams {step_bytes / 1e9:.2f} GB of coefficients "
+                              "(L2: 126 MB), read with evict_first" if step_bytes > 2 * 126e6 else
+                              f"WARNING: a step streams only {step_bytes / 1e6:.0f} MB (L2: 126 MB); raise --kpts-per-step"),
                        "parallelism": f"SC k-points sharded over {world} GPU(s), NCCL all_gather of delta_N rows"
                        if world > 1 else "1 GPU"},
             "sc_kpts_per_s": kpts_per_s, "gpu_launches": int(gpu_launches),
