@@ -45,10 +45,10 @@ METRIC = "coeff_GB_per_s"
 UNIT = "GB/s"
 
 WORKLOADS = {
-    "sige555": "C5: 1000-atom Si-Ge 5x5x5 supercell, 3000 bands, ~100k PWs, det M=500, 200 SC k-points",
-    "mos2_8x8_spinor": "C3: MoS2 8x8 monolayer, spinor, 1200 bands, ~80k PWs, det M=64",
-    "si333_vacancy": "C2: Si 3x3x3 vacancy supercell, 500 bands, ~20k PWs, det M=108, 100 SC k-points",
-    "graphene4x4": "C1: graphene 4x4, 64 bands, ~23k PWs, det M=16, 30 SC k-points",
+    "sige555": "C5: 1000-atom Si-Ge 5x5x5 supercell, 3000 bands, ~100k PWs, det M=500, 200 pc k-points (L-G-X) folding onto 138 SC k-points",
+    "mos2_8x8_spinor": "C3: MoS2 8x8 monolayer, spinor, 1200 bands, ~80k PWs, det M=64, 48 pc k-points (G-M-K-G) folding onto 28 SC k-points",
+    "si333_vacancy": "C2: Si 3x3x3 vacancy supercell, 500 bands, ~20k PWs, det M=108, 100 pc k-points (L-G-X) folding onto 99 SC k-points",
+    "graphene4x4": "C1: graphene 4x4, 64 bands, ~23k PWs, det M=16, 30 pc k-points (K-G-M-K) folding onto 23 SC k-points",
 }
 
 
