@@ -59,6 +59,9 @@ class PcKptsPath:
         return np.concatenate(self.directions, axis=0)
 
 
+MIN_DK = 2.0 * 1e-5     # min_dk (constants_and_types_mod.f90:65)
+
+
 def read_pckpts(path, b_matrix_pc: np.ndarray) -> PcKptsPath:
     """read_pckpts_selected_by_user + kpts_line for every direction
     (define_pckpts_to_be_checked, band_unfolding_routines_mod.f90:486-547)."""
@@ -68,8 +71,14 @@ def read_pckpts(path, b_matrix_pc: np.ndarray) -> PcKptsPath:
     n_line, mode_line, coord_line = lines[1].strip(), lines[2].strip(), lines[3].strip()
     try:
         counts = [int(x) for x in n_line.split()]
+        if not counts:
+            raise ValueError
     except ValueError:
-        raise ValueError("automatic scan for pc-kpts (non-numeric second line) is not supported here")
+        # no number on the second line: the reference scans the directions automatically in steps of
+        # min_dk = 2 * default_tol_for_vec_equality = 2e-5 A^-1 (io_routines_mod.f90:1131-1170,
+        # constants_and_types_mod.f90:65); with stop_if_GUR_fails = .TRUE. it then stops unless every
+        # scanned point folds -- here that is the fold map's FOLDING_VECTOR error
+        counts = None
     toks = mode_line.split()
     zero = 0.0
     if len(toks) > 1:
@@ -104,15 +113,16 @@ def read_pckpts(path, b_matrix_pc: np.ndarray) -> PcKptsPath:
             block.append(np.array([float(x) for x in ln.split()[:3]]))
     if not pairs:
         raise ValueError("no pc-kpt direction found")
-    if len(counts) < len(pairs):
+    if counts is not None and len(counts) < len(pairs):
         counts = [counts[0]] * len(pairs)
     b = np.asarray(b_matrix_pc, dtype=np.float64)
     dirs = []
-    for (ks, ke), nk in zip(pairs, counts):
+    for idir, (ks, ke) in enumerate(pairs):
         if cartesian:
             ks_c, ke_c = TWOPI * ks / a0, TWOPI * ke / a0
         else:
             ks_c, ke_c = ks @ b, ke @ b
+        nk = counts[idir] if counts is not None else int(np.ceil(1.0 + np.linalg.norm(ke_c - ks_c) / MIN_DK))
         if np.linalg.norm(ks_c - ke_c) < np.finfo(float).eps:
             nk = 1
         dirs.append(kpts_line(ks_c, ke_c, nk))

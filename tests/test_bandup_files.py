@@ -94,3 +94,44 @@ def test_band_struc_format(tmp_path):
     sig = np.ones((n, 3, 3)) * 0.25
     BF.write_band_struc(tmp_path / "spin.dat", kp, grid, dN, sigma=sig, spin_proj=np.zeros((n, 3, 2)))
     assert BF.read_band_struc(tmp_path / "spin.dat").shape == (n * 3, 8)
+
+
+def test_readers_against_the_reference_sample_plot_files(tmp_path):
+    """The reference ships one set of real inputs with an output it produced
+    (utils/sample_input_files_task_plot/; committed verbatim in tests/golden/sample_plot_golden.json
+    by make_sample_plot_golden.py).  Its K-G-M-K path on that lattice, sampled 25/25/13 times, must
+    land on the 61 distinct KptCoord values of the reference-made file to its 4 decimals, and the
+    energy column is real_seq(-22, 7, 0.05): 581 values."""
+    import json
+    from pathlib import Path
+    g = json.loads((Path(__file__).parent / "golden" / "sample_plot_golden.json").read_text())
+    for name in ("prim_cell_lattice.in", "energy_info.in"):
+        (tmp_path / name).write_text(g[name])
+    kp_lines = g["KPOINTS_prim_cell.in"].splitlines()
+    assert kp_lines[1].strip() == "Auto"
+    A = BF.read_lattice(tmp_path / "prim_cell_lattice.in")
+    assert np.allclose(A[0], [2.467 * 0.866025403, -2.467 * 0.5, 0.0])
+    b = BF.rec_latt(A) if hasattr(BF, "rec_latt") else 2 * np.pi * np.linalg.inv(A).T
+    kp_lines[1] = "25 25 13"
+    (tmp_path / "KPOINTS_prim_cell.in").write_text("\n".join(kp_lines) + "\n")
+    kpath = BF.read_pckpts(tmp_path / "KPOINTS_prim_cell.in", b)
+    assert [len(d) for d in kpath.directions] == [25, 25, 13]
+    coords, first = [], kpath.zero_of_kpts_scale
+    for d in kpath.directions:                                   # write_band_struc's accumulation
+        c = [first + float(np.linalg.norm(k - d[0])) for k in d]
+        coords += c
+        first = c[-1]
+    got = sorted(set(np.round(coords, 4).tolist()))
+    assert len(got) == len(g["kpt_coords"]) == 61
+    assert np.allclose(got, g["kpt_coords"], atol=1.01e-4)
+    e_fermi, e_start, e_end, de = BF.read_energy_info(tmp_path / "energy_info.in")
+    assert (e_fermi, de) == (-2.4543, 0.05) and abs(e_end - (7.0 + e_fermi)) < 1e-12
+    from oracle import oracle as O
+    lo, hi, n = g["energies_min_max_n"]
+    grid = O.real_seq(lo, hi, de)
+    assert len(grid) == n == 581 and abs(grid[-1] - hi) < 1e-9
+    # the file as shipped asks for the automatic scan: min_dk = 2e-5 A^-1 steps (io_routines_mod.f90:1163-1169)
+    (tmp_path / "auto.in").write_text(g["KPOINTS_prim_cell.in"])
+    auto = BF.read_pckpts(tmp_path / "auto.in", b)
+    lens = [np.linalg.norm(d[-1] - d[0]) for d in auto.directions]
+    assert [len(d) for d in auto.directions] == [int(np.ceil(1.0 + L / 2e-5)) for L in lens]
