@@ -211,8 +211,12 @@ __device__ __forceinline__ void consume_stage(const float4* __restrict__ sv, uin
     for (int u = 0; u < kVecPerThread; ++u) {
       if (sl[u] != 0xFFFFu) {  // a real branch per vector: with det(M) in the hundreds most warps skip it
         const unsigned sa = sl[u] & 0xFFu, sb = sl[u] >> 8;
-        if (sa < nf) bins[sa * kConsumers + tid] += (double)p[2 * u];
-        if (sb < nf) bins[sb * kConsumers + tid] += (double)p[2 * u + 1];
+        if (MODE == 1 && sa == sb) {  // the two spinor components of ONE plane wave: one update
+          bins[sa * kConsumers + tid] += (double)p[2 * u] + (double)p[2 * u + 1];
+        } else {
+          if (sa < nf) bins[sa * kConsumers + tid] += (double)p[2 * u];
+          if (sb < nf) bins[sb * kConsumers + tid] += (double)p[2 * u + 1];
+        }
       }
     }
   }
