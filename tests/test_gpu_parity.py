@@ -941,3 +941,28 @@ def test_host_register_caller_owned_buffer(unfolder):
     assert t_locked < t_pageable * 1.05
     after = unfolder.perform_unfolding(wf, g0=g0, want_selected=False)        # pageable again: still fine
     assert np.array_equal(after.dN, ref.dN)
+
+
+def test_maximum_pckpts_per_submit(unfolder):
+    """BANDUP_GPU_MAX_PCKPTS pc-kpts in one submit (every coset of det M = 108 many times over):
+    rows of pc-kpts sharing a coset are identical and match the oracle; one more is refused."""
+    from bandup_b200._capi import CONST
+    from bandup_b200.unfold import BandupGpuError, PwWavefunction
+    n_max = CONST["BANDUP_GPU_MAX_PCKPTS"]
+    sc = synth.make_scenario("si333_vacancy", scale=0.15)
+    grid = setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 0)
+    wf = PwWavefunction(coeffs, gf, ener)
+    cube = np.array([[i, j, k] for i in range(6) for j in range(6) for k in range(6)], dtype=np.int32)
+    g0 = cube[np.arange(n_max) % len(cube)]
+    res = unfolder.perform_unfolding(wf, g0=g0, want_selected=False)
+    assert res.spectral_weight.shape == (n_max, coeffs.shape[0]) and res.dN.shape == (n_max, len(grid))
+    assert np.array_equal(res.spectral_weight[:len(cube)], res.spectral_weight[len(cube):2 * len(cube)])
+    assert np.array_equal(res.dN[n_max - 1], res.dN[(n_max - 1) % len(cube)])
+    pick = [0, 77, 215]
+    w, dN, ns, _ = oracle_kpt(sc, coeffs, gf, ener, cube[pick].astype(np.float64) @ sc.B_sc, grid)
+    assert np.array_equal(res.n_selected[pick], ns)
+    assert rel_err(res.spectral_weight[pick], w) <= REL_TOL and rel_err(res.dN[pick], dN) <= REL_TOL
+    with pytest.raises(BandupGpuError) as ei:
+        unfolder.submit(7, wf, g0=np.concatenate([g0, g0[:1]]))
+    assert ei.value.code == 5
