@@ -63,9 +63,11 @@ class KptHeader:
 def write_wavecar(path, A: np.ndarray, ecut: float, kpts_frac: Sequence[np.ndarray],
                   coeffs: Sequence[np.ndarray], energies: Sequence[np.ndarray],
                   occupations: Optional[Sequence[np.ndarray]] = None, nspin: int = 1,
-                  extra_pad: int = 0) -> int:
+                  extra_pad: int = 0, coeffs_spin2: Optional[Sequence[np.ndarray]] = None,
+                  energies_spin2: Optional[Sequence[np.ndarray]] = None) -> int:
     """Writes a single-precision WAVECAR.  coeffs[ik] is (n_bands, n_pw, n_spinor) complex64 in the
-    plane-wave order of synth.gen_gvecs (== the reader's enumeration).  Returns nrecl."""
+    plane-wave order of synth.gen_gvecs (== the reader's enumeration).  With nspin = 2 the second
+    spin channel repeats the first unless coeffs_spin2 / energies_spin2 are given.  Returns nrecl."""
     A = np.asarray(A, dtype=np.float64)
     nk = len(kpts_frac)
     nb = coeffs[0].shape[0]
@@ -79,13 +81,15 @@ def write_wavecar(path, A: np.ndarray, ecut: float, kpts_frac: Sequence[np.ndarr
         put(np.array([nrecl, nspin, NPREC_COMPLEX64], dtype="<f8").tobytes())
         put(np.concatenate([[nk, nb, ecut], A.reshape(9)]).astype("<f8").tobytes())
         for _spin in range(nspin):
+            c_src = coeffs_spin2 if (_spin == 1 and coeffs_spin2 is not None) else coeffs
+            e_src = energies_spin2 if (_spin == 1 and energies_spin2 is not None) else energies
             for ik in range(nk):
-                c = np.ascontiguousarray(coeffs[ik], dtype=np.complex64)
+                c = np.ascontiguousarray(c_src[ik], dtype=np.complex64)
                 if c.shape[0] != nb:
                     raise ValueError("every k-point must have the same number of bands")
                 n_pw, nsp = c.shape[1], c.shape[2]
                 occ = np.ones(nb) if occupations is None else np.asarray(occupations[ik], dtype=np.float64)
-                ener = np.asarray(energies[ik], dtype=np.float64)
+                ener = np.asarray(e_src[ik], dtype=np.float64)
                 hdr = np.empty(4 + 3 * nb, dtype="<f8")
                 hdr[0] = n_pw * nsp
                 hdr[1:4] = np.asarray(kpts_frac[ik], dtype=np.float64)

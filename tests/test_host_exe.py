@@ -86,3 +86,39 @@ def test_host_exe_reproduces_the_python_path_and_the_oracle(gpu_lib, unfolder, t
         for f, row in enumerate(sc.folds[iK]):
             got = exe_tab[row * len(grid):(row + 1) * len(grid), 2]
             assert np.allclose(got, d[f], rtol=6e-4, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_second_spin_channel_of_a_spin_polarised_wavecar(gpu_lib, unfolder, tmp_path):
+    """nspin = 2 with different coefficients and energies per channel: -spin_channel 2 (host exe)
+    and spin_channel=2 (Python mirror) unfold the second channel -- equal to the oracle on that
+    channel's data and different from channel 1."""
+    from oracle import oracle as O
+    from bandup_b200.wavecar import write_wavecar
+    sc, data, counts = _job(tmp_path, False)
+    rng = np.random.default_rng(5)
+    data2 = []
+    for c, gf, e in data:
+        c2 = (c * (1.0 + 0.5 * rng.standard_normal(c.shape))).astype(np.complex64)
+        data2.append((c2, gf, np.sort(e + rng.uniform(-0.4, 0.4, e.shape))))
+    write_wavecar(tmp_path / "WAVECAR", sc.A_sc, sc.ecut, list(sc.sc_kpts_frac), [d[0] for d in data],
+                  [d[2] for d in data], nspin=2, coeffs_spin2=[d[0] for d in data2],
+                  energies_spin2=[d[2] for d in data2])
+    tabs = {}
+    for ch in (1, 2):
+        r = subprocess.run([str(EXE), "-no_symm_sckpts", "-no_symm_avg", "-spin_channel", str(ch), "-out_file_nosymm",
+                            f"exe{ch}.dat"], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr + r.stdout
+        tabs[ch] = BF.read_band_struc(tmp_path / f"exe{ch}.dat")
+    assert not np.array_equal(tabs[1][:, 2], tabs[2][:, 2])
+    kpath, grid, dN = BF.unfold_task(unfolder, tmp_path / "WAVECAR", tmp_path / "prim_cell_lattice.in",
+                                     tmp_path / "supercell_lattice.in", tmp_path / "KPOINTS_prim_cell.in",
+                                     tmp_path / "energy_info.in", out_file=str(tmp_path / "py2.dat"), spin_channel=2)
+    assert np.array_equal(BF.read_band_struc(tmp_path / "py2.dat"), tabs[2])
+    for ch, src in ((1, data), (2, data2)):
+        for iK in range(sc.n_sc_kpts):
+            coeffs, gf, ener = src[iK]
+            _, d, _, _ = O.unfold_kpt(coeffs, gf @ sc.B_sc, ener, sc.b_pc, sc.folding_G(iK), grid, norm_mode=1)
+            for f, row in enumerate(sc.folds[iK]):
+                got = tabs[ch][row * len(grid):(row + 1) * len(grid), 2]
+                assert np.allclose(got, d[f], rtol=6e-4, atol=1e-12)
