@@ -122,3 +122,44 @@ def test_second_spin_channel_of_a_spin_polarised_wavecar(gpu_lib, unfolder, tmp_
             for f, row in enumerate(sc.folds[iK]):
                 got = tabs[ch][row * len(grid):(row + 1) * len(grid), 2]
                 assert np.allclose(got, d[f], rtol=6e-4, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_exe_flags_skip_sckpts_and_dont_unfold(gpu_lib, unfolder, tmp_path):
+    """-n_sckpts_to_skip: a hybrid-functional style WAVECAR whose first k-point repeats a later one
+    with meaningless coefficients is unfolded from the later copy (cla_wrappers_mod.f90:258-268,
+    band_unfolding_routines_mod.f90:311-315).  -dont_unfold: P = 1, so delta_N counts the SC bands
+    of every bin (:1346-1351)."""
+    from bandup_b200.wavecar import write_wavecar
+    sc, data, counts = _job(tmp_path, False)
+    base = [str(EXE), "-no_symm_sckpts", "-no_symm_avg"]
+    r = subprocess.run(base + ["-out_file_nosymm", "ref.dat"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = BF.read_band_struc(tmp_path / "ref.dat")
+    rng = np.random.default_rng(9)
+    junk = (rng.standard_normal(data[0][0].shape) + 1j * rng.standard_normal(data[0][0].shape)).astype(np.complex64)
+    write_wavecar(tmp_path / "WAVECAR_hyb", sc.A_sc, sc.ecut, [sc.sc_kpts_frac[0]] + list(sc.sc_kpts_frac),
+                  [junk] + [d[0] for d in data], [data[0][2]] + [d[2] for d in data], extra_pad=1)
+    r = subprocess.run(base + ["-wf_file", "WAVECAR_hyb", "-n_sckpts_to_skip", "1", "-out_file_nosymm", "skip.dat"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(BF.read_band_struc(tmp_path / "skip.dat"), ref)
+    r = subprocess.run(base + ["-wf_file", "WAVECAR_hyb", "-out_file_nosymm", "noskip.dat"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and not np.array_equal(BF.read_band_struc(tmp_path / "noskip.dat"), ref)
+    _, grid, dN = BF.unfold_task(unfolder, tmp_path / "WAVECAR_hyb", tmp_path / "prim_cell_lattice.in",
+                                 tmp_path / "supercell_lattice.in", tmp_path / "KPOINTS_prim_cell.in",
+                                 tmp_path / "energy_info.in", out_file=str(tmp_path / "py_skip.dat"), n_sckpts_to_skip=1)
+    assert np.array_equal(BF.read_band_struc(tmp_path / "py_skip.dat"), ref)
+    # -dont_unfold
+    r = subprocess.run(base + ["-dont_unfold", "-out_file_nosymm", "nounf.dat"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    tab = BF.read_band_struc(tmp_path / "nounf.dat")
+    de = grid[1] - grid[0]
+    for iK in range(sc.n_sc_kpts):
+        ener = data[iK][2]
+        want = np.array([np.sum(np.abs(ener - E) < 0.5 * de - 1e-9) for E in grid], dtype=float)
+        edge = np.array([np.any(np.abs(np.abs(ener - E) - 0.5 * de) <= 1e-9) for E in grid])
+        for row in sc.folds[iK]:
+            got = tab[row * len(grid):(row + 1) * len(grid), 2]
+            assert np.allclose(got[~edge], want[~edge], atol=1e-9)
