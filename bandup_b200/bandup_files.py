@@ -282,7 +282,8 @@ def write_orb_dependent_ebs(path, kpath: PcKptsPath, energy_grid: np.ndarray, va
 def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_file, energy_file,
                 out_file: Optional[str] = None, spin_channel: int = 1, unf_dens_op_file: Optional[str] = None,
                 normal_to_proj_plane: Sequence[float] = (0.0, 0.0, 1.0), origin_for_spin_proj=None,
-                projections=None, orb_out_file: Optional[str] = None, n_sckpts_to_skip: int = 0):
+                projections=None, orb_out_file: Optional[str] = None, n_sckpts_to_skip: int = 0,
+                origin_for_spin_proj_rec=None):
     """`bandup unfold` at file level for -no_symm_sckpts -no_symm_avg: parse the reference's input
     files, run every SC-kpt of the WAVECAR through the GPU (wavecar.unfold_wavecar) and write
     unfolded_EBS_not-symmetry_averaged.dat -- for a spinor WAVECAR with the reference's five spin
@@ -358,6 +359,10 @@ def unfold_task(unfolder, wavecar_path, prim_cell_file, supercell_file, pckpts_f
     if got.row_ids.tolist() != list(range(n)):
         # main_BandUP.f90:114: every requested pc-kpt must have been unfolded exactly once
         raise RuntimeError("not every pc-kpt was unfolded")
+    if origin_for_spin_proj_rec is not None:
+        # -origin_for_spin_proj_rec: fractional w.r.t. the SC reciprocal lattice, wins over the
+        # Cartesian one (cla_wrappers_mod.f90:452-467, band_unfolding_routines_mod.f90:183-189)
+        origin_for_spin_proj = np.asarray(origin_for_spin_proj_rec, dtype=np.float64) @ wc.B_matrix
     if out_file:
         sigma = spin_proj = None
         if spinor_kpts:

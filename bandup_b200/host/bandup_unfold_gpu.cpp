@@ -312,6 +312,7 @@ struct Args {
     return it == kv.end() ? def : it->second;
   }
   bool has(const std::string& k) const { return flag.count(k) != 0; }
+  bool has_value(const std::string& k) const { return kv.count(k) != 0; }
 };
 
 Args parse_args(int argc, char** argv) {
@@ -319,7 +320,7 @@ Args parse_args(int argc, char** argv) {
   const std::vector<std::string> with_value = {"-wf_file", "-pc_file", "-sc_file", "-pckpts_file", "-energy_file",
       "-out_file_nosymm", "-out_file_symm", "-output_file_only_user_selec_direcs_unf_dens_op",
       "-output_file_symm_averaged_unf_dens_op", "-spin_channel", "-n_sckpts_to_skip", "-normal_to_proj_plane",
-      "-origin_for_spin_proj_cart", "-device", "-read_threads", "-outdir", "-saxis", "-n_ranks", "-rank",
+      "-origin_for_spin_proj_cart", "-origin_for_spin_proj_rec", "-device", "-read_threads", "-outdir", "-saxis", "-n_ranks", "-rank",
       "-nccl_id_file", "-ticket_file"};
   const std::vector<std::string> switches = {"-write_unf_dens_op", "-no_symm_sckpts", "-no_symm_avg", "-dont_unfold",
       "-continue_if_not_commensurate", "--continue_if_npw_smaller_than_expected", "-skip_propose_pc_for_given_pc",
@@ -679,6 +680,13 @@ int main(int argc, char** argv) {
   double normal[3] = {0, 0, 1}, origin[3] = {0, 0, 0};
   parse_vec3(args.get("-normal_to_proj_plane", "0, 0, 1"), normal);
   parse_vec3(args.get("-origin_for_spin_proj_cart", "0, 0, 0"), origin);
+  if (args.has_value("-origin_for_spin_proj_rec")) {
+    // fractional w.r.t. the SC reciprocal lattice; it wins over the Cartesian one as in the
+    // reference (cla_wrappers_mod.f90:452-467, band_unfolding_routines_mod.f90:183-189)
+    double rec[3];
+    parse_vec3(args.get("-origin_for_spin_proj_rec", "0, 0, 0"), rec);
+    vec_mat(rec, B_sc, origin);
+  }
   {
     std::FILE* f = std::fopen(out_file.c_str(), "w");
     if (!f) die("ERROR: cannot write " + out_file);

@@ -163,3 +163,36 @@ def test_exe_flags_skip_sckpts_and_dont_unfold(gpu_lib, unfolder, tmp_path):
         for row in sc.folds[iK]:
             got = tab[row * len(grid):(row + 1) * len(grid), 2]
             assert np.allclose(got[~edge], want[~edge], atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_exe_spin_projection_flags(gpu_lib, unfolder, tmp_path):
+    """-normal_to_proj_plane / -origin_for_spin_proj_cart / -origin_for_spin_proj_rec change the two
+    in-plane spin projection columns (calc_spin_projections, band_unfolding_routines_mod.f90:1266-1286)
+    and nothing else; host exe and Python mirror agree, and the fractional origin wins."""
+    sc, data, counts = _job(tmp_path, True)
+    base = [str(EXE), "-no_symm_sckpts", "-no_symm_avg"]
+    files = [tmp_path / n for n in ("WAVECAR", "prim_cell_lattice.in", "supercell_lattice.in", "KPOINTS_prim_cell.in",
+                                    "energy_info.in")]
+    r = subprocess.run(base + ["-out_file_nosymm", "def.dat"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    default = BF.read_band_struc(tmp_path / "def.dat")
+    rec = np.array([0.25, -0.5, 0.0])
+    cart = rec @ sc.B_sc
+    r = subprocess.run(base + ["-out_file_nosymm", "a.dat", "-normal_to_proj_plane", "1, 0, 1", "-origin_for_spin_proj_cart",
+                               "%.12f, %.12f, %.12f" % tuple(cart)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a = BF.read_band_struc(tmp_path / "a.dat")
+    assert np.array_equal(a[:, :6], default[:, :6]) and not np.array_equal(a[:, 6:], default[:, 6:])
+    BF.unfold_task(unfolder, *files, out_file=str(tmp_path / "py_a.dat"), normal_to_proj_plane=(1.0, 0.0, 1.0),
+                   origin_for_spin_proj=cart)
+    assert np.array_equal(BF.read_band_struc(tmp_path / "py_a.dat"), a)
+    assert '_|_ to [ 1.000E+00,  0.000E+00,  1.000E+00].' in (tmp_path / "a.dat").read_text()
+    r = subprocess.run(base + ["-out_file_nosymm", "b.dat", "-normal_to_proj_plane", "1, 0, 1", "-origin_for_spin_proj_rec",
+                               "0.25, -0.5, 0", "-origin_for_spin_proj_cart", "9, 9, 9"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(BF.read_band_struc(tmp_path / "b.dat"), a)
+    BF.unfold_task(unfolder, *files, out_file=str(tmp_path / "py_b.dat"), normal_to_proj_plane=(1.0, 0.0, 1.0),
+                   origin_for_spin_proj=(9.0, 9.0, 9.0), origin_for_spin_proj_rec=rec)
+    assert np.array_equal(BF.read_band_struc(tmp_path / "py_b.dat"), a)
