@@ -669,6 +669,10 @@ int main(int argc, char** argv) {
         std::memcpy(&sigma_all[(size_t)all_ids[r] * rl], &sall[r * rl], sizeof(double) * rl);
     }
     gpu_check(h, bandup_gpu_comm_finalize(h), "comm_finalize");
+    if (rank == 0) {  // every rank is past its last ticket and the collectives: the rendezvous files can go
+      std::remove(args.get("-nccl_id_file", "bandup_gpu_nccl_id").c_str());
+      if (!ticket_file.empty()) std::remove(ticket_file.c_str());
+    }
     if (rank != 0) {  // rank 0 writes the files
       for (auto b : bufs) bandup_gpu_pinned_free(b);
       bandup_gpu_finalize(h);

@@ -141,3 +141,31 @@ def test_bench_two_ranks_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["value"] > 0 and d["e2e"]["value"] > 0
     assert d["cpu_baseline"] is None                     # rank 0 at N = 1 only
+
+
+def test_host_exe_rank_without_kpoints(tmp_path, gpu_lib):
+    """Two ranks, a job with a single SC k-point: one rank has nothing to unfold and still takes part
+    in the collectives; the output equals the one-rank output (static blocks and shared counter)."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from bandup_b200 import bandup_files as BF
+    from tests.test_host_exe import EXE, _job
+    _job(tmp_path, True)
+    BF.write_pckpts(tmp_path / "KPOINTS_prim_cell.in", [([0.0, 0.0, 0.0], [0.0, 0.0, 0.0])], [1])   # Gamma only
+    common = [str(EXE), "-no_symm_sckpts", "-no_symm_avg", "-write_unf_dens_op"]
+    r = subprocess.run(common + ["-out_file_nosymm", "one.dat", "-output_file_only_user_selec_direcs_unf_dens_op", "one_udo.dat"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("SC-kpt #") == 1
+    for tag, extra in (("st", []), ("dy", ["-ticket_file", "tk"])):
+        procs = [subprocess.Popen(common + ["-out_file_nosymm", f"{tag}.dat", "-output_file_only_user_selec_direcs_unf_dens_op",
+                                            f"{tag}_udo.dat", "-n_ranks", "2", "-rank", str(k), "-nccl_id_file", f"id_{tag}"] + extra,
+                                  cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for k in (0, 1)]
+        outs = [p.communicate(timeout=300) for p in procs]
+        assert all(p.returncode == 0 for p in procs), outs
+        assert sorted(o[0].count("SC-kpt #") for o in outs) == [0, 1]
+        assert np.array_equal(BF.read_band_struc(tmp_path / "one.dat"), BF.read_band_struc(tmp_path / f"{tag}.dat"))
+        assert (tmp_path / "one_udo.dat").read_text() == (tmp_path / f"{tag}_udo.dat").read_text()
+        assert not (tmp_path / f"id_{tag}").exists() and not (tmp_path / "tk").exists()     # rank 0 cleaned up
