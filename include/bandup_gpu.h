@@ -71,16 +71,18 @@ extern "C" {
 
 /* ---- lifetime --------------------------------------------------------- */
 
-/* Creates a context on CUDA device `device`.  Fails with ERR_NO_DEVICE when
- * the device is absent or is not compute capability 10.x. */
+/* Creates a context on CUDA device `device` (no counterpart in the reference: called once where
+ * program BandUP_main starts, main_BandUP.f90:52, and released before its end, :199).  Fails with
+ * ERR_NO_DEVICE when the device is absent or is not compute capability 10.x. */
 int bandup_gpu_init(int device, int *handle);
 int bandup_gpu_finalize(int handle);
 /* Human-readable text of the last error on this handle (never NULL). */
 const char *bandup_gpu_last_error(int handle);
 int bandup_gpu_abi_version(void);
 
-/* Pinned host memory for the wavefunction reader to read into, so that
- * submit_kpt's upload is a true asynchronous DMA (optional). */
+/* Pinned host memory for the wavefunction reader to read into (where read_wavecar fills
+ * wf%pw_coeffs, read_wavecar_mod.f90:537-583), so that submit_kpt's upload is a true asynchronous
+ * DMA (optional). */
 int bandup_gpu_pinned_alloc(size_t bytes, void **ptr);
 int bandup_gpu_pinned_free(void *ptr);
 /* The same for memory the caller already owns -- a Fortran ALLOCATEd wf%pw_coeffs, the buffer a
@@ -107,7 +109,8 @@ int bandup_gpu_set_cells(int handle, const double *B_sc, const double *b_pc,
  * nener_out (nullable) receives the number of grid points. */
 int bandup_gpu_set_grid(int handle, double E_start, double E_end, double delta_e,
                         double smearing, int32_t *nener_out);
-/* Copies the energy grid (nener doubles) the kernels use. */
+/* Copies the energy grid (nener doubles) the kernels use: real_seq(E_start, E_end, delta_e)
+ * (lists_and_seqs_mod.f90:188-200 as called at main_BandUP.f90:119-122). */
 int bandup_gpu_get_grid(int handle, double *energies);
 
 /* Replaces the float part of select_coeffs_to_calc_spectral_weights
@@ -175,7 +178,8 @@ int bandup_gpu_submit_kpt_vasp(int handle, int ikpt, int nplane, int n_bands, in
                                double ecut, double two_m_over_hbar_sqrd,
                                const double *band_energies, int n_fold, const int32_t *g0,
                                int *n_spinor_out, int *n_pw_out);
-/* The plane-wave list (int32 [n_pw][3]) of a submitted or still resident k-point. */
+/* The plane-wave list (int32 [n_pw][3]) of a submitted or still resident k-point: wf%G_frac as
+ * read_wavecar leaves it (read_wavecar_mod.f90:275-302). */
 int bandup_gpu_fetch_gvecs(int handle, int ikpt, int32_t *g_frac, int64_t capacity);
 
 /* Blocks until k-point `ikpt` is done and copies out:
@@ -192,6 +196,8 @@ int bandup_gpu_fetch_kpt(int handle, int ikpt, double *weights, double *dN,
                          int32_t *n_selected, double *norms, int32_t *selected,
                          int64_t selected_capacity);
 
+/* SC k-points that may be in flight at once (submitted, not fetched): 2, so that the reader can
+ * fill k-point j+1 (read_wavefunction, main_BandUP.f90:150-153) while j uploads and computes. */
 int bandup_gpu_pipeline_depth(int handle);
 
 /* args%perform_unfold (cla_wrappers_mod.f90, flag -dont_unfold): with 0 every spectral weight
@@ -255,7 +261,8 @@ int bandup_gpu_orb_contrib_matrix(int handle, int n_bands, int n_ao, const doubl
                                   const double *proj, const uint8_t *ao_mask,
                                   const double *band_energies, double max_band_dE,
                                   double min_abs, double *O_out);
-/* Uploads a general operator O [n_bands][n_bands] complex128 (HOST) as the current one. */
+/* Uploads a general operator O [n_bands][n_bands] complex128 (HOST) as the current one: the
+ * `general_operator` argument of UnfDensOp.unfold (unfolding_density_op.py:121-126). */
 int bandup_gpu_set_operator(int handle, int n_bands, const double *O);
 /* Replaces UnfDensOp.unfold(O, multiply_by_N=True, discard_imag=True, clip_interval=(0,N))
  * (unfolding_density_op.py:121-141 as called from orbital_contributions.py:444-458) for every
@@ -307,7 +314,8 @@ int bandup_gpu_symm_average_rho(int handle, int n_dirs, int n_pckpts, int nener,
 size_t bandup_gpu_workspace_bytes(int handle, int n_spinor, int n_pw, int n_bands,
                                   int n_fold);
 
-/* Same computation as submit+fetch but on buffers already in HBM; everything
+/* Same computation as submit+fetch -- the body of the loop over the pc-kpts folding onto one
+ * SC-kpt, main_BandUP.f90:145-172 -- but on buffers already in HBM; everything
  * is enqueued on `stream` (a cudaStream_t; NULL = default stream), nothing is
  * synchronised.  All d_* pointers are device pointers; g0 is a HOST pointer.
  * d_norms, d_slot_out (uint8 [n_pw]: fold id or 255) may be NULL; d_slot_out needs
@@ -382,7 +390,9 @@ int bandup_gpu_gather_rows(int handle, int row_len, const double *rows_local,
 #define BANDUP_GPU_K_SYMM_AVG 5
 #define BANDUP_GPU_K_COUNT 6
 
-/* When enabled, every launch is bracketed by CUDA events on its own stream. */
+/* When enabled, every launch is bracketed by CUDA events on its own stream (the device-side
+ * counterpart of the reference's `times` bookkeeping, print_final_times,
+ * io_routines_mod.f90:1923-1962). */
 int bandup_gpu_set_profiling(int handle, int enabled);
 /* Same, for the kernels whose id bit is set only (bit k = kernel id k): an event pair between two
  * back-to-back launches costs a few microseconds of device time, so a timed region that wants one
