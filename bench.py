@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--kpts-per-step", type=int, default=0,
                     help="SC k-points per GPU per step; 0: as many of the configuration's k-points as fit ~10 GB "
                          "(C5: 4 of 200, C1: all 30)")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 4)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 8)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -414,7 +414,7 @@ def run_b200(args, sc, rank, world, local_rank):
     e2e = None
     t_e2e = (0.0, 0.0)
     if not args.no_e2e:
-        n_e2e = args.e2e_steps or min(args.steps, 4)
+        n_e2e = args.e2e_steps or min(args.steps, 8)
         host = []
         for it in items[:2]:     # two distinct pinned blocks, cycled (2 x 2.4 GB per rank)
             nbytes = nb * it["n_pw"] * nsp * 8
