@@ -77,3 +77,23 @@ def test_rho_text_file_is_what_the_reference_reader_parses(tmp_path):
         want = np.zeros((12, 12), dtype=complex)
         want[g["hermitian_rows"], g["hermitian_cols"]] = np.array(g["hermitian_re"]) + 1j * np.array(g["hermitian_im"])
         assert np.array_equal(dense, want)
+
+
+def test_orbital_choice_matches_the_reference_function():
+    """formatted_orb_choice against what the reference's own function returned for the same 44 inputs
+    (tests/golden/orb_choice_golden.json, made by importing bandupy.orbital_contributions), and
+    ao_mask's combined atom/orbital index (KptInfo.combined_atom_orb_index: iat*n_orbs + iorb)."""
+    import json
+    from pathlib import Path
+    from bandup_b200 import bandup_files as BF
+    cases = json.loads((Path(__file__).parent / "golden" / "orb_choice_golden.json").read_text())
+    assert len(cases) == 44
+    for c in cases:
+        assert BF.formatted_orb_choice(c["choice"], c["supported"]) == c["picked"], c["choice"]
+    with pytest.raises(ValueError):
+        BF.formatted_orb_choice("sp5", cases[0]["supported"])
+    orbitals = cases[0]["supported"]
+    mask = BF.ao_mask(4, orbitals, "p", [1, 3])
+    want = np.zeros((4, len(orbitals)), dtype=np.uint8)
+    want[[1, 3], 1:4] = 1
+    assert np.array_equal(mask.reshape(4, len(orbitals)), want)
