@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <memory>
 #include <thread>
 
 #include "ctx.cuh"
@@ -145,29 +147,53 @@ int upload_block(Ctx* c, void* dst, const void* src, size_t bytes) {
   if (const char* e = std::getenv("BANDUP_GPU_STAGE_THREADS")) n_thr = std::max(1, std::atoi(e));
   // small blocks: smaller chunks, so that the wire starts early and the ring still overlaps
   const size_t chunk = std::min(kStageChunk, std::max(size_t(1) << 20, (bytes / 8 + 4095) & ~size_t(4095)));
-  for (size_t off = 0; off < bytes; off += chunk) {
-    const size_t n = std::min(chunk, bytes - off);
-    const int k = c->stage_next;
-    c->stage_next = (k + 1) % Ctx::kStageBufs;
+  const long n_chunks = (long)((bytes + chunk - 1) / chunk);
+  const size_t part = ((chunk + (size_t)n_thr - 1) / (size_t)n_thr + 4095) & ~size_t(4095);
+  for (int k = 0; k < Ctx::kStageBufs; ++k) {
     CU(c->stage[k].reserve(kStageChunk));
-    if (!c->stage_free[k])
-      CU(cudaEventCreateWithFlags(&c->stage_free[k], cudaEventDisableTiming));
-    else
-      CU(cudaEventSynchronize(c->stage_free[k]));  // its previous chunk has left the buffer
-    char* s = static_cast<char*>(c->stage[k].p);
-    const char* u = static_cast<const char*>(src) + off;
-    const size_t part = ((n + (size_t)n_thr - 1) / (size_t)n_thr + 4095) & ~size_t(4095);
-    std::vector<std::thread> pool;
-    for (int t = 1; t < n_thr; ++t) {
-      const size_t a = part * (size_t)t;
-      if (a >= n) break;
-      pool.emplace_back([=] { std::memcpy(s + a, u + a, std::min(part, n - a)); });
-    }
-    std::memcpy(s, u, std::min(part, n));
-    for (auto& th : pool) th.join();
-    CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, s, n, cudaMemcpyHostToDevice, c->copy));
-    CU(cudaEventRecord(c->stage_free[k], c->copy));
+    if (!c->stage_free[k]) CU(cudaEventCreateWithFlags(&c->stage_free[k], cudaEventDisableTiming));
   }
+  // The copy threads live for the whole block: chunk i may be written once `ready` has reached i
+  // (its ring buffer has been released by the DMA of chunk i - kStageBufs); every thread copies
+  // its slice of the chunk and counts itself in done[i]; the caller's thread takes slice 0 and
+  // puts the chunk on the wire when all slices have landed.
+  const int k0 = c->stage_next;
+  std::atomic<long> ready{-1};
+  std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[(size_t)n_chunks]);
+  for (long i = 0; i < n_chunks; ++i) done[(size_t)i].store(0, std::memory_order_relaxed);
+  char* stage_ptr[Ctx::kStageBufs];
+  for (int k = 0; k < Ctx::kStageBufs; ++k) stage_ptr[k] = static_cast<char*>(c->stage[k].p);
+  const char* base = static_cast<const char*>(src);
+  auto copy_slice = [&](long i, int t) {
+    const size_t off = (size_t)i * chunk, n = std::min(chunk, bytes - off), a = part * (size_t)t;
+    if (a < n) std::memcpy(stage_ptr[(k0 + i) % Ctx::kStageBufs] + a, base + off + a, std::min(part, n - a));
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < n_thr; ++t)
+    pool.emplace_back([&, t] {
+      for (long i = 0; i < n_chunks; ++i) {
+        while (ready.load(std::memory_order_acquire) < i) std::this_thread::yield();
+        if (ready.load(std::memory_order_acquire) >= n_chunks) return;  // the caller gave up
+        copy_slice(i, t);
+        done[(size_t)i].fetch_add(1, std::memory_order_release);
+      }
+    });
+  cudaError_t err = cudaSuccess;
+  for (long i = 0; i < n_chunks && err == cudaSuccess; ++i) {
+    const int k = (int)((k0 + i) % Ctx::kStageBufs);
+    err = cudaEventSynchronize(c->stage_free[k]);  // never recorded yet: returns at once
+    if (err != cudaSuccess) break;
+    ready.store(i, std::memory_order_release);
+    copy_slice(i, 0);
+    while (done[(size_t)i].load(std::memory_order_acquire) < n_thr - 1) std::this_thread::yield();
+    const size_t off = (size_t)i * chunk, n = std::min(chunk, bytes - off);
+    err = cudaMemcpyAsync(static_cast<char*>(dst) + off, stage_ptr[k], n, cudaMemcpyHostToDevice, c->copy);
+    if (err == cudaSuccess) err = cudaEventRecord(c->stage_free[k], c->copy);
+  }
+  ready.store(n_chunks, std::memory_order_release);  // releases threads still waiting after an error
+  for (auto& th : pool) th.join();
+  c->stage_next = (int)((k0 + n_chunks) % Ctx::kStageBufs);
+  if (err != cudaSuccess) return cuda_fail(c, err, "staging a pageable block");
   return BANDUP_GPU_OK;
 }
 
