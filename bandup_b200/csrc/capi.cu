@@ -9,7 +9,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <atomic>
+#include <cstdint>
 #include <memory>
 #include <thread>
 
@@ -133,6 +137,33 @@ void resolve_pending(Ctx* c) {
 // threads copy into a ring of page-locked buffers while the previous chunks are on the wire.
 constexpr size_t kStageChunk = size_t(16) << 20;
 
+// The staging buffer is written once and next read by the DMA engine: streaming (non-temporal)
+// stores skip the read-for-ownership of the destination lines, a third of the copy's DRAM traffic.
+inline void stream_copy(char* dst, const char* src, size_t n) {
+#if defined(__x86_64__) && defined(__SSE2__)
+  size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+  if (head > n) head = n;
+  std::memcpy(dst, src, head);
+  dst += head; src += head; n -= head;
+  const size_t blocks = n / 64;
+  for (size_t i = 0; i < blocks; ++i) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 16));
+    const __m128i c2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 32));
+    const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst), a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 16), b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 32), c2);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 48), d);
+    src += 64; dst += 64;
+  }
+  _mm_sfence();
+  std::memcpy(dst, src, n - blocks * 64);
+#else
+  std::memcpy(dst, src, n);
+#endif
+}
+
 int upload_block(Ctx* c, void* dst, const void* src, size_t bytes) {
   cudaPointerAttributes attr{};
   const bool locked = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
@@ -166,7 +197,7 @@ int upload_block(Ctx* c, void* dst, const void* src, size_t bytes) {
   const char* base = static_cast<const char*>(src);
   auto copy_slice = [&](long i, int t) {
     const size_t off = (size_t)i * chunk, n = std::min(chunk, bytes - off), a = part * (size_t)t;
-    if (a < n) std::memcpy(stage_ptr[(k0 + i) % Ctx::kStageBufs] + a, base + off + a, std::min(part, n - a));
+    if (a < n) stream_copy(stage_ptr[(k0 + i) % Ctx::kStageBufs] + a, base + off + a, std::min(part, n - a));
   };
   std::vector<std::thread> pool;
   for (int t = 1; t < n_thr; ++t)
