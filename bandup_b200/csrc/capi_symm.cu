@@ -23,8 +23,12 @@ int bandup_gpu_symm_average(int handle, int n_dirs, int64_t n_values, const doub
   CU(c->avg_in.reserve(w_off + sizeof(double) * (size_t)n_dirs));
   CU(c->avg_out.reserve(sizeof(double) * (size_t)n_values));
   char* base = static_cast<char*>(c->avg_in.p);
-  CU(cudaMemcpyAsync(base, in, in_bytes, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(base + w_off, weights, sizeof(double) * (size_t)n_dirs, cudaMemcpyHostToDevice, s));
+  // the columns are usually pageable host memory: through the pinned staging ring (copy stream)
+  CU(cudaStreamSynchronize(s));
+  int rc = upload_block(c, base, in, in_bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(base + w_off, weights, sizeof(double) * (size_t)n_dirs, cudaMemcpyHostToDevice, c->copy));
+  CU(cudaStreamSynchronize(c->copy));
   {
     KernelScope k(c, BANDUP_GPU_K_SYMM_AVG, s);
     launch_symm_average(reinterpret_cast<const double*>(base), reinterpret_cast<const double*>(base + w_off),
@@ -75,7 +79,12 @@ int bandup_gpu_symm_average_rho(int handle, int n_dirs, int n_pckpts, int nener,
   char* tmp = static_cast<char*>(c->avg_tmp.p);
   const void* srcs[6] = {pckpt, iener, m1, m2, rho_re, rho_im};
   const size_t dsts[6] = {o_pck, o_ien, o_m1, o_m2, o_re, o_im};
-  for (int a = 0; a < 6; ++a) CU(cudaMemcpyAsync(in + dsts[a], srcs[a], 4 * N, cudaMemcpyHostToDevice, s));
+  CU(cudaStreamSynchronize(s));
+  for (int a = 0; a < 6; ++a) {  // pageable arrays: through the pinned staging ring (copy stream)
+    const int rc = upload_block(c, in + dsts[a], srcs[a], 4 * N);
+    if (rc) return rc;
+  }
+  CU(cudaStreamSynchronize(c->copy));
   static_assert(sizeof(long long) == sizeof(int64_t), "dir_offsets are staged as long long");
   CU(cudaMemcpyAsync(in + o_off, dir_offsets, 8 * ((size_t)n_dirs + 1), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(in + o_w, weights, 8 * (size_t)n_dirs, cudaMemcpyHostToDevice, s));
