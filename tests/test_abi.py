@@ -81,3 +81,75 @@ def test_fortran_shim_matches_header():
     from bandup_b200 import _capi
     for k, v in consts.items():
         assert _capi.CONST[k] == int(v), k
+
+
+def _c_args(name):
+    """[(base type, is_pointer)] of a header prototype."""
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "bandup_gpu.h").read_text(), flags=re.S)
+    m = re.search(r"\b" + name + r"\s*\(([^)]*)\)\s*;", text)
+    out = []
+    for a in m.group(1).split(","):
+        a = a.strip()
+        if a in ("", "void"):
+            continue
+        ptr = a.count("*")
+        a = re.sub(r"\bconst\b|\*", " ", a)
+        toks = a.split()
+        base = " ".join(toks[:-1]) if len(toks) > 1 else toks[0]    # drop the parameter name
+        out.append((base.strip(), ptr))
+    return out
+
+
+def _fortran_interfaces():
+    """{c name: [(arg, fortran type text, has value attribute)]} of every bind(c) interface."""
+    f90 = (ROOT / "fortran" / "bandup_gpu_mod.f90").read_text()
+    f90 = re.sub(r"&\s*\n\s*", " ", f90)                            # join continuation lines
+    out = {}
+    for m in re.finditer(r"function\s+(\w+)\s*\(([^)]*)\)\s*bind\(c,\s*name='(\w+)'\)(.*?)end function \1", f90, re.S):
+        args = [a.strip() for a in m.group(2).split(",") if a.strip()]
+        decl = {}
+        for line in m.group(4).splitlines():
+            line = line.split("!")[0].strip()
+            if "::" not in line:
+                continue
+            left, right = line.split("::", 1)
+            for var in re.split(r",(?![^()]*\))", right):
+                v = re.sub(r"\(.*\)", "", var).strip()
+                decl[v] = (left.strip(), "(" in var)
+        out[m.group(3)] = [(a,) + decl[a] for a in args]
+    return out
+
+
+C_TO_F = {"int": "integer(c_int)", "unsigned": "integer(c_int)", "int32_t": "integer(c_int32_t)",
+          "int64_t": "integer(c_int64_t)", "size_t": "integer(c_size_t)", "double": "real(c_double)",
+          "float": "real(c_float)", "uint8_t": "integer(c_int8_t)", "uint64_t": "integer(c_int64_t)"}
+
+
+def test_fortran_shim_argument_types_and_passing_convention():
+    """The shim cannot be compiled here (no Fortran front end), so every dummy argument is checked
+    against the C prototype: scalars the C side takes by value carry `value` and the matching kind;
+    pointers are either by-reference dummies of the matching kind (scalars or assumed-size arrays)
+    or `type(c_ptr), value`."""
+    n_checked = 0
+    for name, fargs in _fortran_interfaces().items():
+        cargs = _c_args(name)
+        assert len(cargs) == len(fargs), name
+        for (cbase, cptr), (fname, ftype, is_array) in zip(cargs, fargs):
+            has_value = bool(re.search(r"\bvalue\b", ftype))
+            kind = ftype.split(",")[0].replace(" ", "")
+            where = f"{name}({fname}): C `{cbase}{' *' if cptr else ''}` vs Fortran `{ftype}`"
+            if kind == "type(c_ptr)":
+                # a C pointer handed over as an address (T*), or a pointer returned through T**
+                assert (cptr == 1 and has_value) or (cptr == 2 and not has_value), where
+            elif not cptr:
+                assert has_value and not is_array, where             # by-value scalar
+                assert kind == C_TO_F[cbase].replace(" ", ""), where
+            else:
+                assert not has_value, where                          # by reference: Fortran passes the address
+                if cbase in ("void", "char"):
+                    continue
+                if cbase == "bandup_gpu_kpt_desc":
+                    continue
+                assert kind == C_TO_F[cbase].replace(" ", ""), where
+            n_checked += 1
+    assert n_checked > 150
