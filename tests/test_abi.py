@@ -153,3 +153,34 @@ def test_fortran_shim_argument_types_and_passing_convention():
                 assert kind == C_TO_F[cbase].replace(" ", ""), where
             n_checked += 1
     assert n_checked > 150
+
+
+def test_ctypes_binding_argument_types(gpu_lib):
+    """Width and kind of every ctypes argument / return type against the C prototype."""
+    byval = {"int": C.c_int, "unsigned": C.c_uint, "int32_t": C.c_int32, "int64_t": C.c_int64,
+             "size_t": C.c_size_t, "double": C.c_double, "uint64_t": C.c_uint64}
+    pointee = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "double": C.c_double,
+               "float": C.c_float, "uint8_t": C.c_uint8}
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "bandup_gpu.h").read_text(), flags=re.S)
+    n = 0
+    for name in _header_prototypes():
+        fn = getattr(gpu_lib, name)
+        ret = re.search(r"(?:^|\n)((?:const\s+)?[\w]+(?:\s*\*)?)\s*\b" + name + r"\s*\(", text).group(1).strip()
+        ret = re.sub(r"\s*\*", " *", ret)
+        want_ret = {"int": C.c_int, "size_t": C.c_size_t, "int64_t": C.c_int64, "const char *": C.c_char_p}[ret]
+        assert fn.restype is want_ret, f"{name}: returns {ret}, ctypes says {fn.restype}"
+        for i, ((cbase, cptr), at) in enumerate(zip(_c_args(name), fn.argtypes)):
+            where = f"{name} arg {i}: C `{cbase}{'*' * cptr}` vs ctypes {at}"
+            if not cptr:
+                assert at is byval[cbase], where
+            elif at in (C.c_void_p, C.c_char_p):
+                pass                                                  # untyped address
+            else:
+                assert hasattr(at, "_type_"), where                   # POINTER(T)
+                if cptr == 2:
+                    assert at._type_ is C.c_void_p, where
+                elif cbase in pointee:
+                    assert C.sizeof(at._type_) == C.sizeof(pointee[cbase]), where
+                    assert (at._type_ in (C.c_float, C.c_double)) == (cbase in ("float", "double")), where
+            n += 1
+    assert n > 200
