@@ -351,7 +351,21 @@ void parse_vec3(const std::string& s, double* v) {
 
 }  // namespace
 
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// print_time (io_routines_mod.f90:1885-1920): message, seconds, share of the total
+void print_time(const char* message, double t, double total) {
+  if (t == total)
+    std::printf("%s%7.2fs.\n", message, t);
+  else if (t >= 0.1 || (total > 0.0 && 100.0 * t / total >= 1.0))
+    std::printf("%s%7.2fs (%.1f%%).\n", message, t, total > 0.0 ? 100.0 * t / total : 0.0);
+}
+
 int main(int argc, char** argv) {
+  const double t_start = now_s();
+  double t_read = 0.0, t_write = 0.0;  // t_read is only touched by the one read in flight
   const Args args = parse_args(argc, argv);
   const std::string wf_file = args.get("-wf_file", "WAVECAR");
   const std::string out_file = args.get("-out_file_nosymm", "unfolded_EBS_not-symmetry_averaged.dat");
@@ -372,6 +386,7 @@ int main(int argc, char** argv) {
 
   int h = -1;
   gpu_check(-1, bandup_gpu_init(std::atoi(args.get("-device", std::to_string(rank)).c_str()), &h), "bandup_gpu_init");
+  gpu_check(h, bandup_gpu_set_profiling(h, 1), "set_profiling");  // per-kernel times for the final report
   if (n_ranks > 1) {
     const std::string idf = args.get("-nccl_id_file", "bandup_gpu_nccl_id");
     char id[BANDUP_GPU_COMM_ID_BYTES];
@@ -565,13 +580,19 @@ int main(int argc, char** argv) {
 
   std::future<void> ahead;
   if (next_used())
-    ahead = std::async(std::launch::async, [&] { wc.read_band_records(used[0] + 1, spin_channel, bufs[0], read_threads); });
+    ahead = std::async(std::launch::async, [&] {
+      const double t0 = now_s();
+      wc.read_band_records(used[0] + 1, spin_channel, bufs[0], read_threads);
+      t_read += now_s() - t0;
+    });
   for (size_t j = 0; j < used.size(); ++j) {
     ahead.get();
     if (next_used()) {  // one k-point ahead: its records are read while k-point j uploads / computes
       const int i_next = used[j + 1];
       ahead = std::async(std::launch::async, [&, j, i_next] {
+        const double t0 = now_s();
         wc.read_band_records(i_next + 1, spin_channel, bufs[(j + 1) % (size_t)n_buf], read_threads);
+        t_read += now_s() - t0;
       });
     }
     if ((int)inflight.size() >= depth) {
@@ -681,6 +702,7 @@ int main(int argc, char** argv) {
   }
 
   // write_band_struc (io_routines_mod.f90:889-977): '(2(f8.4,2X),ES10.3)' [+ 5 spin columns]
+  const double t_write0 = now_s();
   double normal[3] = {0, 0, 1}, origin[3] = {0, 0, 0};
   parse_vec3(args.get("-normal_to_proj_plane", "0, 0, 1"), normal);
   parse_vec3(args.get("-origin_for_spin_proj_cart", "0, 0, 0"), origin);
@@ -806,8 +828,24 @@ int main(int argc, char** argv) {
     std::fclose(f);
   }
 
+  t_write = now_s() - t_write0;
   std::printf("%zu pc-kpts unfolded from %zu SC-kpts; %lld GPU kernel launches.\n", n_pck, used.size(),
               (long long)bandup_gpu_launch_count(h));
+  {  // print_final_times (io_routines_mod.f90:1923-1962), the categories this host has
+    double ms[BANDUP_GPU_K_COUNT] = {0};
+    for (int k = 0; k < BANDUP_GPU_K_COUNT; ++k) {
+      int64_t n = 0;
+      bandup_gpu_kernel_time(h, k, &ms[k], &n);
+    }
+    const double total = now_s() - t_start;
+    print_time("Total elapsed time:                                               ", total, total);
+    print_time("Time spent reading the wavefunctions file (overlapped):           ", t_read, total);
+    print_time("Time spent calculating spectral weights (GPU kernels):            ",
+               1e-3 * (ms[BANDUP_GPU_K_COSET] + ms[BANDUP_GPU_K_WEIGHTS] + ms[BANDUP_GPU_K_FINALIZE]), total);
+    print_time("Time spent calculating the unfolded N(k,E) (GPU kernels):         ", 1e-3 * ms[BANDUP_GPU_K_DELTA_N], total);
+    print_time("Time spent calculating unfolding-density operators (GPU kernels): ", 1e-3 * ms[BANDUP_GPU_K_RHO], total);
+    print_time("Time spent writing output file(s):                                ", t_write, total);
+  }
   for (auto b : bufs) bandup_gpu_pinned_free(b);
   bandup_gpu_finalize(h);
   ::close(wc.fd);
