@@ -966,3 +966,32 @@ def test_maximum_pckpts_per_submit(unfolder):
     with pytest.raises(BandupGpuError) as ei:
         unfolder.submit(7, wf, g0=np.concatenate([g0, g0[:1]]))
     assert ei.value.code == 5
+
+
+@pytest.mark.parametrize("offset_bytes", [0, 8, 24])
+def test_pageable_staging_handles_odd_sizes_and_misaligned_sources(unfolder, offset_bytes):
+    """The pinned staging ring (streaming 64-byte stores, several copy threads, several chunks)
+    with a block whose size is no multiple of 64 bytes and whose host address is only 8-byte
+    aligned: same numbers as the page-locked upload of the same data."""
+    from bandup_b200.unfold import PwWavefunction, pinned_empty, pinned_free
+    sc = synth.make_scenario("si333_vacancy", scale=0.5)
+    grid = setup(unfolder, sc)
+    coeffs, gf, ener = synth.make_wavefunction(sc, 1)
+    nb, n_pw, nsp = coeffs.shape
+    nbytes = coeffs.nbytes
+    assert nbytes > (8 << 20) and nbytes % 64 != 0          # > 8 chunks of >= 1 MB, ragged tail
+    g0, _ = unfolder.folding_g0(sc.folding_G(1))
+    pin = pinned_empty(nbytes)
+    pin[:] = coeffs.view(np.uint8).reshape(-1)
+    ref = unfolder.perform_unfolding(PwWavefunction(pin.view(np.complex64).reshape(nb, n_pw, nsp), gf, ener), g0=g0,
+                                     want_selected=False)
+    raw = np.empty(nbytes + 64, dtype=np.uint8)
+    base = (-raw.ctypes.data) % 64 + offset_bytes            # 64-byte boundary + the requested offset
+    view = raw[base:base + nbytes]
+    view[:] = coeffs.view(np.uint8).reshape(-1)
+    assert view.ctypes.data % 64 == offset_bytes
+    got = unfolder.perform_unfolding(PwWavefunction(view.view(np.complex64).reshape(nb, n_pw, nsp), gf, ener), g0=g0,
+                                     want_selected=False)
+    assert np.array_equal(got.spectral_weight, ref.spectral_weight) and np.array_equal(got.dN, ref.dN)
+    assert np.array_equal(got.n_selected, ref.n_selected)
+    pinned_free(pin)
