@@ -169,8 +169,13 @@ def write_energy_info(path, e_fermi: float, emin: float, emax: float, dE) -> Non
 
 
 def _es(x: float) -> str:
-    """Fortran ES10.3."""
-    return "%10.3E" % x
+    """Fortran ES10.3: d.dddE+ee; a three-digit exponent drops the letter (d.ddd+eee) as the
+    standard prescribes for Ew.d, and what does not fit the ten columns becomes asterisks."""
+    s = "%.3E" % x
+    mant, exp = s.split("E")
+    if abs(int(exp)) > 99:
+        s = "%s%+04d" % (mant, int(exp))
+    return s.rjust(10) if len(s) <= 10 else "*" * 10
 
 
 def write_band_struc(path, kpath: PcKptsPath, energy_grid: np.ndarray, dN: np.ndarray, e_fermi: float = 0.0,

@@ -298,10 +298,18 @@ struct Wavecar {
   }
 };
 
-std::string es10_3(double x) {
-  char buf[32];
-  std::snprintf(buf, sizeof buf, "%10.3E", x);
-  return buf;
+std::string es10_3(double x) {  // Fortran ES10.3; three-digit exponents drop the letter (d.ddd+eee)
+  char buf[40];
+  std::snprintf(buf, sizeof buf, "%.3E", x);
+  std::string s = buf;
+  const size_t e = s.find('E');
+  const int ex = std::atoi(s.c_str() + e + 1);
+  if (ex > 99 || ex < -99) {
+    std::snprintf(buf, sizeof buf, "%s%+04d", s.substr(0, e).c_str(), ex);
+    s = buf;
+  }
+  if (s.size() > 10) return std::string(10, '*');
+  return std::string(10 - s.size(), ' ') + s;
 }
 
 struct Args {
