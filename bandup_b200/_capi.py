@@ -122,12 +122,14 @@ def load() -> C.CDLL:
                                            C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]),
         "bandup_gpu_gather_rows": (C.c_int, [C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int64), C.c_int64, c_f64p,
                                              C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]),
+        "bandup_gpu_allgather_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
         "bandup_gpu_set_profiling": (C.c_int, [C.c_int, C.c_int]),
         "bandup_gpu_set_profiling_mask": (C.c_int, [C.c_int, C.c_uint]),
         "bandup_gpu_kernel_time": (C.c_int, [C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int64)]),
         "bandup_gpu_reset_kernel_times": (C.c_int, [C.c_int]),
         "bandup_gpu_launch_count": (C.c_int64, [C.c_int]),
         "bandup_gpu_set_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+        "bandup_gpu_set_option": (C.c_int, [C.c_int, C.c_int, C.c_int]),
         "bandup_gpu_synth_fill_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                                    C.c_int64, C.c_uint64, C.c_uint64]),
     }

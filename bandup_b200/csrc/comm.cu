@@ -100,6 +100,18 @@ int bandup_gpu_gather_dN(int handle, const double* dN_local, const int64_t* row_
                                 capacity_rows, n_total);
 }
 
+int bandup_gpu_allgather_device(int handle, void* stream, const double* d_send, double* d_recv, int64_t count) {
+  Ctx* c = get(handle);
+  if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
+  if (!c->comm) return fail(c, BANDUP_GPU_ERR_NOT_CONFIGURED, "call bandup_gpu_comm_init first");
+  if (!d_send || !d_recv || count < 1) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "bad allgather arguments");
+  const NcclApi& n = nccl_api();
+  cudaSetDevice(c->device);
+  const int rc = n.AllGather(d_send, d_recv, (size_t)count, kNcclFloat64, c->comm, static_cast<cudaStream_t>(stream));
+  if (rc != kNcclSuccess) return fail(c, BANDUP_GPU_ERR_NCCL, std::string("ncclAllGather: ") + n.GetErrorString(rc));
+  return BANDUP_GPU_OK;
+}
+
 int bandup_gpu_gather_rows(int handle, int row_len, const double* dN_local, const int64_t* row_ids_local,
                            int64_t n_local, double* dN_all, int64_t* row_ids_all, int64_t capacity_rows,
                            int64_t* n_total) {
@@ -128,6 +140,10 @@ int bandup_gpu_gather_rows(int handle, int row_len, const double* dN_local, cons
     total += v;
   }
   *n_total = total;
+  // count query: every rank sees the same NULL-ness of the outputs (same call on every rank), so
+  // all of them stop here together, before any payload moves
+  if (!dN_all || !row_ids_all) return BANDUP_GPU_OK;
+  if (capacity_rows < total) return fail(c, BANDUP_GPU_ERR_CAPACITY, "capacity_rows too small: need " + std::to_string(total));
   // 2. one padded payload per rank: [row id (exact in a double below 2^53), nener values] per row
   const size_t row = (size_t)nener + 1, per_rank = row * (size_t)n_max;
   std::vector<double> send(per_rank, 0.0);
@@ -143,8 +159,6 @@ int bandup_gpu_gather_rows(int handle, int row_len, const double* dN_local, cons
   std::vector<double> recv(per_rank * (size_t)R);
   CU(cudaMemcpyAsync(recv.data(), c->comm_recv.p, sizeof(double) * recv.size(), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  if (!dN_all || !row_ids_all) return BANDUP_GPU_OK;  // count query only
-  if (capacity_rows < total) return fail(c, BANDUP_GPU_ERR_CAPACITY, "capacity_rows too small: need " + std::to_string(total));
   // 3. rows in ascending global row id; a duplicate id means a pc-kpt was unfolded twice
   std::vector<std::pair<long long, const double*>> rows;
   rows.reserve((size_t)total);

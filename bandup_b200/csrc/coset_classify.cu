@@ -22,6 +22,9 @@ __device__ __forceinline__ int pos_mod(long long v, long long D) {
 // global memory, nothing to zero beforehand).
 __global__ void __launch_bounds__(256)
 k1_coset_classify(const KptGeom* __restrict__ geoms, CosetCommon cc) {
+  // K2 is launched with programmatic stream serialisation: its producer may start prefetching
+  // coefficients now; its consumers wait for this grid to finish before they read slot[]
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const KptGeom& g = geoms[blockIdx.y];
   __shared__ int s_count[kMaxFolds];
   __shared__ int s_key[kMaxFolds][3];
@@ -116,6 +119,28 @@ k1_selected_lists(const uint8_t* __restrict__ slot_tables, size_t slot_pitch, in
     if (threadIdx.x == 0) s_base += total;
     __syncthreads();
   }
+}
+
+// One CTA per (fold, k-point): the rows of a pc-kpt that shares its coset with an earlier one are
+// copies of that one's (replaces 3 * n_fold small device-to-device copies per k-point).
+__global__ void __launch_bounds__(256)
+k1_replicate_rows(const ReplItem* __restrict__ items) {
+  const ReplItem it = items[blockIdx.y];
+  const int f = blockIdx.x;
+  if (f >= it.n_fold) return;
+  const int u = (reinterpret_cast<const int*>(items + gridDim.y) + it.uo_off)[f];
+  const double* __restrict__ ws = it.w_src + (long long)u * it.n_bands;
+  double* __restrict__ wd = it.w_dst + (long long)f * it.n_bands;
+  for (int i = threadIdx.x; i < it.n_bands; i += blockDim.x) wd[i] = ws[i];
+  const double* __restrict__ ds = it.dn_src + (long long)u * it.nener;
+  double* __restrict__ dd = it.dn_dst + (long long)f * it.nener;
+  for (int i = threadIdx.x; i < it.nener; i += blockDim.x) dd[i] = ds[i];
+  if (threadIdx.x == 0) it.ns_dst[f] = it.ns_src[u];
+}
+
+void launch_replicate_rows(const ReplItem* d_items, int n_items, int max_n_fold, cudaStream_t s) {
+  if (n_items <= 0 || max_n_fold <= 0) return;
+  k1_replicate_rows<<<dim3((unsigned)max_n_fold, (unsigned)n_items), 256, 0, s>>>(d_items);
 }
 
 void launch_selected_lists(const uint8_t* d_slot, size_t slot_pitch, int n_pw, int n_fold,

@@ -65,12 +65,21 @@ struct RhoEntry {  // one stored element of an unfolding-density operator (refer
 };
 
 constexpr int kDescRing = 8;
-struct DescSlot {  // pinned + device staging of one batch's KptGeom array
-  KptGeom* h = nullptr;
-  KptGeom* d = nullptr;
+struct DescSlot {  // pinned + device staging of one batch's descriptor block (KptGeom[], ReplItem[], ...)
+  char* h = nullptr;
+  char* d = nullptr;
   size_t cap = 0;
-  cudaEvent_t ev = nullptr;
+  size_t used = 0;                // bytes of the block it holds (a repeated batch re-uses it without a copy)
+  cudaEvent_t copied = nullptr;   // its host->device copy has finished: h may be rewritten
+  cudaEvent_t done = nullptr;     // the kernels that read d have finished: d may be rewritten
+  cudaStream_t stream = nullptr;  // the stream of its last use
+  bool valid = false;
 };
+
+// Host threads that copy slices of a pageable block into the page-locked staging ring
+// (upload_block).  They live as long as the context and sleep on a condition variable between
+// blocks; one job at a time (the ABI is single-caller per handle).
+struct StagePool;
 
 struct Flight {  // one SC k-point in flight
   bool busy = false;      // submitted, not fetched yet
@@ -104,7 +113,10 @@ struct Ctx {
   int32_t M[9] = {0};                    // row-major int_M
   CosetCommon coset{};
   DescSlot desc_ring[kDescRing];
-  int desc_next = 0;
+  int desc_next = 0, desc_last = -1;
+  StagePool* stage_pool = nullptr;
+  bool use_pdl = true;  // K1 -> K2 -> K3 chained with programmatic dependent launch
+  int k2_variant = 0;  // 0 auto, 1 shared-memory bins, 2 register accumulators (when <= 4 cosets)
   std::vector<double> grid;
   DevBuf d_grid;
   NcclComm comm = nullptr;  // delta_N gather across ranks (one process per GPU)
@@ -177,6 +189,7 @@ struct KernelScope {  // brackets one launch with events when profiling is on
 
 // Host -> device copy on the copy stream; pageable sources go through the pinned staging ring.
 int upload_block(Ctx* c, void* dst, const void* src, size_t bytes);
+void stage_pool_destroy(Ctx* c);
 
 // The flight that still holds SC-kpt `ikpt` after it has been fetched (rho, Pauli vectors, the
 // spectral function work on it); error when it is still in flight or its buffers were reused.

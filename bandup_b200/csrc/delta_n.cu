@@ -88,7 +88,8 @@ k3_finalize_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict_
   const int n_bands = g.n_bands, n_fold = g.n_fold;
   const double* __restrict__ band_energies = g.energies;
   const double* __restrict__ partials = g.partials;
-  const int n_chunks = g.n_chunks, nslots = n_fold + 1, perform_unfold = g.perform_unfold;
+  const int n_chunks = g.n_parts, nslots = n_fold + 1, perform_unfold = g.perform_unfold;  // n_chunks: partial rows per band
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // K2's partials (and, through K2, K1's counts)
   {  // ---- finalisation of K2: this CTA's slice of the (band, slot) pairs -------------------
     const long long items = (long long)n_bands * nslots;
     const long long per_cta = (items + gridDim.x - 1) / gridDim.x;
@@ -270,11 +271,11 @@ k3_spectral_function(const double* __restrict__ grid, int nener, double stddev,
 }  // namespace
 
 void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const double* d_grid,
-                    int nener, double sigma, cudaStream_t s) {
+                    int nener, double sigma, bool pdl, cudaStream_t s) {
   if (nener <= 0 || max_n_fold <= 0 || n_kpts <= 0) return;  // set_grid guarantees nener >= 1
   const int bins_per_cta = kK3Threads / 32;
   dim3 grid((unsigned)((nener + bins_per_cta - 1) / bins_per_cta), (unsigned)n_kpts);
-  k3_finalize_delta_n<<<grid, kK3Threads, 0, s>>>(d_geoms, d_grid, nener, sigma);
+  launch_kernel(k3_finalize_delta_n, grid, dim3(kK3Threads), 0, s, pdl, d_geoms, d_grid, nener, sigma);
 }
 
 void launch_spectral_function(const double* d_grid, int nener, double stddev, const double* d_band_energies,

@@ -42,9 +42,10 @@ struct KptGeom {
   int n_fold;
   int chunk_vecs;             // 16-byte vectors per K2 tile (a multiple of the 1024-vector stage)
   int n_chunks;               // tiles per band
+  int n_parts;                // partial rows per band: n_chunks (bins) or n_chunks * 8 warps (registers)
   int perform_unfold;         // 0: -dont_unfold, every spectral weight is 1 (:1346-1351)
   long long tile_begin;       // global index of this k-point's first K2 tile
-  double* partials;           // [n_bands][n_chunks][n_fold+1]; [..][0] = norm part
+  double* partials;           // [n_bands][n_parts][n_fold+1]; [..][0] = norm part
   double* weights;            // [n_fold][n_bands]
   double* norms;              // [n_bands] or null
   double* dN;                 // [n_fold][nener]
@@ -59,13 +60,50 @@ struct KptGeom {
 void launch_coset_classify(const KptGeom* d_geoms, int n_kpts, int max_n_pw, const CosetCommon& cc,
                            cudaStream_t s);
 
+// Rows of pc-kpts that share a coset: dst row f <- unique row unique_of[f] (weights, delta_N,
+// n_selected) for every listed SC-kpt in one launch.
+struct ReplItem {
+  double* w_dst;
+  const double* w_src;
+  double* dn_dst;
+  const double* dn_src;
+  int32_t* ns_dst;
+  const int32_t* ns_src;
+  int uo_off;  // unique_of[n_fold] starts this many ints behind the end of the item array
+  int n_fold, n_bands, nener;
+};
+void launch_replicate_rows(const ReplItem* d_items, int n_items, int max_n_fold, cudaStream_t s);
+
 // Ordered compaction of the 1-based selected indices of every fold (CSR).  d_slot: one table per
 // pass of kMaxFolds folds, slot_pitch bytes apart.
 void launch_selected_lists(const uint8_t* d_slot, size_t slot_pitch, int n_pw, int n_fold,
                            const int32_t* d_n_selected, int32_t* d_selected,
                            cudaStream_t s);
 
+// Launch with or without programmatic stream serialisation (PDL): with it the kernel may start
+// while the previous kernel of the stream still runs and must call griddepcontrol.wait before it
+// touches anything that kernel writes.  K1 -> K2 -> K3 of a batch are chained this way.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                 bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int weights_num_chunks(long long row_elems, int chunk_vecs);
+// K2 accumulator layout: 0 = shared-memory bins, 1/2/4 = that many register accumulators
+// (variant: 0 auto, 1 force bins, 2 registers whenever max_n_fold <= 4)
+int weights_pick_nreg(int variant, int max_n_fold);
+int weights_partials_sub(int nreg);
 size_t weights_partials_bytes(int n_bands, int n_chunks, int n_fold);
 // requested > 0: rounded up to whole stages; 0: chosen from the block shape
 int weights_pick_chunk_vecs(int requested, long long row_elems, int n_bands, int sm_count, int n_spinor);
@@ -76,8 +114,8 @@ int weights_max_folds_supported();
 // Fuses io_routines_mod.f90:1317-1330 (norm) with band_unfolding_routines_mod.f90:638-644 and
 // :1337-1345 (weights, spinor sum).  All k-points of a batch share n_spinor and layout.
 void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int max_n_fold,
-                           int n_spinor, int layout, int ctas_per_sm, int n_stages, int sm_count,
-                           cudaStream_t s);
+                           int n_spinor, int layout, int nreg, int ctas_per_sm, int n_stages, int sm_count,
+                           bool pdl, cudaStream_t s);
 
 // K3 -- first the deterministic tile combine of K2's partials (s = sum_c norm part,
 // S_f = sum_c fold part, weights[f][b] = s > eps ? S_f / s : S_f -- the reference leaves a band
@@ -86,7 +124,7 @@ void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_t
 // (calc_delta_N_pckpt, band_unfolding_routines_mod.f90:719-757, with lambda :701-716
 // and integral_delta_x_minus_x0, math_mod.f90:181-193).
 void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const double* d_grid,
-                    int nener, double sigma, cudaStream_t s);
+                    int nener, double sigma, bool pdl, cudaStream_t s);
 
 // K0 -- plane-wave list of an SC k-point regenerated on the device in the WAVECAR reader's order
 // (read_wavecar_mod.f90:213-304).  count: per-CTA counts + exclusive scan (total at

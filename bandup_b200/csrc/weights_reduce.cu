@@ -26,6 +26,19 @@
 // (conflict-free: bin f of thread t lives at bins[f*256 + t]); then release the
 // stage through its `empty` barrier.  Warp shuffles + one shared-memory hop
 // reduce the tile.  Fully deterministic: no atomics, fixed combination order.
+//
+// Two accumulator layouts (template NREG).  NREG = 0: the shared-memory bins above, for up to
+// kMaxFolds distinct cosets; a real branch per vector, so it is cheapest when selected plane
+// waves are rare (det M in the hundreds).  NREG = 1/2/4: at most NREG distinct cosets, the
+// common case (one to three pc-kpts fold onto an SC-kpt) -- every fold has a REGISTER
+// accumulator fed by predicated adds (no branch, no shared-memory read-modify-write: with a
+// small det M or spinor rows nearly every warp used to take the branch), and the tile epilogue
+// is warp-local (shuffles, one partial per warp: partials[band][chunk][warp][slot]), so the
+// eight consumer warps never meet at a CTA barrier and drift freely across tile boundaries.
+//
+// Launched with programmatic stream serialisation behind K1: the producer starts filling the
+// ring while K1 still classifies (the coefficients do not depend on K1); the consumers wait for
+// K1's slot tables at griddepcontrol.wait.
 #include <cmath>
 
 #include "kernels.cuh"
@@ -222,16 +235,87 @@ __device__ __forceinline__ void consume_stage(const float4* __restrict__ sv, uin
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 3)
+// The same stage with register accumulators: acc[f] of this thread takes the |C|^2 of the
+// elements whose slot id is f.  The eight terms of a stage are combined per fold as one short
+// fp32 run (almost always a single non-zero term: exact) and widened to fp64 once per stage.
+// PAIRED: spinor rows [pw][spinor] on a 16-byte boundary -- a vector is the two components of
+// ONE plane wave and carries one slot id.
+template <int MODE, int NREG, bool FULL, bool PAIRED>
+__device__ __forceinline__ void consume_stage_reg(const float4* __restrict__ sv, uint64_t* full, uint64_t* empty,
+                                                  uint32_t phase, const SlotSrc& ss, int j, int nv, int tid,
+                                                  int lane, double (&acc)[NREG], double& nrm) {
+  unsigned sl[kVecPerThread];
+  float4 v[kVecPerThread];
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    const int i = tid + u * kConsumers;
+    if (PAIRED)
+      sl[u] = (FULL || i < nv) ? (unsigned)__ldg(ss.slot + j + i) : 0xFFu;
+    else
+      sl[u] = (FULL || i < nv) ? slot_pair<MODE>(ss, j + i) : 0xFFFFu;
+  }
+  mbar_wait(full, phase);
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    const int i = tid + u * kConsumers;
+    v[u] = (FULL || i < nv) ? sv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty);
+
+  float run = 0.f;
+  float r[NREG];
+#pragma unroll
+  for (int f = 0; f < NREG; ++f) r[f] = 0.f;
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    const float pa = fmaf(v[u].y, v[u].y, v[u].x * v[u].x);
+    const float pb = fmaf(v[u].w, v[u].w, v[u].z * v[u].z);
+    run += pa;
+    run += pb;
+    if (PAIRED) {
+#pragma unroll
+      for (int f = 0; f < NREG; ++f) {
+        r[f] += (sl[u] == (unsigned)f) ? pa : 0.f;
+        r[f] += (sl[u] == (unsigned)f) ? pb : 0.f;
+      }
+    } else {
+      const unsigned sa = sl[u] & 0xFFu, sb = sl[u] >> 8;
+#pragma unroll
+      for (int f = 0; f < NREG; ++f) {
+        r[f] += (sa == (unsigned)f) ? pa : 0.f;
+        r[f] += (sb == (unsigned)f) ? pb : 0.f;
+      }
+    }
+  }
+  nrm += (double)run;
+#pragma unroll
+  for (int f = 0; f < NREG; ++f) acc[f] += (double)r[f];
+}
+
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_primary() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// |C|^2 of the row head / tail element that does not fill an aligned 16-byte vector
+__device__ __forceinline__ float lone_element(const float2* el, long long e) {
+  const float2 c = el[e];
+  return fmaf(c.y, c.y, c.x * c.x);
+}
+
+template <int MODE, int NREG>
+__global__ void __launch_bounds__(kThreads, NREG ? 2 : 3)
 k2_weights_reduce(const KptGeom* __restrict__ geoms, int n_kpts, long long total_tiles, int max_n_fold,
                   int n_stages) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [n_stages][16 KB] | acc [max_n_fold+1][256] f64 (row 0: norm, row f+1: fold f) | barriers
+  // layout: [n_stages][16 KB] | NREG == 0: acc [max_n_fold+1][256] f64 (row 0: norm, row f+1: fold f) | barriers
   float4* stage_base = reinterpret_cast<float4*>(smem_raw);
   double* acc = reinterpret_cast<double*>(smem_raw + (size_t)n_stages * kStageBytes);
   double* bins = acc + kConsumers;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(acc + (size_t)(max_n_fold + 1) * kConsumers);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(acc + (NREG ? 0 : (size_t)(max_n_fold + 1) * kConsumers));
   uint64_t* empty_bar = full_bar + kMaxStages;
 
   const int tid = threadIdx.x;
@@ -243,9 +327,11 @@ k2_weights_reduce(const KptGeom* __restrict__ geoms, int n_kpts, long long total
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_launch_dependents();  // K3 may take its place on the SMs; it waits for this grid to finish
 
   if (tid >= kConsumers) {
     // ------------------------------ producer ------------------------------
+    // reads the descriptors (uploaded before K1) and the coefficients only: nothing K1 writes
     if (tid == kConsumers) {
       const uint64_t policy = l2_evict_first_policy();
       int s = 0, k = 0;
@@ -270,6 +356,7 @@ k2_weights_reduce(const KptGeom* __restrict__ geoms, int n_kpts, long long total
   }
 
   // -------------------------------- consumers --------------------------------
+  pdl_wait_primary();  // K1's slot tables
   const int lane = tid & 31, warp = tid >> 5;
   int s = 0, k = 0;
   uint32_t phase = 0;
@@ -280,77 +367,114 @@ k2_weights_reduce(const KptGeom* __restrict__ geoms, int n_kpts, long long total
     const unsigned nf = (unsigned)n_fold;
     const SlotSrc ss = make_slot_src<MODE>(g, t.e_al);
     const int j0 = (int)t.j0, j1 = (int)t.j1;  // vectors per row < 2^31
-    for (int f = 0; f < n_fold; ++f) bins[f * kConsumers + tid] = 0.0;
     double nrm = 0.0;
-
-    int j = j0;
-    for (; j + kStageVecs <= j1; j += kStageVecs) {
-      consume_stage<MODE, true>(stage_base + (size_t)s * kStageVecs, full_bar + s, empty_bar + s, phase, ss, j,
-                                kStageVecs, tid, lane, nf, bins, nrm);
-      if (++s == n_stages) {
-        s = 0;
-        phase ^= 1u;
-      }
-    }
-    if (j < j1) {  // last, partial stage of a row
-      consume_stage<MODE, false>(stage_base + (size_t)s * kStageVecs, full_bar + s, empty_bar + s, phase, ss, j,
-                                 j1 - j, tid, lane, nf, bins, nrm);
-      if (++s == n_stages) {
-        s = 0;
-        phase ^= 1u;
-      }
-    }
-
-    // row head / tail elements that do not fill an aligned vector
+    // the row head / tail elements that do not fill an aligned vector fall to thread 0
+    float lone_p[2] = {0.f, 0.f};
+    unsigned lone_q[2] = {kNoFold, kNoFold};
     if (tid == 0) {
       const float2* el = reinterpret_cast<const float2*>(t.row);
-      const long long row_elems = g.row_elems;
+      const long long row_elems = g.row_elems, e_tail = t.e_al + 2 * t.nvb;
       if (t.chunk == 0 && t.e_al == 1 && row_elems > 0) {
-        const float2 c = el[0];
-        const float p = fmaf(c.y, c.y, c.x * c.x);
-        nrm += (double)p;
-        const unsigned q = ss.slot[pw_of<MODE>(0, ss.n_pw)];
-        if (q < nf) bins[q * kConsumers] += (double)p;
+        lone_p[0] = lone_element(el, 0);
+        lone_q[0] = ss.slot[pw_of<MODE>(0, ss.n_pw)];
       }
-      const long long e_tail = t.e_al + 2 * t.nvb;
       if (t.chunk == g.n_chunks - 1 && e_tail < row_elems) {
-        const float2 c = el[e_tail];
-        const float p = fmaf(c.y, c.y, c.x * c.x);
-        nrm += (double)p;
-        const unsigned q = ss.slot[pw_of<MODE>(e_tail, ss.n_pw)];
-        if (q < nf) bins[q * kConsumers] += (double)p;
+        lone_p[1] = lone_element(el, e_tail);
+        lone_q[1] = ss.slot[pw_of<MODE>(e_tail, ss.n_pw)];
       }
+      nrm = (double)lone_p[0] + (double)lone_p[1];
     }
-
-    // tile reduction through shared memory: thread partials are already there for the folds;
-    // warp q adds up row q (256 values: 8 per lane, conflict-free, then a shuffle tree).
-    // Fixed order => bit-reproducible.
-    acc[tid] = nrm;
-    consumer_sync();
     const int nslots = n_fold + 1;
-    double* out = g.partials + ((long long)t.band * g.n_chunks + t.chunk) * nslots;
-    for (int q = warp; q < nslots; q += kConsumers / 32) {
-      const double* r = acc + q * kConsumers + lane;
-      double a = 0.0;
+
+    if constexpr (NREG > 0) {
+      // ---- register accumulators, warp-local epilogue --------------------------------
+      double racc[NREG];
 #pragma unroll
-      for (int i = 0; i < kConsumers / 32; ++i) a += r[32 * i];
-      a = warp_sum(a);
-      if (lane == 0) out[q] = a;
+      for (int f = 0; f < NREG; ++f)
+        racc[f] = (lone_q[0] == (unsigned)f ? (double)lone_p[0] : 0.0) + (lone_q[1] == (unsigned)f ? (double)lone_p[1] : 0.0);
+      const bool paired = MODE == 1 && t.e_al == 0;
+      int j = j0;
+      if (paired) {
+        for (; j + kStageVecs <= j1; j += kStageVecs) {
+          consume_stage_reg<MODE, NREG, true, true>(stage_base + (size_t)s * kStageVecs, full_bar + s,
+                                                                empty_bar + s, phase, ss, j, kStageVecs, tid, lane, racc, nrm);
+          if (++s == n_stages) { s = 0; phase ^= 1u; }
+        }
+        if (j < j1) {
+          consume_stage_reg<MODE, NREG, false, true>(stage_base + (size_t)s * kStageVecs, full_bar + s,
+                                                                 empty_bar + s, phase, ss, j, j1 - j, tid, lane, racc, nrm);
+          if (++s == n_stages) { s = 0; phase ^= 1u; }
+        }
+      } else {
+        for (; j + kStageVecs <= j1; j += kStageVecs) {
+          consume_stage_reg<MODE, NREG, true, false>(stage_base + (size_t)s * kStageVecs, full_bar + s,
+                                                                 empty_bar + s, phase, ss, j, kStageVecs, tid, lane, racc, nrm);
+          if (++s == n_stages) { s = 0; phase ^= 1u; }
+        }
+        if (j < j1) {
+          consume_stage_reg<MODE, NREG, false, false>(stage_base + (size_t)s * kStageVecs, full_bar + s,
+                                                                  empty_bar + s, phase, ss, j, j1 - j, tid, lane, racc, nrm);
+          if (++s == n_stages) { s = 0; phase ^= 1u; }
+        }
+      }
+      // one partial per warp and slot, fixed shuffle tree => bit-reproducible; K3 adds them up
+      double* out = g.partials + (((long long)t.band * g.n_chunks + t.chunk) * (kConsumers / 32) + warp) * nslots;
+      const double v0 = warp_sum(nrm);
+      if (lane == 0) out[0] = v0;
+#pragma unroll
+      for (int f = 0; f < NREG; ++f) {
+        if (f < n_fold) {  // warp-uniform
+          const double vf = warp_sum(racc[f]);
+          if (lane == 0) out[f + 1] = vf;
+        }
+      }
+    } else {
+      // ---- shared-memory bins, CTA-level epilogue ------------------------------------
+      for (int f = 0; f < n_fold; ++f) bins[f * kConsumers + tid] = 0.0;
+      if (tid == 0) {
+        if (lone_q[0] < nf) bins[lone_q[0] * kConsumers] += (double)lone_p[0];
+        if (lone_q[1] < nf) bins[lone_q[1] * kConsumers] += (double)lone_p[1];
+      }
+      int j = j0;
+      for (; j + kStageVecs <= j1; j += kStageVecs) {
+        consume_stage<MODE, true>(stage_base + (size_t)s * kStageVecs, full_bar + s, empty_bar + s, phase, ss, j,
+                                  kStageVecs, tid, lane, nf, bins, nrm);
+        if (++s == n_stages) { s = 0; phase ^= 1u; }
+      }
+      if (j < j1) {  // last, partial stage of a row
+        consume_stage<MODE, false>(stage_base + (size_t)s * kStageVecs, full_bar + s, empty_bar + s, phase, ss, j,
+                                   j1 - j, tid, lane, nf, bins, nrm);
+        if (++s == n_stages) { s = 0; phase ^= 1u; }
+      }
+      // tile reduction through shared memory: thread partials are already there for the folds;
+      // warp q adds up row q (256 values: 8 per lane, conflict-free, then a shuffle tree).
+      // Fixed order => bit-reproducible.
+      acc[tid] = nrm;
+      consumer_sync();
+      double* out = g.partials + ((long long)t.band * g.n_chunks + t.chunk) * nslots;
+      for (int q = warp; q < nslots; q += kConsumers / 32) {
+        const double* r = acc + q * kConsumers + lane;
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < kConsumers / 32; ++i) a += r[32 * i];
+        a = warp_sum(a);
+        if (lane == 0) out[q] = a;
+      }
+      consumer_sync();
     }
-    consumer_sync();
   }
 }
 
 constexpr size_t kSmemBudget = 227 * 1024;
 
-size_t k2_fixed_smem(int n_fold) {  // everything but the stage ring
-  return sizeof(double) * (size_t)(n_fold + 1) * kConsumers + sizeof(uint64_t) * 2 * kMaxStages + 128;
+size_t k2_fixed_smem(int n_fold, bool reg) {  // everything but the stage ring
+  return (reg ? 0 : sizeof(double) * (size_t)(n_fold + 1) * kConsumers) + sizeof(uint64_t) * 2 * kMaxStages + 128;
 }
 
-template <int MODE>
+template <int MODE, int NREG>
 void launch_mode(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int max_n_fold,
-                 int ctas_per_sm, int n_stages, int sm_count, cudaStream_t s) {
-  const size_t fixed = k2_fixed_smem(max_n_fold);
+                 int ctas_per_sm, int n_stages, int sm_count, bool pdl, cudaStream_t s) {
+  const size_t fixed = k2_fixed_smem(max_n_fold, NREG > 0);
   // default: 2 CTAs per SM with 3 stages each (96 KB of loads in flight per SM, about twice
   // what latency x bandwidth asks for; the B200 sweep in profiles/ has 2x3 ahead of 3x4 and of
   // deeper rings by 2-4 %); many folds eat shared memory for the bins, so the ring shrinks
@@ -362,16 +486,28 @@ void launch_mode(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int 
   const size_t per_cta = kSmemBudget / ctas_per_sm - 1024;  // 1 KB per CTA is reserved by the driver
   while (n_stages > 2 && fixed + (size_t)n_stages * kStageBytes > per_cta) --n_stages;
   const size_t smem = fixed + (size_t)n_stages * kStageBytes;
-  cudaFuncSetAttribute(k2_weights_reduce<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kernel = k2_weights_reduce<MODE, NREG>;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_weights_reduce<MODE>, kThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem);
   if (occ < 1) occ = 1;
   if (occ > ctas_per_sm) occ = ctas_per_sm;
   long long grid = (long long)sm_count * occ;
   if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return;
-  k2_weights_reduce<MODE><<<(unsigned)grid, kThreads, smem, s>>>(d_geoms, n_kpts, total_tiles, max_n_fold,
-                                                                  n_stages);
+  launch_kernel(kernel, dim3((unsigned)grid), dim3(kThreads), smem, s, pdl, d_geoms, n_kpts, total_tiles, max_n_fold,
+                n_stages);
+}
+
+template <int MODE>
+void launch_variant(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int max_n_fold, int nreg,
+                    int ctas_per_sm, int n_stages, int sm_count, bool pdl, cudaStream_t s) {
+  switch (nreg) {
+    case 1: launch_mode<MODE, 1>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, pdl, s); break;
+    case 2: launch_mode<MODE, 2>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, pdl, s); break;
+    case 4: launch_mode<MODE, 4>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, pdl, s); break;
+    default: launch_mode<MODE, 0>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, pdl, s); break;
+  }
 }
 
 }  // namespace
@@ -418,8 +554,20 @@ int weights_num_chunks(long long row_elems, int chunk_vecs) {
   return (int)(n < 1 ? 1 : n);
 }
 
+// K2's register-accumulator variant: 1, 2 or 4 accumulators when the batch has at most that
+// many distinct cosets per k-point, 0 = the shared-memory bins.  variant: 0 auto, 1 bins, 2 registers.
+int weights_pick_nreg(int variant, int max_n_fold) {
+  if (variant == 1 || max_n_fold > 4 || max_n_fold < 1) return 0;
+  return max_n_fold <= 1 ? 1 : max_n_fold <= 2 ? 2 : 4;
+}
+
+// partials per (band, chunk): one row of (n_fold + 1) per CTA (bins) or per consumer warp (registers)
+int weights_partials_sub(int nreg) { return nreg > 0 ? kConsumers / 32 : 1; }
+
 size_t weights_partials_bytes(int n_bands, int n_chunks, int n_fold) {
-  return sizeof(double) * (size_t)n_bands * (size_t)n_chunks * (size_t)(n_fold + 1);
+  // room for either layout: n_fold + 1 slots once, or eight warp rows of at most 4 + 1 slots
+  const size_t per = (size_t)(n_fold + 1) > 40 ? (size_t)(n_fold + 1) : 40;
+  return sizeof(double) * (size_t)n_bands * (size_t)n_chunks * per;
 }
 
 int weights_max_folds_supported() {
@@ -430,15 +578,15 @@ int weights_max_folds_supported() {
 }
 
 void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int max_n_fold,
-                           int n_spinor, int layout, int ctas_per_sm, int n_stages, int sm_count,
-                           cudaStream_t s) {
+                           int n_spinor, int layout, int nreg, int ctas_per_sm, int n_stages, int sm_count,
+                           bool pdl, cudaStream_t s) {
   if (n_kpts <= 0 || total_tiles <= 0) return;
   if (n_spinor == 1)
-    launch_mode<0>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, s);
+    launch_variant<0>(d_geoms, n_kpts, total_tiles, max_n_fold, nreg, ctas_per_sm, n_stages, sm_count, pdl, s);
   else if (layout == BANDUP_GPU_LAYOUT_FORTRAN_INMEM)
-    launch_mode<1>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, s);
+    launch_variant<1>(d_geoms, n_kpts, total_tiles, max_n_fold, nreg, ctas_per_sm, n_stages, sm_count, pdl, s);
   else
-    launch_mode<2>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, s);
+    launch_variant<2>(d_geoms, n_kpts, total_tiles, max_n_fold, nreg, ctas_per_sm, n_stages, sm_count, pdl, s);
 }
 
 }  // namespace bandup

@@ -59,3 +59,86 @@ def bind_to_gpu_node(device_index: int, ranks_on_node_hint: int = 1, local_rank:
     except Exception as e:  # pragma: no cover - best effort
         info["error"] = repr(e)
     return info
+
+
+# ---- which GPU a local rank should use -----------------------------------------------------------
+# End to end the path is bound by the host->device copy of the coefficient blocks.  On the 8-GPU
+# boxes pairs of GPUs hang off one PCIe switch and share its uplink: four ranks on GPUs 0-3 get
+# ~29 GB/s each, four ranks on one GPU per switch ~55 GB/s each.  So local ranks are spread over
+# the PCIe tree (farthest first) instead of filling it in index order.
+
+def pci_path(pci_bus_id: str) -> List[str]:
+    """Bridges between the root complex and the device, from sysfs ('pci0000:15', '0000:15:01.0', ...);
+    empty when sysfs does not show the device."""
+    try:
+        real = os.path.realpath(str(Path("/sys/bus/pci/devices") / pci_bus_id.lower()))
+    except OSError:
+        return []
+    parts = [p for p in real.split("/") if p.startswith("pci") or p.count(":") == 2]
+    return parts if len(parts) >= 2 else []
+
+
+def _common_prefix(a: List[str], b: List[str]) -> int:
+    n = 0
+    for x, y in zip(a, b):
+        if x != y:
+            break
+        n += 1
+    return n
+
+
+def spread_order(paths: List[List[str]], numa_nodes: Optional[List[Optional[int]]] = None) -> List[int]:
+    """Order of the devices such that every prefix of it is spread over the PCIe tree as widely as
+    possible: greedy farthest-first on (same NUMA node, shared bridges); ties go to the lower index.
+    Without usable paths: bit-reversed index order (neighbours share a switch on the HGX boards)."""
+    n = len(paths)
+    if n <= 1:
+        return list(range(n))
+    if not all(paths):
+        bits = max(1, (n - 1).bit_length())
+        rev = sorted(range(1 << bits), key=lambda i: int(format(i, f"0{bits}b")[::-1], 2))
+        return [i for i in rev if i < n]
+    numa_nodes = numa_nodes or [None] * n
+
+    def closeness(i: int, j: int) -> int:       # larger = more shared hardware between the two
+        c = _common_prefix(paths[i], paths[j])
+        if numa_nodes[i] is not None and numa_nodes[i] == numa_nodes[j]:
+            c += 1
+        return c
+    order = [0]
+    while len(order) < n:
+        rest = [i for i in range(n) if i not in order]
+        # the candidate whose CLOSEST already-chosen device is the least close; then the one that is
+        # least close to all of them in total
+        best = min(rest, key=lambda i: (max(closeness(i, j) for j in order), sum(closeness(i, j) for j in order), i))
+        order.append(best)
+    return order
+
+
+def device_for_local_rank(local_rank: int, local_world: int) -> dict:
+    """The CUDA device a local rank should use and why: {'device', 'order', 'pci', 'source'}.
+    Deterministic: every rank computes the same order.  BANDUP_B200_GPU_ORDER=0,4,2,... overrides."""
+    import torch
+    n = torch.cuda.device_count()
+    info = {"device": local_rank % max(n, 1), "order": list(range(n)), "source": "index order"}
+    try:
+        env = os.environ.get("BANDUP_B200_GPU_ORDER")
+        bus = []
+        for i in range(n):
+            prop = torch.cuda.get_device_properties(i)
+            bus.append("%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id))
+        if env:
+            order = [int(x) for x in env.split(",")]
+            source = "BANDUP_B200_GPU_ORDER"
+        elif local_world >= n:
+            order, source = list(range(n)), "all visible GPUs in use: index order"
+        else:
+            paths = [pci_path(b) for b in bus]
+            order = spread_order(paths, [gpu_numa_node(b) for b in bus])
+            source = "PCIe tree from sysfs, farthest first" if all(paths) else "no sysfs PCI paths: bit-reversed index order"
+        if sorted(order) != list(range(n)):
+            raise ValueError(f"GPU order {order} is not a permutation of 0..{n - 1}")
+        info.update(device=order[local_rank % n], order=order, pci=bus, source=source)
+    except Exception as e:  # pragma: no cover - best effort
+        info["error"] = repr(e)
+    return info

@@ -54,10 +54,15 @@ class KptTickets:
     def __init__(self, n_kpts: int, store=None, job: str = "0", offset: int = 0, stride: int = 1):
         self.n_kpts = int(n_kpts)
         self.store = store
-        self.key = f"bandup_b200/next_kpt/{job}"
         # without a store: offset, offset+stride, ... (round-robin over ranks when there are several)
         self._local, self._stride = int(offset), max(1, int(stride))
+        self.key = f"bandup_b200/next_kpt/{job}"
         if store is not None:
+            # A counter is never reset, so every use of a job name gets a counter of its own: each
+            # rank counts how many times IT has opened `job` (a key only it increments) and all
+            # ranks open their jobs in the same order, so they agree on the epoch without talking.
+            epoch = int(store.add(f"bandup_b200/epoch/{job}/{int(offset)}", 1))
+            self.key = f"bandup_b200/next_kpt/{job}/{epoch}"
             store.add(self.key, 0)        # creates the counter; every rank may do it
 
     @classmethod

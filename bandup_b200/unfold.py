@@ -526,6 +526,12 @@ class GpuUnfolder:
                                                      tot.value, C.byref(tot)))
         return out.reshape((tot.value,) + shape), oid
 
+    def allgather_device(self, stream: int, d_send: int, d_recv: int, count: int) -> None:
+        """ncclAllGather of `count` doubles per rank between device buffers on the caller's stream
+        (the device-resident form of gather_dN; asynchronous)."""
+        self._check(self._lib.bandup_gpu_allgather_device(self.handle, C.c_void_p(stream), C.c_void_p(d_send),
+                                                          C.c_void_p(d_recv), int(count)))
+
     # -- instrumentation ------------------------------------------------------
     def set_profiling(self, enabled: bool, kernels=None) -> None:
         """Bracket launches with CUDA events; `kernels` (ids) restricts it to those kernels."""
@@ -552,6 +558,10 @@ class GpuUnfolder:
     def set_tuning(self, chunk_vecs: int = 0, ctas_per_sm: int = 0, n_stages: int = 0) -> None:
         self._check(self._lib.bandup_gpu_set_tuning(self.handle, int(chunk_vecs), int(ctas_per_sm),
                                                     int(n_stages)))
+
+    def set_option(self, option: int, value: int) -> None:
+        """bandup_gpu_set_option: CONST['BANDUP_GPU_OPT_K2_VARIANT'] / ['BANDUP_GPU_OPT_DEPENDENT_LAUNCH']."""
+        self._check(self._lib.bandup_gpu_set_option(self.handle, int(option), int(value)))
 
 
 def calc_spin_projections(pauli_vector, cart_coords_kpt, normal_to_proj_plane, origin=None):

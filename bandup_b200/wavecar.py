@@ -283,11 +283,14 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
     # (taken from / returned to a reuse pool: page-locking memory costs about a second per GB)
     bufs = [pinned_pool_get(wavecar.band_block_bytes()) for _ in range(min(4, max(1, len(used))))]
     K_cart = sc_k @ wavecar.B_matrix
+    n_loaded = [0]
 
     def load(j):
         i = used[j]
         fG = np.asarray(pc_kpts_cart)[folds[i]] - K_cart[i]
-        buf = bufs[j % len(bufs)]
+        # the buffers rotate with THIS rank's loads (loads are sequential), not with the k-point index
+        buf = bufs[n_loaded[0] % len(bufs)]
+        n_loaded[0] += 1
         if device_gvecs:   # header + raw records only; the plane-wave list is made on the device
             raw = wavecar.read_band_records(i + 1, ispin, out=buf)      # file -> page-locked memory, here
 

@@ -22,13 +22,13 @@ public :: bandup_gpu_init, bandup_gpu_finalize, bandup_gpu_last_error, &
           bandup_gpu_fetch_kpt, &
           bandup_gpu_pipeline_depth, bandup_gpu_set_profiling, &
           bandup_gpu_kernel_time, bandup_gpu_reset_kernel_times, &
-          bandup_gpu_launch_count, bandup_gpu_set_tuning, &
+          bandup_gpu_launch_count, bandup_gpu_set_tuning, bandup_gpu_set_option, &
           bandup_gpu_rho_count, bandup_gpu_fetch_rho, bandup_gpu_pauli_vectors, &
           bandup_gpu_spectral_function, bandup_gpu_set_perform_unfold, &
           bandup_gpu_orb_contrib_matrix, bandup_gpu_set_operator, bandup_gpu_unfold_operator, &
           bandup_gpu_symm_average, bandup_gpu_symm_average_rho, &
           bandup_gpu_comm_unique_id, bandup_gpu_comm_init, bandup_gpu_comm_finalize, bandup_gpu_gather_dN, &
-          bandup_gpu_gather_rows, &
+          bandup_gpu_gather_rows, bandup_gpu_allgather_device, &
           bandup_gpu_unfold_kpt_f, bandup_gpu_error_message
 public :: BANDUP_GPU_OK, BANDUP_GPU_LAYOUT_FORTRAN_INMEM, BANDUP_GPU_LAYOUT_VASP_RECORD, &
           BANDUP_GPU_MAX_FOLDS
@@ -351,6 +351,16 @@ interface
         integer(c_int) :: bandup_gpu_gather_rows
     end function bandup_gpu_gather_rows
 
+    !! device-resident rows (c_ptr = device addresses), enqueued on the caller's CUDA stream
+    function bandup_gpu_allgather_device(handle, stream, d_send, d_recv, count) &
+        bind(c, name='bandup_gpu_allgather_device')
+        import c_int, c_int64_t, c_ptr
+        integer(c_int), intent(in), value :: handle
+        type(c_ptr), intent(in), value :: stream, d_send, d_recv
+        integer(c_int64_t), intent(in), value :: count
+        integer(c_int) :: bandup_gpu_allgather_device
+    end function bandup_gpu_allgather_device
+
     function bandup_gpu_set_profiling(handle, enabled) bind(c, name='bandup_gpu_set_profiling')
         import c_int
         integer(c_int), intent(in), value :: handle, enabled
@@ -384,6 +394,13 @@ interface
         integer(c_int), intent(in), value :: handle, chunk_vecs, ctas_per_sm, n_stages
         integer(c_int) :: bandup_gpu_set_tuning
     end function bandup_gpu_set_tuning
+
+    function bandup_gpu_set_option(handle, option, value) &
+        bind(c, name='bandup_gpu_set_option')
+        import c_int
+        integer(c_int), intent(in), value :: handle, option, value
+        integer(c_int) :: bandup_gpu_set_option
+    end function bandup_gpu_set_option
 
 end interface
 

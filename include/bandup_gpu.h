@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BANDUP_GPU_ABI_VERSION 4
+#define BANDUP_GPU_ABI_VERSION 5
 
 /* status codes */
 #define BANDUP_GPU_OK 0
@@ -191,7 +191,9 @@ int bandup_gpu_fetch_gvecs(int handle, int ikpt, int32_t *g_frac, int64_t capaci
  *   selected   (nullable) 1-based ascending plane-wave indices, the folds'
  *              lists concatenated (CSR by n_selected); selected_capacity is
  *              the number of int32 available.
- * Any of weights / dN / n_selected may be NULL. */
+ * Any of weights / dN / n_selected may be NULL.  ERR_CAPACITY (selected_capacity too
+ * small; the message names the size needed) consumes nothing: the k-point stays in
+ * flight and may be fetched again with a larger buffer. */
 int bandup_gpu_fetch_kpt(int handle, int ikpt, double *weights, double *dN,
                          int32_t *n_selected, double *norms, int32_t *selected,
                          int64_t selected_capacity);
@@ -368,7 +370,8 @@ int bandup_gpu_comm_init(int handle, int n_ranks, int rank, const void *id);
 int bandup_gpu_comm_finalize(int handle);
 /* Collective.  dN_local [n_local][nener] + the global pc-kpt row id of every row (HOST); every
  * rank receives all rows in ascending row id: dN_all [n_total][nener], row_ids_all [n_total]
- * (HOST, capacity_rows rows).  With dN_all == NULL only *n_total is returned.  A row id
+ * (HOST, capacity_rows rows).  With dN_all == NULL only *n_total is returned (the counts are
+ * exchanged, no rows move).  A row id
  * contributed twice is an error (a pc-kpt unfolded by two ranks). */
 int bandup_gpu_gather_dN(int handle, const double *dN_local, const int64_t *row_ids_local,
                          int64_t n_local, double *dN_all, int64_t *row_ids_all,
@@ -378,6 +381,14 @@ int bandup_gpu_gather_dN(int handle, const double *dN_local, const int64_t *row_
 int bandup_gpu_gather_rows(int handle, int row_len, const double *rows_local,
                            const int64_t *row_ids_local, int64_t n_local, double *rows_all,
                            int64_t *row_ids_all, int64_t capacity_rows, int64_t *n_total);
+
+/* The device-resident form of the collective, for callers whose rows never leave HBM
+ * (bandup_gpu_unfold_device[_batch]): every rank contributes `count` doubles at d_send (pad to
+ * the largest shard), d_recv [n_ranks][count] receives rank r's block at r*count.  One
+ * ncclAllGather enqueued on the caller's `stream` (cudaStream_t); nothing is synchronised and
+ * nothing touches the host. */
+int bandup_gpu_allgather_device(int handle, void *stream, const double *d_send, double *d_recv,
+                                int64_t count);
 
 /* ---- instrumentation ---------------------------------------------------- */
 
@@ -410,6 +421,16 @@ int64_t bandup_gpu_launch_count(int handle);
  * vectors per (band, chunk) tile (rounded up to whole 1024-vector stages),
  * resident CTAs per SM and depth of each CTA's shared-memory stage ring. */
 int bandup_gpu_set_tuning(int handle, int chunk_vecs, int ctas_per_sm, int n_stages);
+
+/* Further switches, for A/B measurements (not while k-points are in flight):
+ *   OPT_K2_VARIANT        accumulators of the weights kernel: 0 = automatic, 1 = per-thread
+ *                         shared-memory bins (any number of cosets), 2 = registers whenever a
+ *                         batch has <= 4 distinct cosets per SC-kpt
+ *   OPT_DEPENDENT_LAUNCH  1 (default): K1 -> K2 -> K3 of a batch are chained with programmatic
+ *                         dependent launch; 0: plain stream order */
+#define BANDUP_GPU_OPT_K2_VARIANT 0
+#define BANDUP_GPU_OPT_DEPENDENT_LAUNCH 1
+int bandup_gpu_set_option(int handle, int option, int value);
 
 /* Fills a device buffer with the synthetic coefficients bench.py and the tests
  * use (same hash as oracle/bandup_oracle.c:bo_synth_fill): n_bands rows of

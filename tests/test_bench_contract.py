@@ -27,6 +27,8 @@ def test_reference_arm_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    f = d["e2e_file"]
+    assert f["value"] > 0 and f["unit"] == "GB/s" and f["sc_kpts"] >= 1 and f["coeff_bytes"] < f["file_bytes"]
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
@@ -35,12 +37,17 @@ def test_b200_arm_json_line():
     d = _run(["--workload", "si333_vacancy", "--steps", "3", "--warmup", "3", "--kpts-per-step", "2",
               "--cpu-seconds", "1"])
     assert BASE_KEYS | {"roofline", "clocks", "gpu_launches"} <= set(d)
-    assert d["n_gpus"] == 1 and d["gpu_launches"] == 3 * 3 and d["value"] > 0
+    # the timed region runs for at least 0.5 s: more steps than asked for, and `steps` says how many
+    assert d["steps"] >= 3 and d["steps_requested"] == 3 and d["timed_region_ms"] >= 500.0
+    assert d["n_gpus"] == 1 and d["gpu_launches"] == 3 * d["steps"] and d["value"] > 0
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
     assert set(rf["kernel_ms_per_step"]) == {"k1_coset_classify", "k2_weights_reduce", "k3_finalize_delta_n"}
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 2 * 500 * 19000 * 8 and e["d2h_bytes_per_step"] > 0
     assert e["value"] < d["value"]                    # host<->device copies are inside the e2e region
+    assert e["e2e_checked"] is True and len(e["h2d_GBps_per_rank"]) == 1 and e["gpu_of_rank"] == [0]
+    f = d["e2e_file"]
+    assert f["value"] > 0 and f["checked_vs_oracle_max_rel_err"] <= 1e-6 and f["page_cache"] == "warm"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]

@@ -446,7 +446,7 @@ def test_device_batch_equals_per_kpt_calls(unfolder):
     d_ws = torch.empty(ws, dtype=torch.uint8, device=dev)
     l0 = unfolder.launch_count()
     unfolder.unfold_device_batch(stream, descs, d_ws.data_ptr(), ws)
-    assert unfolder.launch_count() - l0 == 3                        # K1, K2, K3 once each
+    assert unfolder.launch_count() - l0 == 4                        # K1, K2, K3 once each + one row-replication launch
     for coeffs, gf, ener, fG, t, outs, g0 in host:
         nb, n_pw, _ = coeffs.shape
         w1 = unfolder.workspace_bytes(1, n_pw, nb, g0.shape[0])

@@ -47,6 +47,16 @@ def _worker(rank, world, tmp, ret):
         xrows, xids = u.gather_rows(extra, rid)
         assert np.array_equal(xids, allids) and xrows.shape == (len(allids), dN.shape[1], 3)
         assert np.array_equal(xrows[:, :, 1], -allrows) and np.array_equal(xrows[:, :, 2], allrows + 1.0)
+        # the device-resident form of the collective (what bench.py --gpus N uses once per job)
+        import torch
+        dev = torch.device("cuda", rank)
+        torch.cuda.set_device(dev)
+        send = torch.arange(7, dtype=torch.float64, device=dev) + 100.0 * (rank + 1)
+        recv = torch.zeros((world, 7), dtype=torch.float64, device=dev)
+        u.allgather_device(torch.cuda.current_stream(dev).cuda_stream, send.data_ptr(), recv.data_ptr(), 7)
+        torch.cuda.synchronize()
+        want = np.arange(7)[None, :] + 100.0 * (np.arange(world)[:, None] + 1)
+        assert np.array_equal(recv.cpu().numpy(), want)
         ret[rank] = (allrows, allids, job.my_block, len(rid))
         u.comm_finalize()
 
@@ -141,6 +151,10 @@ def test_bench_two_ranks_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["value"] > 0 and d["e2e"]["value"] > 0
     assert d["cpu_baseline"] is None                     # rank 0 at N = 1 only
+    assert "bandup_gpu_allgather_device" in d["config"]["parallelism"]
+    e = d["e2e"]
+    assert e["e2e_checked"] is True and len(e["h2d_GBps_per_rank"]) == 2 and sorted(e["gpu_of_rank"]) == [0, 1]
+    assert sum(e["kpts_per_rank"]) == 2 * 2 * e["steps"]
 
 
 def test_host_exe_rank_without_kpoints(tmp_path, gpu_lib):

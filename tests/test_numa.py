@@ -1,0 +1,32 @@
+"""Rank -> GPU mapping by PCIe topology (bandup_b200/numa.py): host logic, no GPU needed."""
+from bandup_b200.numa import spread_order
+
+
+def _hgx_paths():
+    # two host bridges, two switches under each, two GPUs per switch: GPUs (0,1), (2,3), (4,5), (6,7)
+    paths = []
+    for g in range(8):
+        hb, sw = g // 4, g // 2
+        paths.append([f"pci0000:{hb:02x}", f"0000:{hb:02x}:01.0", f"0000:{10 + sw:02x}:00.0", f"0000:{20 + g:02x}:00.0"])
+    return paths
+
+
+def test_spread_order_takes_one_gpu_per_switch_first():
+    order = spread_order(_hgx_paths())
+    assert sorted(order) == list(range(8)) and order[0] == 0
+    switches = lambda gpus: {g // 2 for g in gpus}                    # noqa: E731
+    assert len(switches(order[:4])) == 4                                # four ranks: four different switches
+    assert {g // 4 for g in order[:2]} == {0, 1}                        # two ranks: both host bridges
+
+
+def test_spread_order_without_sysfs_is_bit_reversed():
+    assert spread_order([[]] * 8) == [0, 4, 2, 6, 1, 5, 3, 7]
+    assert sorted(spread_order([[]] * 6)) == list(range(6))
+    assert spread_order([[]]) == [0] and spread_order([]) == []
+
+
+def test_spread_order_uses_numa_nodes_when_the_tree_is_flat():
+    # every GPU directly under its own root port: only the NUMA node tells neighbours apart
+    paths = [[f"pci0000:{g:02x}", f"0000:{g:02x}:00.0"] for g in range(4)]
+    order = spread_order(paths, [0, 0, 1, 1])
+    assert {[0, 0, 1, 1][g] for g in order[:2]} == {0, 1}

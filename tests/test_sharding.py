@@ -146,7 +146,13 @@ def _worker_dynamic(rank, world, port, ret):
             job.unfolder.fetch = lambda ikpt: (time.sleep(0.4), fetch(ikpt))[1]
         dist.barrier()
         g = job.run()
-        ret[rank] = (g.dN, g.row_ids, list(job.done_kpts))
+        # a second job under the SAME name starts from a fresh counter (a counter in the store is
+        # never reset: every use of a name gets its own epoch)
+        again = KptTickets.from_default_group(5, job="t1")
+        dist.barrier()
+        mine = list(iter(again.take, None))
+        dist.barrier()
+        ret[rank] = (g.dN, g.row_ids, list(job.done_kpts), mine)
     finally:
         dist.destroy_process_group()
 
@@ -159,7 +165,8 @@ def test_world_size_2_gloo_dynamic_tickets_balance_a_slow_rank():
         ret = mgr.dict()
         mp.spawn(_worker_dynamic, args=(2, _free_port(), ret), nprocs=2, join=True)
         r0, r1 = ret[0], ret[1]
-    for dN, ids, _ in (r0, r1):
+    assert sorted(r0[3] + r1[3]) == list(range(5))                  # the re-used job name handed out 0..4 again
+    for dN, ids, _, _ in (r0, r1):
         assert np.array_equal(ids, single.row_ids)
         assert np.array_equal(dN, single.dN)                        # who computed what does not matter
     assert sorted(r0[2] + r1[2]) == list(range(sc.n_sc_kpts))       # every SC-kpt exactly once
