@@ -348,6 +348,7 @@ struct WorkspaceLayout {
 
 // batch_n: k-points launched together -- the K2 tile size is chosen so that the WHOLE launch
 // has enough tiles to balance the persistent grid (k-points of a job are alike)
+// row_elems: 8-byte units per band row (a complex128 coefficient counts twice)
 int pick_chunk_vecs(const Ctx* c, long long row_elems, int n_bands, int batch_n, int n_spinor) {
   const long long rows = (long long)n_bands * (batch_n > 0 ? batch_n : 1);
   return weights_pick_chunk_vecs(c->chunk_vecs, row_elems, (int)(rows > 2000000000LL ? 2000000000LL : rows),
@@ -356,8 +357,9 @@ int pick_chunk_vecs(const Ctx* c, long long row_elems, int n_bands, int batch_n,
 
 WorkspaceLayout workspace_layout(const Ctx* c, int n_spinor, int n_pw, int n_bands, int n_fold, int batch_n = 1) {
   WorkspaceLayout w;
-  const int cv = pick_chunk_vecs(c, (long long)n_pw * n_spinor, n_bands, batch_n, n_spinor);
-  const int n_chunks = weights_num_chunks((long long)n_pw * n_spinor, cv);
+  const long long row_units = (long long)n_pw * n_spinor * (c->dp_coeffs ? 2 : 1);
+  const int cv = pick_chunk_vecs(c, row_units, n_bands, batch_n, n_spinor);
+  const int n_chunks = weights_num_chunks(row_units, cv);
   // distinct cosets <= pc-kpts: room for the worst case number of passes
   const size_t max_passes = (size_t)((n_fold > 0 ? n_fold : 1) + kMaxFolds - 1) / kMaxFolds;
   size_t off = 0;
@@ -469,8 +471,7 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
       max_repl_fold = std::max(max_repl_fold, it.n_fold);
     }
   }
-  const int nreg = weights_pick_nreg(c->k2_variant, max_fold);
-  const int n_sub = weights_partials_sub(nreg);
+  int bins_rows = 0;  // shared-memory accumulator rows K2 needs: 1 + the most cosets among the k-points on the bins
   // one KptGeom per (k-point, pass of <= kMaxFolds distinct cosets), then the replication items
   const size_t repl_off = (n_geoms_total * sizeof(KptGeom) + 15) & ~size_t(15);
   const size_t uo_off = repl_off + (size_t)n_repl * sizeof(ReplItem);
@@ -493,13 +494,18 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
     it.ns_unique = ns_rows;
     it.d_slot = reinterpret_cast<uint8_t*>(it.ws + wl.slot_off);
     const int passes = it.plan.passes();
+    // accumulator layout of this k-point: registers when its few cosets select a sizeable share of
+    // the plane waves, the shared-memory bins otherwise (and always for a multi-pass k-point)
+    const int nreg = passes > 1 ? 0 : weights_pick_nreg(c->k2_variant, it.plan.n_unique, c->coset.D);
     for (int p = 0; p < passes; ++p) {
       const int u0 = p * kMaxFolds;
       const int nf = std::min(kMaxFolds, it.plan.n_unique - u0);
+      if (nreg == 0) bins_rows = std::max(bins_rows, nf + 1);
       KptGeom& g = geoms[n_geoms++];
       g.coeffs = static_cast<const char*>(it.d_coeffs);
       g.stride_bytes = it.stride_bytes;
       g.row_elems = (long long)it.n_pw * it.n_spinor;
+      g.dp = c->dp_coeffs ? 1 : 0;
       g.n_bands = it.n_bands;
       g.n_pw = it.n_pw;
       g.n_spinor = it.n_spinor;
@@ -511,9 +517,10 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
       g.block_counts = reinterpret_cast<int*>(it.ws + wl.counts_off) + (size_t)kK1MaxBlocks * (size_t)u0;
       g.n_selected = ns_rows + u0;
       g.n_fold = nf;
-      g.chunk_vecs = pick_chunk_vecs(c, g.row_elems, it.n_bands, n, it.n_spinor);
-      g.n_chunks = weights_num_chunks(g.row_elems, g.chunk_vecs);
-      g.n_parts = g.n_chunks * n_sub;
+      g.chunk_vecs = pick_chunk_vecs(c, g.row_elems * (g.dp ? 2 : 1), it.n_bands, n, it.n_spinor);
+      g.n_chunks = weights_num_chunks(g.row_elems * (g.dp ? 2 : 1), g.chunk_vecs);
+      g.nreg = nreg;
+      g.n_parts = g.n_chunks * weights_partials_sub(nreg);
       g.perform_unfold = c->perform_unfold ? 1 : 0;
       g.tile_begin = tiles;
       tiles += (long long)it.n_bands * g.n_chunks;
@@ -548,19 +555,20 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
   const CosetCommon cc = c->coset;
   // event brackets between the launches would serialise them anyway: no dependent launch then
   const unsigned chain = (1u << BANDUP_GPU_K_COSET) | (1u << BANDUP_GPU_K_WEIGHTS) | (1u << BANDUP_GPU_K_DELTA_N);
-  const bool pdl = (c->profiling & chain) == 0 && c->use_pdl;
+  const int pdl = (c->profiling & chain) == 0 ? c->use_pdl : 0;  // bit 0: K1 -> K2, bit 1: K2 -> K3
   {
     KernelScope k(c, BANDUP_GPU_K_COSET, s);
     launch_coset_classify(d_geoms, n_geoms, max_pw, cc, s);
   }
   {
     KernelScope k(c, BANDUP_GPU_K_WEIGHTS, s);
-    launch_weights_reduce(d_geoms, n_geoms, tiles, max_fold, items[0].n_spinor, items[0].layout, nreg, c->ctas_per_sm,
-                          c->n_stages, c->sm_count, pdl, s);
+    launch_weights_reduce(d_geoms, n_geoms, tiles, bins_rows, items[0].n_spinor, items[0].layout, c->dp_coeffs,
+                          c->ctas_per_sm, c->n_stages, c->sm_count, (pdl & 1) != 0, s);
   }
   {
     KernelScope k(c, BANDUP_GPU_K_DELTA_N, s);
-    launch_delta_n(d_geoms, n_geoms, max_fold, static_cast<const double*>(c->d_grid.p), c->nener, c->sigma, pdl, s);
+    launch_delta_n(d_geoms, n_geoms, max_fold, static_cast<const double*>(c->d_grid.p), c->nener, c->sigma,
+                   (pdl & 2) != 0, s);
   }
   if (n_repl > 0) {
     KernelScope k(c, BANDUP_GPU_K_DELTA_N, s);
@@ -587,9 +595,11 @@ int check_shape(Ctx* c, int n_spinor, int n_pw, int n_bands, int layout, long lo
   if (n_pw < 1 || n_bands < 1) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "n_pw and n_bands must be >= 1");
   if (layout != BANDUP_GPU_LAYOUT_FORTRAN_INMEM && layout != BANDUP_GPU_LAYOUT_VASP_RECORD)
     return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "unknown coefficient layout");
-  if (stride < (long long)n_pw * n_spinor * 8 || (stride & 7))
+  const long long esz = c->dp_coeffs ? 16 : 8;
+  if (stride < (long long)n_pw * n_spinor * esz || (stride & (esz - 1)))
     return fail(c, BANDUP_GPU_ERR_INVALID_ARG,
-                "band_stride_bytes must be a multiple of 8 and >= n_pw*n_spinor*8");
+                "band_stride_bytes must be a multiple of " + std::to_string(esz) + " and >= n_pw*n_spinor*" +
+                    std::to_string(esz));
   return BANDUP_GPU_OK;
 }
 
@@ -933,6 +943,8 @@ int bandup_gpu_unfold_device(int handle, void* stream, int n_spinor, int n_pw, i
   if (!d_coeffs || !d_g_frac || !d_band_energies || !g0 || !d_weights || !d_dN || !d_n_selected ||
       !d_workspace)
     return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "NULL device pointer");
+  if (c->dp_coeffs && (reinterpret_cast<uintptr_t>(d_coeffs) & 15))
+    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "complex128 coefficient blocks must be 16-byte aligned");
   std::vector<BatchItem> items(1);
   BatchItem& it = items[0];
   rc = plan_folds(c, n_fold, g0, &it.plan);
@@ -976,6 +988,8 @@ int bandup_gpu_unfold_device_batch(int handle, void* stream, int n_kpts, const b
     if (rc) return rc;
     if (!d.d_coeffs || !d.d_g_frac || !d.d_band_energies || !d.g0 || !d.d_weights || !d.d_dN || !d.d_n_selected)
       return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "NULL pointer in batch descriptor " + std::to_string(i));
+    if (c->dp_coeffs && (reinterpret_cast<uintptr_t>(d.d_coeffs) & 15))
+      return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "complex128 coefficient blocks must be 16-byte aligned");
     BatchItem& it = items[(size_t)i];
     rc = plan_folds(c, d.n_fold, d.g0, &it.plan);
     if (rc) return rc;
@@ -1173,7 +1187,7 @@ int submit_impl(int handle, int ikpt, int n_spinor, int n_pw, int n_bands, int l
   // The buffers of this flight may still be read by its previous kernels only if
   // the caller skipped fetch; fetch synchronises on `done`, so they are idle here.
   const size_t coeff_bytes = (size_t)band_stride_bytes * (size_t)(n_bands - 1) +
-                             (size_t)n_pw * n_spinor * 8;
+                             (size_t)n_pw * n_spinor * (c->dp_coeffs ? 16 : 8);
   const WorkspaceLayout wl = workspace_layout(c, n_spinor, n_pw, n_bands, n_fold);
   CU(fl.coeffs.reserve(coeff_bytes));
   CU(fl.gfrac.reserve(sizeof(int32_t) * 3 * (size_t)n_pw));
@@ -1229,6 +1243,7 @@ int submit_impl(int handle, int ikpt, int n_spinor, int n_pw, int n_bands, int l
   fl.resident = true;
   fl.rho_ready = false;
   fl.layout = layout;
+  fl.dp = c->dp_coeffs;
   fl.stride_bytes = band_stride_bytes;
   for (auto& other : c->flights)  // an older resident copy of the same ikpt is superseded
     if (&other != &fl && !other.busy && other.ikpt == ikpt) other.resident = false;
@@ -1365,8 +1380,17 @@ int bandup_gpu_set_option(int handle, int option, int value) {
       c->k2_variant = value;
       return BANDUP_GPU_OK;
     case BANDUP_GPU_OPT_DEPENDENT_LAUNCH:
-      c->use_pdl = value != 0;
+      if (value < 0 || value > 3) return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "dependent launch: bit 0 = K1->K2, bit 1 = K2->K3");
+      c->use_pdl = value;
       return BANDUP_GPU_OK;
+    case BANDUP_GPU_OPT_COMPLEX128: {
+      for (auto& f : c->flights) {  // resident k-points were uploaded with the other element size
+        f.resident = false;
+        f.rho_ready = false;
+      }
+      c->dp_coeffs = value != 0;
+      return BANDUP_GPU_OK;
+    }
     default:
       return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "unknown option " + std::to_string(option));
   }

@@ -108,7 +108,7 @@ int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t* n_energie
       launch_rho_gather(fl->coeffs.p, fl->stride_bytes, fl->n_pw, fl->n_spinor, nb, fl->layout, nu,
                         static_cast<const int32_t*>(fl->selected.p),
                         static_cast<const long long*>(fl->sel_off.p),
-                        static_cast<const double*>(fl->norms.p), fl->csel.p, s);
+                        static_cast<const double*>(fl->norms.p), fl->csel.p, fl->dp, s);
     }
     {
       KernelScope k(c, BANDUP_GPU_K_RHO, s);
@@ -234,7 +234,7 @@ int bandup_gpu_pauli_vectors(int handle, int ikpt, double* sigma) {
     launch_pauli(fl->coeffs.p, fl->stride_bytes, fl->n_pw, fl->layout, static_cast<const double*>(fl->norms.p),
                  static_cast<const RhoPair*>(fl->pairs.p), n_pairs, cells,
                  static_cast<const long long*>(fl->pair_off.p), static_cast<double*>(contrib.p),
-                 static_cast<double*>(fl->trace_out.p), s);
+                 static_cast<double*>(fl->trace_out.p), fl->dp, s);
   }
   std::vector<double> h(3 * (size_t)cells);
   e = cudaGetLastError();

@@ -87,6 +87,7 @@ struct Flight {  // one SC k-point in flight
   int ikpt = -1;
   int n_spinor = 0, n_pw = 0, n_bands = 0, n_fold = 0, n_unique = 0, layout = 0;
   long long stride_bytes = 0;
+  bool dp = false;  // uploaded as complex128
   std::vector<int> unique_of;  // pc-kpt (user fold) -> distinct coset
   DevBuf coeffs, gfrac, energies, weights, dN, nsel, norms, slot, selected, workspace;
   PinBuf h_weights, h_dN, h_nsel, h_norms;
@@ -115,7 +116,8 @@ struct Ctx {
   DescSlot desc_ring[kDescRing];
   int desc_next = 0, desc_last = -1;
   StagePool* stage_pool = nullptr;
-  bool use_pdl = true;  // K1 -> K2 -> K3 chained with programmatic dependent launch
+  bool dp_coeffs = false;  // kind_cplx_coeffs = dp: every coefficient block is complex128
+  int use_pdl = 3;  // programmatic dependent launch: bit 0 = K2 behind K1, bit 1 = K3 behind K2
   int k2_variant = 0;  // 0 auto, 1 shared-memory bins, 2 register accumulators (when <= 4 cosets)
   std::vector<double> grid;
   DevBuf d_grid;

@@ -31,8 +31,10 @@ constexpr int kK1MaxBlocks = 128;  // CTAs of K1 per SC-kpt (each leaves one row
 struct KptGeom {
   const char* coeffs;         // first band record
   long long stride_bytes;     // distance between band records
-  long long row_elems;        // n_pw * n_spinor complex64 per band
+  long long row_elems;        // n_pw * n_spinor coefficients per band
   int n_bands, n_pw, n_spinor, layout;
+  int dp;                     // 1: complex128 coefficients (16 bytes per element)
+  int nreg;                   // K2 accumulators of this k-point: 0 = shared-memory bins, 1/2/4 = registers
   const int32_t* g_frac;      // [n_pw][3]
   const double* energies;     // [n_bands]
   uint8_t* slot;              // [n_pw], 2-byte aligned: fold id of every plane wave, kNoFold = none
@@ -100,12 +102,13 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 }
 
 int weights_num_chunks(long long row_elems, int chunk_vecs);
-// K2 accumulator layout: 0 = shared-memory bins, 1/2/4 = that many register accumulators
-// (variant: 0 auto, 1 force bins, 2 registers whenever max_n_fold <= 4)
-int weights_pick_nreg(int variant, int max_n_fold);
+// K2 accumulator layout of a k-point: 0 = shared-memory bins, 1/2/4 = that many register
+// accumulators (variant: 0 automatic by n_fold / |det M|, 1 bins always, 2 registers whenever n_fold <= 4)
+int weights_pick_nreg(int variant, int n_fold, long long det_m);
 int weights_partials_sub(int nreg);
 size_t weights_partials_bytes(int n_bands, int n_chunks, int n_fold);
-// requested > 0: rounded up to whole stages; 0: chosen from the block shape
+// requested > 0: rounded up to whole stages; 0: chosen from the block shape.  row_elems here and
+// in weights_num_chunks counts 8-byte units (complex64 elements; a complex128 element counts twice)
 int weights_pick_chunk_vecs(int requested, long long row_elems, int n_bands, int sm_count, int n_spinor);
 int weights_max_folds_supported();
 
@@ -113,8 +116,9 @@ int weights_max_folds_supported();
 // the batch; per (band, chunk) tile the band-norm part and the per-fold masked |C|^2 sums.
 // Fuses io_routines_mod.f90:1317-1330 (norm) with band_unfolding_routines_mod.f90:638-644 and
 // :1337-1345 (weights, spinor sum).  All k-points of a batch share n_spinor and layout.
-void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int max_n_fold,
-                           int n_spinor, int layout, int nreg, int ctas_per_sm, int n_stages, int sm_count,
+// bins_rows: 1 + the largest n_fold among the k-points with nreg == 0 (0 when there is none)
+void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int bins_rows,
+                           int n_spinor, int layout, bool dp, int ctas_per_sm, int n_stages, int sm_count,
                            bool pdl, cudaStream_t s);
 
 // K3 -- first the deterministic tile combine of K2's partials (s = sum_c norm part,
@@ -160,7 +164,7 @@ void launch_rho_plan(const double* d_grid, int nener, double sigma, const double
 void launch_scan(const int* d_in, int n, long long* d_out, cudaStream_t s);
 void launch_rho_gather(const void* d_coeffs, long long stride_bytes, int n_pw, int n_spinor,
                        int n_bands, int layout, int n_fold, const int32_t* d_lists,
-                       const long long* d_sel_off, const double* d_norms, void* d_csel,
+                       const long long* d_sel_off, const double* d_norms, void* d_csel, bool dp,
                        cudaStream_t s);
 void launch_rho_pairs(const double* d_grid, int nener, double sigma, const double* d_band_energies,
                       int n_bands, int n_fold, const double* d_dN, int cap, int n_spinor,
@@ -172,7 +176,7 @@ void launch_orb_contrib(int n_bands, int n_ao, const void* d_dual, const void* d
 // K6: expectation values of the Pauli matrices, Re Tr(rho . sigma_i), spinor wavefunctions only
 void launch_pauli(const void* d_coeffs, long long stride_bytes, int n_pw, int layout, const double* d_norms,
                   const RhoPair* d_pairs, long long n_pairs, int n_cells, const long long* d_pair_off,
-                  double* d_contrib, double* d_sigma, cudaStream_t s);
+                  double* d_contrib, double* d_sigma, bool dp, cudaStream_t s);
 void launch_trace(int n_cells, int n_bands, const double* d_dN, const long long* d_pair_off,
                   const RhoPair* d_pairs, const void* d_O, double min_abs_rho, int clip, double* d_out,
                   cudaStream_t s);

@@ -165,7 +165,7 @@ __device__ __forceinline__ long long elem_of(int pw, int is, int n_pw) {
 }
 
 // csel layout per fold u: [band][spinor][j], j < n_sel(u); folds concatenated by sel_off
-template <int MODE>
+template <int MODE, typename T>  // T = float2 (complex64) or double2 (complex128 build, rounded here)
 __global__ void __launch_bounds__(256)
 k4_gather(const char* __restrict__ coeffs, long long stride_bytes, int n_pw, int n_spinor,
           int n_bands, const int32_t* __restrict__ lists, const long long* __restrict__ sel_off,
@@ -173,7 +173,7 @@ k4_gather(const char* __restrict__ coeffs, long long stride_bytes, int n_pw, int
   const int band = blockIdx.x, u = blockIdx.y;
   const long long off = sel_off[u];
   const int n_sel = (int)(sel_off[u + 1] - off);
-  const float2* row = reinterpret_cast<const float2*>(coeffs + (long long)band * stride_bytes);
+  const T* row = reinterpret_cast<const T*>(coeffs + (long long)band * stride_bytes);
   const double s = norms[band];
   // inner_prod > epsilon: coeffs = (1/sqrt(|inner_prod|)) * coeffs, rounded back to complex(sp)
   const double fac = s > kEps ? 1.0 / sqrt(fabs(s)) : 1.0;
@@ -181,13 +181,14 @@ k4_gather(const char* __restrict__ coeffs, long long stride_bytes, int n_pw, int
   for (int t = threadIdx.x; t < n_sel * n_spinor; t += blockDim.x) {
     const int is = t / n_sel, j = t - is * n_sel;
     const int pw = lists[off + j] - 1;  // lists are 1-based like selected_coeff_indices
-    const float2 c = row[elem_of<MODE>(pw, is, n_pw)];
+    const T c = row[elem_of<MODE>(pw, is, n_pw)];
     float2 r;
     if (s > kEps) {
       r.x = (float)(fac * (double)c.x);
       r.y = (float)(fac * (double)c.y);
     } else {
-      r = c;
+      r.x = (float)c.x;
+      r.y = (float)c.y;
     }
     dst[t] = r;
   }
@@ -336,7 +337,7 @@ k5_trace(int n_cells, int n_bands, const double* __restrict__ dN_all,
 //   sigma_z = <m2 a|m1 a> - <m2 b|m1 b>,   <u|v> = sum_G conj(u) v  (renormalised coefficients)
 //   upper element rho(m1,m2), m1 < m2:  rho12 sigma(m2,m1) + conj(rho12) conj(sigma(m2,m1))
 // Only stored elements (|rho| >= 1e-5) enter, as in the reference's rhos(:).  One CTA per pair.
-template <int MODE>  // 1: [pw][spinor] interleaved, 2: [spinor][pw] blocked
+template <int MODE, typename T>  // 1: [pw][spinor] interleaved, 2: [spinor][pw] blocked; T = float2 | double2
 __global__ void __launch_bounds__(256)
 k6_pauli_pairs(const char* __restrict__ coeffs, long long stride_bytes, int n_pw,
                const double* __restrict__ norms, const RhoPair* __restrict__ pairs,
@@ -348,12 +349,12 @@ k6_pauli_pairs(const char* __restrict__ coeffs, long long stride_bytes, int n_pw
     if (threadIdx.x < 3) out[threadIdx.x] = 0.0;
     return;
   }
-  const float2* r1 = reinterpret_cast<const float2*>(coeffs + (long long)pr.m1 * stride_bytes);
-  const float2* r2 = reinterpret_cast<const float2*>(coeffs + (long long)pr.m2 * stride_bytes);
+  const T* r1 = reinterpret_cast<const T*>(coeffs + (long long)pr.m1 * stride_bytes);
+  const T* r2 = reinterpret_cast<const T*>(coeffs + (long long)pr.m2 * stride_bytes);
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ab, ba, aa, bb (re, im each)
   for (int pw = threadIdx.x; pw < n_pw; pw += blockDim.x) {
     const long long ia = (MODE == 1) ? 2LL * pw : pw, ib = (MODE == 1) ? 2LL * pw + 1 : (long long)n_pw + pw;
-    const float2 xa = r2[ia], xb = r2[ib], ya = r1[ia], yb = r1[ib];  // x: band m2 (bra), y: band m1 (ket)
+    const T xa = r2[ia], xb = r2[ib], ya = r1[ia], yb = r1[ib];  // x: band m2 (bra), y: band m1 (ket)
     const double xar = xa.x, xai = xa.y, xbr = xb.x, xbi = xb.y, yar = ya.x, yai = ya.y, ybr = yb.x, ybi = yb.y;
     acc[0] += xar * ybr + xai * ybi;  acc[1] += xar * ybi - xai * ybr;   // conj(x_a) y_b
     acc[2] += xbr * yar + xbi * yai;  acc[3] += xbr * yai - xbi * yar;   // conj(x_b) y_a
@@ -435,18 +436,20 @@ void launch_scan(const int* d_in, int n, long long* d_out, cudaStream_t s) {
 
 void launch_rho_gather(const void* d_coeffs, long long stride_bytes, int n_pw, int n_spinor,
                        int n_bands, int layout, int n_fold, const int32_t* d_lists,
-                       const long long* d_sel_off, const double* d_norms, void* d_csel,
+                       const long long* d_sel_off, const double* d_norms, void* d_csel, bool dp,
                        cudaStream_t s) {
   if (n_bands <= 0 || n_fold <= 0) return;
   dim3 g((unsigned)n_bands, (unsigned)n_fold);
   const char* c = static_cast<const char*>(d_coeffs);
   float2* o = static_cast<float2*>(d_csel);
-  if (n_spinor == 1)
-    k4_gather<0><<<g, 256, 0, s>>>(c, stride_bytes, n_pw, n_spinor, n_bands, d_lists, d_sel_off, d_norms, o);
-  else if (layout == BANDUP_GPU_LAYOUT_FORTRAN_INMEM)
-    k4_gather<1><<<g, 256, 0, s>>>(c, stride_bytes, n_pw, n_spinor, n_bands, d_lists, d_sel_off, d_norms, o);
-  else
-    k4_gather<2><<<g, 256, 0, s>>>(c, stride_bytes, n_pw, n_spinor, n_bands, d_lists, d_sel_off, d_norms, o);
+  const int mode = n_spinor == 1 ? 0 : layout == BANDUP_GPU_LAYOUT_FORTRAN_INMEM ? 1 : 2;
+#define BANDUP_GATHER(M, T) k4_gather<M, T><<<g, 256, 0, s>>>(c, stride_bytes, n_pw, n_spinor, n_bands, d_lists, d_sel_off, d_norms, o)
+  if (dp) {
+    if (mode == 0) BANDUP_GATHER(0, double2); else if (mode == 1) BANDUP_GATHER(1, double2); else BANDUP_GATHER(2, double2);
+  } else {
+    if (mode == 0) BANDUP_GATHER(0, float2); else if (mode == 1) BANDUP_GATHER(1, float2); else BANDUP_GATHER(2, float2);
+  }
+#undef BANDUP_GATHER
 }
 
 void launch_rho_pairs(const double* d_grid, int nener, double sigma, const double* d_band_energies,
@@ -473,14 +476,19 @@ void launch_orb_contrib(int n_bands, int n_ao, const void* d_dual, const void* d
 
 void launch_pauli(const void* d_coeffs, long long stride_bytes, int n_pw, int layout, const double* d_norms,
                   const RhoPair* d_pairs, long long n_pairs, int n_cells, const long long* d_pair_off,
-                  double* d_contrib, double* d_sigma, cudaStream_t s) {
+                  double* d_contrib, double* d_sigma, bool dp, cudaStream_t s) {
   if (n_cells <= 0) return;
   const char* c = static_cast<const char*>(d_coeffs);
   if (n_pairs > 0) {
-    if (layout == BANDUP_GPU_LAYOUT_FORTRAN_INMEM)
-      k6_pauli_pairs<1><<<(unsigned)n_pairs, 256, 0, s>>>(c, stride_bytes, n_pw, d_norms, d_pairs, d_contrib);
+    const bool inter = layout == BANDUP_GPU_LAYOUT_FORTRAN_INMEM;
+    if (dp && inter)
+      k6_pauli_pairs<1, double2><<<(unsigned)n_pairs, 256, 0, s>>>(c, stride_bytes, n_pw, d_norms, d_pairs, d_contrib);
+    else if (dp)
+      k6_pauli_pairs<2, double2><<<(unsigned)n_pairs, 256, 0, s>>>(c, stride_bytes, n_pw, d_norms, d_pairs, d_contrib);
+    else if (inter)
+      k6_pauli_pairs<1, float2><<<(unsigned)n_pairs, 256, 0, s>>>(c, stride_bytes, n_pw, d_norms, d_pairs, d_contrib);
     else
-      k6_pauli_pairs<2><<<(unsigned)n_pairs, 256, 0, s>>>(c, stride_bytes, n_pw, d_norms, d_pairs, d_contrib);
+      k6_pauli_pairs<2, float2><<<(unsigned)n_pairs, 256, 0, s>>>(c, stride_bytes, n_pw, d_norms, d_pairs, d_contrib);
   }
   k6_pauli_cells<<<(n_cells + 127) / 128, 128, 0, s>>>(n_cells, d_pair_off, d_contrib, d_sigma);
 }

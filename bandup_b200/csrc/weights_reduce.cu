@@ -134,8 +134,9 @@ __device__ __forceinline__ TileGeom tile_geom(const KptGeom* __restrict__ geoms,
   t.chunk = (int)(local / g->n_bands);
   t.band = (int)(local - (long long)t.chunk * g->n_bands);
   t.row = g->coeffs + (long long)t.band * g->stride_bytes;
-  t.e_al = (int)((reinterpret_cast<unsigned long long>(t.row) >> 3) & 1ull);
-  t.nvb = (g->row_elems - t.e_al) >> 1;
+  // complex128 rows: one element per 16-byte vector, always aligned (the API insists on it)
+  t.e_al = g->dp ? 0 : (int)((reinterpret_cast<unsigned long long>(t.row) >> 3) & 1ull);
+  t.nvb = g->dp ? g->row_elems : (g->row_elems - t.e_al) >> 1;
   t.j0 = (long long)t.chunk * g->chunk_vecs;
   t.j1 = t.j0 + g->chunk_vecs;
   if (t.j1 > t.nvb) t.j1 = t.nvb;
@@ -293,6 +294,43 @@ __device__ __forceinline__ void consume_stage_reg(const float4* __restrict__ sv,
   for (int f = 0; f < NREG; ++f) acc[f] += (double)r[f];
 }
 
+// The same stage for complex128 coefficients (a `kind_cplx_coeffs = dp` build of the reference,
+// constants_and_types_mod.f90:60): one element per 16-byte vector, |C|^2 and every sum in fp64.
+// NREG > 0: register accumulators; NREG == 0: the per-thread shared-memory bins.
+template <int MODE, int NREG, bool FULL>
+__device__ __forceinline__ void consume_stage_dp(const float4* __restrict__ sv, uint64_t* full, uint64_t* empty,
+                                                 uint32_t phase, const SlotSrc& ss, int j, int nv, int tid,
+                                                 int lane, unsigned nf, double* __restrict__ bins,
+                                                 double (&acc)[NREG > 0 ? NREG : 1], double& nrm) {
+  unsigned sl[kVecPerThread];
+  double2 v[kVecPerThread];
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    const int i = tid + u * kConsumers;
+    sl[u] = (FULL || i < nv) ? (unsigned)__ldg(ss.slot + pw_of<MODE>(j + i, ss.n_pw)) : 0xFFu;
+  }
+  mbar_wait(full, phase);
+  const double2* __restrict__ dv = reinterpret_cast<const double2*>(sv);
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    const int i = tid + u * kConsumers;
+    v[u] = (FULL || i < nv) ? dv[i] : make_double2(0.0, 0.0);
+  }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty);
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    const double p = fma(v[u].y, v[u].y, v[u].x * v[u].x);
+    nrm += p;
+    if (NREG > 0) {
+#pragma unroll
+      for (int f = 0; f < NREG; ++f) acc[f] += (sl[u] == (unsigned)f) ? p : 0.0;
+    } else if (sl[u] < nf) {
+      bins[sl[u] * kConsumers + tid] += p;
+    }
+  }
+}
+
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
@@ -306,16 +344,156 @@ __device__ __forceinline__ float lone_element(const float2* el, long long e) {
   return fmaf(c.y, c.y, c.x * c.x);
 }
 
-template <int MODE, int NREG>
-__global__ void __launch_bounds__(kThreads, NREG ? 2 : 3)
-k2_weights_reduce(const KptGeom* __restrict__ geoms, int n_kpts, long long total_tiles, int max_n_fold,
+struct Ring {  // a consumer's view of the CTA's stage ring
+  float4* stage_base;
+  uint64_t* full_bar;
+  uint64_t* empty_bar;
+  int n_stages;
+  int s;
+  uint32_t phase;
+  __device__ __forceinline__ void advance() {
+    if (++s == n_stages) {
+      s = 0;
+      phase ^= 1u;
+    }
+  }
+  __device__ __forceinline__ const float4* stage() const { return stage_base + (size_t)s * kStageVecs; }
+};
+
+struct LoneElems {  // the row head / tail elements of a tile (thread 0 only), complex64 rows only
+  float p[2];
+  unsigned q[2];
+};
+
+// One tile with register accumulators (at most NREG distinct cosets) and a warp-local epilogue:
+// one partial per warp and slot, partials[band][chunk][warp][slot] -- the eight consumer warps never
+// meet at a CTA barrier.
+template <int MODE, int NREG, bool DP>
+__device__ __forceinline__ void tile_registers(const TileGeom& t, const SlotSrc& ss, Ring& r, const LoneElems& lone,
+                                               double nrm, int tid, int lane, int warp) {
+  const KptGeom& g = *t.g;
+  const int n_fold = g.n_fold, nslots = n_fold + 1;
+  const int j0 = (int)t.j0, j1 = (int)t.j1;  // vectors per row < 2^31
+  double racc[NREG];
+#pragma unroll
+  for (int f = 0; f < NREG; ++f)
+    racc[f] = (lone.q[0] == (unsigned)f ? (double)lone.p[0] : 0.0) + (lone.q[1] == (unsigned)f ? (double)lone.p[1] : 0.0);
+  int j = j0;
+  if constexpr (DP) {
+    for (; j + kStageVecs <= j1; j += kStageVecs) {
+      consume_stage_dp<MODE, NREG, true>(r.stage(), r.full_bar + r.s, r.empty_bar + r.s, r.phase, ss, j, kStageVecs, tid,
+                                         lane, 0u, nullptr, racc, nrm);
+      r.advance();
+    }
+    if (j < j1) {
+      consume_stage_dp<MODE, NREG, false>(r.stage(), r.full_bar + r.s, r.empty_bar + r.s, r.phase, ss, j, j1 - j, tid,
+                                          lane, 0u, nullptr, racc, nrm);
+      r.advance();
+    }
+  } else if (MODE == 1 && t.e_al == 0) {  // spinor rows [pw][spinor] on a 16-byte boundary
+    for (; j + kStageVecs <= j1; j += kStageVecs) {
+      consume_stage_reg<MODE, NREG, true, true>(r.stage(), r.full_bar + r.s, r.empty_bar + r.s, r.phase, ss, j,
+                                                kStageVecs, tid, lane, racc, nrm);
+      r.advance();
+    }
+    if (j < j1) {
+      consume_stage_reg<MODE, NREG, false, true>(r.stage(), r.full_bar + r.s, r.empty_bar + r.s, r.phase, ss, j, j1 - j,
+                                                 tid, lane, racc, nrm);
+      r.advance();
+    }
+  } else {
+    for (; j + kStageVecs <= j1; j += kStageVecs) {
+      consume_stage_reg<MODE, NREG, true, false>(r.stage(), r.full_bar + r.s, r.empty_bar + r.s, r.phase, ss, j,
+                                                 kStageVecs, tid, lane, racc, nrm);
+      r.advance();
+    }
+    if (j < j1) {
+      consume_stage_reg<MODE, NREG, false, false>(r.stage(), r.full_bar + r.s, r.empty_bar + r.s, r.phase, ss, j, j1 - j,
+                                                  tid, lane, racc, nrm);
+      r.advance();
+    }
+  }
+  // fixed shuffle tree => bit-reproducible; K3 adds the warps' partials up in warp order
+  double* out = g.partials + (((long long)t.band * g.n_chunks + t.chunk) * (kConsumers / 32) + warp) * nslots;
+  const double v0 = warp_sum(nrm);
+  if (lane == 0) out[0] = v0;
+#pragma unroll
+  for (int f = 0; f < NREG; ++f) {
+    if (f < n_fold) {  // warp-uniform
+      const double vf = warp_sum(racc[f]);
+      if (lane == 0) out[f + 1] = vf;
+    }
+  }
+}
+
+// One tile with the per-thread shared-memory bins (up to kMaxFolds distinct cosets) and the
+// CTA-level epilogue: partials[band][chunk][slot].
+template <int MODE, bool DP>
+__device__ __forceinline__ void tile_bins(const TileGeom& t, const SlotSrc& ss, Ring& r, const LoneElems& lone,
+                                          double nrm, double* __restrict__ acc, int tid, int lane, int warp) {
+  const KptGeom& g = *t.g;
+  const int n_fold = g.n_fold, nslots = n_fold + 1;
+  const unsigned nf = (unsigned)n_fold;
+  const int j0 = (int)t.j0, j1 = (int)t.j1;
+  double* bins = acc + kConsumers;
+  for (int f = 0; f < n_fold; ++f) bins[f * kConsumers + tid] = 0.0;
+  if (!DP && tid == 0) {
+    if (lone.q[0] < nf) bins[lone.q[0] * kConsumers] += (double)lone.p[0];
+    if (lone.q[1] < nf) bins[lone.q[1] * kConsumers] += (double)lone.p[1];
+  }
+  int j = j0;
+  if constexpr (DP) {
+    double unused[1] = {0.0};
+    for (; j + kStageVecs <= j1; j += kStageVecs) {
+      consume_stage_dp<MODE, 0, true>(r.stage(), r.full_bar + r.s, r.empty_bar + r.s, r.phase, ss, j, kStageVecs, tid,
+                                      lane, nf, bins, unused, nrm);
+      r.advance();
+    }
+    if (j < j1) {
+      consume_stage_dp<MODE, 0, false>(r.stage(), r.full_bar + r.s, r.empty_bar + r.s, r.phase, ss, j, j1 - j, tid, lane,
+                                       nf, bins, unused, nrm);
+      r.advance();
+    }
+  } else {
+    for (; j + kStageVecs <= j1; j += kStageVecs) {
+      consume_stage<MODE, true>(r.stage(), r.full_bar + r.s, r.empty_bar + r.s, r.phase, ss, j, kStageVecs, tid, lane,
+                                nf, bins, nrm);
+      r.advance();
+    }
+    if (j < j1) {  // last, partial stage of a row
+      consume_stage<MODE, false>(r.stage(), r.full_bar + r.s, r.empty_bar + r.s, r.phase, ss, j, j1 - j, tid, lane, nf,
+                                 bins, nrm);
+      r.advance();
+    }
+  }
+  // tile reduction through shared memory: thread partials are already there for the folds;
+  // warp q adds up row q (256 values: 8 per lane, conflict-free, then a shuffle tree).
+  // Fixed order => bit-reproducible.
+  acc[tid] = nrm;
+  consumer_sync();
+  double* out = g.partials + ((long long)t.band * g.n_chunks + t.chunk) * nslots;
+  for (int q = warp; q < nslots; q += kConsumers / 32) {
+    const double* row = acc + q * kConsumers + lane;
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < kConsumers / 32; ++i) a += row[32 * i];
+    a = warp_sum(a);
+    if (lane == 0) out[q] = a;
+  }
+  consumer_sync();
+}
+
+// bins_rows: rows of the shared-memory accumulator block = 1 + the largest n_fold among the
+// k-points that use the bins (0 when every k-point of the batch uses registers).
+template <int MODE, bool DP>
+__global__ void __launch_bounds__(kThreads, 2)
+k2_weights_reduce(const KptGeom* __restrict__ geoms, int n_kpts, long long total_tiles, int bins_rows,
                   int n_stages) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [n_stages][16 KB] | NREG == 0: acc [max_n_fold+1][256] f64 (row 0: norm, row f+1: fold f) | barriers
+  // layout: [n_stages][16 KB] | acc [bins_rows][256] f64 (row 0: norm, row f+1: fold f) | barriers
   float4* stage_base = reinterpret_cast<float4*>(smem_raw);
   double* acc = reinterpret_cast<double*>(smem_raw + (size_t)n_stages * kStageBytes);
-  double* bins = acc + kConsumers;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(acc + (NREG ? 0 : (size_t)(max_n_fold + 1) * kConsumers));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(acc + (size_t)bins_rows * kConsumers);
   uint64_t* empty_bar = full_bar + kMaxStages;
 
   const int tid = threadIdx.x;
@@ -327,7 +505,7 @@ k2_weights_reduce(const KptGeom* __restrict__ geoms, int n_kpts, long long total
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  pdl_launch_dependents();  // K3 may take its place on the SMs; it waits for this grid to finish
+  pdl_launch_dependents();  // K3 may be scheduled behind this grid; it waits for it to finish
 
   if (tid >= kConsumers) {
     // ------------------------------ producer ------------------------------
@@ -358,135 +536,68 @@ k2_weights_reduce(const KptGeom* __restrict__ geoms, int n_kpts, long long total
   // -------------------------------- consumers --------------------------------
   pdl_wait_primary();  // K1's slot tables
   const int lane = tid & 31, warp = tid >> 5;
-  int s = 0, k = 0;
-  uint32_t phase = 0;
+  Ring ring{stage_base, full_bar, empty_bar, n_stages, 0, 0u};
+  int k = 0;
   for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const TileGeom t = tile_geom(geoms, n_kpts, k, tile);
     const KptGeom& g = *t.g;
-    const int n_fold = g.n_fold;
-    const unsigned nf = (unsigned)n_fold;
     const SlotSrc ss = make_slot_src<MODE>(g, t.e_al);
-    const int j0 = (int)t.j0, j1 = (int)t.j1;  // vectors per row < 2^31
     double nrm = 0.0;
     // the row head / tail elements that do not fill an aligned vector fall to thread 0
-    float lone_p[2] = {0.f, 0.f};
-    unsigned lone_q[2] = {kNoFold, kNoFold};
-    if (tid == 0) {
+    LoneElems lone{{0.f, 0.f}, {kNoFold, kNoFold}};
+    if (!DP && tid == 0) {
       const float2* el = reinterpret_cast<const float2*>(t.row);
       const long long row_elems = g.row_elems, e_tail = t.e_al + 2 * t.nvb;
       if (t.chunk == 0 && t.e_al == 1 && row_elems > 0) {
-        lone_p[0] = lone_element(el, 0);
-        lone_q[0] = ss.slot[pw_of<MODE>(0, ss.n_pw)];
+        lone.p[0] = lone_element(el, 0);
+        lone.q[0] = ss.slot[pw_of<MODE>(0, ss.n_pw)];
       }
       if (t.chunk == g.n_chunks - 1 && e_tail < row_elems) {
-        lone_p[1] = lone_element(el, e_tail);
-        lone_q[1] = ss.slot[pw_of<MODE>(e_tail, ss.n_pw)];
+        lone.p[1] = lone_element(el, e_tail);
+        lone.q[1] = ss.slot[pw_of<MODE>(e_tail, ss.n_pw)];
       }
-      nrm = (double)lone_p[0] + (double)lone_p[1];
+      nrm = (double)lone.p[0] + (double)lone.p[1];
     }
-    const int nslots = n_fold + 1;
-
-    if constexpr (NREG > 0) {
-      // ---- register accumulators, warp-local epilogue --------------------------------
-      double racc[NREG];
-#pragma unroll
-      for (int f = 0; f < NREG; ++f)
-        racc[f] = (lone_q[0] == (unsigned)f ? (double)lone_p[0] : 0.0) + (lone_q[1] == (unsigned)f ? (double)lone_p[1] : 0.0);
-      const bool paired = MODE == 1 && t.e_al == 0;
-      int j = j0;
-      if (paired) {
-        for (; j + kStageVecs <= j1; j += kStageVecs) {
-          consume_stage_reg<MODE, NREG, true, true>(stage_base + (size_t)s * kStageVecs, full_bar + s,
-                                                                empty_bar + s, phase, ss, j, kStageVecs, tid, lane, racc, nrm);
-          if (++s == n_stages) { s = 0; phase ^= 1u; }
-        }
-        if (j < j1) {
-          consume_stage_reg<MODE, NREG, false, true>(stage_base + (size_t)s * kStageVecs, full_bar + s,
-                                                                 empty_bar + s, phase, ss, j, j1 - j, tid, lane, racc, nrm);
-          if (++s == n_stages) { s = 0; phase ^= 1u; }
-        }
-      } else {
-        for (; j + kStageVecs <= j1; j += kStageVecs) {
-          consume_stage_reg<MODE, NREG, true, false>(stage_base + (size_t)s * kStageVecs, full_bar + s,
-                                                                 empty_bar + s, phase, ss, j, kStageVecs, tid, lane, racc, nrm);
-          if (++s == n_stages) { s = 0; phase ^= 1u; }
-        }
-        if (j < j1) {
-          consume_stage_reg<MODE, NREG, false, false>(stage_base + (size_t)s * kStageVecs, full_bar + s,
-                                                                  empty_bar + s, phase, ss, j, j1 - j, tid, lane, racc, nrm);
-          if (++s == n_stages) { s = 0; phase ^= 1u; }
-        }
-      }
-      // one partial per warp and slot, fixed shuffle tree => bit-reproducible; K3 adds them up
-      double* out = g.partials + (((long long)t.band * g.n_chunks + t.chunk) * (kConsumers / 32) + warp) * nslots;
-      const double v0 = warp_sum(nrm);
-      if (lane == 0) out[0] = v0;
-#pragma unroll
-      for (int f = 0; f < NREG; ++f) {
-        if (f < n_fold) {  // warp-uniform
-          const double vf = warp_sum(racc[f]);
-          if (lane == 0) out[f + 1] = vf;
-        }
-      }
-    } else {
-      // ---- shared-memory bins, CTA-level epilogue ------------------------------------
-      for (int f = 0; f < n_fold; ++f) bins[f * kConsumers + tid] = 0.0;
-      if (tid == 0) {
-        if (lone_q[0] < nf) bins[lone_q[0] * kConsumers] += (double)lone_p[0];
-        if (lone_q[1] < nf) bins[lone_q[1] * kConsumers] += (double)lone_p[1];
-      }
-      int j = j0;
-      for (; j + kStageVecs <= j1; j += kStageVecs) {
-        consume_stage<MODE, true>(stage_base + (size_t)s * kStageVecs, full_bar + s, empty_bar + s, phase, ss, j,
-                                  kStageVecs, tid, lane, nf, bins, nrm);
-        if (++s == n_stages) { s = 0; phase ^= 1u; }
-      }
-      if (j < j1) {  // last, partial stage of a row
-        consume_stage<MODE, false>(stage_base + (size_t)s * kStageVecs, full_bar + s, empty_bar + s, phase, ss, j,
-                                   j1 - j, tid, lane, nf, bins, nrm);
-        if (++s == n_stages) { s = 0; phase ^= 1u; }
-      }
-      // tile reduction through shared memory: thread partials are already there for the folds;
-      // warp q adds up row q (256 values: 8 per lane, conflict-free, then a shuffle tree).
-      // Fixed order => bit-reproducible.
-      acc[tid] = nrm;
-      consumer_sync();
-      double* out = g.partials + ((long long)t.band * g.n_chunks + t.chunk) * nslots;
-      for (int q = warp; q < nslots; q += kConsumers / 32) {
-        const double* r = acc + q * kConsumers + lane;
-        double a = 0.0;
-#pragma unroll
-        for (int i = 0; i < kConsumers / 32; ++i) a += r[32 * i];
-        a = warp_sum(a);
-        if (lane == 0) out[q] = a;
-      }
-      consumer_sync();
+    // the accumulator layout is a property of the k-point (host: weights_pick_nreg)
+    switch (g.nreg) {
+      case 1: tile_registers<MODE, 1, DP>(t, ss, ring, lone, nrm, tid, lane, warp); break;
+      case 2: tile_registers<MODE, 2, DP>(t, ss, ring, lone, nrm, tid, lane, warp); break;
+      case 4: tile_registers<MODE, 4, DP>(t, ss, ring, lone, nrm, tid, lane, warp); break;
+      default: tile_bins<MODE, DP>(t, ss, ring, lone, nrm, acc, tid, lane, warp); break;
     }
   }
 }
 
 constexpr size_t kSmemBudget = 227 * 1024;
 
-size_t k2_fixed_smem(int n_fold, bool reg) {  // everything but the stage ring
-  return (reg ? 0 : sizeof(double) * (size_t)(n_fold + 1) * kConsumers) + sizeof(uint64_t) * 2 * kMaxStages + 128;
+size_t k2_fixed_smem(int bins_rows) {  // everything but the stage ring
+  return sizeof(double) * (size_t)bins_rows * kConsumers + sizeof(uint64_t) * 2 * kMaxStages + 128;
 }
 
-template <int MODE, int NREG>
-void launch_mode(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int max_n_fold,
+template <int MODE, bool DP>
+void launch_mode(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int bins_rows,
                  int ctas_per_sm, int n_stages, int sm_count, bool pdl, cudaStream_t s) {
-  const size_t fixed = k2_fixed_smem(max_n_fold, NREG > 0);
+  const size_t fixed = k2_fixed_smem(bins_rows);
   // default: 2 CTAs per SM with 3 stages each (96 KB of loads in flight per SM, about twice
   // what latency x bandwidth asks for; the B200 sweep in profiles/ has 2x3 ahead of 3x4 and of
   // deeper rings by 2-4 %); many folds eat shared memory for the bins, so the ring shrinks
   // before occupancy does
   if (ctas_per_sm <= 0) ctas_per_sm = 2;
+  if (ctas_per_sm > 2) ctas_per_sm = 2;  // the kernel is compiled for two resident CTAs per SM
   if (n_stages <= 0) n_stages = 3;
   if (n_stages > kMaxStages) n_stages = kMaxStages;
   while (ctas_per_sm > 1 && (fixed + 2 * (size_t)kStageBytes + 1024) * ctas_per_sm > kSmemBudget) --ctas_per_sm;
   const size_t per_cta = kSmemBudget / ctas_per_sm - 1024;  // 1 KB per CTA is reserved by the driver
   while (n_stages > 2 && fixed + (size_t)n_stages * kStageBytes > per_cta) --n_stages;
-  const size_t smem = fixed + (size_t)n_stages * kStageBytes;
-  auto kernel = k2_weights_reduce<MODE, NREG>;
+  size_t smem = fixed + (size_t)n_stages * kStageBytes;
+  // The persistent grid hands every CTA the same share of the tiles, so the CTAs must be spread
+  // evenly: ctas_per_sm on every SM, never three here and one there.  When the kernel is launched
+  // behind K1 with programmatic dependent launch, K1's last CTAs still occupy some SMs and the
+  // block scheduler would pack the others.  Claiming shared memory so that exactly ctas_per_sm fit
+  // makes the extra CTAs wait for their SM instead.
+  const size_t claim = kSmemBudget / (size_t)(ctas_per_sm + 1) + 1024;
+  if (smem < claim) smem = claim < per_cta ? claim : per_cta;
+  auto kernel = k2_weights_reduce<MODE, DP>;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem);
@@ -495,19 +606,19 @@ void launch_mode(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int 
   long long grid = (long long)sm_count * occ;
   if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return;
-  launch_kernel(kernel, dim3((unsigned)grid), dim3(kThreads), smem, s, pdl, d_geoms, n_kpts, total_tiles, max_n_fold,
+  launch_kernel(kernel, dim3((unsigned)grid), dim3(kThreads), smem, s, pdl, d_geoms, n_kpts, total_tiles, bins_rows,
                 n_stages);
 }
 
-template <int MODE>
-void launch_variant(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int max_n_fold, int nreg,
-                    int ctas_per_sm, int n_stages, int sm_count, bool pdl, cudaStream_t s) {
-  switch (nreg) {
-    case 1: launch_mode<MODE, 1>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, pdl, s); break;
-    case 2: launch_mode<MODE, 2>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, pdl, s); break;
-    case 4: launch_mode<MODE, 4>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, pdl, s); break;
-    default: launch_mode<MODE, 0>(d_geoms, n_kpts, total_tiles, max_n_fold, ctas_per_sm, n_stages, sm_count, pdl, s); break;
-  }
+template <bool DP>
+void launch_precision(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int bins_rows, int n_spinor,
+                      int layout, int ctas_per_sm, int n_stages, int sm_count, bool pdl, cudaStream_t s) {
+  if (n_spinor == 1)
+    launch_mode<0, DP>(d_geoms, n_kpts, total_tiles, bins_rows, ctas_per_sm, n_stages, sm_count, pdl, s);
+  else if (layout == BANDUP_GPU_LAYOUT_FORTRAN_INMEM)
+    launch_mode<1, DP>(d_geoms, n_kpts, total_tiles, bins_rows, ctas_per_sm, n_stages, sm_count, pdl, s);
+  else
+    launch_mode<2, DP>(d_geoms, n_kpts, total_tiles, bins_rows, ctas_per_sm, n_stages, sm_count, pdl, s);
 }
 
 }  // namespace
@@ -554,11 +665,16 @@ int weights_num_chunks(long long row_elems, int chunk_vecs) {
   return (int)(n < 1 ? 1 : n);
 }
 
-// K2's register-accumulator variant: 1, 2 or 4 accumulators when the batch has at most that
-// many distinct cosets per k-point, 0 = the shared-memory bins.  variant: 0 auto, 1 bins, 2 registers.
-int weights_pick_nreg(int variant, int max_n_fold) {
-  if (variant == 1 || max_n_fold > 4 || max_n_fold < 1) return 0;
-  return max_n_fold <= 1 ? 1 : max_n_fold <= 2 ? 2 : 4;
+// Accumulator layout of one k-point (pass): 0 = per-thread shared-memory bins (any number of
+// cosets; a real branch per vector, cheapest when selected plane waves are rare), 1/2/4 = that many
+// register accumulators with predicated adds (no branch, no shared-memory read-modify-write;
+// every element costs a compare and an add per accumulator, so it pays when selected plane waves
+// are frequent: n_fold / |det M| >= 1/32 -- graphene 4x4 and the spinor 8x8 cell, not the
+// 500-fold Si-Ge cell).  variant: 0 automatic, 1 bins always, 2 registers whenever n_fold <= 4.
+int weights_pick_nreg(int variant, int n_fold, long long det_m) {
+  if (variant == 1 || n_fold > 4 || n_fold < 1) return 0;
+  if (variant == 0 && (long long)n_fold * 32 < det_m) return 0;
+  return n_fold <= 1 ? 1 : n_fold <= 2 ? 2 : 4;
 }
 
 // partials per (band, chunk): one row of (n_fold + 1) per CTA (bins) or per consumer warp (registers)
@@ -577,16 +693,16 @@ int weights_max_folds_supported() {
   return nf;
 }
 
-void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int max_n_fold,
-                           int n_spinor, int layout, int nreg, int ctas_per_sm, int n_stages, int sm_count,
+void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int bins_rows,
+                           int n_spinor, int layout, bool dp, int ctas_per_sm, int n_stages, int sm_count,
                            bool pdl, cudaStream_t s) {
   if (n_kpts <= 0 || total_tiles <= 0) return;
-  if (n_spinor == 1)
-    launch_variant<0>(d_geoms, n_kpts, total_tiles, max_n_fold, nreg, ctas_per_sm, n_stages, sm_count, pdl, s);
-  else if (layout == BANDUP_GPU_LAYOUT_FORTRAN_INMEM)
-    launch_variant<1>(d_geoms, n_kpts, total_tiles, max_n_fold, nreg, ctas_per_sm, n_stages, sm_count, pdl, s);
+  if (dp)
+    launch_precision<true>(d_geoms, n_kpts, total_tiles, bins_rows, n_spinor, layout, ctas_per_sm, n_stages, sm_count,
+                           pdl, s);
   else
-    launch_variant<2>(d_geoms, n_kpts, total_tiles, max_n_fold, nreg, ctas_per_sm, n_stages, sm_count, pdl, s);
+    launch_precision<false>(d_geoms, n_kpts, total_tiles, bins_rows, n_spinor, layout, ctas_per_sm, n_stages, sm_count,
+                            pdl, s);
 }
 
 }  // namespace bandup

@@ -48,7 +48,8 @@ def _fortran_order(latt: np.ndarray) -> np.ndarray:
 @dataclass
 class PwWavefunction:
     """type(pw_wavefunction) (constants_and_types_mod.f90:140-153), hot-path fields only."""
-    pw_coeffs: np.ndarray                 # complex64 (n_bands, n_pw, n_spinor) or a raw record buffer
+    pw_coeffs: np.ndarray                 # complex64 (n_bands, n_pw, n_spinor) or a raw record buffer;
+    #                                       complex128 for a `kind_cplx_coeffs = dp` build (OPT_COMPLEX128)
     G_frac: np.ndarray                    # int32 (n_pw, 3)
     band_energies: np.ndarray             # float64 (n_bands,)
     kpt_frac_coords: Optional[np.ndarray] = None
@@ -63,7 +64,9 @@ class PwWavefunction:
         self.band_energies = np.ascontiguousarray(self.band_energies, dtype=np.float64)
         if self.layout == LAYOUT_FORTRAN_INMEM and self.pw_coeffs.ndim == 3:
             c = self.pw_coeffs
-            if c.dtype != np.complex64 or not c.flags.c_contiguous:
+            if c.dtype == np.complex128:
+                c = np.ascontiguousarray(c)
+            elif c.dtype != np.complex64 or not c.flags.c_contiguous:
                 c = np.ascontiguousarray(c, dtype=np.complex64)
             self.pw_coeffs = c
             self.n_bands, self.n_pw, self.n_spinor = c.shape
@@ -72,7 +75,8 @@ class PwWavefunction:
         if not self.n_bands:
             self.n_bands = int(self.band_energies.shape[0])
         if not self.band_stride_bytes:
-            self.band_stride_bytes = self.n_pw * self.n_spinor * 8
+            dp = isinstance(self.pw_coeffs, np.ndarray) and self.pw_coeffs.dtype == np.complex128
+            self.band_stride_bytes = self.n_pw * self.n_spinor * (16 if dp else 8)
         if self.G_frac.shape != (self.n_pw, 3):
             raise ValueError("G_frac must be (n_pw, 3)")
         if self.band_energies.shape != (self.n_bands,):
@@ -560,8 +564,14 @@ class GpuUnfolder:
                                                     int(n_stages)))
 
     def set_option(self, option: int, value: int) -> None:
-        """bandup_gpu_set_option: CONST['BANDUP_GPU_OPT_K2_VARIANT'] / ['BANDUP_GPU_OPT_DEPENDENT_LAUNCH']."""
+        """bandup_gpu_set_option: CONST['BANDUP_GPU_OPT_K2_VARIANT'] / ['BANDUP_GPU_OPT_DEPENDENT_LAUNCH'] /
+        ['BANDUP_GPU_OPT_COMPLEX128']."""
         self._check(self._lib.bandup_gpu_set_option(self.handle, int(option), int(value)))
+
+    def set_complex128(self, enabled: bool) -> None:
+        """The reference's `kind_cplx_coeffs = dp` build (constants_and_types_mod.f90:60): from now on
+        every coefficient block handed to this unfolder is complex128."""
+        self.set_option(CONST["BANDUP_GPU_OPT_COMPLEX128"], int(bool(enabled)))
 
 
 def calc_spin_projections(pauli_vector, cart_coords_kpt, normal_to_proj_plane, origin=None):

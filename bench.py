@@ -77,7 +77,8 @@ def parse_args():
     ap.add_argument("--no-e2e-file", action="store_true", help="skip the file-level end-to-end measurement")
     ap.add_argument("--file-kpts", type=int, default=2, help="SC k-points in the synthetic WAVECAR of e2e_file")
     ap.add_argument("--k2-variant", type=int, default=0, help="0 auto, 1 shared-memory bins, 2 register accumulators")
-    ap.add_argument("--no-dependent-launch", action="store_true", help="plain stream order instead of PDL between K1, K2, K3")
+    ap.add_argument("--dependent-launch", type=int, default=3,
+                    help="programmatic dependent launch: bit 0 = K2 behind K1, bit 1 = K3 behind K2 (3 = both, 0 = none)")
     ap.add_argument("--gpu-order", default="", help="CUDA device of local rank i, comma separated (default: spread over the PCIe tree)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -530,8 +531,8 @@ def run_b200(args, sc, rank, world, local_rank):
         u.set_tuning(*[int(x) for x in args.tuning.split(",")])
     if args.k2_variant:
         u.set_option(CONST["BANDUP_GPU_OPT_K2_VARIANT"], args.k2_variant)
-    if args.no_dependent_launch:
-        u.set_option(CONST["BANDUP_GPU_OPT_DEPENDENT_LAUNCH"], 0)
+    if args.dependent_launch != 3:
+        u.set_option(CONST["BANDUP_GPU_OPT_DEPENDENT_LAUNCH"], args.dependent_launch)
     if world > 1:
         # the library's own communicator (ncclCommInitRank inside libbandup_gpu.so): rank 0 makes the
         # id, torch.distributed carries its 128 bytes to the others (MPI_Bcast in a Fortran host)
@@ -624,7 +625,7 @@ def run_b200(args, sc, rank, world, local_rank):
     ec1.record()
     torch.cuda.synchronize()
     est_ms = max_over_ranks(ec0.elapsed_time(ec1) / 3.0)
-    n_steps = max(args.steps, int(np.ceil(args.min_seconds * 1e3 / max(est_ms, 1e-3))))
+    n_steps = max(args.steps, int(np.ceil(1.1 * args.min_seconds * 1e3 / max(est_ms, 1e-3))))
     # per-kernel breakdown in its own untimed pass: an event pair between back-to-back launches
     # costs device time and serialises the dependent-launch chain
     u.set_profiling(True)
@@ -886,7 +887,7 @@ def run_b200(args, sc, rank, world, local_rank):
                               "(L2: 126 MB), read with evict_first" if step_bytes > 2 * 126e6 else
                               f"WARNING: a step streams only {step_bytes / 1e6:.0f} MB (L2: 126 MB); raise --kpts-per-step"),
                        "k2_variant": {0: "auto", 1: "shared-memory bins", 2: "register accumulators"}[args.k2_variant],
-                       "dependent_launch": not args.no_dependent_launch,
+                       "dependent_launch": args.dependent_launch,
                        "parallelism": f"SC k-points sharded over {world} GPU(s); delta_N rows gathered once per job by "
                                       "bandup_gpu_allgather_device (ncclAllGather inside libbandup_gpu.so)"
                        if world > 1 else "1 GPU"},

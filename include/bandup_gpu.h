@@ -422,14 +422,23 @@ int64_t bandup_gpu_launch_count(int handle);
  * resident CTAs per SM and depth of each CTA's shared-memory stage ring. */
 int bandup_gpu_set_tuning(int handle, int chunk_vecs, int ctas_per_sm, int n_stages);
 
-/* Further switches, for A/B measurements (not while k-points are in flight):
+/* Further switches (not while k-points are in flight; the first two exist for A/B measurements):
  *   OPT_K2_VARIANT        accumulators of the weights kernel: 0 = automatic, 1 = per-thread
  *                         shared-memory bins (any number of cosets), 2 = registers whenever a
  *                         batch has <= 4 distinct cosets per SC-kpt
- *   OPT_DEPENDENT_LAUNCH  1 (default): K1 -> K2 -> K3 of a batch are chained with programmatic
- *                         dependent launch; 0: plain stream order */
+ *   OPT_DEPENDENT_LAUNCH  programmatic dependent launch inside a batch: bit 0 = K2 behind K1,
+ *                         bit 1 = K3 behind K2; 3 (default) = both, 0 = plain stream order
+ *   OPT_COMPLEX128        the reference's `kind_cplx_coeffs = dp` build
+ *                         (constants_and_types_mod.f90:60; needed for a double-precision WAVECAR,
+ *                         nprec = 45210, read_wavecar_mod.f90:363-377): 1 = EVERY coefficient
+ *                         pointer handed to this handle refers to complex128 elements (16 bytes;
+ *                         band_stride_bytes a multiple of 16, device blocks 16-byte aligned).
+ *                         Norms, |C|^2 and all sums are then fp64 throughout; rho and the Pauli
+ *                         vectors are formed from the renormalised coefficients rounded to
+ *                         complex64 (their outputs are single precision in this ABI).  Default 0. */
 #define BANDUP_GPU_OPT_K2_VARIANT 0
 #define BANDUP_GPU_OPT_DEPENDENT_LAUNCH 1
+#define BANDUP_GPU_OPT_COMPLEX128 2
 int bandup_gpu_set_option(int handle, int option, int value);
 
 /* Fills a device buffer with the synthetic coefficients bench.py and the tests

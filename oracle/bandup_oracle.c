@@ -668,6 +668,81 @@ int bo_unfold_kpt(float complex *coeffs, int n_spinor, int64_t n_pw,
   return empty;
 }
 
+/* ---- a `kind_cplx_coeffs = dp` build of the reference (constants_and_types_mod.f90:60; the
+ * build a double-precision WAVECAR, nprec = 45210, needs: read_wavecar_mod.f90:363-377) --------
+ * The same three loops with complex(dp) coefficients: the dot_product of the renormalisation
+ * (io_routines_mod.f90:1321-1324) accumulates sequentially in double, the rescale
+ * (:1325-1327) stays in double, abs() in spectral_weight_for_coeff
+ * (band_unfolding_routines_mod.f90:638-644) is the double-precision cabs. */
+void bo_renormalize_dp(double complex *coeffs, int n_spinor, int64_t n_pw,
+                       int n_bands, double *norms_out) {
+#pragma omp parallel for schedule(guided)
+  for (int ib = 0; ib < n_bands; ++ib) {
+    double complex *c = coeffs + (int64_t)ib * n_pw * n_spinor;
+    double s = 0.0;
+    for (int is = 0; is < n_spinor; ++is) {
+      double acc = 0.0;
+      for (int64_t ig = 0; ig < n_pw; ++ig) {
+        double re = creal(c[ig * n_spinor + is]);
+        double im = cimag(c[ig * n_spinor + is]);
+        acc += re * re + im * im;
+      }
+      s += acc;
+    }
+    if (norms_out) norms_out[ib] = s;
+    if (s > BO_EPS_DP) {
+      double f = 1.0 / sqrt(fabs(s));
+      for (int64_t e = 0; e < n_pw * n_spinor; ++e) c[e] = f * creal(c[e]) + f * cimag(c[e]) * I;
+    }
+  }
+}
+
+void bo_spectral_weights_dp(const double complex *coeffs, int n_spinor,
+                            int64_t n_pw, int n_bands, const int32_t *sel,
+                            int64_t n_sel, double *weights) {
+  for (int ib = 0; ib < n_bands; ++ib) weights[ib] = 0.0;
+  for (int is = 0; is < n_spinor; ++is) {
+#pragma omp parallel for schedule(guided)
+    for (int ib = 0; ib < n_bands; ++ib) {
+      const double complex *c = coeffs + (int64_t)ib * n_pw * n_spinor;
+      double w = 0.0;
+      for (int64_t i = 0; i < n_sel; ++i) {
+        int64_t ig = (int64_t)sel[i] - 1;
+        double a = cabs(c[ig * n_spinor + is]);
+        w = w + a * a;
+      }
+      weights[ib] = weights[ib] + w;
+    }
+  }
+}
+
+int bo_unfold_kpt_dp(double complex *coeffs, int n_spinor, int64_t n_pw,
+                     int n_bands, const double *G_cart, const double *sc_ener,
+                     const double *b_pc, const double *folding_G, int n_fold,
+                     const double *energies, int64_t nener, double smearing,
+                     double *weights /*[n_fold][n_bands]*/,
+                     double *dN /*[n_fold][nener]*/, int32_t *n_selected,
+                     double *norms_out) {
+  int empty = 0;
+  bo_renormalize_dp(coeffs, n_spinor, n_pw, n_bands, norms_out);
+  int32_t *sel = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_pw > 0 ? n_pw : 1));
+  for (int f = 0; f < n_fold; ++f) {
+    int64_t ns = bo_select_coeffs(G_cart, n_pw, folding_G + 3 * f, b_pc, sel, NULL);
+    n_selected[f] = (int32_t)ns;
+    if (ns == 0) {
+      ++empty;
+      for (int ib = 0; ib < n_bands; ++ib) weights[(int64_t)f * n_bands + ib] = 0.0;
+      for (int64_t ie = 0; ie < nener; ++ie) dN[(int64_t)f * nener + ie] = 0.0;
+      continue;
+    }
+    bo_spectral_weights_dp(coeffs, n_spinor, n_pw, n_bands, sel, ns, weights + (int64_t)f * n_bands);
+    bo_delta_N(energies, nener, sc_ener, weights + (int64_t)f * n_bands, n_bands, smearing,
+               dN + (int64_t)f * nener);
+  }
+  free(sel);
+  return empty;
+}
+
 /* ---- Synthetic coefficient generator shared (bit-for-bit) with the CUDA
  * generator in bandup_b200/csrc/synth.cuh: a counter-based hash so any
  * (seed, ikpt, band, element) value can be produced without a file.

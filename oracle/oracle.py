@@ -70,6 +70,9 @@ def lib() -> C.CDLL:
         L.bo_unfold_kpt.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, _f64p, _f64p, _f64p, _f64p,
                                     C.c_int, _f64p, C.c_int64, C.c_double, C.c_int, _f64p, _f64p, _i32p,
                                     _f64p]
+        L.bo_unfold_kpt_dp.restype = C.c_int
+        L.bo_unfold_kpt_dp.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, _f64p, _f64p, _f64p, _f64p,
+                                       C.c_int, _f64p, C.c_int64, C.c_double, _f64p, _f64p, _i32p, _f64p]
         L.bo_synth_fill.restype = None
         L.bo_synth_fill.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64]
         L.bo_synth_fill_rows.restype = None
@@ -225,6 +228,26 @@ def unfold_kpt(coeffs, G_cart, sc_ener, b_pc, folding_G, energies, smearing=0.0,
                         nf, _p(en, _f64p), en.shape[0], float(smearing), int(norm_mode), _p(w, _f64p),
                         _p(dN, _f64p), _p(ns, _i32p), _p(times, _f64p))
     return w, dN, ns, times
+
+
+def unfold_kpt_dp(coeffs, G_cart, sc_ener, b_pc, folding_G, energies, smearing=0.0):
+    """The same sequence as a `kind_cplx_coeffs = dp` build of the reference runs it
+    (constants_and_types_mod.f90:60): complex128 coefficients, double-precision dot_product, abs and
+    rescale.  Returns weights, dN, n_selected, norms (before renormalisation)."""
+    c = np.array(coeffs, dtype=np.complex128, order="C", copy=True)
+    nb, npw, nsp = c.shape
+    g, e, b = _f64(G_cart), _f64(sc_ener), _f64(b_pc)
+    fg = _f64(np.atleast_2d(folding_G))
+    en = _f64(energies)
+    nf = fg.shape[0]
+    w = np.zeros((nf, nb))
+    dN = np.zeros((nf, en.shape[0]))
+    ns = np.zeros(nf, dtype=np.int32)
+    norms = np.zeros(nb)
+    lib().bo_unfold_kpt_dp(c.ctypes.data, nsp, npw, nb, _p(g, _f64p), _p(e, _f64p), _p(b, _f64p), _p(fg, _f64p),
+                           nf, _p(en, _f64p), en.shape[0], float(smearing), _p(w, _f64p), _p(dN, _f64p),
+                           _p(ns, _i32p), _p(norms, _f64p))
+    return w, dN, ns, norms
 
 
 def synth_fill(row_elems, n_bands, seed, ikpt, band0=0, out=None):

@@ -938,7 +938,8 @@ def test_host_register_caller_owned_buffer(unfolder):
         host_unregister(coeffs)
     assert np.array_equal(got.spectral_weight, ref.spectral_weight) and np.array_equal(got.dN, ref.dN)
     print(f"upload+unfold of {coeffs.nbytes / 1e6:.0f} MB: pageable {t_pageable * 1e3:.2f} ms, registered {t_locked * 1e3:.2f} ms")
-    assert t_locked < t_pageable * 1.5            # pageable goes through the staging ring at ~PCIe rate too
+    # no timing assertion: both go at about the PCIe rate (pageable through the staging ring), and a
+    # 22 MB upload is too short to rank them reliably
     after = unfolder.perform_unfolding(wf, g0=g0, want_selected=False)        # pageable again: still fine
     assert np.array_equal(after.dN, ref.dN)
 

@@ -288,3 +288,29 @@ def test_symm_average_rho_c_equals_numpy_twin(seed, n_dirs, equal):
         k, e, m1, m2, rho = case["cols"]
         keep = avg[k, e - 1] >= ON.MIN_DN_SYMM_AVG
         assert np.array_equal(got[4], rho[keep]) and np.array_equal(got[2], m1[keep])
+
+
+def test_dp_build_oracle_c_equals_numpy_and_tracks_the_sp_build():
+    """The `kind_cplx_coeffs = dp` restatement (complex128 coefficients, everything in double):
+    C == NumPy twin to rounding; fed with float-representable coefficients it agrees with the
+    default single-precision build to the latter's own rounding (~1e-6)."""
+    from bandup_b200 import synth
+    from oracle import oracle as O
+    from oracle import oracle_np as ON
+    for name, scale in (("graphene4x4", 0.15), ("mos2_8x8_spinor", 0.05)):
+        sc = synth.make_scenario(name, scale=scale)
+        coeffs, gf, ener = synth.make_wavefunction(sc, 1)
+        gc = gf @ sc.B_sc
+        fG = sc.folding_G(1)
+        grid = O.real_seq(*sc.energy_window())
+        rng = np.random.default_rng(5)
+        c128 = coeffs.astype(np.complex128) * (1.0 + 1e-9 * rng.standard_normal(coeffs.shape))   # not float-representable
+        w, dN, ns, norms = O.unfold_kpt_dp(c128, gc, ener, sc.b_pc, fG, grid)
+        w2, dN2, ns2, norms2 = ON.unfold_kpt_dp(c128, gc, ener, sc.b_pc, fG, grid)
+        assert np.array_equal(ns, ns2) and ns.min() > 0
+        assert np.allclose(w, w2, rtol=1e-12, atol=1e-300) and np.allclose(norms, norms2, rtol=1e-12)
+        assert np.allclose(dN, dN2, rtol=1e-12, atol=1e-300)
+        w_sp, dN_sp, ns_sp, _ = O.unfold_kpt(coeffs, gc, ener, sc.b_pc, fG, grid, norm_mode=1)
+        w_dp, _, ns_dp, _ = O.unfold_kpt_dp(coeffs.astype(np.complex128), gc, ener, sc.b_pc, fG, grid)
+        assert np.array_equal(ns_sp, ns_dp)
+        assert np.max(np.abs(w_sp - w_dp) / np.maximum(np.abs(w_dp), 1e-12)) < 5e-6
