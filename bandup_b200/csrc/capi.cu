@@ -568,7 +568,7 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
   {
     KernelScope k(c, BANDUP_GPU_K_DELTA_N, s);
     launch_delta_n(d_geoms, n_geoms, max_fold, static_cast<const double*>(c->d_grid.p), c->nener, c->sigma,
-                   (pdl & 2) != 0, s);
+                   c->sm_count, (pdl & 2) != 0, s);
   }
   if (n_repl > 0) {
     KernelScope k(c, BANDUP_GPU_K_DELTA_N, s);

@@ -128,7 +128,7 @@ void launch_weights_reduce(const KptGeom* d_geoms, int n_kpts, long long total_t
 // (calc_delta_N_pckpt, band_unfolding_routines_mod.f90:719-757, with lambda :701-716
 // and integral_delta_x_minus_x0, math_mod.f90:181-193).
 void launch_delta_n(const KptGeom* d_geoms, int n_kpts, int max_n_fold, const double* d_grid,
-                    int nener, double sigma, bool pdl, cudaStream_t s);
+                    int nener, double sigma, int sm_count, bool pdl, cudaStream_t s);
 
 // K0 -- plane-wave list of an SC k-point regenerated on the device in the WAVECAR reader's order
 // (read_wavecar_mod.f90:213-304).  count: per-CTA counts + exclusive scan (total at

@@ -669,11 +669,11 @@ int weights_num_chunks(long long row_elems, int chunk_vecs) {
 // cosets; a real branch per vector, cheapest when selected plane waves are rare), 1/2/4 = that many
 // register accumulators with predicated adds (no branch, no shared-memory read-modify-write;
 // every element costs a compare and an add per accumulator, so it pays when selected plane waves
-// are frequent: n_fold / |det M| >= 1/32 -- graphene 4x4 and the spinor 8x8 cell, not the
-// 500-fold Si-Ge cell).  variant: 0 automatic, 1 bins always, 2 registers whenever n_fold <= 4.
+// are frequent: n_fold / |det M| >= 1/128 -- graphene 4x4, the spinor 8x8 cell, Si 3x3x3, not the
+// 500-fold Si-Ge cell with its three pc-kpts per SC-kpt; profiles/r02_k2_variants.md).  variant: 0 automatic, 1 bins always, 2 registers whenever n_fold <= 4.
 int weights_pick_nreg(int variant, int n_fold, long long det_m) {
   if (variant == 1 || n_fold > 4 || n_fold < 1) return 0;
-  if (variant == 0 && (long long)n_fold * 32 < det_m) return 0;
+  if (variant == 0 && (long long)n_fold * 128 < det_m) return 0;
   return n_fold <= 1 ? 1 : n_fold <= 2 ? 2 : 4;
 }
 

@@ -142,3 +142,92 @@ def device_for_local_rank(local_rank: int, local_world: int) -> dict:
     except Exception as e:  # pragma: no cover - best effort
         info["error"] = repr(e)
     return info
+
+
+# ---- measured uplink sharing ------------------------------------------------------------------------
+# On virtualised boxes sysfs shows a flat PCI bus, so the tree above says nothing.  The copy engines
+# do: two GPUs behind one switch uplink each get about half their solo host->device rate when they
+# copy at the same time.  probe_h2d_groups() measures exactly that (a few hundred ms of copies) and
+# returns the groups; run it in a throw-away process (`python -m bandup_b200.numa --probe`) so that
+# the contexts it opens on every GPU die with it.
+
+def probe_h2d_groups(mbytes: int = 96, share_below: float = 0.78) -> dict:
+    import torch
+    n = torch.cuda.device_count()
+    nbytes = int(mbytes) << 20
+    host, devb, streams = [], [], []
+    for i in range(n):
+        with torch.cuda.device(i):
+            host.append(torch.empty(nbytes, dtype=torch.uint8, pin_memory=True))
+            devb.append(torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{i}"))
+            streams.append(torch.cuda.Stream(device=i))
+
+    def rates(devs, reps=3):
+        """GB/s of every device in `devs`, all copying at once."""
+        best = [0.0] * len(devs)
+        for _ in range(reps):
+            ev = []
+            for d in devs:
+                torch.cuda.synchronize(d)
+            for d in devs:
+                with torch.cuda.device(d), torch.cuda.stream(streams[d]):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    devb[d].copy_(host[d], non_blocking=True)
+                    devb[d].copy_(host[d], non_blocking=True)
+                    b.record()
+                    ev.append((a, b))
+            for k, d in enumerate(devs):
+                torch.cuda.synchronize(d)
+                best[k] = max(best[k], 2 * nbytes / (ev[k][0].elapsed_time(ev[k][1]) * 1e-3) / 1e9)
+        return best
+
+    for i in range(n):
+        rates([i], reps=1)                      # warm the contexts and the pinned mappings
+    solo = [rates([i])[0] for i in range(n)]
+    group_of = [-1] * n
+    groups: List[List[int]] = []
+    for i in range(n):
+        if group_of[i] >= 0:
+            continue
+        group_of[i] = len(groups)
+        groups.append([i])
+        for j in range(i + 1, n):
+            if group_of[j] >= 0:
+                continue
+            ri, rj = rates([i, j])
+            if min(ri / solo[i], rj / solo[j]) < share_below:
+                group_of[j] = group_of[i]
+                groups[-1].append(j)
+    order: List[int] = []
+    depth = 0
+    while len(order) < n:                       # one GPU of every group, then the second of every group, ...
+        for g in groups:
+            if depth < len(g):
+                order.append(g[depth])
+        depth += 1
+    return {"solo_GBps": [round(x, 1) for x in solo], "groups": groups, "order": order,
+            "source": "measured: pairs of GPUs copying host->device at once (bandup_b200.numa.probe_h2d_groups)"}
+
+
+def probed_gpu_order(timeout_s: float = 120.0) -> Optional[dict]:
+    """probe_h2d_groups() in a child process; None when it fails."""
+    import json
+    import subprocess
+    import sys
+    try:
+        r = subprocess.run([sys.executable, "-m", "bandup_b200.numa", "--probe"], capture_output=True, text=True,
+                           timeout=timeout_s, cwd=str(Path(__file__).resolve().parent.parent))
+        for line in reversed(r.stdout.splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+    except Exception:
+        pass
+    return None
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+    if "--probe" in sys.argv:
+        print(json.dumps(probe_h2d_groups()), flush=True)

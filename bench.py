@@ -71,6 +71,7 @@ def parse_args():
     ap.add_argument("--kpts-per-step", type=int, default=0,
                     help="SC k-points per GPU per step; 0: as many of the configuration's k-points as fit ~10 GB "
                          "(C5: 4 of 200, C1: all 30)")
+    ap.add_argument("--kpt-offset", type=int, default=0, help="first SC k-point of rank 0's shard (A/B runs on other parts of the path)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 8)")
     ap.add_argument("--min-seconds", type=float, default=0.5,
                     help="the device-timed region runs at least this long (more steps than --steps if need be)")
@@ -79,6 +80,7 @@ def parse_args():
     ap.add_argument("--k2-variant", type=int, default=0, help="0 auto, 1 shared-memory bins, 2 register accumulators")
     ap.add_argument("--dependent-launch", type=int, default=3,
                     help="programmatic dependent launch: bit 0 = K2 behind K1, bit 1 = K3 behind K2 (3 = both, 0 = none)")
+    ap.add_argument("--no-gpu-probe", action="store_true", help="do not measure which GPUs share a host uplink (N < visible GPUs)")
     ap.add_argument("--gpu-order", default="", help="CUDA device of local rank i, comma separated (default: spread over the PCIe tree)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -494,25 +496,42 @@ def run_b200(args, sc, rank, world, local_rank):
     from bandup_b200 import build as _build
     if rank == 0:
         _build.build()
-    # which GPU this local rank drives: spread over the PCIe tree before filling it (the end-to-end
-    # path is bound by host->device copies and neighbouring GPUs share a switch uplink)
-    from bandup_b200.numa import device_for_local_rank
+    # Which GPU this local rank drives.  End to end the path is bound by host->device copies, and GPUs
+    # behind one PCIe switch share its uplink, so fewer ranks than GPUs are spread over the uplinks
+    # instead of filling the box in index order: rank 0 measures which GPUs slow each other down
+    # (bandup_b200.numa.probe_h2d_groups, in a child process) and tells the others over gloo, before
+    # any rank binds to a device.  --gpu-order overrides; with every GPU in use it is index order.
+    from bandup_b200.numa import device_for_local_rank, probed_gpu_order
     if args.gpu_order:
         os.environ["BANDUP_B200_GPU_ORDER"] = args.gpu_order
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    devinfo = device_for_local_rank(local_rank, local_world)
-    cuda_idx = devinfo["device"]
     if world > 1:
         # keep stdout to the one JSON line: NCCL prints its version banner there at the VERSION and
         # WARN levels (showVersion in NCCL's init.cc; the level may also come from /etc/nccl.conf);
         # an explicit INFO/TRACE from the caller is respected
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
             os.environ["NCCL_DEBUG"] = "NONE"
+        dist.init_process_group("cpu:gloo,cuda:nccl")      # NCCL binds to the current device at its first use
+        probe = [None]
+        if not args.gpu_order and not args.no_gpu_probe and local_world < torch.cuda.device_count():
+            if rank == 0:
+                probe[0] = probed_gpu_order()
+            dist.broadcast_object_list(probe, src=0, device=torch.device("cpu"))      # over gloo: no GPU is bound yet
+            if probe[0] and sorted(probe[0].get("order", [])) == list(range(torch.cuda.device_count())):
+                os.environ["BANDUP_B200_GPU_ORDER"] = ",".join(str(i) for i in probe[0]["order"])
+        devinfo = device_for_local_rank(local_rank, local_world)
+        if probe[0]:
+            devinfo["source"] = probe[0]["source"]
+            devinfo["h2d_groups"] = probe[0]["groups"]
+            devinfo["h2d_solo_GBps"] = probe[0]["solo_GBps"]
+        cuda_idx = devinfo["device"]
         torch.cuda.set_device(cuda_idx)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", cuda_idx))
-        dist.barrier()
+        dist.all_reduce(torch.zeros(1, device=torch.device("cuda", cuda_idx)))      # first NCCL use: binds the device
+        torch.cuda.synchronize()
     else:
         _build.build()
+        devinfo = device_for_local_rank(local_rank, local_world)
+        cuda_idx = devinfo["device"]
     from bandup_b200.unfold import (GpuUnfolder, PwWavefunction, LAYOUT_FORTRAN_INMEM, pinned_empty, pinned_free, K_COSET,
                                     K_WEIGHTS, K_DELTA_N)
 
@@ -537,7 +556,7 @@ def run_b200(args, sc, rank, world, local_rank):
         # the library's own communicator (ncclCommInitRank inside libbandup_gpu.so): rank 0 makes the
         # id, torch.distributed carries its 128 bytes to the others (MPI_Bcast in a Fortran host)
         box = [GpuUnfolder.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
+        dist.broadcast_object_list(box, src=0, device=torch.device("cpu"))
         u.comm_init(world, rank, box[0])
     nener = len(grid)
     nb, nsp = sc.n_bands, sc.n_spinor
@@ -548,7 +567,7 @@ def run_b200(args, sc, rank, world, local_rank):
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     # this rank's shard of SC k-points (contiguous blocks of the K list)
-    my_k = [(rank * kps + j) % sc.n_sc_kpts for j in range(kps)]
+    my_k = [(args.kpt_offset + rank * kps + j) % sc.n_sc_kpts for j in range(kps)]
     items = []
     for iK in my_k:
         gf = sc.gvecs(iK)
@@ -598,10 +617,12 @@ def run_b200(args, sc, rank, world, local_rank):
         if world > 1:
             u.allgather_device(stream, d_dn.data_ptr(), d_dn_all.data_ptr(), d_dn.numel())
 
+    _bar = torch.zeros(1, device=dev)
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.all_reduce(_bar)       # NCCL on this rank's device
         torch.cuda.synchronize()
 
     def max_over_ranks(x: float) -> float:
@@ -812,6 +833,7 @@ def run_b200(args, sc, rank, world, local_rank):
                "kpts_per_rank": counts,
                "h2d_GBps_per_rank": [round(v, 2) for v in h2d_rates],
                "gpu_of_rank": gpu_of_rank, "gpu_order": devinfo.get("order"), "gpu_order_source": devinfo.get("source"),
+               "h2d_groups": devinfo.get("h2d_groups"), "h2d_solo_GBps": devinfo.get("h2d_solo_GBps"),
                "pci_of_gpu": devinfo.get("pci"),
                "e2e_checked": checked_all,
                "e2e_check": "every rank's last fetched weights / delta_N / n_selected / norms == the device-resident "
@@ -897,7 +919,7 @@ def run_b200(args, sc, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     u.close()
     if world > 1:
-        dist.barrier()
+        barrier()
         dist.destroy_process_group()
 
 

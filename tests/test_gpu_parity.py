@@ -996,3 +996,52 @@ def test_pageable_staging_handles_odd_sizes_and_misaligned_sources(unfolder, off
     assert np.array_equal(got.spectral_weight, ref.spectral_weight) and np.array_equal(got.dN, ref.dN)
     assert np.array_equal(got.n_selected, ref.n_selected)
     pinned_free(pin)
+
+
+@pytest.mark.parametrize("name,scale,n_kpts", [("graphene4x4", 0.08, 24), ("si333_vacancy", 0.12, 48)])
+def test_device_batch_of_many_kpoints(unfolder, name, scale, n_kpts):
+    """A whole (shrunken) job in ONE batch: dozens of SC k-points make K3 give every warp several
+    energy bins (three for the graphene job, four for the Si one) and K2 mix the register and the
+    shared-memory accumulators per k-point; every row against the oracle, and the second,
+    identical call (descriptor block re-used on the device) gives bit-identical results."""
+    import torch
+    from bandup_b200.unfold import LAYOUT_FORTRAN_INMEM
+    sc = synth.make_scenario(name, scale=scale, n_kpts=n_kpts)
+    grid = setup(unfolder, sc)
+    nener = len(grid)
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    assert sc.n_sc_kpts * ((nener + 7) // 8) > 2 * 4 * 148           # enough CTAs for several bins per warp
+    kpts, host = [], []
+    for iK in range(sc.n_sc_kpts):
+        coeffs, gf, ener = synth.make_wavefunction(sc, iK)
+        fG = sc.folding_G(iK)
+        if iK == 1:                                                  # a k-point on the shared-memory bins (> 4 cosets)
+            extra = np.array([[1, 0, 0], [0, 1, 0], [1, 1, 0], [2, 1, 0], [1, 2, 0]], dtype=np.float64) @ sc.B_sc
+            fG = np.concatenate([fG, fG[:1] + extra])
+        g0, _ = unfolder.folding_g0(fG)
+        nb, n_pw, _ = coeffs.shape
+        nf = g0.shape[0]
+        t = dict(c=torch.from_numpy(coeffs.view(np.float32).reshape(nb, n_pw, 2)).to(dev),
+                 g=torch.from_numpy(gf).to(dev), e=torch.from_numpy(ener).to(dev),
+                 w=torch.zeros((nf, nb), dtype=torch.float64, device=dev),
+                 dn=torch.zeros((nf, nener), dtype=torch.float64, device=dev),
+                 ns=torch.zeros(nf, dtype=torch.int32, device=dev))
+        host.append((coeffs, gf, ener, fG, t))
+        kpts.append(dict(n_spinor=1, n_pw=n_pw, n_bands=nb, layout=LAYOUT_FORTRAN_INMEM, band_stride_bytes=n_pw * 8,
+                         d_coeffs=t["c"].data_ptr(), d_g_frac=t["g"].data_ptr(), d_band_energies=t["e"].data_ptr(),
+                         g0=g0, d_weights=t["w"].data_ptr(), d_dN=t["dn"].data_ptr(), d_n_selected=t["ns"].data_ptr()))
+    descs, keep = unfolder.make_batch(kpts)
+    ws = unfolder.batch_workspace_bytes(descs)
+    d_ws = torch.empty(ws, dtype=torch.uint8, device=dev)
+    unfolder.unfold_device_batch(stream, descs, d_ws.data_ptr(), ws)
+    torch.cuda.synchronize()
+    first = [(t["w"].clone(), t["dn"].clone()) for *_, t in host]
+    unfolder.unfold_device_batch(stream, descs, d_ws.data_ptr(), ws)
+    torch.cuda.synchronize()
+    for (coeffs, gf, ener, fG, t), (w1, dn1) in zip(host, first):
+        assert torch.equal(t["w"], w1) and torch.equal(t["dn"], dn1)
+        w, dN, ns, _ = oracle_kpt(sc, coeffs, gf, ener, fG, grid)
+        assert np.array_equal(t["ns"].cpu().numpy(), ns)
+        assert rel_err(t["w"].cpu().numpy(), w) <= REL_TOL
+        assert rel_err(t["dn"].cpu().numpy(), dN) <= REL_TOL
