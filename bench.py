@@ -71,6 +71,9 @@ def parse_args():
     ap.add_argument("--kpts-per-step", type=int, default=0,
                     help="SC k-points per GPU per step; 0: as many of the configuration's k-points as fit ~10 GB "
                          "(C5: 4 of 200, C1: all 30)")
+    ap.add_argument("--complex128", action="store_true",
+                    help="the reference's kind_cplx_coeffs = dp build: the same blocks as complex128 (16-byte elements); "
+                         "no CPU baseline / file leg")
     ap.add_argument("--kpt-offset", type=int, default=0, help="first SC k-point of rank 0's shard (A/B runs on other parts of the path)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 8)")
     ap.add_argument("--min-seconds", type=float, default=0.5,
@@ -560,9 +563,13 @@ def run_b200(args, sc, rank, world, local_rank):
         u.comm_init(world, rank, box[0])
     nener = len(grid)
     nb, nsp = sc.n_bands, sc.n_spinor
+    esz = 16 if args.complex128 else 8          # bytes per coefficient
+    if args.complex128:
+        u.set_complex128(True)
+        args.no_cpu_baseline = args.no_e2e_file = True
     kps = args.kpts_per_step
     if kps <= 0:  # one batch = as much of the job as ~10 GB of HBM holds (small cells: the whole job)
-        kps = max(1, min(sc.n_sc_kpts, int(10e9 // (nb * sc.gvecs(0).shape[0] * nsp * 8))))
+        kps = max(1, min(sc.n_sc_kpts, int(10e9 // (nb * sc.gvecs(0).shape[0] * nsp * esz))))
     rng = np.random.default_rng(SEED + rank)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
@@ -577,6 +584,8 @@ def run_b200(args, sc, rank, world, local_rank):
         ener = make_energies(sc, rng)
         d_c = torch.empty((nb, n_pw * nsp, 2), dtype=torch.float32, device=dev)
         u.synth_fill_device(stream, d_c.data_ptr(), n_pw * nsp, nb, n_pw * nsp * 8, SEED, iK)
+        if args.complex128:     # the same numbers widened to complex128
+            d_c = torch.view_as_real(torch.view_as_complex(d_c).to(torch.complex128)).contiguous()
         ws = u.workspace_bytes(nsp, n_pw, nb, nf)
         items.append(dict(
             iK=iK, n_pw=n_pw, nf=nf, g0=g0, gf=gf, ener=ener, d_c=d_c,
@@ -589,12 +598,12 @@ def run_b200(args, sc, rank, world, local_rank):
     d_dn = torch.zeros((kps, nf_max, nener), dtype=torch.float64, device=dev)
     d_dn_all = torch.empty((world, kps, nf_max, nener), dtype=torch.float64, device=dev) if world > 1 else None
     torch.cuda.synchronize()
-    step_bytes = sum(nb * it["n_pw"] * nsp * 8 for it in items)
+    step_bytes = sum(nb * it["n_pw"] * nsp * esz for it in items)
 
     # one batch descriptor per step: K1, K2, K3 are each launched once for all kps k-points
     descs, _keep = u.make_batch([dict(
         n_spinor=nsp, n_pw=it["n_pw"], n_bands=nb, layout=LAYOUT_FORTRAN_INMEM,
-        band_stride_bytes=it["n_pw"] * nsp * 8, d_coeffs=it["d_c"].data_ptr(), d_g_frac=it["d_g"].data_ptr(),
+        band_stride_bytes=it["n_pw"] * nsp * esz, d_coeffs=it["d_c"].data_ptr(), d_g_frac=it["d_g"].data_ptr(),
         d_band_energies=it["d_e"].data_ptr(), g0=it["g0"], d_weights=it["d_w"].data_ptr(),
         d_dN=d_dn[j].data_ptr(), d_n_selected=it["d_ns"].data_ptr()) for j, it in enumerate(items)])
     ws_batch = u.batch_workspace_bytes(descs)
@@ -603,7 +612,7 @@ def run_b200(args, sc, rank, world, local_rank):
     def step():
         if args.per_kpt_launch:
             for j, it in enumerate(items):
-                u.unfold_device(stream, nsp, it["n_pw"], nb, LAYOUT_FORTRAN_INMEM, it["n_pw"] * nsp * 8,
+                u.unfold_device(stream, nsp, it["n_pw"], nb, LAYOUT_FORTRAN_INMEM, it["n_pw"] * nsp * esz,
                                 it["d_c"].data_ptr(), it["d_g"].data_ptr(), it["d_e"].data_ptr(), it["g0"],
                                 it["d_w"].data_ptr(), d_dn[j].data_ptr(), it["d_ns"].data_ptr(),
                                 it["d_ws"].data_ptr(), it["ws"])
@@ -733,15 +742,16 @@ def run_b200(args, sc, rank, world, local_rank):
         n_e2e = args.e2e_steps or min(args.steps, 8)
         host = []
         for it in items[:2]:     # two distinct pinned blocks, cycled (2 x 2.4 GB per rank)
-            nbytes = nb * it["n_pw"] * nsp * 8
+            nbytes = nb * it["n_pw"] * nsp * esz
             h = pinned_empty(nbytes)
             torch.from_numpy(h).copy_(it["d_c"].view(torch.uint8).reshape(-1))
             host.append((h, it))
         torch.cuda.synchronize()
-        wfs = [PwWavefunction(h.view(np.complex64).reshape(nb, it["n_pw"], nsp), it["gf"], it["ener"])
+        ctype = np.complex128 if args.complex128 else np.complex64
+        wfs = [PwWavefunction(h.view(ctype).reshape(nb, it["n_pw"], nsp), it["gf"], it["ener"])
                for h, it in host]
         seq = [(i % len(host)) for i in range(kps)]
-        h2d = sum(nb * host[i][1]["n_pw"] * nsp * 8 + host[i][1]["n_pw"] * 12 + nb * 8 for i in seq)
+        h2d = sum(nb * host[i][1]["n_pw"] * nsp * esz + host[i][1]["n_pw"] * 12 + nb * 8 for i in seq)
         d2h = sum(host[i][1]["nf"] * (nb + nener) * 8 + host[i][1]["nf"] * 4 + nb * 8 for i in seq)
 
         def e2e_step(base):
@@ -762,7 +772,7 @@ def run_b200(args, sc, rank, world, local_rank):
         from bandup_b200.sharding import KptTickets
         n_total = kps * n_e2e * world
         tickets = KptTickets.from_default_group(n_total, job="bench_e2e")
-        blk_bytes = [nb * host[i][1]["n_pw"] * nsp * 8 for i in range(len(host))]
+        blk_bytes = [nb * host[i][1]["n_pw"] * nsp * esz for i in range(len(host))]
         blk_h2d = [b + host[i][1]["n_pw"] * 12 + nb * 8 for i, b in enumerate(blk_bytes)]
         blk_d2h = [host[i][1]["nf"] * (nb + nener) * 8 + host[i][1]["nf"] * 4 + nb * 8 for i in range(len(host))]
         mine = 0
@@ -793,7 +803,7 @@ def run_b200(args, sc, rank, world, local_rank):
             c_dn = torch.zeros((it["nf"], nener), dtype=torch.float64, device=dev)
             c_ns = torch.zeros(it["nf"], dtype=torch.int32, device=dev)
             c_nr = torch.zeros(nb, dtype=torch.float64, device=dev)
-            u.unfold_device(stream, nsp, it["n_pw"], nb, LAYOUT_FORTRAN_INMEM, it["n_pw"] * nsp * 8,
+            u.unfold_device(stream, nsp, it["n_pw"], nb, LAYOUT_FORTRAN_INMEM, it["n_pw"] * nsp * esz,
                             it["d_c"].data_ptr(), it["d_g"].data_ptr(), it["d_e"].data_ptr(), it["g0"],
                             c_w.data_ptr(), c_dn.data_ptr(), c_ns.data_ptr(), it["d_ws"].data_ptr(), it["ws"],
                             d_norms=c_nr.data_ptr())
@@ -846,7 +856,7 @@ def run_b200(args, sc, rank, world, local_rank):
             try:
                 pg = np.empty_like(host[0][0])
                 pg[:] = host[0][0]
-                wf_pg = PwWavefunction(pg.view(np.complex64).reshape(nb, host[0][1]["n_pw"], nsp), host[0][1]["gf"],
+                wf_pg = PwWavefunction(pg.view(ctype).reshape(nb, host[0][1]["n_pw"], nsp), host[0][1]["gf"],
                                        host[0][1]["ener"])
                 u.submit(20_000, wf_pg, g0=host[0][1]["g0"])
                 u.fetch(20_000)
@@ -898,9 +908,11 @@ def run_b200(args, sc, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": n_steps,
             "steps_requested": args.steps, "timed_region_ms": ms,
             "warmup": n_warm, "ms_per_step": ms / n_steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "c64 in, f32 |C|^2, f64 accumulate",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "c128 in, f64 |C|^2, f64 accumulate" if args.complex128 else "c64 in, f32 |C|^2, f64 accumulate",
             "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "kpts_per_step_per_gpu": kps, "n_bands": nb,
+            "config": {"workload": WORKLOADS[args.workload] + (" [complex128 coefficients]" if args.complex128 else ""),
+                       "kpts_per_step_per_gpu": kps, "n_bands": nb,
                        "n_spinor": nsp, "n_pw": [it["n_pw"] for it in items],
                        "n_fold": [it["nf"] for it in items], "nener": nener,
                        "launches": "per SC k-point" if args.per_kpt_launch else

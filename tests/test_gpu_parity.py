@@ -998,10 +998,10 @@ def test_pageable_staging_handles_odd_sizes_and_misaligned_sources(unfolder, off
     pinned_free(pin)
 
 
-@pytest.mark.parametrize("name,scale,n_kpts", [("graphene4x4", 0.08, 24), ("si333_vacancy", 0.12, 48)])
+@pytest.mark.parametrize("name,scale,n_kpts", [("graphene4x4", 0.08, 36), ("si333_vacancy", 0.12, 48)])
 def test_device_batch_of_many_kpoints(unfolder, name, scale, n_kpts):
     """A whole (shrunken) job in ONE batch: dozens of SC k-points make K3 give every warp several
-    energy bins (three for the graphene job, four for the Si one) and K2 mix the register and the
+    energy bins (two or three for the graphene job, four for the Si one) and K2 mix the register and the
     shared-memory accumulators per k-point; every row against the oracle, and the second,
     identical call (descriptor block re-used on the device) gives bit-identical results."""
     import torch
@@ -1011,7 +1011,7 @@ def test_device_batch_of_many_kpoints(unfolder, name, scale, n_kpts):
     nener = len(grid)
     dev = torch.device("cuda:0")
     stream = torch.cuda.current_stream(dev).cuda_stream
-    assert sc.n_sc_kpts * ((nener + 7) // 8) > 2 * 4 * 148           # enough CTAs for several bins per warp
+    assert sc.n_sc_kpts * ((nener + 7) // 8) > 4 * 148               # enough CTAs for several bins per warp
     kpts, host = [], []
     for iK in range(sc.n_sc_kpts):
         coeffs, gf, ener = synth.make_wavefunction(sc, iK)
