@@ -515,6 +515,7 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
       g.slot = reinterpret_cast<uint8_t*>(it.ws + wl.slot_off + wl.slot_pitch * (size_t)p);
       g.slot_shift = reinterpret_cast<uint8_t*>(it.ws + wl.slot_shift_off + wl.slot_pitch * (size_t)p);
       g.block_counts = reinterpret_cast<int*>(it.ws + wl.counts_off) + (size_t)kK1MaxBlocks * (size_t)u0;
+      g.k1_blocks = 0;  // filled in below, once the largest k-point of the batch is known
       g.n_selected = ns_rows + u0;
       g.n_fold = nf;
       g.chunk_vecs = pick_chunk_vecs(c, g.row_elems * (g.dp ? 2 : 1), it.n_bands, n, it.n_spinor);
@@ -548,6 +549,8 @@ int run_batch(Ctx* c, cudaStream_t s, std::vector<BatchItem>& items) {
     if (it.n_bands > max_bands) max_bands = it.n_bands;
     if (it.n_pw > max_pw) max_pw = it.n_pw;
   }
+  const int k1_blocks = coset_classify_blocks(max_pw);
+  for (int q = 0; q < n_geoms; ++q) geoms[q].k1_blocks = k1_blocks;
   cudaError_t e = cudaSuccess;
   const char* d_blob = stage_descriptors(c, s, blob, &e);
   if (!d_blob) return cuda_fail(c, e, "staging the batch descriptors");

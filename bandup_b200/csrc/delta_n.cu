@@ -254,7 +254,7 @@ k3_finalize_delta_n(const KptGeom* __restrict__ geoms, const double* __restrict_
     if (blockIdx.x == 0) {  // size(selected_coeff_indices) of every fold: K1's per-CTA counts
       for (int f = warp; f < n_fold; f += kK3Warps) {
         int n = 0;
-        for (int bk = lane; bk < kK1MaxBlocks; bk += 32) n += g.block_counts[bk * n_fold + f];
+        for (int bk = lane; bk < g.k1_blocks; bk += 32) n += g.block_counts[bk * n_fold + f];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
         if (lane == 0) g.n_selected[f] = n;

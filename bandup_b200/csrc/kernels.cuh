@@ -39,7 +39,9 @@ struct KptGeom {
   const double* energies;     // [n_bands]
   uint8_t* slot;              // [n_pw], 2-byte aligned: fold id of every plane wave, kNoFold = none
   uint8_t* slot_shift;        // [n_pw], slot_shift[i] = slot[i+1]
-  int* block_counts;          // [kK1MaxBlocks][n_fold] plane waves per fold seen by each K1 CTA
+  int* block_counts;          // [k1_blocks][n_fold] plane waves per fold seen by each K1 CTA
+  int k1_blocks;              // CTAs K1 runs per k-point in this batch (<= kK1MaxBlocks)
+  int pad_;
   int32_t* n_selected;        // [n_fold]
   int n_fold;
   int chunk_vecs;             // 16-byte vectors per K2 tile (a multiple of the 1024-vector stage)
@@ -59,6 +61,8 @@ struct KptGeom {
 // slot[pw] = index of the fold whose coset contains G(pw), else kNoFold; slot_shift lets K2
 // fetch the two slot ids of a 16-byte vector with one aligned 16-bit load whatever the row's
 // alignment.  Per-CTA fold counts go to block_counts (summed by K3: no atomics, no memset).
+// CTAs per k-point for a batch whose largest k-point has max_n_pw plane waves (four per thread)
+int coset_classify_blocks(int max_n_pw);
 void launch_coset_classify(const KptGeom* d_geoms, int n_kpts, int max_n_pw, const CosetCommon& cc,
                            cudaStream_t s);
 

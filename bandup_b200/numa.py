@@ -144,14 +144,38 @@ def device_for_local_rank(local_rank: int, local_world: int) -> dict:
     return info
 
 
-# ---- measured uplink sharing ------------------------------------------------------------------------
+# ---- measured host-link sharing -----------------------------------------------------------------------
 # On virtualised boxes sysfs shows a flat PCI bus, so the tree above says nothing.  The copy engines
-# do: two GPUs behind one switch uplink each get about half their solo host->device rate when they
-# copy at the same time.  probe_h2d_groups() measures exactly that (a few hundred ms of copies) and
-# returns the groups; run it in a throw-away process (`python -m bandup_b200.numa --probe`) so that
-# the contexts it opens on every GPU die with it.
+# do.  On the 8-GPU boxes here any two GPUs copy host->device at their full 55 GB/s together, but GPUs
+# 0-3 share a ~115 GB/s path and GPUs 4-7 another: four ranks on GPUs 0-3 get 29 GB/s each, four
+# ranks on {0, 1, 4, 5} the full rate.  probe_h2d_order() finds such an order without knowing the
+# topology: starting from GPU 0 it keeps adding the GPU with which the set's TOTAL measured rate
+# (all copying at once) is highest, lowest index on ties.  28 short copy tests for 8 GPUs; run it in a
+# throw-away process (`python -m bandup_b200.numa --probe`) so that the contexts it opens on every
+# GPU die with it.
 
-def probe_h2d_groups(mbytes: int = 96, share_below: float = 0.78) -> dict:
+def greedy_order(n: int, total_rate, tie: float = 0.03):
+    """GPU 0, then always the GPU with which the chosen set's total rate (total_rate(list of devices),
+    all active at once) is highest; a candidate must beat the best so far by more than `tie` to
+    displace a lower index.  Returns (order, total rate of every prefix)."""
+    if n <= 0:
+        return [], []
+    order = [0]
+    prefix_total = [float(total_rate([0]))]
+    while len(order) < n:
+        best_g, best_t = -1, -1.0
+        for g in range(n):
+            if g in order:
+                continue
+            t = float(total_rate(order + [g]))
+            if best_g < 0 or t > best_t * (1.0 + tie):
+                best_g, best_t = g, t
+        order.append(best_g)
+        prefix_total.append(best_t)
+    return order, prefix_total
+
+
+def probe_h2d_order(mbytes: int = 96, tie: float = 0.03) -> dict:
     import torch
     n = torch.cuda.device_count()
     nbytes = int(mbytes) << 20
@@ -162,8 +186,8 @@ def probe_h2d_groups(mbytes: int = 96, share_below: float = 0.78) -> dict:
             devb.append(torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{i}"))
             streams.append(torch.cuda.Stream(device=i))
 
-    def rates(devs, reps=3):
-        """GB/s of every device in `devs`, all copying at once."""
+    def rates(devs, reps=2):
+        """GB/s of every device in `devs`, all copying at once (best of `reps`)."""
         best = [0.0] * len(devs)
         for _ in range(reps):
             ev = []
@@ -185,33 +209,15 @@ def probe_h2d_groups(mbytes: int = 96, share_below: float = 0.78) -> dict:
     for i in range(n):
         rates([i], reps=1)                      # warm the contexts and the pinned mappings
     solo = [rates([i])[0] for i in range(n)]
-    group_of = [-1] * n
-    groups: List[List[int]] = []
-    for i in range(n):
-        if group_of[i] >= 0:
-            continue
-        group_of[i] = len(groups)
-        groups.append([i])
-        for j in range(i + 1, n):
-            if group_of[j] >= 0:
-                continue
-            ri, rj = rates([i, j])
-            if min(ri / solo[i], rj / solo[j]) < share_below:
-                group_of[j] = group_of[i]
-                groups[-1].append(j)
-    order: List[int] = []
-    depth = 0
-    while len(order) < n:                       # one GPU of every group, then the second of every group, ...
-        for g in groups:
-            if depth < len(g):
-                order.append(g[depth])
-        depth += 1
-    return {"solo_GBps": [round(x, 1) for x in solo], "groups": groups, "order": order,
-            "source": "measured: pairs of GPUs copying host->device at once (bandup_b200.numa.probe_h2d_groups)"}
+    order, prefix_total = greedy_order(n, lambda devs: sum(rates(devs)), tie)
+    return {"solo_GBps": [round(x, 1) for x in solo], "order": order,
+            "prefix_total_GBps": [round(x, 1) for x in prefix_total],
+            "source": "measured: greedy order by total host->device rate of the GPUs copying at once "
+                      "(bandup_b200.numa.probe_h2d_order)"}
 
 
 def probed_gpu_order(timeout_s: float = 120.0) -> Optional[dict]:
-    """probe_h2d_groups() in a child process; None when it fails."""
+    """probe_h2d_order() in a child process; None when it fails."""
     import json
     import subprocess
     import sys
@@ -230,4 +236,4 @@ if __name__ == "__main__":
     import json
     import sys
     if "--probe" in sys.argv:
-        print(json.dumps(probe_h2d_groups()), flush=True)
+        print(json.dumps(probe_h2d_order()), flush=True)

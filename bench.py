@@ -502,7 +502,7 @@ def run_b200(args, sc, rank, world, local_rank):
     # Which GPU this local rank drives.  End to end the path is bound by host->device copies, and GPUs
     # behind one PCIe switch share its uplink, so fewer ranks than GPUs are spread over the uplinks
     # instead of filling the box in index order: rank 0 measures which GPUs slow each other down
-    # (bandup_b200.numa.probe_h2d_groups, in a child process) and tells the others over gloo, before
+    # (bandup_b200.numa.probe_h2d_order, in a child process) and tells the others over gloo, before
     # any rank binds to a device.  --gpu-order overrides; with every GPU in use it is index order.
     from bandup_b200.numa import device_for_local_rank, probed_gpu_order
     if args.gpu_order:
@@ -525,7 +525,7 @@ def run_b200(args, sc, rank, world, local_rank):
         devinfo = device_for_local_rank(local_rank, local_world)
         if probe[0]:
             devinfo["source"] = probe[0]["source"]
-            devinfo["h2d_groups"] = probe[0]["groups"]
+            devinfo["h2d_prefix_total_GBps"] = probe[0].get("prefix_total_GBps")
             devinfo["h2d_solo_GBps"] = probe[0]["solo_GBps"]
         cuda_idx = devinfo["device"]
         torch.cuda.set_device(cuda_idx)
@@ -843,7 +843,7 @@ def run_b200(args, sc, rank, world, local_rank):
                "kpts_per_rank": counts,
                "h2d_GBps_per_rank": [round(v, 2) for v in h2d_rates],
                "gpu_of_rank": gpu_of_rank, "gpu_order": devinfo.get("order"), "gpu_order_source": devinfo.get("source"),
-               "h2d_groups": devinfo.get("h2d_groups"), "h2d_solo_GBps": devinfo.get("h2d_solo_GBps"),
+               "h2d_probe_prefix_total_GBps": devinfo.get("h2d_prefix_total_GBps"), "h2d_solo_GBps": devinfo.get("h2d_solo_GBps"),
                "pci_of_gpu": devinfo.get("pci"),
                "e2e_checked": checked_all,
                "e2e_check": "every rank's last fetched weights / delta_N / n_selected / norms == the device-resident "

@@ -42,6 +42,9 @@ def _oracle_rhos(sc, coeffs, gf, ener, fG, grid, sigma=None):
     return out, np.array(dNs)
 
 
+GREY = {"near_threshold": 0, "stored_for_sure": 0}      # running count over this module's rho comparisons
+
+
 def _check_rho(res, want, nb):
     got_keys = {(int(f), int(i)) for f, i in zip(res.fold, res.iener)}
     for key, (rho, rho32) in want.items():
@@ -51,6 +54,14 @@ def _check_rho(res, want, nb):
         small = np.abs(rho) < 0.8e-5          # dropped for sure
         assert np.all(np.abs(dense[big] - rho[big]) <= 2e-6 * scale + 2e-7 * np.abs(rho[big]))
         assert not dense[small].any()
+        # elements within 20 % of the store threshold (|rho| >= 1e-5 is decided on the fp32 value, so the
+        # fp64 oracle cannot say which side they fall on) may be stored or dropped -- but a stored one
+        # must carry the right value, and they are counted (GREY) so the exemption stays visible
+        grey = ~big & ~small
+        stored = grey & (dense != 0)
+        assert np.all(np.abs(dense[stored] - rho[stored]) <= 2e-6 * scale + 2e-7 * np.abs(rho[stored]))
+        GREY["near_threshold"] += int(grey.sum())
+        GREY["stored_for_sure"] += int(big.sum())
         # the reference's own single-precision accumulation is within its rounding of ours
         assert np.all(np.abs(dense[big] - rho32[big]) <= 3e-5 * scale)
         assert np.allclose(dense, dense.conj().T)
@@ -375,3 +386,13 @@ def test_projected_unfold_full_size_config4(unfolder):
         assert abs(vals[0, ie - 1] - want) <= 1e-9 * max(1.0, abs(want))
         checked += 1
     assert checked == len(ies)
+
+
+def test_zz_rho_elements_near_the_store_threshold_are_rare():
+    """Runs last in this module: of all rho elements compared above, how many sat within 20 % of the
+    1e-5 store threshold (where only the value, not the stored/dropped decision, can be checked)."""
+    if GREY["stored_for_sure"] == 0:
+        pytest.skip("the rho comparisons of this module were not run")
+    share = GREY["near_threshold"] / GREY["stored_for_sure"]
+    print(f"rho elements near the store threshold: {GREY['near_threshold']} of {GREY['stored_for_sure']} stored ({share:.2%})")
+    assert share < 0.25

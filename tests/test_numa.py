@@ -30,3 +30,22 @@ def test_spread_order_uses_numa_nodes_when_the_tree_is_flat():
     paths = [[f"pci0000:{g:02x}", f"0000:{g:02x}:00.0"] for g in range(4)]
     order = spread_order(paths, [0, 0, 1, 1])
     assert {[0, 0, 1, 1][g] for g in order[:2]} == {0, 1}
+
+
+def test_greedy_order_avoids_the_shared_host_path():
+    """The 8-GPU boxes measured here: every GPU copies at 55 GB/s alone and in pairs, GPUs 0-3 share a
+    115 GB/s path, GPUs 4-7 a 142 GB/s one, the host feeds 225 GB/s in all.  Four ranks must end up
+    two and two, not on GPUs 0-3 (which is what index order gives: 29 GB/s each)."""
+    from bandup_b200.numa import greedy_order
+
+    def total(devs):
+        a = min(115.0, 55.0 * sum(1 for d in devs if d < 4))
+        b = min(142.0, 55.0 * sum(1 for d in devs if d >= 4))
+        return min(225.0, a + b)
+    order, prefix = greedy_order(8, total)
+    assert sorted(order) == list(range(8)) and order[:2] == [0, 1]
+    assert sum(1 for d in order[:4] if d < 4) == 2 and prefix[3] == 220.0
+    assert total([0, 1, 2, 3]) == 115.0                      # what index order would have given
+    # no sharing at all: index order
+    assert greedy_order(4, lambda devs: 55.0 * len(devs))[0] == [0, 1, 2, 3]
+    assert greedy_order(0, total) == ([], [])
