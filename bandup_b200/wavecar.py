@@ -27,6 +27,7 @@ import numpy as np
 from . import synth
 
 NPREC_COMPLEX64 = 45200
+NPREC_COMPLEX128 = 45210      # WAVECAR_double: needs a `kind_cplx_coeffs = dp` build of the reference (:363-377)
 READ_THREADS = int(os.environ.get("BANDUP_GPU_READ_THREADS", str(min(16, os.cpu_count() or 8))))
 
 
@@ -64,27 +65,29 @@ def write_wavecar(path, A: np.ndarray, ecut: float, kpts_frac: Sequence[np.ndarr
                   coeffs: Sequence[np.ndarray], energies: Sequence[np.ndarray],
                   occupations: Optional[Sequence[np.ndarray]] = None, nspin: int = 1,
                   extra_pad: int = 0, coeffs_spin2: Optional[Sequence[np.ndarray]] = None,
-                  energies_spin2: Optional[Sequence[np.ndarray]] = None) -> int:
-    """Writes a single-precision WAVECAR.  coeffs[ik] is (n_bands, n_pw, n_spinor) complex64 in the
-    plane-wave order of synth.gen_gvecs (== the reader's enumeration).  With nspin = 2 the second
-    spin channel repeats the first unless coeffs_spin2 / energies_spin2 are given.  Returns nrecl."""
+                  energies_spin2: Optional[Sequence[np.ndarray]] = None, double: bool = False) -> int:
+    """Writes a WAVECAR (single precision; `double`: complex128 records, nprec = 45210).  coeffs[ik] is
+    (n_bands, n_pw, n_spinor) in the plane-wave order of synth.gen_gvecs (== the reader's enumeration).
+    With nspin = 2 the second spin channel repeats the first unless coeffs_spin2 / energies_spin2 are
+    given.  Returns nrecl."""
     A = np.asarray(A, dtype=np.float64)
     nk = len(kpts_frac)
     nb = coeffs[0].shape[0]
     max_plane = max(c.shape[1] * c.shape[2] for c in coeffs)
-    nrecl = max(8 * max_plane, 8 * (4 + 3 * nb), 8 * 12) + 8 * int(extra_pad)
+    esz, ctype = (16, np.complex128) if double else (8, np.complex64)
+    nrecl = max(esz * max_plane, 8 * (4 + 3 * nb), 8 * 12) + esz * int(extra_pad)
     with open(path, "wb") as f:
         def put(rec_bytes: bytes):
             assert len(rec_bytes) <= nrecl
             f.write(rec_bytes + b"\0" * (nrecl - len(rec_bytes)))
 
-        put(np.array([nrecl, nspin, NPREC_COMPLEX64], dtype="<f8").tobytes())
+        put(np.array([nrecl, nspin, NPREC_COMPLEX128 if double else NPREC_COMPLEX64], dtype="<f8").tobytes())
         put(np.concatenate([[nk, nb, ecut], A.reshape(9)]).astype("<f8").tobytes())
         for _spin in range(nspin):
             c_src = coeffs_spin2 if (_spin == 1 and coeffs_spin2 is not None) else coeffs
             e_src = energies_spin2 if (_spin == 1 and energies_spin2 is not None) else energies
             for ik in range(nk):
-                c = np.ascontiguousarray(c_src[ik], dtype=np.complex64)
+                c = np.ascontiguousarray(c_src[ik], dtype=ctype)
                 if c.shape[0] != nb:
                     raise ValueError("every k-point must have the same number of bands")
                 n_pw, nsp = c.shape[1], c.shape[2]
@@ -99,7 +102,7 @@ def write_wavecar(path, A: np.ndarray, ecut: float, kpts_frac: Sequence[np.ndarr
                 put(hdr.tobytes())
                 for ib in range(nb):
                     # spinor-up block, then spinor-down block
-                    put(np.ascontiguousarray(c[ib].T).astype("<c8").tobytes())
+                    put(np.ascontiguousarray(c[ib].T).astype("<c16" if double else "<c8").tobytes())
     return nrecl
 
 
@@ -113,9 +116,12 @@ class Wavecar:
             self.nrecl = int(round(head[0]))
             self.nspin = int(round(head[1]))
             self.nprec = int(round(head[2]))
-            if self.nprec != NPREC_COMPLEX64:
-                # read_wavecar_mod.f90:360-377: a WAVECAR_double needs a dp build of the reference
-                raise ValueError("double-precision WAVECAR: only complex64 coefficients are supported")
+            if self.nprec not in (NPREC_COMPLEX64, NPREC_COMPLEX128):
+                raise ValueError(f"unexpected precision tag {self.nprec} in the WAVECAR header")
+            # read_wavecar_mod.f90:360-377: a WAVECAR_double needs a dp build of the reference; here the
+            # unfolder is switched to complex128 coefficients (GpuUnfolder.set_complex128) by unfold_wavecar
+            self.double = self.nprec == NPREC_COMPLEX128
+            self.elem_bytes = 16 if self.double else 8
             if self.nrecl < 96 or self.nrecl % 8:
                 raise ValueError(f"unexpected record length {self.nrecl}")
             f.seek(self.nrecl)
@@ -209,7 +215,8 @@ class Wavecar:
         de-interleave used only by tests; the GPU path consumes read_band_records directly."""
         g, nsp = self.gvecs(ikpt, ispin)
         raw = self.read_band_records(ikpt, ispin).reshape(self.nbands, self.nrecl)
-        c = raw[:, :8 * g.shape[0] * nsp].copy().view("<c8").reshape(self.nbands, nsp, g.shape[0])
+        c = raw[:, :self.elem_bytes * g.shape[0] * nsp].copy().view("<c16" if self.double else "<c8").reshape(
+            self.nbands, nsp, g.shape[0])
         return np.ascontiguousarray(c.transpose(0, 2, 1))
 
     def submit_to(self, unfolder, job_ikpt: int, ikpt: int, folding_G: np.ndarray, ispin: int = 1,
@@ -265,6 +272,8 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
     from .unfold import pinned_pool_get, pinned_pool_put
     unfolder.verify_commens(rec_latt_pc, wavecar.B_matrix)
     grid = unfolder.set_energy_grid(E_start, E_end, delta_e)
+    if hasattr(unfolder, "set_complex128"):
+        unfolder.set_complex128(wavecar.double)      # a WAVECAR_double: the reference's dp build
     sc_k = np.array([wavecar.kpt_header(i + 1, ispin).kpt_frac_coords for i in range(wavecar.nkpts)])
     if hasattr(unfolder, "get_geom_unfolding_relations"):     # K7 on the device
         # -n_sckpts_to_skip: the first k-points of a hybrid-functional WAVECAR carry no bands

@@ -142,3 +142,28 @@ def test_complex128_rho_and_pauli_vectors(unfolder):
         sure = (np.abs(a) >= 1.2e-5) | (np.abs(b) >= 1.2e-5)        # clear of the 1e-5 store threshold
         assert np.all(np.abs(a[sure] - b[sure]) <= 2e-6 * max(1.0, np.abs(a).max()))
     assert np.max(np.abs(pv_dp - pv_sp)) <= 5e-6 and np.abs(pv_sp).max() > 1e-3
+
+
+@pytest.mark.parametrize("name,scale", [("graphene4x4", 0.1), ("mos2_8x8_spinor", 0.05)])
+def test_double_precision_wavecar_file(unfolder, tmp_path, name, scale):
+    """A WAVECAR_double (nprec = 45210, complex128 records -- the file a `kind_cplx_coeffs = dp` build of
+    the reference reads, read_wavecar_mod.f90:363-377) through the file-level path: raw records
+    uploaded as they lie, plane-wave list made on the device, against the dp oracle."""
+    from bandup_b200.wavecar import Wavecar, unfold_wavecar, write_wavecar
+    from oracle import oracle as O
+    sc = synth.make_scenario(name, scale=scale, n_kpts=9)
+    data = [synth.make_wavefunction(sc, iK) for iK in range(sc.n_sc_kpts)]
+    c128 = [_c128(d[0], 11 + i) for i, d in enumerate(data)]
+    path = tmp_path / "WAVECAR_double"
+    write_wavecar(path, sc.A_sc, sc.ecut, list(sc.sc_kpts_frac), c128, [d[2] for d in data], extra_pad=1, double=True)
+    wc = Wavecar(path)
+    assert wc.double and wc.elem_bytes == 16
+    assert np.array_equal(wc.coefficients(1), c128[0])
+    got, grid = unfold_wavecar(unfolder, wc, sc.b_pc, sc.pc_kpts_cart, *sc.energy_window())
+    host_g, _ = unfold_wavecar(unfolder, wc, sc.b_pc, sc.pc_kpts_cart, *sc.energy_window(), device_gvecs=False)
+    assert np.array_equal(got.dN, host_g.dN)
+    for iK in range(sc.n_sc_kpts):
+        _, gf, ener = data[iK]
+        _, dN, _, _ = O.unfold_kpt_dp(c128[iK], gf @ sc.B_sc, ener, sc.b_pc, sc.folding_G(iK), grid)
+        assert rel_err(got.dN[np.asarray(sc.folds[iK])], dN) <= TOL_DP
+    unfolder.set_complex128(False)
