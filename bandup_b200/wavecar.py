@@ -262,12 +262,15 @@ def fold_pckpts_onto_sckpts(pc_kpts_cart: np.ndarray, sc_kpts_frac: np.ndarray, 
 def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_cart: np.ndarray,
                    E_start: float, E_end: float, delta_e: float, ispin: int = 1, rank: int = 0,
                    world_size: int = 1, device=None, group=None, after_fetch=None, device_gvecs: bool = True,
-                   n_sckpts_to_skip: int = 0):
+                   n_sckpts_to_skip: int = 0, reader: str = "pread"):
     """The reference's main loop (main_BandUP.f90:131-177) over a WAVECAR under its no-symmetry
     flags (-no_symm_sckpts -no_symm_avg): every SC-kpt of the file, all pc-kpts folding onto it in
-    one pass, raw band records read into two page-locked buffers and uploaded as they are while the
-    previous k-point computes.  Returns sharding.GatheredDeltaN (rows in pc-kpt order) and the
-    energy grid."""
+    one pass, the raw band records uploaded as they are while the previous k-point computes.
+    reader = "pread": the records of k-point j+1 are read (threaded preadv) into a page-locked buffer
+    by a helper thread while j uploads; "mmap": the file is mapped and the mapping handed to the
+    library as it is -- its staging ring then copies 16 MB chunks out of the page cache while the
+    previous chunks are on the wire, so a k-point's read and its upload overlap each other too.
+    Returns sharding.GatheredDeltaN (rows in pc-kpt order) and the energy grid."""
     from .sharding import ShardedUnfoldJob
     from .unfold import pinned_pool_get, pinned_pool_put
     unfolder.verify_commens(rec_latt_pc, wavecar.B_matrix)
@@ -290,13 +293,22 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
     # two buffers more than the pipeline depth: k-points j-1 and j-2 may be in flight and j+1 is being
     # read ahead while j is submitted; a buffer is refilled only after its k-point was fetched
     # (taken from / returned to a reuse pool: page-locking memory costs about a second per GB)
-    bufs = [pinned_pool_get(wavecar.band_block_bytes()) for _ in range(min(4, max(1, len(used))))]
+    use_mmap = reader == "mmap" and device_gvecs
+    mm = np.memmap(wavecar.path, dtype=np.uint8, mode="r") if use_mmap else None
+    bufs = [] if use_mmap else [pinned_pool_get(wavecar.band_block_bytes()) for _ in range(min(4, max(1, len(used))))]
     K_cart = sc_k @ wavecar.B_matrix
     n_loaded = [0]
 
     def load(j):
         i = used[j]
         fG = np.asarray(pc_kpts_cart)[folds[i]] - K_cart[i]
+        if use_mmap:       # no copy here: the library stages the mapped (pageable) records chunk by chunk
+            base = (wavecar.header_record(i + 1, ispin) + 1) * wavecar.nrecl
+            raw = mm[base:base + wavecar.band_block_bytes()]
+
+            def submit_mapped(u, job_ikpt, folding_G):
+                wavecar.submit_to(u, job_ikpt, i + 1, folding_G, ispin, raw=raw)
+            return submit_mapped, fG, np.asarray(folds[i])
         # the buffers rotate with THIS rank's loads (loads are sequential), not with the k-point index
         buf = bufs[n_loaded[0] % len(bufs)]
         n_loaded[0] += 1
@@ -311,7 +323,7 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
     # load() only touches the file and its own buffer, so the next k-point is parsed by a helper
     # thread while this one uploads and computes (file parsing overlaps compute)
     job = ShardedUnfoldJob(unfolder, len(used), costs, load, rank=rank, world_size=world_size, depth=2,
-                           after_fetch=after_fetch, prefetch=True)
+                           after_fetch=after_fetch, prefetch=not use_mmap)
     try:
         got = job.run(device=device, group=group)
     finally:

@@ -52,7 +52,7 @@ if rep.exists():
             "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum", "l1tex__t_sector_hit_rate.pct",
             "lts__t_sector_hit_rate.pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
     md = [f"# ncu --set full, k2_weights_reduce ({tag}, {workload})", "",
-          "`ncu --set full --clock-control none --import-source on -k regex:k2_weights_reduce -s 2 -c 2`", "",
+          "`ncu --set full --clock-control none --import-source on -k regex:k2_weights_reduce -s 1 -c 2`", "",
           "| metric | unit | launch 1 | launch 2 |", "|---|---|---|---|"]
     vals = {}
     for w in want:
@@ -69,8 +69,12 @@ if rep.exists():
     traffic = sum(rd) / len(rd) + sum(wr) / len(wr)
     md += ["", f"DRAM traffic per launch (read + write, mean of the captured launches): **{traffic / 1e9:.4f} GB**."]
     (P / f"{out}_k2_ncu.md").write_text("\n".join(md) + "\n")
+    # the capture belongs to ONE build of the library: bench.py reports it as roofline.traffic only
+    # while bandup_b200/lib/libbandup_gpu.digest (a hash of every source and flag) still says the same
+    digest_file = G / f"{tag}_lib.digest"
+    digest = (digest_file if digest_file.exists() else ROOT / "bandup_b200" / "lib" / "libbandup_gpu.digest").read_text().strip()
     (P / "k2_traffic.json").write_text(json.dumps(
-        {"workload": workload, "dram_bytes_per_launch": traffic,
+        {"workload": workload, "dram_bytes_per_launch": traffic, "lib_digest": digest,
          "source": f"profiles/{out}_k2_ncu.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}, indent=1) + "\n")
     det = subprocess.run(["ncu", "-i", str(rep), "--page", "details"], capture_output=True, text=True).stdout
     (P / f"{out}_k2_ncu_details.txt").write_text(det)
