@@ -578,13 +578,14 @@ template <int MODE, bool DP>
 void launch_mode(const KptGeom* d_geoms, int n_kpts, long long total_tiles, int bins_rows,
                  int ctas_per_sm, int n_stages, int sm_count, bool pdl, cudaStream_t s) {
   const size_t fixed = k2_fixed_smem(bins_rows);
-  // default: 2 CTAs per SM with 3 stages each (96 KB of loads in flight per SM, about twice
-  // what latency x bandwidth asks for; the B200 sweep in profiles/ has 2x3 ahead of 3x4 and of
-  // deeper rings by 2-4 %); many folds eat shared memory for the bins, so the ring shrinks
-  // before occupancy does
+  // default: 2 CTAs per SM with 4 stages each (128 KB of loads in flight per SM; the round-2 sweep
+  // under the power cap, profiles/r02_ring_sweep.md, has 2x4 ahead of 2x3 by 1-2 % on the small and
+  // medium cells and level on the 1000-atom cell, one CTA per SM with 6-12 stages 5-20 % behind);
+  // the fourth stage is free: it fits the shared memory the CTA claims anyway (see below).  Many
+  // folds eat shared memory for the bins, so the ring shrinks before occupancy does
   if (ctas_per_sm <= 0) ctas_per_sm = 2;
   if (ctas_per_sm > 2) ctas_per_sm = 2;  // the kernel is compiled for two resident CTAs per SM
-  if (n_stages <= 0) n_stages = 3;
+  if (n_stages <= 0) n_stages = 4;
   if (n_stages > kMaxStages) n_stages = kMaxStages;
   while (ctas_per_sm > 1 && (fixed + 2 * (size_t)kStageBytes + 1024) * ctas_per_sm > kSmemBudget) --ctas_per_sm;
   const size_t per_cta = kSmemBudget / ctas_per_sm - 1024;  // 1 KB per CTA is reserved by the driver

@@ -262,14 +262,15 @@ def fold_pckpts_onto_sckpts(pc_kpts_cart: np.ndarray, sc_kpts_frac: np.ndarray, 
 def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_cart: np.ndarray,
                    E_start: float, E_end: float, delta_e: float, ispin: int = 1, rank: int = 0,
                    world_size: int = 1, device=None, group=None, after_fetch=None, device_gvecs: bool = True,
-                   n_sckpts_to_skip: int = 0, reader: str = "pread"):
+                   n_sckpts_to_skip: int = 0, reader: str = "mmap"):
     """The reference's main loop (main_BandUP.f90:131-177) over a WAVECAR under its no-symmetry
     flags (-no_symm_sckpts -no_symm_avg): every SC-kpt of the file, all pc-kpts folding onto it in
     one pass, the raw band records uploaded as they are while the previous k-point computes.
-    reader = "pread": the records of k-point j+1 are read (threaded preadv) into a page-locked buffer
-    by a helper thread while j uploads; "mmap": the file is mapped and the mapping handed to the
-    library as it is -- its staging ring then copies 16 MB chunks out of the page cache while the
-    previous chunks are on the wire, so a k-point's read and its upload overlap each other too.
+    reader = "mmap" (default): the file is mapped and the mapping handed to the library as it is -- its
+    staging ring copies 16 MB chunks out of the page cache while the previous chunks are on the wire,
+    so a k-point's read and its upload overlap each other (C5: 50 GB/s of file data against 39 for
+    "pread"); "pread": the records of k-point j+1 are read (threaded preadv) into a page-locked
+    buffer by a helper thread while j uploads.
     Returns sharding.GatheredDeltaN (rows in pc-kpt order) and the energy grid."""
     from .sharding import ShardedUnfoldJob
     from .unfold import pinned_pool_get, pinned_pool_put
