@@ -79,3 +79,36 @@ if rep.exists():
     det = subprocess.run(["ncu", "-i", str(rep), "--page", "details"], capture_output=True, text=True).stdout
     (P / f"{out}_k2_ncu_details.txt").write_text(det)
 print("wrote profiles/%s_*" % out)
+
+# ---- the other captures of gpu_final.sh: spinor K2, complex128 K2, the K1/K2/K3 chain of the small cells
+WANT2 = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+         "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static"]
+extra = [("k2_spinor", "K2 on the MoS2 8x8 spinor workload (C3): k-points with 7/4/5/4/2/2 pc-kpts, registers and bins mixed"),
+         ("k2_c128", "K2 on complex128 coefficients (C5 shape, `bench.py --complex128`)"),
+         ("c1", "K1, K2, K3 of one step of the graphene 4x4 job (C1, 23 SC-kpts in one batch)"),
+         ("c2", "K1, K2, K3 of one step of the Si 3x3x3 job (C2, 99 SC-kpts in one batch)")]
+md = [f"# ncu --set full, the other captures of `scripts/gpu_final.sh {tag}`", "",
+      "Per-launch times under ncu are cold-cache and serialised (no dependent-launch overlap): compare shares and",
+      "bytes, not absolutes.", ""]
+for suffix, title in extra:
+    rep = G / f"{tag}_{suffix}.ncu-rep"
+    if not rep.exists():
+        continue
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    if len(rr) < 3:
+        continue
+    hdr = rr[0]
+    names = [r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("<unnamed>::", "").replace("unnamed>::", "")
+             for r in rr[2:]]
+    md += [f"## {title}", "", "| metric | unit | " + " | ".join(f"`{n}`" for n in names) + " |", "|---|---|" + "---|" * len(names)]
+    for w in WANT2:
+        if w in hdr:
+            i = hdr.index(w)
+            md.append(f"| `{w}` | {rr[1][i]} | " + " | ".join(r[i] for r in rr[2:]) + " |")
+    md.append("")
+(P / f"{out}_other_ncu.md").write_text("\n".join(md) + "\n")
+print("wrote profiles/%s_other_ncu.md" % out)

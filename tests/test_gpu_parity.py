@@ -986,7 +986,7 @@ def test_pageable_staging_handles_odd_sizes_and_misaligned_sources(unfolder, off
     pin[:] = coeffs.view(np.uint8).reshape(-1)
     ref = unfolder.perform_unfolding(PwWavefunction(pin.view(np.complex64).reshape(nb, n_pw, nsp), gf, ener), g0=g0,
                                      want_selected=False)
-    raw = np.empty(nbytes + 64, dtype=np.uint8)
+    raw = np.empty(nbytes + 128, dtype=np.uint8)            # room for the alignment slack (< 64) plus the offset
     base = (-raw.ctypes.data) % 64 + offset_bytes            # 64-byte boundary + the requested offset
     view = raw[base:base + nbytes]
     view[:] = coeffs.view(np.uint8).reshape(-1)
