@@ -130,3 +130,59 @@ def test_every_band_full_size_all_entry_points(unfolder, name, iK, odd):
     inside = (ener > grid[0] - 0.5 * de) & (ener < grid[-1] + 0.5 * de)
     got_w, got_dn = results["host pinned"][0], results["host pinned"][1]
     assert np.allclose(got_dn.sum(axis=1), got_w[:, inside].sum(axis=1), rtol=1e-12)
+
+
+def test_block_larger_than_4_GiB(unfolder):
+    """Maximum sizes: one SC k-point whose coefficient block does not fit 32-bit byte offsets
+    (5400 bands x 100381 plane waves x 8 B = 4.34 GB > 2^32; rows alternate between 16-byte aligned
+    and 8 bytes off), through the device-resident batch entry and through the host path from
+    pageable memory (staging ring, chunk offsets beyond 4 GiB).  Every band against the oracle."""
+    import torch
+    from bandup_b200.unfold import LAYOUT_FORTRAN_INMEM, PwWavefunction
+    from oracle import oracle as O
+    sc = synth.make_scenario("sige555")
+    assert np.array_equal(unfolder.verify_commens(sc.b_pc, sc.B_sc), sc.M)
+    grid = unfolder.set_energy_grid(*sc.energy_window())
+    iK, nb = 1, 5400
+    gf = sc.gvecs(iK)
+    n_pw = gf.shape[0]
+    assert n_pw % 2 == 1 and nb * n_pw * 8 > (1 << 32)
+    fG = sc.folding_G(iK)
+    g0, _ = unfolder.folding_g0(fG)
+    nf = g0.shape[0]
+    rng = np.random.default_rng(5)
+    ener = np.sort(rng.uniform(sc.e_fermi - 20.5, sc.e_fermi + 5.5, nb))
+    block = O.synth_fill(n_pw, nb, SEED, iK)
+    nbytes = block.nbytes
+
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    d_c = torch.from_numpy(block.view(np.uint8).reshape(-1)).to(dev)
+    d_g, d_e = torch.from_numpy(gf).to(dev), torch.from_numpy(ener).to(dev)
+    d_w = torch.zeros((nf, nb), dtype=torch.float64, device=dev)
+    d_dn = torch.zeros((nf, len(grid)), dtype=torch.float64, device=dev)
+    d_ns = torch.zeros(nf, dtype=torch.int32, device=dev)
+    d_nr = torch.zeros(nb, dtype=torch.float64, device=dev)
+    descs, keep = unfolder.make_batch([dict(
+        n_spinor=1, n_pw=n_pw, n_bands=nb, layout=LAYOUT_FORTRAN_INMEM, band_stride_bytes=n_pw * 8,
+        d_coeffs=d_c.data_ptr(), d_g_frac=d_g.data_ptr(), d_band_energies=d_e.data_ptr(), g0=g0,
+        d_weights=d_w.data_ptr(), d_dN=d_dn.data_ptr(), d_n_selected=d_ns.data_ptr(), d_norms=d_nr.data_ptr())])
+    ws = unfolder.batch_workspace_bytes(descs)
+    d_ws = torch.empty(ws, dtype=torch.uint8, device=dev)
+    unfolder.unfold_device_batch(stream, descs, d_ws.data_ptr(), ws)
+    torch.cuda.synchronize()
+    results = {"device": (d_w.cpu().numpy(), d_dn.cpu().numpy(), d_ns.cpu().numpy(), d_nr.cpu().numpy())}
+    del d_c, d_ws
+
+    unfolder.submit(1, PwWavefunction(block.reshape(nb, n_pw, 1), gf, ener), g0=g0)   # pageable NumPy memory
+    r = unfolder.fetch(1)
+    results["host pageable"] = (r.spectral_weight, r.dN, r.n_selected, r.band_norms)
+
+    _, norms = O.renormalize(block.reshape(nb, n_pw, 1), 1)
+    w, dN, ns, _ = O.unfold_kpt(block.reshape(nb, n_pw, 1), gf @ sc.B_sc, ener, sc.b_pc, fG, grid, norm_mode=1,
+                                in_place=True)
+    assert ns.min() > 0 and nbytes > (1 << 32)
+    for tag, got in results.items():
+        _check(f"4 GiB block, {tag}", *got, (w, dN, ns, norms))
+    # the last band lies beyond the 4 GiB mark: its weights are real numbers, not a wrapped row's
+    assert np.all(results["device"][0][:, -1] > 0)

@@ -1045,3 +1045,97 @@ def test_device_batch_of_many_kpoints(unfolder, name, scale, n_kpts):
         assert np.array_equal(t["ns"].cpu().numpy(), ns)
         assert rel_err(t["w"].cpu().numpy(), w) <= REL_TOL
         assert rel_err(t["dn"].cpu().numpy(), dN) <= REL_TOL
+
+
+@pytest.mark.parametrize("n_spinor,layout_name", [(1, "LAYOUT_FORTRAN_INMEM"), (2, "LAYOUT_FORTRAN_INMEM"),
+                                                  (2, "LAYOUT_VASP_RECORD")])
+def test_device_batch_writes_stay_inside_their_buffers(unfolder, n_spinor, layout_name):
+    """Guard bands (compute-sanitizer is not available on the GPU pool): inputs, outputs and the
+    workspace of a batch are carved out of ONE arena filled with a pattern, 256 bytes apart; after
+    the batch -- k-points with even and odd n_pw, 1 / 3 / 9 / 70 distinct cosets, i.e. register
+    accumulators, shared-memory bins and a second pass, plus replicated rows -- every byte outside
+    the outputs and the workspace (of exactly the size the library asked for) is what it was, every
+    output element has been written, and the weights of a band over all cosets sum to one."""
+    import torch
+    from bandup_b200 import unfold as U
+    layout = getattr(U, layout_name)
+    sc = synth.make_scenario("si333_vacancy", scale=0.2)
+    grid = setup(unfolder, sc)
+    nener = len(grid)
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    cube = np.array([[i, j, k] for i in range(6) for j in range(6) for k in range(6)], dtype=np.int32)
+    lab = synth.coset_labels(cube, sc.M)
+    _, first = np.unique(lab, return_index=True)
+    reps = cube[np.sort(first)]                                       # one vector per coset (108 of them)
+    assert len(reps) == 108
+    rng = np.random.default_rng(77)
+    GUARD = 256
+    plan, cursor = [], GUARD
+
+    def carve(nbytes, align=16, shift=0):
+        nonlocal cursor
+        off = (cursor + align - 1) // align * align + shift
+        cursor = off + nbytes + GUARD
+        return off
+
+    kpts_host = []
+    for iK, (nb, trim, g0) in enumerate([(7, 0, reps[:1]), (5, 1, reps[3:6]), (6, 0, reps[10:19]), (4, 1, reps[:70]),
+                                         (3, 0, np.concatenate([reps, reps[:5]]))]):
+        gf = sc.gvecs(iK)
+        if trim:
+            gf = gf[:-1] if gf.shape[0] % 2 == 0 else gf
+        else:
+            gf = gf if gf.shape[0] % 2 == 0 else gf[:-1]
+        n_pw = gf.shape[0]
+        assert n_pw % 2 == trim
+        row = n_pw * n_spinor
+        coeffs = (rng.standard_normal((nb, row)) + 1j * rng.standard_normal((nb, row))).astype(np.complex64)
+        ener = np.sort(rng.uniform(sc.e_fermi - 20, sc.e_fermi + 5, nb))
+        nf = len(g0)
+        # odd scalar rows make every other band start 8 bytes off a 16-byte boundary anyway; shift one block too
+        o = dict(c=carve(coeffs.nbytes, shift=8 if iK == 2 else 0), g=carve(gf.nbytes), e=carve(ener.nbytes),
+                 w=carve(nf * nb * 8), dn=carve(nf * nener * 8), ns=carve(nf * 4), nr=carve(nb * 8))
+        kpts_host.append((coeffs, np.ascontiguousarray(gf), ener, np.ascontiguousarray(g0), o, nb, n_pw, nf))
+    arena_bytes = cursor
+    arena = torch.full((arena_bytes,), 0xA5, dtype=torch.uint8, device=dev)
+    base = arena.data_ptr()
+    assert base % 256 == 0
+    writable = torch.zeros(arena_bytes, dtype=torch.bool, device=dev)
+    kpts = []
+    for coeffs, gf, ener, g0, o, nb, n_pw, nf in kpts_host:
+        for key, arr in (("c", coeffs), ("g", gf), ("e", ener)):
+            arena[o[key]:o[key] + arr.nbytes].copy_(torch.from_numpy(arr.view(np.uint8).reshape(-1)))
+        for key, n in (("w", nf * nb * 8), ("dn", nf * nener * 8), ("ns", nf * 4), ("nr", nb * 8)):
+            writable[o[key]:o[key] + n] = True
+        kpts.append(dict(n_spinor=n_spinor, n_pw=n_pw, n_bands=nb, layout=layout, band_stride_bytes=n_pw * n_spinor * 8,
+                         d_coeffs=base + o["c"], d_g_frac=base + o["g"], d_band_energies=base + o["e"], g0=g0,
+                         d_weights=base + o["w"], d_dN=base + o["dn"], d_n_selected=base + o["ns"],
+                         d_norms=base + o["nr"]))
+    descs, keep = unfolder.make_batch(kpts)
+    ws = unfolder.batch_workspace_bytes(descs)
+    ws_arena = torch.full((GUARD + ws + GUARD,), 0x5A, dtype=torch.uint8, device=dev)
+    before = arena.clone()
+    for variant in (0, 1, 2):
+        unfolder.set_option(U.CONST["BANDUP_GPU_OPT_K2_VARIANT"], variant)
+        unfolder.unfold_device_batch(stream, descs, ws_arena.data_ptr() + GUARD, ws)
+        torch.cuda.synchronize()
+        assert bool(torch.all((arena == before) | writable)), f"variant {variant}: a write outside the output buffers"
+        assert bool(torch.all(ws_arena[:GUARD] == 0x5A)) and bool(torch.all(ws_arena[GUARD + ws:] == 0x5A)), \
+            f"variant {variant}: a write outside the workspace"
+        host_arena = arena.cpu().numpy()
+        for coeffs, gf, ener, g0, o, nb, n_pw, nf in kpts_host:
+            w = host_arena[o["w"]:o["w"] + nf * nb * 8].view(np.float64).reshape(nf, nb)
+            dn = host_arena[o["dn"]:o["dn"] + nf * nener * 8].view(np.float64)
+            ns = host_arena[o["ns"]:o["ns"] + nf * 4].view(np.int32)
+            nr = host_arena[o["nr"]:o["nr"] + nb * 8].view(np.float64)
+            pattern = np.frombuffer(bytes([0xA5]) * 8, dtype=np.float64)[0]
+            assert not np.any(w == pattern) and not np.any(dn == pattern) and not np.any(nr == pattern)
+            assert np.all(ns >= 0) and np.all(ns <= n_pw)
+            assert np.all(np.isfinite(w)) and np.all(w >= 0) and np.all(w <= 1 + 1e-9)
+            if nf >= 108:
+                assert int(ns[:108].sum()) == n_pw
+                assert np.allclose(w[:108].sum(axis=0), 1.0, atol=1e-7)
+                assert np.array_equal(w[108:], w[:5])                 # the replicated rows
+        arena.copy_(before)
+    unfolder.set_option(U.CONST["BANDUP_GPU_OPT_K2_VARIANT"], 0)
