@@ -3,6 +3,7 @@
 // ceiling K2 is compared with.   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o peak_read peak_read.cu
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 __global__ void __launch_bounds__(256) k_ldg(const float4* __restrict__ p, size_t n, float* out) {
@@ -76,18 +77,21 @@ template <typename F> float time_ms(F f, int reps) {
   float ms; cudaEventElapsedTime(&ms, a, b); return ms / reps;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  // reps per configuration: 5 = a burst of ~7 ms; 400 = ~0.5 s, long enough to run into the board's power cap
+  // like bench.py's timed region does
+  const int reps = argc > 1 ? atoi(argv[1]) : 5;
   const size_t bytes = (size_t)9600 << 20;  // ~10 GB >> L2
   char* d; float* out;
   cudaMalloc(&d, bytes); cudaMalloc(&out, 4); cudaMemset(d, 1, bytes);
   for (int cta = 2; cta <= 8; cta *= 2) {
-    float ms = time_ms([&] { k_ldg<<<148 * cta, 256>>>((const float4*)d, bytes / 16, out); }, 5);
+    float ms = time_ms([&] { k_ldg<<<148 * cta, 256>>>((const float4*)d, bytes / 16, out); }, reps);
     printf("ldg.128 x8  ctas/SM=%d  %.1f GB/s\n", cta, bytes / ms / 1e6);
   }
   auto run_bulk = [&](auto kern, int stages, int sb, int cta) {
     size_t smem = (size_t)stages * sb + 16 * stages + 128;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    float ms = time_ms([&] { kern<<<148 * cta, 288, smem>>>(d, bytes, out); }, 5);
+    float ms = time_ms([&] { kern<<<148 * cta, 288, smem>>>(d, bytes, out); }, reps);
     printf("bulk ring   ctas/SM=%d stages=%d stage=%d KB  %.1f GB/s   (%s)\n", cta, stages, sb >> 10, bytes / ms / 1e6,
            cudaGetErrorString(cudaGetLastError()));
   };
