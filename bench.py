@@ -69,8 +69,10 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sige555", choices=sorted(WORKLOADS))
     ap.add_argument("--kpts-per-step", type=int, default=0,
-                    help="SC k-points per GPU per step; 0: as many of the configuration's k-points as fit ~10 GB "
-                         "(C5: 4 of 200, C1: all 30)")
+                    help="SC k-points per GPU per step; 0: as many of the configuration's k-points as fit --batch-gb "
+                         "(C5: 16 of 138, C1: all 23)")
+    ap.add_argument("--batch-gb", type=float, default=40.0,
+                    help="HBM budget of one batch's coefficient blocks when --kpts-per-step is 0")
     ap.add_argument("--complex128", action="store_true",
                     help="the reference's kind_cplx_coeffs = dp build: the same blocks as complex128 (16-byte elements); "
                          "no CPU baseline / file leg")
@@ -573,8 +575,11 @@ def run_b200(args, sc, rank, world, local_rank):
         u.set_complex128(True)
         args.no_cpu_baseline = args.no_e2e_file = True
     kps = args.kpts_per_step
-    if kps <= 0:  # one batch = as much of the job as ~10 GB of HBM holds (small cells: the whole job)
-        kps = max(1, min(sc.n_sc_kpts, int(10e9 // (nb * sc.gvecs(0).shape[0] * nsp * esz))))
+    if kps <= 0:
+        # one batch = as much of the job as ~40 GB of the 180 GB of HBM holds (small cells: the whole
+        # job; the 1000-atom cell: 16 SC-kpts).  K1/K3 and K2's ramp and drain are paid once per batch:
+        # 4 / 8 / 16 SC-kpts of C5 per launch run at 7174 / 7251 / 7293 GB/s whole step on the same board
+        kps = max(1, min(sc.n_sc_kpts, int(args.batch_gb * 1e9 // (nb * sc.gvecs(0).shape[0] * nsp * esz))))
     rng = np.random.default_rng(SEED + rank)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
@@ -737,6 +742,8 @@ def run_b200(args, sc, rank, world, local_rank):
             elif t.get("workload") == args.workload and abs(t["dram_bytes_per_launch"] / k2_bytes - 1.0) < 0.05:
                 roofline["traffic"] = t["dram_bytes_per_launch"]
                 roofline["traffic_source"] = t.get("source")
+            else:
+                roofline["traffic_dropped"] = "profiles/k2_traffic.json is of another workload or launch shape"
         except Exception:
             pass
 
@@ -898,7 +905,7 @@ def run_b200(args, sc, rank, world, local_rank):
         from oracle import oracle as O
         O.build()
         os.sched_setaffinity(0, all_cpus)        # the CPU baseline gets every host core again
-        gbs, ckps, cores, done, phases = cpu_sample(sc, my_k, args.cpu_seconds, kps)
+        gbs, ckps, cores, done, phases = cpu_sample(sc, my_k, args.cpu_seconds, min(kps, 8))
         # the reference author's habit: OMP_NUM_THREADS = n_cores/2 (tutorial run script)
         half = max(1, cores // 2)
         gbs_half, _, _, _, _ = cpu_sample(sc, my_k, args.cpu_seconds / 4, 1, threads=half)
