@@ -86,7 +86,7 @@ WANT2 = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.su
          "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
          "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
          "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static"]
-extra = [("k2_spinor", "K2 on the MoS2 8x8 spinor workload (C3): k-points with 7/4/5/4/2/2 pc-kpts, registers and bins mixed"),
+extra = [("k2_spinor", "K2 on the MoS2 8x8 spinor workload (C3, 26 SC-kpts per launch with 1-7 pc-kpts each: register accumulators and shared-memory bins mixed)"),
          ("k2_c128", "K2 on complex128 coefficients (C5 shape, `bench.py --complex128`)"),
          ("c1", "K1, K2, K3 of one step of the graphene 4x4 job (C1, 23 SC-kpts in one batch)"),
          ("c2", "K1, K2, K3 of one step of the Si 3x3x3 job (C2, 99 SC-kpts in one batch)")]
