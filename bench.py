@@ -367,6 +367,40 @@ def cpu_sample(sc, k_indices, seconds_budget, max_kpts, threads=None):
     return tot_bytes / tot_t / 1e9, done / tot_t, cores, done, phases
 
 
+def batch_kpts(args, sc):
+    """SC k-points per GPU per step (--kpts-per-step, else what fits --batch-gb)."""
+    esz = 16 if args.complex128 else 8
+    n = args.kpts_per_step
+    if n <= 0:
+        # one batch = as much of the job as ~40 GB of the 180 GB of HBM holds (small cells: the whole
+        # job; the 1000-atom cell: 16 SC-kpts).  K1/K3 and K2's ramp and drain are paid once per batch:
+        # 4 / 8 / 16 SC-kpts of C5 per launch run at 7174 / 7251 / 7293 GB/s whole step on the same board
+        per_kpt = sc.n_bands * sc.gvecs(0).shape[0] * sc.n_spinor * esz
+        n = max(1, min(sc.n_sc_kpts, int(args.batch_gb * 1e9 // per_kpt)))
+    return n
+
+
+def workload_config(args, sc, world, kps, n_pw, n_fold, nener):
+    """The `config` object of the JSON line: the workload and how the B200 arm runs it.  The reference
+    arm prints the same object for the same arguments (it times a bounded sample of that workload)."""
+    esz = 16 if args.complex128 else 8
+    step_bytes = sum(sc.n_bands * n * sc.n_spinor * esz for n in n_pw)
+    return {"workload": WORKLOADS[args.workload] + (" [complex128 coefficients]" if args.complex128 else ""),
+            "kpts_per_step_per_gpu": kps, "n_bands": sc.n_bands,
+            "n_spinor": sc.n_spinor, "n_pw": [int(n) for n in n_pw],
+            "n_fold": [int(n) for n in n_fold], "nener": int(nener),
+            "launches": "per SC k-point" if args.per_kpt_launch else
+            "one launch of K1, K2, K3 per step (bandup_gpu_unfold_device_batch)",
+            "l2": (f"inputs larger than L2: every step streams {step_bytes / 1e9:.2f} GB of coefficients "
+                   "(L2: 126 MB), read with evict_first" if step_bytes > 2 * 126e6 else
+                   f"WARNING: a step streams only {step_bytes / 1e6:.0f} MB (L2: 126 MB); raise --kpts-per-step"),
+            "k2_variant": {0: "auto", 1: "shared-memory bins", 2: "register accumulators"}[args.k2_variant],
+            "dependent_launch": args.dependent_launch,
+            "parallelism": f"SC k-points sharded over {world} GPU(s); delta_N rows gathered once per job by "
+                           "bandup_gpu_allgather_device (ncclAllGather inside libbandup_gpu.so)"
+            if world > 1 else "1 GPU"}
+
+
 def run_reference(args, sc, rank, world):
     if rank != 0:
         return
@@ -382,16 +416,20 @@ def run_reference(args, sc, rank, world):
     e2e_file = None
     if not args.no_e2e_file:
         e2e_file = reference_file_leg(args, sc)
+    # the B200 arm's configuration for the same arguments (rank 0's batch)
+    kps_b = batch_kpts(args, sc)
+    my_k = [(args.kpt_offset + j) % sc.n_sc_kpts for j in range(kps_b)]
     line = {
         "metric": METRIC, "value": gbs, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
         "steps": n_s, "warmup": n_w, "ms_per_step": 1e3 / kps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "c64 in, f32 |C|^2, f64 accumulate",
         "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "kpts_per_step": 1, "n_bands": sc.n_bands,
-                   "n_spinor": sc.n_spinor},
+        "config": workload_config(args, sc, world, kps_b, [sc.gvecs(iK).shape[0] for iK in my_k],
+                                  [len(sc.folding_G(iK)) for iK in my_k], len(O.real_seq(*sc.energy_window()))),
         "sc_kpts_per_s": kps,
         "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{done} full-size SC k-points, one per step; C+OpenMP restatement of "
+                         "sample": f"{done} full-size SC k-points of the workload, one per step (a whole batch per "
+                                   "step would take minutes on the host); C+OpenMP restatement of "
                                    "the reference loops (Fortran unbuildable here: no Fortran compiler)",
                          "phase_seconds": {"renormalise": phases[0], "select+weights": phases[1],
                                            "delta_N": phases[2]}},
@@ -574,12 +612,7 @@ def run_b200(args, sc, rank, world, local_rank):
     if args.complex128:
         u.set_complex128(True)
         args.no_cpu_baseline = args.no_e2e_file = True
-    kps = args.kpts_per_step
-    if kps <= 0:
-        # one batch = as much of the job as ~40 GB of the 180 GB of HBM holds (small cells: the whole
-        # job; the 1000-atom cell: 16 SC-kpts).  K1/K3 and K2's ramp and drain are paid once per batch:
-        # 4 / 8 / 16 SC-kpts of C5 per launch run at 7174 / 7251 / 7293 GB/s whole step on the same board
-        kps = max(1, min(sc.n_sc_kpts, int(args.batch_gb * 1e9 // (nb * sc.gvecs(0).shape[0] * nsp * esz))))
+    kps = batch_kpts(args, sc)
     rng = np.random.default_rng(SEED + rank)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
@@ -923,20 +956,7 @@ def run_b200(args, sc, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None,
             "dtype": "c128 in, f64 |C|^2, f64 accumulate" if args.complex128 else "c64 in, f32 |C|^2, f64 accumulate",
             "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload] + (" [complex128 coefficients]" if args.complex128 else ""),
-                       "kpts_per_step_per_gpu": kps, "n_bands": nb,
-                       "n_spinor": nsp, "n_pw": [it["n_pw"] for it in items],
-                       "n_fold": [it["nf"] for it in items], "nener": nener,
-                       "launches": "per SC k-point" if args.per_kpt_launch else
-                       "one launch of K1, K2, K3 per step (bandup_gpu_unfold_device_batch)",
-                       "l2": (f"inputs larger than L2: every step streams {step_bytes / 1e9:.2f} GB of coefficients "
-                              "(L2: 126 MB), read with evict_first" if step_bytes > 2 * 126e6 else
-                              f"WARNING: a step streams only {step_bytes / 1e6:.0f} MB (L2: 126 MB); raise --kpts-per-step"),
-                       "k2_variant": {0: "auto", 1: "shared-memory bins", 2: "register accumulators"}[args.k2_variant],
-                       "dependent_launch": args.dependent_launch,
-                       "parallelism": f"SC k-points sharded over {world} GPU(s); delta_N rows gathered once per job by "
-                                      "bandup_gpu_allgather_device (ncclAllGather inside libbandup_gpu.so)"
-                       if world > 1 else "1 GPU"},
+            "config": workload_config(args, sc, world, kps, [it["n_pw"] for it in items], [it["nf"] for it in items], nener),
             "sc_kpts_per_s": kpts_per_s, "gpu_launches": int(gpu_launches),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_file": e2e_file, "clocks": clocks,
         }

@@ -51,3 +51,31 @@ def test_b200_arm_json_line():
     assert f["value"] > 0 and f["checked_vs_oracle_max_rel_err"] <= 1e-6 and f["page_cache"] == "warm"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
+    # the reference arm names the same configuration
+    r = _run(["--impl", "reference", "--workload", "si333_vacancy", "--steps", "1", "--warmup", "0", "--kpts-per-step", "2",
+              "--no-e2e-file"])
+    assert r["config"] == d["config"] and r["metric"] == d["metric"] and r["unit"] == d["unit"]
+
+
+def test_both_arms_print_the_same_config_object():
+    """--impl reference names the B200 arm's configuration (it times a bounded sample of it): the
+    `config` objects come from one function, so the driver's same-config check sees equal dicts."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from bandup_b200 import synth
+    from oracle import oracle as O
+    args = types.SimpleNamespace(workload="graphene4x4", complex128=False, kpts_per_step=0, batch_gb=40.0,
+                                 per_kpt_launch=False, k2_variant=0, dependent_launch=3, kpt_offset=0)
+    sc = synth.make_scenario("graphene4x4")
+    kps = bench.batch_kpts(args, sc)
+    assert kps == sc.n_sc_kpts                            # the whole job of a small cell is one batch
+    my_k = list(range(kps))
+    cfg = bench.workload_config(args, sc, 1, kps, [sc.gvecs(i).shape[0] for i in my_k],
+                                [len(sc.folding_G(i)) for i in my_k], len(O.real_seq(*sc.energy_window())))
+    d = _run(["--impl", "reference", "--workload", "graphene4x4", "--steps", "1", "--warmup", "0", "--no-e2e-file"])
+    assert d["config"] == cfg and "model" not in cfg and cfg["kpts_per_step_per_gpu"] == kps
+    args.workload = "sige555"
+    assert bench.batch_kpts(args, synth.make_scenario("sige555")) == 16
