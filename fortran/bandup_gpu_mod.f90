@@ -31,12 +31,38 @@ public :: bandup_gpu_init, bandup_gpu_finalize, bandup_gpu_last_error, &
           bandup_gpu_gather_rows, bandup_gpu_allgather_device, &
           bandup_gpu_unfold_kpt_f, bandup_gpu_error_message
 public :: BANDUP_GPU_OK, BANDUP_GPU_LAYOUT_FORTRAN_INMEM, BANDUP_GPU_LAYOUT_VASP_RECORD, &
-          BANDUP_GPU_MAX_FOLDS
+          BANDUP_GPU_MAX_FOLDS, BANDUP_GPU_MAX_PCKPTS, BANDUP_GPU_COMM_ID_BYTES, &
+          BANDUP_GPU_ERR_INVALID_ARG, BANDUP_GPU_ERR_CUDA, BANDUP_GPU_ERR_NOT_COMMENSURATE, &
+          BANDUP_GPU_ERR_FOLDING_VECTOR, BANDUP_GPU_ERR_TOO_MANY_FOLDS, BANDUP_GPU_ERR_BAD_HANDLE, &
+          BANDUP_GPU_ERR_NOT_CONFIGURED, BANDUP_GPU_ERR_UNKNOWN_KPT, BANDUP_GPU_ERR_NO_DEVICE, &
+          BANDUP_GPU_ERR_CAPACITY, BANDUP_GPU_ERR_DELTA_N_ZERO, BANDUP_GPU_ERR_INT_OVERFLOW, &
+          BANDUP_GPU_ERR_NCCL, &
+          BANDUP_GPU_OPT_K2_VARIANT, BANDUP_GPU_OPT_DEPENDENT_LAUNCH, BANDUP_GPU_OPT_COMPLEX128
 
 integer(c_int), parameter :: BANDUP_GPU_OK = 0
 integer(c_int), parameter :: BANDUP_GPU_LAYOUT_FORTRAN_INMEM = 0
 integer(c_int), parameter :: BANDUP_GPU_LAYOUT_VASP_RECORD = 1
 integer(c_int), parameter :: BANDUP_GPU_MAX_FOLDS = 64
+integer(c_int), parameter :: BANDUP_GPU_MAX_PCKPTS = 4096
+integer(c_int), parameter :: BANDUP_GPU_COMM_ID_BYTES = 128
+! status codes (include/bandup_gpu.h); the message is bandup_gpu_error_message(handle)
+integer(c_int), parameter :: BANDUP_GPU_ERR_INVALID_ARG = 1
+integer(c_int), parameter :: BANDUP_GPU_ERR_CUDA = 2
+integer(c_int), parameter :: BANDUP_GPU_ERR_NOT_COMMENSURATE = 3
+integer(c_int), parameter :: BANDUP_GPU_ERR_FOLDING_VECTOR = 4
+integer(c_int), parameter :: BANDUP_GPU_ERR_TOO_MANY_FOLDS = 5
+integer(c_int), parameter :: BANDUP_GPU_ERR_BAD_HANDLE = 6
+integer(c_int), parameter :: BANDUP_GPU_ERR_NOT_CONFIGURED = 7
+integer(c_int), parameter :: BANDUP_GPU_ERR_UNKNOWN_KPT = 8
+integer(c_int), parameter :: BANDUP_GPU_ERR_NO_DEVICE = 9
+integer(c_int), parameter :: BANDUP_GPU_ERR_CAPACITY = 10
+integer(c_int), parameter :: BANDUP_GPU_ERR_DELTA_N_ZERO = 11
+integer(c_int), parameter :: BANDUP_GPU_ERR_INT_OVERFLOW = 12
+integer(c_int), parameter :: BANDUP_GPU_ERR_NCCL = 13
+! bandup_gpu_set_option
+integer(c_int), parameter :: BANDUP_GPU_OPT_K2_VARIANT = 0
+integer(c_int), parameter :: BANDUP_GPU_OPT_DEPENDENT_LAUNCH = 1
+integer(c_int), parameter :: BANDUP_GPU_OPT_COMPLEX128 = 2   ! kind_cplx_coeffs = dp builds
 
 interface
 
