@@ -1,3 +1,4 @@
+# step rate vs SC k-points per launch on the two small cells (1 GPU): graphene 12..184, Si 3x3x3 25..198 per batch.
 set -x
 mkdir -p gpurun_out
 T=${1:-r02i}
