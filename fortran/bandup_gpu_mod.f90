@@ -19,7 +19,7 @@ public :: bandup_gpu_init, bandup_gpu_finalize, bandup_gpu_last_error, &
           bandup_gpu_host_register, bandup_gpu_host_unregister, &
           bandup_gpu_set_cells, bandup_gpu_set_grid, bandup_gpu_get_grid, &
           bandup_gpu_folding_g0, bandup_gpu_fold_map, bandup_gpu_submit_kpt, bandup_gpu_submit_kpt_vasp, &
-          bandup_gpu_fetch_kpt, &
+          bandup_gpu_fetch_kpt, bandup_gpu_fetch_gvecs, &
           bandup_gpu_pipeline_depth, bandup_gpu_set_profiling, &
           bandup_gpu_kernel_time, bandup_gpu_reset_kernel_times, &
           bandup_gpu_launch_count, bandup_gpu_set_tuning, bandup_gpu_set_option, &
@@ -201,6 +201,16 @@ interface
         integer(c_int), intent(out) :: n_spinor_out, n_pw_out
         integer(c_int) :: bandup_gpu_submit_kpt_vasp
     end function bandup_gpu_submit_kpt_vasp
+
+    ! wf%G_frac of a k-point submitted through bandup_gpu_submit_kpt_vasp (the list was regenerated
+    ! on the device, read_wavecar_mod.f90:275-302): g_frac(3, capacity), capacity >= n_pw
+    function bandup_gpu_fetch_gvecs(handle, ikpt, g_frac, capacity) bind(c, name='bandup_gpu_fetch_gvecs')
+        import c_int, c_int32_t, c_int64_t
+        integer(c_int), intent(in), value :: handle, ikpt
+        integer(c_int32_t), intent(out) :: g_frac(3,*)
+        integer(c_int64_t), intent(in), value :: capacity
+        integer(c_int) :: bandup_gpu_fetch_gvecs
+    end function bandup_gpu_fetch_gvecs
 
     ! weights(n_bands, n_fold), dN(nener, n_fold) in Fortran order.  Optional C outputs
     ! are passed as type(c_ptr): c_null_ptr to skip, c_loc(array) otherwise.

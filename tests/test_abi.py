@@ -184,3 +184,96 @@ def test_ctypes_binding_argument_types(gpu_lib):
                     assert (at._type_ in (C.c_float, C.c_double)) == (cbase in ("float", "double")), where
             n += 1
     assert n > 200
+
+
+def _crack_shim():
+    """The shim as parsed by NumPy's Fortran front end (numpy.f2py.crackfortran: a real free-form
+    Fortran 90 parser, independent of the regular expressions used above)."""
+    import contextlib
+    import io
+    cf = pytest.importorskip("numpy.f2py.crackfortran")
+    cf.verbose = 0
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink), contextlib.redirect_stderr(sink):
+        blocks = cf.crackfortran([str(ROOT / "fortran" / "bandup_gpu_mod.f90")])
+    return blocks
+
+
+def test_fortran_shim_parses_as_fortran():
+    """No Fortran compiler here, but a Fortran parser: the module must come out as one module with
+    one interface block and the two contained procedures, every bind(c) function with a typed
+    result and every dummy argument declared with the kind and passing convention the C prototype
+    asks for."""
+    blocks = _crack_shim()
+    assert [b["block"] for b in blocks] == ["module"] and blocks[0]["name"] == "bandup_gpu"
+    body = blocks[0]["body"]
+    assert [b["block"] for b in body] == ["interface", "function", "subroutine"]
+    assert [b["name"] for b in body[1:]] == ["bandup_gpu_error_message", "bandup_gpu_unfold_kpt_f"]
+    protos = _header_prototypes()
+    lower = {k.lower(): k for k in protos}                 # Fortran names are case-insensitive
+    kinds = {"int": ("integer", "c_int"), "unsigned": ("integer", "c_int"), "int32_t": ("integer", "c_int32_t"),
+             "int64_t": ("integer", "c_int64_t"), "size_t": ("integer", "c_size_t"),
+             "double": ("real", "c_double"), "float": ("real", "c_float"), "uint8_t": ("integer", "c_int8_t"),
+             "uint64_t": ("integer", "c_int64_t")}
+    n_args = 0
+    funcs = body[0]["body"]
+    assert len(funcs) == len({f["name"] for f in funcs}) >= 40
+    for f in funcs:
+        assert f["block"] == "function", f["name"]
+        cname = lower[f["name"]]
+        res = f["vars"][f["name"]]
+        assert res["typespec"] in ("integer", "type"), cname      # int / size_t / int64_t status, or const char*
+        cargs = _c_args(cname)
+        assert len(cargs) == len(f["args"]) == protos[cname], cname
+        for (cbase, cptr), a in zip(cargs, f["args"]):
+            v = f["vars"][a]
+            assert "typespec" in v, f"{cname}: dummy argument {a} is not declared"
+            by_value = "value" in v.get("attrspec", [])
+            where = f"{cname}({a}): C `{cbase}{'*' * cptr}` vs {v}"
+            if v["typespec"] == "type":
+                assert v["typename"] == "c_ptr", where
+                assert (cptr == 1 and by_value) or (cptr == 2 and not by_value), where
+            elif cptr == 0:
+                assert by_value and "dimension" not in v, where
+                assert (v["typespec"], v["kindselector"]["kind"]) == kinds[cbase], where
+            else:
+                assert not by_value, where
+                if cbase in kinds:
+                    assert (v["typespec"], v["kindselector"]["kind"]) == kinds[cbase], where
+            n_args += 1
+    assert n_args > 150
+
+
+def test_fortran_interface_bodies_import_what_they_use():
+    """An interface body does not see the host's `use iso_c_binding`: every c_* kind or type a
+    body names must be on its own `import` line (a classic compile error otherwise)."""
+    f90 = re.sub(r"&\s*\n\s*", " ", (ROOT / "fortran" / "bandup_gpu_mod.f90").read_text())
+    iface = f90[f90.index("\ninterface"):f90.index("\nend interface")]
+    n = 0
+    for m in re.finditer(r"function\s+(\w+)\s*\([^)]*\)\s*bind\(c,[^)]*\)(.*?)end function \1", iface, re.S):
+        text = "\n".join(l.split("!")[0] for l in m.group(2).splitlines())
+        imp = re.search(r"^\s*import\s+(?:::)?\s*(.*)$", text, re.M)
+        assert imp, f"{m.group(1)} has no import statement"
+        imported = {t.strip().lower() for t in imp.group(1).split(",")}
+        used = {t.lower() for t in re.findall(r"\bc_\w+", text.replace(imp.group(0), ""))}
+        assert used <= imported, f"{m.group(1)} uses {sorted(used - imported)} without importing them"
+        assert imported <= used, f"{m.group(1)} imports {sorted(imported - used)} and never uses them"
+        n += 1
+    assert n >= 40
+
+
+def test_fortran_shim_source_form():
+    """Free-form limits a compiler enforces: lines of at most 132 characters, at most 39
+    continuation lines per statement (Fortran 95; 255 from 2003 on), balanced block ends."""
+    lines = (ROOT / "fortran" / "bandup_gpu_mod.f90").read_text().splitlines()
+    assert max(len(l) for l in lines) <= 132
+    run = 0
+    for l in lines:
+        code = l.split("!")[0].rstrip()
+        run = run + 1 if code.endswith("&") else 0
+        assert run <= 39
+    code = "\n".join(l.split("!")[0] for l in lines).lower()
+    for opener, closer in [(r"^\s*function\s+\w+", r"^\s*end function"), (r"^\s*subroutine\s+\w+", r"^\s*end subroutine"),
+                           (r"^\s*interface\s*$", r"^\s*end interface"), (r"^\s*module\s+\w+", r"^\s*end module"),
+                           (r"\bthen\s*$", r"^\s*end\s*if\b"), (r"^\s*do\b", r"^\s*end\s*do\b")]:
+        assert len(re.findall(opener, code, re.M)) == len(re.findall(closer, code, re.M)), opener
