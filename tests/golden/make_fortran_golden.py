@@ -1,0 +1,277 @@
+"""Golden vectors for the Fortran half of the path, produced by EXECUTING the reference's own
+source files (oracle/f90interp.py interprets them where they lie under /root/reference/src; this
+image has no Fortran compiler).  Run in the build container only:
+
+    python tests/golden/make_fortran_golden.py          # writes tests/golden/fortran_golden.npz/.json
+
+What runs, per case, all of it the reference's text:
+  get_rec_latt, check_if_pc_and_SC_are_commensurate              (crystals_mod.f90:41-73,186-202)
+  n_Gvecs_2b_generated, populate_wf_with_G_vec_coords             (read_wavecar_mod.f90:151-304)
+  the band renormalisation block of read_wavefunction             (io_routines_mod.f90:1317-1330)
+  real_seq                                                        (lists_and_seqs_mod.f90:188-200)
+  select_coeffs_to_calc_spectral_weights -> vec_in_latt -> same_vector (band_unfolding_routines_mod.f90:550-612)
+  perform_unfolding as a whole: spectral_weight_for_coeff, get_delta_Ns_for_EBS -> calc_delta_N_pckpt
+      -> lambda -> integral_delta_x_minus_x0, calc_rho and its sparsification, get_SC_pauli_matrix_elmnts,
+      trace_AB, calc_spin_projections                              (:615-651, :701-786, :1046-1510)
+  get_delta_Ns_for_EBS with a smearing, calc_spectral_function     (:654-698, :760-786)
+The inputs (cells, k-points, synthetic coefficients and band energies) are stored next to the outputs.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import f90interp as F  # noqa: E402
+
+REF = Path("/root/reference/src")
+FILES = ["constants_and_types_mod.f90", "math_mod.f90", "lists_and_seqs_mod.f90", "crystals_mod.f90",
+         "band_unfolding_routines_mod.f90", "io_routines_mod.f90", "vasp_related_modules/read_wavecar_mod.f90"]
+R8, I4, LG = np.float64, np.int32, np.bool_
+
+
+def interpreter(perform_unfold=True, write_unf_dens_op=True):
+    it = F.Interp()
+    for f in FILES:
+        it.load(REF / f)
+    it.overrides["time_now"] = lambda: R8(0.0)
+    args = F.FStruct("comm_line_args", perform_unfold=LG(perform_unfold), write_unf_dens_op=LG(write_unf_dens_op),
+                     normal_to_proj_plane=np.array([0.0, 0.0, 1.0]))
+    it.set_module_variable("args", args)
+    return it
+
+
+def decl(it, text):
+    return F.parse_declaration(text, it._eval_module_const)[0]
+
+
+def struct_array(it, typename, n):
+    a = np.empty(n, dtype=object)
+    for i in range(n):
+        a[i] = it.new_struct(typename)
+    return a
+
+
+def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, grid, seed, *,
+             perform_unfold=True, zero_band=None, folding_noise=0.0, smearing=None, sf_std=None):
+    """pc_kpts_frac_sc: the pc-kpts to unfold onto, in fractional SC reciprocal coordinates
+    (K + an SC reciprocal lattice vector each)."""
+    it = interpreter(perform_unfold)
+    rng = np.random.default_rng(seed)
+    out = {}
+    a_pc = np.asarray(a_pc, dtype=R8)
+    A_sc = np.asarray(M, dtype=R8) @ a_pc
+    b_pc, B_sc = F.Var(np.zeros((3, 3)), None), F.Var(np.zeros((3, 3)), None)
+    it.call("get_rec_latt", a_pc, b_pc)
+    it.call("get_rec_latt", A_sc, B_sc)
+    b_pc, B_sc = b_pc.value, B_sc.value
+    crystal_pc = F.FStruct("crystal_3d", rec_latt_vecs=b_pc, latt_vecs=a_pc)
+    crystal_sc = F.FStruct("crystal_3d", rec_latt_vecs=B_sc, latt_vecs=A_sc)
+    comm, Mout = F.Var(LG(False), None), F.Var(np.zeros((3, 3)), None)
+    it.call("check_if_pc_and_sc_are_commensurate", comm, Mout, crystal_pc, crystal_sc)
+    out.update(a_pc=a_pc, A_sc=A_sc, b_pc=b_pc, B_sc=B_sc, commensurate=np.array(bool(comm.value)), M=Mout.value)
+
+    # ---- the plane-wave list as read_wavecar builds it -----------------------------------
+    wf = it.new_struct("pw_wavefunction")
+    kf = np.asarray(kpt_frac, dtype=R8)
+    b1, b2, b3 = B_sc[0].copy(), B_sc[1].copy(), B_sc[2].copy()
+    n_g = int(it.call("n_gvecs_2b_generated", kf, R8(ecut), b1, b2, b3))
+    wf["n_pw"], wf["n_bands"], wf["n_spinor"] = I4(n_g), I4(n_bands), I4(n_spinor)
+    it.call("populate_wf_with_g_vec_coords", wf, kf, R8(ecut), b1, b2, b3)
+    g_frac = np.array([g["coord"] for g in wf["g_frac"]], dtype=np.int32)
+    g_cart = np.array([g["coord"] for g in wf["g_cart"]], dtype=R8)
+    out.update(kpt_frac=kf, ecut=np.array(ecut), g_frac=g_frac, g_cart=g_cart)
+
+    # ---- synthetic coefficients, band energies, energy grid ---------------------------------
+    kg = (g_frac + kf) @ B_sc
+    env = np.exp(-np.sum(kg * kg, axis=1) / (2.0 * 0.2624658 * ecut / 4.0))
+    c = (rng.standard_normal((n_spinor, n_g, n_bands)) + 1j * rng.standard_normal((n_spinor, n_g, n_bands)))
+    c *= env[None, :, None] * rng.uniform(0.2, 3.0, size=(1, 1, n_bands))
+    c = c.astype(np.complex64)
+    if zero_band is not None:
+        c[:, :, zero_band] = 0
+    e_start, e_end, d_e = grid
+    egrid = F.Var(None, decl(it, "real(kind=dp), dimension(:), allocatable :: return_list"))
+    it.call("real_seq", R8(e_start), R8(e_end), R8(d_e), egrid)
+    egrid = egrid.value
+    ener = np.sort(rng.uniform(e_start - 0.3, e_end + 0.3, size=n_bands))
+    if n_bands >= 4:
+        ener[1] = ener[0]                                     # an exact duplicate
+        ener[2] = egrid[len(egrid) // 2] + 0.5 * (egrid[1] - egrid[0])   # exactly on a bin edge
+        ener[3] = ener[2] + 1e-3                             # a close neighbour (shares bins: rho pairs)
+        ener = np.sort(ener)
+    out.update(coeffs_in=c.copy(), band_energies=ener, energy_grid=egrid)
+    wf["pw_coeffs"] = c
+    wf["band_energies"] = ener.astype(R8)
+
+    # ---- the renormalisation block of read_wavefunction -------------------------------------
+    it.exec_statements(REF / "io_routines_mod.f90", 1317, 1330, {
+        "wf": (wf, None),
+        "read_coefficients": (LG(True), "logical :: read_coefficients"),
+        "iband": (None, "integer :: iband"), "i": (None, "integer :: i"),
+        "inner_prod": (None, _inner_prod_decl(it)),
+    })
+    out["coeffs_renormalised"] = wf["pw_coeffs"].copy()
+
+    # ---- geometric unfolding relations for ONE SC-kpt, one direction, n_fold pc-kpts -------
+    K_cart = kf @ B_sc
+    n_fold = len(pc_kpts_frac_sc)
+    gur = it.new_struct("geom_unfolding_relations_for_each_sckpt")
+    gur["list_of_sckpts"] = struct_array(it, "vec3d", 1)
+    gur["list_of_sckpts"][0]["coord"][:] = K_cart
+    gur["sckpt"] = struct_array(it, "selected_pcbz_directions", 1)
+    gur["sckpt"][0]["selec_pcbz_dir"] = struct_array(it, "needed_pcbz_dirs_for_ebs", 1)
+    gur["sckpt"][0]["selec_pcbz_dir"][0]["needed_dir"] = struct_array(it, "list_of_trial_folding_pckpts", 1)
+    pck = struct_array(it, "trial_folding_pckpt", n_fold)
+    gur["sckpt"][0]["selec_pcbz_dir"][0]["needed_dir"][0]["pckpt"] = pck
+    folding_G = np.zeros((n_fold, 3))
+    for f, kk in enumerate(pc_kpts_frac_sc):
+        k_cart = np.asarray(kk, dtype=R8) @ B_sc + folding_noise * rng.standard_normal(3)
+        pck[f]["scoords"][:] = k_cart
+        pck[f]["coords"][:] = k_cart
+        pck[f]["folds"] = LG(True)
+        folding_G[f] = k_cart - K_cart
+    out["pckpts_cart"] = np.array([p["scoords"] for p in pck])
+    out["K_cart"] = K_cart
+    delta_N = it.new_struct("unfoldedquantities")
+    delta_N["selec_pcbz_dir"] = struct_array(it, "unfoldedquantities_info_for_needed_pcbz_dirs", 1)
+    delta_N["selec_pcbz_dir"][0]["needed_dir"] = struct_array(it, "list_of_pckpts_for_unfolded_quantities", 1)
+    uq = struct_array(it, "unfolded_quantities_for_given_pckpt", n_fold)
+    delta_N["selec_pcbz_dir"][0]["needed_dir"][0]["pckpt"] = uq
+    times = it.new_struct("timekeeping")
+    nener = len(egrid)
+    sel_all, w_all, dn_all = [], [], []
+    rho_rows = []          # (fold, iener, m1, m2, re, im), 1-based like the reference
+    sigma = np.zeros((n_fold, nener, 3))
+    proj = np.zeros((n_fold, nener, 2))
+    for f in range(n_fold):
+        ci = gur["current_index"]
+        ci["i_sckpt"], ci["i_selec_pcbz_dir"], ci["i_needed_dirs"], ci["ipc_kpt"] = I4(1), I4(1), I4(1), I4(f + 1)
+        sel = F.Var(None, decl(it, "integer, dimension(:), allocatable :: selected_coeff_indices"))
+        it.call("select_coeffs_to_calc_spectral_weights", sel, wf, crystal_pc, gur)
+        if sel.value is None:
+            sel_all.append(np.zeros(0, dtype=np.int32))
+            w_all.append(np.full(n_bands, np.nan))
+            dn_all.append(np.full(nener, np.nan))
+            continue
+        sel_all.append(sel.value.copy())
+        it.call("perform_unfolding", delta_N, times, gur, wf, sel.value, egrid)
+        q = uq[f]
+        dn_all.append(q["dn"].copy())
+        # the weights are a local of perform_unfolding: re-run its weight statements (:1335-1345)
+        sw = it.exec_statements(REF / "band_unfolding_routines_mod.f90", 1335, 1351, {
+            "wf": (wf, None), "times": (times, None),
+            "selected_coeff_indices": (sel.value, decl(it, "integer, dimension(:), allocatable :: selected_coeff_indices")),
+            "spectral_weight": (np.zeros(n_bands), decl(it, "real(kind=dp), dimension(:), allocatable :: spectral_weight")),
+            "n_wf_components": (I4(n_spinor), "integer :: n_wf_components"),
+            "i_spinor": (None, "integer :: i_spinor"),
+        })["spectral_weight"].value
+        w_all.append(sw.copy())
+        if q["rhos"] is not None:
+            for r in q["rhos"]:
+                if r["rho"] is None:
+                    continue
+                for v, bi in zip(r["rho"], r["band_indices"]):
+                    rho_rows.append((f, int(r["iener_in_full_pc_egrid"]), int(bi["indices"][0]), int(bi["indices"][1]),
+                                     float(v.real), float(v.imag)))
+        if n_spinor == 2:
+            sigma[f] = q["sigma"]
+            proj[f, :, 0] = q["spin_proj_perp"]
+            proj[f, :, 1] = q["spin_proj_para"]
+    out["folding_G"] = folding_G
+    out["selected"] = np.concatenate(sel_all) if sel_all else np.zeros(0, dtype=np.int32)
+    out["n_selected"] = np.array([len(s) for s in sel_all], dtype=np.int32)
+    out["weights"] = np.array(w_all)
+    out["delta_N"] = np.array(dn_all)
+    out["rho"] = np.array(rho_rows, dtype=R8).reshape(-1, 6)
+    if n_spinor == 2:
+        out["sigma"] = sigma
+        out["spin_proj"] = proj
+    if smearing is not None:
+        dn_s = []
+        for f in range(n_fold):
+            v = F.Var(None, decl(it, "real(kind=dp), dimension(:), allocatable :: delta_n_pckpt"))
+            it.call("get_delta_ns_for_ebs", v, egrid, wf["band_energies"], np.nan_to_num(out["weights"][f]),
+                    smearing_for_delta_function=R8(smearing))
+            dn_s.append(v.value.copy())
+        out["smearing"] = np.array(smearing)
+        out["delta_N_smeared"] = np.array(dn_s)
+    if sf_std is not None:
+        v = F.Var(None, decl(it, "real(kind=dp), dimension(:), allocatable :: sf_at_pckpt"))
+        it.call("calc_spectral_function", v, egrid, wf["band_energies"], np.nan_to_num(out["weights"][0]), R8(sf_std))
+        out["sf_std"] = np.array(sf_std)
+        out["spectral_function"] = v.value.copy()
+    out["perform_unfold"] = np.array(perform_unfold)
+    out["n_spinor"] = np.array(n_spinor)
+    print(f"{name}: n_pw {n_g}, n_fold {n_fold}, selected {out['n_selected'].tolist()}, rho entries {len(rho_rows)}, "
+          f"{it.n_statements} Fortran statements executed", flush=True)
+    return out, it.n_statements
+
+
+def _inner_prod_decl(it):
+    """inner_prod as read_wavefunction declares it (the declaration is looked up in the source so
+    that its kind is the reference's, not a guess)."""
+    for no, s in it.files[str(REF / "io_routines_mod.f90")]:
+        if F.is_declaration(s) and "inner_prod" in s and 1200 < no < 1317:
+            for d in F.parse_declaration(s, it._eval_module_const):
+                if d.name == "inner_prod":
+                    return d
+    raise RuntimeError("declaration of inner_prod not found")
+
+
+tri = [[3.1, 0.0, 0.0], [0.4, 2.9, 0.0], [0.3, -0.2, 3.4]]            # triclinic pc (Angstrom)
+hexa = [[3.16, 0.0, 0.0], [-1.58, 2.7366, 0.0], [0.0, 0.0, 9.0]]
+fcc = [[0.0, 2.7, 2.7], [2.7, 0.0, 2.7], [2.7, 2.7, 0.0]]
+SPECS = [
+    # name, a_pc, M, K (frac SC), ecut, n_spinor, n_bands, pc-kpts (frac SC rec. coords), grid, seed, extras
+    ("triclinic_scalar", tri, [[2, 0, 0], [1, 2, 0], [0, 1, 2]], [0.25, 0.1, -0.3], 58.0, 1, 6,
+     [[0.25, 0.1, -0.3], [1.25, 0.1, -0.3], [0.25, 1.1, 0.7], [-0.75, 2.1, -1.3]], (-3.0, 2.0, 0.25), 11,
+     dict(smearing=0.2, sf_std=0.15)),
+    ("hex_spinor", hexa, [[2, 1, 0], [-1, 1, 0], [0, 0, 1]], [1.0 / 3.0, 0.0, 0.0], 43.0, 2, 5,
+     [[1.0 / 3.0, 0.0, 0.0], [4.0 / 3.0, 1.0, 0.0]], (-2.0, 2.0, 0.5), 12, {}),
+    ("fcc_negative_det", fcc, [[1, -1, 1], [-1, 1, 1], [1, 1, -2]], [0.0, 0.5, 0.5], 56.0, 1, 5,
+     [[0.0, 0.5, 0.5], [1.0, 0.5, 1.5], [0.0, 1.5, 0.5]], (-2.0, 2.0, 0.5), 13, dict(zero_band=2)),
+    ("tolerance_ladder", tri, [[2, 0, 0], [0, 1, 0], [0, 0, 1]], [0.1, 0.2, 0.3], 60.0, 1, 4,
+     [[1.1, 0.2, 0.3]], (-1.0, 1.0, 0.5), 14, dict(folding_noise=1.2e-5)),
+    ("dont_unfold", fcc, [[2, 0, 0], [0, 2, 0], [0, 0, 1]], [0.5, 0.0, 0.0], 40.0, 1, 5,
+     [[0.5, 0.0, 0.0], [1.5, 1.0, 0.0]], (-2.0, 2.0, 0.5), 15, dict(perform_unfold=False)),
+]
+
+
+def main():
+    t0 = time.time()
+    cases = {}
+    n_stmt = 0
+    only = sys.argv[1:]
+    for name, a_pc, M, K, ecut, nsp, nb, pck, grid, seed, extra in SPECS:
+        if only and name not in only:
+            continue
+        out, n = run_case(name, a_pc, M, K, ecut, nsp, nb, pck, grid, seed, **extra)
+        n_stmt += n
+        for k, v in out.items():
+            cases[f"{name}/{k}"] = v
+    if only:
+        return
+    here = Path(__file__).resolve().parent
+    np.savez_compressed(here / "fortran_golden.npz", **cases)
+    manifest = {
+        "source": "the reference's Fortran sources executed by oracle/f90interp.py (an interpreter; no Fortran "
+                  "compiler exists in the build image)",
+        "script": "tests/golden/make_fortran_golden.py",
+        "reference_files_sha256": {f: hashlib.sha256((REF / f).read_bytes()).hexdigest() for f in FILES},
+        "fortran_statements_executed": n_stmt,
+        "cases": [s[0] for s in SPECS],
+        "seconds": round(time.time() - t0, 1),
+    }
+    (here / "fortran_golden.json").write_text(json.dumps(manifest, indent=1) + "\n")
+    print(json.dumps(manifest, indent=1))
+
+
+if __name__ == "__main__":
+    main()

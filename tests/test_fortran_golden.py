@@ -1,0 +1,263 @@
+"""The oracle (C and NumPy restatements) against golden vectors produced by EXECUTING the
+reference's own Fortran sources (tests/golden/make_fortran_golden.py, through the interpreter
+oracle/f90interp.py -- the build image has no Fortran compiler).  This is what pins the
+Fortran-derived half of the oracle; tests/test_gpu_fortran_golden.py holds the CUDA path against
+the same vectors."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import oracle_np as ON
+
+GOLD = Path(__file__).resolve().parent / "golden"
+CASES = json.loads((GOLD / "fortran_golden.json").read_text())["cases"]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD / "fortran_golden.npz")
+
+
+def case(gold, name):
+    pre = name + "/"
+    return {k[len(pre):]: gold[k] for k in gold.files if k.startswith(pre)}
+
+
+def bands_first(c):
+    """(n_spinor, n_pw, n_bands) as the Fortran array is indexed -> the oracle's (n_bands, n_pw, n_spinor)."""
+    return np.ascontiguousarray(np.transpose(c, (2, 1, 0)))
+
+
+def rel(a, b, floor=1e-300):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if np.size(a) else 0.0
+
+
+def folds(g):
+    off = np.concatenate([[0], np.cumsum(g["n_selected"])])
+    return [(f, g["selected"][off[f]:off[f + 1]]) for f in range(len(g["n_selected"]))]
+
+
+def test_manifest_names_the_reference_files():
+    m = json.loads((GOLD / "fortran_golden.json").read_text())
+    assert m["fortran_statements_executed"] > 500000
+    assert set(m["reference_files_sha256"]) >= {"band_unfolding_routines_mod.f90", "io_routines_mod.f90",
+                                               "crystals_mod.f90", "math_mod.f90", "lists_and_seqs_mod.f90"}
+    ref = Path("/root/reference/src")
+    if ref.exists():      # build container only: the fixtures belong to THIS reference tree
+        import hashlib
+        for f, h in m["reference_files_sha256"].items():
+            assert hashlib.sha256((ref / f).read_bytes()).hexdigest() == h, f
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cells_and_commensurability(gold, name):
+    g = case(gold, name)
+    assert np.array_equal(O.rec_latt(g["a_pc"]), g["b_pc"])          # get_rec_latt, bit for bit
+    assert np.array_equal(O.rec_latt(g["A_sc"]), g["B_sc"])
+    assert np.allclose(ON.rec_latt(g["a_pc"]), g["b_pc"], rtol=1e-15, atol=1e-18)
+    ok, M, iM = O.commensurate(g["b_pc"], g["B_sc"])
+    assert ok and bool(g["commensurate"])
+    assert np.array_equal(M, g["M"])                                  # transpose(matmul(b, inv(B)))
+    ok2, M2 = ON.commensurate(g["b_pc"], g["B_sc"])[:2]
+    assert ok2 and np.allclose(M2, g["M"], rtol=0, atol=1e-12)
+    # the supercell really is M a -- up to the sign get_rec_latt drops for a left-handed cell (it divides by
+    # |a1.(a2 x a3)|, crystals_mod.f90:194-197, so such a cell gets -B: the same lattice, and M changes sign)
+    hand = np.sign(np.linalg.det(g["A_sc"]) * np.linalg.det(g["a_pc"]))
+    assert np.allclose(hand * (iM @ g["a_pc"]), g["A_sc"], atol=1e-9)
+    if name == "fcc_negative_det":
+        assert hand == -1.0
+
+
+def test_non_commensurate_cells_are_reported():
+    ok, M, _ = O.commensurate(np.eye(3) * 1.0, np.eye(3) * 0.37)
+    assert not ok
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_plane_wave_list_is_the_readers(gold, name):
+    g = case(gold, name)
+    gf, gc = O.gen_gvecs(g["kpt_frac"], float(g["ecut"]), g["B_sc"])
+    assert np.array_equal(gf, g["g_frac"])                           # count, order and indices
+    assert np.array_equal(gc, g["g_cart"])                           # ig1p*b1 + ig2p*b2 + ig3p*b3, bit for bit
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_renormalisation(gold, name):
+    g = case(gold, name)
+    cin, want = bands_first(g["coeffs_in"]), bands_first(g["coeffs_renormalised"])
+    faithful, norms_sp = O.renormalize(cin, norm_mode=0)
+    # the reference's own arithmetic (sp dot_product, dp scale, rounded to sp): bit for bit
+    assert np.array_equal(faithful.view(np.float32), want.view(np.float32))
+    exact, norms = O.renormalize(cin, norm_mode=1)
+    assert rel(norms_sp, norms, 1e-30) < 5e-6                         # the sp sum is 1e-6..5e-6 off
+    assert np.max(np.abs(exact - want)) < 5e-6 * np.max(np.abs(want))
+    np_faithful = ON.renormalize(cin, norm_mode=0)[0]
+    assert np.array_equal(np_faithful.view(np.float32), want.view(np.float32))
+    if name == "fcc_negative_det":                                    # its band 3 is all zeros: left alone (:1325)
+        assert not np.any(want[2]) and norms[2] == 0.0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_selection(gold, name):
+    g = case(gold, name)
+    Binv = np.linalg.inv(g["B_sc"])
+    iM = np.rint(g["M"]).astype(np.int32)
+    for f, sel in folds(g):
+        got, tol = O.select_coeffs(g["g_cart"], g["folding_G"][f], g["b_pc"])
+        assert np.array_equal(got, sel)                               # float vec_in_latt recipe
+        assert np.array_equal(ON.select_coeffs(g["g_cart"], g["folding_G"][f], g["b_pc"])[0], sel)
+        g0 = np.rint(g["folding_G"][f] @ Binv).astype(np.int32)
+        assert np.array_equal(O.select_coeffs_int(g["g_frac"], g0, iM), sel)   # integer cosets (what K1 does)
+        if name == "tolerance_ladder":
+            assert tol > 1.05e-5                                      # the escalation loop really ran
+        else:
+            assert abs(tol - 1e-5) < 1e-12
+    assert np.all(g["n_selected"] > 0)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_spectral_weights_and_delta_N(gold, name):
+    g = case(gold, name)
+    cren = bands_first(g["coeffs_renormalised"])
+    for f, sel in folds(g):
+        if bool(g["perform_unfold"]):
+            w = O.spectral_weights(cren, sel)
+            assert rel(w, g["weights"][f]) < 1e-15                    # same terms, same order, in dp
+            # the NumPy twin takes abs() with NumPy's vectorised fp32 hypot: one ulp of fp32 per term at most
+            assert rel(ON.spectral_weights(cren, sel), g["weights"][f]) < 2e-7
+        else:
+            assert np.array_equal(g["weights"][f], np.ones_like(g["weights"][f]))   # -dont_unfold (:1346-1351)
+        dn = O.delta_N(g["energy_grid"], g["band_energies"], g["weights"][f])
+        assert np.max(np.abs(dn - g["delta_N"][f])) <= 1e-15 * max(1.0, np.max(g["delta_N"][f]))
+        dn_np = ON.delta_N(g["energy_grid"], g["band_energies"], g["weights"][f])
+        assert np.max(np.abs(dn_np - g["delta_N"][f])) <= 1e-13 * max(1.0, np.max(g["delta_N"][f]))
+    # a band exactly on a bin edge counts half in both bins (lambda = 1/2): the cases plant one
+    e, grid = g["band_energies"], g["energy_grid"]
+    d = grid[1] - grid[0]
+    on_edge = [m for m in range(len(e)) if np.any(e[m] == grid + 0.5 * d)]
+    if name != "tolerance_ladder":
+        assert on_edge
+    for m in on_edge:
+        i = int(np.nonzero(e[m] == grid + 0.5 * d)[0][0])
+        eps = float(np.finfo(np.float64).eps)          # sigma = epsilon(1.0_dp): the box
+        assert O.lam(grid[i], e[m], d, eps) == 0.5 and O.lam(grid[i + 1], e[m], d, eps) == 0.5
+
+
+def test_whole_kpt_entry_point_of_the_oracle(gold):
+    """bo_unfold_kpt (what bench.py's CPU arm times) from the raw inputs, against the golden run."""
+    for name in CASES:
+        g = case(gold, name)
+        if not bool(g["perform_unfold"]):
+            continue
+        w, dn, ns, _ = O.unfold_kpt(bands_first(g["coeffs_in"]), g["g_cart"], g["band_energies"], g["b_pc"],
+                                    g["folding_G"], g["energy_grid"], norm_mode=0)
+        assert np.array_equal(ns, g["n_selected"])
+        assert rel(w, g["weights"]) < 1e-15
+        assert np.max(np.abs(dn - g["delta_N"])) <= 1e-15
+        w1, dn1, _, _ = O.unfold_kpt(bands_first(g["coeffs_in"]), g["g_cart"], g["band_energies"], g["b_pc"],
+                                     g["folding_G"], g["energy_grid"], norm_mode=1)
+        assert rel(w1, g["weights"], 1e-12) < 5e-6 and np.max(np.abs(dn1 - g["delta_N"])) < 5e-6
+
+
+def test_gaussian_smearing_and_spectral_function(gold):
+    g = case(gold, "triclinic_scalar")
+    s = float(g["smearing"])
+    for f in range(len(g["n_selected"])):
+        dn = O.delta_N(g["energy_grid"], g["band_energies"], g["weights"][f], smearing=s)
+        assert np.max(np.abs(dn - g["delta_N_smeared"][f])) <= 1e-15
+        assert np.max(np.abs(ON.delta_N(g["energy_grid"], g["band_energies"], g["weights"][f], smearing=s)
+                             - g["delta_N_smeared"][f])) <= 1e-13
+    sf = O.spectral_function(g["energy_grid"], g["band_energies"], g["weights"][0], float(g["sf_std"]))
+    assert rel(sf, g["spectral_function"], 1e-200) < 1e-14
+    sf_np = ON.spectral_function(g["energy_grid"], g["band_energies"], g["weights"][0], float(g["sf_std"]))
+    assert rel(sf_np, g["spectral_function"], 1e-200) < 1e-12
+
+
+def rho_lists(g, f, sel, oracle_rho):
+    """The (iener, m1, m2, value) entries perform_unfolding appends for fold f (:1372-1428)."""
+    grid, dn = g["energy_grid"], g["delta_N"][f]
+    d = grid[1] - grid[0]
+    out = []
+    for ie in range(len(grid)):
+        if not dn[ie] >= 1e-3:
+            continue
+        rho = oracle_rho(sel, dn[ie], grid[ie], d)
+        for m1 in range(rho.shape[0]):
+            for m2 in range(rho.shape[1]):
+                if np.abs(np.complex64(rho[m1, m2])) < np.float32(1e-5):
+                    continue
+                out.append((ie + 1, m1 + 1, m2 + 1, rho[m1, m2]))
+    return out
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c != "dont_unfold"])
+def test_unfolding_density_operator(gold, name):
+    g = case(gold, name)
+    cren = bands_first(g["coeffs_renormalised"])
+    n = 0
+    for f, sel in folds(g):
+        want = g["rho"][g["rho"][:, 0] == f]
+        got = rho_lists(g, f, sel, lambda s, dn, E, d: O.calc_rho(cren, s, g["band_energies"], dn, E, d))
+        assert [(int(r[1]), int(r[2]), int(r[3])) for r in want] == [t[:3] for t in got]    # which, and in which order
+        for r, t in zip(want, got):
+            v = np.complex64(complex(r[4], r[5]))
+            assert t[3] == v                                           # complex(sp) arithmetic, bit for bit
+        got_np = rho_lists(g, f, sel, lambda s, dn, E, d: ON.calc_rho(cren, s, g["band_energies"], dn, E, d))
+        assert [t[:3] for t in got_np] == [t[:3] for t in got]
+        for a, b in zip(got_np, got):
+            assert abs(complex(a[3]) - complex(b[3])) < 2e-6 * max(1e-5, abs(complex(b[3])))
+        n += len(got)
+    assert n == len(g["rho"]) > 0
+
+
+def test_pauli_vectors_and_spin_projections(gold):
+    g = case(gold, "hex_spinor")
+    from bandup_b200.unfold import calc_spin_projections      # 3-vector algebra the host does (:1266-1286)
+    cren = bands_first(g["coeffs_renormalised"])
+    grid = g["energy_grid"]
+    d = grid[1] - grid[0]
+    nb = cren.shape[0]
+    checked = 0
+    for f, sel in folds(g):
+        rows = g["rho"][g["rho"][:, 0] == f]
+        rhos = {}
+        for r in rows:
+            rhos.setdefault(int(r[1]), np.zeros((nb, nb), dtype=np.complex128))[int(r[2]) - 1, int(r[3]) - 1] = \
+                complex(r[4], r[5])
+        # energies with delta_N >= 1e-3 but no stored element still get a (zero) Pauli vector
+        for ie in np.nonzero(g["delta_N"][f] >= 1e-3)[0]:
+            rhos.setdefault(int(ie) + 1, np.zeros((nb, nb), dtype=np.complex128))
+        vecs = ON.unfolded_pauli_vectors(cren, g["band_energies"], grid, rhos, d)
+        for ie, v in vecs.items():
+            want = g["sigma"][f, ie - 1]
+            assert np.max(np.abs(v - want)) < 5e-6 * max(1.0, np.max(np.abs(want)))   # sp inner products
+            perp, para = calc_spin_projections(want, g["pckpts_cart"][f], np.array([0.0, 0.0, 1.0]),
+                                               origin=np.zeros(3))
+            assert abs(perp - g["spin_proj"][f, ie - 1, 0]) < 1e-12
+            assert abs(para - g["spin_proj"][f, ie - 1, 1]) < 1e-12
+            checked += 1
+        untouched = np.setdiff1d(np.arange(len(grid)), np.array(sorted(vecs)) - 1)
+        assert not np.any(g["sigma"][f, untouched])
+    assert checked >= 3
+
+
+@pytest.mark.skipif(not Path("/root/reference/src").exists(),
+                    reason="the reference sources exist in the build container only")
+@pytest.mark.parametrize("name", ["hex_spinor", "dont_unfold"])
+def test_goldens_regenerate_from_the_reference_sources(gold, name):
+    """Re-executes the reference's Fortran for two of the cases and compares with the committed
+    fixture, array by array, bit by bit (the generator is deterministic)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_fortran_golden", GOLD / "make_fortran_golden.py")
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    s = [x for x in gen.SPECS if x[0] == name][0]
+    out, n_statements = gen.run_case(*s[:10], **s[10])
+    assert n_statements > 50000
+    g = case(gold, name)
+    assert set(out) == set(g)
+    for k, v in out.items():
+        assert np.array_equal(np.asarray(v), g[k], equal_nan=True), k

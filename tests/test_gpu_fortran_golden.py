@@ -1,0 +1,141 @@
+"""The CUDA path, through the C ABI, against golden vectors produced by EXECUTING the reference's
+own Fortran sources (tests/golden/make_fortran_golden.py; interpreter: oracle/f90interp.py).
+No oracle in between: what is compared is the reference's output and the library's.
+Tolerances (BASELINE.json north_star): selected indices and the plane-wave list bit-exact; weights,
+delta_N, rho, Pauli vectors within 1e-6 relative (abs floor 1e-12 / 1e-9 for single-precision
+sums) -- the golden run renormalises with the reference's single-precision dot_product, the
+library with an fp64 norm, which is where the last 1e-7 comes from."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = Path(__file__).resolve().parent / "golden"
+CASES = json.loads((GOLD / "fortran_golden.json").read_text())["cases"]
+REL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD / "fortran_golden.npz")
+
+
+def case(gold, name):
+    pre = name + "/"
+    return {k[len(pre):]: gold[k] for k in gold.files if k.startswith(pre)}
+
+
+def rel(a, b, floor=1e-12):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if np.size(a) else 0.0
+
+
+def configure(u, g, smearing=None):
+    M = u.verify_commens(g["b_pc"], g["B_sc"])
+    assert np.array_equal(M, np.rint(g["M"]).astype(np.int32))       # nint(M) of the reference's M
+    grid = g["energy_grid"]
+    got = u.set_energy_grid(grid[0], grid[-1], grid[1] - grid[0], smearing_for_delta_function=smearing)
+    assert np.array_equal(got, grid)                                  # real_seq, bit for bit
+    return grid
+
+
+def wavefunction(g):
+    from bandup_b200.unfold import PwWavefunction
+    c = np.ascontiguousarray(np.transpose(g["coeffs_in"], (2, 1, 0)))  # (n_bands, n_pw, n_spinor)
+    return PwWavefunction(c, g["g_frac"], g["band_energies"])
+
+
+def selected_lists(g):
+    off = np.concatenate([[0], np.cumsum(g["n_selected"])])
+    return [g["selected"][off[f]:off[f + 1]] for f in range(len(g["n_selected"]))]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_unfold_against_the_reference_run(unfolder, gold, name):
+    g = case(gold, name)
+    configure(unfolder, g)
+    unfolder.set_perform_unfold(bool(g["perform_unfold"]))
+    res = unfolder.perform_unfolding(wavefunction(g), folding_G=g["folding_G"], ikpt=1, want_selected=True)
+    assert np.array_equal(res.n_selected, g["n_selected"])
+    for a, b in zip(res.selected_coeff_indices, selected_lists(g)):
+        assert np.array_equal(a, b)                                    # coset indices, bit-exact
+    assert rel(res.spectral_weight, g["weights"]) <= REL
+    assert rel(res.dN, g["delta_N"]) <= REL
+    if name == "fcc_negative_det":                                     # the all-zero band stays unscaled
+        assert res.band_norms[2] == 0.0 and not np.any(res.spectral_weight[:, 2])
+    if not bool(g["perform_unfold"]):
+        assert np.array_equal(res.spectral_weight, np.ones_like(res.spectral_weight))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_device_plane_wave_list_against_the_reference_reader(unfolder, gold, name):
+    """bandup_gpu_submit_kpt_vasp: raw band records in, plane-wave list regenerated on the device."""
+    g = case(gold, name)
+    configure(unfolder, g)
+    unfolder.set_perform_unfold(bool(g["perform_unfold"]))
+    cin = g["coeffs_in"]                                               # (n_spinor, n_pw, n_bands)
+    nsp, npw, nb = cin.shape
+    nplane = nsp * npw
+    nrecl = 8 * nplane + 40                                            # padded records, as in a real file
+    rec = np.zeros((nb, nrecl), dtype=np.uint8)
+    for b in range(nb):
+        row = np.concatenate([cin[s, :, b] for s in range(nsp)]).astype(np.complex64)
+        rec[b, :8 * nplane] = row.view(np.uint8)
+    got_nsp, got_npw = unfolder.submit_vasp(3, rec, nrecl, nplane, nb, g["kpt_frac"], float(g["ecut"]),
+                                            g["band_energies"], folding_G=g["folding_G"])
+    assert (got_nsp, got_npw) == (nsp, npw)
+    assert np.array_equal(unfolder.fetch_gvecs(3, npw), g["g_frac"])   # count, order, indices
+    res = unfolder.fetch(3, want_selected=True)
+    assert np.array_equal(res.n_selected, g["n_selected"])
+    for a, b in zip(res.selected_coeff_indices, selected_lists(g)):
+        assert np.array_equal(a, b)
+    assert rel(res.spectral_weight, g["weights"]) <= REL
+    assert rel(res.dN, g["delta_N"]) <= REL
+
+
+def test_gaussian_smearing_and_spectral_function_against_the_reference_run(unfolder, gold):
+    g = case(gold, "triclinic_scalar")
+    configure(unfolder, g, smearing=float(g["smearing"]))
+    res = unfolder.perform_unfolding(wavefunction(g), folding_G=g["folding_G"], ikpt=1)
+    assert rel(res.dN, g["delta_N_smeared"]) <= REL
+    sf = unfolder.calc_spectral_function(1, len(g["n_selected"]), float(g["sf_std"]))
+    assert rel(sf[0], g["spectral_function"], 1e-12) <= REL
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c != "dont_unfold"])
+def test_unfolding_density_operator_against_the_reference_run(unfolder, gold, name):
+    g = case(gold, name)
+    configure(unfolder, g)
+    unfolder.perform_unfolding(wavefunction(g), folding_G=g["folding_G"], ikpt=1)
+    ops = unfolder.calc_rho(1)
+    want = g["rho"]
+    # which elements are stored, and in which order (fold, energy, m1, m2): identical
+    assert np.array_equal(ops.fold, want[:, 0].astype(np.int32))
+    assert np.array_equal(ops.iener, want[:, 1].astype(np.int32))
+    assert np.array_equal(ops.m1, want[:, 2].astype(np.int32))
+    assert np.array_equal(ops.m2, want[:, 3].astype(np.int32))
+    ref = (want[:, 4] + 1j * want[:, 5])
+    # rho is a complex(sp) quantity in the reference: 1e-6 of its scale (|rho| <= 1), elements near the
+    # 1e-5 storage threshold included
+    assert np.max(np.abs(ops.rho - ref)) <= 2e-6
+
+
+def test_pauli_vectors_against_the_reference_run(unfolder, gold):
+    from bandup_b200.unfold import calc_spin_projections
+    g = case(gold, "hex_spinor")
+    configure(unfolder, g)
+    unfolder.perform_unfolding(wavefunction(g), folding_G=g["folding_G"], ikpt=1)
+    unfolder.calc_rho(1)
+    n_fold = len(g["n_selected"])
+    sig = unfolder.pauli_vectors(1, n_fold)
+    assert sig.shape == g["sigma"].shape
+    assert np.max(np.abs(sig - g["sigma"])) <= 5e-6                    # sp inner products over all plane waves
+    assert np.any(np.abs(g["sigma"]) > 1e-3)
+    for f in range(n_fold):
+        for ie in np.nonzero(np.any(g["sigma"][f] != 0.0, axis=1))[0]:
+            perp, para = calc_spin_projections(sig[f, ie], g["pckpts_cart"][f], np.array([0.0, 0.0, 1.0]),
+                                               origin=np.zeros(3))
+            assert abs(perp - g["spin_proj"][f, ie, 0]) <= 1e-5
+            assert abs(para - g["spin_proj"][f, ie, 1]) <= 1e-5
