@@ -59,9 +59,12 @@ def struct_array(it, typename, n):
 
 
 def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, grid, seed, *,
-             perform_unfold=True, zero_band=None, folding_noise=0.0, smearing=None, sf_std=None):
+             perform_unfold=True, zero_band=None, folding_noise=0.0, smearing=None, sf_std=None, dir_weights=None):
     """pc_kpts_frac_sc: the pc-kpts to unfold onto, in fractional SC reciprocal coordinates
-    (K + an SC reciprocal lattice vector each)."""
+    (K + an SC reciprocal lattice vector each).  With dir_weights it is a list of such lists, one
+    per needed direction (the symmetry-equivalent copies of ONE pcbz direction, all of them folding
+    onto this SC-kpt here), and get_delta_Ns_for_output averages over them with those weights;
+    rows of the per-pc-kpt outputs are then numbered direction-major."""
     it = interpreter(perform_unfold)
     rng = np.random.default_rng(seed)
     out = {}
@@ -119,40 +122,47 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
     })
     out["coeffs_renormalised"] = wf["pw_coeffs"].copy()
 
-    # ---- geometric unfolding relations for ONE SC-kpt, one direction, n_fold pc-kpts -------
+    # ---- geometric unfolding relations for ONE SC-kpt, one pcbz direction, its needed directions ----
     K_cart = kf @ B_sc
-    n_fold = len(pc_kpts_frac_sc)
+    dirs = pc_kpts_frac_sc if dir_weights is not None else [pc_kpts_frac_sc]
+    n_dirs, n_k = len(dirs), len(dirs[0])
+    n_fold = n_dirs * n_k
     gur = it.new_struct("geom_unfolding_relations_for_each_sckpt")
     gur["list_of_sckpts"] = struct_array(it, "vec3d", 1)
     gur["list_of_sckpts"][0]["coord"][:] = K_cart
     gur["sckpt"] = struct_array(it, "selected_pcbz_directions", 1)
     gur["sckpt"][0]["selec_pcbz_dir"] = struct_array(it, "needed_pcbz_dirs_for_ebs", 1)
-    gur["sckpt"][0]["selec_pcbz_dir"][0]["needed_dir"] = struct_array(it, "list_of_trial_folding_pckpts", 1)
-    pck = struct_array(it, "trial_folding_pckpt", n_fold)
-    gur["sckpt"][0]["selec_pcbz_dir"][0]["needed_dir"][0]["pckpt"] = pck
-    folding_G = np.zeros((n_fold, 3))
-    for f, kk in enumerate(pc_kpts_frac_sc):
-        k_cart = np.asarray(kk, dtype=R8) @ B_sc + folding_noise * rng.standard_normal(3)
-        pck[f]["scoords"][:] = k_cart
-        pck[f]["coords"][:] = k_cart
-        pck[f]["folds"] = LG(True)
-        folding_G[f] = k_cart - K_cart
-    out["pckpts_cart"] = np.array([p["scoords"] for p in pck])
-    out["K_cart"] = K_cart
+    gur["sckpt"][0]["selec_pcbz_dir"][0]["needed_dir"] = struct_array(it, "list_of_trial_folding_pckpts", n_dirs)
     delta_N = it.new_struct("unfoldedquantities")
     delta_N["selec_pcbz_dir"] = struct_array(it, "unfoldedquantities_info_for_needed_pcbz_dirs", 1)
-    delta_N["selec_pcbz_dir"][0]["needed_dir"] = struct_array(it, "list_of_pckpts_for_unfolded_quantities", 1)
-    uq = struct_array(it, "unfolded_quantities_for_given_pckpt", n_fold)
-    delta_N["selec_pcbz_dir"][0]["needed_dir"][0]["pckpt"] = uq
+    delta_N["selec_pcbz_dir"][0]["needed_dir"] = struct_array(it, "list_of_pckpts_for_unfolded_quantities", n_dirs)
+    folding_G = np.zeros((n_fold, 3))
+    pck_all, uq_all = [], []
+    for d, kks in enumerate(dirs):
+        pck = struct_array(it, "trial_folding_pckpt", n_k)
+        gur["sckpt"][0]["selec_pcbz_dir"][0]["needed_dir"][d]["pckpt"] = pck
+        uq = struct_array(it, "unfolded_quantities_for_given_pckpt", n_k)
+        delta_N["selec_pcbz_dir"][0]["needed_dir"][d]["pckpt"] = uq
+        for f, kk in enumerate(kks):
+            k_cart = np.asarray(kk, dtype=R8) @ B_sc + folding_noise * rng.standard_normal(3)
+            pck[f]["scoords"][:] = k_cart
+            pck[f]["coords"][:] = k_cart
+            pck[f]["folds"] = LG(True)
+            folding_G[d * n_k + f] = k_cart - K_cart
+            pck_all.append(pck[f])
+            uq_all.append(uq[f])
+    out["pckpts_cart"] = np.array([p["scoords"] for p in pck_all])
+    out["K_cart"] = K_cart
     times = it.new_struct("timekeeping")
     nener = len(egrid)
     sel_all, w_all, dn_all = [], [], []
-    rho_rows = []          # (fold, iener, m1, m2, re, im), 1-based like the reference
+    rho_rows = []          # (row, iener, m1, m2, re, im), 1-based like the reference except the row
     sigma = np.zeros((n_fold, nener, 3))
     proj = np.zeros((n_fold, nener, 2))
     for f in range(n_fold):
         ci = gur["current_index"]
-        ci["i_sckpt"], ci["i_selec_pcbz_dir"], ci["i_needed_dirs"], ci["ipc_kpt"] = I4(1), I4(1), I4(1), I4(f + 1)
+        ci["i_sckpt"], ci["i_selec_pcbz_dir"] = I4(1), I4(1)
+        ci["i_needed_dirs"], ci["ipc_kpt"] = I4(f // n_k + 1), I4(f % n_k + 1)
         sel = F.Var(None, decl(it, "integer, dimension(:), allocatable :: selected_coeff_indices"))
         it.call("select_coeffs_to_calc_spectral_weights", sel, wf, crystal_pc, gur)
         if sel.value is None:
@@ -162,7 +172,7 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
             continue
         sel_all.append(sel.value.copy())
         it.call("perform_unfolding", delta_N, times, gur, wf, sel.value, egrid)
-        q = uq[f]
+        q = uq_all[f]
         dn_all.append(q["dn"].copy())
         # the weights are a local of perform_unfolding: re-run its weight statements (:1335-1345)
         sw = it.exec_statements(REF / "band_unfolding_routines_mod.f90", 1335, 1351, {
@@ -173,13 +183,7 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
             "i_spinor": (None, "integer :: i_spinor"),
         })["spectral_weight"].value
         w_all.append(sw.copy())
-        if q["rhos"] is not None:
-            for r in q["rhos"]:
-                if r["rho"] is None:
-                    continue
-                for v, bi in zip(r["rho"], r["band_indices"]):
-                    rho_rows.append((f, int(r["iener_in_full_pc_egrid"]), int(bi["indices"][0]), int(bi["indices"][1]),
-                                     float(v.real), float(v.imag)))
+        rho_rows += rho_entries(f, q["rhos"])
         if n_spinor == 2:
             sigma[f] = q["sigma"]
             proj[f, :, 0] = q["spin_proj_perp"]
@@ -193,6 +197,29 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
     if n_spinor == 2:
         out["sigma"] = sigma
         out["spin_proj"] = proj
+    if dir_weights is not None:
+        # ---- get_delta_Ns_for_output: the average over the needed directions (:789-1043) ----------
+        all_dirs = struct_array(it, "irr_bz_directions", 1)
+        all_dirs[0]["irr_dir"] = struct_array(it, "bz_direction", n_dirs)
+        for d, wgt in enumerate(dir_weights):
+            all_dirs[0]["irr_dir"][d]["weight"] = R8(wgt)
+        only_sel = it.new_struct("unfoldedquantitiesforoutput")
+        avgd = it.new_struct("unfoldedquantitiesforoutput")
+        it.call("get_delta_ns_for_output", only_sel, avgd, delta_N, all_dirs, gur["sckpt"][0], times)
+        pk = avgd["pcbz_dir"][0]["pckpt"]
+        out["dir_weights"] = np.asarray(dir_weights, dtype=R8)
+        out["n_dirs"] = np.array(n_dirs)
+        out["avg_delta_N"] = np.array([p["dn"] for p in pk])
+        avg_rows = []
+        for k, p in enumerate(pk):
+            avg_rows += rho_entries(k, p["rhos"], by_position=True)
+        out["avg_rho"] = np.array(avg_rows, dtype=R8).reshape(-1, 6)
+        if n_spinor == 2:
+            out["avg_sigma"] = np.array([p["sigma"] for p in pk])
+            out["avg_spin_proj"] = np.array([np.stack([p["spin_proj_perp"], p["spin_proj_para"]], axis=1) for p in pk])
+        # what "only the selected directions" keeps is the first needed direction, unchanged
+        assert all(np.array_equal(a["dn"], b["dn"]) for a, b in
+                   zip(only_sel["pcbz_dir"][0]["pckpt"], delta_N["selec_pcbz_dir"][0]["needed_dir"][0]["pckpt"]))
     if smearing is not None:
         dn_s = []
         for f in range(n_fold):
@@ -212,6 +239,24 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
     print(f"{name}: n_pw {n_g}, n_fold {n_fold}, selected {out['n_selected'].tolist()}, rho entries {len(rho_rows)}, "
           f"{it.n_statements} Fortran statements executed", flush=True)
     return out, it.n_statements
+
+
+def rho_entries(row, rhos, by_position=False):
+    """(row, iener, m1, m2, re, im) of the stored elements of an array of UnfoldDensityOpContainer, in the
+    order the reference appended them.  by_position: the averaged operators sit at index iener of an
+    array over the whole energy grid (:868-871); unused slots have no elements."""
+    rows = []
+    if rhos is None:
+        return rows
+    for pos, r in enumerate(rhos):
+        if r["rho"] is None:
+            continue
+        ie = int(r["iener_in_full_pc_egrid"])
+        if by_position:
+            assert ie == pos + 1
+        for v, bi in zip(r["rho"], r["band_indices"]):
+            rows.append((row, ie, int(bi["indices"][0]), int(bi["indices"][1]), float(v.real), float(v.imag)))
+    return rows
 
 
 def _inner_prod_decl(it):
@@ -241,6 +286,13 @@ SPECS = [
      [[1.1, 0.2, 0.3]], (-1.0, 1.0, 0.5), 14, dict(folding_noise=1.2e-5)),
     ("dont_unfold", fcc, [[2, 0, 0], [0, 2, 0], [0, 0, 1]], [0.5, 0.0, 0.0], 40.0, 1, 5,
      [[0.5, 0.0, 0.0], [1.5, 1.0, 0.0]], (-2.0, 2.0, 0.5), 15, dict(perform_unfold=False)),
+    # three needed directions x two pc-kpts each, averaged by get_delta_Ns_for_output
+    ("symm_avg_scalar", tri, [[2, 0, 0], [1, 2, 0], [0, 1, 2]], [0.2, -0.1, 0.4], 45.0, 1, 6,
+     [[[0.2, -0.1, 0.4], [1.2, -0.1, 0.4]], [[0.2, 0.9, 1.4], [-0.8, 1.9, 0.4]], [[1.2, 0.9, 0.4], [0.2, -0.1, 1.4]]],
+     (-3.0, 2.0, 0.5), 16, dict(dir_weights=[0.5, 0.3, 0.2])),
+    ("symm_avg_spinor", hexa, [[2, 1, 0], [-1, 1, 0], [0, 0, 1]], [0.0, 0.25, 0.0], 36.0, 2, 5,
+     [[[0.0, 0.25, 0.0], [1.0, 0.25, 0.0]], [[1.0, 1.25, 0.0], [0.0, 1.25, 1.0]]],
+     (-2.0, 2.0, 0.5), 17, dict(dir_weights=[0.75, 0.25])),
 ]
 
 

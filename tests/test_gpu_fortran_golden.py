@@ -139,3 +139,58 @@ def test_pauli_vectors_against_the_reference_run(unfolder, gold):
                                                origin=np.zeros(3))
             assert abs(perp - g["spin_proj"][f, ie, 0]) <= 1e-5
             assert abs(para - g["spin_proj"][f, ie, 1]) <= 1e-5
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c.startswith("symm_avg")])
+def test_symmetry_average_against_the_reference_run(unfolder, gold, name):
+    """K8/K9 (bandup_gpu_symm_average, bandup_gpu_symm_average_rho) fed with the reference's own
+    per-direction delta_N / rho / spin columns, against what get_delta_Ns_for_output made of them."""
+    from bandup_b200.unfold import UnfoldDensityOps
+    g = case(gold, name)
+    n_dirs = int(g["n_dirs"])
+    n_k = len(g["n_selected"]) // n_dirs
+    w = g["dir_weights"]
+    avg = unfolder.symm_average(w, g["delta_N"].reshape(n_dirs, n_k, -1))
+    assert np.array_equal(avg, g["avg_delta_N"])                       # bit for bit
+    ops = []
+    for d in range(n_dirs):
+        r = g["rho"][(g["rho"][:, 0] >= d * n_k) & (g["rho"][:, 0] < (d + 1) * n_k)]
+        ops.append(UnfoldDensityOps(0, (r[:, 0] - d * n_k).astype(np.int32), r[:, 1].astype(np.int32),
+                                    r[:, 2].astype(np.int32), r[:, 3].astype(np.int32),
+                                    (r[:, 4] + 1j * r[:, 5]).astype(np.complex64)))
+    res = unfolder.symm_average_rho(w, ops, avg, g["weights"].shape[1])
+    want = g["avg_rho"]
+    for got, col in zip((res.fold, res.iener, res.m1, res.m2), range(4)):
+        assert np.array_equal(got, want[:, col].astype(np.int32))
+    ref = (want[:, 4] + 1j * want[:, 5]).astype(np.complex64)
+    assert np.array_equal(res.rho.view(np.uint32), ref.view(np.uint32))  # complex(sp), bit for bit
+    if "avg_sigma" in g:
+        sig = g["sigma"].reshape((n_dirs, n_k) + g["sigma"].shape[1:])
+        assert np.array_equal(unfolder.symm_average(w, sig), g["avg_sigma"])
+        pr = g["spin_proj"].reshape((n_dirs, n_k) + g["spin_proj"].shape[1:])
+        assert np.array_equal(unfolder.symm_average(w, pr), g["avg_spin_proj"])
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c.startswith("symm_avg")])
+def test_unfold_then_average_end_to_end(unfolder, gold, name):
+    """The whole post-read flow on the device for one SC-kpt: unfold every (direction, pc-kpt), rho,
+    then the averages -- against the reference's averaged output."""
+    from bandup_b200.unfold import UnfoldDensityOps
+    g = case(gold, name)
+    configure(unfolder, g)
+    n_dirs = int(g["n_dirs"])
+    n_fold = len(g["n_selected"])
+    n_k = n_fold // n_dirs
+    res = unfolder.perform_unfolding(wavefunction(g), folding_G=g["folding_G"], ikpt=1)
+    rho = unfolder.calc_rho(1)
+    w = g["dir_weights"]
+    avg = unfolder.symm_average(w, res.dN.reshape(n_dirs, n_k, -1))
+    assert rel(avg, g["avg_delta_N"]) <= REL
+    ops = []
+    for d in range(n_dirs):
+        s = (rho.fold >= d * n_k) & (rho.fold < (d + 1) * n_k)
+        ops.append(UnfoldDensityOps(0, rho.fold[s] - d * n_k, rho.iener[s], rho.m1[s], rho.m2[s], rho.rho[s]))
+    out = unfolder.symm_average_rho(w, ops, avg, g["weights"].shape[1])
+    want = g["avg_rho"]
+    assert np.array_equal(np.stack([out.fold, out.iener, out.m1, out.m2], axis=1), want[:, :4].astype(np.int32))
+    assert np.max(np.abs(out.rho - (want[:, 4] + 1j * want[:, 5]))) <= 2e-6
