@@ -7,14 +7,29 @@
  * may load this library; the product path (bandup_b200/, libbandup_gpu.so)
  * never does.
  *
- * PARITY STATUS: **parity unpinned** for every function in this file.  The
- * reference ships no tests, golden vectors or fixtures for this path
- *  and its Fortran cannot be compiled in this image
- * (no Fortran front end).  What pins this file instead: an independent NumPy
- * restatement (oracle/oracle_np.py) must agree with it, and analytic
- * invariants (sum over cosets of P = 1, perfect-supercell weights in {0,1},
- * float lattice test == integer coset test) are asserted in tests/.
- * The Python half of the projected variant IS pinned, see oracle/oracle_np.py.
+ * PARITY STATUS: pinned against the reference's own Fortran, EXECUTED BY AN
+ * INTERPRETER, not compiled.  The reference ships no tests, golden vectors or
+ * fixtures for this path and this image has no
+ * Fortran front end, so oracle/_ref cannot be built.  Instead
+ * oracle/f90interp.py interprets the reference's source files where they lie
+ * (/root/reference/src: get_rec_latt, check_if_pc_and_SC_are_commensurate,
+ * populate_wf_with_G_vec_coords, the renormalisation block of
+ * read_wavefunction, select_coeffs_to_calc_spectral_weights, perform_unfolding
+ * with everything below it, get_delta_Ns_for_EBS with a smearing,
+ * calc_spectral_function, get_delta_Ns_for_output) on seeded inputs;
+ * tests/golden/make_fortran_golden.py is the generating script and
+ * tests/golden/fortran_golden.npz the committed result (7 cases, 1.6 M Fortran
+ * statements).  tests/test_fortran_golden.py holds every function of this file
+ * against those vectors: plane-wave list, renormalised coefficients, selected
+ * indices, rho and the symmetry averages bit for bit; weights, delta_N and the
+ * spectral function to 1e-15.  What that does NOT pin: code generation of a
+ * particular Fortran compiler (the interpreter evaluates every operation in the
+ * kind Fortran prescribes, without reassociation or fused multiply-add -- what
+ * gfortran -O2 does on baseline x86-64, src/Makefile:23-30), the order OpenMP
+ * threads append selected indices in (ascending here), file I/O.
+ * Also asserted in tests/: agreement with an independent NumPy restatement
+ * (oracle/oracle_np.py) and analytic invariants (sum over cosets of P = 1,
+ * perfect-supercell weights in {0,1}, float lattice test == integer coset test).
  *
  * Conventions: 3x3 matrices are row-major with ROW i = vector i, i.e.
  * m[3*i+j] == fortran_matrix(i+1, j+1).  All reference citations are relative

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  May be imported by tests/, __graft_entry__.smoke()
 and bench.py's cpu_baseline / --impl reference legs; never by bandup_b200.
-Parity status: **parity unpinned** (see the header of bandup_oracle.c).
+Parity status: pinned against the reference's Fortran as executed by oracle/f90interp.py
+(tests/golden/fortran_golden.npz, tests/test_fortran_golden.py); see the header of bandup_oracle.c.
 """
 from __future__ import annotations
 

@@ -1,6 +1,7 @@
 """CPU tests of the oracle itself: C restatement vs the independent NumPy restatement,
 plus the analytic invariants that stand in for the reference's missing test-suite.
-(The reference has no golden vectors for the Fortran path: parity unpinned)"""
+(The reference ships no golden vectors for the Fortran path; tests/test_fortran_golden.py holds
+the oracle against vectors made by executing the reference's sources with oracle/f90interp.py.)"""
 import math
 
 import numpy as np
