@@ -40,8 +40,6 @@ int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t* n_energie
                          int64_t* n_entries) {
   Ctx* c = get(handle);
   if (!c) return fail(nullptr, BANDUP_GPU_ERR_BAD_HANDLE, "bad handle");
-  if (!c->perform_unfold)
-    return fail(c, BANDUP_GPU_ERR_INVALID_ARG, "rho with -dont_unfold is not offered by the GPU path");
   if (!(min_dN >= kEpsDp))
     return fail(c, BANDUP_GPU_ERR_DELTA_N_ZERO,
                 "ERROR (calc_rho): delta_N = 0. (min_dN must be >= epsilon(1.0_dp); the reference uses 1e-3)");
@@ -65,7 +63,7 @@ int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t* n_energie
     KernelScope k(c, BANDUP_GPU_K_RHO, s);
     // perform_unfolding calls calc_rho WITHOUT std_dev (:1404-1407): lambda is the box
     // (sigma = epsilon) here whatever smearing the delta_N grid was given
-    launch_rho_plan(d_grid, nener, kEpsDp, d_ener, nb, nu, fl->d_dn_unique, min_dN, cap,
+    launch_rho_plan(d_grid, nener, kEpsDp, d_ener, nb, nu, fl->d_dn_unique, min_dN, cap, c->perform_unfold,
                     static_cast<int*>(fl->pair_count.p), static_cast<long long*>(fl->pair_off.p),
                     static_cast<int*>(fl->overflow.p), s);
     c->launches++;  // plan + scan
@@ -112,7 +110,7 @@ int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t* n_energie
     }
     {
       KernelScope k(c, BANDUP_GPU_K_RHO, s);
-      launch_rho_pairs(d_grid, nener, kEpsDp, d_ener, nb, nu, fl->d_dn_unique, cap, fl->n_spinor,
+      launch_rho_pairs(d_grid, nener, kEpsDp, d_ener, nb, nu, fl->d_dn_unique, cap, fl->n_spinor, c->perform_unfold,
                        static_cast<const long long*>(fl->sel_off.p), fl->csel.p,
                        static_cast<const int*>(fl->pair_count.p),
                        static_cast<const long long*>(fl->pair_off.p), static_cast<RhoPair*>(fl->pairs.p), s);

@@ -163,7 +163,7 @@ struct RhoPair {  // one upper-triangle element of an unfolding-density operator
 int rho_active_cap(int n_bands);
 // K4a + scan: pair_count[f*nener + ie], pair_off = exclusive prefix (n+1 entries).
 void launch_rho_plan(const double* d_grid, int nener, double sigma, const double* d_band_energies,
-                     int n_bands, int n_fold, const double* d_dN, double min_dN, int cap,
+                     int n_bands, int n_fold, const double* d_dN, double min_dN, int cap, bool perform_unfold,
                      int* d_pair_count, long long* d_pair_off, int* d_overflow, cudaStream_t s);
 void launch_scan(const int* d_in, int n, long long* d_out, cudaStream_t s);
 void launch_rho_gather(const void* d_coeffs, long long stride_bytes, int n_pw, int n_spinor,
@@ -171,7 +171,7 @@ void launch_rho_gather(const void* d_coeffs, long long stride_bytes, int n_pw, i
                        const long long* d_sel_off, const double* d_norms, void* d_csel, bool dp,
                        cudaStream_t s);
 void launch_rho_pairs(const double* d_grid, int nener, double sigma, const double* d_band_energies,
-                      int n_bands, int n_fold, const double* d_dN, int cap, int n_spinor,
+                      int n_bands, int n_fold, const double* d_dN, int cap, int n_spinor, bool perform_unfold,
                       const long long* d_sel_off, const void* d_csel, const int* d_pair_count,
                       const long long* d_pair_off, RhoPair* d_pairs, cudaStream_t s);
 void launch_orb_contrib(int n_bands, int n_ao, const void* d_dual, const void* d_proj,

@@ -80,9 +80,10 @@ __device__ int build_active(const double* __restrict__ band_energies, int n_band
 }
 
 // number of b >= a with (lam_a * lam_b) / dN >= 1e-5, for row a
+// perform_unfold == 0: the -dont_unfold branch of calc_rho (:1136-1154), whose m1 loop takes ALL bands
 __device__ __forceinline__ int row_pairs(const ActiveList& act, int n_act, int a, double dN,
-                                         int n_bands) {
-  if (act.band[a] >= n_bands - 1) return 0;  // `do m1=1, n_SC_bands - 1` (:1096)
+                                         int n_bands, int perform_unfold) {
+  if (perform_unfold && act.band[a] >= n_bands - 1) return 0;  // `do m1=1, n_SC_bands - 1` (:1096)
   int c = 0;
   for (int b = a; b < n_act; ++b)
     if (__ddiv_rn(__dmul_rn(act.lam[a], act.lam[b]), dN) >= kMinPrefactor) ++c;
@@ -92,7 +93,7 @@ __device__ __forceinline__ int row_pairs(const ActiveList& act, int n_act, int a
 __global__ void __launch_bounds__(256)
 k4_rho_plan(const double* __restrict__ grid, int nener, double sigma,
             const double* __restrict__ band_energies, int n_bands,
-            const double* __restrict__ dN_all, double min_dN, int cap,
+            const double* __restrict__ dN_all, double min_dN, int cap, int perform_unfold,
             int* __restrict__ pair_count /*[n_fold][nener]*/, int* __restrict__ overflow) {
   extern __shared__ unsigned char smem[];
   ActiveList act;
@@ -120,7 +121,7 @@ k4_rho_plan(const double* __restrict__ grid, int nener, double sigma,
   if (threadIdx.x == 0) s_total = 0;
   __syncthreads();
   int mine = 0;
-  for (int a = threadIdx.x; a < n_act; a += blockDim.x) mine += row_pairs(act, n_act, a, dN, n_bands);
+  for (int a = threadIdx.x; a < n_act; a += blockDim.x) mine += row_pairs(act, n_act, a, dN, n_bands, perform_unfold);
   if (mine) atomicAdd(&s_total, mine);  // integer sum: order-independent
   __syncthreads();
   if (threadIdx.x == 0) pair_count[blockIdx.x] = s_total;
@@ -197,7 +198,7 @@ k4_gather(const char* __restrict__ coeffs, long long stride_bytes, int n_pw, int
 __global__ void __launch_bounds__(256)
 k4_rho_pairs(const double* __restrict__ grid, int nener, double sigma,
              const double* __restrict__ band_energies, int n_bands,
-             const double* __restrict__ dN_all, int cap, int n_spinor,
+             const double* __restrict__ dN_all, int cap, int n_spinor, int perform_unfold,
              const long long* __restrict__ sel_off, const float2* __restrict__ csel,
              const int* __restrict__ pair_count, const long long* __restrict__ pair_off,
              RhoPair* __restrict__ pairs) {
@@ -214,7 +215,8 @@ k4_rho_pairs(const double* __restrict__ grid, int nener, double sigma,
   const double half_de = __dmul_rn(0.5, delta_e);
   const double sqrt2_sigma = __dmul_rn(sqrt(2.0), sigma);
   const int n_act = build_active(band_energies, n_bands, grid[ie], half_de, sqrt2_sigma, cap, act, s_scratch);
-  for (int a = threadIdx.x; a < n_act; a += blockDim.x) row_off[a + 1] = row_pairs(act, n_act, a, dN, n_bands);
+  for (int a = threadIdx.x; a < n_act; a += blockDim.x)
+    row_off[a + 1] = row_pairs(act, n_act, a, dN, n_bands, perform_unfold);
   __syncthreads();
   if (threadIdx.x == 0) {
     row_off[0] = 0;
@@ -236,6 +238,22 @@ k4_rho_pairs(const double* __restrict__ grid, int nener, double sigma,
       const double pref = __ddiv_rn(__dmul_rn(act.lam[a], act.lam[b]), dN);
       if (pref < kMinPrefactor) continue;
       const int m2 = act.band[b];
+      if (!perform_unfold) {
+        // -dont_unfold (:1136-1154): rho(m1,m2) = 1 for every coupled pair, then the whole matrix is
+        // divided by the number of bands with lambda >= 1e-5 -- the active list; complex(sp)/real(dp)
+        // is formed in dp and stored to sp.  With the box lambda the full matrix is symmetric, so
+        // the upper triangle kept here expands to it.
+        if (lane == 0) {
+          RhoPair p;
+          p.m1 = m1;
+          p.m2 = m2;
+          p.re = (float)(1.0 / (double)n_act);
+          p.im = 0.0f;
+          out[k] = p;
+        }
+        ++k;
+        continue;
+      }
       const float2* c2 = base + (long long)m2 * len;
       // dot_product(a, b) = sum conj(a) * b, accumulated in fp64 (the reference accumulates in
       // complex(sp); the fp64 sum is the better-conditioned of the two)
@@ -419,14 +437,14 @@ int rho_active_cap(int n_bands) {
 }
 
 void launch_rho_plan(const double* d_grid, int nener, double sigma, const double* d_band_energies,
-                     int n_bands, int n_fold, const double* d_dN, double min_dN, int cap,
+                     int n_bands, int n_fold, const double* d_dN, double min_dN, int cap, bool perform_unfold,
                      int* d_pair_count, long long* d_pair_off, int* d_overflow, cudaStream_t s) {
   const int n = n_fold * nener;
   if (n <= 0) return;
   const size_t smem = rho_plan_smem(cap);
   cudaFuncSetAttribute(k4_rho_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k4_rho_plan<<<n, 256, smem, s>>>(d_grid, nener, sigma, d_band_energies, n_bands, d_dN, min_dN, cap,
-                                   d_pair_count, d_overflow);
+                                   perform_unfold ? 1 : 0, d_pair_count, d_overflow);
   k4_scan<<<1, 1024, 0, s>>>(d_pair_count, n, d_pair_off);
 }
 
@@ -453,7 +471,7 @@ void launch_rho_gather(const void* d_coeffs, long long stride_bytes, int n_pw, i
 }
 
 void launch_rho_pairs(const double* d_grid, int nener, double sigma, const double* d_band_energies,
-                      int n_bands, int n_fold, const double* d_dN, int cap, int n_spinor,
+                      int n_bands, int n_fold, const double* d_dN, int cap, int n_spinor, bool perform_unfold,
                       const long long* d_sel_off, const void* d_csel, const int* d_pair_count,
                       const long long* d_pair_off, RhoPair* d_pairs, cudaStream_t s) {
   const int n = n_fold * nener;
@@ -461,7 +479,7 @@ void launch_rho_pairs(const double* d_grid, int nener, double sigma, const doubl
   const size_t smem = rho_pairs_smem(cap);
   cudaFuncSetAttribute(k4_rho_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k4_rho_pairs<<<n, 256, smem, s>>>(d_grid, nener, sigma, d_band_energies, n_bands, d_dN, cap, n_spinor,
-                                    d_sel_off, static_cast<const float2*>(d_csel), d_pair_count,
+                                    perform_unfold ? 1 : 0, d_sel_off, static_cast<const float2*>(d_csel), d_pair_count,
                                     d_pair_off, d_pairs);
 }
 

@@ -226,7 +226,9 @@ int bandup_gpu_spectral_function(int handle, int ikpt, double std_dev, double *s
  *   rho(m1,m2) = lambda(m1) lambda(m2) / dN * sum_spinor sum_{G in sel} conj(C_m1) C_m2
  * between the bands with lambda >= 1e-5 (m1 = 1..n_bands-1 only, prefactor >= 1e-5); lambda is
  * the box (sigma = epsilon) whatever smearing the grid was given, because perform_unfolding
- * calls calc_rho without std_dev (:1404-1407).
+ * calls calc_rho without std_dev (:1404-1407).  After bandup_gpu_set_perform_unfold(0) it is the
+ * other branch of calc_rho (:1136-1154): rho(m1,m2) = 1 / (number of bands with lambda >= 1e-5)
+ * for every coupled pair, m1 over ALL bands.
  * It blocks until done and returns
  *   n_energies  number of (pc-kpt, energy) operators with at least one coupled band pair
  *   n_entries   number of stored elements, |rho| >= 1e-5, both triangles (:1416-1425)

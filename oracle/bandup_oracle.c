@@ -493,6 +493,35 @@ int bo_calc_rho(const float complex *coeffs, int n_spinor, int64_t n_pw,
   return 0;
 }
 
+/* ---- band_unfolding_routines_mod.f90:1136-1154  calc_rho, -dont_unfold branch --
+ * rho(m1,m2) = 1 where lambda(m1) >= 1e-5 and lambda(m1) lambda(m2) / delta_N >= 1e-5 (m1 and m2
+ * over ALL bands), then rho = rho / real(n_picked_bands, dp): complex(sp) / real(dp) formed in dp
+ * and stored to sp. */
+int bo_calc_rho_dont_unfold(int n_bands, const double *sc_ener, double delta_N, double pc_ener,
+                            double delta_e, double sigma, float complex *rho) {
+  if (delta_N < BO_EPS_DP) return 1;
+  if (sigma <= 0.0) sigma = BO_EPS_DP;
+  const double min_pref = 1e-5;
+  memset(rho, 0, sizeof(float complex) * (size_t)n_bands * (size_t)n_bands);
+  int n_picked = 0;
+  for (int m1 = 0; m1 < n_bands; ++m1) {
+    double l1 = bo_lambda(pc_ener, sc_ener[m1], delta_e, sigma);
+    if (l1 < min_pref) continue;
+    ++n_picked;
+    for (int m2 = 0; m2 < n_bands; ++m2) {
+      double l2 = bo_lambda(pc_ener, sc_ener[m2], delta_e, sigma);
+      if ((l1 * l2) / delta_N < min_pref) continue;
+      rho[(int64_t)m1 * n_bands + m2] = 1.0f;
+    }
+  }
+  if (n_picked > 0)
+    for (int64_t i = 0; i < (int64_t)n_bands * n_bands; ++i) {
+      double re = (double)crealf(rho[i]) / (double)n_picked, im = (double)cimagf(rho[i]) / (double)n_picked;
+      rho[i] = (float)re + (float)im * I;
+    }
+  return 0;
+}
+
 /* ---- band_unfolding_routines_mod.f90:789-855, :975-1043  symmetry average --
  * avrgd = 0; do i_needed_dirs: avrgd = avrgd + weight * x(i_needed_dirs) -- dp, direction order.
  * in [n_dirs][n_values], out [n_values]. */

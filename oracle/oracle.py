@@ -212,6 +212,20 @@ def calc_rho(coeffs, sel, sc_ener, delta_N_val, pc_ener, delta_e, sigma=0.0):
     return rho
 
 
+def calc_rho_dont_unfold(sc_ener, delta_N_val, pc_ener, delta_e, sigma=0.0):
+    """The -dont_unfold branch of calc_rho (band_unfolding_routines_mod.f90:1136-1154)."""
+    e = _f64(sc_ener)
+    nb = e.shape[0]
+    rho = np.zeros((nb, nb), dtype=np.complex64)
+    L = lib()
+    L.bo_calc_rho_dont_unfold.restype = C.c_int
+    L.bo_calc_rho_dont_unfold.argtypes = [C.c_int, _f64p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    if L.bo_calc_rho_dont_unfold(nb, _p(e, _f64p), float(delta_N_val), float(pc_ener), float(delta_e), float(sigma),
+                                 rho.ctypes.data):
+        raise ZeroDivisionError("calc_rho: delta_N = 0")
+    return rho
+
+
 def unfold_kpt(coeffs, G_cart, sc_ener, b_pc, folding_G, energies, smearing=0.0, norm_mode=1,
                in_place=False):
     """The reference's per-SC-kpt sequence.  Returns weights, dN, n_selected, times[3]."""

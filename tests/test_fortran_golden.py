@@ -193,19 +193,25 @@ def rho_lists(g, f, sel, oracle_rho):
     return out
 
 
-@pytest.mark.parametrize("name", [c for c in CASES if c != "dont_unfold"])
+@pytest.mark.parametrize("name", CASES)
 def test_unfolding_density_operator(gold, name):
     g = case(gold, name)
     cren = bands_first(g["coeffs_renormalised"])
     n = 0
+    unfold = bool(g["perform_unfold"])
     for f, sel in folds(g):
         want = g["rho"][g["rho"][:, 0] == f]
-        got = rho_lists(g, f, sel, lambda s, dn, E, d: O.calc_rho(cren, s, g["band_energies"], dn, E, d))
+        if unfold:
+            c_rho = lambda s, dn, E, d: O.calc_rho(cren, s, g["band_energies"], dn, E, d)
+        else:                                                          # calc_rho's other branch (:1136-1154)
+            c_rho = lambda s, dn, E, d: O.calc_rho_dont_unfold(g["band_energies"], dn, E, d)
+        got = rho_lists(g, f, sel, c_rho)
         assert [(int(r[1]), int(r[2]), int(r[3])) for r in want] == [t[:3] for t in got]    # which, and in which order
         for r, t in zip(want, got):
             v = np.complex64(complex(r[4], r[5]))
             assert t[3] == v                                           # complex(sp) arithmetic, bit for bit
-        got_np = rho_lists(g, f, sel, lambda s, dn, E, d: ON.calc_rho(cren, s, g["band_energies"], dn, E, d))
+        got_np = rho_lists(g, f, sel, lambda s, dn, E, d: ON.calc_rho(cren, s, g["band_energies"], dn, E, d,
+                                                                      perform_unfold=unfold))
         assert [t[:3] for t in got_np] == [t[:3] for t in got]
         for a, b in zip(got_np, got):
             # the NumPy twin forms the inner products in fp64: off by the reference's own sp rounding,

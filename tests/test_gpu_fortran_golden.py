@@ -104,10 +104,11 @@ def test_gaussian_smearing_and_spectral_function_against_the_reference_run(unfol
     assert rel(sf[0], g["spectral_function"], 1e-12) <= REL
 
 
-@pytest.mark.parametrize("name", [c for c in CASES if c != "dont_unfold"])
+@pytest.mark.parametrize("name", CASES)
 def test_unfolding_density_operator_against_the_reference_run(unfolder, gold, name):
     g = case(gold, name)
     configure(unfolder, g)
+    unfolder.set_perform_unfold(bool(g["perform_unfold"]))             # False: calc_rho's other branch
     unfolder.perform_unfolding(wavefunction(g), folding_G=g["folding_G"], ikpt=1)
     ops = unfolder.calc_rho(1)
     want = g["rho"]
