@@ -42,7 +42,7 @@ _libm.hypotf.argtypes = [ctypes.c_float, ctypes.c_float]
 _libm.hypot.restype = ctypes.c_double
 _libm.hypot.argtypes = [ctypes.c_double, ctypes.c_double]
 
-I4, R4, R8, C4, C8, LG = np.int32, np.float32, np.float64, np.complex64, np.complex128, np.bool_
+I4, I8, R4, R8, C4, C8, LG = np.int32, np.int64, np.float32, np.float64, np.complex64, np.complex128, np.bool_
 
 
 class FortranStop(Exception):
@@ -423,7 +423,7 @@ class FType:
 
     def dtype(self):
         if self.base == "integer":
-            return I4
+            return I8 if self.kind == 8 else I4
         if self.base == "real":
             return R8 if self.kind == 8 else R4
         if self.base == "complex":
@@ -605,6 +605,7 @@ class Interp:
         self.overrides = {}
         self.defines = tuple(defines)
         self.files = {}
+        self.units = {}
         self.n_statements = 0
 
     # ---- loading ------------------------------------------------------------------------
@@ -946,9 +947,14 @@ class Interp:
                     self._select(st, fr)
                 elif k == "skip":
                     pass
+                elif k == "write":
+                    if st[1] not in ("*", "6", "0"):
+                        raise NotImplementedError(f"write to unit {st[1]} (only messages to the terminal are skipped)")
+                elif k in ("open", "close", "read"):
+                    self._io(k, st[1], st[2], fr)
                 else:
                     raise FortranError(f"statement kind {k}")
-            except (FortranError, NotImplementedError, KeyError, TypeError, ValueError, IndexError) as e:
+            except (FortranError, NotImplementedError, KeyError, TypeError, ValueError, IndexError, OSError) as e:
                 if not getattr(e, "_located", False):
                     e.args = (f"{e.args[0] if e.args else e!r}  [line {st[-1]} of "
                               f"{fr.proc.path if fr.proc else '?'}]",) + tuple(e.args[1:])
@@ -1066,6 +1072,86 @@ class Interp:
     def _assign(self, target, value, fr):
         r = self.ref(target, fr)
         r.assign(value)
+
+    # ---- unformatted direct-access / stream input (what read_wavecar does) ---------------------
+    def _io(self, kind, ctl, items, fr):
+        def val(key, default=None):
+            return self.eval(ctl[key], fr) if key in ctl else default
+
+        def set_iostat(code):
+            if "iostat" in ctl:
+                self._assign(ctl["iostat"], I4(code), fr)
+            elif code:
+                raise FortranError(f"{kind}: I/O error {code} and no iostat=")
+        if ctl.get("unit") == "*":
+            raise NotImplementedError("list-directed / terminal input")
+        unit = int(val("unit"))
+        if kind == "open":
+            access = str(val("access", "sequential")).strip().lower()
+            if access not in ("direct", "stream"):
+                raise NotImplementedError(f"open with access='{access}'")
+            if str(val("form", "unformatted")).strip().lower() != "unformatted":
+                raise NotImplementedError("formatted files")
+            try:
+                fh = open(str(val("file")).strip(), "rb")
+            except OSError:
+                return set_iostat(2)
+            self.units[unit] = (fh, access, int(val("recl", 0)))
+            return set_iostat(0)
+        if kind == "close":
+            ent = self.units.pop(unit, None)
+            if ent:
+                ent[0].close()
+            return None
+        if unit not in self.units:
+            raise FortranError(f"read from unit {unit}, which is not open")
+        if any(k.startswith("_") or k == "fmt" for k in ctl):
+            raise NotImplementedError("formatted read")
+        fh, access, recl = self.units[unit]
+        if access == "direct":
+            start = (int(val("rec")) - 1) * recl       # recl in bytes (gfortran; ifort with -assume byterecl)
+            limit = start + recl
+        else:
+            start, limit = int(val("pos")) - 1, None
+        fh.seek(0, 2)
+        size = fh.tell()
+        cursor = [start]
+
+        def take(ref):
+            cur = ref.get()
+            if cur is None:
+                raise FortranError("read into an unallocated array")
+            a = np.asarray(cur)
+            if a.dtype == object:
+                raise NotImplementedError("read into a derived-type item")
+            n = a.size * a.dtype.itemsize
+            if cursor[0] + n > size or (limit is not None and cursor[0] + n > limit):
+                raise EOFError
+            fh.seek(cursor[0])
+            raw = np.frombuffer(fh.read(n), dtype=a.dtype.newbyteorder("<"))
+            cursor[0] += n
+            ref.assign(raw.reshape(a.shape, order="F") if a.ndim else raw[0])
+
+        def walk(it):
+            if it[0] == "ido":
+                _, exprs, var, lo, hi, stp = it
+                v = fr.lookup(var)
+                s_ = int(self.eval(stp, fr)) if stp is not None else 1
+                i, h = int(self.eval(lo, fr)), int(self.eval(hi, fr))
+                while (s_ > 0 and i <= h) or (s_ < 0 and i >= h):
+                    v.value = I4(i)
+                    for x in exprs:
+                        walk(x)
+                    i += s_
+                v.value = I4(i)                # an I/O implied-do variable keeps its final value
+            else:
+                take(self.ref(it, fr))
+        try:
+            for it in items:
+                walk(it)
+        except EOFError:
+            return set_iostat(-1)
+        return set_iostat(0)
 
     # ---- references (things that can be assigned to) ----------------------------------------
     def ref(self, ast, fr):
@@ -1474,9 +1560,29 @@ def parse_block(stmts, i, terminators):
             block.append(("skip", no) if s == "continue" else (s, no))
         elif re.match(r"^stop\b", s):
             block.append(("stop", s[4:].strip(), no))
-        elif re.match(r"^(write|print|read|open|close|rewind|flush|format|nullify)\b", s) and _top_level_eq(s) < 0:
-            block.append(("skip", no))
-        elif re.match(r"^(write|read|open|close)\s*\(", s):
+        elif re.match(r"^(open|close|read)\s*\(", s):
+            kw = s[:s.index("(")].strip()
+            inside, rest = _head_paren(s, kw)
+            ctl = {}
+            for pos, part in enumerate(_split_top(inside)):
+                eq = _top_level_eq(part)
+                if eq >= 0:
+                    ctl[part[:eq].strip()] = parse_expr(part[eq + 1:].strip())
+                else:
+                    ctl["unit" if pos == 0 else f"_{pos}"] = part.strip() if part.strip() == "*" else parse_expr(part)
+            items = []
+            if kw == "read" and rest:
+                p = Parser(tokenize(rest))
+                while True:
+                    items.append(p.ac_item())
+                    if p.at_end():
+                        break
+                    p.expect(",")
+            block.append((kw, ctl, items, no))
+        elif re.match(r"^(write|print)\b", s):
+            m = re.match(r"^write\s*\(\s*(?:unit\s*=\s*)?([^,)]*)", s)
+            block.append(("write", m.group(1).strip() if m else "*", no))
+        elif re.match(r"^(rewind|flush|format|nullify)\b", s) and _top_level_eq(s) < 0:
             block.append(("skip", no))
         else:
             toks = tokenize(s)
@@ -1527,7 +1633,7 @@ def describe(v):
         return "character", None, None, rank
     k = a.dtype.kind
     if k in "iu":
-        return "integer", 4, None, rank
+        return "integer", a.dtype.itemsize, None, rank
     if k == "f":
         return "real", a.dtype.itemsize, None, rank
     if k == "c":
@@ -1580,7 +1686,7 @@ def result_dtype(a, b):
         return C8 if bits == 8 else C4
     if "f" in (ka, kb):
         return R8 if bits == 8 else R4
-    return I4
+    return I8 if 8 in (da.itemsize, db.itemsize) else I4
 
 
 def _cabs(z):
@@ -1647,9 +1753,9 @@ def binop(op, a, b):
         if op == "*":
             return x * y
         if op == "/":
-            if dt is I4:
-                q = np.trunc(np.asarray(x, dtype=np.float64) / np.asarray(y, dtype=np.float64))
-                q = q.astype(I4)
+            if dt in (I4, I8):     # integer division truncates toward zero
+                xa, ya = np.asarray(x, dtype=np.int64), np.asarray(y, dtype=np.int64)
+                q = (np.sign(xa) * np.sign(ya) * (np.abs(xa) // np.abs(ya))).astype(dt)
                 return q[()] if q.ndim == 0 else q
             return x / y
     raise FortranError(f"operator {op}")
@@ -1694,10 +1800,7 @@ def _sqrt(x):
 def _mod(a, p):
     dt = result_dtype(a, p)
     x, y = convert(a, dt), convert(p, dt)
-    if dt is I4:
-        r = np.fmod(x, y)
-        return r
-    return np.fmod(x, y)        # sign of the dividend, exact
+    return np.fmod(x, y)        # sign of the dividend, exact (integers and reals alike)
 
 
 def _nint(x, kind=None):
@@ -1834,7 +1937,7 @@ INTRINSICS = {
     "cmplx": _cmplx, "conjg": _conjg, "aimag": _aimag, "size": _size,
     "lbound": lambda a, dim=None: I4(1), "ubound": lambda a, dim=None: _size(a, dim),
     "epsilon": _epsilon, "kind": _kind, "selected_real_kind": _selected_real_kind,
-    "selected_int_kind": lambda r: I4(4 if int(r) <= 9 else 8),
+    "selected_int_kind": lambda r: I4(4 if int(r) <= 9 else 8), "int8": lambda x: convert(x, I8),
     "sum": _sum, "dot_product": _dot_product, "matmul": _matmul, "transpose": lambda a: np.transpose(a),
     "any": lambda a: LG(np.any(a)), "all": lambda a: LG(np.all(a)), "count": lambda a: I4(np.count_nonzero(a)),
     "max": _minmax(np.maximum), "min": _minmax(np.minimum), "max0": _minmax(np.maximum), "min0": _minmax(np.minimum),

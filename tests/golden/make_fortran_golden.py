@@ -59,12 +59,18 @@ def struct_array(it, typename, n):
 
 
 def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, grid, seed, *,
-             perform_unfold=True, zero_band=None, folding_noise=0.0, smearing=None, sf_std=None, dir_weights=None):
+             perform_unfold=True, zero_band=None, folding_noise=0.0, smearing=None, sf_std=None, dir_weights=None,
+             wavecar=None):
     """pc_kpts_frac_sc: the pc-kpts to unfold onto, in fractional SC reciprocal coordinates
     (K + an SC reciprocal lattice vector each).  With dir_weights it is a list of such lists, one
     per needed direction (the symmetry-equivalent copies of ONE pcbz direction, all of them folding
     onto this SC-kpt here), and get_delta_Ns_for_output averages over them with those weights;
-    rows of the per-pc-kpt outputs are then numbered direction-major."""
+    rows of the per-pc-kpt outputs are then numbered direction-major.
+    wavecar: dict(other_kpt=[..], extra_pad=n, adjust_c=bool) -- the wavefunction does not come from
+    populate_wf_with_G_vec_coords + synthetic arrays but from the reference's READER: a synthetic
+    two-k-point WAVECAR is written (bandup_b200.wavecar.write_wavecar; this k-point is the second one)
+    and read_wavecar itself parses it (records, spinor decision, the 2m/hbar^2 adjustment loop when
+    adjust_c asks for a file with one plane wave more than the stock constant yields)."""
     it = interpreter(perform_unfold)
     rng = np.random.default_rng(seed)
     out = {}
@@ -84,34 +90,82 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
     wf = it.new_struct("pw_wavefunction")
     kf = np.asarray(kpt_frac, dtype=R8)
     b1, b2, b3 = B_sc[0].copy(), B_sc[1].copy(), B_sc[2].copy()
-    n_g = int(it.call("n_gvecs_2b_generated", kf, R8(ecut), b1, b2, b3))
-    wf["n_pw"], wf["n_bands"], wf["n_spinor"] = I4(n_g), I4(n_bands), I4(n_spinor)
-    it.call("populate_wf_with_g_vec_coords", wf, kf, R8(ecut), b1, b2, b3)
-    g_frac = np.array([g["coord"] for g in wf["g_frac"]], dtype=np.int32)
-    g_cart = np.array([g["coord"] for g in wf["g_cart"]], dtype=R8)
-    out.update(kpt_frac=kf, ecut=np.array(ecut), g_frac=g_frac, g_cart=g_cart)
-
-    # ---- synthetic coefficients, band energies, energy grid ---------------------------------
-    kg = (g_frac + kf) @ B_sc
-    env = np.exp(-np.sum(kg * kg, axis=1) / (2.0 * 0.2624658 * ecut / 4.0))
-    c = (rng.standard_normal((n_spinor, n_g, n_bands)) + 1j * rng.standard_normal((n_spinor, n_g, n_bands)))
-    c *= env[None, :, None] * rng.uniform(0.2, 3.0, size=(1, 1, n_bands))
-    c = c.astype(np.complex64)
-    if zero_band is not None:
-        c[:, :, zero_band] = 0
     e_start, e_end, d_e = grid
     egrid = F.Var(None, decl(it, "real(kind=dp), dimension(:), allocatable :: return_list"))
     it.call("real_seq", R8(e_start), R8(e_end), R8(d_e), egrid)
     egrid = egrid.value
-    ener = np.sort(rng.uniform(e_start - 0.3, e_end + 0.3, size=n_bands))
-    if n_bands >= 4:
-        ener[1] = ener[0]                                     # an exact duplicate
-        ener[2] = egrid[len(egrid) // 2] + 0.5 * (egrid[1] - egrid[0])   # exactly on a bin edge
-        ener[3] = ener[2] + 1e-3                             # a close neighbour (shares bins: rho pairs)
-        ener = np.sort(ener)
+
+    def synthetic(g_frac_, k_):
+        kg = (g_frac_ + k_) @ B_sc
+        env = np.exp(-np.sum(kg * kg, axis=1) / (2.0 * 0.2624658 * ecut / 4.0))
+        n_ = len(g_frac_)
+        c_ = (rng.standard_normal((n_spinor, n_, n_bands)) + 1j * rng.standard_normal((n_spinor, n_, n_bands)))
+        c_ *= env[None, :, None] * rng.uniform(0.2, 3.0, size=(1, 1, n_bands))
+        c_ = c_.astype(np.complex64)
+        if zero_band is not None:
+            c_[:, :, zero_band] = 0
+        e_ = np.sort(rng.uniform(e_start - 0.3, e_end + 0.3, size=n_bands))
+        if n_bands >= 4:
+            e_[1] = e_[0]                                     # an exact duplicate
+            e_[2] = egrid[len(egrid) // 2] + 0.5 * (egrid[1] - egrid[0])   # exactly on a bin edge
+            e_[3] = e_[2] + 1e-3                             # a close neighbour (shares bins: rho pairs)
+            e_ = np.sort(e_)
+        return c_, e_
+
+    if wavecar is None:
+        # ---- the plane-wave list as read_wavecar builds it ---------------------------------
+        n_g = int(it.call("n_gvecs_2b_generated", kf, R8(ecut), b1, b2, b3))
+        wf["n_pw"], wf["n_bands"], wf["n_spinor"] = I4(n_g), I4(n_bands), I4(n_spinor)
+        it.call("populate_wf_with_g_vec_coords", wf, kf, R8(ecut), b1, b2, b3)
+        g_frac = np.array([g["coord"] for g in wf["g_frac"]], dtype=np.int32)
+        c, ener = synthetic(g_frac, kf)
+        wf["pw_coeffs"] = c
+        wf["band_energies"] = ener.astype(R8)
+    else:
+        # ---- a synthetic WAVECAR, parsed by the reference's reader ---------------------------------
+        import tempfile
+        from bandup_b200 import synth
+        from bandup_b200.wavecar import write_wavecar
+        c0 = float(it.module_value("vasp_2m_over_hbar_sqrd").value)
+        c_file = c0
+        if wavecar.get("adjust_c"):
+            # put the cutoff a hair below one plane wave's kinetic energy: the stock constant leaves it
+            # out, the constant + 1e-10 takes it in -- the file holds one plane wave more than the
+            # reader first expects, and its adjustment loop has to find that (:459-472)
+            wide = synth.gen_gvecs(kf, ecut * 1.05, B_sc, c0)
+            kg = (wide + kf) @ B_sc
+            et = np.sum(kg * kg, axis=1) / c0
+            target = np.sort(et[et < ecut])[-3]
+            ecut = float(target * (1.0 - 3e-10))
+            c_file = c0 + 1e-10
+        kpts = [np.asarray(wavecar["other_kpt"], dtype=R8), kf]
+        lists = [synth.gen_gvecs(k_, ecut, B_sc, c_file) for k_ in kpts]
+        data = [synthetic(g_, k_) for g_, k_ in zip(lists, kpts)]
+        with tempfile.TemporaryDirectory() as tmp:
+            path = Path(tmp) / "WAVECAR"
+            nrecl = write_wavecar(path, A_sc, ecut, kpts, [np.ascontiguousarray(np.transpose(d[0], (2, 1, 0))) for d in data],
+                                  [d[1] for d in data], extra_pad=int(wavecar.get("extra_pad", 0)))
+            out["wavecar_bytes"] = np.frombuffer(path.read_bytes(), dtype=np.uint8).copy()
+            out["wavecar_nrecl"] = np.array(nrecl)
+            out["wavecar_ikpt"] = np.array(2)
+            it.overrides["available_io_unit"] = lambda *a: I4(60 + len(it.units))
+            wf["i_spin"] = I4(1)
+            iost = F.Var(I4(-7), None)
+            it.call("read_wavecar", wf, str(path), I4(2), iostat=iost)
+            assert int(iost.value) == 0 and not it.units
+        if wavecar.get("adjust_c"):
+            assert len(lists[1]) == len(synth.gen_gvecs(kf, ecut, B_sc, c0)) + 1
+        n_g = int(wf["n_pw"])
+        assert n_g == len(lists[1]) and int(wf["n_spinor"]) == n_spinor and int(wf["n_bands"]) == n_bands
+        g_frac = np.array([g["coord"] for g in wf["g_frac"]], dtype=np.int32)
+        c, ener = wf["pw_coeffs"].copy(), wf["band_energies"].copy()
+        out.update(reader_A_matrix=wf["a_matrix"].copy(), reader_B_matrix=wf["b_matrix"].copy(),
+                   reader_encut=np.array(wf["encut"]), reader_vcell=np.array(wf["vcell"]),
+                   reader_occupations=wf["band_occupations"].copy(), reader_kpt_frac=wf["kpt_frac_coords"].copy(),
+                   reader_n_spin=np.array(wf["n_spin"]), reader_is_spinor=np.array(bool(wf["is_spinor"])))
+    g_cart = np.array([g["coord"] for g in wf["g_cart"]], dtype=R8)
+    out.update(kpt_frac=kf, ecut=np.array(ecut), g_frac=g_frac, g_cart=g_cart)
     out.update(coeffs_in=c.copy(), band_energies=ener, energy_grid=egrid)
-    wf["pw_coeffs"] = c
-    wf["band_energies"] = ener.astype(R8)
 
     # ---- the renormalisation block of read_wavefunction -------------------------------------
     it.exec_statements(REF / "io_routines_mod.f90", 1317, 1330, {
@@ -293,6 +347,13 @@ SPECS = [
     ("symm_avg_spinor", hexa, [[2, 1, 0], [-1, 1, 0], [0, 0, 1]], [0.0, 0.25, 0.0], 36.0, 2, 5,
      [[[0.0, 0.25, 0.0], [1.0, 0.25, 0.0]], [[1.0, 1.25, 0.0], [0.0, 1.25, 1.0]]],
      (-2.0, 2.0, 0.5), 17, dict(dir_weights=[0.75, 0.25])),
+    # the wavefunction comes out of the reference's own WAVECAR reader (a synthetic two-k-point file)
+    ("wavecar_scalar", tri, [[2, 0, 0], [1, 2, 0], [0, 1, 2]], [0.3, 0.15, -0.2], 40.0, 1, 5,
+     [[0.3, 0.15, -0.2], [1.3, 1.15, -0.2]], (-2.0, 2.0, 0.5), 18,
+     dict(wavecar=dict(other_kpt=[0.0, 0.0, 0.0], extra_pad=3))),
+    ("wavecar_spinor_adjusted_cutoff", hexa, [[2, 1, 0], [-1, 1, 0], [0, 0, 1]], [0.21, 0.13, 0.05], 36.0, 2, 4,
+     [[0.21, 0.13, 0.05], [1.21, 0.13, 0.05]], (-2.0, 2.0, 0.5), 19,
+     dict(wavecar=dict(other_kpt=[0.5, 0.0, 0.0], extra_pad=0, adjust_c=True))),
 ]
 
 

@@ -375,3 +375,54 @@ end module t
         it.call("s", np.zeros(3))
     with pytest.raises(F.FortranError):
         it.call("u", F.Var(np.float64(0), None))
+
+
+def test_unformatted_direct_and_stream_reads(tmp_path):
+    """The two access modes read_wavecar uses: direct records (rec=, recl in bytes) and a stream
+    position (pos=), with implied-do item lists, array sections and 8-byte integers."""
+    rec = 64
+    data = np.zeros(3 * rec, dtype=np.uint8)
+    data[0:24] = np.array([float(rec), 2.0, 45200.0]).view(np.uint8)
+    data[rec:rec + 8 + 32] = np.concatenate([np.array([7.0]), np.array([1 + 2j, 3 - 4j])
+                                             .view(np.float64)]).view(np.uint8)
+    data[2 * rec:2 * rec + 32] = np.array([1 + 1j, 2 + 2j, 3 + 3j, 4 + 4j], dtype=np.complex64).view(np.uint8)
+    path = tmp_path / "records.bin"
+    path.write_bytes(data.tobytes())
+    it = interp(tmp_path, """
+module t
+use kinds
+contains
+subroutine rd(file, head, z, c, ios_past_end)
+  character(len=*), intent(in) :: file
+  real(kind=dp), dimension(1:4), intent(out) :: head
+  complex(kind=dp), dimension(1:2), intent(out) :: z
+  complex(kind=sp), dimension(1:2,1:2), intent(out) :: c
+  integer, intent(out) :: ios_past_end
+  integer(kind=selected_int_kind(18)) :: nrecl, pos
+  real(kind=dp) :: x
+  integer :: u, ios, j
+  u = 11
+  nrecl = 24
+  open(unit=u, file=file, access='direct', recl=nrecl, iostat=ios, status='old')
+  read(unit=u, rec=1, iostat=ios) x
+  close(unit=u)
+  nrecl = nint(x)
+  open(unit=u, file=file, access='direct', recl=nrecl, iostat=ios, status='old')
+  read(unit=u, rec=1) (head(j), j=1,3)
+  read(unit=u, rec=2) head(4), (z(j), j=1,2)
+  read(unit=u, rec=9, iostat=ios_past_end) x
+  close(u)
+  open(unit=u, file=file, access='stream', iostat=ios, status='old')
+  pos = 1 + 2*nrecl
+  read(unit=u, pos=pos) (c(j,:), j=1,2)
+  close(u)
+end subroutine rd
+end module t
+""")
+    head, z = F.Var(np.zeros(4), None), F.Var(np.zeros(2, dtype=np.complex128), None)
+    c, ios = F.Var(np.zeros((2, 2), dtype=np.complex64), None), F.Var(np.int32(0), None)
+    it.call("rd", str(path), head, z, c, ios)
+    assert head.value.tolist() == [64.0, 2.0, 45200.0, 7.0]
+    assert z.value.tolist() == [1 + 2j, 3 - 4j]
+    assert c.value.tolist() == [[1 + 1j, 2 + 2j], [3 + 3j, 4 + 4j]]      # c(1,:) then c(2,:)
+    assert int(ios.value) != 0 and not it.units

@@ -79,7 +79,10 @@ def test_non_commensurate_cells_are_reported():
 @pytest.mark.parametrize("name", CASES)
 def test_plane_wave_list_is_the_readers(gold, name):
     g = case(gold, name)
-    gf, gc = O.gen_gvecs(g["kpt_frac"], float(g["ecut"]), g["B_sc"])
+    # the file of this case holds one plane wave more than the stock 2m/hbar^2 yields; read_wavecar's
+    # adjustment loop (read_wavecar_mod.f90:459-472) ended on the constant + 1e-10
+    c = float(np.float32(0.262465831)) + 1e-10 if name == "wavecar_spinor_adjusted_cutoff" else 0.0
+    gf, gc = O.gen_gvecs(g["kpt_frac"], float(g["ecut"]), g["B_sc"], c)
     assert np.array_equal(gf, g["g_frac"])                           # count, order and indices
     assert np.array_equal(gc, g["g_cart"])                           # ig1p*b1 + ig2p*b2 + ig3p*b3, bit for bit
 
@@ -250,6 +253,40 @@ def test_pauli_vectors_and_spin_projections(gold):
         untouched = np.setdiff1d(np.arange(len(grid)), np.array(sorted(vecs)) - 1)
         assert not np.any(g["sigma"][f, untouched])
     assert checked >= 3
+
+
+WAVECAR_CASES = [c for c in CASES if c.startswith("wavecar")]
+
+
+@pytest.mark.parametrize("name", WAVECAR_CASES)
+def test_wavecar_parser_against_the_reference_reader(gold, name, tmp_path):
+    """The same synthetic WAVECAR through bandup_b200.wavecar (the host-side parser of the raw-record
+    path) and through the reference's read_wavecar (interpreted): header fields, scalar/spinor
+    decision, plane-wave list -- with the 2m/hbar^2 adjustment in one case -- energies, coefficients."""
+    from bandup_b200.wavecar import Wavecar
+    g = case(gold, name)
+    path = tmp_path / "WAVECAR"
+    path.write_bytes(g["wavecar_bytes"].tobytes())
+    wc = Wavecar(path)
+    ik = int(g["wavecar_ikpt"])
+    assert wc.nrecl == int(g["wavecar_nrecl"]) and wc.nspin == int(g["reader_n_spin"]) == 1
+    assert wc.encut == float(g["reader_encut"]) == float(g["ecut"])
+    assert np.array_equal(wc.A_matrix, g["reader_A_matrix"]) and np.array_equal(wc.A_matrix, g["A_sc"])
+    assert np.allclose(wc.B_matrix, g["reader_B_matrix"], rtol=1e-15, atol=0)
+    # the reader rebuilds B from the file's A (twopi*cross/Vcell): the same matrix get_rec_latt gave
+    assert np.allclose(g["reader_B_matrix"], g["B_sc"], rtol=1e-15, atol=1e-18)
+    h = wc.kpt_header(ik)
+    assert np.array_equal(h.kpt_frac_coords, g["reader_kpt_frac"])
+    assert np.array_equal(h.band_energies, g["band_energies"])
+    assert np.array_equal(h.band_occupations, g["reader_occupations"])
+    gf, nsp = wc.gvecs(ik)
+    assert nsp == int(g["n_spinor"]) == (2 if bool(g["reader_is_spinor"]) else 1)
+    assert np.array_equal(gf, g["g_frac"])
+    assert h.nplane == nsp * len(gf)
+    assert np.array_equal(wc.coefficients(ik), bands_first(g["coeffs_in"]))      # (n_bands, n_pw, n_spinor)
+    if name == "wavecar_spinor_adjusted_cutoff":
+        stock = O.gen_gvecs(g["kpt_frac"], float(g["ecut"]), g["B_sc"])[0]
+        assert len(stock) == len(gf) - 1                                   # the loop had work to do
 
 
 AVG_CASES = [c for c in CASES if c.startswith("symm_avg")]

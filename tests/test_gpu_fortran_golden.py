@@ -195,3 +195,34 @@ def test_unfold_then_average_end_to_end(unfolder, gold, name):
     want = g["avg_rho"]
     assert np.array_equal(np.stack([out.fold, out.iener, out.m1, out.m2], axis=1), want[:, :4].astype(np.int32))
     assert np.max(np.abs(out.rho - (want[:, 4] + 1j * want[:, 5]))) <= 2e-6
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c.startswith("wavecar")])
+def test_wavecar_file_to_delta_N_against_the_reference_run(unfolder, gold, name, tmp_path):
+    """The reference's whole loop body on an identical synthetic WAVECAR: its own read_wavecar (records,
+    spinor decision, 2m/hbar^2 adjustment), renormalisation, selection, perform_unfolding -- against
+    the file handed to the library as raw band records with the plane-wave list made on the device."""
+    from bandup_b200.wavecar import Wavecar
+    g = case(gold, name)
+    path = tmp_path / "WAVECAR"
+    path.write_bytes(g["wavecar_bytes"].tobytes())
+    wc = Wavecar(path)
+    M = unfolder.verify_commens(g["b_pc"], wc.B_matrix)               # the SC lattice as the file gives it
+    assert np.array_equal(M, np.rint(g["M"]).astype(np.int32))
+    eg = g["energy_grid"]
+    unfolder.set_energy_grid(eg[0], eg[-1], eg[1] - eg[0])
+    ik = int(g["wavecar_ikpt"])
+    nsp, npw = wc.submit_to(unfolder, 5, ik, g["folding_G"])
+    assert (nsp, npw) == (int(g["n_spinor"]), len(g["g_frac"]))
+    assert np.array_equal(unfolder.fetch_gvecs(5, npw), g["g_frac"])
+    res = unfolder.fetch(5, want_selected=True)
+    assert np.array_equal(res.n_selected, g["n_selected"])
+    assert np.array_equal(np.concatenate(res.selected_coeff_indices), g["selected"])
+    assert rel(res.spectral_weight, g["weights"]) <= REL
+    assert rel(res.dN, g["delta_N"]) <= REL
+    ops = unfolder.calc_rho(5)
+    want = g["rho"]
+    assert np.array_equal(np.stack([ops.fold, ops.iener, ops.m1, ops.m2], axis=1), want[:, :4].astype(np.int32))
+    assert np.max(np.abs(ops.rho - (want[:, 4] + 1j * want[:, 5]))) <= 2e-6
+    if nsp == 2:
+        assert np.max(np.abs(unfolder.pauli_vectors(5, len(g["n_selected"])) - g["sigma"])) <= 5e-6
