@@ -16,17 +16,17 @@
  * populate_wf_with_G_vec_coords, the renormalisation block of
  * read_wavefunction, select_coeffs_to_calc_spectral_weights, perform_unfolding
  * with everything below it, get_delta_Ns_for_EBS with a smearing,
- * calc_spectral_function, get_delta_Ns_for_output) on seeded inputs;
- * tests/golden/make_fortran_golden.py is the generating script and
- * tests/golden/fortran_golden.npz the committed result (7 cases, 1.6 M Fortran
- * statements).  tests/test_fortran_golden.py holds every function of this file
+ * calc_spectral_function, get_delta_Ns_for_output, read_wavecar on synthetic
+ * WAVECAR files) on seeded inputs; tests/golden/make_fortran_golden.py is the
+ * generating script and tests/golden/fortran_golden.npz the committed result
+ * (9 cases, 1.85 M Fortran statements).  tests/test_fortran_golden.py holds every function of this file
  * against those vectors: plane-wave list, renormalised coefficients, selected
  * indices, rho and the symmetry averages bit for bit; weights, delta_N and the
  * spectral function to 1e-15.  What that does NOT pin: code generation of a
  * particular Fortran compiler (the interpreter evaluates every operation in the
  * kind Fortran prescribes, without reassociation or fused multiply-add -- what
  * gfortran -O2 does on baseline x86-64, src/Makefile:23-30), the order OpenMP
- * threads append selected indices in (ascending here), file I/O.
+ * threads append selected indices in (ascending here), the output writers.
  * Also asserted in tests/: agreement with an independent NumPy restatement
  * (oracle/oracle_np.py) and analytic invariants (sum over cosets of P = 1,
  * perfect-supercell weights in {0,1}, float lattice test == integer coset test).

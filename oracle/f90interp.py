@@ -23,8 +23,11 @@ faithfully, because the goldens depend on it:
   * `!$omp` directives are comments: loops run in index order, which is one of the orders an
     OpenMP run may produce (the reference's results do not depend on it except for the order of
     the selected-coefficient list, which it leaves to thread arrival).
-Not supported (raises NotImplementedError): array lower bounds other than 1, I/O (write/print are
-skipped), pointers beyond simple aliasing, `where`/`forall`, internal procedures.
+  * unformatted direct-access and stream input (open/read/close as read_wavecar uses them: rec=
+    with recl in bytes, pos=, implied-do item lists, array sections); integer(8).
+Not supported (raises NotImplementedError): array lower bounds other than 1, formatted and
+sequential I/O (messages written to the terminal are skipped, any other write is refused), pointers
+beyond simple aliasing, `where`/`forall`, internal procedures.
 """
 from __future__ import annotations
 
