@@ -36,10 +36,17 @@ FILES = ["constants_and_types_mod.f90", "math_mod.f90", "lists_and_seqs_mod.f90"
 R8, I4, LG = np.float64, np.int32, np.bool_
 
 
-def interpreter(perform_unfold=True, write_unf_dens_op=True):
+def interpreter(perform_unfold=True, write_unf_dens_op=True, dp_build=False):
     it = F.Interp()
     for f in FILES:
         it.load(REF / f)
+    if dp_build:
+        # the build the reference asks for when the WAVECAR is double precision: "change the variable
+        # kind_cplx_coeffs from sp to dp ... and recompile" (read_wavecar_mod.f90:363-377,
+        # constants_and_types_mod.f90:60) -- here: the parameter is given the value dp before anything
+        # that depends on it is evaluated
+        assert "kind_cplx_coeffs" not in it.mod_vals
+        it.mod_vals["kind_cplx_coeffs"] = F.Var(I4(int(it.module_value("dp").value)), it.mod_decls["kind_cplx_coeffs"])
     it.overrides["time_now"] = lambda: R8(0.0)
     args = F.FStruct("comm_line_args", perform_unfold=LG(perform_unfold), write_unf_dens_op=LG(write_unf_dens_op),
                      normal_to_proj_plane=np.array([0.0, 0.0, 1.0]))
@@ -60,7 +67,7 @@ def struct_array(it, typename, n):
 
 def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, grid, seed, *,
              perform_unfold=True, zero_band=None, folding_noise=0.0, smearing=None, sf_std=None, dir_weights=None,
-             wavecar=None):
+             wavecar=None, dp_build=False):
     """pc_kpts_frac_sc: the pc-kpts to unfold onto, in fractional SC reciprocal coordinates
     (K + an SC reciprocal lattice vector each).  With dir_weights it is a list of such lists, one
     per needed direction (the symmetry-equivalent copies of ONE pcbz direction, all of them folding
@@ -71,7 +78,7 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
     two-k-point WAVECAR is written (bandup_b200.wavecar.write_wavecar; this k-point is the second one)
     and read_wavecar itself parses it (records, spinor decision, the 2m/hbar^2 adjustment loop when
     adjust_c asks for a file with one plane wave more than the stock constant yields)."""
-    it = interpreter(perform_unfold)
+    it = interpreter(perform_unfold, dp_build=dp_build)
     rng = np.random.default_rng(seed)
     out = {}
     a_pc = np.asarray(a_pc, dtype=R8)
@@ -101,7 +108,7 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
         n_ = len(g_frac_)
         c_ = (rng.standard_normal((n_spinor, n_, n_bands)) + 1j * rng.standard_normal((n_spinor, n_, n_bands)))
         c_ *= env[None, :, None] * rng.uniform(0.2, 3.0, size=(1, 1, n_bands))
-        c_ = c_.astype(np.complex64)
+        c_ = c_.astype(np.complex128 if dp_build else np.complex64)
         if zero_band is not None:
             c_[:, :, zero_band] = 0
         e_ = np.sort(rng.uniform(e_start - 0.3, e_end + 0.3, size=n_bands))
@@ -144,7 +151,7 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
         with tempfile.TemporaryDirectory() as tmp:
             path = Path(tmp) / "WAVECAR"
             nrecl = write_wavecar(path, A_sc, ecut, kpts, [np.ascontiguousarray(np.transpose(d[0], (2, 1, 0))) for d in data],
-                                  [d[1] for d in data], extra_pad=int(wavecar.get("extra_pad", 0)))
+                                  [d[1] for d in data], extra_pad=int(wavecar.get("extra_pad", 0)), double=dp_build)
             out["wavecar_bytes"] = np.frombuffer(path.read_bytes(), dtype=np.uint8).copy()
             out["wavecar_nrecl"] = np.array(nrecl)
             out["wavecar_ikpt"] = np.array(2)
@@ -289,6 +296,7 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
         out["sf_std"] = np.array(sf_std)
         out["spectral_function"] = v.value.copy()
     out["perform_unfold"] = np.array(perform_unfold)
+    out["dp_build"] = np.array(dp_build)
     out["n_spinor"] = np.array(n_spinor)
     print(f"{name}: n_pw {n_g}, n_fold {n_fold}, selected {out['n_selected'].tolist()}, rho entries {len(rho_rows)}, "
           f"{it.n_statements} Fortran statements executed", flush=True)
@@ -354,6 +362,12 @@ SPECS = [
     ("wavecar_spinor_adjusted_cutoff", hexa, [[2, 1, 0], [-1, 1, 0], [0, 0, 1]], [0.21, 0.13, 0.05], 36.0, 2, 4,
      [[0.21, 0.13, 0.05], [1.21, 0.13, 0.05]], (-2.0, 2.0, 0.5), 19,
      dict(wavecar=dict(other_kpt=[0.5, 0.0, 0.0], extra_pad=0, adjust_c=True))),
+    # the reference built with kind_cplx_coeffs = dp: complex128 coefficients, a WAVECAR_double
+    ("dp_build_scalar", fcc, [[2, 0, 0], [0, 2, 0], [0, 0, 2]], [0.25, 0.25, 0.0], 44.0, 1, 5,
+     [[0.25, 0.25, 0.0], [1.25, 0.25, 1.0], [0.25, 1.25, 0.0]], (-2.0, 2.0, 0.5), 20, dict(dp_build=True)),
+    ("dp_build_wavecar_double_spinor", hexa, [[2, 1, 0], [-1, 1, 0], [0, 0, 1]], [0.1, 0.3, 0.0], 33.0, 2, 4,
+     [[0.1, 0.3, 0.0], [1.1, 1.3, 0.0]], (-2.0, 2.0, 0.5), 21,
+     dict(dp_build=True, wavecar=dict(other_kpt=[0.0, 0.0, 0.5], extra_pad=1))),
 ]
 
 

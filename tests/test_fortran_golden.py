@@ -14,6 +14,8 @@ from oracle import oracle_np as ON
 
 GOLD = Path(__file__).resolve().parent / "golden"
 CASES = json.loads((GOLD / "fortran_golden.json").read_text())["cases"]
+DP_CASES = [c for c in CASES if c.startswith("dp_build")]        # the reference with kind_cplx_coeffs = dp
+SP_CASES = [c for c in CASES if c not in DP_CASES]
 
 
 @pytest.fixture(scope="module")
@@ -87,7 +89,7 @@ def test_plane_wave_list_is_the_readers(gold, name):
     assert np.array_equal(gc, g["g_cart"])                           # ig1p*b1 + ig2p*b2 + ig3p*b3, bit for bit
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", SP_CASES)
 def test_renormalisation(gold, name):
     g = case(gold, name)
     cin, want = bands_first(g["coeffs_in"]), bands_first(g["coeffs_renormalised"])
@@ -121,7 +123,7 @@ def test_selection(gold, name):
     assert np.all(g["n_selected"] > 0)
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", SP_CASES)
 def test_spectral_weights_and_delta_N(gold, name):
     g = case(gold, name)
     cren = bands_first(g["coeffs_renormalised"])
@@ -151,7 +153,7 @@ def test_spectral_weights_and_delta_N(gold, name):
 
 def test_whole_kpt_entry_point_of_the_oracle(gold):
     """bo_unfold_kpt (what bench.py's CPU arm times) from the raw inputs, against the golden run."""
-    for name in CASES:
+    for name in SP_CASES:
         g = case(gold, name)
         if not bool(g["perform_unfold"]):
             continue
@@ -196,7 +198,7 @@ def rho_lists(g, f, sel, oracle_rho):
     return out
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", SP_CASES)
 def test_unfolding_density_operator(gold, name):
     g = case(gold, name)
     cren = bands_first(g["coeffs_renormalised"])
@@ -255,7 +257,45 @@ def test_pauli_vectors_and_spin_projections(gold):
     assert checked >= 3
 
 
-WAVECAR_CASES = [c for c in CASES if c.startswith("wavecar")]
+@pytest.mark.parametrize("name", DP_CASES)
+def test_double_precision_build(gold, name):
+    """`kind_cplx_coeffs = dp` (constants_and_types_mod.f90:60): complex128 coefficients, every
+    dot_product, abs and rescale in double precision -- the dp entry points of both oracles against
+    the reference run in that configuration."""
+    g = case(gold, name)
+    assert g["coeffs_in"].dtype == np.complex128 and bool(g["dp_build"])
+    cin = bands_first(g["coeffs_in"])
+    w, dn, ns, norms = O.unfold_kpt_dp(cin, g["g_cart"], g["band_energies"], g["b_pc"], g["folding_G"],
+                                       g["energy_grid"])
+    assert np.array_equal(ns, g["n_selected"])
+    assert rel(w, g["weights"]) < 1e-14 and np.max(np.abs(dn - g["delta_N"])) < 1e-14
+    w2, dn2, ns2, norms2 = ON.unfold_kpt_dp(cin, g["g_cart"], g["band_energies"], g["b_pc"], g["folding_G"],
+                                            g["energy_grid"])
+    assert np.array_equal(ns2, ns) and rel(w2, g["weights"]) < 1e-13 and np.max(np.abs(dn2 - g["delta_N"])) < 1e-13
+    assert rel(norms, norms2, 1e-30) < 1e-14
+    # renormalised coefficients: (1/sqrt(s)) * C in double precision
+    want = bands_first(g["coeffs_renormalised"])
+    got = cin / np.sqrt(norms)[:, None, None]
+    assert np.max(np.abs(got - want)) <= 4e-16 * np.max(np.abs(want))
+    # a single-precision treatment of the same numbers is 1e-8 or more away: this really is the dp path
+    w_sp = O.unfold_kpt(cin.astype(np.complex64), g["g_cart"], g["band_energies"], g["b_pc"], g["folding_G"],
+                        g["energy_grid"], norm_mode=1)[0]
+    assert rel(w_sp, g["weights"]) > 1e-9
+    # rho in complex(dp): the NumPy twin (fp64 inner products) to 1e-13
+    off = np.concatenate([[0], np.cumsum(g["n_selected"])])
+    n = 0
+    for f in range(len(ns)):
+        sel = g["selected"][off[f]:off[f + 1]]
+        rows = g["rho"][g["rho"][:, 0] == f]
+        got_np = rho_lists(g, f, sel, lambda s_, dn_, E, d: ON.calc_rho(want, s_, g["band_energies"], dn_, E, d))
+        assert [t[:3] for t in got_np] == [(int(r[1]), int(r[2]), int(r[3])) for r in rows]
+        for t, r in zip(got_np, rows):
+            assert abs(complex(t[3]) - complex(r[4], r[5])) < 1e-13
+        n += len(rows)
+    assert n == len(g["rho"]) > 0
+
+
+WAVECAR_CASES = [c for c in CASES if "wavecar" in c]
 
 
 @pytest.mark.parametrize("name", WAVECAR_CASES)
@@ -284,6 +324,7 @@ def test_wavecar_parser_against_the_reference_reader(gold, name, tmp_path):
     assert np.array_equal(gf, g["g_frac"])
     assert h.nplane == nsp * len(gf)
     assert np.array_equal(wc.coefficients(ik), bands_first(g["coeffs_in"]))      # (n_bands, n_pw, n_spinor)
+    assert wc.double == bool(g["dp_build"]) == (g["coeffs_in"].dtype == np.complex128)
     if name == "wavecar_spinor_adjusted_cutoff":
         stock = O.gen_gvecs(g["kpt_frac"], float(g["ecut"]), g["B_sc"])[0]
         assert len(stock) == len(gf) - 1                                   # the loop had work to do
