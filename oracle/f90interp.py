@@ -609,6 +609,7 @@ class Interp:
         self.defines = tuple(defines)
         self.files = {}
         self.units = {}
+        self.call_counts = {}
         self.n_statements = 0
 
     # ---- loading ------------------------------------------------------------------------
@@ -676,6 +677,8 @@ class Interp:
         if d.init is None:
             v = Var(self._default_value(d, Frame(self, None)), d)
         else:
+            if d.dims and not d.allocatable:     # `shape(x)` may appear in the initialiser of x itself
+                self.mod_vals[name] = Var(self._default_value(d, Frame(self, None)), d)
             val = self.eval(d.init, Frame(self, None))
             v = Var(self._convert_for(d, val), d)
         self.mod_vals[name] = v
@@ -729,7 +732,18 @@ class Interp:
             return
         p.decls = {}
         exe = []
+        in_type = None
         for no, s in p.stmts:
+            if in_type is not None:          # a derived type defined inside the procedure
+                if re.match(r"^end\s*type", s):
+                    in_type = None
+                elif is_declaration(s):
+                    self.types[in_type].append((no, s))
+                continue
+            if re.match(r"^type\s*(,\s*\w+\s*)*(::)?\s*\w+$", s) and not s.startswith("type("):
+                in_type = re.split(r"::|\s", s)[-1].strip()
+                self.types[in_type] = []
+                continue
             if is_declaration(s):
                 for d in parse_declaration(s, self._eval_module_const):
                     p.decls[d.name] = d
@@ -815,6 +829,7 @@ class Interp:
         if p is None:
             raise FortranError(f"unknown procedure {name}")
         self._prepare(p)
+        self.call_counts[p.name] = self.call_counts.get(p.name, 0) + 1
         fr = Frame(self, p)
         bound = {}
         for pos, (kw, val, ref) in enumerate(prepared):
@@ -835,6 +850,11 @@ class Interp:
                 v = None if d.intent == "out" else val
             elif d.dims or d.ftype.base in ("type", "character"):
                 v = val
+                if d.intent == "out" and isinstance(val, FStruct):
+                    for _, st in self.types.get(val.typename, []):
+                        for cd in parse_declaration(st, self._eval_module_const):
+                            if cd.allocatable:
+                                val[cd.name] = None
                 if d.dims and val is None:
                     # An unallocated array handed to an assumed-shape dummy is not standard Fortran,
                     # but the reference does it (trace_AB on an operator without entries, guarded by
@@ -1225,6 +1245,11 @@ class Interp:
             return e[1]
         if k == "comp":
             base = self.eval(e[1], fr)
+            if isinstance(base, np.ndarray) and base.dtype == object:      # a(:)%c: the array of the components
+                vals = [x[e[2]] for x in base.reshape(-1, order="F")]
+                if any(isinstance(v, np.ndarray) or v is None for v in vals):
+                    raise NotImplementedError("array-valued component of an array section")
+                return np.array(vals, dtype=np.asarray(vals[0]).dtype).reshape(base.shape, order="F")
             if not isinstance(base, FStruct):
                 raise FortranError(f"component {e[2]} of something that is not a derived-type scalar")
             return base[e[2]]

@@ -32,7 +32,8 @@ from oracle import f90interp as F  # noqa: E402
 
 REF = Path("/root/reference/src")
 FILES = ["constants_and_types_mod.f90", "math_mod.f90", "lists_and_seqs_mod.f90", "crystals_mod.f90",
-         "band_unfolding_routines_mod.f90", "io_routines_mod.f90", "vasp_related_modules/read_wavecar_mod.f90"]
+         "band_unfolding_routines_mod.f90", "io_routines_mod.f90", "vasp_related_modules/read_wavecar_mod.f90",
+         "symmetry_mod.f90"]
 R8, I4, LG = np.float64, np.int32, np.bool_
 
 
@@ -49,7 +50,9 @@ def interpreter(perform_unfold=True, write_unf_dens_op=True, dp_build=False):
         it.mod_vals["kind_cplx_coeffs"] = F.Var(I4(int(it.module_value("dp").value)), it.mod_decls["kind_cplx_coeffs"])
     it.overrides["time_now"] = lambda: R8(0.0)
     args = F.FStruct("comm_line_args", perform_unfold=LG(perform_unfold), write_unf_dens_op=LG(write_unf_dens_op),
-                     normal_to_proj_plane=np.array([0.0, 0.0, 1.0]))
+                     normal_to_proj_plane=np.array([0.0, 0.0, 1.0]), no_symm_sckpts=LG(True),
+                     origin_for_spin_proj_passed_in_rec=LG(False), origin_for_spin_proj_cartesian=np.zeros(3),
+                     origin_for_spin_proj_rec=np.zeros(3), n_sckpts_to_skip=I4(0))
     it.set_module_variable("args", args)
     return it
 
@@ -303,6 +306,56 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
     return out, it.n_statements
 
 
+def run_gur_case(name, a_pc, M, sckpts_frac, fold_onto, g_shifts, n_skip, seed, noise=0.0):
+    """get_geom_unfolding_relations (band_unfolding_routines_mod.f90:137-483, with get_star,
+    reduce_point_to_bz, point_is_in_bz, pt_eqv_by_point_group_symop behind it) under -no_symm_sckpts:
+    which SC-kpt every pc-kpt folds onto.  pc-kpt i = SC-kpt fold_onto[i] + the SC reciprocal lattice
+    vector g_shifts[i] (+ noise, so that the wrapper has to raise its tolerance)."""
+    it = interpreter()
+    rng = np.random.default_rng(seed)
+    args = it.mod_vals["args"].value
+    args["n_sckpts_to_skip"] = I4(n_skip)
+    a_pc = np.asarray(a_pc, dtype=R8)
+    A_sc = np.asarray(M, dtype=R8) @ a_pc
+    b_pc, B_sc = F.Var(np.zeros((3, 3)), None), F.Var(np.zeros((3, 3)), None)
+    it.call("get_rec_latt", a_pc, b_pc)
+    it.call("get_rec_latt", A_sc, B_sc)
+    b_pc, B_sc = b_pc.value, B_sc.value
+    crystal_pc, crystal_sc = it.new_struct("crystal_3d"), it.new_struct("crystal_3d")
+    crystal_pc["latt_vecs"][:], crystal_pc["rec_latt_vecs"][:] = a_pc, b_pc
+    crystal_sc["latt_vecs"][:], crystal_sc["rec_latt_vecs"][:] = A_sc, B_sc
+    sck = np.asarray(sckpts_frac, dtype=R8) @ B_sc
+    pck = np.array([sck[j] + np.asarray(g, dtype=R8) @ B_sc for j, g in zip(fold_onto, g_shifts)])
+    pck = pck + noise * rng.standard_normal(pck.shape)
+    n_k = len(pck)
+    list_of_sckpts = struct_array(it, "vec3d", len(sck))
+    for s_, v in zip(list_of_sckpts, sck):
+        s_["coord"][:] = v
+    to_check = it.new_struct("selected_pcbz_directions")
+    to_check["selec_pcbz_dir"] = struct_array(it, "needed_pcbz_dirs_for_ebs", 1)
+    to_check["selec_pcbz_dir"][0]["needed_dir"] = struct_array(it, "list_of_trial_folding_pckpts", 1)
+    pts = struct_array(it, "trial_folding_pckpt", n_k)
+    to_check["selec_pcbz_dir"][0]["needed_dir"][0]["pckpt"] = pts
+    for p_, v in zip(pts, pck):
+        p_["coords"][:] = v
+    gur = it.new_struct("geom_unfolding_relations_for_each_sckpt")
+    it.call("get_geom_unfolding_relations", gur, list_of_sckpts, to_check, crystal_pc, crystal_sc)
+    folds = np.array([[bool(gur["sckpt"][s_]["selec_pcbz_dir"][0]["needed_dir"][0]["pckpt"][k]["folds"])
+                       for k in range(n_k)] for s_ in range(len(sck))])
+    fold_sckpt = np.array([int(np.nonzero(folds[:, k])[0][0]) if folds[:, k].any() else -1 for k in range(n_k)],
+                          dtype=np.int32)
+    attempts = it.call_counts["get_gur_not_public"]
+    scoords = np.array([gur["sckpt"][fold_sckpt[k]]["selec_pcbz_dir"][0]["needed_dir"][0]["pckpt"][k]["scoords"]
+                        if fold_sckpt[k] >= 0 else np.full(3, np.nan) for k in range(n_k)])
+    out = dict(a_pc=a_pc, A_sc=A_sc, b_pc=b_pc, B_sc=B_sc, sckpts_cart=sck, pckpts_cart=pck, folds=folds,
+               fold_sckpt=fold_sckpt, n_attempts=np.array(attempts), n_sckpts_to_skip=np.array(n_skip),
+               n_pckpts=np.array(int(gur["n_pckpts"])), n_folding_pckpts=np.array(int(gur["n_folding_pckpts"])),
+               sckpt_used=np.array(gur["sckpt_used_for_unfolding"], dtype=bool), scoords=scoords)
+    print(f"{name}: {n_k} pc-kpts onto {len(sck)} SC-kpts, fold map {fold_sckpt.tolist()}, {attempts} attempt(s), "
+          f"{it.n_statements} Fortran statements executed", flush=True)
+    return out, it.n_statements
+
+
 def rho_entries(row, rhos, by_position=False):
     """(row, iener, m1, m2, re, im) of the stored elements of an array of UnfoldDensityOpContainer, in the
     order the reference appended them.  by_position: the averaged operators sit at index iener of an
@@ -371,11 +424,32 @@ SPECS = [
 ]
 
 
+GUR_SPECS = [
+    # name, a_pc, M, SC-kpts (frac), SC-kpt each pc-kpt folds onto, its SC reciprocal lattice shift, n_sckpts_to_skip, seed, noise
+    ("gur_no_symmetry", tri, [[2, 0, 0], [1, 2, 0], [0, 1, 2]],
+     [[0.0, 0.0, 0.0], [0.5, 0.0, 0.0], [0.25, 0.1, -0.3], [0.5, 0.5, 0.5], [0.1, 0.2, 0.3]],
+     [2, 0, 4, 1, 3, 2, 4, 0], [[0, 0, 0], [1, 0, 0], [0, 1, 1], [-1, 2, 0], [1, 1, 1], [2, -1, 0], [0, 0, -2], [0, 3, 1]],
+     0, 31, 0.0),
+    # the first SC-kpt is skipped (-n_sckpts_to_skip 1) although a duplicate of it comes later in the list;
+    # one pc-kpt is off its lattice point by ~2e-5, so the wrapper raises the tolerance
+    ("gur_skip_and_tolerance", fcc, [[2, 0, 0], [0, 2, 0], [0, 0, 1]],
+     [[0.5, 0.0, 0.0], [0.0, 0.5, 0.0], [0.5, 0.0, 0.0], [0.25, 0.25, 0.0]],
+     [2, 1, 3, 2, 1], [[0, 0, 0], [1, 0, 1], [0, 1, 0], [1, 1, 0], [0, 0, 1]], 1, 32, 1.0e-5),
+]
+
+
 def main():
     t0 = time.time()
     cases = {}
     n_stmt = 0
     only = sys.argv[1:]
+    for spec in GUR_SPECS:
+        if only and spec[0] not in only:
+            continue
+        out, n = run_gur_case(*spec)
+        n_stmt += n
+        for k, v in out.items():
+            cases[f"{spec[0]}/{k}"] = v
     for name, a_pc, M, K, ecut, nsp, nb, pck, grid, seed, extra in SPECS:
         if only and name not in only:
             continue
@@ -394,6 +468,7 @@ def main():
         "reference_files_sha256": {f: hashlib.sha256((REF / f).read_bytes()).hexdigest() for f in FILES},
         "fortran_statements_executed": n_stmt,
         "cases": [s[0] for s in SPECS],
+        "gur_cases": [s[0] for s in GUR_SPECS],
         "seconds": round(time.time() - t0, 1),
     }
     (here / "fortran_golden.json").write_text(json.dumps(manifest, indent=1) + "\n")

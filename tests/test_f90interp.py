@@ -426,3 +426,46 @@ end module t
     assert z.value.tolist() == [1 + 2j, 3 - 4j]
     assert c.value.tolist() == [[1 + 1j, 2 + 2j], [3 + 3j, 4 + 4j]]      # c(1,:) then c(2,:)
     assert int(ios.value) != 0 and not it.units
+
+
+def test_local_types_components_of_array_sections_and_intent_out_structures(tmp_path):
+    it = interp(tmp_path, """
+module t
+use kinds
+real(kind=dp), dimension(1:2,1:2), parameter :: eye = reshape(real((/ 1, 0, 0, 1 /), kind=dp), shape(eye))
+type :: bag
+  integer :: n
+  integer, dimension(:), allocatable :: items
+end type bag
+contains
+subroutine fill(b, n)
+  type(bag), intent(out) :: b          ! allocatable components are deallocated on entry
+  integer, intent(in) :: n
+  allocate(b%items(1:n))               ! ... so this may be called twice on the same object
+  b%items = n
+  b%n = n
+end subroutine fill
+function flags(n) result(c)
+  integer, intent(in) :: n
+  integer :: c
+  type :: entry
+    logical :: seen
+    integer :: weight
+  end type entry
+  type(entry), dimension(:), allocatable :: list
+  integer :: i
+  allocate(list(1:n))
+  do i = 1, n
+    list(i)%seen = mod(i, 3) == 0
+    list(i)%weight = i
+  enddo
+  c = 100*count(.not. list(:)%seen) + sum(list(:)%weight)
+end function flags
+end module t
+""")
+    assert np.array_equal(it.module_value("eye").value, np.eye(2))
+    b = it.new_struct("bag")
+    it.call("fill", b, np.int32(3))
+    it.call("fill", b, np.int32(2))
+    assert b["items"].tolist() == [2, 2] and int(b["n"]) == 2
+    assert int(it.call("flags", np.int32(7))) == 100 * 5 + 28

@@ -14,6 +14,7 @@ from oracle import oracle_np as ON
 
 GOLD = Path(__file__).resolve().parent / "golden"
 CASES = json.loads((GOLD / "fortran_golden.json").read_text())["cases"]
+GUR_CASES = json.loads((GOLD / "fortran_golden.json").read_text())["gur_cases"]
 DP_CASES = [c for c in CASES if c.startswith("dp_build")]        # the reference with kind_cplx_coeffs = dp
 SP_CASES = [c for c in CASES if c not in DP_CASES]
 
@@ -374,6 +375,33 @@ def test_symmetry_average_over_the_needed_directions(gold, name):
         assert np.array_equal(O.symm_average(w, pr), g["avg_spin_proj"])
 
 
+@pytest.mark.parametrize("name", GUR_CASES)
+def test_fold_search_against_the_reference_run(gold, name):
+    """get_geom_unfolding_relations as the reference ran it (-no_symm_sckpts): the first SC-kpt of the
+    list -- the skipped ones excepted -- whose difference to the pc-kpt is an SC reciprocal lattice
+    vector, with the wrapper's tolerance steps of 0.05e-5.  Brute force with the oracle's vec_in_latt."""
+    g = case(gold, name)
+    skip, attempts = int(g["n_sckpts_to_skip"]), int(g["n_attempts"])
+    tol = 1e-5 + (attempts - 1) * 0.05e-5
+
+    def brute(t):
+        out = np.full(len(g["pckpts_cart"]), -1)
+        for i, k in enumerate(g["pckpts_cart"]):
+            for s_ in range(skip, len(g["sckpts_cart"])):
+                if O.vec_in_latt(k - g["sckpts_cart"][s_], g["B_sc"], t):
+                    out[i] = s_
+                    break
+        return out
+    assert np.array_equal(brute(tol), g["fold_sckpt"])
+    assert int(g["n_folding_pckpts"]) == int(g["n_pckpts"]) == len(g["fold_sckpt"])
+    assert np.array_equal(g["folds"].sum(axis=0), np.ones(len(g["fold_sckpt"])))       # one SC-kpt each
+    assert np.array_equal(g["sckpt_used"], np.isin(np.arange(len(g["sckpts_cart"])), g["fold_sckpt"]))
+    assert np.array_equal(g["scoords"], g["pckpts_cart"])                              # identity operation only
+    if attempts > 1:
+        assert np.any(brute(tol - 0.05e-5) < 0)                                        # the attempt before failed
+        assert np.all(g["fold_sckpt"] >= skip) and skip > 0
+
+
 @pytest.mark.skipif(not Path("/root/reference/src").exists(),
                     reason="the reference sources exist in the build container only")
 @pytest.mark.parametrize("name", ["hex_spinor", "dont_unfold"])
@@ -391,3 +419,17 @@ def test_goldens_regenerate_from_the_reference_sources(gold, name):
     assert set(out) == set(g)
     for k, v in out.items():
         assert np.array_equal(np.asarray(v), g[k], equal_nan=True), k
+
+
+@pytest.mark.skipif(not Path("/root/reference/src").exists(),
+                    reason="the reference sources exist in the build container only")
+def test_fold_search_golden_regenerates(gold):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_fortran_golden", GOLD / "make_fortran_golden.py")
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    out, _ = gen.run_gur_case(*gen.GUR_SPECS[0])
+    g = case(gold, gen.GUR_SPECS[0][0])
+    assert set(out) == set(g)
+    for k, v in out.items():
+        assert np.array_equal(np.asarray(v), g[k]), k

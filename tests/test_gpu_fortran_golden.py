@@ -232,3 +232,15 @@ def test_wavecar_file_to_delta_N_against_the_reference_run(unfolder, gold, name,
     assert np.max(np.abs(ops.rho - (want[:, 4] + 1j * want[:, 5]))) <= 2e-6
     if nsp == 2:
         assert np.max(np.abs(unfolder.pauli_vectors(5, len(g["n_selected"])) - g["sigma"])) <= 5e-6
+
+
+@pytest.mark.parametrize("name", json.loads((GOLD / "fortran_golden.json").read_text())["gur_cases"])
+def test_fold_map_against_the_reference_run(unfolder, gold, name):
+    """K7 (bandup_gpu_fold_map) against the reference's get_geom_unfolding_relations run: the SC-kpt
+    every pc-kpt folds onto, skipped SC-kpts, and the tolerance the escalation ended on."""
+    g = case(gold, name)
+    unfolder.verify_commens(g["b_pc"], g["B_sc"])
+    fs, fe, tol = unfolder.get_geom_unfolding_relations(g["pckpts_cart"], g["sckpts_cart"],
+                                                        n_sckpts_to_skip=int(g["n_sckpts_to_skip"]))
+    assert np.array_equal(fs, g["fold_sckpt"]) and np.array_equal(fe, g["fold_sckpt"])
+    assert abs(tol - (1e-5 + (int(g["n_attempts"]) - 1) * 0.05e-5)) < 1e-15
