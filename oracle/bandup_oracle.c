@@ -19,8 +19,8 @@
  * calc_spectral_function, get_delta_Ns_for_output, read_wavecar on synthetic
  * WAVECAR files) on seeded inputs; tests/golden/make_fortran_golden.py is the
  * generating script and tests/golden/fortran_golden.npz the committed result
- * (11 cases, two of them the reference as a kind_cplx_coeffs = dp build;
- * 2.2 M Fortran statements).  tests/test_fortran_golden.py holds every function of this file
+ * (13 cases, two of them the reference as a kind_cplx_coeffs = dp build, two
+ * the fold search get_geom_unfolding_relations; 2.4 M Fortran statements).  tests/test_fortran_golden.py holds every function of this file
  * against those vectors: plane-wave list, renormalised coefficients, selected
  * indices, rho and the symmetry averages bit for bit; weights, delta_N and the
  * spectral function to 1e-15.  What that does NOT pin: code generation of a
