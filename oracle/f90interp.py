@@ -496,10 +496,6 @@ def _matching_paren(s, i):
     raise FortranError(f"unbalanced parentheses in {s!r}")
 
 
-class Scope:
-    """Where names are looked up while a declaration's kind/bounds are evaluated."""
-
-
 def is_declaration(stmt):
     return bool(_DECL_START.match(stmt)) and "::" in stmt and not re.match(r"^type\s*::", stmt)
 
@@ -648,7 +644,6 @@ class Interp:
                 if h and (in_contains or module is None):
                     body = []
                     i += 1
-                    depth = 1
                     while True:
                         t = stmts[i][1]
                         if re.match(r"^end\s*(subroutine|function)\b", t) or t == "end":
@@ -812,14 +807,13 @@ class Interp:
         """Call a procedure from Python.  Arguments are values, or Var objects for arguments the
         procedure defines (intent(out)/inout): read .value afterwards."""
         actuals = [(None, a) for a in args] + list(kwargs.items())
-        fr = Frame(self, None)
         prepared = []
         for kw, a in actuals:
             if isinstance(a, Var):
                 prepared.append((kw, a.value, _VarRef(a)))
             else:
                 prepared.append((kw, a, None))
-        return self._invoke(name, prepared, fr)
+        return self._invoke(name, prepared, None)
 
     def _invoke(self, name, prepared, caller):
         """prepared: [(kw, value, ref or None)]"""
@@ -901,7 +895,7 @@ class Interp:
             return fr.vars[p.result].value
         return None
 
-    def exec_statements(self, path, first_line, last_line, frame_vars, decl_source=None):
+    def exec_statements(self, path, first_line, last_line, frame_vars):
         """Execute the statements whose first physical line lies in [first_line, last_line] of a
         loaded file, with `frame_vars` {name: (value, Decl or declaration text)} as the local
         variables.  Returns the frame's variables."""
