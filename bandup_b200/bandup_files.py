@@ -194,7 +194,8 @@ def write_band_struc(path, kpath: PcKptsPath, energy_grid: np.ndarray, dN: np.nd
             f.write("# The quantization axis assumed was saxis = [%s, %s, %s]\n" % tuple(_es(v) for v in saxis))
             f.write('# The projection axis used for "#Spin _|_ k" is also _|_ to [%s, %s, %s].\n'
                     % tuple(_es(v) for v in normal_to_proj_plane))
-            f.write("#KptCoord #E-E_Fermi #delta_N   #sigma_x    #sigma_y    #sigma_z    #Spin _|_ k #Spin // k \n")
+            # '(3(A,1X), 2X, 5(A,1X))' (:930-933): the last label carries its own blank and is followed by 1X
+            f.write("#KptCoord #E-E_Fermi #delta_N   #sigma_x    #sigma_y    #sigma_z    #Spin _|_ k #Spin // k  \n")
         else:
             f.write("#KptCoord #E-E_Fermi #delta_N \n")
         coord_first = kpath.zero_of_kpts_scale

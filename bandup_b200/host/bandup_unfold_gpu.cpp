@@ -733,7 +733,8 @@ int main(int argc, char** argv) {
                    es10_3(sax[1]).c_str(), es10_3(sax[2]).c_str());
       std::fprintf(f, "# The projection axis used for \"#Spin _|_ k\" is also _|_ to [%s, %s, %s].\n",
                    es10_3(normal[0]).c_str(), es10_3(normal[1]).c_str(), es10_3(normal[2]).c_str());
-      std::fprintf(f, "#KptCoord #E-E_Fermi #delta_N   #sigma_x    #sigma_y    #sigma_z    #Spin _|_ k #Spin // k \n");
+      // '(3(A,1X), 2X, 5(A,1X))' (:930-933): the last label carries its own blank and is followed by 1X
+      std::fprintf(f, "#KptCoord #E-E_Fermi #delta_N   #sigma_x    #sigma_y    #sigma_z    #Spin _|_ k #Spin // k  \n");
     }
     else
       std::fprintf(f, "#KptCoord #E-E_Fermi #delta_N \n");

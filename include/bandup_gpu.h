@@ -235,8 +235,9 @@ int bandup_gpu_spectral_function(int handle, int ikpt, double std_dev, double *s
  * min_dN < epsilon(1.0_dp) is refused with ERR_DELTA_N_ZERO (calc_rho's fatal branch). */
 int bandup_gpu_rho_count(int handle, int ikpt, double min_dN, int64_t *n_energies,
                          int64_t *n_entries);
-/* Copies the elements counted by the last bandup_gpu_rho_count(ikpt), in the reference's
- * append order (pc-kpt, energy ascending, m1 outer, m2 inner):
+/* Copies the elements counted by the last bandup_gpu_rho_count(ikpt), in the order
+ * perform_unfolding appends them to rhos(iener2)%rho / %band_indices
+ * (band_unfolding_routines_mod.f90:1416-1427; pc-kpt, energy ascending, m1 outer, m2 inner):
  *   fold   0-based index into the submit's pc-kpt list
  *   iener  1-based index into the energy grid   (iener_in_full_pc_egrid)
  *   m1,m2  1-based band indices                 (band_indices)
@@ -370,7 +371,10 @@ int bandup_gpu_unfold_device_batch(int handle, void *stream, int n_kpts,
 int bandup_gpu_comm_unique_id(void *id);
 int bandup_gpu_comm_init(int handle, int n_ranks, int rank, const void *id);
 int bandup_gpu_comm_finalize(int handle);
-/* Collective.  dN_local [n_local][nener] + the global pc-kpt row id of every row (HOST); every
+/* Collective.  The SC-kpt loop of the reference (main_BandUP.f90:131-177) is what the ranks share;
+ * the table it fills, delta_N%...%pckpt(:)%dN, is consumed after the loop by get_delta_Ns_for_output
+ * and the writers (:187-191), which is where every rank needs all rows.
+ * dN_local [n_local][nener] + the global pc-kpt row id of every row (HOST); every
  * rank receives all rows in ascending row id: dN_all [n_total][nener], row_ids_all [n_total]
  * (HOST, capacity_rows rows).  With dN_all == NULL only *n_total is returned (the counts are
  * exchanged, no rows move).  A row id
@@ -379,7 +383,8 @@ int bandup_gpu_gather_dN(int handle, const double *dN_local, const int64_t *row_
                          int64_t n_local, double *dN_all, int64_t *row_ids_all,
                          int64_t capacity_rows, int64_t *n_total);
 
-/* The same collective for rows of any length (the spin columns: sigma rows of 3*nener doubles). */
+/* The same collective for rows of any length (the spin columns perform_unfolding fills next to dN,
+ * band_unfolding_routines_mod.f90:1431-1508: sigma rows of 3*nener doubles). */
 int bandup_gpu_gather_rows(int handle, int row_len, const double *rows_local,
                            const int64_t *row_ids_local, int64_t n_local, double *rows_all,
                            int64_t *row_ids_all, int64_t capacity_rows, int64_t *n_total);

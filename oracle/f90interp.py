@@ -964,9 +964,8 @@ class Interp:
                     self._select(st, fr)
                 elif k == "skip":
                     pass
-                elif k == "write":
-                    if st[1] not in ("*", "6", "0"):
-                        raise NotImplementedError(f"write to unit {st[1]} (only messages to the terminal are skipped)")
+                elif k == "fwrite":
+                    self._formatted_write(st[1], st[2], st[3], fr)
                 elif k in ("open", "close", "read"):
                     self._io(k, st[1], st[2], fr)
                 else:
@@ -1105,10 +1104,15 @@ class Interp:
         unit = int(val("unit"))
         if kind == "open":
             access = str(val("access", "sequential")).strip().lower()
+            if access == "sequential":       # a formatted text file, opened for writing on the first write
+                if str(val("form", "formatted")).strip().lower() != "formatted":
+                    raise NotImplementedError("sequential unformatted files")
+                self.units[unit] = (None, "sequential", str(val("file")).strip())
+                return set_iostat(0)
             if access not in ("direct", "stream"):
                 raise NotImplementedError(f"open with access='{access}'")
             if str(val("form", "unformatted")).strip().lower() != "unformatted":
-                raise NotImplementedError("formatted files")
+                raise NotImplementedError("formatted direct/stream files")
             try:
                 fh = open(str(val("file")).strip(), "rb")
             except OSError:
@@ -1117,7 +1121,7 @@ class Interp:
             return set_iostat(0)
         if kind == "close":
             ent = self.units.pop(unit, None)
-            if ent:
+            if ent and ent[0] is not None:
                 ent[0].close()
             return None
         if unit not in self.units:
@@ -1125,6 +1129,8 @@ class Interp:
         if any(k.startswith("_") or k == "fmt" for k in ctl):
             raise NotImplementedError("formatted read")
         fh, access, recl = self.units[unit]
+        if access == "sequential":
+            raise NotImplementedError("formatted sequential input")
         if access == "direct":
             start = (int(val("rec")) - 1) * recl       # recl in bytes (gfortran; ifort with -assume byterecl)
             limit = start + recl
@@ -1169,6 +1175,42 @@ class Interp:
         except EOFError:
             return set_iostat(-1)
         return set_iostat(0)
+
+    def _formatted_write(self, unit_ast, fmt_ast, items, fr):
+        unit = int(self.eval(unit_ast, fr))
+        if unit not in self.units or self.units[unit][1] != "sequential":
+            raise FortranError(f"formatted write to unit {unit}, which is not open for it")
+        if fmt_ast is None or (fmt_ast[0] == "name" and fmt_ast[1] == "*"):
+            raise NotImplementedError("list-directed output")
+        fmt = self.eval(fmt_ast, fr)
+        values = []
+
+        def emit(it):
+            if it[0] == "ido":
+                _, exprs, var, lo, hi, stp = it
+                v = fr.lookup(var)
+                s_ = int(self.eval(stp, fr)) if stp is not None else 1
+                i, h = int(self.eval(lo, fr)), int(self.eval(hi, fr))
+                while (s_ > 0 and i <= h) or (s_ < 0 and i >= h):
+                    v.value = I4(i)
+                    for x in exprs:
+                        emit(x)
+                    i += s_
+                v.value = I4(i)
+            else:
+                x = self.eval(it, fr)
+                if isinstance(x, np.ndarray):
+                    values.extend(x.reshape(-1, order="F"))
+                else:
+                    values.append(x)
+        for it in items:
+            emit(it)
+        text = format_record(fmt, values)
+        fh, access, path = self.units[unit]
+        if fh is None:
+            fh = open(path, "w")
+            self.units[unit] = (fh, access, path)
+        fh.write(text)
 
     # ---- references (things that can be assigned to) ----------------------------------------
     def ref(self, ast, fr):
@@ -1601,9 +1643,33 @@ def parse_block(stmts, i, terminators):
                         break
                     p.expect(",")
             block.append((kw, ctl, items, no))
-        elif re.match(r"^(write|print)\b", s):
-            m = re.match(r"^write\s*\(\s*(?:unit\s*=\s*)?([^,)]*)", s)
-            block.append(("write", m.group(1).strip() if m else "*", no))
+        elif re.match(r"^write\s*\(", s):
+            inside, rest = _head_paren(s, "write")
+            parts = _split_top(inside)
+            unit_txt = re.sub(r"^unit\s*=\s*", "", parts[0]).strip()
+            if unit_txt in ("*", "6", "0"):              # a message to the terminal: not evaluated at all
+                block.append(("skip", no))
+            else:
+                fmt_txt = None
+                for pos, part in enumerate(parts[1:], 1):
+                    eq = _top_level_eq(part)
+                    if eq >= 0 and part[:eq].strip() == "fmt":
+                        fmt_txt = part[eq + 1:].strip()
+                    elif eq < 0 and pos == 1:
+                        fmt_txt = part.strip()
+                    else:
+                        raise FortranError(f"line {no}: write control item {part!r} is not supported")
+                items = []
+                if rest:
+                    p = Parser(tokenize(rest))
+                    while True:
+                        items.append(p.ac_item())
+                        if p.at_end():
+                            break
+                        p.expect(",")
+                block.append(("fwrite", parse_expr(unit_txt), None if fmt_txt is None else parse_expr(fmt_txt), items, no))
+        elif re.match(r"^print\b", s):
+            block.append(("skip", no))
         elif re.match(r"^(rewind|flush|format|nullify)\b", s) and _top_level_eq(s) < 0:
             block.append(("skip", no))
         else:
@@ -1781,6 +1847,135 @@ def binop(op, a, b):
                 return q[()] if q.ndim == 0 else q
             return x / y
     raise FortranError(f"operator {op}")
+
+
+# --------------------------------------------------------------------------------------------
+# formatted output: the edit descriptors the reference's writers use
+# --------------------------------------------------------------------------------------------
+
+def _parse_format(spec):
+    """'(2(f8.4,2X),ES10.3)' -> a nested list of (repeat, item); item = ('lit', text), ('x', n), ('/',),
+    ('a', w), ('i', w), ('f', w, d), ('es', w, d), ('e', w, d) or a nested list."""
+    s = spec.strip()
+    if not (s.startswith("(") and s.endswith(")")):
+        raise FortranError(f"format {spec!r}")
+    pos = [1]
+
+    def group():
+        out = []
+        while True:
+            while pos[0] < len(s) and s[pos[0]] in " ,":
+                pos[0] += 1
+            ch = s[pos[0]]
+            if ch == ")":
+                pos[0] += 1
+                return out
+            if ch in "'\"":
+                j = pos[0] + 1
+                buf = []
+                while True:
+                    if s[j] == ch:
+                        if j + 1 < len(s) and s[j + 1] == ch:
+                            buf.append(ch)
+                            j += 2
+                            continue
+                        break
+                    buf.append(s[j])
+                    j += 1
+                out.append((1, ("lit", "".join(buf))))
+                pos[0] = j + 1
+                continue
+            if ch == "/":
+                out.append((1, ("/",)))
+                pos[0] += 1
+                continue
+            m = re.match(r"(\d+)?\s*", s[pos[0]:])
+            rep = int(m.group(1)) if m.group(1) else None
+            pos[0] += m.end()
+            ch = s[pos[0]]
+            if ch == "(":
+                pos[0] += 1
+                out.append((rep or 1, group()))
+                continue
+            m = re.match(r"(es|en|[a-z])\s*(\d+)?(?:\.(\d+))?", s[pos[0]:].lower())
+            if not m:
+                raise FortranError(f"format {spec!r} at {s[pos[0]:]!r}")
+            pos[0] += m.end()
+            code, w, d = m.group(1), m.group(2), m.group(3)
+            if code == "x":
+                out.append((1, ("x", rep or 1)))
+            elif code in ("a", "i", "l"):
+                out.append((rep or 1, (code, int(w) if w else None)))
+            elif code in ("f", "es", "e", "d", "g"):
+                out.append((rep or 1, (code, int(w), int(d))))
+            else:
+                raise NotImplementedError(f"edit descriptor {code!r} in {spec!r}")
+    return group()
+
+
+def _fmt_es(x, w, d):
+    t = f"{float(x):.{d}E}"
+    mant, ex = t.split("E")
+    e = int(ex)
+    body = mant + (f"E{'+' if e >= 0 else '-'}{abs(e):02d}" if abs(e) <= 99 else f"{'+' if e >= 0 else '-'}{abs(e):03d}")
+    return body.rjust(w) if len(body) <= w else "*" * w
+
+
+def _fmt_f(x, w, d):
+    t = f"{float(x):.{d}f}"
+    if len(t) > w and t.startswith("0."):
+        t = t[1:]
+    elif len(t) > w and t.startswith("-0."):
+        t = "-" + t[2:]
+    return t.rjust(w) if len(t) <= w else "*" * w
+
+
+def format_record(spec, values):
+    """One formatted WRITE: the text it produces, records ending in a newline (no format reversion:
+    more items than data descriptors is refused)."""
+    flat = []
+
+    def expand(items):
+        for rep, it in items:
+            for _ in range(rep):
+                if isinstance(it, list):
+                    expand(it)
+                else:
+                    flat.append(it)
+    expand(_parse_format(spec))
+    out, line, vi = [], [], 0
+    for it in flat:
+        k = it[0]
+        if k == "lit":
+            line.append(it[1])
+        elif k == "x":
+            line.append(" " * it[1])
+        elif k == "/":
+            out.append("".join(line))
+            line = []
+        else:
+            if vi >= len(values):
+                break                         # output stops at the first data descriptor without an item
+            v = values[vi]
+            vi += 1
+            if k == "a":
+                t = str(v)
+                line.append(t if it[1] is None else (t.rjust(it[1]) if len(t) <= it[1] else t[:it[1]]))
+            elif k == "i":
+                t = str(int(v))
+                line.append(t if not it[1] else (t.rjust(it[1]) if len(t) <= it[1] else "*" * it[1]))
+            elif k == "l":
+                line.append(("T" if bool(v) else "F").rjust(it[1] or 1))
+            elif k == "f":
+                line.append(_fmt_f(v, it[1], it[2]))
+            elif k == "es":
+                line.append(_fmt_es(v, it[1], it[2]))
+            else:
+                raise NotImplementedError(f"edit descriptor {k!r}")
+    if vi < len(values):
+        raise NotImplementedError("format reversion (more output items than data edit descriptors)")
+    out.append("".join(line))
+    return "\n".join(out) + "\n"
 
 
 # --------------------------------------------------------------------------------------------

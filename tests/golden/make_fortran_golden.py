@@ -50,7 +50,8 @@ def interpreter(perform_unfold=True, write_unf_dens_op=True, dp_build=False):
         it.mod_vals["kind_cplx_coeffs"] = F.Var(I4(int(it.module_value("dp").value)), it.mod_decls["kind_cplx_coeffs"])
     it.overrides["time_now"] = lambda: R8(0.0)
     args = F.FStruct("comm_line_args", perform_unfold=LG(perform_unfold), write_unf_dens_op=LG(write_unf_dens_op),
-                     normal_to_proj_plane=np.array([0.0, 0.0, 1.0]), no_symm_sckpts=LG(True),
+                     normal_to_proj_plane=np.array([0.0, 0.0, 1.0]), saxis=np.array([0.0, 0.0, 1.0]),
+                     no_symm_sckpts=LG(True),
                      origin_for_spin_proj_passed_in_rec=LG(False), origin_for_spin_proj_cartesian=np.zeros(3),
                      origin_for_spin_proj_rec=np.zeros(3), n_sckpts_to_skip=I4(0))
     it.set_module_variable("args", args)
@@ -281,6 +282,15 @@ def run_case(name, a_pc, M, kpt_frac, ecut, n_spinor, n_bands, pc_kpts_frac_sc, 
         if n_spinor == 2:
             out["avg_sigma"] = np.array([p["sigma"] for p in pk])
             out["avg_spin_proj"] = np.array([np.stack([p["spin_proj_perp"], p["spin_proj_para"]], axis=1) for p in pk])
+        # ---- write_band_struc: the unfolded_EBS_*.dat file of the averaged quantities (io_routines_mod.f90:889-977)
+        import tempfile
+        it.overrides["file_header_bandup"] = lambda: "# File created by BandUP (interpreted for a golden vector)"
+        with tempfile.TemporaryDirectory() as tmp:
+            ebs = Path(tmp) / "unfolded_EBS_symmetry-averaged.dat"
+            it.call("write_band_struc", str(ebs), gur["sckpt"][0], egrid, avgd, ef=R8(0.37), zero_of_kpts_scale=R8(0.25))
+            assert not it.units
+            out["ebs_file"] = np.frombuffer(ebs.read_bytes(), dtype=np.uint8).copy()
+        out["ebs_e_fermi"], out["ebs_zero_of_kpts_scale"] = np.array(0.37), np.array(0.25)
         # what "only the selected directions" keeps is the first needed direction, unchanged
         assert all(np.array_equal(a["dn"], b["dn"]) for a, b in
                    zip(only_sel["pcbz_dir"][0]["pckpt"], delta_N["selec_pcbz_dir"][0]["needed_dir"][0]["pckpt"]))

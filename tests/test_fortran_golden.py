@@ -375,6 +375,28 @@ def test_symmetry_average_over_the_needed_directions(gold, name):
         assert np.array_equal(O.symm_average(w, pr), g["avg_spin_proj"])
 
 
+@pytest.mark.parametrize("name", AVG_CASES)
+def test_unfolded_ebs_file_is_what_the_reference_writes(gold, name, tmp_path):
+    """write_band_struc (io_routines_mod.f90:889-977), executed from the reference on the averaged
+    quantities of the case, against bandup_files.write_band_struc (what BandUP_gpu.x and unfold_task
+    write): every byte after the first header line (which carries version and time stamp)."""
+    from bandup_b200 import bandup_files as BF
+    g = case(gold, name)
+    want = g["ebs_file"].tobytes().decode()
+    n_dirs = int(g["n_dirs"])
+    n_k = len(g["n_selected"]) // n_dirs
+    kpath = BF.PcKptsPath([g["pckpts_cart"][:n_k]], float(g["ebs_zero_of_kpts_scale"]))   # the first needed direction
+    out = tmp_path / "ebs.dat"
+    spinor = "avg_sigma" in g
+    BF.write_band_struc(out, kpath, g["energy_grid"], g["avg_delta_N"], e_fermi=float(g["ebs_e_fermi"]),
+                        sigma=g["avg_sigma"] if spinor else None, spin_proj=g["avg_spin_proj"] if spinor else None)
+    got = out.read_text()
+    assert got.splitlines()[0].startswith("# File created by") and want.splitlines()[0].startswith("# File created by")
+    assert got.split("\n", 1)[1] == want.split("\n", 1)[1]
+    data = BF.read_band_struc(out)                                   # and it loads the way `bandup plot` loads it
+    assert data.shape == (n_k * len(g["energy_grid"]), 8 if spinor else 3)
+
+
 @pytest.mark.parametrize("name", GUR_CASES)
 def test_fold_search_against_the_reference_run(gold, name):
     """get_geom_unfolding_relations as the reference ran it (-no_symm_sckpts): the first SC-kpt of the
