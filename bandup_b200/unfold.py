@@ -606,6 +606,55 @@ def pinned_empty(nbytes: int) -> np.ndarray:
     return arr
 
 
+def pick_fastest(rates: Sequence[float], n_keep: int) -> List[int]:
+    """Indices of the n_keep candidates to keep: anything within 2 % of the best counts as equally
+    near and then the lower index wins (no churn on a box whose memory is all alike); the rest by rate."""
+    fast = max(rates) * 0.98
+    order = sorted(range(len(rates)), key=lambda i: (0, i) if rates[i] >= fast else (1, -rates[i]))
+    return sorted(order[:n_keep])
+
+
+def pinned_empty_near(nbytes: int, n_keep: int = 1, spares: int = 2, device: int = 0, slice_mb: int = 256):
+    """n_keep page-locked buffers of nbytes each, chosen by MEASUREMENT among n_keep + spares
+    candidates: the ones a host->device copy reads fastest.  Returns (buffers, GB/s of every
+    candidate, indices kept).
+
+    Why: the GPU boxes are virtual machines that show ONE NUMA node (numa_node = -1, `lscpu`: one
+    socket) while their memory spans the host's sockets, so there is nothing to bind to -- yet a block
+    that happens to lie behind the far socket uploads at 42-48 GB/s instead of the link's 55.5
+    (same box, same GPU, one process in three: gpurun_out/r02x_bench*.json).  The copy engine can
+    tell the blocks apart even though sysfs cannot.  torch only provides the device scratch, the
+    stream and the events of the timing."""
+    import torch
+    n_keep, spares = max(1, int(n_keep)), max(0, int(spares))
+    cands = [pinned_empty(nbytes) for _ in range(n_keep + spares)]
+    if spares == 0:
+        return cands, [None] * n_keep, list(range(n_keep))
+    step = min(int(nbytes), int(slice_mb) << 20)
+    with torch.cuda.device(device):
+        scratch = torch.empty(step, dtype=torch.uint8, device=f"cuda:{device}")
+        stream = torch.cuda.Stream(device=device)
+        rates = []
+        for h in cands:
+            src = torch.from_numpy(h)
+            with torch.cuda.stream(stream):
+                scratch.copy_(src[:step], non_blocking=True)          # warm the mapping
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for off in range(0, int(nbytes) - step + 1, step):
+                    scratch.copy_(src[off:off + step], non_blocking=True)
+                b.record()
+            stream.synchronize()
+            moved = ((int(nbytes) - step) // step + 1) * step
+            rates.append(moved / (a.elapsed_time(b) * 1e-3) / 1e9)
+        del scratch
+    keep = pick_fastest(rates, n_keep)
+    for i in range(len(cands)):
+        if i not in keep:
+            pinned_free(cands[i])
+    return [cands[i] for i in keep], [round(r, 2) for r in rates], keep
+
+
 def host_register(arr: np.ndarray) -> None:
     """Page-lock a NumPy array the caller owns, in place (bandup_gpu_host_register), so that
     submits from it are asynchronous DMA; host_unregister(arr) before it is freed."""

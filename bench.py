@@ -92,6 +92,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="do not pin the rank to the CPU cores of its GPU's NUMA node")
+    ap.add_argument("--no-pinned-probe", action="store_true",
+                    help="e2e: take the first page-locked blocks instead of the fastest of four candidates")
     ap.add_argument("--tuning", default="", help="chunk_vecs,ctas_per_sm,n_stages of K2 (0 = default), for sweeps")
     ap.add_argument("--per-kpt-launch", action="store_true",
                     help="launch K1..K3 once per SC k-point instead of once per step (batch)")
@@ -580,7 +582,7 @@ def run_b200(args, sc, rank, world, local_rank):
         _build.build()
         devinfo = device_for_local_rank(local_rank, local_world)
         cuda_idx = devinfo["device"]
-    from bandup_b200.unfold import (GpuUnfolder, PwWavefunction, LAYOUT_FORTRAN_INMEM, pinned_empty, pinned_free, K_COSET,
+    from bandup_b200.unfold import (GpuUnfolder, PwWavefunction, LAYOUT_FORTRAN_INMEM, pinned_empty, pinned_empty_near, pinned_free, K_COSET,
                                     K_WEIGHTS, K_DELTA_N)
 
     from bandup_b200._capi import CONST
@@ -786,9 +788,16 @@ def run_b200(args, sc, rank, world, local_rank):
     if not args.no_e2e:
         n_e2e = args.e2e_steps or min(args.steps, 8)
         host = []
-        for it in items[:2]:     # two distinct pinned blocks, cycled (2 x 2.4 GB per rank)
+        # two distinct pinned blocks, cycled (2 x 2.4 GB per rank), the two of four candidates that a
+        # host->device copy reads fastest: the boxes are VMs with a hidden host NUMA layout
+        # (bandup_b200.unfold.pinned_empty_near)
+        src_items = items[:2]
+        blk_max = max(nb * it["n_pw"] * nsp * esz for it in src_items)
+        blocks, cand_rates, cand_kept = pinned_empty_near(blk_max, n_keep=len(src_items),
+                                                          spares=0 if args.no_pinned_probe else 2, device=cuda_idx)
+        for h_full, it in zip(blocks, src_items):
             nbytes = nb * it["n_pw"] * nsp * esz
-            h = pinned_empty(nbytes)
+            h = h_full[:nbytes]
             torch.from_numpy(h).copy_(it["d_c"].view(torch.uint8).reshape(-1))
             host.append((h, it))
         torch.cuda.synchronize()
@@ -894,7 +903,10 @@ def run_b200(args, sc, rank, world, local_rank):
                "e2e_check": "every rank's last fetched weights / delta_N / n_selected / norms == the device-resident "
                             "entry point's for the same block, bit for bit (outside the timed region)",
                "timer": "host monotonic clock between device synchronisations, max over ranks",
-               "bound": "cudaMemcpyAsync H2D of the coefficient blocks over the host PCIe fabric", "numa": numa}
+               "bound": "cudaMemcpyAsync H2D of the coefficient blocks over the host PCIe fabric", "numa": numa,
+               "pinned_block_probe": {"candidates_GBps": cand_rates, "kept": cand_kept,
+                                      "what": "rank 0's page-locked candidate blocks, one timed upload each; the fastest are "
+                                              "the job's host buffers (the VM hides the host's NUMA layout)"}}
         if world == 1:
             # the drop-in caller's case: the same call from PAGEABLE memory (a Fortran ALLOCATE), which
             # the library moves through its pinned staging ring; informational, not the headline

@@ -998,6 +998,26 @@ def test_pageable_staging_handles_odd_sizes_and_misaligned_sources(unfolder, off
     pinned_free(pin)
 
 
+def test_pinned_blocks_chosen_by_measured_upload_rate(unfolder):
+    """pinned_empty_near: n_keep + spares page-locked candidates, one timed upload each, the
+    fastest kept (the VM hides which host socket a block lies behind); the kept blocks are ordinary
+    page-locked buffers of the library's allocator."""
+    from bandup_b200.unfold import _PINNED, pinned_empty_near, pinned_free
+    live = len(_PINNED)
+    nbytes = (24 << 20) + 40
+    bufs, rates, kept = pinned_empty_near(nbytes, n_keep=2, spares=2, slice_mb=8)
+    assert len(bufs) == 2 and len(rates) == 4 and kept == sorted(kept) and len(set(kept)) == 2
+    assert all(r > 1.0 for r in rates) and min(rates[i] for i in kept) >= 0.98 * max(r for i, r in enumerate(rates) if i not in kept)
+    assert all(b.size == nbytes and b.dtype == np.uint8 for b in bufs) and len(_PINNED) == live + 2
+    bufs[0][:] = 7
+    for b in bufs:
+        pinned_free(b)
+    one, r1, k1 = pinned_empty_near(1 << 20, spares=0)
+    assert len(one) == 1 and r1 == [None] and k1 == [0]
+    pinned_free(one[0])
+    assert len(_PINNED) == live
+
+
 @pytest.mark.parametrize("name,scale,n_kpts", [("graphene4x4", 0.08, 36), ("si333_vacancy", 0.12, 48)])
 def test_device_batch_of_many_kpoints(unfolder, name, scale, n_kpts):
     """A whole (shrunken) job in ONE batch: dozens of SC k-points make K3 give every warp several

@@ -49,3 +49,12 @@ def test_greedy_order_avoids_the_shared_host_path():
     # no sharing at all: index order
     assert greedy_order(4, lambda devs: 55.0 * len(devs))[0] == [0, 1, 2, 3]
     assert greedy_order(0, total) == ([], [])
+
+
+def test_pinned_candidates_are_picked_by_rate_with_stable_ties():
+    """bandup_b200.unfold.pick_fastest: the rule behind pinned_empty_near (the timing itself needs a GPU)."""
+    from bandup_b200.unfold import pick_fastest
+    assert pick_fastest([55.54, 55.55, 55.55, 55.53], 2) == [0, 1]          # all alike: first come
+    assert pick_fastest([42.1, 55.5, 47.0, 55.4], 2) == [1, 3]              # two far blocks dropped
+    assert pick_fastest([42.1, 55.5, 47.0, 43.0], 2) == [1, 2]              # one near block: next best by rate
+    assert pick_fastest([50.0], 1) == [0]
