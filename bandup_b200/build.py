@@ -21,7 +21,7 @@ LIB = LIBDIR / "libbandup_gpu.so"
 HOST_SRC = PKG / "host" / "bandup_unfold_gpu.cpp"
 HOST_EXE = LIBDIR / "BandUP_gpu.x"   # the native (C++) host above the C ABI: `bandup unfold` without symmetry
 SOURCES = ["capi.cu", "capi_projected.cu", "capi_symm.cu", "coset_classify.cu", "weights_reduce.cu", "delta_n.cu", "rho.cu", "symm_average.cu", "gvecs.cu", "fold_map.cu", "comm.cu", "synth.cu"]
-HEADERS = [CSRC / "kernels.cuh", CSRC / "ctx.cuh", CSRC / "nccl_dyn.h", PKG.parent / "include" / "bandup_gpu.h"]
+HEADERS = [CSRC / "kernels.cuh", CSRC / "ctx.cuh", CSRC / "nccl_dyn.h", CSRC / "stage_pipeline.h", PKG.parent / "include" / "bandup_gpu.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -9,15 +9,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#if defined(__x86_64__)
-#include <emmintrin.h>
-#endif
-#include <condition_variable>
 #include <cstdint>
 #include <memory>
 #include <thread>
 
 #include "ctx.cuh"
+#include "stage_pipeline.h"
 
 namespace bandup {
 
@@ -133,87 +130,31 @@ void resolve_pending(Ctx* c) {
 // Host -> device copy of a coefficient block on the copy stream.  Page-locked memory
 // (bandup_gpu_pinned_alloc, bandup_gpu_host_register) is a single asynchronous DMA.  Pageable
 // memory -- what a Fortran ALLOCATE gives the reference's reader -- would make cudaMemcpyAsync
-// stage it internally at 2-3 GB/s (measured); here it is cut into 16 MB chunks that a few host
-// threads copy into a ring of page-locked buffers while the previous chunks are on the wire.
+// stage it internally at 2-3 GB/s (measured); here it goes through the staging pipeline of
+// stage_pipeline.h: 16 MB chunks through a ring of page-locked buffers, copied in 256 KB pieces by a
+// few host threads while the previous chunks are on the wire.
 constexpr size_t kStageChunk = size_t(16) << 20;
+constexpr size_t kStagePiece = size_t(256) << 10;
 
-// The staging buffer is written once and next read by the DMA engine: streaming (non-temporal)
-// stores skip the read-for-ownership of the destination lines, a third of the copy's DRAM traffic.
-inline void stream_copy(char* dst, const char* src, size_t n) {
-#if defined(__x86_64__) && defined(__SSE2__)
-  size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
-  if (head > n) head = n;
-  std::memcpy(dst, src, head);
-  dst += head; src += head; n -= head;
-  const size_t blocks = n / 64;
-  for (size_t i = 0; i < blocks; ++i) {
-    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src));
-    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 16));
-    const __m128i c2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 32));
-    const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 48));
-    _mm_stream_si128(reinterpret_cast<__m128i*>(dst), a);
-    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 16), b);
-    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 32), c2);
-    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 48), d);
-    src += 64; dst += 64;
-  }
-  _mm_sfence();
-  std::memcpy(dst, src, n - blocks * 64);
-#else
-  std::memcpy(dst, src, n);
-#endif
-}
-
-struct StagePool {
-  std::vector<std::thread> threads;
-  std::mutex m;
-  std::condition_variable cv_work, cv_done;
-  bool stop = false;
-  long job = 0;       // incremented for every block
-  long ready = -1;    // chunks of the current job released for copying
-  long n_chunks = 0;
-  int n_workers = 0;  // worker threads (the caller's thread copies slice 0 itself)
-  std::vector<int> done;  // workers finished with chunk i
-  // the current block
-  const char* base = nullptr;
-  char* stage_ptr[Ctx::kStageBufs] = {nullptr, nullptr, nullptr};
-  size_t chunk = 0, bytes = 0, part = 0;
-  int k0 = 0;
-
-  void copy_slice(long i, int t) const {
-    const size_t off = (size_t)i * chunk, n = std::min(chunk, bytes - off), a = part * (size_t)t;
-    if (a < n) stream_copy(stage_ptr[(k0 + i) % Ctx::kStageBufs] + a, base + off + a, std::min(part, n - a));
-  }
-  void worker(int t) {
-    long seen = 0;
-    std::unique_lock<std::mutex> lk(m);
-    for (;;) {
-      cv_work.wait(lk, [&] { return stop || job != seen; });
-      if (stop) return;
-      seen = job;
-      for (long i = 0; i < n_chunks; ++i) {
-        cv_work.wait(lk, [&] { return stop || ready >= i; });
-        if (stop) return;
-        if (ready >= n_chunks) break;  // the caller gave up on this block
-        lk.unlock();
-        copy_slice(i, t);
-        lk.lock();
-        if (++done[(size_t)i] == n_workers) cv_done.notify_one();
-      }
+struct StageTuning {  // BANDUP_GPU_STAGE_CHUNK_KB / _PIECE_KB / _NT: for sweeps (scripts/gpu_stage.sh)
+  size_t chunk = kStageChunk, piece = kStagePiece;
+  bool streaming = true;
+  StageTuning() {
+    if (const char* e = std::getenv("BANDUP_GPU_STAGE_CHUNK_KB")) {
+      const long kb = std::atol(e);
+      if (kb >= 64 && kb <= (long)(kStageChunk >> 10)) chunk = (size_t)kb << 10;
     }
-  }
-  explicit StagePool(int n_thr) : n_workers(n_thr - 1) {
-    for (int t = 1; t < n_thr; ++t) threads.emplace_back([this, t] { worker(t); });
-  }
-  ~StagePool() {
-    {
-      std::lock_guard<std::mutex> lk(m);
-      stop = true;
+    if (const char* e = std::getenv("BANDUP_GPU_STAGE_PIECE_KB")) {
+      const long kb = std::atol(e);
+      if (kb >= 4) piece = (size_t)kb << 10;
     }
-    cv_work.notify_all();
-    for (auto& th : threads) th.join();
+    if (const char* e = std::getenv("BANDUP_GPU_STAGE_NT")) streaming = std::atoi(e) != 0;
   }
 };
+const StageTuning& stage_tuning() {
+  static const StageTuning t;
+  return t;
+}
 
 void stage_pool_destroy(Ctx* c) {
   delete c->stage_pool;
@@ -237,6 +178,28 @@ int stage_threads() {
   return std::max(1, std::min(n, 8));
 }
 
+namespace {
+struct CopyStreamWire {  // the wire of the staging pipeline: DMAs on the context's copy stream
+  Ctx* c;
+  char* dst;
+  cudaError_t err = cudaSuccess;
+  bool ready(int k) {
+    const cudaError_t e = cudaEventQuery(c->stage_free[k]);  // never recorded yet: success
+    if (e == cudaErrorNotReady) {
+      cudaGetLastError();  // not an error, but the runtime remembers it as the last one
+      return false;
+    }
+    if (e != cudaSuccess && err == cudaSuccess) err = e;  // let the next send report it
+    return true;
+  }
+  int send(int k, size_t off, size_t n) {
+    if (err == cudaSuccess) err = cudaMemcpyAsync(dst + off, c->stage[k].p, n, cudaMemcpyHostToDevice, c->copy);
+    if (err == cudaSuccess) err = cudaEventRecord(c->stage_free[k], c->copy);
+    return err == cudaSuccess ? 0 : 1;
+  }
+};
+}  // namespace
+
 int upload_block(Ctx* c, void* dst, const void* src, size_t bytes) {
   cudaPointerAttributes attr{};
   const bool locked = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
@@ -247,59 +210,21 @@ int upload_block(Ctx* c, void* dst, const void* src, size_t bytes) {
     return BANDUP_GPU_OK;
   }
   if (!c->stage_pool) c->stage_pool = new StagePool(stage_threads());
-  StagePool& sp = *c->stage_pool;
-  const int n_thr = sp.n_workers + 1;
   // small blocks: smaller chunks, so that the wire starts early and the ring still overlaps
-  const size_t chunk = std::min(kStageChunk, std::max(size_t(1) << 20, (bytes / 8 + 4095) & ~size_t(4095)));
+  const StageTuning& tune = stage_tuning();
+  const size_t chunk = std::min(tune.chunk, std::max(std::min(size_t(1) << 20, tune.chunk), (bytes / 8 + 4095) & ~size_t(4095)));
   const long n_chunks = (long)((bytes + chunk - 1) / chunk);
+  char* ring[Ctx::kStageBufs];
   for (int k = 0; k < Ctx::kStageBufs; ++k) {
     CU(c->stage[k].reserve(kStageChunk));
     if (!c->stage_free[k]) CU(cudaEventCreateWithFlags(&c->stage_free[k], cudaEventDisableTiming));
+    ring[k] = static_cast<char*>(c->stage[k].p);
   }
-  // Chunk i may be written once `ready` has reached i (its ring buffer has been released by the
-  // DMA of chunk i - kStageBufs); every thread copies its slice of the chunk and counts itself in
-  // done[i]; the caller's thread takes slice 0 and puts the chunk on the wire when all slices have
-  // landed.
-  {
-    std::lock_guard<std::mutex> lk(sp.m);
-    sp.base = static_cast<const char*>(src);
-    for (int k = 0; k < Ctx::kStageBufs; ++k) sp.stage_ptr[k] = static_cast<char*>(c->stage[k].p);
-    sp.chunk = chunk;
-    sp.bytes = bytes;
-    sp.part = ((chunk + (size_t)n_thr - 1) / (size_t)n_thr + 4095) & ~size_t(4095);
-    sp.k0 = c->stage_next;
-    sp.n_chunks = n_chunks;
-    sp.ready = -1;
-    sp.done.assign((size_t)n_chunks, 0);
-    sp.job++;
-  }
-  sp.cv_work.notify_all();
-  cudaError_t err = cudaSuccess;
-  for (long i = 0; i < n_chunks && err == cudaSuccess; ++i) {
-    const int k = (int)((sp.k0 + i) % Ctx::kStageBufs);
-    err = cudaEventSynchronize(c->stage_free[k]);  // never recorded yet: returns at once
-    if (err != cudaSuccess) break;
-    {
-      std::lock_guard<std::mutex> lk(sp.m);
-      sp.ready = i;
-    }
-    sp.cv_work.notify_all();
-    sp.copy_slice(i, 0);
-    {
-      std::unique_lock<std::mutex> lk(sp.m);
-      sp.cv_done.wait(lk, [&] { return sp.done[(size_t)i] >= sp.n_workers; });
-    }
-    const size_t off = (size_t)i * chunk, n = std::min(chunk, bytes - off);
-    err = cudaMemcpyAsync(static_cast<char*>(dst) + off, sp.stage_ptr[k], n, cudaMemcpyHostToDevice, c->copy);
-    if (err == cudaSuccess) err = cudaEventRecord(c->stage_free[k], c->copy);
-  }
-  {
-    std::lock_guard<std::mutex> lk(sp.m);
-    sp.ready = n_chunks;  // releases workers still waiting after an error; a finished job stays finished
-  }
-  sp.cv_work.notify_all();
-  c->stage_next = (int)((sp.k0 + n_chunks) % Ctx::kStageBufs);
-  if (err != cudaSuccess) return cuda_fail(c, err, "staging a pageable block");
+  CopyStreamWire wire{c, static_cast<char*>(dst)};
+  const int rc = c->stage_pool->run(static_cast<const char*>(src), bytes, ring, Ctx::kStageBufs, c->stage_next, chunk,
+                                    tune.piece, wire, tune.streaming);
+  c->stage_next = (int)((c->stage_next + n_chunks) % Ctx::kStageBufs);
+  if (rc != 0) return cuda_fail(c, wire.err, "staging a pageable block");
   return BANDUP_GPU_OK;
 }
 

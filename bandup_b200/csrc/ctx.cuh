@@ -76,10 +76,10 @@ struct DescSlot {  // pinned + device staging of one batch's descriptor block (K
   bool valid = false;
 };
 
-// Host threads that copy slices of a pageable block into the page-locked staging ring
-// (upload_block).  They live as long as the context and sleep on a condition variable between
-// blocks; one job at a time (the ABI is single-caller per handle).
-struct StagePool;
+// Host threads that copy pieces of a pageable block into the page-locked staging ring
+// (upload_block, stage_pipeline.h).  They live as long as the context and sleep on a condition
+// variable between blocks; one job at a time (the ABI is single-caller per handle).
+class StagePool;
 
 struct Flight {  // one SC k-point in flight
   bool busy = false;      // submitted, not fetched yet
@@ -126,9 +126,9 @@ struct Ctx {
   DevBuf comm_send, comm_recv;
   DevBuf gvec_scratch;  // per-CTA counts/offsets of the device plane-wave enumeration
   // pageable caller memory goes to the device through these page-locked chunks (upload_block)
-  static constexpr int kStageBufs = 3;
+  static constexpr int kStageBufs = 4;
   PinBuf stage[kStageBufs];
-  cudaEvent_t stage_free[kStageBufs] = {nullptr, nullptr, nullptr};
+  cudaEvent_t stage_free[kStageBufs] = {};
   int stage_next = 0;
   DevBuf avg_in, avg_out, avg_tmp;  // symmetry averaging (K8/K9) staging
   DevBuf d_proj_dual, d_proj, d_ao_mask, d_proj_ener;  // inputs of the orbital-contribution matrix
