@@ -794,7 +794,8 @@ def run_b200(args, sc, rank, world, local_rank):
         src_items = items[:2]
         blk_max = max(nb * it["n_pw"] * nsp * esz for it in src_items)
         blocks, cand_rates, cand_kept = pinned_empty_near(blk_max, n_keep=len(src_items),
-                                                          spares=0 if args.no_pinned_probe else 2, device=cuda_idx)
+                                                          spares=0 if args.no_pinned_probe else (2 if world == 1 else 1),
+                                                          device=cuda_idx)
         for h_full, it in zip(blocks, src_items):
             nbytes = nb * it["n_pw"] * nsp * esz
             h = h_full[:nbytes]

@@ -7,13 +7,16 @@ T=${1:-rf}
 cp bandup_b200/lib/libbandup_gpu.digest gpurun_out/${T}_lib.digest
 python __graft_entry__.py --smoke > gpurun_out/${T}_smoke.log 2>&1; tail -2 gpurun_out/${T}_smoke.log
 timeout 1500 python -m pytest tests -m gpu -q --maxfail=15 -rf -s 2>&1 | grep -v "^$" | tail -40 > gpurun_out/${T}_pytest.log; tail -6 gpurun_out/${T}_pytest.log
+CMD="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --min-seconds 0"
+$CMD > gpurun_out/${T}_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_ncu1.log 2>&1
+$CMD > gpurun_out/${T}_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k2_weights_reduce -s 1 -c 2 -o gpurun_out/${T}_k2 $CMD > gpurun_out/${T}_ncu2.log 2>&1
+# the K2 capture stamps profiles/k2_traffic.json (on this box's copy of the repo) BEFORE the bench lines are
+# taken, so that they carry roofline.traffic of this very build; the same summary is re-made at home
+python scripts/summarize_ncu.py ${T} ${T}box > gpurun_out/${T}_summarize.log 2>&1; cp profiles/k2_traffic.json gpurun_out/${T}_k2_traffic.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_ref.json 2>gpurun_out/${T}_ref.err
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; tail -3 gpurun_out/${T}_bench.err
 for wl in graphene4x4 si333_vacancy mos2_8x8_spinor; do timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --workload $wl > gpurun_out/${T}_bench_$wl.json 2>gpurun_out/${T}_bench_$wl.err; done
 timeout 600 python bench.py --steps 10 --warmup 3 --complex128 > gpurun_out/${T}_bench_c128.json 2>gpurun_out/${T}_bench_c128.err
-CMD="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --min-seconds 0"
-$CMD > gpurun_out/${T}_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_ncu1.log 2>&1
-$CMD > gpurun_out/${T}_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k2_weights_reduce -s 1 -c 2 -o gpurun_out/${T}_k2 $CMD > gpurun_out/${T}_ncu2.log 2>&1
 CMD3="$CMD --workload mos2_8x8_spinor"
 $CMD3 > gpurun_out/${T}_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k2_weights_reduce -s 1 -c 1 -o gpurun_out/${T}_k2_spinor $CMD3 > gpurun_out/${T}_ncu3.log 2>&1
 CMD4="$CMD --workload graphene4x4"
