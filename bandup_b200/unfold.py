@@ -625,12 +625,30 @@ def pinned_empty_near(nbytes: int, n_keep: int = 1, spares: int = 2, device: int
     (same box, same GPU, one process in three: gpurun_out/r02x_bench*.json).  The copy engine can
     tell the blocks apart even though sysfs cannot.  torch only provides the device scratch, the
     stream and the events of the timing."""
-    import torch
+    if int(nbytes) < 1:
+        raise ValueError("pinned_empty_near needs nbytes >= 1")
     n_keep, spares = max(1, int(n_keep)), max(0, int(spares))
-    cands = [pinned_empty(nbytes) for _ in range(n_keep + spares)]
-    if spares == 0:
-        return cands, [None] * n_keep, list(range(n_keep))
-    step = min(int(nbytes), int(slice_mb) << 20)
+    cands = []
+    try:
+        for _ in range(n_keep + spares):
+            cands.append(pinned_empty(nbytes))
+        if spares == 0:
+            return cands, [None] * n_keep, list(range(n_keep))
+        rates = _upload_rates(cands, int(nbytes), device, min(int(nbytes), max(1, int(slice_mb)) << 20))
+    except BaseException:
+        for h in cands:          # nothing is handed out: give the candidates back
+            pinned_free(h)
+        raise
+    keep = pick_fastest(rates, n_keep)
+    for i in range(len(cands)):
+        if i not in keep:
+            pinned_free(cands[i])
+    return [cands[i] for i in keep], [round(r, 2) for r in rates], keep
+
+
+def _upload_rates(cands, nbytes: int, device: int, step: int) -> List[float]:
+    """GB/s of one host->device copy of every candidate block, in slices of `step` bytes."""
+    import torch
     with torch.cuda.device(device):
         scratch = torch.empty(step, dtype=torch.uint8, device=f"cuda:{device}")
         stream = torch.cuda.Stream(device=device)
@@ -648,11 +666,7 @@ def pinned_empty_near(nbytes: int, n_keep: int = 1, spares: int = 2, device: int
             moved = ((int(nbytes) - step) // step + 1) * step
             rates.append(moved / (a.elapsed_time(b) * 1e-3) / 1e9)
         del scratch
-    keep = pick_fastest(rates, n_keep)
-    for i in range(len(cands)):
-        if i not in keep:
-            pinned_free(cands[i])
-    return [cands[i] for i in keep], [round(r, 2) for r in rates], keep
+    return rates
 
 
 def host_register(arr: np.ndarray) -> None:
