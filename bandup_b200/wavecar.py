@@ -268,7 +268,7 @@ def unfold_wavecar(unfolder, wavecar: Wavecar, rec_latt_pc: np.ndarray, pc_kpts_
     one pass, the raw band records uploaded as they are while the previous k-point computes.
     reader = "mmap" (default): the file is mapped and the mapping handed to the library as it is -- its
     staging ring copies 16 MB chunks out of the page cache while the previous chunks are on the wire,
-    so a k-point's read and its upload overlap each other (C5: 50 GB/s of file data against 39 for
+    so a k-point's read and its upload overlap each other (C5: 52 GB/s of file data against 38-39 for
     "pread"); "pread": the records of k-point j+1 are read (threaded preadv) into a page-locked
     buffer by a helper thread while j uploads.
     Returns sharding.GatheredDeltaN (rows in pc-kpt order) and the energy grid."""
