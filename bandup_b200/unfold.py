@@ -630,9 +630,14 @@ def pinned_empty_near(nbytes: int, n_keep: int = 1, spares: int = 2, device: int
     n_keep, spares = max(1, int(n_keep)), max(0, int(spares))
     cands = []
     try:
-        for _ in range(n_keep + spares):
-            cands.append(pinned_empty(nbytes))
-        if spares == 0:
+        for i in range(n_keep + spares):
+            try:
+                cands.append(pinned_empty(nbytes))
+            except BandupGpuError:
+                if i < n_keep:
+                    raise
+                break                # a spare the host has no room for: choose among what there is
+        if len(cands) == n_keep:
             return cands, [None] * n_keep, list(range(n_keep))
         rates = _upload_rates(cands, int(nbytes), device, min(int(nbytes), max(1, int(slice_mb)) << 20))
     except BaseException:
