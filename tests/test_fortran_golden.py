@@ -455,3 +455,43 @@ def test_fold_search_golden_regenerates(gold):
     assert set(out) == set(g)
     for k, v in out.items():
         assert np.array_equal(np.asarray(v), g[k]), k
+
+
+def _sample_plot_check_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_sample_plot_writer_check", GOLD / "make_sample_plot_writer_check.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.skipif(not Path("/root/reference/utils/sample_input_files_task_plot").exists(),
+                    reason="the reference tree exists in the build container only")
+def test_interpreted_writer_reproduces_a_file_written_by_a_compiled_bandup():
+    """The one output of a real (compiled) BandUP run in the reference tree,
+    utils/sample_input_files_task_plot/unfolded_EBS_symmetry-averaged.dat (63 pc-kpts x 581 energies):
+    real_seq + write_band_struc EXECUTED from the reference sources on its path, window and delta_N
+    column print every one of its 36 603 data lines, text for text -- the interpreter's arithmetic and
+    edit descriptors against a compiled build, on the routine that also wrote the golden EBS files."""
+    mod = _sample_plot_check_module()
+    mine, ref, n_statements = mod.run()
+    assert len(ref) == 63 * 581 and n_statements > 100000
+    assert mine == ref
+    rec = json.loads((GOLD / "sample_plot_writer_check.json").read_text())
+    assert rec["sha256_reference_file_lines"] == mod.digest(ref) == rec["sha256_interpreted_writer_lines"]
+
+
+def test_product_writer_reproduces_a_file_written_by_a_compiled_bandup():
+    """The same file from the product's writer (bandup_files.write_band_struc: what unfold_task and
+    BandUP_gpu.x print) on the committed inputs and the file's delta_N column (sample_plot_dN.npz):
+    the SHA-256 of its 36 603 data lines is the one of the compiled program's file
+    (sample_plot_writer_check.json, made where the reference tree exists).  Runs anywhere."""
+    mod = _sample_plot_check_module()
+    z = np.load(GOLD / "sample_plot_dN.npz")
+    nener, n_k = (int(x) for x in z["shape"])
+    d = np.zeros(nener * n_k)
+    d[z["idx"]] = z["val"].astype(np.float64)
+    lines = mod.product_writer_lines(d.reshape(nener, n_k))
+    rec = json.loads((GOLD / "sample_plot_writer_check.json").read_text())
+    assert rec["differing_lines"] == 0 and len(lines) == rec["data_lines"] == 36603
+    assert mod.digest(lines) == rec["sha256_reference_file_lines"]
