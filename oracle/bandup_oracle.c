@@ -27,7 +27,8 @@
  * particular Fortran compiler (the interpreter evaluates every operation in the
  * kind Fortran prescribes, without reassociation or fused multiply-add -- what
  * gfortran -O2 does on baseline x86-64, src/Makefile:23-30), the order OpenMP
- * threads append selected indices in (ascending here).  The interpreter itself
+ * threads append selected indices in (ascending here), the rho-file writer
+ * (write_unf_dens_op: held by the reference's own Python reader instead).  The interpreter itself
  * is held against a COMPILED BandUP where the reference tree allows it: real_seq
  * + write_band_struc, interpreted, print all 36 603 data lines of
  * utils/sample_input_files_task_plot/unfolded_EBS_symmetry-averaged.dat text for
